@@ -1,0 +1,231 @@
+/*
+ * da_b200.h — C-ABI of the B200-native domain-adaptation hot path.
+ *
+ * One shared library (libda_b200.so, sm_100a only) replaces every native op the
+ * reference reaches on its DA path.  The reference itself ships no native code
+ * (/root/reference/setup.py:220, ext_modules=[]); what it binds is mmcv-full's
+ * `ext_module` (mmcv.ops.RoIAlign, sigmoid_focal_loss) plus ATen/cuDNN/cuBLAS
+ * through torch.nn.  Each entry point below cites the reference call site it
+ * replaces (path:line under /root/reference).
+ *
+ * Conventions (same as mmcv's ext_module):
+ *   - the CALLER owns every buffer, including workspaces (query *_workspace_bytes);
+ *     the library never allocates device memory;
+ *   - all pointers are device pointers unless the name ends in _host;
+ *   - kernels are enqueued on `stream` and never synchronise;
+ *   - return 0 on success, a DA_ERR_* code otherwise; da_last_error() gives the
+ *     message for the calling thread;
+ *   - no torch types, no C++ types: plain pointers, ints, floats.
+ *
+ * Layouts: activation tensors are NHWC ("channels-last", the physical layout of a
+ * torch channels_last tensor).  The reference's NCHW tensors enter through
+ * da_nchw_to_nhwc.  RoI features keep the reference layout [R,C,ph,pw]
+ * (DA_ROI_OUT_RCHW) because the bbox head flattens them as (c,ph,pw)
+ * (mmdet/models/roi_heads/bbox_heads/convfc_bbox_head.py:208).
+ */
+#ifndef DA_B200_H_
+#define DA_B200_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* da_stream_t; /* cudaStream_t */
+
+enum da_status {
+  DA_OK = 0,
+  DA_ERR_INVALID_ARG = 1,
+  DA_ERR_UNSUPPORTED = 2,
+  DA_ERR_CUDA = 3,
+  DA_ERR_WORKSPACE = 4,
+  DA_ERR_ROI_BATCH_INDEX = 5 /* reported asynchronously through the error flag of the workspace */
+};
+
+enum da_dtype { DA_F32 = 0, DA_BF16 = 1 };
+
+enum da_roi_out_layout { DA_ROI_OUT_RCHW = 0, DA_ROI_OUT_RHWC = 1 };
+
+/* GEMM engine of the dense contractions (conv / FC). */
+enum da_engine {
+  DA_ENGINE_SIMT_F32 = 0,   /* CUDA-core fp32 FMA: bit-faithful fp32 parity mode          */
+  DA_ENGINE_UMMA_BF16 = 1,  /* tcgen05.mma kind::f16 (bf16 in, fp32 TMEM accumulate)      */
+  DA_ENGINE_UMMA_BF16X3 = 2 /* 3-term split bf16 (hi*hi + hi*lo + lo*hi), ~1e-5 relative  */
+};
+
+/* ---- library ------------------------------------------------------------ */
+int da_version(void);
+const char* da_last_error(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+int64_t da_launch_count(void);
+void da_launch_count_reset(void);
+
+/* ---- layout + GRL --------------------------------------------------------
+ * GRL: mmdet/models/roi_heads/instance_da.py:14-40 (_GradientScalarLayer): forward is the
+ * identity, backward is weight * grad.  Normally folded into a dgrad epilogue
+ * (out_scale of da_conv_backward_data); this standalone form serves callers that
+ * wrap an arbitrary torch sub-graph. */
+int da_grl_backward(const void* grad_out, void* grad_in, int dtype, int64_t n, float weight,
+                    da_stream_t stream);
+int da_nchw_to_nhwc(const void* src, int src_dtype, void* dst, int dst_dtype,
+                    int N, int C, int H, int W, da_stream_t stream);
+int da_nhwc_to_nchw(const void* src, int src_dtype, void* dst, int dst_dtype,
+                    int N, int C, int H, int W, da_stream_t stream);
+/* 3-term bf16 split of an fp32 tensor: hi=bf16(x), lo=bf16(x-hi). */
+int da_split_bf16(const float* src, void* hi, void* lo, int64_t n, da_stream_t stream);
+int da_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, da_stream_t stream);
+
+/* ---- RoIAlign ------------------------------------------------------------
+ * Replaces mmcv.ops.RoIAlign (ext_module.roi_align_forward / roi_align_backward,
+ * mmcv-full 1.3.17) as built at mmdet/models/roi_heads/roi_extractors/base_roi_extractor.py:54-60
+ * and called at single_level_roi_extractor.py:79,103.  pool_mode='avg'.
+ * rois: [R,5] fp32 (batch_ind, x1, y1, x2, y2) in image pixels.
+ *
+ * Workspace: da_roi_align_workspace_bytes(R,H,W) bytes.  Layout: int32 err_flag[4], one meta
+ * record per RoI, then per RoI the separable tap-weight tables ((H+W) rows of 8 floats).  After the stream is synchronised err_flag[0] != 0 means some
+ * RoI carried a batch index outside [0,N); such RoIs produce zeros.
+ * grid_out (nullable): int32 [R,2] = (roi_bin_grid_h, roi_bin_grid_w), the sampling grid. */
+size_t da_roi_align_workspace_bytes(int R, int H, int W);
+int da_roi_align_forward(const void* feat_nhwc, int feat_dtype, int N, int C, int H, int W,
+                         const float* rois, int R, int pooled_h, int pooled_w,
+                         float spatial_scale, int sampling_ratio, int aligned,
+                         void* out, int out_dtype, int out_layout,
+                         int32_t* grid_out, void* workspace, size_t workspace_bytes,
+                         da_stream_t stream);
+/* grad_in_nhwc [N,H,W,C] fp32 is written exactly once per element (no atomics, no
+ * pre-zeroing required). */
+int da_roi_align_backward(const void* grad_out, int grad_dtype, int out_layout,
+                          const float* rois, int R, int pooled_h, int pooled_w,
+                          float spatial_scale, int sampling_ratio, int aligned,
+                          float* grad_in_nhwc, int N, int C, int H, int W,
+                          void* workspace, size_t workspace_bytes, da_stream_t stream);
+/* FPN level mapping, single_level_roi_extractor.py:36-55. levels_out int32 [R]. */
+int da_map_roi_levels(const float* rois, int R, int num_levels, float finest_scale,
+                      int32_t* levels_out, da_stream_t stream);
+
+/* ---- domain losses -------------------------------
+ * Every forward writes fp32 scalars on the device; every backward takes the upstream
+ * gradient as a DEVICE scalar pointer (nullable = 1) times a host scalar `scale`
+ * (lambda weights, and -1 of the GRL when the caller folds it here). */
+
+/* L1/L2 pixel loss: resnet_da_daf_org.py:816-822 (whole_batch=1) and
+ * resnet_da_cbam.py:971-979 (whole_batch=0).  logits [N,L] fp32, domain int32 [N].
+ * partial: workspace of da_pixel_loss_workspace_bytes(N,L). */
+size_t da_pixel_loss_workspace_bytes(int N, int64_t L);
+int da_pixel_domain_loss_forward(const float* logits, int N, int64_t L, const int32_t* domain,
+                                 int whole_batch, float* loss_out, void* workspace,
+                                 size_t workspace_bytes, da_stream_t stream);
+int da_pixel_domain_loss_backward(const float* logits, int N, int64_t L, const int32_t* domain,
+                                  int whole_batch, const float* grad_loss, float scale,
+                                  float* dlogits, da_stream_t stream);
+
+/* L3/L4 cross-entropy over 2 classes, mean over rows: nn.CrossEntropyLoss at
+ * resnet_da_cbam.py:966-968 (raw logits, on_sigmoid=0) and resnet_da.py:846-848 /
+ * DAFaster_rcnn_Orig.py:177-188 (applied to sigmoid outputs, on_sigmoid=1, Q4).
+ * z [R,2] raw logits; pred_out (nullable) receives sigmoid(z) when on_sigmoid. */
+int da_ce2_forward(const float* z, const int32_t* labels, int R, int on_sigmoid,
+                   float* pred_out, float* loss_out, da_stream_t stream);
+int da_ce2_backward(const float* z, const int32_t* labels, int R, int on_sigmoid,
+                    const float* grad_loss, float scale, const float* grad_pred,
+                    float* dz, da_stream_t stream);
+
+/* L6 sigmoid focal loss, mean over k*2: mmdet/models/losses/focal_loss.py:12-57,60-103
+ * (mmcv sigmoid_focal_loss_forward/backward). u [k,2], labels in {0,1}. */
+int da_focal2_forward(const float* u, const int32_t* labels, int k, float gamma, float alpha,
+                      float* loss_out, da_stream_t stream);
+int da_focal2_backward(const float* u, const int32_t* labels, int k, float gamma, float alpha,
+                       const float* grad_loss, float scale, float* du, da_stream_t stream);
+
+/* L7 consistency regulariser: DAFaster_rcnn_Orig.py:161-175.
+ * m = mean(sigmoid(img_logits[0..n_img))); loss = sum_r |m - sigmoid(ins_pred[r, label_r])|.
+ * mean_out: device scalar (kept for backward). */
+int da_consistency_forward(const float* img_logits, int64_t n_img, const float* ins_pred,
+                           const int32_t* labels, int R, float* mean_out, float* loss_out,
+                           da_stream_t stream);
+int da_consistency_backward(const float* img_logits, int64_t n_img, const float* ins_pred,
+                            const int32_t* labels, int R, const float* mean_in,
+                            const float* grad_loss, float scale,
+                            float* d_img_logits, float* d_ins_pred, da_stream_t stream);
+
+/* ---- 1-channel head tail (terminal conv of ImgAlignmentHead / LocalAlignmentHead) ------
+ * resnet_da_daf_org.py:125,131 (conv2 512->1 + bias + ReLU) and resnet_da_cbam.py:87,112
+ * (conv3 C->1, no bias).  x [M,K] NHWC rows (f32 or bf16), w [K] f32.
+ * logits[m] = act(dot(x[m,:], w) + bias). */
+int da_pixel_head_forward(const void* x, int x_dtype, int64_t M, int K, const float* w,
+                          const float* bias, int relu, float* logits, da_stream_t stream);
+/* dl'[m] = dlogits[m] masked by (post_relu_logits[m] > 0) when post_relu_logits != NULL;
+ * dx[m,k] = dl'[m] * w[k] (nullable), dw[k] = sum_m dl'[m]*x[m,k], dbias = sum_m dl'[m].
+ * workspace: da_pixel_head_workspace_bytes(M,K). */
+size_t da_pixel_head_workspace_bytes(int64_t M, int K);
+int da_pixel_head_backward(const void* x, int x_dtype, int64_t M, int K, const float* w,
+                           const float* dlogits, const float* post_relu_logits,
+                           void* dx, int dx_dtype, float* dw, float* dbias,
+                           void* workspace, size_t workspace_bytes, da_stream_t stream);
+
+/* ---- dense contractions: domain-classifier convs and FC stacks ------------------------
+ * One implicit-GEMM for every conv of the DA heads (nn.Conv2d at resnet_da_daf_org.py:124-125,
+ * resnet_da_cbam.py:83-87,123-146, resnet_da.py:89-91, roi_heads/local_da.py:56-61) and every
+ * nn.Linear (instance_da.py:52-56,111-113; H=W=KH=KW=1).
+ *   x  [N,H,W,Cin]  NHWC, dtype x_dtype
+ *   w  [Cout,KH,KW,Cin] ("OHWI" = torch channels_last weight), dtype x_dtype
+ *   y  [N,OH,OW,Cout], OH=(H+2*pad-KH)/stride+1
+ * Epilogue: v = acc*scale[c] + shift[c] (nullable: 1 / 0; bias or folded eval-mode BN, Q9);
+ *           if relu: v=max(v,0); if drop_p>0: v = keep(seed,idx) ? v/(1-drop_p) : 0.
+ * The dropout keep-mask is a stateless counter hash of (seed, element index): backward
+ * regenerates it, da_dropout_mask exports it for the oracle. */
+typedef struct da_conv_desc {
+  int N, H, W, Cin;
+  int Cout, KH, KW;
+  int stride, pad;
+  int engine;   /* enum da_engine */
+  int x_dtype;  /* dtype of x, w (and of dy in backward) */
+  int y_dtype;  /* dtype of y (forward) / dx (backward data) */
+} da_conv_desc;
+
+size_t da_conv_workspace_bytes(const da_conv_desc* d);
+int da_conv_forward(const da_conv_desc* d, const void* x, const void* w,
+                    const float* scale, const float* shift, int relu,
+                    float drop_p, uint64_t drop_seed,
+                    void* y, void* workspace, size_t workspace_bytes, da_stream_t stream);
+/* dz = dy * act'(y): fuses the activation derivative of THIS layer's forward epilogue
+ * (relu mask from y, dropout mask regenerated, BN scale) into one pass.  With dv the
+ * gradient w.r.t. v = acc*scale+shift it also reduces (both nullable)
+ *   dshift[c] = sum_m dv[m,c]            (bias / BN beta gradient)
+ *   dvdot[c]  = sum_m dv[m,c] * v[m,c]   (BN gamma gradient = (dvdot - beta*dshift)/gamma)
+ * dy, y and dz share dtype y_dtype == x_dtype.  Workspace: da_conv_workspace_bytes(d). */
+int da_conv_act_backward(const da_conv_desc* d, const void* dy, const void* y,
+                         const float* scale, int relu, float drop_p, uint64_t drop_seed,
+                         void* dz, float* dshift, float* dvdot, void* workspace,
+                         size_t workspace_bytes, da_stream_t stream);
+/* dx = out_scale * conv_transpose(dz, w).  out_scale carries the GRL weight (-lambda) when
+ * x is the head input, so the reversed gradient is emitted in the same pass. */
+int da_conv_backward_data(const da_conv_desc* d, const void* dz, const void* w,
+                          float out_scale, void* dx, void* workspace, size_t workspace_bytes,
+                          da_stream_t stream);
+/* dw [Cout,KH,KW,Cin] fp32 = sum over pixels dz^T x */
+int da_conv_backward_weight(const da_conv_desc* d, const void* x, const void* dz,
+                            float* dw, void* workspace, size_t workspace_bytes,
+                            da_stream_t stream);
+int da_dropout_mask(uint64_t seed, int64_t n, float drop_p, uint8_t* keep_out, da_stream_t stream);
+
+/* global average pool over H*W (F.avg_pool2d(x,(H,W)) at resnet_da_cbam.py:186, resnet_da.py:101):
+ * x [N,H,W,C] -> y [N,C] fp32; backward broadcasts dy/(H*W). */
+size_t da_global_avgpool_workspace_bytes(int N, int C);
+int da_global_avgpool_forward(const void* x, int x_dtype, int N, int HW, int C, float* y,
+                              void* workspace, size_t workspace_bytes, da_stream_t stream);
+int da_global_avgpool_backward(const float* dy, int N, int HW, int C, void* dx, int dx_dtype,
+                               da_stream_t stream);
+
+/* NonLocalBlock attention core (instance_da.py:150-192, resnet_da_deep.py:402-445):
+ * softmax over the QUERY axis (nn.Softmax(dim=1) on [b,q,k], Q11).  s [T,T] fp32 row-major
+ * with s[q,k]; p[q,k] = exp(s[q,k]) / sum_q' exp(s[q',k]).  backward: ds from dp and p. */
+int da_softmax_dim0_forward(const float* s, int T, int ldk, float* p, da_stream_t stream);
+int da_softmax_dim0_backward(const float* p, const float* dp, int T, int ldk, float* ds,
+                             da_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DA_B200_H_ */

@@ -1,0 +1,104 @@
+"""ctypes binding of libda_b200.so (the C-ABI declared in include/da_b200.h).
+
+The library is the product: there is no CPU or PyTorch fallback.  Importing this module
+without a built library raises immediately ("fail loudly"), and every wrapper raises
+RuntimeError with da_last_error() when a call returns non-zero -- the same error surface
+mmcv's ext_module gives the reference (AT_CUDA_CHECK -> RuntimeError).
+"""
+import ctypes
+import os
+from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t,
+                    c_uint64, c_void_p)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libda_b200.so")
+
+# enums of include/da_b200.h
+DA_F32, DA_BF16 = 0, 1
+ROI_OUT_RCHW, ROI_OUT_RHWC = 0, 1
+ENGINE_SIMT_F32, ENGINE_UMMA_BF16, ENGINE_UMMA_BF16X3 = 0, 1, 2
+ENGINES = {"simt_f32": ENGINE_SIMT_F32, "umma_bf16": ENGINE_UMMA_BF16, "umma_bf16x3": ENGINE_UMMA_BF16X3}
+
+
+class ConvDesc(Structure):
+    _fields_ = [("N", c_int), ("H", c_int), ("W", c_int), ("Cin", c_int),
+                ("Cout", c_int), ("KH", c_int), ("KW", c_int),
+                ("stride", c_int), ("pad", c_int),
+                ("engine", c_int), ("x_dtype", c_int), ("y_dtype", c_int)]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C unsupervised_domain_adaptation_object_detection_implementation_b200/csrc`. "
+            "There is no CPU fallback for the DA hot path.")
+    return ctypes.CDLL(LIB_PATH)
+
+
+lib = _load()
+
+P, I, F, S, L, U64 = c_void_p, c_int, c_float, c_size_t, c_int64, c_uint64
+CD = POINTER(ConvDesc)
+
+# name -> (restype, argtypes); every symbol include/da_b200.h declares
+SIGNATURES = {
+    "da_version": (I, []),
+    "da_last_error": (c_char_p, []),
+    "da_launch_count": (L, []),
+    "da_launch_count_reset": (None, []),
+    "da_grl_backward": (I, [P, P, I, L, F, P]),
+    "da_nchw_to_nhwc": (I, [P, I, P, I, I, I, I, I, P]),
+    "da_nhwc_to_nchw": (I, [P, I, P, I, I, I, I, I, P]),
+    "da_split_bf16": (I, [P, P, P, L, P]),
+    "da_cast": (I, [P, I, P, I, L, P]),
+    "da_roi_align_workspace_bytes": (S, [I, I, I]),
+    "da_roi_align_forward": (I, [P, I, I, I, I, I, P, I, I, I, F, I, I, P, I, I, P, P, S, P]),
+    "da_roi_align_backward": (I, [P, I, I, P, I, I, I, F, I, I, P, I, I, I, I, P, S, P]),
+    "da_map_roi_levels": (I, [P, I, I, F, P, P]),
+    "da_pixel_loss_workspace_bytes": (S, [I, L]),
+    "da_pixel_domain_loss_forward": (I, [P, I, L, P, I, P, P, S, P]),
+    "da_pixel_domain_loss_backward": (I, [P, I, L, P, I, P, F, P, P]),
+    "da_ce2_forward": (I, [P, P, I, I, P, P, P]),
+    "da_ce2_backward": (I, [P, P, I, I, P, F, P, P, P]),
+    "da_focal2_forward": (I, [P, P, I, F, F, P, P]),
+    "da_focal2_backward": (I, [P, P, I, F, F, P, F, P, P]),
+    "da_consistency_forward": (I, [P, L, P, P, I, P, P, P]),
+    "da_consistency_backward": (I, [P, L, P, P, I, P, P, F, P, P, P]),
+    "da_pixel_head_forward": (I, [P, I, L, I, P, P, I, P, P]),
+    "da_pixel_head_workspace_bytes": (S, [L, I]),
+    "da_pixel_head_backward": (I, [P, I, L, I, P, P, P, P, I, P, P, P, S, P]),
+    "da_conv_workspace_bytes": (S, [CD]),
+    "da_conv_forward": (I, [CD, P, P, P, P, I, F, U64, P, P, S, P]),
+    "da_conv_act_backward": (I, [CD, P, P, P, I, F, U64, P, P, P, P, S, P]),
+    "da_conv_backward_data": (I, [CD, P, P, F, P, P, S, P]),
+    "da_conv_backward_weight": (I, [CD, P, P, P, P, S, P]),
+    "da_dropout_mask": (I, [U64, L, F, P, P]),
+    "da_global_avgpool_workspace_bytes": (S, [I, I]),
+    "da_global_avgpool_forward": (I, [P, I, I, I, I, P, P, S, P]),
+    "da_global_avgpool_backward": (I, [P, I, I, I, P, I, P]),
+    "da_softmax_dim0_forward": (I, [P, I, I, P, P]),
+    "da_softmax_dim0_backward": (I, [P, P, I, I, P, P]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)  # AttributeError here == header/library mismatch: fail loudly
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def last_error():
+    return lib.da_last_error().decode("utf-8", "replace")
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise RuntimeError(f"libda_b200 {what} failed (code {rc}): {last_error()}")
+
+
+def launch_count():
+    return int(lib.da_launch_count())
+
+
+def reset_launch_count():
+    lib.da_launch_count_reset()

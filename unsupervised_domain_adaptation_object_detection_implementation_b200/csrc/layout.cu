@@ -1,0 +1,133 @@
+// Library plumbing (error string, launch counter) + layout / elementwise kernels:
+// NCHW<->NHWC transposes (the reference's tensors are NCHW contiguous),
+// dtype casts, the bf16 hi/lo split used by the BF16X3 engine, the standalone GRL
+// backward (instance_da.py:20-23) and the exported dropout keep-mask.
+#include "da_common.cuh"
+#include <string.h>
+
+namespace da {
+
+static thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// [N][C][HW] -> [N][HW][C] (and the reverse), 32x32 tiles through padded smem
+template <typename TS, typename TD>
+__global__ void transpose_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int rows, int cols) {
+  // src is [rows][cols] per batch (blockIdx.z), dst is [cols][rows]
+  __shared__ float tile[32][33];
+  const size_t boff = (size_t)blockIdx.z * rows * cols;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[j][threadIdx.x] = to_f32<TS>(src[boff + (size_t)r * cols + c]);
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) dst[boff + (size_t)c * rows + r] = from_f32<TD>(tile[threadIdx.x][j]);
+  }
+}
+
+template <typename TS, typename TD>
+__global__ void cast_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int64_t n, float mul) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = from_f32<TD>(to_f32<TS>(src[i]) * mul);
+}
+
+__global__ void split_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi,
+                                  __nv_bfloat16* __restrict__ lo, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = src[i];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+__global__ void dropout_mask_kernel(uint64_t seed, int64_t n, uint32_t thr, uint8_t* __restrict__ keep) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    keep[i] = drop_hash(seed, (uint64_t)i) >= thr ? 1 : 0;
+}
+
+static inline int ew_blocks(int64_t n) {
+  int64_t b = (n + 255) / 256;
+  const int64_t cap = (int64_t)num_sms() * 16;
+  return (int)(b > cap ? cap : (b < 1 ? 1 : b));
+}
+
+template <typename TS, typename TD>
+static int launch_transpose(const void* src, void* dst, int batch, int rows, int cols, cudaStream_t st) {
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32, batch);
+  DA_REQUIRE(grid.y <= 65535 && grid.z <= 65535, DA_ERR_UNSUPPORTED, "transpose: grid too large");
+  transpose_kernel<TS, TD><<<grid, dim3(32, 8), 0, st>>>((const TS*)src, (TD*)dst, rows, cols);
+  DA_LAUNCH_CHECK();
+  return DA_OK;
+}
+static int transpose_dispatch(const void* src, int sd, void* dst, int dd, int batch, int rows, int cols, cudaStream_t st) {
+  if (sd == DA_F32 && dd == DA_F32) return launch_transpose<float, float>(src, dst, batch, rows, cols, st);
+  if (sd == DA_F32 && dd == DA_BF16) return launch_transpose<float, __nv_bfloat16>(src, dst, batch, rows, cols, st);
+  if (sd == DA_BF16 && dd == DA_F32) return launch_transpose<__nv_bfloat16, float>(src, dst, batch, rows, cols, st);
+  if (sd == DA_BF16 && dd == DA_BF16) return launch_transpose<__nv_bfloat16, __nv_bfloat16>(src, dst, batch, rows, cols, st);
+  DA_REQUIRE(false, DA_ERR_INVALID_ARG, "transpose: bad dtype %d/%d", sd, dd);
+}
+
+}  // namespace da
+
+using namespace da;
+
+extern "C" int da_version(void) { return 100; }
+extern "C" const char* da_last_error(void) { return g_err; }
+extern "C" int64_t da_launch_count(void) { return g_launches.load(); }
+extern "C" void da_launch_count_reset(void) { g_launches.store(0); }
+
+extern "C" int da_nchw_to_nhwc(const void* src, int src_dtype, void* dst, int dst_dtype,
+                               int N, int C, int H, int W, da_stream_t stream) {
+  DA_REQUIRE(src && dst && N > 0 && C > 0 && H > 0 && W > 0, DA_ERR_INVALID_ARG, "nchw_to_nhwc: bad args");
+  return transpose_dispatch(src, src_dtype, dst, dst_dtype, N, C, H * W, (cudaStream_t)stream);
+}
+extern "C" int da_nhwc_to_nchw(const void* src, int src_dtype, void* dst, int dst_dtype,
+                               int N, int C, int H, int W, da_stream_t stream) {
+  DA_REQUIRE(src && dst && N > 0 && C > 0 && H > 0 && W > 0, DA_ERR_INVALID_ARG, "nhwc_to_nchw: bad args");
+  return transpose_dispatch(src, src_dtype, dst, dst_dtype, N, H * W, C, (cudaStream_t)stream);
+}
+
+static int cast_scaled(const void* src, int sd, void* dst, int dd, int64_t n, float mul, cudaStream_t st) {
+  if (n == 0) return DA_OK;
+  DA_REQUIRE(src && dst && n > 0, DA_ERR_INVALID_ARG, "cast: bad args");
+  const int b = ew_blocks(n);
+  if (sd == DA_F32 && dd == DA_F32) cast_kernel<float, float><<<b, 256, 0, st>>>((const float*)src, (float*)dst, n, mul);
+  else if (sd == DA_F32 && dd == DA_BF16) cast_kernel<float, __nv_bfloat16><<<b, 256, 0, st>>>((const float*)src, (__nv_bfloat16*)dst, n, mul);
+  else if (sd == DA_BF16 && dd == DA_F32) cast_kernel<__nv_bfloat16, float><<<b, 256, 0, st>>>((const __nv_bfloat16*)src, (float*)dst, n, mul);
+  else if (sd == DA_BF16 && dd == DA_BF16) cast_kernel<__nv_bfloat16, __nv_bfloat16><<<b, 256, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, n, mul);
+  else DA_REQUIRE(false, DA_ERR_INVALID_ARG, "cast: bad dtype %d/%d", sd, dd);
+  DA_LAUNCH_CHECK();
+  return DA_OK;
+}
+extern "C" int da_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, da_stream_t stream) {
+  return cast_scaled(src, src_dtype, dst, dst_dtype, n, 1.f, (cudaStream_t)stream);
+}
+extern "C" int da_grl_backward(const void* grad_out, void* grad_in, int dtype, int64_t n, float weight,
+                               da_stream_t stream) {
+  return cast_scaled(grad_out, dtype, grad_in, dtype, n, weight, (cudaStream_t)stream);
+}
+extern "C" int da_split_bf16(const float* src, void* hi, void* lo, int64_t n, da_stream_t stream) {
+  if (n == 0) return DA_OK;
+  DA_REQUIRE(src && hi && lo && n > 0, DA_ERR_INVALID_ARG, "split_bf16: bad args");
+  split_bf16_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n);
+  DA_LAUNCH_CHECK();
+  return DA_OK;
+}
+extern "C" int da_dropout_mask(uint64_t seed, int64_t n, float drop_p, uint8_t* keep_out, da_stream_t stream) {
+  if (n == 0) return DA_OK;
+  DA_REQUIRE(keep_out && n > 0 && drop_p >= 0.f && drop_p < 1.f, DA_ERR_INVALID_ARG, "dropout_mask: bad args");
+  dropout_mask_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(seed, n, drop_threshold(drop_p), keep_out);
+  DA_LAUNCH_CHECK();
+  return DA_OK;
+}

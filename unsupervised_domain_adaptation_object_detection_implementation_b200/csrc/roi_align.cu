@@ -1,0 +1,527 @@
+// RoIAlign forward / backward for sm_100a — replaces mmcv.ops.RoIAlign on the DA hot path
+// (reference call sites: mmdet/models/roi_heads/roi_extractors/base_roi_extractor.py:54-60,
+//  single_level_roi_extractor.py:79,103).  Algorithm contract: SURVEY.md Appendix A
+// (mmcv-full 1.3.17 roi_align_cuda_kernel.cuh == torchvision roi_align lineage), avg mode.
+//
+// B200 design (HBM-bound op):
+//   * features are NHWC so that a warp reads 32 consecutive channels of one pixel
+//     (128 B, coalesced); every footprint pixel of an RoI is read ONCE per channel;
+//   * bilinear sampling is separable: out[ph,pw] = 1/count * sum_y sum_x Wy[y,ph] Wx[x,pw] f[y,x]
+//     where Wy/Wx are the per-axis sums of the bilinear tap weights of all samples of a
+//     bin.  A tiny prep kernel builds (Wy,Wx) and the sampling grid (gh,gw) per RoI with the
+//     reference's exact fp32 operation order (no FMA contraction), the pooling kernels
+//     stage them in shared memory;
+//   * forward: CTA = (RoI, 256-channel block); 49 accumulators per channel live in
+//     registers; the [256][49] result tile is transposed through shared memory so the
+//     reference layout [R,C,7,7] is written as one contiguous 50 KB run;
+//   * backward: gather, no atomics: CTA = (image, 16x32-pixel tile, 32-channel block) keeps
+//     its slice of grad_input in shared memory, walks the RoIs overlapping the tile in
+//     index order (deterministic), and writes every grad_input element exactly once.
+#include "da_common.cuh"
+
+namespace da {
+
+constexpr int P = 7;          // pooled size supported by the register-tiled kernels
+constexpr int PP = P * P;     // 49
+constexpr int WROW = 8;       // floats per weight-table row (7 bins + pad)
+
+struct __align__(16) RoiMeta {
+  int b;        // batch index, -1 when invalid / out of range
+  int gh, gw;   // sampling grid (roi_bin_grid_h / _w)
+  int y_lo, ny; // first footprint row, number of rows (0 = empty)
+  int x_lo, nx;
+  int count;    // max(gh*gw,1)
+};
+
+// workspace layout: int err[4] | RoiMeta[R] | float tables[R][(H+W)*8]
+__host__ __device__ inline size_t ws_meta_off() { return 16; }
+__host__ __device__ inline size_t ws_table_off(int R) {
+  return 16 + ((size_t)R * sizeof(RoiMeta) + 255) / 256 * 256;
+}
+
+// One axis of the reference's sample enumeration.  Thread `bin` (0..6) walks its g samples.
+// Mode 0: return (min low index, max high index) of valid samples through lo/hi.
+// Mode 1: accumulate tap weights into tab[(idx - base)*8 + bin].
+__device__ __forceinline__ void axis_samples(float start, float bin_size, int g, int bin,
+                                             int extent, int mode, int base, float* tab,
+                                             int& lo, int& hi) {
+  const float fext = (float)extent;
+  for (int i = 0; i < g; ++i) {
+    // reference: start + p*bin + (i + .5f) * bin / g   (left-to-right, no contraction)
+    float v = __fadd_rn(__fadd_rn(start, __fmul_rn((float)bin, bin_size)),
+                        __fdiv_rn(__fmul_rn((float)i + .5f, bin_size), (float)g));
+    if (v < -1.0f || v > fext) continue;  // sample contributes 0
+    if (v <= 0.f) v = 0.f;
+    int l = (int)v, h;
+    if (l >= extent - 1) { h = l = extent - 1; v = (float)l; } else { h = l + 1; }
+    const float lw = v - (float)l, hw = 1.f - lw;
+    if (mode == 0) {
+      lo = min(lo, l);
+      hi = max(hi, h);
+    } else {
+      tab[(l - base) * WROW + bin] += hw;
+      tab[(h - base) * WROW + bin] += lw;
+    }
+  }
+}
+
+// grid = R blocks of 32 threads.
+__global__ void roi_prep_kernel(const float* __restrict__ rois, int R, int N, int H, int W,
+                                float spatial_scale, int sampling_ratio, int aligned,
+                                unsigned char* __restrict__ ws, int32_t* __restrict__ grid_out) {
+  const int r = blockIdx.x;
+  const int lane = threadIdx.x;
+  int* err = reinterpret_cast<int*>(ws);
+  RoiMeta* metas = reinterpret_cast<RoiMeta*>(ws + ws_meta_off());
+  float* tab = reinterpret_cast<float*>(ws + ws_table_off(R)) + (size_t)r * (H + W) * WROW;
+
+  const float* roi = rois + (size_t)r * 5;
+  const float fb = roi[0];
+  int b = (int)fb;
+  const float offset = aligned ? 0.5f : 0.f;
+  const float x1 = __fsub_rn(__fmul_rn(roi[1], spatial_scale), offset);
+  const float y1 = __fsub_rn(__fmul_rn(roi[2], spatial_scale), offset);
+  const float x2 = __fsub_rn(__fmul_rn(roi[3], spatial_scale), offset);
+  const float y2 = __fsub_rn(__fmul_rn(roi[4], spatial_scale), offset);
+  float rw = __fsub_rn(x2, x1), rh = __fsub_rn(y2, y1);
+  if (!aligned) { rw = fmaxf(rw, 1.f); rh = fmaxf(rh, 1.f); }
+  const float bh = __fdiv_rn(rh, (float)P), bw = __fdiv_rn(rw, (float)P);
+  int gh = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(__fdiv_rn(rh, (float)P));
+  int gw = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(__fdiv_rn(rw, (float)P));
+  if (!(fb >= 0.f) || b < 0 || b >= N) {  // also catches NaN
+    if (lane == 0) atomicExch(&err[0], 1);
+    b = -1;
+  }
+  const int gh_s = max(gh, 0), gw_s = max(gw, 0);  // negative grid == empty loops in the reference
+
+  int lo = 0x7fffffff, hi = -1;
+  if (lane < P) axis_samples(x1, bw, gw_s, lane, W, 0, 0, nullptr, lo, hi);
+  else if (lane >= 8 && lane < 8 + P) axis_samples(y1, bh, gh_s, lane - 8, H, 0, 0, nullptr, lo, hi);
+  // segmented (8-lane) min / max
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  const int x_lo = __shfl_sync(0xffffffffu, lo, 0), x_hi = __shfl_sync(0xffffffffu, hi, 0);
+  const int y_lo = __shfl_sync(0xffffffffu, lo, 8), y_hi = __shfl_sync(0xffffffffu, hi, 8);
+  int nx = (x_hi >= x_lo) ? x_hi - x_lo + 1 : 0;
+  int ny = (y_hi >= y_lo) ? y_hi - y_lo + 1 : 0;
+  if (nx == 0 || ny == 0 || b < 0) { nx = 0; ny = 0; }
+
+  // tables: wy rows [0,ny) then wx rows at offset H*8
+  float* wy = tab;
+  float* wx = tab + (size_t)H * WROW;
+  for (int i = lane; i < ny * WROW; i += 32) wy[i] = 0.f;
+  for (int i = lane; i < nx * WROW; i += 32) wx[i] = 0.f;
+  __syncwarp();
+  if (nx > 0) {
+    int d0, d1;
+    if (lane < P) axis_samples(x1, bw, gw_s, lane, W, 1, x_lo, wx, d0, d1);
+    else if (lane >= 8 && lane < 8 + P) axis_samples(y1, bh, gh_s, lane - 8, H, 1, y_lo, wy, d0, d1);
+  }
+  if (lane == 0) {
+    RoiMeta m;
+    m.b = b; m.gh = gh; m.gw = gw;
+    m.y_lo = ny ? y_lo : 0; m.ny = ny; m.x_lo = nx ? x_lo : 0; m.nx = nx;
+    m.count = max(gh * gw, 1);
+    metas[r] = m;
+    if (grid_out) { grid_out[2 * r] = gh; grid_out[2 * r + 1] = gw; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------
+constexpr int FWD_THREADS = 128;
+constexpr int FWD_CB = 256;  // channels per CTA (2 per thread)
+
+template <typename TIn> struct FwdMap;
+template <> struct FwdMap<float> {  // channels (t, t+128): two coalesced 128 B warp loads per pixel
+  __device__ static int chan(int t, int j) { return t + 128 * j; }
+  __device__ static int stage(int cl, int k) { return cl * PP + k; }
+  __device__ static int stage_linear(int i) { return i; }
+};
+template <> struct FwdMap<__nv_bfloat16> {  // channels (2t, 2t+1): one packed 4 B load per pixel
+  __device__ static int chan(int t, int j) { return 2 * t + j; }
+  __device__ static int stage(int cl, int k) { return cl * PP + k + (cl >> 5); }
+  __device__ static int stage_linear(int i) { return i + ((i / PP) >> 5); }
+};
+
+template <typename TIn>
+__device__ __forceinline__ void load2(const TIn* p, bool v0, bool v1, float& f0, float& f1);
+template <>
+__device__ __forceinline__ void load2<float>(const float* p, bool v0, bool v1, float& f0, float& f1) {
+  f0 = v0 ? __ldg(p) : 0.f;
+  f1 = v1 ? __ldg(p + 128) : 0.f;
+}
+template <>
+__device__ __forceinline__ void load2<__nv_bfloat16>(const __nv_bfloat16* p, bool v0, bool v1,
+                                                     float& f0, float& f1) {
+  if (v1) {  // both valid (C even): one 32-bit load
+    const unsigned u = __ldg(reinterpret_cast<const unsigned*>(p));
+    f0 = __uint_as_float(u << 16);
+    f1 = __uint_as_float(u & 0xffff0000u);
+  } else {
+    f0 = v0 ? __bfloat162float(p[0]) : 0.f;
+    f1 = 0.f;
+  }
+}
+
+template <typename TIn, typename TOut, int kLayout>
+__global__ void __launch_bounds__(FWD_THREADS, 3)
+roi_align_fwd_kernel(const TIn* __restrict__ feat, int C, int H, int W, int R,
+                     const unsigned char* __restrict__ ws, TOut* __restrict__ out) {
+  extern __shared__ __align__(16) float smem[];
+  const int r = blockIdx.y;
+  const int c0 = blockIdx.x * FWD_CB;
+  const int t = threadIdx.x;
+  const RoiMeta m = reinterpret_cast<const RoiMeta*>(ws + ws_meta_off())[r];
+  const int nch = min(FWD_CB, C - c0);
+
+  // smem: [wy: ny*8][wx: nx*8][stage: 256*49 + 8]
+  float* wy_s = smem;
+  float* wx_s = smem + (size_t)H * WROW;
+  float* stage = smem + (size_t)(H + W) * WROW;
+  {
+    const float* tab = reinterpret_cast<const float*>(ws + ws_table_off(R)) + (size_t)r * (H + W) * WROW;
+    const float4* gy = reinterpret_cast<const float4*>(tab);
+    const float4* gx = reinterpret_cast<const float4*>(tab + (size_t)H * WROW);
+    float4* sy = reinterpret_cast<float4*>(wy_s);
+    float4* sx = reinterpret_cast<float4*>(wx_s);
+    for (int i = t; i < m.ny * 2; i += FWD_THREADS) sy[i] = gy[i];
+    for (int i = t; i < m.nx * 2; i += FWD_THREADS) sx[i] = gx[i];
+  }
+  __syncthreads();
+
+  float acc0[PP], acc1[PP];
+#pragma unroll
+  for (int k = 0; k < PP; ++k) { acc0[k] = 0.f; acc1[k] = 0.f; }
+
+  const int ca = FwdMap<TIn>::chan(t, 0), cb = FwdMap<TIn>::chan(t, 1);
+  const bool va = ca < nch, vb = cb < nch;
+
+  if (m.ny > 0 && (va || vb)) {
+    const TIn* base = feat + (((size_t)m.b * H + m.y_lo) * W + m.x_lo) * C + c0 + ca;
+    for (int ry = 0; ry < m.ny; ++ry) {
+      float T0[P], T1[P];
+#pragma unroll
+      for (int q = 0; q < P; ++q) { T0[q] = 0.f; T1[q] = 0.f; }
+      const TIn* prow = base + (size_t)ry * W * C;
+#pragma unroll 4
+      for (int rx = 0; rx < m.nx; ++rx) {
+        float f0, f1;
+        load2<TIn>(prow + (size_t)rx * C, va, vb, f0, f1);
+        const float4 wa = reinterpret_cast<const float4*>(wx_s)[rx * 2];
+        const float4 wb = reinterpret_cast<const float4*>(wx_s)[rx * 2 + 1];
+        T0[0] = fmaf(wa.x, f0, T0[0]); T1[0] = fmaf(wa.x, f1, T1[0]);
+        T0[1] = fmaf(wa.y, f0, T0[1]); T1[1] = fmaf(wa.y, f1, T1[1]);
+        T0[2] = fmaf(wa.z, f0, T0[2]); T1[2] = fmaf(wa.z, f1, T1[2]);
+        T0[3] = fmaf(wa.w, f0, T0[3]); T1[3] = fmaf(wa.w, f1, T1[3]);
+        T0[4] = fmaf(wb.x, f0, T0[4]); T1[4] = fmaf(wb.x, f1, T1[4]);
+        T0[5] = fmaf(wb.y, f0, T0[5]); T1[5] = fmaf(wb.y, f1, T1[5]);
+        T0[6] = fmaf(wb.z, f0, T0[6]); T1[6] = fmaf(wb.z, f1, T1[6]);
+      }
+      const float4 ya = reinterpret_cast<const float4*>(wy_s)[ry * 2];
+      const float4 yb = reinterpret_cast<const float4*>(wy_s)[ry * 2 + 1];
+      const float wyv[P] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z};
+#pragma unroll
+      for (int ph = 0; ph < P; ++ph) {
+        if (wyv[ph] != 0.f) {  // CTA-uniform: all threads share the RoI
+#pragma unroll
+          for (int pw = 0; pw < P; ++pw) {
+            acc0[ph * P + pw] = fmaf(wyv[ph], T0[pw], acc0[ph * P + pw]);
+            acc1[ph * P + pw] = fmaf(wyv[ph], T1[pw], acc1[ph * P + pw]);
+          }
+        }
+      }
+    }
+  }
+  const float cnt = (float)m.count;
+
+  if (kLayout == DA_ROI_OUT_RHWC) {
+    // [R,7,7,C]: lanes already map to consecutive channels
+    TOut* o = out + (size_t)r * PP * C + c0;
+#pragma unroll
+    for (int k = 0; k < PP; ++k) {
+      if (va) o[(size_t)k * C + ca] = from_f32<TOut>(acc0[k] / cnt);
+      if (vb) o[(size_t)k * C + cb] = from_f32<TOut>(acc1[k] / cnt);
+    }
+  } else {
+    // [R,C,7,7]: transpose through smem, then write the contiguous nch*49 run coalesced
+#pragma unroll
+    for (int k = 0; k < PP; ++k) {
+      stage[FwdMap<TIn>::stage(ca, k)] = acc0[k] / cnt;
+      stage[FwdMap<TIn>::stage(cb, k)] = acc1[k] / cnt;
+    }
+    __syncthreads();
+    TOut* o = out + ((size_t)r * C + c0) * PP;
+    const int total = nch * PP;
+    for (int i = t; i < total; i += FWD_THREADS)
+      o[i] = from_f32<TOut>(stage[FwdMap<TIn>::stage_linear(i)]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// backward (gather, atomics-free)
+// ---------------------------------------------------------------------------------------
+constexpr int BWD_THREADS = 256;
+constexpr int BWD_TY = 16, BWD_TX = 32;  // pixel tile
+constexpr int BWD_CB = 32;               // channels per CTA (one per lane)
+constexpr int BWD_LIST = 1024;           // RoI list chunk
+
+template <typename TG, int kLayout>
+__global__ void __launch_bounds__(BWD_THREADS, 2)
+roi_align_bwd_kernel(const TG* __restrict__ grad_out, int C, int H, int W, int R,
+                     const unsigned char* __restrict__ ws, float* __restrict__ grad_in,
+                     int tiles_x) {
+  extern __shared__ __align__(16) float smem[];
+  // smem: acc[TY*TX*32] | g[32*49] | wy[TY*8] | wx[TX*8] | list[BWD_LIST] | misc
+  float* acc = smem;
+  float* g_s = acc + BWD_TY * BWD_TX * BWD_CB;
+  float* wy_s = g_s + BWD_CB * PP + 16;
+  float* wx_s = wy_s + BWD_TY * WROW;
+  int* list = reinterpret_cast<int*>(wx_s + BWD_TX * WROW);
+  __shared__ int s_count;
+  __shared__ int s_wcount[BWD_THREADS / 32];
+
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * BWD_CB;
+  const int ty0 = (blockIdx.x / tiles_x) * BWD_TY, tx0 = (blockIdx.x % tiles_x) * BWD_TX;
+  const int ty1 = min(ty0 + BWD_TY, H), tx1 = min(tx0 + BWD_TX, W);
+  const RoiMeta* metas = reinterpret_cast<const RoiMeta*>(ws + ws_meta_off());
+  const float* tables = reinterpret_cast<const float*>(ws + ws_table_off(R));
+  const bool cvalid = (c0 + lane) < C;
+
+  for (int i = t; i < BWD_TY * BWD_TX * BWD_CB; i += BWD_THREADS) acc[i] = 0.f;
+
+  for (int rbase = 0; rbase < R; rbase += BWD_LIST) {
+    // ---- ordered compaction of the RoIs of image b that touch this tile
+    if (t == 0) s_count = 0;
+    __syncthreads();
+    const int rend = min(rbase + BWD_LIST, R);
+    for (int r0 = rbase; r0 < rend; r0 += BWD_THREADS) {
+      const int r = r0 + t;
+      bool hit = false;
+      if (r < rend) {
+        const RoiMeta m = metas[r];
+        hit = (m.b == b) && m.ny > 0 && m.y_lo < ty1 && m.y_lo + m.ny > ty0 &&
+              m.x_lo < tx1 && m.x_lo + m.nx > tx0;
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, hit);
+      if (lane == 0) s_wcount[wid] = __popc(bal);
+      __syncthreads();
+      int off = s_count;
+      for (int w = 0; w < wid; ++w) off += s_wcount[w];
+      if (hit) list[off + __popc(bal & ((1u << lane) - 1u))] = r;
+      __syncthreads();
+      if (t == 0) {
+        int tot = 0;
+        for (int w = 0; w < BWD_THREADS / 32; ++w) tot += s_wcount[w];
+        s_count += tot;
+      }
+      __syncthreads();
+    }
+    const int n_list = s_count;
+
+    // ---- walk the list in RoI order
+    for (int li = 0; li < n_list; ++li) {
+      const int r = list[li];
+      const RoiMeta m = metas[r];
+      const int ya = max(m.y_lo, ty0), yb = min(m.y_lo + m.ny, ty1);  // rows [ya,yb)
+      const int xa = max(m.x_lo, tx0), xb = min(m.x_lo + m.nx, tx1);
+      // stage grad_out[r, c0:c0+32, 49] and the table slices
+      if (kLayout == DA_ROI_OUT_RCHW) {
+        const TG* g = grad_out + ((size_t)r * C + c0) * PP;
+        const int total = min(BWD_CB, C - c0) * PP;
+        for (int i = t; i < BWD_CB * PP; i += BWD_THREADS) g_s[i] = (i < total) ? to_f32<TG>(g[i]) : 0.f;
+      } else {
+        const TG* g = grad_out + (size_t)r * PP * C + c0;
+        for (int i = t; i < BWD_CB * PP; i += BWD_THREADS) {
+          const int k = i >> 5, cl = i & 31;
+          g_s[cl * PP + k] = (c0 + cl < C) ? to_f32<TG>(g[(size_t)k * C + cl]) : 0.f;
+        }
+      }
+      const float* tab = tables + (size_t)r * (H + W) * WROW;
+      const float inv_count = 1.f / (float)m.count;
+      for (int i = t; i < (yb - ya) * WROW; i += BWD_THREADS)
+        wy_s[i] = tab[(size_t)(ya - m.y_lo) * WROW + i] * inv_count;
+      for (int i = t; i < (xb - xa) * WROW; i += BWD_THREADS)
+        wx_s[i] = tab[(size_t)H * WROW + (size_t)(xa - m.x_lo) * WROW + i];
+      __syncthreads();
+
+      // warp `wid` takes rows ya+wid, ya+wid+8, ...; lane = channel
+      for (int y = ya + wid; y < yb; y += BWD_THREADS / 32) {
+        float U[P];
+#pragma unroll
+        for (int q = 0; q < P; ++q) U[q] = 0.f;
+        const float4 wa = reinterpret_cast<const float4*>(wy_s)[(y - ya) * 2];
+        const float4 wb = reinterpret_cast<const float4*>(wy_s)[(y - ya) * 2 + 1];
+        const float wyv[P] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z};
+#pragma unroll
+        for (int ph = 0; ph < P; ++ph) {
+          if (wyv[ph] != 0.f) {
+#pragma unroll
+            for (int pw = 0; pw < P; ++pw)
+              U[pw] = fmaf(wyv[ph], g_s[lane * PP + ph * P + pw], U[pw]);
+          }
+        }
+        float* arow = acc + ((size_t)(y - ty0) * BWD_TX + (xa - tx0)) * BWD_CB + lane;
+        for (int x = xa; x < xb; ++x) {
+          const float4 xa4 = reinterpret_cast<const float4*>(wx_s)[(x - xa) * 2];
+          const float4 xb4 = reinterpret_cast<const float4*>(wx_s)[(x - xa) * 2 + 1];
+          float v = xa4.x * U[0];
+          v = fmaf(xa4.y, U[1], v); v = fmaf(xa4.z, U[2], v); v = fmaf(xa4.w, U[3], v);
+          v = fmaf(xb4.x, U[4], v); v = fmaf(xb4.y, U[5], v); v = fmaf(xb4.z, U[6], v);
+          arow[(x - xa) * BWD_CB] += v;
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- write the tile once (NHWC: 32 channels = 128 B per pixel)
+  for (int i = t; i < BWD_TY * BWD_TX * BWD_CB; i += BWD_THREADS) {
+    const int cl = i & 31, p = i >> 5;
+    const int y = ty0 + p / BWD_TX, x = tx0 + p % BWD_TX;
+    if (y < H && x < W && c0 + cl < C)
+      grad_in[(((size_t)b * H + y) * W + x) * C + c0 + cl] = acc[i];
+  }
+  (void)cvalid;
+}
+
+__global__ void map_roi_levels_kernel(const float* __restrict__ rois, int R, int num_levels,
+                                      float finest_scale, int32_t* __restrict__ out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const float* q = rois + (size_t)r * 5;
+  // scale = sqrt((x2-x1)*(y2-y1)); lvl = floor(log2(scale/finest + 1e-6)) clamped
+  const float s = sqrtf(__fmul_rn(__fsub_rn(q[3], q[1]), __fsub_rn(q[4], q[2])));
+  float l = floorf(log2f(__fadd_rn(__fdiv_rn(s, finest_scale), 1e-6f)));
+  // NaN (negative area) -> clamp(min) in torch yields NaN -> .long() is implementation
+  // defined; we map it to level 0.
+  int lv = (l != l) ? 0 : (int)fminf(fmaxf(l, 0.f), (float)(num_levels - 1));
+  out[r] = lv;
+}
+
+}  // namespace da
+
+using namespace da;
+
+extern "C" size_t da_roi_align_workspace_bytes(int R, int H, int W) {
+  if (R < 0) R = 0;
+  return ws_table_off(R) + (size_t)R * (size_t)(H + W) * WROW * sizeof(float) + 256;
+}
+
+static int check_common(int N, int C, int H, int W, int R, int ph, int pw, const void* rois,
+                        const void* ws, size_t ws_bytes) {
+  DA_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0, DA_ERR_INVALID_ARG, "roi_align: bad feature shape [%d,%d,%d,%d]", N, C, H, W);
+  DA_REQUIRE(R >= 0, DA_ERR_INVALID_ARG, "roi_align: negative RoI count %d", R);
+  DA_REQUIRE(ph == P && pw == P, DA_ERR_UNSUPPORTED, "roi_align: only output_size=7 is built (got %dx%d)", ph, pw);
+  DA_REQUIRE(R == 0 || rois != nullptr, DA_ERR_INVALID_ARG, "roi_align: rois is null");
+  DA_REQUIRE(R == 0 || ws != nullptr, DA_ERR_WORKSPACE, "roi_align: workspace is null");
+  DA_REQUIRE(ws_bytes >= da_roi_align_workspace_bytes(R, H, W), DA_ERR_WORKSPACE,
+             "roi_align: workspace too small (%zu < %zu)", ws_bytes, da_roi_align_workspace_bytes(R, H, W));
+  DA_REQUIRE((size_t)(H + W) * WROW * 4 + (FWD_CB * PP + 8) * 4 <= 220 * 1024, DA_ERR_UNSUPPORTED,
+             "roi_align: H+W=%d too large for the shared-memory weight tables", H + W);
+  return DA_OK;
+}
+
+static int run_prep(const float* rois, int R, int N, int H, int W, float scale, int sr, int aligned,
+                    void* ws, int32_t* grid_out, cudaStream_t st) {
+  DA_CUDA_OK(cudaMemsetAsync(ws, 0, 16, st));
+  roi_prep_kernel<<<R, 32, 0, st>>>(rois, R, N, H, W, scale, sr, aligned, (unsigned char*)ws, grid_out);
+  DA_LAUNCH_CHECK();
+  return DA_OK;
+}
+
+template <typename TIn, typename TOut>
+static int launch_fwd(const void* feat, int C, int H, int W, int R, const void* ws, void* out,
+                      int layout, cudaStream_t st) {
+  const size_t smem = ((size_t)(H + W) * WROW + FWD_CB * PP + 8) * sizeof(float);
+  dim3 grid((C + FWD_CB - 1) / FWD_CB, R);
+  if (layout == DA_ROI_OUT_RCHW) {
+    auto k = roi_align_fwd_kernel<TIn, TOut, DA_ROI_OUT_RCHW>;
+    DA_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, FWD_THREADS, smem, st>>>((const TIn*)feat, C, H, W, R, (const unsigned char*)ws, (TOut*)out);
+  } else {
+    auto k = roi_align_fwd_kernel<TIn, TOut, DA_ROI_OUT_RHWC>;
+    DA_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, FWD_THREADS, smem, st>>>((const TIn*)feat, C, H, W, R, (const unsigned char*)ws, (TOut*)out);
+  }
+  DA_LAUNCH_CHECK();
+  return DA_OK;
+}
+
+extern "C" int da_roi_align_forward(const void* feat, int feat_dtype, int N, int C, int H, int W,
+                                    const float* rois, int R, int pooled_h, int pooled_w,
+                                    float spatial_scale, int sampling_ratio, int aligned,
+                                    void* out, int out_dtype, int out_layout, int32_t* grid_out,
+                                    void* workspace, size_t workspace_bytes, da_stream_t stream) {
+  int rc = check_common(N, C, H, W, R, pooled_h, pooled_w, rois, workspace, workspace_bytes);
+  if (rc) return rc;
+  DA_REQUIRE(out_layout == DA_ROI_OUT_RCHW || out_layout == DA_ROI_OUT_RHWC, DA_ERR_INVALID_ARG, "roi_align: bad out_layout %d", out_layout);
+  if (R == 0) return DA_OK;  // single_level_roi_extractor.py:77-78: empty RoI set -> empty output
+  DA_REQUIRE(feat && out, DA_ERR_INVALID_ARG, "roi_align: null feature/output pointer");
+  DA_REQUIRE(feat_dtype != DA_BF16 || (C % 2 == 0), DA_ERR_UNSUPPORTED, "roi_align: bf16 features need even C");
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = run_prep(rois, R, N, H, W, spatial_scale, sampling_ratio, aligned, workspace, grid_out, st);
+  if (rc) return rc;
+  if (feat_dtype == DA_F32 && out_dtype == DA_F32) return launch_fwd<float, float>(feat, C, H, W, R, workspace, out, out_layout, st);
+  if (feat_dtype == DA_F32 && out_dtype == DA_BF16) return launch_fwd<float, __nv_bfloat16>(feat, C, H, W, R, workspace, out, out_layout, st);
+  if (feat_dtype == DA_BF16 && out_dtype == DA_F32) return launch_fwd<__nv_bfloat16, float>(feat, C, H, W, R, workspace, out, out_layout, st);
+  if (feat_dtype == DA_BF16 && out_dtype == DA_BF16) return launch_fwd<__nv_bfloat16, __nv_bfloat16>(feat, C, H, W, R, workspace, out, out_layout, st);
+  DA_REQUIRE(false, DA_ERR_INVALID_ARG, "roi_align: bad dtype %d/%d", feat_dtype, out_dtype);
+}
+
+template <typename TG>
+static int launch_bwd(const void* g, int layout, int N, int C, int H, int W, int R, const void* ws,
+                      float* gin, cudaStream_t st) {
+  const size_t smem = ((size_t)BWD_TY * BWD_TX * BWD_CB + BWD_CB * PP + 16 + (BWD_TY + BWD_TX) * WROW) * sizeof(float) +
+                      BWD_LIST * sizeof(int);
+  const int tiles_x = (W + BWD_TX - 1) / BWD_TX, tiles_y = (H + BWD_TY - 1) / BWD_TY;
+  dim3 grid(tiles_x * tiles_y, (C + BWD_CB - 1) / BWD_CB, N);
+  DA_REQUIRE(grid.y <= 65535 && grid.z <= 65535, DA_ERR_UNSUPPORTED, "roi_align_backward: grid too large");
+  if (layout == DA_ROI_OUT_RCHW) {
+    auto k = roi_align_bwd_kernel<TG, DA_ROI_OUT_RCHW>;
+    DA_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, BWD_THREADS, smem, st>>>((const TG*)g, C, H, W, R, (const unsigned char*)ws, gin, tiles_x);
+  } else {
+    auto k = roi_align_bwd_kernel<TG, DA_ROI_OUT_RHWC>;
+    DA_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, BWD_THREADS, smem, st>>>((const TG*)g, C, H, W, R, (const unsigned char*)ws, gin, tiles_x);
+  }
+  DA_LAUNCH_CHECK();
+  return DA_OK;
+}
+
+extern "C" int da_roi_align_backward(const void* grad_out, int grad_dtype, int out_layout,
+                                     const float* rois, int R, int pooled_h, int pooled_w,
+                                     float spatial_scale, int sampling_ratio, int aligned,
+                                     float* grad_in, int N, int C, int H, int W,
+                                     void* workspace, size_t workspace_bytes, da_stream_t stream) {
+  int rc = check_common(N, C, H, W, R, pooled_h, pooled_w, rois, workspace, workspace_bytes);
+  if (rc) return rc;
+  DA_REQUIRE(grad_in != nullptr, DA_ERR_INVALID_ARG, "roi_align_backward: grad_in is null");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (R == 0) {
+    DA_CUDA_OK(cudaMemsetAsync(grad_in, 0, (size_t)N * C * H * W * sizeof(float), st));
+    return DA_OK;
+  }
+  DA_REQUIRE(grad_out != nullptr, DA_ERR_INVALID_ARG, "roi_align_backward: grad_out is null");
+  rc = run_prep(rois, R, N, H, W, spatial_scale, sampling_ratio, aligned, workspace, nullptr, st);
+  if (rc) return rc;
+  if (grad_dtype == DA_F32) return launch_bwd<float>(grad_out, out_layout, N, C, H, W, R, workspace, grad_in, st);
+  if (grad_dtype == DA_BF16) return launch_bwd<__nv_bfloat16>(grad_out, out_layout, N, C, H, W, R, workspace, grad_in, st);
+  DA_REQUIRE(false, DA_ERR_INVALID_ARG, "roi_align_backward: bad dtype %d", grad_dtype);
+}
+
+extern "C" int da_map_roi_levels(const float* rois, int R, int num_levels, float finest_scale,
+                                 int32_t* levels_out, da_stream_t stream) {
+  DA_REQUIRE(R >= 0 && num_levels > 0, DA_ERR_INVALID_ARG, "map_roi_levels: bad args");
+  if (R == 0) return DA_OK;
+  map_roi_levels_kernel<<<(R + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rois, R, num_levels, finest_scale, levels_out);
+  DA_LAUNCH_CHECK();
+  return DA_OK;
+}

@@ -1,0 +1,995 @@
+// tcgen05 / TMEM / TMA implicit-GEMM engine for the domain-classifier convs and FC stacks
+// (DA_ENGINE_UMMA_BF16, DA_ENGINE_UMMA_BF16X3) — sm_100a only.
+//
+// One warp-specialised kernel serves forward and data-gradient ("NT" form: both operands
+// K-major), a second one the weight gradient ("TN" form: both operands MN-major, the
+// reduction runs over pixels):
+//
+//   warp 0 (1 thread)  TMA producer : cp.async.bulk.tensor boxes -> 128B-swizzled smem ring
+//   warp 1 (1 thread)  MMA issuer   : tcgen05.mma.cta_group::1.kind::f16, fp32 accumulator in TMEM
+//   warps 2..5         epilogue     : tcgen05.ld TMEM -> registers -> fused epilogue -> global
+//
+// Implicit GEMM without im2col: activations are NHWC, so for one filter tap the A tile of a
+// BHxBW patch of output pixels is a rank-4 TMA box (64 channels, BW, BH, 1 image) whose
+// start coordinate is shifted by the tap; out-of-bounds (padding) is zero-filled by TMA.
+// Stride-s convolutions use s*s "parity" tensor maps (base pointer shifted by the parity,
+// pixel strides multiplied by s), so no element-stride traversal is needed.  The data
+// gradient of a strided conv is run per output-parity class with the subset of taps that
+// reaches that class.  GRL: the data-gradient epilogue multiplies by out_scale (= -lambda),
+// so the reversed gradient is emitted by the same pass (instance_da.py:20-23).
+//
+// BF16X3: fp32 operands are split x = hi + lo (bf16 each) and the kernel accumulates
+// hi*hi + hi*lo + lo*hi into the same TMEM accumulator (3 k-passes), ~2^-16 relative.
+#include "da_common.cuh"
+#include <cuda.h>
+#include <string.h>
+
+namespace da {
+
+// ---------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trapped kernel, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) {
+      printf("da_b200: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives once every previously issued tcgen05.mma of this thread has completed.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+#define DA_TMEM_LD32(taddr, v)                                                                        \
+  asm volatile(                                                                                       \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                       \
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                        \
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"        \
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), \
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),       \
+        "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),     \
+        "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),     \
+        "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                                          \
+      : "r"(taddr)                                                                                    \
+      : "memory")
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptors (cute::UMMA::SmemDescriptor bit layout, version 1, SWIZZLE_128B).
+// K-major tile: rows of 128 B (64 bf16 of K), 8-row swizzle atoms 1024 B apart (SBO).
+__device__ __forceinline__ uint64_t desc_kmajor_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// MN-major tile: rows (one k each) of 128 B = 64 bf16 of M/N; 8 k-rows per atom (SBO = 1024 B);
+// the next 64-element block along M/N starts lbo_bytes further (LBO).
+__device__ __forceinline__ uint64_t desc_mnmajor_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, M x N, majors.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------
+// kernel parameters
+// ---------------------------------------------------------------------------------------
+constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int STAGES = 5;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+constexpr int NT_THREADS = 192;
+constexpr int MAX_TAPS = 16;
+constexpr size_t NT_SMEM = 1024 + (size_t)STAGES * (A_BYTES + B_BYTES) + 256;
+
+struct TapInfo {
+  int map;  // which parity tensor map of A
+  int dh, dw;
+  int bk;   // K offset of this tap inside the B matrix
+};
+
+struct NtParams {
+  CUtensorMap a_map[2][4];  // [hi/lo term][parity]
+  CUtensorMap b_map[2];     // [hi/lo term]
+  TapInfo taps[MAX_TAPS];
+  int num_taps, kchunks;    // k iterations per term = num_taps * kchunks
+  int num_terms;
+  int term_a[3], term_b[3];
+  int flat;                 // A is a flat [M,K] matrix (1x1 / FC)
+  int BH, BW, bw_shift;     // patch shape (BH*BW == 128, powers of two)
+  int TH, TW;               // extent of the tile grid in (class) pixels
+  int tiles_h, tiles_w;
+  long long M_flat;
+  // output addressing: pixel (n, i, j) of the tile grid -> y[((n*OHf + i*os+oa)*OWf + j*os+ob)*Cout + c]
+  int OHf, OWf, os, oa, ob, Cout;
+  const float* scale;
+  const float* shift;
+  int relu;
+  float drop_p;
+  unsigned long long seed;
+  float out_scale;
+  void* y;
+  int y_dtype;
+  float* partial;  // split-K: fp32 [splits][numel(y)]
+  long long y_numel;
+};
+
+template <typename T> struct Pack;
+template <> struct Pack<__nv_bfloat16> {
+  __device__ static void store8(__nv_bfloat16* p, const float* v) {
+    uint4 u;
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+    u.x = *reinterpret_cast<unsigned*>(&a); u.y = *reinterpret_cast<unsigned*>(&b);
+    u.z = *reinterpret_cast<unsigned*>(&c); u.w = *reinterpret_cast<unsigned*>(&d);
+    *reinterpret_cast<uint4*>(p) = u;
+  }
+};
+
+// Fused epilogue of one 32-column chunk of one accumulator row.
+__device__ __forceinline__ void nt_epilogue_row(const NtParams& P, const uint32_t* v, size_t row_off, int c_base,
+                                                bool raw_partial, float* partial) {
+  const int ncols = min(32, P.Cout - c_base);
+  if (ncols <= 0) return;
+  float f[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+  if (raw_partial) {
+    float* o = partial + row_off + c_base;
+    if (ncols == 32 && ((row_off + c_base) & 3) == 0) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+    } else {
+      for (int j = 0; j < ncols; ++j) o[j] = f[j];
+    }
+    return;
+  }
+  const uint32_t thr = drop_threshold(P.drop_p);
+  const float keep_scale = P.drop_p > 0.f ? 1.f / (1.f - P.drop_p) : 1.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int c = c_base + j;
+    float x = f[j] * P.out_scale;
+    if (j < ncols) {
+      if (P.scale) x *= __ldg(P.scale + c);
+      if (P.shift) x += __ldg(P.shift + c);
+    }
+    if (P.relu) x = fmaxf(x, 0.f);
+    if (P.drop_p > 0.f) x = (drop_hash(P.seed, (uint64_t)(row_off + c)) >= thr) ? x * keep_scale : 0.f;
+    f[j] = x;
+  }
+  if (P.y_dtype == DA_BF16) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(P.y) + row_off + c_base;
+    if (ncols == 32 && ((row_off + c_base) & 7) == 0) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) Pack<__nv_bfloat16>::store8(o + j, f + j);
+    } else {
+      for (int j = 0; j < ncols; ++j) o[j] = __float2bfloat16_rn(f[j]);
+    }
+  } else {
+    float* o = reinterpret_cast<float*>(P.y) + row_off + c_base;
+    if (ncols == 32 && ((row_off + c_base) & 3) == 0) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+    } else {
+      for (int j = 0; j < ncols; ++j) o[j] = f[j];
+    }
+  }
+}
+
+// grid: (pixel tiles, Cout tiles, k-splits)
+__global__ void __launch_bounds__(NT_THREADS, 1)
+umma_nt_kernel(const __grid_constant__ NtParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_s = base, b_s = base + STAGES * A_BYTES;
+  const uint32_t bars = b_s + STAGES * B_BYTES;  // full[STAGES], empty[STAGES], tmem_full, tmem_slot
+  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull = bars + 16 * STAGES, tslot = tfull + 8;
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  volatile uint32_t* tslot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tslot - base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // tile coordinates
+  int n_img = 0, i0 = 0, j0 = 0;
+  long long m0 = 0;
+  if (P.flat) {
+    m0 = (long long)blockIdx.x * BM;
+  } else {
+    const int per_img = P.tiles_h * P.tiles_w;
+    n_img = blockIdx.x / per_img;
+    const int t = blockIdx.x % per_img;
+    i0 = (t / P.tiles_w) * P.BH;
+    j0 = (t % P.tiles_w) * P.BW;
+  }
+  const int c0 = blockIdx.y * BN;
+  const int total_iters = P.num_terms * P.num_taps * P.kchunks;
+  const int splits = gridDim.z;
+  const int per_split = (total_iters + splits - 1) / splits;
+  const int it_begin = blockIdx.z * per_split;
+  const int it_end = min(it_begin + per_split, total_iters);
+  const int n_iters = max(it_end - it_begin, 0);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tslot, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tslot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int k = 0; k < n_iters; ++k) {
+        const int it = it_begin + k;
+        const int s = k % STAGES;
+        const uint32_t ph = (k / STAGES) & 1;
+        mbar_wait(empty0 + 8 * s, ph ^ 1);
+        const int per_term = P.num_taps * P.kchunks;
+        const int term = it / per_term, rem = it % per_term;
+        const int tap = rem / P.kchunks, kc = rem % P.kchunks;
+        const TapInfo ti = P.taps[tap];
+        mbar_expect_tx(full0 + 8 * s, A_BYTES + B_BYTES);
+        if (P.flat)
+          tma_load_2d(a_s + s * A_BYTES, &P.a_map[P.term_a[term]][0], full0 + 8 * s, kc * BK, (int)m0);
+        else
+          tma_load_4d(a_s + s * A_BYTES, &P.a_map[P.term_a[term]][ti.map], full0 + 8 * s, kc * BK, j0 + ti.dw, i0 + ti.dh, n_img);
+        tma_load_2d(b_s + s * B_BYTES, &P.b_map[P.term_b[term]], full0 + 8 * s, ti.bk + kc * BK, c0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN, 0, 0);
+      for (int k = 0; k < n_iters; ++k) {
+        const int s = k % STAGES;
+        const uint32_t ph = (k / STAGES) & 1;
+        mbar_wait(full0 + 8 * s, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < BK / 16; ++kk) {
+          const uint64_t ad = desc_kmajor_sw128(a_s + s * A_BYTES + kk * 32);
+          const uint64_t bd = desc_kmajor_sw128(b_s + s * B_BYTES + kk * 32);
+          umma_bf16(tmem_base, ad, bd, idesc, (k > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(empty0 + 8 * s);
+      }
+      umma_commit(tfull);
+    }
+  } else {
+    // epilogue warps 2..5 -> TMEM lane quadrant (warp % 4)
+    const int q = warp & 3;
+    const int r = q * 32 + lane;  // accumulator row == pixel within the tile
+    bool valid;
+    size_t row_off;
+    if (P.flat) {
+      const long long m = m0 + r;
+      valid = m < P.M_flat;
+      row_off = (size_t)m * P.Cout;
+    } else {
+      const int i = i0 + (r >> P.bw_shift), j = j0 + (r & (P.BW - 1));
+      valid = (i < P.TH) && (j < P.TW);
+      row_off = (((size_t)n_img * P.OHf + (size_t)i * P.os + P.oa) * P.OWf + (size_t)j * P.os + P.ob) * P.Cout;
+    }
+    const bool raw = splits > 1;
+    float* partial = raw ? P.partial + (size_t)blockIdx.z * P.y_numel : nullptr;
+    if (n_iters > 0) {
+      mbar_wait(tfull, 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int cc = 0; cc < BN / 32; ++cc) {
+      uint32_t v[32];
+      if (n_iters > 0) {
+        DA_TMEM_LD32(tmem_base + ((uint32_t)(q * 32) << 16) + cc * 32, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      if (valid) nt_epilogue_row(P, v, row_off, c0 + cc * 32, raw, partial);
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// split-K finish: y = epilogue(sum_s partial[s])
+__global__ void nt_splitk_finish_kernel(const float* __restrict__ partial, int splits, long long numel, int Cout,
+                                        const float* __restrict__ scale, const float* __restrict__ shift, int relu,
+                                        float drop_p, unsigned long long seed, float out_scale, void* y, int y_dtype) {
+  const uint32_t thr = drop_threshold(drop_p);
+  const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += (long long)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += partial[(size_t)s * numel + i];
+    const int c = (int)(i % Cout);
+    float x = acc * out_scale;
+    if (scale) x *= scale[c];
+    if (shift) x += shift[c];
+    if (relu) x = fmaxf(x, 0.f);
+    if (drop_p > 0.f) x = (drop_hash(seed, (uint64_t)i) >= thr) ? x * keep_scale : 0.f;
+    if (y_dtype == DA_BF16) reinterpret_cast<__nv_bfloat16*>(y)[i] = __float2bfloat16_rn(x);
+    else reinterpret_cast<float*>(y)[i] = x;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// weight gradient ("TN"): dW[co, tap, ci] = sum_pix dZ[pix, co] * X[pix_in(tap), ci]
+// ---------------------------------------------------------------------------------------
+constexpr int WK = 64;  // pixels per k-step
+constexpr int W_A_BYTES = BM * WK * 2, W_B_BYTES = BN * WK * 2;
+
+struct TnParams {
+  CUtensorMap a_map[2];     // dZ [hi/lo]: (Cout, OW, OH, N) or flat (Cout, M)
+  CUtensorMap b_map[2][4];  // X  [hi/lo][parity]
+  TapInfo taps[MAX_TAPS];
+  int num_taps, num_terms;
+  int term_a[3], term_b[3];
+  int flat;
+  int BH, BW;               // pixel patch per k-step (BH*BW == 64)
+  int tiles_h, tiles_w, NB; // patch grid
+  long long M_flat;
+  int Cout, Cin;
+  float* dw;                // [Cout, taps, Cin] fp32 (or partial [splits][...])
+  long long dw_numel;
+};
+
+// grid: (Cout tiles, Cin tiles, taps * splits)
+__global__ void __launch_bounds__(NT_THREADS, 1)
+umma_tn_kernel(const __grid_constant__ TnParams P, int splits) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_s = base, b_s = base + STAGES * W_A_BYTES;
+  const uint32_t bars = b_s + STAGES * W_B_BYTES;
+  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull = bars + 16 * STAGES, tslot = tfull + 8;
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  volatile uint32_t* tslot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tslot - base));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int co0 = blockIdx.x * BM, ci0 = blockIdx.y * BN;
+  const int tap = blockIdx.z % P.num_taps, split = blockIdx.z / P.num_taps;
+  const TapInfo ti = P.taps[tap];
+  const long long patches = P.flat ? (P.M_flat + WK - 1) / WK : (long long)P.NB * P.tiles_h * P.tiles_w;
+  const long long total_iters = patches * P.num_terms;
+  const long long per_split = (total_iters + splits - 1) / splits;
+  const long long it_begin = split * per_split;
+  const long long it_end = (it_begin + per_split < total_iters) ? it_begin + per_split : total_iters;
+  const int n_iters = (int)((it_end > it_begin) ? it_end - it_begin : 0);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tslot, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tslot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int k = 0; k < n_iters; ++k) {
+        const long long it = it_begin + k;
+        const int s = k % STAGES;
+        const uint32_t ph = (k / STAGES) & 1;
+        mbar_wait(empty0 + 8 * s, ph ^ 1);
+        const int term = (int)(it / patches);
+        const long long patch = it % patches;
+        mbar_expect_tx(full0 + 8 * s, W_A_BYTES + W_B_BYTES);
+        const uint32_t fb = full0 + 8 * s;
+        const uint32_t ad = a_s + s * W_A_BYTES, bd = b_s + s * W_B_BYTES;
+        if (P.flat) {
+          const int m = (int)(patch * WK);
+          tma_load_2d(ad, &P.a_map[P.term_a[term]], fb, co0, m);
+          tma_load_2d(ad + W_A_BYTES / 2, &P.a_map[P.term_a[term]], fb, co0 + 64, m);
+          tma_load_2d(bd, &P.b_map[P.term_b[term]][0], fb, ci0, m);
+          tma_load_2d(bd + W_B_BYTES / 2, &P.b_map[P.term_b[term]][0], fb, ci0 + 64, m);
+        } else {
+          const int per_img = P.tiles_h * P.tiles_w;
+          const int n = (int)(patch / per_img), t = (int)(patch % per_img);
+          const int i0 = (t / P.tiles_w) * P.BH, j0 = (t % P.tiles_w) * P.BW;
+          tma_load_4d(ad, &P.a_map[P.term_a[term]], fb, co0, j0, i0, n);
+          tma_load_4d(ad + W_A_BYTES / 2, &P.a_map[P.term_a[term]], fb, co0 + 64, j0, i0, n);
+          tma_load_4d(bd, &P.b_map[P.term_b[term]][ti.map], fb, ci0, j0 + ti.dw, i0 + ti.dh, n);
+          tma_load_4d(bd + W_B_BYTES / 2, &P.b_map[P.term_b[term]][ti.map], fb, ci0 + 64, j0 + ti.dw, i0 + ti.dh, n);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN, 1, 1);
+      for (int k = 0; k < n_iters; ++k) {
+        const int s = k % STAGES;
+        const uint32_t ph = (k / STAGES) & 1;
+        mbar_wait(full0 + 8 * s, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < WK / 16; ++kk) {
+          // 16 k-rows = 2 swizzle atoms of 1024 B
+          const uint64_t adsc = desc_mnmajor_sw128(a_s + s * W_A_BYTES + kk * 2048, W_A_BYTES / 2);
+          const uint64_t bdsc = desc_mnmajor_sw128(b_s + s * W_B_BYTES + kk * 2048, W_B_BYTES / 2);
+          umma_bf16(tmem_base, adsc, bdsc, idesc, (k > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(empty0 + 8 * s);
+      }
+      umma_commit(tfull);
+    }
+  } else {
+    const int q = warp & 3;
+    const int co = co0 + q * 32 + lane;
+    float* out = P.dw + (size_t)split * P.dw_numel;
+    if (n_iters > 0) {
+      mbar_wait(tfull, 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int cc = 0; cc < BN / 32; ++cc) {
+      uint32_t v[32];
+      if (n_iters > 0) {
+        DA_TMEM_LD32(tmem_base + ((uint32_t)(q * 32) << 16) + cc * 32, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      const int cb = ci0 + cc * 32;
+      if (co < P.Cout && cb < P.Cin) {
+        float* o = out + ((size_t)co * P.num_taps + tap) * P.Cin + cb;
+        const int ncols = min(32, P.Cin - cb);
+        if (ncols == 32 && (P.Cin & 3) == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(o + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                            __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        } else {
+          for (int j = 0; j < ncols; ++j) o[j] = __uint_as_float(v[j]);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+__global__ void sum_splits_kernel(const float* __restrict__ part, int splits, long long n, float* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += part[(size_t)s * n + i];
+    out[i] = acc;
+  }
+}
+
+// [O][T][I] -> [I][T][O] (weights for the data gradient), with optional hi/lo split
+template <typename TS>
+__global__ void weight_oti_to_ito_kernel(const TS* __restrict__ src, __nv_bfloat16* __restrict__ hi,
+                                         __nv_bfloat16* __restrict__ lo, int O, int T, int I) {
+  __shared__ float tile[32][33];
+  const int t = blockIdx.z;
+  const int i0 = blockIdx.x * 32, o0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int o = o0 + j, i = i0 + threadIdx.x;
+    if (o < O && i < I) tile[j][threadIdx.x] = to_f32<TS>(src[((size_t)o * T + t) * I + i]);
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int i = i0 + j, o = o0 + threadIdx.x;
+    if (o < O && i < I) {
+      const float v = tile[threadIdx.x][j];
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      const size_t d = ((size_t)i * T + t) * O + o;
+      hi[d] = h;
+      if (lo) lo[d] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+  }
+}
+
+__global__ void cast_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+__global__ void split_hi_lo_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi,
+                                   __nv_bfloat16* __restrict__ lo, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = src[i];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// bf16 tensor map, innermost dim first.  rank 2 or 4.
+static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box) {
+  EncodeTiledFn fn = get_encode();
+  DA_REQUIRE(fn != nullptr, DA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t gd[5];
+  cuuint64_t gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i < rank - 1; ++i) gs[i] = strides_bytes[i];
+  DA_REQUIRE(((uintptr_t)base & 15) == 0, DA_ERR_INVALID_ARG, "tensor map base %p is not 16-byte aligned", base);
+  for (int i = 0; i < rank - 1; ++i)
+    DA_REQUIRE((gs[i] & 15) == 0, DA_ERR_UNSUPPORTED, "tensor map stride %llu is not a multiple of 16 bytes (channel counts must be multiples of 8)", (unsigned long long)gs[i]);
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DA_REQUIRE(r == CUDA_SUCCESS, DA_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return DA_OK;
+}
+
+static inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+static inline int posmod(int a, int b) { int m = a % b; return m < 0 ? m + b : m; }
+static inline int ilog2(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }
+
+// Pick the BHxBW patch (BH*BW == pixels, powers of two) that wastes the fewest tile pixels.
+static void pick_patch(int TH, int TW, int pixels, int* BH, int* BW) {
+  long long best = -1;
+  for (int bw = 1; bw <= pixels; bw <<= 1) {
+    const int bh = pixels / bw;
+    if (bw > 256 || bh > 256) continue;
+    const long long cover = (long long)((TH + bh - 1) / bh) * bh * ((TW + bw - 1) / bw) * bw;
+    if (best < 0 || cover < best || (cover == best && bw > *BW)) { best = cover; *BH = bh; *BW = bw; }
+  }
+}
+
+// Parity tensor maps of an NHWC activation tensor [N,H,W,C] for a stride-s gather:
+// map (pa,pb): pixel (i,j) -> x[n, s*i+pa, s*j+pb, :].  box = (64 ch, BW, BH, 1).
+static int make_parity_maps(CUtensorMap* maps, bool* present, const __nv_bfloat16* x, int N, int H, int W, int C, int s,
+                            int BH, int BW) {
+  for (int pa = 0; pa < s; ++pa)
+    for (int pb = 0; pb < s; ++pb) {
+      const int idx = pa * s + pb;
+      const int Hp = (H - pa + s - 1) / s, Wp = (W - pb + s - 1) / s;
+      present[idx] = (Hp > 0 && Wp > 0);
+      if (!present[idx]) continue;
+      const uint64_t dims[4] = {(uint64_t)C, (uint64_t)Wp, (uint64_t)Hp, (uint64_t)N};
+      const uint64_t strides[3] = {(uint64_t)s * C * 2, (uint64_t)s * W * C * 2, (uint64_t)H * W * C * 2};
+      const uint32_t box[4] = {64, (uint32_t)BW, (uint32_t)BH, 1};
+      int rc = encode_map(&maps[idx], x + ((size_t)pa * W + pb) * C, 4, dims, strides, box);
+      if (rc) return rc;
+    }
+  return DA_OK;
+}
+
+struct Geom {
+  int N, H, W, Cin, Cout, KH, KW, s, p, OH, OW;
+};
+static Geom geom_of(const da_conv_desc* d) {
+  Geom g{d->N, d->H, d->W, d->Cin, d->Cout, d->KH, d->KW, d->stride, d->pad, 0, 0};
+  g.OH = (d->H + 2 * d->pad - d->KH) / d->stride + 1;
+  g.OW = (d->W + 2 * d->pad - d->KW) / d->stride + 1;
+  return g;
+}
+static inline bool is_flat(const Geom& g) { return g.KH == 1 && g.KW == 1 && g.s == 1 && g.p == 0; }
+
+static int pick_splits(long long ctas, int k_iters) {
+  const int sms = num_sms();
+  if (ctas >= sms || k_iters < 8) return 1;
+  int s = (int)((sms + ctas - 1) / ctas);
+  if (s > k_iters / 4) s = k_iters / 4;
+  if (s > 16) s = 16;
+  return s < 1 ? 1 : s;
+}
+
+// ---- workspace layout -------------------------------------------------------------------
+// [0] fp32 split-K partials / wgrad partials   (part_bytes)
+// [1] operand staging: bf16 hi/lo copies of x (or dz) and of the weights (stage_bytes)
+static size_t part_bytes(const Geom& g) {
+  const size_t y = (size_t)g.N * g.OH * g.OW * g.Cout, x = (size_t)g.N * g.H * g.W * g.Cin;
+  const size_t w = (size_t)g.Cout * g.KH * g.KW * g.Cin;
+  size_t m = y > x ? y : x;
+  if (w > m) m = w;
+  // split-K only runs when fewer than one wave of 128x128 tiles exists, so the tensor that
+  // is split never exceeds ~160 tiles
+  const size_t cap = (size_t)160 * BM * BN;
+  if (m > cap) m = cap;
+  return align_up(m * 16 * sizeof(float), 256);
+}
+static size_t stage_bytes(const Geom& g) {
+  const size_t y = (size_t)g.N * g.OH * g.OW * g.Cout, x = (size_t)g.N * g.H * g.W * g.Cin;
+  const size_t w = (size_t)g.Cout * g.KH * g.KW * g.Cin;
+  // worst case (wgrad BF16X3): hi+lo of x and of dz; forward/dgrad: hi+lo of one activation + hi+lo weights
+  return align_up(2 * 2 * (x + y) + 2 * 2 * w + 1024, 256);
+}
+size_t umma_workspace_bytes(const da_conv_desc* d) {
+  if (d->engine == DA_ENGINE_SIMT_F32) return 0;
+  const Geom g = geom_of(d);
+  return part_bytes(g) + stage_bytes(g);
+}
+
+static int ew_blocks(long long n) {
+  long long b = (n + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  return (int)(b > cap ? cap : (b < 1 ? 1 : b));
+}
+
+// Prepare bf16 operand(s) from the caller's tensor: returns hi (and lo for BF16X3) pointers.
+static int prep_operand(const void* src, int dtype, long long n, int engine, uint8_t*& stage, const __nv_bfloat16** hi,
+                        const __nv_bfloat16** lo, cudaStream_t st) {
+  *lo = nullptr;
+  if (dtype == DA_BF16) {
+    DA_REQUIRE(engine == DA_ENGINE_UMMA_BF16, DA_ERR_UNSUPPORTED, "BF16X3 engine needs fp32 operands");
+    *hi = (const __nv_bfloat16*)src;
+    return DA_OK;
+  }
+  __nv_bfloat16* h = (__nv_bfloat16*)stage;
+  stage += align_up((size_t)n * 2, 256);
+  if (engine == DA_ENGINE_UMMA_BF16X3) {
+    __nv_bfloat16* l = (__nv_bfloat16*)stage;
+    stage += align_up((size_t)n * 2, 256);
+    split_hi_lo_kernel<<<ew_blocks(n), 256, 0, st>>>((const float*)src, h, l, n);
+    DA_LAUNCH_CHECK();
+    *lo = l;
+  } else {
+    cast_to_bf16_kernel<<<ew_blocks(n), 256, 0, st>>>((const float*)src, h, n);
+    DA_LAUNCH_CHECK();
+  }
+  *hi = h;
+  return DA_OK;
+}
+
+static void set_terms(int engine, int* num_terms, int* ta, int* tb) {
+  if (engine == DA_ENGINE_UMMA_BF16X3) {
+    *num_terms = 3;
+    ta[0] = 0; tb[0] = 0;  // hi*hi
+    ta[1] = 0; tb[1] = 1;  // hi*lo
+    ta[2] = 1; tb[2] = 0;  // lo*hi
+  } else {
+    *num_terms = 1;
+    ta[0] = tb[0] = 0; ta[1] = tb[1] = ta[2] = tb[2] = 0;
+  }
+}
+
+static int launch_nt(NtParams& P, long long pixel_tiles, int k_iters, void* ws_part, size_t part_cap, cudaStream_t st) {
+  const int n_tiles = (P.Cout + BN - 1) / BN;
+  // split-K partials are indexed like y; a strided (parity-class) launch only owns part of y
+  int splits = (P.os == 1) ? pick_splits(pixel_tiles * n_tiles, k_iters) : 1;
+  while (splits > 1 && (size_t)splits * P.y_numel * sizeof(float) > part_cap) --splits;
+  P.partial = (float*)ws_part;
+  DA_REQUIRE(pixel_tiles <= 0x7fffffffll, DA_ERR_UNSUPPORTED, "umma: too many tiles");
+  static bool attr_set = false;
+  if (!attr_set) {
+    DA_CUDA_OK(cudaFuncSetAttribute(umma_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NT_SMEM));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)pixel_tiles, n_tiles, splits);
+  umma_nt_kernel<<<grid, NT_THREADS, NT_SMEM, st>>>(P);
+  DA_LAUNCH_CHECK();
+  if (splits > 1) {
+    nt_splitk_finish_kernel<<<ew_blocks(P.y_numel), 256, 0, st>>>(P.partial, splits, P.y_numel, P.Cout, P.scale, P.shift,
+                                                                  P.relu, P.drop_p, P.seed, P.out_scale, P.y, P.y_dtype);
+    DA_LAUNCH_CHECK();
+  }
+  return DA_OK;
+}
+
+int umma_conv_forward(const da_conv_desc* d, const void* x, const void* w, const float* scale, const float* shift,
+                      int relu, float drop_p, uint64_t seed, void* y, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const Geom g = geom_of(d);
+  DA_REQUIRE(g.Cin % 8 == 0, DA_ERR_UNSUPPORTED, "umma conv: Cin=%d must be a multiple of 8", g.Cin);
+  DA_REQUIRE(g.KH * g.KW <= MAX_TAPS, DA_ERR_UNSUPPORTED, "umma conv: at most %d filter taps", MAX_TAPS);
+  DA_REQUIRE(g.s <= 2, DA_ERR_UNSUPPORTED, "umma conv: stride %d not built (1 or 2)", g.s);
+  DA_REQUIRE(ws && ws_bytes >= umma_workspace_bytes(d), DA_ERR_WORKSPACE, "umma conv forward: workspace too small (%zu < %zu)", ws_bytes, umma_workspace_bytes(d));
+  uint8_t* stage = (uint8_t*)ws + part_bytes(g);
+  const __nv_bfloat16 *xh, *xl, *wh, *wl;
+  int rc = prep_operand(x, d->x_dtype, (long long)g.N * g.H * g.W * g.Cin, d->engine, stage, &xh, &xl, st);
+  if (rc) return rc;
+  rc = prep_operand(w, d->x_dtype, (long long)g.Cout * g.KH * g.KW * g.Cin, d->engine, stage, &wh, &wl, st);
+  if (rc) return rc;
+
+  NtParams P;
+  memset(&P, 0, sizeof(P));
+  set_terms(d->engine, &P.num_terms, P.term_a, P.term_b);
+  P.kchunks = (g.Cin + BK - 1) / BK;
+  P.Cout = g.Cout; P.OHf = g.OH; P.OWf = g.OW; P.os = 1; P.oa = 0; P.ob = 0;
+  P.scale = scale; P.shift = shift; P.relu = relu; P.drop_p = drop_p; P.seed = seed; P.out_scale = 1.f;
+  P.y = y; P.y_dtype = d->y_dtype; P.y_numel = (long long)g.N * g.OH * g.OW * g.Cout;
+  const int Ktot = g.KH * g.KW * g.Cin;
+  long long pixel_tiles;
+  const __nv_bfloat16* xs[2] = {xh, xl};
+  const __nv_bfloat16* wsrc[2] = {wh, wl};
+  for (int t = 0; t < (wl ? 2 : 1); ++t) {
+    const uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)g.Cout};
+    const uint64_t strides[1] = {(uint64_t)Ktot * 2};
+    const uint32_t box[2] = {BK, BN};
+    rc = encode_map(&P.b_map[t], wsrc[t], 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  if (is_flat(g)) {
+    P.flat = 1;
+    P.M_flat = (long long)g.N * g.H * g.W;
+    P.num_taps = 1;
+    P.taps[0] = TapInfo{0, 0, 0, 0};
+    for (int t = 0; t < (xl ? 2 : 1); ++t) {
+      const uint64_t dims[2] = {(uint64_t)g.Cin, (uint64_t)P.M_flat};
+      const uint64_t strides[1] = {(uint64_t)g.Cin * 2};
+      const uint32_t box[2] = {BK, BM};
+      rc = encode_map(&P.a_map[t][0], xs[t], 2, dims, strides, box);
+      if (rc) return rc;
+    }
+    pixel_tiles = (P.M_flat + BM - 1) / BM;
+  } else {
+    P.flat = 0;
+    P.TH = g.OH; P.TW = g.OW;
+    pick_patch(g.OH, g.OW, BM, &P.BH, &P.BW);
+    P.bw_shift = ilog2(P.BW);
+    P.tiles_h = (g.OH + P.BH - 1) / P.BH; P.tiles_w = (g.OW + P.BW - 1) / P.BW;
+    bool present[4] = {false, false, false, false};
+    for (int t = 0; t < (xl ? 2 : 1); ++t) {
+      rc = make_parity_maps(P.a_map[t], present, xs[t], g.N, g.H, g.W, g.Cin, g.s, P.BH, P.BW);
+      if (rc) return rc;
+    }
+    int nt = 0;
+    for (int kh = 0; kh < g.KH; ++kh)
+      for (int kw = 0; kw < g.KW; ++kw) {
+        const int pa = posmod(kh - g.p, g.s), pb = posmod(kw - g.p, g.s);
+        if (!present[pa * g.s + pb]) continue;
+        P.taps[nt++] = TapInfo{pa * g.s + pb, floordiv(kh - g.p, g.s), floordiv(kw - g.p, g.s), (kh * g.KW + kw) * g.Cin};
+      }
+    P.num_taps = nt;
+    pixel_tiles = (long long)g.N * P.tiles_h * P.tiles_w;
+  }
+  return launch_nt(P, pixel_tiles, P.num_terms * P.num_taps * P.kchunks, ws, part_bytes(g), st);
+}
+
+int umma_conv_backward_data(const da_conv_desc* d, const void* dz, const void* w, float out_scale, void* dx, void* ws,
+                            size_t ws_bytes, cudaStream_t st) {
+  const Geom g = geom_of(d);
+  DA_REQUIRE(g.Cin % 8 == 0 && g.Cout % 8 == 0, DA_ERR_UNSUPPORTED, "umma dgrad: channels must be multiples of 8");
+  DA_REQUIRE(g.KH * g.KW <= MAX_TAPS && g.s <= 2, DA_ERR_UNSUPPORTED, "umma dgrad: unsupported filter/stride");
+  DA_REQUIRE(ws && ws_bytes >= umma_workspace_bytes(d), DA_ERR_WORKSPACE, "umma dgrad: workspace too small");
+  uint8_t* stage = (uint8_t*)ws + part_bytes(g);
+  const int taps = g.KH * g.KW;
+  const __nv_bfloat16 *zh, *zl;
+  int rc = prep_operand(dz, d->x_dtype, (long long)g.N * g.OH * g.OW * g.Cout, d->engine, stage, &zh, &zl, st);
+  if (rc) return rc;
+  // weights re-laid out as Wd[ci][tap][co] (K-major over (tap,co))
+  const size_t wn = (size_t)g.Cout * taps * g.Cin;
+  __nv_bfloat16* wdh = (__nv_bfloat16*)stage; stage += align_up(wn * 2, 256);
+  __nv_bfloat16* wdl = nullptr;
+  if (d->engine == DA_ENGINE_UMMA_BF16X3) { wdl = (__nv_bfloat16*)stage; stage += align_up(wn * 2, 256); }
+  {
+    dim3 grid((g.Cin + 31) / 32, (g.Cout + 31) / 32, taps);
+    if (d->x_dtype == DA_F32) weight_oti_to_ito_kernel<float><<<grid, dim3(32, 8), 0, st>>>((const float*)w, wdh, wdl, g.Cout, taps, g.Cin);
+    else weight_oti_to_ito_kernel<__nv_bfloat16><<<grid, dim3(32, 8), 0, st>>>((const __nv_bfloat16*)w, wdh, wdl, g.Cout, taps, g.Cin);
+    DA_LAUNCH_CHECK();
+  }
+  NtParams base;
+  memset(&base, 0, sizeof(base));
+  set_terms(d->engine, &base.num_terms, base.term_a, base.term_b);
+  base.kchunks = (g.Cout + BK - 1) / BK;
+  base.Cout = g.Cin;  // GEMM N dimension = input channels
+  base.OHf = g.H; base.OWf = g.W;
+  base.relu = 0; base.drop_p = 0.f; base.out_scale = out_scale;
+  base.y = dx; base.y_dtype = d->y_dtype; base.y_numel = (long long)g.N * g.H * g.W * g.Cin;
+  const int Ktot = taps * g.Cout;
+  const __nv_bfloat16* wsrc[2] = {wdh, wdl};
+  const __nv_bfloat16* zs[2] = {zh, zl};
+  for (int t = 0; t < (wdl ? 2 : 1); ++t) {
+    const uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)g.Cin};
+    const uint64_t strides[1] = {(uint64_t)Ktot * 2};
+    const uint32_t box[2] = {BK, BN};
+    rc = encode_map(&base.b_map[t], wsrc[t], 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  if (is_flat(g)) {
+    NtParams P = base;
+    P.flat = 1; P.M_flat = (long long)g.N * g.H * g.W; P.num_taps = 1; P.taps[0] = TapInfo{0, 0, 0, 0};
+    P.os = 1;
+    for (int t = 0; t < (zl ? 2 : 1); ++t) {
+      const uint64_t dims[2] = {(uint64_t)g.Cout, (uint64_t)P.M_flat};
+      const uint64_t strides[1] = {(uint64_t)g.Cout * 2};
+      const uint32_t box[2] = {BK, BM};
+      rc = encode_map(&P.a_map[t][0], zs[t], 2, dims, strides, box);
+      if (rc) return rc;
+    }
+    return launch_nt(P, (P.M_flat + BM - 1) / BM, P.num_terms * P.kchunks, ws, part_bytes(g), st);
+  }
+  // one launch per input-pixel parity class (a,b): h = s*i + a, w = s*j + b
+  for (int a = 0; a < g.s; ++a)
+    for (int b = 0; b < g.s; ++b) {
+      NtParams P = base;
+      P.flat = 0;
+      P.TH = (g.H - a + g.s - 1) / g.s; P.TW = (g.W - b + g.s - 1) / g.s;
+      if (P.TH <= 0 || P.TW <= 0) continue;
+      P.os = g.s; P.oa = a; P.ob = b;
+      pick_patch(P.TH, P.TW, BM, &P.BH, &P.BW);
+      P.bw_shift = ilog2(P.BW);
+      P.tiles_h = (P.TH + P.BH - 1) / P.BH; P.tiles_w = (P.TW + P.BW - 1) / P.BW;
+      bool present[4];
+      for (int t = 0; t < (zl ? 2 : 1); ++t) {
+        rc = make_parity_maps(P.a_map[t], present, zs[t], g.N, g.OH, g.OW, g.Cout, 1, P.BH, P.BW);
+        if (rc) return rc;
+      }
+      int nt = 0;
+      for (int kh = 0; kh < g.KH; ++kh)
+        for (int kw = 0; kw < g.KW; ++kw) {
+          const int th = a + g.p - kh, tw = b + g.p - kw;  // oh = i + th/s when s | th
+          if (posmod(th, g.s) != 0 || posmod(tw, g.s) != 0) continue;
+          P.taps[nt++] = TapInfo{0, floordiv(th, g.s), floordiv(tw, g.s), (kh * g.KW + kw) * g.Cout};
+        }
+      P.num_taps = nt;
+      rc = launch_nt(P, (long long)g.N * P.tiles_h * P.tiles_w, P.num_terms * nt * P.kchunks, ws, part_bytes(g), st);
+      if (rc) return rc;
+    }
+  return DA_OK;
+}
+
+int umma_conv_backward_weight(const da_conv_desc* d, const void* x, const void* dz, float* dw, void* ws,
+                              size_t ws_bytes, cudaStream_t st) {
+  const Geom g = geom_of(d);
+  DA_REQUIRE(g.Cin % 8 == 0 && g.Cout % 8 == 0, DA_ERR_UNSUPPORTED, "umma wgrad: channels must be multiples of 8");
+  DA_REQUIRE(g.KH * g.KW <= MAX_TAPS && g.s <= 2, DA_ERR_UNSUPPORTED, "umma wgrad: unsupported filter/stride");
+  DA_REQUIRE(ws && ws_bytes >= umma_workspace_bytes(d), DA_ERR_WORKSPACE, "umma wgrad: workspace too small");
+  uint8_t* stage = (uint8_t*)ws + part_bytes(g);
+  const __nv_bfloat16 *xh, *xl, *zh, *zl;
+  int rc = prep_operand(x, d->x_dtype, (long long)g.N * g.H * g.W * g.Cin, d->engine, stage, &xh, &xl, st);
+  if (rc) return rc;
+  rc = prep_operand(dz, d->x_dtype, (long long)g.N * g.OH * g.OW * g.Cout, d->engine, stage, &zh, &zl, st);
+  if (rc) return rc;
+
+  TnParams P;
+  memset(&P, 0, sizeof(P));
+  set_terms(d->engine, &P.num_terms, P.term_a, P.term_b);
+  P.Cout = g.Cout; P.Cin = g.Cin;
+  P.dw_numel = (long long)g.Cout * g.KH * g.KW * g.Cin;
+  const __nv_bfloat16* xs[2] = {xh, xl};
+  const __nv_bfloat16* zs[2] = {zh, zl};
+  long long patches;
+  if (is_flat(g)) {
+    P.flat = 1; P.M_flat = (long long)g.N * g.H * g.W; P.num_taps = 1; P.taps[0] = TapInfo{0, 0, 0, 0};
+    for (int t = 0; t < (zl ? 2 : 1); ++t) {
+      const uint64_t da_[2] = {(uint64_t)g.Cout, (uint64_t)P.M_flat};
+      const uint64_t sa[1] = {(uint64_t)g.Cout * 2};
+      const uint32_t box[2] = {64, WK};
+      rc = encode_map(&P.a_map[t], zs[t], 2, da_, sa, box);
+      if (rc) return rc;
+      const uint64_t db[2] = {(uint64_t)g.Cin, (uint64_t)P.M_flat};
+      const uint64_t sb[1] = {(uint64_t)g.Cin * 2};
+      rc = encode_map(&P.b_map[t][0], xs[t], 2, db, sb, box);
+      if (rc) return rc;
+    }
+    patches = (P.M_flat + WK - 1) / WK;
+  } else {
+    P.flat = 0;
+    pick_patch(g.OH, g.OW, WK, &P.BH, &P.BW);
+    P.tiles_h = (g.OH + P.BH - 1) / P.BH; P.tiles_w = (g.OW + P.BW - 1) / P.BW; P.NB = g.N;
+    bool present[4] = {false, false, false, false}, pz[4];
+    for (int t = 0; t < (zl ? 2 : 1); ++t) {
+      CUtensorMap tmp[4];
+      rc = make_parity_maps(tmp, pz, zs[t], g.N, g.OH, g.OW, g.Cout, 1, P.BH, P.BW);
+      if (rc) return rc;
+      P.a_map[t] = tmp[0];
+      rc = make_parity_maps(P.b_map[t], present, xs[t], g.N, g.H, g.W, g.Cin, g.s, P.BH, P.BW);
+      if (rc) return rc;
+    }
+    int nt = 0;
+    for (int kh = 0; kh < g.KH; ++kh)
+      for (int kw = 0; kw < g.KW; ++kw) {
+        const int pa = posmod(kh - g.p, g.s), pb = posmod(kw - g.p, g.s);
+        // taps whose parity plane is empty contribute nothing; they keep a slot (map 0 with an
+        // always-out-of-bounds shift) so that dW stays densely indexed by (kh,kw)
+        if (!present[pa * g.s + pb]) { P.taps[nt++] = TapInfo{0, 1 << 20, 1 << 20, 0}; continue; }
+        P.taps[nt++] = TapInfo{pa * g.s + pb, floordiv(kh - g.p, g.s), floordiv(kw - g.p, g.s), 0};
+      }
+    P.num_taps = nt;
+    patches = (long long)g.N * P.tiles_h * P.tiles_w;
+  }
+  const long long tiles = (long long)((g.Cout + BM - 1) / BM) * ((g.Cin + BN - 1) / BN) * P.num_taps;
+  long long k_iters = patches * P.num_terms;
+  int splits = pick_splits(tiles, (int)(k_iters > 1000000 ? 1000000 : k_iters));
+  while (splits > 1 && (size_t)splits * P.dw_numel * sizeof(float) > part_bytes(g)) --splits;
+  DA_REQUIRE(P.num_taps * splits <= 65535, DA_ERR_UNSUPPORTED, "umma wgrad: grid too large");
+  P.dw = splits > 1 ? (float*)ws : dw;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DA_CUDA_OK(cudaFuncSetAttribute(umma_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NT_SMEM));
+    attr_set = true;
+  }
+  dim3 grid((g.Cout + BM - 1) / BM, (g.Cin + BN - 1) / BN, P.num_taps * splits);
+  umma_tn_kernel<<<grid, NT_THREADS, NT_SMEM, st>>>(P, splits);
+  DA_LAUNCH_CHECK();
+  if (splits > 1) {
+    sum_splits_kernel<<<ew_blocks(P.dw_numel), 256, 0, st>>>((const float*)ws, splits, P.dw_numel, dw);
+    DA_LAUNCH_CHECK();
+  }
+  return DA_OK;
+}
+
+}  // namespace da

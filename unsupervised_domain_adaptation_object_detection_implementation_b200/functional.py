@@ -1,0 +1,578 @@
+"""torch.autograd bindings of the C-ABI kernels (libda_b200.so).
+
+PyTorch is plumbing here: it owns device memory, streams and the autograd tape; every
+forward/backward below is ONE or a few calls into the library on the current CUDA stream.
+Tensors that are not on a CUDA device raise: there is no CPU fallback (the CPU restatement
+lives in oracle/ and is test infrastructure only).
+
+Activation layout inside the DA heads is NHWC ([N,H,W,C] contiguous); `to_nhwc` accepts the
+reference's NCHW tensors (zero-copy when they are channels_last).
+"""
+import ctypes
+
+import torch
+from torch.autograd import Function
+
+from . import _lib
+from ._lib import lib, check
+
+_WS = {}
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("libda_b200 kernels need CUDA tensors (sm_100a); there is no CPU fallback")
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _code(dtype):
+    if dtype == torch.float32:
+        return _lib.DA_F32
+    if dtype == torch.bfloat16:
+        return _lib.DA_BF16
+    raise RuntimeError(f"unsupported dtype {dtype} (float32 / bfloat16 only)")
+
+
+def workspace(nbytes, device, tag="default"):
+    """Caller-owned scratch (the library never allocates).  Grown on demand, reused."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+    buf = _WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1024), dtype=torch.uint8, device=device)
+        _WS[key] = buf
+    return buf
+
+
+# --------------------------------------------------------------------------------------
+# engine selection
+# --------------------------------------------------------------------------------------
+_ENGINE = ["umma_bf16"]
+
+
+def set_engine(name):
+    """'umma_bf16' (tcgen05, default), 'umma_bf16x3' (split-precision tcgen05, fp32 in/out)
+    or 'simt_f32' (CUDA-core fp32 parity engine)."""
+    if name not in _lib.ENGINES:
+        raise ValueError(f"unknown engine {name!r}; choose from {sorted(_lib.ENGINES)}")
+    _ENGINE[0] = name
+
+
+def get_engine():
+    return _ENGINE[0]
+
+
+def act_dtype(engine=None):
+    return torch.bfloat16 if (engine or _ENGINE[0]) == "umma_bf16" else torch.float32
+
+
+# --------------------------------------------------------------------------------------
+# layout
+# --------------------------------------------------------------------------------------
+class _NCHWtoNHWC(Function):
+    @staticmethod
+    def forward(ctx, x, dtype):
+        _require_cuda(x)
+        N, C, H, W = x.shape
+        x = x.contiguous()
+        out = torch.empty((N, H, W, C), dtype=dtype, device=x.device)
+        check(lib.da_nchw_to_nhwc(_ptr(x), _code(x.dtype), _ptr(out), _code(dtype), N, C, H, W, _stream()), "nchw_to_nhwc")
+        ctx.src_dtype = x.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        N, H, W, C = g.shape
+        g = g.contiguous()
+        out = torch.empty((N, C, H, W), dtype=ctx.src_dtype, device=g.device)
+        check(lib.da_nhwc_to_nchw(_ptr(g), _code(g.dtype), _ptr(out), _code(out.dtype), N, C, H, W, _stream()), "nhwc_to_nchw")
+        return out, None
+
+
+class _Cast(Function):
+    @staticmethod
+    def forward(ctx, x, dtype):
+        ctx.src_dtype = x.dtype
+        x = x.contiguous()
+        out = torch.empty(x.shape, dtype=dtype, device=x.device)
+        check(lib.da_cast(_ptr(x), _code(x.dtype), _ptr(out), _code(dtype), x.numel(), _stream()), "cast")
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        out = torch.empty(g.shape, dtype=ctx.src_dtype, device=g.device)
+        check(lib.da_cast(_ptr(g), _code(g.dtype), _ptr(out), _code(out.dtype), g.numel(), _stream()), "cast")
+        return out, None
+
+
+def cast(x, dtype):
+    return x if x.dtype == dtype else _Cast.apply(x, dtype)
+
+
+def to_nhwc(x, dtype=None):
+    """NCHW (logical) tensor -> contiguous [N,H,W,C] in `dtype`.  Zero-copy for channels_last."""
+    _require_cuda(x)
+    dtype = dtype or x.dtype
+    if x.dim() != 4:
+        raise RuntimeError("to_nhwc expects a 4-D NCHW tensor")
+    v = x.permute(0, 2, 3, 1)
+    if v.is_contiguous():  # channels_last storage: NHWC is a view
+        return cast(v, dtype)
+    return _NCHWtoNHWC.apply(x, dtype)
+
+
+def nhwc_to_nchw_view(y):
+    """[N,H,W,C] -> logical NCHW view (channels_last strides, no copy)."""
+    return y.permute(0, 3, 1, 2)
+
+
+class _GRL(Function):
+    """mmdet/models/roi_heads/instance_da.py:14-23 (_GradientScalarLayer)."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        ctx.weight = float(weight)
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        _require_cuda(g)
+        g = g.contiguous()
+        out = torch.empty_like(g)
+        check(lib.da_grl_backward(_ptr(g), _ptr(out), _code(g.dtype), g.numel(), ctx.weight, _stream()), "grl_backward")
+        return out, None
+
+
+def gradient_scalar(x, weight):
+    return _GRL.apply(x, weight)
+
+
+# --------------------------------------------------------------------------------------
+# RoIAlign
+# --------------------------------------------------------------------------------------
+class RoIAlignFunction(Function):
+    """mmcv.ops.roi_align.RoIAlignFunction replacement (avg pooling, 7x7)."""
+
+    @staticmethod
+    def forward(ctx, feat, rois, output_size, spatial_scale, sampling_ratio, aligned, out_dtype=None,
+                out_layout="rchw", validate=False):
+        _require_cuda(feat, rois)
+        if feat.dim() != 4 or rois.dim() != 2 or rois.shape[1] != 5:
+            raise RuntimeError("roi_align: feat must be [N,C,H,W] and rois [R,5]")
+        ph, pw = (output_size, output_size) if isinstance(output_size, int) else tuple(output_size)
+        N, C, H, W = feat.shape
+        R = rois.shape[0]
+        out_dtype = out_dtype or feat.dtype
+        f = to_nhwc(feat.detach())
+        rois_c = rois.detach().to(torch.float32).contiguous()
+        layout = _lib.ROI_OUT_RCHW if out_layout == "rchw" else _lib.ROI_OUT_RHWC
+        shape = (R, C, ph, pw) if out_layout == "rchw" else (R, ph, pw, C)
+        out = torch.empty(shape, dtype=out_dtype, device=feat.device)
+        grid = torch.empty((R, 2), dtype=torch.int32, device=feat.device)
+        nbytes = lib.da_roi_align_workspace_bytes(R, H, W)
+        ws = workspace(nbytes, feat.device, "roi")
+        check(lib.da_roi_align_forward(_ptr(f), _code(f.dtype), N, C, H, W, _ptr(rois_c), R, ph, pw,
+                                       float(spatial_scale), int(sampling_ratio), int(bool(aligned)),
+                                       _ptr(out), _code(out_dtype), layout, _ptr(grid), _ptr(ws), ws.numel(),
+                                       _stream()), "roi_align_forward")
+        if validate and R > 0:
+            flag = ws[:4].view(torch.int32)[0].item()
+            if flag != 0:
+                raise RuntimeError("roi_align: a RoI carries a batch index outside [0, N) (reference Q1)")
+        ctx.save_for_backward(rois_c)
+        ctx.cfg = (N, C, H, W, ph, pw, float(spatial_scale), int(sampling_ratio), int(bool(aligned)), layout, feat.dtype)
+        ctx.sampling_grid = grid
+        ctx.mark_non_differentiable(grid)
+        return out, grid
+
+    @staticmethod
+    def backward(ctx, gout, _ggrid):
+        (rois_c,) = ctx.saved_tensors
+        N, C, H, W, ph, pw, scale, sr, aligned, layout, fdtype = ctx.cfg
+        R = rois_c.shape[0]
+        gout = gout.contiguous()
+        gin = torch.empty((N, H, W, C), dtype=torch.float32, device=gout.device)
+        ws = workspace(lib.da_roi_align_workspace_bytes(R, H, W), gout.device, "roi")
+        check(lib.da_roi_align_backward(_ptr(gout), _code(gout.dtype), layout, _ptr(rois_c), R, ph, pw, scale, sr,
+                                        aligned, _ptr(gin), N, C, H, W, _ptr(ws), ws.numel(), _stream()),
+              "roi_align_backward")
+        g = nhwc_to_nchw_view(gin)
+        if fdtype != torch.float32:
+            g = g.to(fdtype)
+        return g, None, None, None, None, None, None, None, None
+
+
+def roi_align(feat, rois, output_size=7, spatial_scale=1.0, sampling_ratio=0, aligned=True, out_dtype=None,
+              out_layout="rchw", validate=False, return_grid=False):
+    out, grid = RoIAlignFunction.apply(feat, rois, output_size, spatial_scale, sampling_ratio, aligned, out_dtype,
+                                       out_layout, validate)
+    return (out, grid) if return_grid else out
+
+
+def map_roi_levels(rois, num_levels, finest_scale=56.0):
+    """single_level_roi_extractor.py:36-55."""
+    _require_cuda(rois)
+    rois_c = rois.detach().to(torch.float32).contiguous()
+    out = torch.empty((rois_c.shape[0],), dtype=torch.int32, device=rois.device)
+    check(lib.da_map_roi_levels(_ptr(rois_c), rois_c.shape[0], int(num_levels), float(finest_scale), _ptr(out), _stream()),
+          "map_roi_levels")
+    return out.long()
+
+
+# --------------------------------------------------------------------------------------
+# losses
+# --------------------------------------------------------------------------------------
+def _as_i32(t, device):
+    if not torch.is_tensor(t):
+        t = torch.as_tensor(t, device=device)
+    return t.to(device=device, dtype=torch.int32).contiguous()
+
+
+class PixelDomainLossFunction(Function):
+    """L1/L2: 0.5*mean(sigmoid(p)^2) (source) / 0.5*mean(sigmoid(1-p)^2) (target)."""
+
+    @staticmethod
+    def forward(ctx, logits, domain, whole_batch):
+        _require_cuda(logits)
+        x = logits.contiguous().float()
+        N = x.shape[0]
+        Lp = x.numel() // N
+        dom = _as_i32(domain, x.device)
+        loss = torch.empty((), dtype=torch.float32, device=x.device)
+        ws = workspace(lib.da_pixel_loss_workspace_bytes(N, Lp), x.device, "loss")
+        check(lib.da_pixel_domain_loss_forward(_ptr(x), N, Lp, _ptr(dom), int(whole_batch), _ptr(loss), _ptr(ws),
+                                               ws.numel(), _stream()), "pixel_domain_loss_forward")
+        ctx.save_for_backward(x, dom)
+        ctx.whole = int(whole_batch)
+        ctx.shape = logits.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        x, dom = ctx.saved_tensors
+        N = x.shape[0]
+        Lp = x.numel() // N
+        g = g.contiguous().float()
+        dx = torch.empty_like(x)
+        check(lib.da_pixel_domain_loss_backward(_ptr(x), N, Lp, _ptr(dom), ctx.whole, _ptr(g), 1.0, _ptr(dx), _stream()),
+              "pixel_domain_loss_backward")
+        return dx.view(ctx.shape), None, None
+
+
+def pixel_domain_loss(logits, domain, whole_batch):
+    return PixelDomainLossFunction.apply(logits, domain, whole_batch)
+
+
+class CE2Function(Function):
+    """nn.CrossEntropyLoss over 2 classes on raw logits or on sigmoid outputs (Q4).
+    Returns (loss, pred) where pred = sigmoid(z) (what the reference heads return)."""
+
+    @staticmethod
+    def forward(ctx, z, labels, on_sigmoid):
+        _require_cuda(z)
+        zc = z.contiguous().float()
+        R = zc.shape[0]
+        lab = _as_i32(labels, zc.device)
+        loss = torch.empty((), dtype=torch.float32, device=zc.device)
+        pred = torch.empty_like(zc)
+        check(lib.da_ce2_forward(_ptr(zc), _ptr(lab), R, int(on_sigmoid), _ptr(pred), _ptr(loss), _stream()), "ce2_forward")
+        ctx.save_for_backward(zc, lab)
+        ctx.on_sigmoid = int(on_sigmoid)
+        return loss, pred
+
+    @staticmethod
+    def backward(ctx, gloss, gpred):
+        zc, lab = ctx.saved_tensors
+        R = zc.shape[0]
+        dz = torch.empty_like(zc)
+        gl = gloss.contiguous().float()
+        gp = gpred.contiguous().float() if (gpred is not None and ctx.on_sigmoid) else None
+        check(lib.da_ce2_backward(_ptr(zc), _ptr(lab), R, ctx.on_sigmoid, _ptr(gl), 1.0, _ptr(gp), _ptr(dz), _stream()),
+              "ce2_backward")
+        return dz, None, None
+
+
+def ce2(z, labels, on_sigmoid):
+    return CE2Function.apply(z, labels, on_sigmoid)
+
+
+class Focal2Function(Function):
+    """mmcv sigmoid_focal_loss on [k,2] with mean reduction (losses/focal_loss.py:60-103)."""
+
+    @staticmethod
+    def forward(ctx, u, labels, gamma, alpha):
+        _require_cuda(u)
+        uc = u.contiguous().float()
+        k = uc.shape[0]
+        lab = _as_i32(labels, uc.device)
+        loss = torch.empty((), dtype=torch.float32, device=uc.device)
+        check(lib.da_focal2_forward(_ptr(uc), _ptr(lab), k, float(gamma), float(alpha), _ptr(loss), _stream()), "focal2_forward")
+        ctx.save_for_backward(uc, lab)
+        ctx.cfg = (float(gamma), float(alpha))
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        uc, lab = ctx.saved_tensors
+        du = torch.empty_like(uc)
+        g = g.contiguous().float()
+        check(lib.da_focal2_backward(_ptr(uc), _ptr(lab), uc.shape[0], ctx.cfg[0], ctx.cfg[1], _ptr(g), 1.0, _ptr(du),
+                                     _stream()), "focal2_backward")
+        return du, None, None, None
+
+
+def sigmoid_focal_loss2(u, labels, gamma=2.0, alpha=0.25):
+    return Focal2Function.apply(u, labels, gamma, alpha)
+
+
+class ConsistencyFunction(Function):
+    """DAFaster_rcnn_Orig.py:161-175 in closed form: sum_r |mean(sigmoid(img)) - sigmoid(pred[r,label_r])|."""
+
+    @staticmethod
+    def forward(ctx, img_logits, ins_pred, labels):
+        _require_cuda(img_logits, ins_pred)
+        a = img_logits.contiguous().float()
+        p = ins_pred.contiguous().float()
+        lab = _as_i32(labels, a.device)
+        loss = torch.empty((), dtype=torch.float32, device=a.device)
+        mean = torch.empty((), dtype=torch.float32, device=a.device)
+        check(lib.da_consistency_forward(_ptr(a), a.numel(), _ptr(p), _ptr(lab), p.shape[0], _ptr(mean), _ptr(loss),
+                                         _stream()), "consistency_forward")
+        ctx.save_for_backward(a, p, lab, mean)
+        ctx.img_shape = img_logits.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        a, p, lab, mean = ctx.saved_tensors
+        g = g.contiguous().float()
+        da_ = torch.empty_like(a)
+        dp = torch.empty_like(p)
+        check(lib.da_consistency_backward(_ptr(a), a.numel(), _ptr(p), _ptr(lab), p.shape[0], _ptr(mean), _ptr(g), 1.0,
+                                          _ptr(da_), _ptr(dp), _stream()), "consistency_backward")
+        return da_.view(ctx.img_shape), dp, None
+
+
+def consistency_loss(img_logits, ins_pred, labels):
+    return ConsistencyFunction.apply(img_logits, ins_pred, labels)
+
+
+# --------------------------------------------------------------------------------------
+# dense layers (conv / linear) with fused epilogue
+# --------------------------------------------------------------------------------------
+def _conv_desc(N, H, W, Cin, Cout, KH, KW, stride, pad, engine, x_dtype, y_dtype):
+    return _lib.ConvDesc(N, H, W, Cin, Cout, KH, KW, stride, pad, _lib.ENGINES[engine], _code(x_dtype), _code(y_dtype))
+
+
+def _w_ohwi(w):
+    """Parameter [O,I,KH,KW] (or [O,I]) -> contiguous [O,KH,KW,I] view (zero-copy when the
+    parameter is stored channels_last, which DenseConv does at construction)."""
+    if w.dim() == 2:
+        return w.contiguous().view(w.shape[0], 1, 1, w.shape[1])
+    v = w.permute(0, 2, 3, 1)
+    return v if v.is_contiguous() else v.contiguous()
+
+
+class DenseLayerFunction(Function):
+    """y = dropout(relu(conv(x, w) * scale + shift)), NHWC in / NHWC out.
+
+    Backward: activation derivative + dgrad (times `grl`, the gradient-reversal weight when x
+    is a head input) + wgrad + the two column sums that give d(scale), d(shift)."""
+
+    @staticmethod
+    def forward(ctx, x, w, scale, shift, stride, pad, relu, drop_p, seed, engine, grl, out_dtype):
+        _require_cuda(x, w)
+        N, H, W_, Cin = x.shape
+        wv = _w_ohwi(w.detach())
+        Cout, KH, KW, _ = wv.shape
+        x = x.contiguous()
+        if wv.dtype != x.dtype:
+            wv = cast(wv, x.dtype)
+        out_dtype = out_dtype or x.dtype
+        OH = (H + 2 * pad - KH) // stride + 1
+        OW = (W_ + 2 * pad - KW) // stride + 1
+        y = torch.empty((N, OH, OW, Cout), dtype=out_dtype, device=x.device)
+        desc = _conv_desc(N, H, W_, Cin, Cout, KH, KW, stride, pad, engine, x.dtype, out_dtype)
+        ws = workspace(lib.da_conv_workspace_bytes(ctypes.byref(desc)), x.device, "conv")
+        sc = None if scale is None else scale.detach().float().contiguous()
+        sh = None if shift is None else shift.detach().float().contiguous()
+        check(lib.da_conv_forward(ctypes.byref(desc), _ptr(x), _ptr(wv), _ptr(sc), _ptr(sh), int(relu), float(drop_p),
+                                  int(seed), _ptr(y), _ptr(ws), ws.numel(), _stream()), "conv_forward")
+        ctx.save_for_backward(x, wv, y, sc, sh)
+        ctx.cfg = (stride, pad, int(relu), float(drop_p), int(seed), engine, grl, w.shape, w.dtype, out_dtype)
+        ctx.has = (scale is not None, shift is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wv, y, sc, sh = ctx.saved_tensors
+        stride, pad, relu, drop_p, seed, engine, grl, wshape, wdtype, out_dtype = ctx.cfg
+        N, H, W_, Cin = x.shape
+        Cout, KH, KW, _ = wv.shape
+        dev = x.device
+        # dz in the operand dtype of this layer
+        desc_a = _conv_desc(N, H, W_, Cin, Cout, KH, KW, stride, pad, engine, out_dtype, out_dtype)
+        ws = workspace(lib.da_conv_workspace_bytes(ctypes.byref(desc_a)), dev, "conv")
+        dy = cast(dy.contiguous(), out_dtype)
+        need_scale, need_shift = ctx.needs_input_grad[2], ctx.needs_input_grad[3]
+        trivial = (not relu) and drop_p == 0.0 and sc is None and not (need_scale or need_shift)
+        dshift = dvdot = None
+        if trivial:
+            dz = dy
+        else:
+            dz = torch.empty_like(dy)
+            if need_scale or need_shift:
+                dshift = torch.empty((Cout,), dtype=torch.float32, device=dev)
+            if need_scale:
+                dvdot = torch.empty((Cout,), dtype=torch.float32, device=dev)
+            check(lib.da_conv_act_backward(ctypes.byref(desc_a), _ptr(dy), _ptr(y), _ptr(sc), relu, drop_p, seed, _ptr(dz),
+                                           _ptr(dshift), _ptr(dvdot), _ptr(ws), ws.numel(), _stream()), "conv_act_backward")
+        dz = cast(dz, x.dtype)
+        dx = dw = dscale = None
+        if ctx.needs_input_grad[0]:
+            desc_d = _conv_desc(N, H, W_, Cin, Cout, KH, KW, stride, pad, engine, x.dtype, x.dtype)
+            dx = torch.empty_like(x)
+            check(lib.da_conv_backward_data(ctypes.byref(desc_d), _ptr(dz), _ptr(wv), float(grl), _ptr(dx), _ptr(ws),
+                                            ws.numel(), _stream()), "conv_backward_data")
+        if ctx.needs_input_grad[1]:
+            desc_w = _conv_desc(N, H, W_, Cin, Cout, KH, KW, stride, pad, engine, x.dtype, x.dtype)
+            dwv = torch.empty((Cout, KH, KW, Cin), dtype=torch.float32, device=dev)
+            check(lib.da_conv_backward_weight(ctypes.byref(desc_w), _ptr(x), _ptr(dz), _ptr(dwv), _ptr(ws), ws.numel(),
+                                              _stream()), "conv_backward_weight")
+            dw = dwv.view(wshape) if len(wshape) == 2 else dwv.permute(0, 3, 1, 2)
+            if wdtype != torch.float32:
+                dw = dw.to(wdtype)
+        if need_scale:
+            # v = acc*scale + shift  =>  d(scale) = sum dv*acc = (dvdot - shift*dshift) / scale
+            t = sh if sh is not None else torch.zeros_like(dshift)
+            safe = torch.where(sc == 0, torch.ones_like(sc), sc)
+            dscale = torch.where(sc == 0, torch.zeros_like(sc), (dvdot - t * dshift) / safe)
+        return dx, dw, dscale, (dshift if need_shift else None), None, None, None, None, None, None, None, None
+
+
+def _umma_ok(x, w):
+    cin = x.shape[-1]
+    cout = w.shape[0]
+    taps = 1 if w.dim() == 2 else w.shape[2] * w.shape[3]
+    return cin % 8 == 0 and cout % 8 == 0 and taps <= 16
+
+
+def dense_layer(x, w, scale=None, shift=None, stride=1, pad=0, relu=False, drop_p=0.0, seed=0, engine=None,
+                grl=1.0, out_dtype=None):
+    engine = engine or get_engine()
+    if engine != "simt_f32" and not (_umma_ok(x, w) and stride <= 2):
+        engine = "simt_f32"  # shapes the tensor-core tiles cannot express (e.g. the 2-logit FC)
+    return DenseLayerFunction.apply(x, w, scale, shift, stride, pad, relu, drop_p, seed, engine, grl, out_dtype)
+
+
+def dropout_keep_mask(seed, shape, drop_p, device):
+    """The exact keep-mask the fused epilogues use (exported for the oracle)."""
+    n = 1
+    for s in shape:
+        n *= int(s)
+    out = torch.empty((n,), dtype=torch.uint8, device=device)
+    check(lib.da_dropout_mask(int(seed), n, float(drop_p), _ptr(out), _stream()), "dropout_mask")
+    return out.view(*shape).bool()
+
+
+class PixelHeadFunction(Function):
+    """Terminal 1-channel conv (+bias)(+ReLU): logits[m] = act(x[m,:].w + b)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, relu):
+        _require_cuda(x, w)
+        x = x.contiguous()
+        K = x.shape[-1]
+        M = x.numel() // K
+        wv = w.detach().reshape(-1).float().contiguous()
+        bv = None if bias is None else bias.detach().reshape(-1).float().contiguous()
+        logits = torch.empty(x.shape[:-1], dtype=torch.float32, device=x.device)
+        check(lib.da_pixel_head_forward(_ptr(x), _code(x.dtype), M, K, _ptr(wv), _ptr(bv), int(relu), _ptr(logits), _stream()),
+              "pixel_head_forward")
+        ctx.save_for_backward(x, wv, logits)
+        ctx.cfg = (int(relu), w.shape, bias is not None)
+        return logits
+
+    @staticmethod
+    def backward(ctx, g):
+        x, wv, logits = ctx.saved_tensors
+        relu, wshape, has_bias = ctx.cfg
+        K = x.shape[-1]
+        M = x.numel() // K
+        g = g.contiguous().float()
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw = torch.empty((K,), dtype=torch.float32, device=x.device)
+        db = torch.empty((1,), dtype=torch.float32, device=x.device) if has_bias else None
+        ws = workspace(lib.da_pixel_head_workspace_bytes(M, K), x.device, "head")
+        check(lib.da_pixel_head_backward(_ptr(x), _code(x.dtype), M, K, _ptr(wv), _ptr(g), _ptr(logits) if relu else None,
+                                         _ptr(dx), _code(x.dtype), _ptr(dw), _ptr(db), _ptr(ws), ws.numel(), _stream()),
+              "pixel_head_backward")
+        return dx, dw.view(wshape), db, None
+
+
+def pixel_head(x, w, bias=None, relu=False):
+    return PixelHeadFunction.apply(x, w, bias, relu)
+
+
+class GlobalAvgPoolFunction(Function):
+    @staticmethod
+    def forward(ctx, x):
+        _require_cuda(x)
+        x = x.contiguous()
+        N, H, W_, C = x.shape
+        y = torch.empty((N, C), dtype=torch.float32, device=x.device)
+        ws = workspace(lib.da_global_avgpool_workspace_bytes(N, C), x.device, "pool")
+        check(lib.da_global_avgpool_forward(_ptr(x), _code(x.dtype), N, H * W_, C, _ptr(y), _ptr(ws), ws.numel(), _stream()),
+              "global_avgpool_forward")
+        ctx.cfg = (x.shape, x.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        shape, dtype = ctx.cfg
+        N, H, W_, C = shape
+        g = g.contiguous().float()
+        dx = torch.empty(shape, dtype=dtype, device=g.device)
+        check(lib.da_global_avgpool_backward(_ptr(g), N, H * W_, C, _ptr(dx), _code(dtype), _stream()), "global_avgpool_backward")
+        return dx
+
+
+def global_avgpool(x):
+    return GlobalAvgPoolFunction.apply(x)
+
+
+class SoftmaxDim0Function(Function):
+    """nn.Softmax(dim=1) of NonLocalBlock on [b,q,k] == softmax over the query axis (Q11)."""
+
+    @staticmethod
+    def forward(ctx, s):
+        _require_cuda(s)
+        s = s.contiguous().float()
+        T = s.shape[0]
+        if s.dim() != 2 or s.shape[1] != T:
+            raise RuntimeError("softmax_dim0 expects a square [T,T] matrix")
+        p = torch.empty_like(s)
+        check(lib.da_softmax_dim0_forward(_ptr(s), T, T, _ptr(p), _stream()), "softmax_dim0_forward")
+        ctx.save_for_backward(p)
+        return p
+
+    @staticmethod
+    def backward(ctx, dp):
+        (p,) = ctx.saved_tensors
+        dp = dp.contiguous().float()
+        ds = torch.empty_like(p)
+        check(lib.da_softmax_dim0_backward(_ptr(p), _ptr(dp), p.shape[0], p.shape[0], _ptr(ds), _stream()),
+              "softmax_dim0_backward")
+        return ds
+
+
+def softmax_dim0(s):
+    return SoftmaxDim0Function.apply(s)

@@ -1,0 +1,80 @@
+"""RoI construction and extraction on the DA path.
+
+  bbox2roi / bbox2roi_train   mmdet/core/bbox/transforms.py:59-78,
+                              mmdet/models/roi_heads/standard_roi_head_da_v5.py:12-33   (R1)
+  SingleRoIExtractor          mmdet/models/roi_heads/roi_extractors/single_level_roi_extractor.py:9-115,
+                              base_roi_extractor.py:37-60                               (R2)
+"""
+import torch
+import torch.nn as nn
+
+from . import functional as F_
+from . import ops
+
+
+def bbox2roi(bbox_list):
+    """list of [n_i,4+] boxes -> [sum n_i, 5] rois (batch_ind, x1, y1, x2, y2); batch_ind is the
+    image index stored as float, exactly as the reference builds it."""
+    rois_list = []
+    for img_id, bboxes in enumerate(bbox_list):
+        if bboxes.size(0) > 0:
+            img_inds = bboxes.new_full((bboxes.size(0), 1), img_id)
+            rois = torch.cat([img_inds, bboxes[:, :4]], dim=-1)
+        else:
+            rois = bboxes.new_zeros((0, 5))
+        rois_list.append(rois)
+    return torch.cat(rois_list, 0)
+
+
+def bbox2roi_train(bbox_list):
+    """Per-image list variant (standard_roi_head_da_v5.py:12-33).  batch_ind = image index; the
+    caller must pool from the FULL [N,C,H,W] map (the reference slices the map to
+    batch size 1 and reads out of bounds for image 1)."""
+    rois = bbox2roi(bbox_list)
+    out, start = [], 0
+    for b in bbox_list:
+        out.append(rois[start:start + b.size(0)])
+        start += b.size(0)
+    return out
+
+
+class SingleRoIExtractor(nn.Module):
+    """Same config surface as the reference: roi_layer=dict(type='RoIAlign', output_size=7,
+    sampling_ratio=0), out_channels, featmap_strides, finest_scale."""
+
+    def __init__(self, roi_layer, out_channels, featmap_strides, finest_scale=56, init_cfg=None):
+        super().__init__()
+        cfg = dict(roi_layer)
+        layer_type = cfg.pop("type")
+        layer_cls = getattr(ops, layer_type)  # looked up by name like mmcv.ops
+        self.roi_layers = nn.ModuleList([layer_cls(spatial_scale=1.0 / s, **cfg) for s in featmap_strides])
+        self.out_channels = out_channels
+        self.featmap_strides = list(featmap_strides)
+        self.finest_scale = finest_scale
+        self.fp16_enabled = False
+
+    @property
+    def num_inputs(self):
+        return len(self.featmap_strides)
+
+    def map_roi_levels(self, rois, num_levels):
+        return F_.map_roi_levels(rois, num_levels, float(self.finest_scale))
+
+    def forward(self, feats, rois, roi_scale_factor=None):
+        if roi_scale_factor is not None:
+            raise NotImplementedError("roi_scale_factor is not used on the DA path")
+        out_size = self.roi_layers[0].output_size
+        num_levels = len(feats)
+        if num_levels == 1:
+            if len(rois) == 0:
+                return feats[0].new_zeros(0, self.out_channels, *out_size)
+            return self.roi_layers[0](feats[0], rois)
+        roi_feats = feats[0].new_zeros(rois.size(0), self.out_channels, *out_size)
+        target_lvls = self.map_roi_levels(rois, num_levels)
+        for i in range(num_levels):
+            inds = (target_lvls == i).nonzero(as_tuple=False).squeeze(1)
+            if inds.numel() > 0:
+                roi_feats[inds] = self.roi_layers[i](feats[i], rois[inds])
+            else:
+                roi_feats = roi_feats + feats[i].sum() * 0.0
+        return roi_feats
