@@ -1,0 +1,416 @@
+#!/usr/bin/env python
+"""bench.py — DA hot-path train step (BASELINE.json metric "DA train-step img-pairs/s").
+
+One "step" = one pass of the DA hot path over one batch of synthetic source+target pairs at the
+reference's DAF Faster R-CNN R50-DC5 topology on 1024x2048 inputs (C5 = [2,2048,64,128] per pair,
+512 RoIs per image):
+
+    ImgAlignmentHead + pixel loss (H1,L1) -> RoIAlign 7x7 (R2) -> shared FCs (F1) ->
+    InstanceAlignmentHead + CE (I1,L4) -> consistency loss (L7) -> backward of all of it
+    (reversed, lambda-scaled gradient into C5; RoIAlign backward; all weight gradients)
+    -> [N>1: one NCCL gradient all-reduce] -> SGD step on every parameter of the path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+`value`  : pairs/s with inputs already resident in HBM (CUDA events, max over ranks).
+`e2e`    : same step through the public module API with HOST (pinned) inputs: H2D of the features
+           and RoIs and D2H of the loss inside the timed region.
+`roofline`: the dominant kernel of the step, timed alone with CUDA events.
+`cpu_baseline` / `--impl reference`: the oracle port (reference algorithm restated for CPU,
+           oracle/) on the box's host cores, on a bounded sample scaled to the full workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOAD = "daf_org_r50dc5_da_hot_path_1024x2048"
+C, H, W, STRIDE = 2048, 64, 128, 16
+ROIS_PER_IMG = 512
+FC_OUT = 1024
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--engine", default="umma_bf16", choices=["umma_bf16", "umma_bf16x3", "simt_f32"])
+    ap.add_argument("--pairs-per-gpu", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=20.0)
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p.get("bf16_tflops_sustained"),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# synthetic inputs
+# ----------------------------------------------------------------------------------------------
+def make_host_inputs(pairs, seed, dtype):
+    """Pinned host tensors: C5 features (NHWC storage, post-ReLU statistics) and per-image proposals."""
+    g = torch.Generator().manual_seed(seed)
+    n = 2 * pairs
+    c5 = torch.relu(torch.randn(n, H, W, C, generator=g)).to(dtype).pin_memory()
+    u = torch.rand(n, ROIS_PER_IMG, 4, generator=g)
+    x1 = u[..., 0] * (W * STRIDE - 33)
+    y1 = u[..., 1] * (H * STRIDE - 33)
+    lo, hi = torch.log(torch.tensor(16.0)), torch.log(torch.tensor(512.0))
+    w = torch.exp(lo + u[..., 2] * (hi - lo))
+    h = torch.exp(lo + u[..., 3] * (hi - lo))
+    boxes = torch.stack([x1, y1, torch.clamp(x1 + w, max=float(W * STRIDE)), torch.clamp(y1 + h, max=float(H * STRIDE))], -1)
+    return c5, boxes.contiguous().pin_memory()
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import unsupervised_domain_adaptation_object_detection_implementation_b200 as uda
+    from unsupervised_domain_adaptation_object_detection_implementation_b200 import dist as ddist, functional as F_, hotpath, _lib
+    import torch.distributed as dist
+
+    rank, local, world = ddist.init_from_env("nccl")
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback for the product path)"
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    uda.set_engine(args.engine)
+    act = F_.act_dtype()
+    pairs = args.pairs_per_gpu
+
+    torch.manual_seed(0)
+    model = hotpath.DAFOrgHotPath(C, STRIDE, FC_OUT).to(dev).train()
+    params = ddist.trainable_parameters(model, model.unused_parameters())
+    opt = torch.optim.SGD(params, lr=1e-3, momentum=0.9, weight_decay=5e-4)   # reference recipe (faster_rcnn_r50_daf_c2f.py:8)
+    reducer = ddist.FlatGradAllReduce(params) if world > 1 else None
+
+    # two input sets (alternated); each is > L2 (C5 alone is 67 MB bf16 per pair, FC1's weight 411 MB)
+    host = [make_host_inputs(pairs, 1000 * rank + s, act) for s in range(2)]
+    resident = [(c5.to(dev), bx.to(dev)) for c5, bx in host]
+    h2d_bytes = host[0][0].numel() * host[0][0].element_size() + host[0][1].numel() * 4
+    loss_host = torch.zeros(1).pin_memory()
+
+    def step_on(c5_dev, boxes_dev):
+        total = None
+        for p in range(pairs):
+            c5 = c5_dev[2 * p:2 * p + 2].permute(0, 3, 1, 2).requires_grad_(True)    # logical NCHW, channels_last storage
+            props = [boxes_dev[2 * p], boxes_dev[2 * p + 1]]
+            losses = model.forward_train(c5, props, [0, 1])
+            loss, _ = hotpath.parse_losses(losses)
+            loss.backward()
+            total = loss.detach() if total is None else total + loss.detach()
+        if reducer is not None:
+            reducer()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return total
+
+    def step_resident(i):
+        return step_on(*resident[i % 2])
+
+    def step_e2e(i):
+        c5_h, bx_h = host[i % 2]
+        c5_d = c5_h.to(dev, non_blocking=True)
+        bx_d = bx_h.to(dev, non_blocking=True)
+        loss = step_on(c5_d, bx_d)
+        loss_host.copy_(loss.reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the user reads the loss every step
+        return loss_host
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, sample_clocks):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        _lib.reset_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = _lib.launch_count()
+        clocks = sampler.stop() if sampler else None
+        return ddist.max_over_ranks(ms, dev), launches, clocks
+
+    ms_res, launches, clocks = timed(step_resident, args.steps, max(args.warmup, 3), True)
+    ms_e2e, _, _ = timed(step_e2e, args.steps, 2, False)
+    total_pairs = pairs * world * args.steps
+    value = total_pairs / (ms_res / 1e3)
+    e2e_value = total_pairs / (ms_e2e / 1e3)
+
+    out = {
+        "metric": "da_train_step_img_pairs_per_s", "value": round(value, 3), "unit": "img-pairs/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_res / args.steps, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.engine == "umma_bf16" else "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "pairs_per_gpu": pairs, "c5": [2 * pairs, C, H, W], "rois_per_img": ROIS_PER_IMG,
+                   "engine": args.engine, "step": "H1+L1, RoIAlign fwd/bwd, shared FCs, I1+L4, L7, backward, SGD",
+                   "l2_policy": "inputs_and_weights_exceed_L2 (C5 67MB/pair bf16, FC1 weight 411MB, RoI features 205MB); two input sets alternated"},
+        "e2e": {"value": round(e2e_value, 3), "unit": "img-pairs/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4,
+                "ms_per_step": round(ms_e2e / args.steps, 4)},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if rank == 0:
+        out["roofline"], out["kernels"] = kernel_rooflines(dev, act, ms_res / args.steps)
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_reference(args.cpu_budget_s)
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def kernel_rooflines(dev, act, step_ms):
+    """Per-kernel timings of the hot kernels, each alone, CUDA events, inputs larger than L2 or L2
+    flushed between launches.  Returns (roofline of the dominant kernel, table)."""
+    from unsupervised_domain_adaptation_object_detection_implementation_b200 import functional as F_
+    pk = peaks()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    g = torch.Generator(device=dev).manual_seed(0)
+    N, R = 4, 2048   # BASELINE config 4: 4 images, 2048 RoIs
+    feat = torch.relu(torch.randn(N, H, W, C, device=dev, generator=g)).to(act).permute(0, 3, 1, 2)
+    cpu_g = torch.Generator().manual_seed(1)
+    u = torch.rand(R, 4, generator=cpu_g)
+    x1, y1 = u[:, 0] * (W * STRIDE - 33), u[:, 1] * (H * STRIDE - 33)
+    wh = torch.exp(torch.log(torch.tensor(16.0)) + u[:, 2:] * (torch.log(torch.tensor(512.0)) - torch.log(torch.tensor(16.0))))
+    rois = torch.stack([(torch.arange(R) // (R // N)).float(), x1, y1, torch.clamp(x1 + wh[:, 0], max=W * STRIDE),
+                        torch.clamp(y1 + wh[:, 1], max=H * STRIDE)], 1).to(dev)
+    es = feat.element_size()
+
+    def time_it(fn, iters=10):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        return sum(ts[:max(1, len(ts) // 2)]) / max(1, len(ts) // 2)
+
+    table = {}
+    out = F_.roi_align(feat, rois, 7, 1.0 / STRIDE)
+    fwd_bytes = R * C * 49 * es + N * C * H * W * es + R * 20
+    t = time_it(lambda: F_.roi_align(feat, rois, 7, 1.0 / STRIDE))
+    table["roi_align_fwd"] = {"ms": round(t, 4), "bytes": fwd_bytes, "gbs": round(fwd_bytes / t / 1e6, 1),
+                              "frac": round(fwd_bytes / t / 1e6 / pk["hbm_gbs"], 4), "note": "incl. the RoI prep kernel"}
+    gout = torch.randn(out.shape, device=dev, generator=g).to(out.dtype)
+    fr = feat.detach().requires_grad_(True)
+    o2 = F_.roi_align(fr, rois, 7, 1.0 / STRIDE)
+    bwd_bytes = R * C * 49 * es + N * C * H * W * 4 + R * 20
+    t = time_it(lambda: torch.autograd.grad(o2, fr, gout, retain_graph=True))
+    table["roi_align_bwd"] = {"ms": round(t, 4), "bytes": bwd_bytes, "gbs": round(bwd_bytes / t / 1e6, 1),
+                              "frac": round(bwd_bytes / t / 1e6 / pk["hbm_gbs"], 4)}
+    # H1 conv1: 1x1 2048->512 on one pair's C5 (M=16384)
+    x = torch.relu(torch.randn(2, H, W, C, device=dev, generator=g)).to(act)
+    w1 = (torch.randn(512, C, 1, 1, device=dev, generator=g) * C ** -0.5)
+    b1 = torch.zeros(512, device=dev)
+    fl = 2.0 * 2 * H * W * C * 512
+    t = time_it(lambda: F_.dense_layer(x, w1, None, b1, relu=True))
+    table["h1_conv1_fwd"] = {"ms": round(t, 4), "flops": fl, "tflops": round(fl / t / 1e9, 1), "frac": round(fl / t / 1e9 / pk["bf16_tflops"], 4),
+                             "note": "incl. the fp32->bf16 weight cast"}
+    # F1 FC1: [1024,100352] x [100352 -> 1024]
+    a = torch.randn(1024, 1, 1, C * 49, device=dev, generator=g).to(act)
+    wf = torch.randn(FC_OUT, C * 49, device=dev, generator=g) * (C * 49) ** -0.5
+    wf_act = wf.to(act)
+    fl = 2.0 * 1024 * C * 49 * FC_OUT
+    t = time_it(lambda: F_.dense_layer(a, wf_act, None, None, relu=True))
+    table["fc1_fwd"] = {"ms": round(t, 4), "flops": fl, "tflops": round(fl / t / 1e9, 1), "frac": round(fl / t / 1e9 / pk["bf16_tflops"], 4)}
+    dom = max(table, key=lambda k: table[k]["ms"])
+    d = table[dom]
+    if "bytes" in d:
+        roof = {"kernel": dom, "bound": "hbm", "achieved": d["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": d["frac"],
+                "traffic": None, "peak_source": pk["source"], "share_of_step": round(d["ms"] / step_ms, 4)}
+    else:
+        roof = {"kernel": dom, "bound": "tensor", "achieved": d["tflops"], "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": d["frac"], "traffic": None, "peak_source": pk["source"], "share_of_step": round(d["ms"] / step_ms, 4)}
+    return roof, table
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU reference arm (oracle port; the one place bench.py may execute oracle/)
+# ----------------------------------------------------------------------------------------------
+def cpu_reference_step(rows, rois_per_img, threads, state):
+    """One bounded sample of the workload on the CPU, fp32, reference algorithm (oracle/da_oracle.py,
+    oracle/roi_align_ref.c).  rows: feature-map rows of C5 used for H1 (of H); rois_per_img of 512.
+    Returns seconds per component."""
+    from oracle import da_oracle, roi_align as oracle_roi
+    import torch.nn.functional as F
+    t = {}
+    c5 = state["c5"]
+    t0 = time.perf_counter()
+    x = c5[:, :, :rows].clone().requires_grad_(True)
+    img_feat = da_oracle.img_alignment_head(x, state["sd_img"])
+    loss = 0.1 * da_oracle.daf_image_loss(img_feat, torch.tensor([0, 1]))
+    loss.backward()
+    t["img_head"] = time.perf_counter() - t0
+    R = 2 * rois_per_img
+    rois = state["rois"][:R].clone()
+    rois[:, 0] = (torch.arange(R) >= rois_per_img).float()
+    t0 = time.perf_counter()
+    pooled, _, _ = oracle_roi.roi_align_forward(c5.numpy(), rois.numpy(), 7, 1.0 / STRIDE, threads=threads)
+    t["roi_fwd"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    feats_in = torch.from_numpy(pooled).flatten(1).requires_grad_(True)
+    f = F.relu(F.linear(feats_in, state["fc1_w"], state["fc1_b"]))
+    f = F.relu(F.linear(f, state["fc2_w"], state["fc2_b"]))
+    labels = (torch.arange(R) >= rois_per_img).long()
+    pred = torch.sigmoid(da_oracle.instance_alignment_logits(f, state["sd_ins"]))
+    l = 0.1 * da_oracle.ce2(pred, labels) + 0.1 * da_oracle.consistency_loss(img_feat.detach(), pred, labels)
+    l.backward()
+    t["fc_instance"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    oracle_roi.roi_align_backward(feats_in.grad.view(R, C, 7, 7).numpy(), rois.numpy(), (2, C, H, W), 7, 1.0 / STRIDE)
+    t["roi_bwd"] = time.perf_counter() - t0
+    return t
+
+
+def cpu_reference_state():
+    from unsupervised_domain_adaptation_object_detection_implementation_b200 import da_heads
+    g = torch.Generator().manual_seed(0)
+    st = {"c5": torch.relu(torch.randn(2, C, H, W, generator=g))}
+    u = torch.rand(2 * ROIS_PER_IMG, 4, generator=g)
+    x1, y1 = u[:, 0] * (W * STRIDE - 33), u[:, 1] * (H * STRIDE - 33)
+    wh = torch.exp(torch.log(torch.tensor(16.0)) + u[:, 2:] * (torch.log(torch.tensor(512.0)) - torch.log(torch.tensor(16.0))))
+    st["rois"] = torch.stack([torch.zeros(len(u)), x1, y1, torch.clamp(x1 + wh[:, 0], max=W * STRIDE), torch.clamp(y1 + wh[:, 1], max=H * STRIDE)], 1)
+    st["sd_img"] = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in da_heads.ImgAlignmentHead(C).state_dict().items()}
+    st["sd_ins"] = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k and "num_batches" not in k)
+                    for k, v in da_heads.InstanceAlignmentHead().state_dict().items()}
+    st["fc1_w"] = (torch.randn(FC_OUT, C * 49, generator=g) * (C * 49) ** -0.5).requires_grad_(True)
+    st["fc1_b"] = torch.zeros(FC_OUT, requires_grad=True)
+    st["fc2_w"] = (torch.randn(FC_OUT, FC_OUT, generator=g) * FC_OUT ** -0.5).requires_grad_(True)
+    st["fc2_b"] = torch.zeros(FC_OUT, requires_grad=True)
+    return st
+
+
+def scaled_pairs_per_s(t, rows, rois_per_img):
+    """Scale the bounded sample to one full pair: H1 is linear in rows, RoIAlign / FC / instance head in RoIs
+    (the k x k attention of the instance head is quadratic; its linear scaling UNDER-estimates the CPU time)."""
+    full = t["img_head"] * (H / rows) + (t["roi_fwd"] + t["roi_bwd"] + t["fc_instance"]) * (ROIS_PER_IMG / rois_per_img)
+    return 1.0 / full, full
+
+
+def pick_sample(budget_s, threads, state):
+    t = cpu_reference_step(8, 2, threads, state)      # probe (also warms the allocator / thread pools)
+    t = cpu_reference_step(8, 2, threads, state)
+    per_row = t["img_head"] / 8
+    per_roi = (t["roi_fwd"] + t["roi_bwd"] + t["fc_instance"]) / 2
+    rows = int(max(8, min(H, (0.4 * budget_s) / max(per_row, 1e-6))))
+    rois = int(max(2, min(ROIS_PER_IMG, (0.6 * budget_s) / max(per_roi, 1e-6))))
+    return rows, rois
+
+
+def cpu_reference(budget_s):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    state = cpu_reference_state()
+    rows, rois = pick_sample(budget_s, cores, state)
+    t = cpu_reference_step(rows, rois, cores, state)
+    v, full = scaled_pairs_per_s(t, rows, rois)
+    return {"value": round(v, 5), "unit": "img-pairs/s", "cores": cores, "kind": "port",
+            "sample": f"H1+L1 on {rows}/{H} rows of C5; RoIAlign fwd/bwd + shared FCs + instance head on {rois}/{ROIS_PER_IMG} RoIs per image; "
+                      f"scaled linearly to one full pair ({full:.1f} s); fp32; oracle port (torch CPU + oracle/roi_align_ref.c)",
+            "seconds": {k: round(x, 3) for k, x in t.items()}}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    state = cpu_reference_state()
+    total = max(args.steps + args.warmup, 1)
+    rows, rois = pick_sample(min(150.0 / total, 20.0), cores, state)
+    for _ in range(args.warmup):
+        cpu_reference_step(rows, rois, cores, state)
+    vals, t0 = [], time.perf_counter()
+    for _ in range(args.steps):
+        vals.append(scaled_pairs_per_s(cpu_reference_step(rows, rois, cores, state), rows, rois)[0])
+    wall = time.perf_counter() - t0
+    v = len(vals) / sum(1.0 / x for x in vals)
+    sample = (f"each step: H1+L1 on {rows}/{H} rows of C5; RoIAlign fwd/bwd + shared FCs + instance head on {rois}/{ROIS_PER_IMG} "
+              f"RoIs per image; scaled linearly to a full pair; fp32 oracle port on {cores} host threads")
+    print(json.dumps({
+        "impl": "reference", "metric": "da_train_step_img_pairs_per_s", "value": round(v, 5), "unit": "img-pairs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 / v, 2),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "pairs_per_gpu": 1, "c5": [2, C, H, W], "rois_per_img": ROIS_PER_IMG},
+        "cpu_baseline": {"value": round(v, 5), "unit": "img-pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(v, 5), "unit": "img-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": round(wall, 1)}))
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -1,0 +1,246 @@
+"""ORACLE — test infrastructure only; never imported by the product path.
+
+CPU restatement (plain PyTorch, fp32 or fp64, any device torch supports) of the reference's DA
+hot path.  Every function cites the reference lines it follows (paths under /root/reference).
+The head functions take the head's state_dict (identical keys to the reference classes), so the
+same seeded parameters drive the reference classes, this oracle and the CUDA modules.
+
+Parity status: PINNED — tests/test_oracle_cpu.py checks every function here against golden
+vectors produced by the reference's own classes (oracle/make_golden.py imports them in place
+from /root/reference under an mmcv stub) and checks each closed-form loss against a literal
+transcription of the reference's Python loops.
+"""
+import torch
+import torch.nn.functional as F
+
+
+# --------------------------------------------------------------------------------------
+# GRL — mmdet/models/roi_heads/instance_da.py:14-23
+# --------------------------------------------------------------------------------------
+class _GRL(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w):
+        ctx.w = w
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.w * g.clone(), None
+
+
+def grl(x, weight=-1.0):
+    return _GRL.apply(x, weight)
+
+
+def _bn_eval(x, sd, p, eps=1e-5):
+    """nn.BatchNorm2d in eval mode (Q9: norm_eval=True keeps DA-head BN frozen while training)."""
+    shape = (1, -1) + (1,) * (x.dim() - 2)
+    return (x - sd[p + ".running_mean"].view(shape)) * torch.rsqrt(sd[p + ".running_var"].view(shape) + eps) \
+        * sd[p + ".weight"].view(shape) + sd[p + ".bias"].view(shape)
+
+
+def _drop(x, mask):
+    """F.dropout(p=0.5, training=True) with an injected keep-mask (RNG streams cannot be matched, Q9)."""
+    return x if mask is None else x * mask.to(x.dtype) * 2.0
+
+
+# --------------------------------------------------------------------------------------
+# H1 ImgAlignmentHead — mmdet/models/backbones/resnet_da_daf_org.py:120-133
+# --------------------------------------------------------------------------------------
+def img_alignment_head(x, sd):
+    x = grl(x)
+    x = F.relu(F.conv2d(x, sd["conv1.weight"], sd["conv1.bias"]))
+    return F.relu(F.conv2d(x, sd["conv2.weight"], sd["conv2.bias"]))
+
+
+# --------------------------------------------------------------------------------------
+# H2 LocalAlignmentHead — mmdet/models/backbones/resnet_da_cbam.py:77-115
+# --------------------------------------------------------------------------------------
+def local_alignment_head(x, sd, masks=(None, None)):
+    x = grl(x)
+    x = _drop(F.relu(_bn_eval(F.conv2d(x, sd["conv1.weight"]), sd, "bn1")), masks[0])
+    x = _drop(F.relu(_bn_eval(F.conv2d(x, sd["conv2.weight"]), sd, "bn2")), masks[1])
+    return F.conv2d(x, sd["conv3.weight"])
+
+
+# --------------------------------------------------------------------------------------
+# H3 GlobalAlignmentHead — resnet_da_cbam.py:117-195 (dead Res-CBAM branch of :176-179 skipped,
+# Q10: conv4 consumes `res`, so the branch cannot influence the output) and
+# resnet_da_deep.py:206-303 (same head without the branch)
+# --------------------------------------------------------------------------------------
+def global_alignment_head(x, sd, masks=(None, None, None, None)):
+    x = grl(x)
+    res = _drop(F.relu(_bn_eval(F.conv2d(x, sd["conv1.weight"], None, 2, 1), sd, "bn1")), masks[0])
+    x = _drop(F.relu(_bn_eval(F.conv2d(res, sd["conv4.weight"], None, 2, 1), sd, "bn4")), masks[1])
+    x = _drop(F.relu(_bn_eval(F.conv2d(x, sd["conv5.weight"], None, 2, 1), sd, "bn5")), masks[2])
+    x = F.avg_pool2d(x, (x.size(2), x.size(3))).view(x.size(0), -1)
+    x = _drop(F.relu(F.linear(x, sd["fc1.weight"], sd["fc1.bias"])), masks[3])
+    return F.linear(x, sd["fc2.weight"], sd["fc2.bias"])
+
+
+# --------------------------------------------------------------------------------------
+# H4 SRM — mmdet/models/backbones/resnet_da.py:83-104 (padding=1 on the 1x1, padding=3 on the 3x3, Q12)
+# --------------------------------------------------------------------------------------
+def srm_logits(x, sd, masks=(None, None)):
+    x = grl(x)
+    x = _drop(F.relu(_bn_eval(F.conv2d(x, sd["conv1.weight"], sd["conv1.bias"], 1, 1), sd, "bn1")), masks[0])
+    x = _drop(F.relu(_bn_eval(F.conv2d(x, sd["conv2.weight"], sd["conv2.bias"], 1, 3), sd, "bn2")), masks[1])
+    x = F.avg_pool2d(x, (x.size(2), x.size(3))).view(x.size(0), -1)
+    return F.linear(x, sd["fc.weight"], sd["fc.bias"])
+
+
+def srm(x, sd, masks=(None, None)):
+    return torch.sigmoid(srm_logits(x, sd, masks))
+
+
+# --------------------------------------------------------------------------------------
+# NonLocalBlock — mmdet/models/roi_heads/instance_da.py:150-192 (softmax over dim=1 of [b,q,k], Q11)
+# --------------------------------------------------------------------------------------
+def non_local_block(x, sd, p=""):
+    b, c, h, w = x.shape
+    ic = c // 2
+    x_phi = F.conv2d(x, sd[p + "conv_phi.weight"]).view(b, ic, -1)
+    x_theta = F.conv2d(x, sd[p + "conv_theta.weight"]).view(b, ic, -1).permute(0, 2, 1)
+    x_g = F.conv2d(x, sd[p + "conv_g.weight"]).view(b, ic, -1).permute(0, 2, 1)
+    att = torch.softmax(torch.matmul(x_theta, x_phi), dim=1)
+    y = torch.matmul(att, x_g).permute(0, 2, 1).contiguous().view(b, ic, h, w)
+    return F.conv2d(y, sd[p + "conv_mask.weight"]) + x
+
+
+# H5 NonLocalAlignmentHead — mmdet/models/backbones/resnet_da_deep.py:122-164
+def non_local_alignment_head(x, sd, mask=None):
+    x = grl(x)
+    x = _drop(F.relu(_bn_eval(F.conv2d(x, sd["conv1.weight"]), sd, "bn1")), mask)
+    return non_local_block(x, sd, "nlb1.")
+
+
+# --------------------------------------------------------------------------------------
+# I1 InstanceAlignmentHead — instance_da.py:42-86 ; I2 InstanceAlignmentHead_DAF — :103-131
+# --------------------------------------------------------------------------------------
+def instance_alignment_logits(x, sd, masks=(None, None)):
+    x = grl(x)
+    x = x.unsqueeze(0).permute(0, 2, 1).contiguous().unsqueeze(2)  # [1,C,1,k]
+    x = non_local_block(x, sd, "nlb.")
+    x = x.permute(3, 1, 0, 2).contiguous().squeeze(-1).squeeze(-1)  # [k,C]
+    x = _drop(F.relu(F.linear(x, sd["fc1.weight"], sd["fc1.bias"])), masks[0])
+    x = _drop(F.relu(F.linear(x, sd["fc2.weight"], sd["fc2.bias"])), masks[1])
+    return F.linear(x, sd["fc3.weight"], sd["fc3.bias"])
+
+
+def instance_alignment_daf_logits(x, sd, masks=(None, None)):
+    x = grl(x)
+    x = _drop(F.relu(F.linear(x, sd["fc1.weight"], sd["fc1.bias"])), masks[0])
+    x = _drop(F.relu(F.linear(x, sd["fc2.weight"], sd["fc2.bias"])), masks[1])
+    return F.linear(x, sd["fc3.weight"], sd["fc3.bias"])
+
+
+# --------------------------------------------------------------------------------------
+# losses — closed forms and literal loop transcriptions
+# --------------------------------------------------------------------------------------
+def daf_image_loss_loop(patch_feat, gt_domain):
+    """Literal: resnet_da_daf_org.py:816-822 (note: the loop variable only selects the branch)."""
+    losses = []
+    for i in range(len(patch_feat)):
+        if gt_domain[i] == 0:
+            losses.append(0.5 * torch.mean(torch.sigmoid(patch_feat) ** 2))
+        elif gt_domain[i] == 1:
+            losses.append(0.5 * torch.mean(torch.sigmoid(1 - patch_feat) ** 2))
+    return sum(losses)
+
+
+def daf_image_loss(patch_feat, gt_domain):
+    """L1 closed form."""
+    n_src = int((gt_domain == 0).sum())
+    n_tgt = int((gt_domain == 1).sum())
+    return 0.5 * (n_src * torch.mean(torch.sigmoid(patch_feat) ** 2) + n_tgt * torch.mean(torch.sigmoid(1 - patch_feat) ** 2))
+
+
+def patch_loss_loop(local_feat, gt_domain):
+    """Literal: resnet_da_cbam.py:971-979."""
+    losses = []
+    for i, patch_feat in enumerate(local_feat):
+        if gt_domain[i] == 0:
+            losses.append(0.5 * torch.mean(torch.sigmoid(patch_feat) ** 2))
+        elif gt_domain[i] == 1:
+            losses.append(0.5 * torch.mean(torch.sigmoid(1 - patch_feat) ** 2))
+    return sum(losses)
+
+
+def patch_loss(local_feat, gt_domain):
+    """L2 closed form."""
+    n = local_feat.shape[0]
+    flat = local_feat.reshape(n, -1)
+    d = gt_domain.view(n, 1).to(flat.dtype)
+    src = 0.5 * torch.mean(torch.sigmoid(flat) ** 2, dim=1)
+    tgt = 0.5 * torch.mean(torch.sigmoid(1 - flat) ** 2, dim=1)
+    return (torch.where(d.view(-1) == 0, src, torch.zeros_like(src)) + torch.where(d.view(-1) == 1, tgt, torch.zeros_like(tgt))).sum()
+
+
+def ce2(u, labels):
+    """L3 / L4: nn.CrossEntropyLoss()(u, labels) (resnet_da_cbam.py:966-968; on sigmoid outputs at
+    resnet_da.py:846-848 and DAFaster_rcnn_Orig.py:185-186 -> pass u = sigmoid(z))."""
+    return F.cross_entropy(u, labels.long())
+
+
+def focal2(u, labels, gamma=2.0, alpha=0.25):
+    """L6: py_sigmoid_focal_loss, mmdet/models/losses/focal_loss.py:12-57 with the one-hot target of
+    FocalLoss.forward (:166-168); mean over k*2."""
+    p = u.sigmoid()
+    t = F.one_hot(labels.long(), num_classes=3)[:, :2].type_as(u)
+    pt = (1 - p) * t + p * (1 - t)
+    fw = (alpha * t + (1 - alpha) * (1 - t)) * pt.pow(gamma)
+    return (F.binary_cross_entropy_with_logits(u, t, reduction="none") * fw).mean()
+
+
+def consistency_loss_loop(imgs_feat, ins_preds, ins_labels):
+    """Literal: DAFaster_rcnn_Orig.py:161-175 (device-parametrised)."""
+    loss = torch.zeros((), dtype=imgs_feat.dtype, device=imgs_feat.device)
+    for i, img_feat in enumerate(imgs_feat):
+        img_logit = torch.sigmoid(imgs_feat)
+        I = torch.nonzero(img_logit).size()[0]
+        img_logit = img_logit.sum() / I
+        for j, ins_label in enumerate(ins_labels):
+            if ins_label == i:
+                ins_logit = torch.sigmoid(ins_preds[j])
+                loss = loss + torch.dist(img_logit, ins_logit[i], p=2)
+    return loss
+
+
+def consistency_loss(imgs_feat, ins_preds, ins_labels):
+    """L7 closed form: sum_r |mean(sigmoid(imgs_feat)) - sigmoid(ins_preds[r, label_r])|."""
+    m = torch.sigmoid(imgs_feat).mean()
+    lab = ins_labels.long()
+    valid = (lab >= 0) & (lab < imgs_feat.shape[0]) & (lab < 2)
+    s = torch.sigmoid(ins_preds.gather(1, lab.clamp(0, 1).view(-1, 1)).view(-1))
+    return (torch.abs(m - s) * valid.to(s.dtype)).sum()
+
+
+# --------------------------------------------------------------------------------------
+# RoI construction — mmdet/core/bbox/transforms.py:59-78
+# --------------------------------------------------------------------------------------
+def bbox2roi(bbox_list):
+    rois_list = []
+    for img_id, bboxes in enumerate(bbox_list):
+        if bboxes.size(0) > 0:
+            img_inds = bboxes.new_full((bboxes.size(0), 1), img_id)
+            rois = torch.cat([img_inds, bboxes[:, :4]], dim=-1)
+        else:
+            rois = bboxes.new_zeros((0, 5))
+        rois_list.append(rois)
+    return torch.cat(rois_list, 0)
+
+
+# --------------------------------------------------------------------------------------
+# Composite: the DAF-Org DA losses on given features (DAFaster_rcnn_Orig.py:143-157 weights)
+# --------------------------------------------------------------------------------------
+def daf_org_da_losses(c5, bbox_feats, gt_domain, sd_img, sd_ins, lam=(0.1, 0.1, 0.1)):
+    """c5 [N,C,H,W]; bbox_feats = [feat_src [R0,1024], feat_tgt [R1,1024]] ->
+    dict(globle_da_loss, local_da_loss, consistency_loss) exactly as forward_train weights them."""
+    img_feat = img_alignment_head(c5, sd_img)
+    g_loss = daf_image_loss(img_feat, gt_domain)
+    labels = torch.cat([torch.zeros(len(bbox_feats[0])), torch.ones(len(bbox_feats[1]))]).long().to(c5.device)
+    pred = torch.sigmoid(instance_alignment_logits(torch.cat(bbox_feats, 0), sd_ins))
+    l_loss = ce2(pred, labels)
+    c_loss = consistency_loss(img_feat, pred, labels)
+    return dict(globle_da_loss=lam[0] * g_loss, local_da_loss=lam[1] * l_loss, consistency_loss=lam[2] * c_loss), \
+        img_feat, pred

@@ -1,0 +1,150 @@
+"""ORACLE — test infrastructure only.  Generates tests/golden/*.pt in the BUILD CONTAINER.
+
+Runs the reference's own classes (loaded in place from /root/reference by oracle/ref_loader.py) and
+torchvision's C++ RoIAlign (the stand-in for mmcv-full 1.3.17's kernel) on seeded
+inputs, and stores the small input/output vectors.  Parameters are NOT stored: they are a pure
+function of (state_dict key, seed) — oracle/seeded.py — on both sides.
+
+    python -m oracle.make_golden            # from the repo root
+"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_loader, seeded  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _summ(t):
+    """Large tensors are stored as (norm, first 32, last 32, strided sample)."""
+    t = t.detach().float().reshape(-1)
+    if t.numel() <= 4096:
+        return {"full": t.clone()}
+    idx = torch.linspace(0, t.numel() - 1, 512).long()
+    return {"norm": t.norm().item(), "head": t[:32].clone(), "tail": t[-32:].clone(), "idx": idx, "sample": t[idx].clone()}
+
+
+def head_case(name, module, x, seed=0):
+    module = module.float().eval()  # eval: dropout off, BN frozen (== training with norm_eval, Q9)
+    seeded.fill_state_(module, seed, prefix=name + ".")
+    x = x.clone().requires_grad_(True)
+    out = module(x)
+    outs = out if isinstance(out, tuple) else (out,)
+    cot = [seeded.seeded_tensor(f"{name}.cot{i}", o.shape, seed) for i, o in enumerate(outs)]
+    loss = sum((o * c).sum() for o, c in zip(outs, cot))
+    loss.backward()
+    rec = {"x": x.detach().clone(), "out": [o.detach().clone() for o in outs], "cot": cot,
+           "dx": x.grad.detach().clone(), "seed": seed,
+           "dparams": {k: _summ(p.grad) for k, p in module.named_parameters() if p.grad is not None},
+           "no_grad_params": [k for k, p in module.named_parameters() if p.grad is None]}
+    torch.save(rec, os.path.join(OUT, f"head_{name}.pt"))
+    print(f"head_{name}: out {[tuple(o.shape) for o in outs]} |dx|={x.grad.norm():.4f}")
+
+
+def roi_align_case():
+    import torchvision  # noqa: F401
+    N, C, H, W, stride = 2, 8, 20, 30, 16
+    feat = seeded.seeded_tensor("roi.feat", (N, C, H, W), 0)
+    rois = torch.cat([seeded.synthetic_rois(24, N, H * stride, W * stride, 0, 16.0, 300.0),
+                      seeded.adversarial_rois(N, H * stride, W * stride)], 0)
+    f = feat.clone().requires_grad_(True)
+    out = torch.ops.torchvision.roi_align(f, rois, 1.0 / stride, 7, 7, 0, True)
+    cot = seeded.seeded_tensor("roi.cot", out.shape, 0)
+    (out * cot).sum().backward()
+    # the sampling grid in fp32, same operation order as the kernels (no FMA on the CPU build)
+    s = torch.tensor(1.0 / stride, dtype=torch.float32)
+    x1, y1, x2, y2 = [rois[:, i] * s - 0.5 for i in (1, 2, 3, 4)]
+    gh = torch.ceil((y2 - y1) / 7.0).int()
+    gw = torch.ceil((x2 - x1) / 7.0).int()
+    rec = {"feat": feat, "rois": rois, "stride": stride, "out": out.detach().clone(), "cot": cot,
+           "dfeat": f.grad.detach().clone(), "grid": torch.stack([gh, gw], 1), "batch_idx": rois[:, 0].int()}
+    # non-aligned, fixed sampling ratio variant (mmcv's legacy mode is reachable through the same module)
+    out2 = torch.ops.torchvision.roi_align(feat, rois[:24], 1.0 / stride, 7, 7, 2, False)
+    rec["out_legacy_sr2"] = out2.clone()
+    torch.save(rec, os.path.join(OUT, "roi_align_torchvision.pt"))
+    print("roi_align:", tuple(out.shape), "grid max", int(gh.max()), int(gw.max()))
+
+
+def backbone_loss_cases(ns):
+    """Run the reference backbones' forward_train on a tiny image: pins the loss tails L1/L2/L3 to
+    the reference's own code (resnet_da_daf_org.py:796-824, resnet_da_cbam.py:934-993, resnet_da.py:821-850)."""
+    torch.manual_seed(0)
+    common = dict(depth=50, num_stages=4, strides=(1, 2, 2, 1), dilations=(1, 1, 1, 2), out_indices=(3,),
+                  frozen_stages=1, norm_eval=True, style="pytorch")
+    img = torch.randn(2, 3, 64, 96)
+    gt = torch.tensor([0, 1])
+    rec = {}
+    # DAF-Org: L1 on ImgAlignmentHead output
+    m = ns.daf_org.ResNet_DAF(**common)
+    torch.nn.init.normal_(m.da_head_top.conv1.weight, 0, 0.05)
+    torch.nn.init.normal_(m.da_head_top.conv2.weight, 0, 0.2)
+    m.train()
+    outs, loss, patch = m.forward_train(img, gt)
+    rec["daf_org"] = {"patch_feat": patch.detach().clone(), "loss": loss.detach().clone(), "gt": gt}
+    outs, loss_tt, _ = m.forward_train(img, torch.tensor([1, 1]))
+    rec["daf_org_tt"] = {"loss": loss_tt.detach().clone(), "gt": torch.tensor([1, 1])}
+    # MAF: L3 on sigmoid outputs of the three SRM heads (eval() for determinism: dropout off)
+    m = ns.maf.ResNet_DA(**common)
+    m.eval()
+    feats = {}
+    hooks = [getattr(m, n).register_forward_hook(lambda mod, i, o, n=n: feats.__setitem__(n, o.detach().clone()))
+             for n in ("da_head_bottom", "da_head_mid", "da_head_top")]
+    outs, losses = m.forward_train(img, gt)
+    for h in hooks:
+        h.remove()
+    rec["maf"] = {"preds": [feats["da_head_bottom"], feats["da_head_mid"], feats["da_head_top"]],
+                  "losses": losses.detach().clone(), "gt": gt}
+    # CBAM: L3 on raw logits of the two Global heads + L2 on the Local head
+    m = ns.cbam.ResNet_DA_CBAM(**common)
+    torch.nn.init.normal_(m.local_da_head_bottom.conv3.weight, 0, 0.3)
+    m.eval()
+    feats = {}
+    hooks = [getattr(m, n).register_forward_hook(lambda mod, i, o, n=n: feats.__setitem__(n, o.detach().clone()))
+             for n in ("local_da_head_bottom", "da_head_mid", "da_head_top")]
+    outs, glob, patch = m.forward_train(img, gt)
+    for h in hooks:
+        h.remove()
+    rec["cbam"] = {"local_feat": feats["local_da_head_bottom"], "logits": [feats["da_head_mid"], feats["da_head_top"]],
+                   "global_losses": glob.detach().clone(), "patch_loss": patch.detach().clone(), "gt": gt}
+    torch.save(rec, os.path.join(OUT, "backbone_loss_tails.pt"))
+    print("backbone loss tails: daf_org", float(rec["daf_org"]["loss"]), "maf", rec["maf"]["losses"].tolist(),
+          "cbam", rec["cbam"]["global_losses"].tolist(), float(rec["cbam"]["patch_loss"]))
+
+
+def focal_case(ns):
+    u = seeded.seeded_tensor("focal.u", (40, 2), 0, scale=2.0).requires_grad_(True)
+    labels = (seeded.seeded_tensor("focal.lab", (40,), 0) > 0).long()
+    # FocalLoss.forward on CPU: one-hot with num_classes+1 then slice (focal_loss.py:166-168)
+    t = torch.nn.functional.one_hot(labels, num_classes=3)[:, :2]
+    loss = ns.focal.py_sigmoid_focal_loss(u, t, None, gamma=2.0, alpha=0.25, reduction="mean")
+    loss.backward()
+    torch.save({"u": u.detach().clone(), "labels": labels, "loss": loss.detach().clone(), "du": u.grad.clone()},
+               os.path.join(OUT, "focal_loss.pt"))
+    print("focal:", float(loss))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ns = ref_loader.load()
+    roi_align_case()
+    fm = seeded.feature_map
+    head_case("img_alignment", ns.daf_org.ImgAlignmentHead(64), fm("x.img", (2, 64, 6, 10)))
+    head_case("local_alignment", ns.cbam.LocalAlignmentHead(64), fm("x.local", (2, 64, 6, 10)))
+    head_case("global_alignment_cbam", ns.cbam.GlobalAlignmentHead(64), fm("x.global", (2, 64, 12, 20)))
+    head_case("global_alignment_deep", ns.deep.GlobalAlignmentHead(64), fm("x.globald", (2, 64, 13, 19)))
+    head_case("srm", ns.maf.SRM(64), fm("x.srm", (2, 64, 6, 10)))
+    head_case("non_local_alignment", ns.deep.NonLocalAlignmentHead(64), fm("x.nla", (2, 64, 4, 6)))
+    head_case("instance_alignment", ns.instance.InstanceAlignmentHead(), fm("x.ins", (24, 1024)))
+    head_case("instance_alignment_daf", ns.instance.InstanceAlignmentHead_DAF(), fm("x.insd", (24, 1024)))
+    backbone_loss_cases(ns)
+    focal_case(ns)
+    total = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
+    print(f"golden fixtures: {total / 1e6:.2f} MB in {OUT}")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,43 @@
+"""Shared helpers of the parity tests."""
+import torch
+
+import unsupervised_domain_adaptation_object_detection_implementation_b200 as uda
+from unsupervised_domain_adaptation_object_detection_implementation_b200 import da_heads
+from oracle import da_oracle, seeded
+
+# golden name -> (module factory of THIS repo, oracle function(x, sd), input is 4-D feature map?)
+HEADS = {
+    "img_alignment": (lambda: da_heads.ImgAlignmentHead(64), da_oracle.img_alignment_head),
+    "local_alignment": (lambda: da_heads.LocalAlignmentHead(64), da_oracle.local_alignment_head),
+    "global_alignment_cbam": (lambda: da_heads.GlobalAlignmentHead(64), da_oracle.global_alignment_head),
+    "global_alignment_deep": (lambda: da_heads.GlobalAlignmentHeadDeep(64), da_oracle.global_alignment_head),
+    "srm": (lambda: da_heads.SRM(64), da_oracle.srm),
+    "non_local_alignment": (lambda: da_heads.NonLocalAlignmentHead(64), da_oracle.non_local_alignment_head),
+    "instance_alignment": (lambda: da_heads.InstanceAlignmentHead(), lambda x, sd: torch.sigmoid(da_oracle.instance_alignment_logits(x, sd))),
+    "instance_alignment_daf": (lambda: da_heads.InstanceAlignmentHead_DAF(), lambda x, sd: torch.sigmoid(da_oracle.instance_alignment_daf_logits(x, sd))),
+}
+
+
+def build_head(name, seed=0):
+    m = HEADS[name][0]().float().eval()
+    seeded.fill_state_(m, seed, prefix=name + ".")
+    return m
+
+
+def rel_err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def check_summary(grad, summ, tol):
+    """Compare a gradient tensor against the (possibly subsampled) golden record."""
+    g = grad.detach().float().cpu().reshape(-1)
+    if "full" in summ:
+        ref = summ["full"]
+        scale = ref.abs().max().clamp_min(1e-30)
+        return float((g - ref).abs().max() / scale)
+    ref = summ["sample"]
+    scale = max(float(ref.abs().max()), 1e-30)
+    e1 = float((g[summ["idx"]] - ref).abs().max()) / scale
+    e2 = abs(float(g.norm()) - summ["norm"]) / max(summ["norm"], 1e-30)
+    return max(e1, e2)

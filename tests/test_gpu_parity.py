@@ -1,0 +1,365 @@
+"""GPU parity suite (-m gpu): the CUDA path, called through the C-ABI (ctypes -> libda_b200.so),
+against the oracle and the committed golden vectors.
+
+Tolerances (BASELINE.json north_star): sampling grids / batch indices bit-exact; fp32 values,
+losses and gradients <= 1e-5 relative (to the max magnitude of the reference tensor) on the fp32
+engines; the tcgen05 bf16 engine is stated separately (bf16 inputs, fp32 accumulate: 2e-2).
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import unsupervised_domain_adaptation_object_detection_implementation_b200 as uda  # noqa: E402
+from unsupervised_domain_adaptation_object_detection_implementation_b200 import functional as F_, ops, da_losses  # noqa: E402
+from unsupervised_domain_adaptation_object_detection_implementation_b200.roi_extractors import SingleRoIExtractor, bbox2roi  # noqa: E402
+from oracle import da_oracle, roi_align as oracle_roi, seeded  # noqa: E402
+from helpers import HEADS, build_head, rel_err, check_summary  # noqa: E402
+
+DEV = "cuda"
+FP32_TOL = 1e-5
+BF16X3_TOL = 2e-4
+BF16_TOL = 3e-2
+
+
+@pytest.fixture(autouse=True)
+def _engine_reset():
+    yield
+    uda.set_engine("umma_bf16")
+
+
+# ---------------------------------------------------------------------------- RoIAlign
+def _roi_case(golden):
+    g = golden("roi_align_torchvision.pt")
+    return g, g["feat"].to(DEV), g["rois"].to(DEV), 1.0 / g["stride"]
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_roi_align_forward_backward_vs_golden(golden, channels_last):
+    g, feat, rois, scale = _roi_case(golden)
+    if channels_last:
+        feat = feat.contiguous(memory_format=torch.channels_last)
+    feat.requires_grad_(True)
+    out, grid = F_.roi_align(feat, rois, 7, scale, 0, True, return_grid=True)
+    assert torch.equal(grid.cpu(), g["grid"])                                  # bit-exact sampling grid
+    assert rel_err(out, g["out"]) <= FP32_TOL
+    (out * g["cot"].to(DEV)).sum().backward()
+    assert rel_err(feat.grad, g["dfeat"]) <= FP32_TOL
+
+
+def test_roi_align_layouts_dtypes_and_module_surface(golden):
+    g, feat, rois, scale = _roi_case(golden)
+    layer = ops.RoIAlign(output_size=7, spatial_scale=scale, sampling_ratio=0)      # mmcv.ops.RoIAlign signature
+    assert layer.output_size == (7, 7) and layer.aligned is True
+    out = layer(feat, rois)
+    assert rel_err(out, g["out"]) <= FP32_TOL
+    out_hwc = F_.roi_align(feat, rois, 7, scale, 0, True, out_layout="rhwc")
+    assert rel_err(out_hwc.permute(0, 3, 1, 2), g["out"]) <= FP32_TOL
+    # legacy (aligned=False, sampling_ratio=2)
+    out2 = F_.roi_align(feat, rois[:24], 7, scale, 2, False)
+    assert rel_err(out2, g["out_legacy_sr2"]) <= FP32_TOL
+    # bf16 features: compare with the oracle evaluated on the bf16-rounded map (fp32 accumulation)
+    fb = feat.to(torch.bfloat16)
+    ref, _, _ = oracle_roi.roi_align_forward(fb.float().cpu().numpy(), rois.cpu().numpy(), 7, scale)
+    ob = F_.roi_align(fb, rois, 7, scale, 0, True, out_dtype=torch.float32)
+    assert rel_err(ob, torch.from_numpy(ref)) <= FP32_TOL
+    ob16 = F_.roi_align(fb, rois, 7, scale, 0, True)
+    assert ob16.dtype == torch.bfloat16 and rel_err(ob16.float(), torch.from_numpy(ref)) <= 1e-2
+
+
+def test_roi_align_edge_cases():
+    feat = seeded.seeded_tensor("edge.feat", (2, 6, 9, 11), 0).to(DEV)
+    empty = F_.roi_align(feat, torch.zeros(0, 5, device=DEV), 7, 0.25)
+    assert empty.shape == (0, 6, 7, 7)
+    feat.requires_grad_(True)
+    out = F_.roi_align(feat, torch.zeros(0, 5, device=DEV), 7, 0.25)
+    out.sum().backward()
+    assert float(feat.grad.abs().max()) == 0.0
+    # batch index out of range: bounds-checked -> zeros, and raises when validated
+    bad = torch.tensor([[2.0, 0, 0, 16, 16], [-1.0, 0, 0, 16, 16], [1.0, 4, 4, 30, 30]], device=DEV)
+    out = F_.roi_align(feat.detach(), bad, 7, 0.25)
+    assert float(out[:2].abs().max()) == 0.0 and float(out[2].abs().max()) > 0
+    with pytest.raises(RuntimeError, match="batch index"):
+        F_.roi_align(feat.detach(), bad, 7, 0.25, validate=True)
+    with pytest.raises(RuntimeError):
+        F_.roi_align(feat.detach(), bad, 5, 0.25)           # only output_size=7 is built
+
+
+@pytest.mark.parametrize("C,H,W,R", [(320, 33, 47, 300), (256, 64, 128, 512), (2, 5, 7, 40)])
+def test_roi_align_vs_oracle_ragged_shapes(C, H, W, R):
+    N, stride = 3, 8
+    feat = seeded.seeded_tensor("rag.feat", (N, C, H, W), 2)
+    rois = torch.cat([seeded.synthetic_rois(R // N, N, H * stride, W * stride, 2, 6.0, 400.0),
+                      seeded.adversarial_rois(N, H * stride, W * stride)])
+    ref, grid_ref, _ = oracle_roi.roi_align_forward(feat.numpy(), rois.numpy(), 7, 1.0 / stride, threads=8)
+    f = feat.to(DEV).requires_grad_(True)
+    out, grid = F_.roi_align(f, rois.to(DEV), 7, 1.0 / stride, 0, True, return_grid=True)
+    assert np.array_equal(grid.cpu().numpy(), grid_ref)
+    assert rel_err(out, torch.from_numpy(ref)) <= FP32_TOL
+    cot = seeded.seeded_tensor("rag.cot", tuple(out.shape), 2)
+    (out * cot.to(DEV)).sum().backward()
+    gref = oracle_roi.roi_align_backward(cot.numpy(), rois.numpy(), (N, C, H, W), 7, 1.0 / stride)
+    assert rel_err(f.grad, torch.from_numpy(gref)) <= FP32_TOL
+
+
+def test_roi_align_full_size_properties():
+    """BASELINE config 4 size (4 x 2048 x 64 x 128, 2048 RoIs): size-independent properties."""
+    N, C, H, W, R = 4, 2048, 64, 128, 2048
+    rois = seeded.synthetic_rois(R // N, N, H * 16, W * 16, 0).to(DEV)
+    g = torch.Generator(device=DEV).manual_seed(0)
+    f1 = torch.randn(N, H, W, C, device=DEV, generator=g).permute(0, 3, 1, 2)   # channels_last storage
+    f2 = torch.randn(N, H, W, C, device=DEV, generator=g).permute(0, 3, 1, 2)
+    o1, o2 = F_.roi_align(f1, rois, 7, 1 / 16), F_.roi_align(f2, rois, 7, 1 / 16)
+    o12 = F_.roi_align(2.0 * f1 - f2, rois, 7, 1 / 16)
+    assert rel_err(o12, 2.0 * o1 - o2) <= 1e-5                                 # linearity
+    ones = F_.roi_align(torch.ones_like(f1), rois, 7, 1 / 16)                   # RoIs lie inside the image
+    assert float((ones - 1).abs().max()) <= 1e-5                               # partition of unity
+    # adjointness <A f, g> == <f, A^T g>: ties backward to forward at full size
+    f1 = f1.detach().requires_grad_(True)
+    cot = torch.randn(R, C, 7, 7, device=DEV, generator=g)
+    out = F_.roi_align(f1, rois, 7, 1 / 16)
+    lhs = (out.double() * cot.double()).sum()
+    out.backward(cot)
+    rhs = (f1.grad.double() * f1.detach().double()).sum()
+    assert abs(float(lhs - rhs)) <= 1e-6 * abs(float(lhs))
+    # a slice against the oracle
+    sub = rois[:16].clone()
+    sub[:, 0] = 0
+    ref, _, _ = oracle_roi.roi_align_forward(f1[:1, :64].detach().cpu().numpy(), sub.cpu().numpy(), 7, 1 / 16)
+    got = F_.roi_align(f1[:1, :64].detach().contiguous(), sub, 7, 1 / 16)
+    assert rel_err(got, torch.from_numpy(ref)) <= FP32_TOL
+
+
+def test_single_roi_extractor_and_level_mapping():
+    ext = SingleRoIExtractor(dict(type="RoIAlign", output_size=7, sampling_ratio=0), out_channels=16, featmap_strides=[4, 8, 16, 32])
+    feats = [seeded.seeded_tensor(f"fpn{i}", (2, 16, 128 >> i, 192 >> i), 0).to(DEV) for i in range(4)]
+    boxes = [seeded.synthetic_rois(50, 1, 512, 768, s, 8.0, 700.0)[:, 1:] for s in (0, 1)]
+    rois = bbox2roi([b.to(DEV) for b in boxes])
+    lv = ext.map_roi_levels(rois, 4)
+    assert np.array_equal(lv.cpu().numpy(), oracle_roi.map_roi_levels(rois.cpu().numpy(), 4, 56.0))   # bit-exact
+    out = ext(feats, rois)
+    ref = np.zeros((rois.shape[0], 16, 7, 7), np.float32)
+    for i in range(4):
+        idx = (lv == i).nonzero().squeeze(1).cpu().numpy()
+        if len(idx):
+            ref[idx] = oracle_roi.roi_align_forward(feats[i].cpu().numpy(), rois.cpu().numpy()[idx], 7, 1.0 / (4 << i))[0]
+    assert rel_err(out, torch.from_numpy(ref)) <= FP32_TOL
+    single = SingleRoIExtractor(dict(type="RoIAlign", output_size=7, sampling_ratio=0), out_channels=16, featmap_strides=[16])
+    assert single([feats[2]], rois[:0]).shape == (0, 16, 7, 7)
+
+
+# ---------------------------------------------------------------------------- losses
+def _grad_pair(fn_cuda, fn_ref, tensors):
+    cu = [t.to(DEV).float().requires_grad_(True) for t in tensors]
+    rf = [t.double().requires_grad_(True) for t in tensors]
+    a, b = fn_cuda(*cu), fn_ref(*rf)
+    a.backward(torch.tensor(0.7, device=DEV))
+    (b * 0.7).backward()
+    return a, b, cu, rf
+
+
+@pytest.mark.parametrize("gt", [[0, 1], [1, 0], [0, 0], [1, 1], [0, 1, 1, 0]])
+@pytest.mark.parametrize("whole", [True, False])
+def test_pixel_domain_loss(gt, whole):
+    n = len(gt)
+    p = seeded.seeded_tensor("pl.p", (n, 1, 37, 53), 0, scale=2.0)
+    gtt = torch.tensor(gt)
+    ref_fn = da_oracle.daf_image_loss if whole else da_oracle.patch_loss
+    a, b, cu, rf = _grad_pair(lambda x: F_.pixel_domain_loss(x, gtt.to(DEV), whole), lambda x: ref_fn(x, gtt), [p])
+    assert abs(float(a) - float(b)) <= FP32_TOL * abs(float(b))
+    assert rel_err(cu[0].grad, rf[0].grad) <= FP32_TOL
+
+
+def test_pixel_domain_loss_large_map():
+    p = seeded.seeded_tensor("pl.big", (2, 1, 128, 256), 1, scale=3.0)
+    gtt = torch.tensor([0, 1])
+    for whole, ref_fn in ((True, da_oracle.daf_image_loss), (False, da_oracle.patch_loss)):
+        a = F_.pixel_domain_loss(p.to(DEV), gtt.to(DEV), whole)
+        assert abs(float(a) - float(ref_fn(p.double(), gtt))) <= FP32_TOL * float(a)
+
+
+@pytest.mark.parametrize("on_sigmoid", [False, True])
+@pytest.mark.parametrize("R", [2, 1024, 1500])
+def test_ce2(on_sigmoid, R):
+    z = seeded.seeded_tensor("ce.z", (R, 2), 0, scale=2.0)
+    lab = (seeded.seeded_tensor("ce.l", (R,), 0) > 0).long()
+    ref = lambda x: da_oracle.ce2(torch.sigmoid(x) if on_sigmoid else x, lab)
+    a, b, cu, rf = _grad_pair(lambda x: F_.ce2(x, lab.to(DEV), on_sigmoid)[0], ref, [z])
+    assert abs(float(a) - float(b)) <= FP32_TOL * abs(float(b))
+    assert rel_err(cu[0].grad, rf[0].grad) <= FP32_TOL
+    if on_sigmoid:
+        _, pred = F_.ce2(z.to(DEV), lab.to(DEV), True)
+        assert rel_err(pred, torch.sigmoid(z)) <= 1e-6
+
+
+def test_ce2_known_answer():
+    loss, _ = F_.ce2(torch.tensor([[100.0, -100.0]], device=DEV), torch.tensor([1], device=DEV), False)
+    assert abs(float(loss) - 200.0) < 1e-3     # reference tests/test_metrics/test_losses.py:18-33
+
+
+def test_focal_vs_reference_golden(golden):
+    g = golden("focal_loss.pt")
+    u = g["u"].to(DEV).requires_grad_(True)
+    loss = da_losses.FocalLoss(gamma=2.0, alpha=0.25)(u, g["labels"].to(DEV))
+    assert abs(float(loss) - float(g["loss"])) <= FP32_TOL * float(g["loss"])
+    loss.backward()
+    assert rel_err(u.grad, g["du"]) <= FP32_TOL
+    with pytest.raises(NotImplementedError):
+        da_losses.FocalLoss(use_sigmoid=False)
+
+
+@pytest.mark.parametrize("R", [0, 30, 1024])
+def test_consistency_loss(R):
+    img = seeded.feature_map("cs.img", (2, 1, 32, 64), 0)
+    pred = torch.sigmoid(seeded.seeded_tensor("cs.pred", (R, 2), 0))
+    lab = torch.cat([torch.zeros(R // 2), torch.ones(R - R // 2)]).long()
+    a, b, cu, rf = _grad_pair(lambda i, p: F_.consistency_loss(i, p, lab.to(DEV)),
+                              lambda i, p: da_oracle.consistency_loss(i, p, lab), [img, pred])
+    assert abs(float(a) - float(b)) <= FP32_TOL * max(abs(float(b)), 1e-6)
+    if R:
+        assert rel_err(cu[0].grad, rf[0].grad) <= 1e-4      # sign() sum of +-1 terms, fp32 mean
+        assert rel_err(cu[1].grad, rf[1].grad) <= FP32_TOL
+        if R <= 64:
+            c = da_oracle.consistency_loss_loop(img.double(), pred.double(), lab)
+            assert abs(float(a) - float(c)) <= FP32_TOL * abs(float(c))
+
+
+def test_grl_and_softmax_dim0():
+    x = seeded.seeded_tensor("grl.x", (5, 7), 0).to(DEV).requires_grad_(True)
+    (F_.gradient_scalar(x, -0.3) * 2.0).sum().backward()
+    assert torch.allclose(x.grad, torch.full_like(x, -0.6))
+    s = seeded.seeded_tensor("sm.s", (96, 96), 0, scale=3.0)
+    a = s.to(DEV).requires_grad_(True)
+    b = s.double().requires_grad_(True)
+    pa, pb = F_.softmax_dim0(a), torch.softmax(b, dim=0)
+    assert rel_err(pa, pb) <= FP32_TOL
+    cot = seeded.seeded_tensor("sm.c", (96, 96), 0)
+    (pa * cot.to(DEV)).sum().backward()
+    (pb * cot.double()).sum().backward()
+    assert rel_err(a.grad, b.grad) <= FP32_TOL
+
+
+# ---------------------------------------------------------------------------- dense engines
+CONV_CASES = [
+    # N, H, W, Cin, Cout, k, stride, pad
+    (2, 9, 13, 64, 128, 1, 1, 0),      # flat 1x1
+    (2, 9, 13, 64, 72, 1, 1, 1),       # 1x1 with padding (SRM conv1, Q12)
+    (2, 10, 14, 64, 136, 3, 1, 1),
+    (2, 11, 15, 128, 64, 3, 2, 1),     # stride 2, odd extent (Global heads)
+    (1, 8, 12, 64, 192, 3, 1, 3),      # padding 3 (SRM conv2)
+    (3, 1, 1, 192, 256, 1, 1, 0),      # FC
+    (2, 7, 7, 64, 64, 3, 2, 1),        # RoI-conv flavour (local_da.py)
+]
+
+
+def _conv_ref(x, w, stride, pad):
+    return torch.nn.functional.conv2d(x.double(), w.double(), None, stride, pad)
+
+
+@pytest.mark.parametrize("engine,tol", [("simt_f32", FP32_TOL), ("umma_bf16x3", BF16X3_TOL), ("umma_bf16", BF16_TOL)])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_dense_layer_engines(engine, tol, case):
+    N, H, W, Cin, Cout, k, stride, pad = case
+    x = seeded.seeded_tensor("cv.x", (N, Cin, H, W), 0)
+    w = seeded.seeded_tensor("cv.w", (Cout, Cin, k, k), 0, scale=(Cin * k * k) ** -0.5)
+    scale = seeded.seeded_tensor("cv.s", (Cout,), 0, "uniform")
+    shift = seeded.seeded_tensor("cv.t", (Cout,), 0, scale=0.1)
+    xr, wr = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    sr, tr = scale.double().requires_grad_(True), shift.double().requires_grad_(True)
+    yr = torch.relu(_conv_ref(xr, wr, stride, pad) * sr.view(1, -1, 1, 1) + tr.view(1, -1, 1, 1))
+    cot = seeded.seeded_tensor("cv.c", tuple(yr.shape), 0)
+    (yr * cot.double()).sum().backward()
+
+    dt = F_.act_dtype(engine)
+    xc = x.to(DEV).requires_grad_(True)
+    wc = w.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    sc, tc = scale.to(DEV).requires_grad_(True), shift.to(DEV).requires_grad_(True)
+    y = F_.dense_layer(F_.to_nhwc(xc, dt), wc, sc, tc, stride=stride, pad=pad, relu=True, engine=engine, grl=-1.0)
+    y_nchw = y.permute(0, 3, 1, 2).float()
+    assert rel_err(y_nchw, yr) <= tol
+    (y_nchw * cot.to(DEV)).sum().backward()
+    assert rel_err(xc.grad, -xr.grad) <= tol * 3          # GRL folded into the data gradient
+    assert rel_err(wc.grad, wr.grad) <= tol * 3
+    assert rel_err(tc.grad, tr.grad) <= tol * 3
+    assert rel_err(sc.grad, sr.grad) <= tol * 10
+
+
+@pytest.mark.parametrize("engine", ["simt_f32", "umma_bf16x3"])
+def test_dense_layer_dropout_mask_is_exported(engine):
+    N, H, W, Cin, Cout = 2, 6, 8, 64, 128
+    x = seeded.seeded_tensor("dr.x", (N, H, W, Cin), 0).to(DEV).requires_grad_(True)
+    w = seeded.seeded_tensor("dr.w", (Cout, Cin, 1, 1), 0, scale=Cin ** -0.5).to(DEV).requires_grad_(True)
+    seed = 1234567
+    y = F_.dense_layer(x, w, relu=True, drop_p=0.5, seed=seed, engine=engine)
+    keep = F_.dropout_keep_mask(seed, (N, H, W, Cout), 0.5, DEV)
+    assert 0.4 < float(keep.float().mean()) < 0.6
+    ref = torch.relu(x.detach().double() @ w.detach().double().view(Cout, Cin).t()) * keep.double() * 2.0
+    tol = FP32_TOL if engine == "simt_f32" else BF16X3_TOL
+    assert rel_err(y, ref) <= tol
+    y.sum().backward()
+    xr = x.detach().double().requires_grad_(True)
+    (torch.relu(xr @ w.detach().double().view(Cout, Cin).t()) * keep.double() * 2.0).sum().backward()
+    assert rel_err(x.grad, xr.grad) <= tol * 3
+
+
+# ---------------------------------------------------------------------------- heads vs reference golden
+@pytest.mark.parametrize("engine,tol", [("simt_f32", FP32_TOL), ("umma_bf16x3", BF16X3_TOL), ("umma_bf16", BF16_TOL)])
+@pytest.mark.parametrize("name", sorted(HEADS))
+def test_heads_match_reference_golden(golden, name, engine, tol):
+    g = golden(f"head_{name}.pt")
+    uda.set_engine(engine)
+    m = build_head(name, g["seed"]).to(DEV)
+    x = g["x"].to(DEV).requires_grad_(True)
+    out = m(x)
+    out = out[0] if isinstance(out, tuple) else out
+    assert out.shape == g["out"][0].shape
+    assert rel_err(out.float(), g["out"][0]) <= tol
+    (out.float() * g["cot"][0].to(DEV)).sum().backward()
+    gtol = tol * 5
+    assert rel_err(x.grad, g["dx"]) <= gtol
+    params = dict(m.named_parameters())
+    for k, summ in g["dparams"].items():
+        assert params[k].grad is not None, k
+        assert check_summary(params[k].grad, summ, gtol) <= max(gtol, 2e-5), k
+    for k in g["no_grad_params"]:            # dead branch (Q10) / unused BN (Q9): no gradient, as in the reference
+        assert params[k].grad is None, k
+
+
+def test_head_dropout_training_mode_statistics():
+    uda.set_engine("simt_f32")
+    m = build_head("local_alignment").to(DEV).train()
+    assert not m.bn1.training and not m.bn2.training          # Q9: BN stays in eval
+    x = seeded.feature_map("x.local", (2, 64, 6, 10)).to(DEV)
+    a, b = m(x), m(x)
+    assert float((a - b).abs().max()) > 0                     # dropout active, fresh seed per call
+    m.eval()
+    assert float((m(x) - m(x)).abs().max()) == 0.0
+
+
+def test_daf_org_composite_losses_vs_oracle():
+    """H1 + L1 + I1 + L4 + L7 with the reference's lambda weights (DAFaster_rcnn_Orig.py:143-157)."""
+    uda.set_engine("simt_f32")
+    img_head, ins_head = build_head("img_alignment").to(DEV), build_head("instance_alignment").to(DEV)
+    c5 = seeded.feature_map("cmp.c5", (2, 64, 8, 12), 0)
+    feats = [seeded.feature_map("cmp.f0", (20, 1024), 0), seeded.feature_map("cmp.f1", (28, 1024), 0)]
+    gt = torch.tensor([0, 1])
+    sd_img = {k: v.cpu().double() for k, v in img_head.state_dict().items()}
+    sd_ins = {k: v.cpu().double() for k, v in ins_head.state_dict().items()}
+    c5r = c5.double().requires_grad_(True)
+    fr = [f.double().requires_grad_(True) for f in feats]
+    ref, _, _ = da_oracle.daf_org_da_losses(c5r, fr, gt, sd_img, sd_ins)
+    sum(ref.values()).backward()
+
+    c5c = c5.to(DEV).requires_grad_(True)
+    fc = [f.to(DEV).requires_grad_(True) for f in feats]
+    img_feat = img_head(c5c)
+    labels = torch.cat([torch.zeros(20), torch.ones(28)]).long().to(DEV)
+    l4, pred = da_losses.instance_ce_loss(ins_head.forward_logits(torch.cat(fc, 0)), labels)
+    got = dict(globle_da_loss=0.1 * da_losses.daf_image_loss(img_feat, gt.to(DEV)), local_da_loss=0.1 * l4,
+               consistency_loss=0.1 * da_losses.consistency_loss(img_feat, pred, labels))
+    for k in ref:
+        assert abs(float(got[k]) - float(ref[k])) <= FP32_TOL * abs(float(ref[k])), k
+    sum(got.values()).backward()
+    assert rel_err(c5c.grad, c5r.grad) <= 5e-5
+    assert rel_err(fc[0].grad, fr[0].grad) <= 5e-5 and rel_err(fc[1].grad, fr[1].grad) <= 5e-5

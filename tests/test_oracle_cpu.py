@@ -1,0 +1,190 @@
+"""CPU suite (-m "not gpu"): pins the ORACLE against the golden vectors the reference's own
+classes produced (tests/golden, generator oracle/make_golden.py), checks the closed-form losses
+against literal transcriptions of the reference loops, and checks the C-ABI surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import da_oracle, roi_align as oracle_roi, seeded
+from helpers import HEADS, build_head, rel_err, check_summary
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---------------------------------------------------------------- RoIAlign oracle
+def test_roi_align_oracle_matches_torchvision_golden(golden):
+    g = golden("roi_align_torchvision.pt")
+    out, grid, bidx = oracle_roi.roi_align_forward(g["feat"].numpy(), g["rois"].numpy(), 7, 1.0 / g["stride"], 0, True)
+    ref = g["out"].numpy()
+    assert np.abs(out - ref).max() <= 1e-6 * np.abs(ref).max()
+    assert np.array_equal(grid, g["grid"].numpy())            # sampling grid: bit-exact
+    assert np.array_equal(bidx, g["batch_idx"].numpy())       # batch indices: bit-exact
+    gin = oracle_roi.roi_align_backward(g["cot"].numpy(), g["rois"].numpy(), tuple(g["feat"].shape), 7, 1.0 / g["stride"], 0, True)
+    dref = g["dfeat"].numpy()
+    assert np.abs(gin - dref).max() <= 1e-5 * np.abs(dref).max()
+
+
+def test_roi_align_oracle_legacy_mode(golden):
+    g = golden("roi_align_torchvision.pt")
+    out, _, _ = oracle_roi.roi_align_forward(g["feat"].numpy(), g["rois"][:24].numpy(), 7, 1.0 / g["stride"], 2, False)
+    ref = g["out_legacy_sr2"].numpy()
+    assert np.abs(out - ref).max() <= 1e-6 * np.abs(ref).max()
+
+
+def test_roi_align_oracle_live_torchvision():
+    torchvision = pytest.importorskip("torchvision")
+    feat = seeded.seeded_tensor("live.feat", (3, 5, 17, 23), 1)
+    rois = torch.cat([seeded.synthetic_rois(40, 3, 17 * 8, 23 * 8, 1, 4.0, 200.0), seeded.adversarial_rois(3, 17 * 8, 23 * 8)])
+    ref = torch.ops.torchvision.roi_align(feat, rois, 1.0 / 8, 7, 7, 0, True).numpy()
+    out, _, _ = oracle_roi.roi_align_forward(feat.numpy(), rois.numpy(), 7, 1.0 / 8, 0, True)
+    assert np.abs(out - ref).max() <= 1e-6 * np.abs(ref).max()
+
+
+def test_roi_align_oracle_edge_cases():
+    feat = np.ones((1, 2, 8, 8), np.float32)
+    # empty RoI set, batch index out of range (Q1: bounds-checked -> zeros), zero-area RoI
+    out, grid, _ = oracle_roi.roi_align_forward(feat, np.zeros((0, 5), np.float32), 7, 0.25)
+    assert out.shape == (0, 2, 7, 7)
+    rois = np.array([[3, 0, 0, 16, 16], [0, 8, 8, 8, 8], [0, 4, 4, 20, 20]], np.float32)
+    out, grid, bidx = oracle_roi.roi_align_forward(feat, rois, 7, 0.25)
+    assert np.all(out[0] == 0) and np.all(out[1] == 0)
+    assert grid[1].tolist() == [0, 0]
+    assert np.allclose(out[2], 1.0)
+
+
+def test_map_roi_levels_matches_reference_formula():
+    rois = seeded.synthetic_rois(200, 1, 1024, 2048, 3, 8.0, 900.0)
+    scale = torch.sqrt((rois[:, 3] - rois[:, 1]) * (rois[:, 4] - rois[:, 2]))
+    ref = torch.floor(torch.log2(scale / 56 + 1e-6)).clamp(min=0, max=3).long()  # single_level_roi_extractor.py:51-54
+    got = oracle_roi.map_roi_levels(rois.numpy(), 4, 56.0)
+    assert np.array_equal(got, ref.numpy())
+
+
+# ---------------------------------------------------------------- heads oracle vs reference golden
+@pytest.mark.parametrize("name", sorted(HEADS))
+def test_head_oracle_matches_reference_golden(golden, name):
+    g = golden(f"head_{name}.pt")
+    m = build_head(name, g["seed"])          # THIS repo's module: same state_dict keys as the reference class
+    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in m.state_dict().items()}
+    x = g["x"].clone().requires_grad_(True)
+    out = HEADS[name][1](x, sd)
+    assert rel_err(out, g["out"][0]) <= 2e-6
+    (out * g["cot"][0]).sum().backward()
+    assert rel_err(x.grad, g["dx"]) <= 2e-5
+    for k, summ in g["dparams"].items():
+        assert sd[k].grad is not None, k
+        assert check_summary(sd[k].grad, summ, 1e-4) <= 1e-4, k
+    # parameters the reference never reaches (dead branch Q10, unused BN Q9) get no gradient there either
+    for k in g["no_grad_params"]:
+        assert k in sd
+
+
+def test_state_dict_keys_match_reference_surface():
+    """parameter names/shapes of the DA modules."""
+    m = build_head("global_alignment_cbam")
+    sd = m.state_dict()
+    assert sd["conv1.weight"].shape == (32, 64, 3, 3) and sd["CBAM.conv.weight"].shape == (1, 2, 7, 7)
+    assert sd["CBAM.mlp.0.weight"].shape == (2, 32, 1, 1) and sd["fc2.weight"].shape == (2, 8)
+    m = build_head("instance_alignment")
+    sd = m.state_dict()
+    assert sd["nlb.conv_phi.weight"].shape == (512, 1024, 1, 1) and sd["fc3.weight"].shape == (2, 512)
+    assert "bn1.running_mean" in sd and "bn2.weight" in sd
+    assert set(p for p, _ in m.named_parameters() if p.startswith("bn")) == {"bn1.weight", "bn1.bias", "bn2.weight", "bn2.bias"}
+    m = build_head("srm")
+    assert m.state_dict()["conv2.weight"].shape == (144, 16, 3, 3) and m.conv1.padding == (1, 1) and m.conv2.padding == (3, 3)
+
+
+# ---------------------------------------------------------------- loss tails vs the reference backbones
+def test_loss_tails_match_reference_backbones(golden):
+    g = golden("backbone_loss_tails.pt")
+    d = g["daf_org"]
+    assert abs(float(da_oracle.daf_image_loss(d["patch_feat"], d["gt"])) - float(d["loss"])) <= 1e-6
+    assert abs(float(da_oracle.daf_image_loss_loop(d["patch_feat"], d["gt"])) - float(d["loss"])) <= 1e-6
+    assert abs(float(da_oracle.daf_image_loss(d["patch_feat"], g["daf_org_tt"]["gt"])) - float(g["daf_org_tt"]["loss"])) <= 1e-6
+    m = g["maf"]
+    for pred, ref in zip(m["preds"], m["losses"]):
+        assert abs(float(da_oracle.ce2(pred, m["gt"])) - float(ref)) <= 1e-6   # CE on sigmoid outputs (Q4)
+    c = g["cbam"]
+    for z, ref in zip(c["logits"], c["global_losses"]):
+        assert abs(float(da_oracle.ce2(z, c["gt"])) - float(ref)) <= 1e-6
+    assert abs(float(da_oracle.patch_loss(c["local_feat"], c["gt"])) - float(c["patch_loss"])) <= 1e-6
+    assert abs(float(da_oracle.patch_loss_loop(c["local_feat"], c["gt"])) - float(c["patch_loss"])) <= 1e-6
+
+
+def test_focal_matches_reference(golden):
+    g = golden("focal_loss.pt")
+    u = g["u"].clone().requires_grad_(True)
+    loss = da_oracle.focal2(u, g["labels"])
+    assert abs(float(loss) - float(g["loss"])) <= 1e-6
+    loss.backward()
+    assert rel_err(u.grad, g["du"]) <= 1e-5
+
+
+def test_reference_known_answer_ce():
+    """The only golden numbers the reference's tests hold near the path
+    (tests/test_metrics/test_losses.py:18-33): CE([[100,-100]], label 1) == 200."""
+    assert abs(float(da_oracle.ce2(torch.tensor([[100.0, -100.0]]), torch.tensor([1]))) - 200.0) < 1e-4
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_closed_forms_match_loop_transcriptions(seed):
+    img = seeded.feature_map("cf.img", (2, 1, 5, 7), seed).double()
+    pred = torch.sigmoid(seeded.seeded_tensor("cf.pred", (30, 2), seed).double())
+    labels = torch.cat([torch.zeros(13), torch.ones(17)]).long()
+    a = da_oracle.consistency_loss(img, pred, labels)
+    b = da_oracle.consistency_loss_loop(img, pred, labels)
+    assert abs(float(a - b)) <= 1e-10
+    for gt in ([0, 1], [1, 0], [0, 0], [1, 1]):
+        gt = torch.tensor(gt)
+        p = seeded.seeded_tensor("cf.p", (2, 1, 5, 7), seed).double()
+        assert abs(float(da_oracle.daf_image_loss(p, gt) - da_oracle.daf_image_loss_loop(p, gt))) <= 1e-12
+        assert abs(float(da_oracle.patch_loss(p, gt) - da_oracle.patch_loss_loop(p, gt))) <= 1e-12
+
+
+def test_bbox2roi_batch_indices():
+    boxes = [torch.rand(5, 4), torch.zeros(0, 4), torch.rand(3, 5)]
+    from unsupervised_domain_adaptation_object_detection_implementation_b200.roi_extractors import bbox2roi, bbox2roi_train
+    rois = bbox2roi(boxes)
+    assert torch.equal(rois, da_oracle.bbox2roi(boxes))
+    assert rois[:, 0].tolist() == [0.0] * 5 + [2.0] * 3
+    per = bbox2roi_train(boxes)
+    assert [len(p) for p in per] == [5, 0, 3] and torch.equal(torch.cat(per), rois)
+
+
+# ---------------------------------------------------------------- C-ABI surface
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "da_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(da_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_c_abi_exports_every_declared_symbol():
+    from unsupervised_domain_adaptation_object_detection_implementation_b200 import _lib
+    syms = _declared_symbols()
+    assert len(syms) >= 30
+    so = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [s for s in syms if not hasattr(so, s)]
+    assert not missing, missing
+    assert sorted(_lib.SIGNATURES) == syms          # the ctypes table covers the header exactly
+    assert so.da_version() >= 100
+
+
+def test_product_path_refuses_cpu_tensors():
+    from unsupervised_domain_adaptation_object_detection_implementation_b200 import functional as F_
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        F_.roi_align(torch.zeros(1, 4, 8, 8), torch.zeros(1, 5), 7, 1.0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        F_.pixel_domain_loss(torch.zeros(2, 1, 4, 4), torch.tensor([0, 1]), True)
+
+
+def test_product_package_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "unsupervised_domain_adaptation_object_detection_implementation_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
