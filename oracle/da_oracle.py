@@ -32,6 +32,24 @@ def grl(x, weight=-1.0):
     return _GRL.apply(x, weight)
 
 
+class _STEQuant(torch.autograd.Function):
+    """bf16 storage emulation: round in forward, identity in backward (the CUDA bf16 engine stores
+    activations / operands in bf16 and treats the rounding as identity in its backward)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def _q(x, q):
+    """q=None: exact math.  q='bf16': emulate the bf16 engine's storage points."""
+    return x if q is None else _STEQuant.apply(x)
+
+
 def _bn_eval(x, sd, p, eps=1e-5):
     """nn.BatchNorm2d in eval mode (Q9: norm_eval=True keeps DA-head BN frozen while training)."""
     shape = (1, -1) + (1,) * (x.dim() - 2)
@@ -47,19 +65,19 @@ def _drop(x, mask):
 # --------------------------------------------------------------------------------------
 # H1 ImgAlignmentHead — mmdet/models/backbones/resnet_da_daf_org.py:120-133
 # --------------------------------------------------------------------------------------
-def img_alignment_head(x, sd):
-    x = grl(x)
-    x = F.relu(F.conv2d(x, sd["conv1.weight"], sd["conv1.bias"]))
+def img_alignment_head(x, sd, q=None):
+    x = _q(grl(x), q)
+    x = _q(F.relu(F.conv2d(x, _q(sd["conv1.weight"], q), sd["conv1.bias"])), q)
     return F.relu(F.conv2d(x, sd["conv2.weight"], sd["conv2.bias"]))
 
 
 # --------------------------------------------------------------------------------------
 # H2 LocalAlignmentHead — mmdet/models/backbones/resnet_da_cbam.py:77-115
 # --------------------------------------------------------------------------------------
-def local_alignment_head(x, sd, masks=(None, None)):
-    x = grl(x)
-    x = _drop(F.relu(_bn_eval(F.conv2d(x, sd["conv1.weight"]), sd, "bn1")), masks[0])
-    x = _drop(F.relu(_bn_eval(F.conv2d(x, sd["conv2.weight"]), sd, "bn2")), masks[1])
+def local_alignment_head(x, sd, masks=(None, None), q=None):
+    x = _q(grl(x), q)
+    x = _q(_drop(F.relu(_bn_eval(F.conv2d(x, _q(sd["conv1.weight"], q)), sd, "bn1")), masks[0]), q)
+    x = _q(_drop(F.relu(_bn_eval(F.conv2d(x, _q(sd["conv2.weight"], q)), sd, "bn2")), masks[1]), q)
     return F.conv2d(x, sd["conv3.weight"])
 
 
@@ -68,11 +86,11 @@ def local_alignment_head(x, sd, masks=(None, None)):
 # Q10: conv4 consumes `res`, so the branch cannot influence the output) and
 # resnet_da_deep.py:206-303 (same head without the branch)
 # --------------------------------------------------------------------------------------
-def global_alignment_head(x, sd, masks=(None, None, None, None)):
-    x = grl(x)
-    res = _drop(F.relu(_bn_eval(F.conv2d(x, sd["conv1.weight"], None, 2, 1), sd, "bn1")), masks[0])
-    x = _drop(F.relu(_bn_eval(F.conv2d(res, sd["conv4.weight"], None, 2, 1), sd, "bn4")), masks[1])
-    x = _drop(F.relu(_bn_eval(F.conv2d(x, sd["conv5.weight"], None, 2, 1), sd, "bn5")), masks[2])
+def global_alignment_head(x, sd, masks=(None, None, None, None), q=None):
+    x = _q(grl(x), q)
+    res = _q(_drop(F.relu(_bn_eval(F.conv2d(x, _q(sd["conv1.weight"], q), None, 2, 1), sd, "bn1")), masks[0]), q)
+    x = _q(_drop(F.relu(_bn_eval(F.conv2d(res, _q(sd["conv4.weight"], q), None, 2, 1), sd, "bn4")), masks[1]), q)
+    x = _q(_drop(F.relu(_bn_eval(F.conv2d(x, _q(sd["conv5.weight"], q), None, 2, 1), sd, "bn5")), masks[2]), q)
     x = F.avg_pool2d(x, (x.size(2), x.size(3))).view(x.size(0), -1)
     x = _drop(F.relu(F.linear(x, sd["fc1.weight"], sd["fc1.bias"])), masks[3])
     return F.linear(x, sd["fc2.weight"], sd["fc2.bias"])
@@ -81,57 +99,57 @@ def global_alignment_head(x, sd, masks=(None, None, None, None)):
 # --------------------------------------------------------------------------------------
 # H4 SRM — mmdet/models/backbones/resnet_da.py:83-104 (padding=1 on the 1x1, padding=3 on the 3x3, Q12)
 # --------------------------------------------------------------------------------------
-def srm_logits(x, sd, masks=(None, None)):
-    x = grl(x)
-    x = _drop(F.relu(_bn_eval(F.conv2d(x, sd["conv1.weight"], sd["conv1.bias"], 1, 1), sd, "bn1")), masks[0])
-    x = _drop(F.relu(_bn_eval(F.conv2d(x, sd["conv2.weight"], sd["conv2.bias"], 1, 3), sd, "bn2")), masks[1])
+def srm_logits(x, sd, masks=(None, None), q=None):
+    x = _q(grl(x), q)
+    x = _q(_drop(F.relu(_bn_eval(F.conv2d(x, _q(sd["conv1.weight"], q), sd["conv1.bias"], 1, 1), sd, "bn1")), masks[0]), q)
+    x = _q(_drop(F.relu(_bn_eval(F.conv2d(x, _q(sd["conv2.weight"], q), sd["conv2.bias"], 1, 3), sd, "bn2")), masks[1]), q)
     x = F.avg_pool2d(x, (x.size(2), x.size(3))).view(x.size(0), -1)
     return F.linear(x, sd["fc.weight"], sd["fc.bias"])
 
 
-def srm(x, sd, masks=(None, None)):
-    return torch.sigmoid(srm_logits(x, sd, masks))
+def srm(x, sd, masks=(None, None), q=None):
+    return torch.sigmoid(srm_logits(x, sd, masks, q))
 
 
 # --------------------------------------------------------------------------------------
 # NonLocalBlock — mmdet/models/roi_heads/instance_da.py:150-192 (softmax over dim=1 of [b,q,k], Q11)
 # --------------------------------------------------------------------------------------
-def non_local_block(x, sd, p=""):
+def non_local_block(x, sd, p="", q=None):
     b, c, h, w = x.shape
     ic = c // 2
-    x_phi = F.conv2d(x, sd[p + "conv_phi.weight"]).view(b, ic, -1)
-    x_theta = F.conv2d(x, sd[p + "conv_theta.weight"]).view(b, ic, -1).permute(0, 2, 1)
-    x_g = F.conv2d(x, sd[p + "conv_g.weight"]).view(b, ic, -1).permute(0, 2, 1)
-    att = torch.softmax(torch.matmul(x_theta, x_phi), dim=1)
-    y = torch.matmul(att, x_g).permute(0, 2, 1).contiguous().view(b, ic, h, w)
-    return F.conv2d(y, sd[p + "conv_mask.weight"]) + x
+    x_phi = _q(F.conv2d(x, _q(sd[p + "conv_phi.weight"], q)), q).view(b, ic, -1)
+    x_theta = _q(F.conv2d(x, _q(sd[p + "conv_theta.weight"], q)), q).view(b, ic, -1).permute(0, 2, 1)
+    x_g = _q(F.conv2d(x, _q(sd[p + "conv_g.weight"], q)), q).view(b, ic, -1).permute(0, 2, 1)
+    att = _q(torch.softmax(torch.matmul(x_theta, x_phi), dim=1), q)
+    y = _q(torch.matmul(att, x_g), q).permute(0, 2, 1).contiguous().view(b, ic, h, w)
+    return _q(F.conv2d(y, _q(sd[p + "conv_mask.weight"], q)), q) + x
 
 
 # H5 NonLocalAlignmentHead — mmdet/models/backbones/resnet_da_deep.py:122-164
-def non_local_alignment_head(x, sd, mask=None):
-    x = grl(x)
-    x = _drop(F.relu(_bn_eval(F.conv2d(x, sd["conv1.weight"]), sd, "bn1")), mask)
-    return non_local_block(x, sd, "nlb1.")
+def non_local_alignment_head(x, sd, mask=None, q=None):
+    x = _q(grl(x), q)
+    x = _q(_drop(F.relu(_bn_eval(F.conv2d(x, _q(sd["conv1.weight"], q)), sd, "bn1")), mask), q)
+    return non_local_block(x, sd, "nlb1.", q)
 
 
 # --------------------------------------------------------------------------------------
 # I1 InstanceAlignmentHead — instance_da.py:42-86 ; I2 InstanceAlignmentHead_DAF — :103-131
 # --------------------------------------------------------------------------------------
-def instance_alignment_logits(x, sd, masks=(None, None)):
-    x = grl(x)
+def instance_alignment_logits(x, sd, masks=(None, None), q=None):
+    x = _q(grl(x), q)
     x = x.unsqueeze(0).permute(0, 2, 1).contiguous().unsqueeze(2)  # [1,C,1,k]
-    x = non_local_block(x, sd, "nlb.")
+    x = non_local_block(x, sd, "nlb.", q)
     x = x.permute(3, 1, 0, 2).contiguous().squeeze(-1).squeeze(-1)  # [k,C]
-    x = _drop(F.relu(F.linear(x, sd["fc1.weight"], sd["fc1.bias"])), masks[0])
-    x = _drop(F.relu(F.linear(x, sd["fc2.weight"], sd["fc2.bias"])), masks[1])
-    return F.linear(x, sd["fc3.weight"], sd["fc3.bias"])
+    x = _q(_drop(F.relu(F.linear(x, _q(sd["fc1.weight"], q), sd["fc1.bias"])), masks[0]), q)
+    x = _q(_drop(F.relu(F.linear(x, _q(sd["fc2.weight"], q), sd["fc2.bias"])), masks[1]), q)
+    return F.linear(x, _q(sd["fc3.weight"], q), sd["fc3.bias"])
 
 
-def instance_alignment_daf_logits(x, sd, masks=(None, None)):
-    x = grl(x)
-    x = _drop(F.relu(F.linear(x, sd["fc1.weight"], sd["fc1.bias"])), masks[0])
-    x = _drop(F.relu(F.linear(x, sd["fc2.weight"], sd["fc2.bias"])), masks[1])
-    return F.linear(x, sd["fc3.weight"], sd["fc3.bias"])
+def instance_alignment_daf_logits(x, sd, masks=(None, None), q=None):
+    x = _q(grl(x), q)
+    x = _q(_drop(F.relu(F.linear(x, _q(sd["fc1.weight"], q), sd["fc1.bias"])), masks[0]), q)
+    x = _q(_drop(F.relu(F.linear(x, _q(sd["fc2.weight"], q), sd["fc2.bias"])), masks[1]), q)
+    return F.linear(x, _q(sd["fc3.weight"], q), sd["fc3.bias"])
 
 
 # --------------------------------------------------------------------------------------

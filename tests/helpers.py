@@ -13,8 +13,10 @@ HEADS = {
     "global_alignment_deep": (lambda: da_heads.GlobalAlignmentHeadDeep(64), da_oracle.global_alignment_head),
     "srm": (lambda: da_heads.SRM(64), da_oracle.srm),
     "non_local_alignment": (lambda: da_heads.NonLocalAlignmentHead(64), da_oracle.non_local_alignment_head),
-    "instance_alignment": (lambda: da_heads.InstanceAlignmentHead(), lambda x, sd: torch.sigmoid(da_oracle.instance_alignment_logits(x, sd))),
-    "instance_alignment_daf": (lambda: da_heads.InstanceAlignmentHead_DAF(), lambda x, sd: torch.sigmoid(da_oracle.instance_alignment_daf_logits(x, sd))),
+    "instance_alignment": (lambda: da_heads.InstanceAlignmentHead(),
+                           lambda x, sd, q=None: torch.sigmoid(da_oracle.instance_alignment_logits(x, sd, q=q))),
+    "instance_alignment_daf": (lambda: da_heads.InstanceAlignmentHead_DAF(),
+                               lambda x, sd, q=None: torch.sigmoid(da_oracle.instance_alignment_daf_logits(x, sd, q=q))),
 }
 
 
