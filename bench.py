@@ -121,7 +121,7 @@ def make_host_inputs(pairs, seed, dtype):
 # ----------------------------------------------------------------------------------------------
 def run_ours(args):
     import unsupervised_domain_adaptation_object_detection_implementation_b200 as uda
-    from unsupervised_domain_adaptation_object_detection_implementation_b200 import dist as ddist, functional as F_, hotpath, _lib
+    from unsupervised_domain_adaptation_object_detection_implementation_b200 import dist as ddist, functional as F_, hotpath, optim, _lib
     import torch.distributed as dist
 
     rank, local, world = ddist.init_from_env("nccl")
@@ -135,7 +135,7 @@ def run_ours(args):
     torch.manual_seed(0)
     model = hotpath.DAFOrgHotPath(C, STRIDE, FC_OUT).to(dev).train()
     params = ddist.trainable_parameters(model, model.unused_parameters())
-    opt = torch.optim.SGD(params, lr=1e-3, momentum=0.9, weight_decay=5e-4)   # reference recipe (faster_rcnn_r50_daf_c2f.py:8)
+    opt = optim.FusedSGD(params, lr=1e-3, momentum=0.9, weight_decay=5e-4)    # reference recipe (faster_rcnn_r50_daf_c2f.py:8)
     reducer = ddist.FlatGradAllReduce(params) if world > 1 else None
 
     # two input sets (alternated); each is > L2 (C5 alone is 67 MB bf16 per pair, FC1's weight 411 MB)

@@ -77,6 +77,13 @@ int da_nhwc_to_nchw(const void* src, int src_dtype, void* dst, int dst_dtype,
 int da_split_bf16(const float* src, void* hi, void* lo, int64_t n, da_stream_t stream);
 int da_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, da_stream_t stream);
 
+/* SGD step of the reference recipe (torch.optim.SGD built from da_configs/faster_rcnn/
+ * faster_rcnn_r50_daf_c2f.py:8 by mmdet/apis/train.py:127): momentum, weight decay, dampening 0,
+ * no nesterov:  d = grad + wd*w;  buf = first_step ? d : mu*buf + d;  w -= lr*buf.
+ * w_bf16 (nullable): bf16 shadow of w refreshed in the same pass (operand of the tcgen05 engine). */
+int da_sgd_step(float* w, const float* grad, float* momentum_buf, int64_t n, float lr, float momentum,
+                float weight_decay, int first_step, void* w_bf16, da_stream_t stream);
+
 /* ---- RoIAlign ------------------------------------------------------------
  * Replaces mmcv.ops.RoIAlign (ext_module.roi_align_forward / roi_align_backward,
  * mmcv-full 1.3.17) as built at mmdet/models/roi_heads/roi_extractors/base_roi_extractor.py:54-60

@@ -334,8 +334,9 @@ def test_heads_match_reference_golden(golden, name, engine, tol):
 def test_heads_bf16_engine_vs_bf16_emulating_oracle(golden, name):
     """tcgen05 bf16 engine (the throughput mode), stated separately: the oracle is evaluated with the
     SAME bf16 storage points (operands and stored activations rounded to bf16, fp32/fp64 math in
-    between).  Tolerance 3e-2 of the tensor's max magnitude for values, 6e-2 for gradients (dy and dz
-    are additionally rounded to bf16 in the CUDA backward)."""
+    between).  Tolerance 3e-2 of the tensor's max magnitude for values, 6e-2 for the input gradient
+    (dy and dz are additionally rounded to bf16 in the CUDA backward), 5e-2 relative Frobenius error
+    for weight gradients."""
     g = golden(f"head_{name}.pt")
     uda.set_engine("umma_bf16")
     m = build_head(name, g["seed"])
@@ -352,7 +353,10 @@ def test_heads_bf16_engine_vs_bf16_emulating_oracle(golden, name):
     assert rel_err(x.grad, xr.grad) <= 2 * BF16_TOL
     for k, p in m.named_parameters():
         if sd[k].grad is not None and p.grad is not None and k.endswith("weight") and p.dim() >= 2:
-            assert rel_err(p.grad, sd[k].grad) <= 2 * BF16_TOL, k
+            # weight gradients deep in the stack accumulate bf16 rounding of dy/dz at every layer:
+            # bounded in the Frobenius norm
+            a, b = p.grad.double().cpu(), sd[k].grad.double()
+            assert float((a - b).norm() / b.norm()) <= 5e-2, k
 
 
 def test_head_dropout_training_mode_statistics():
@@ -392,3 +396,25 @@ def test_daf_org_composite_losses_vs_oracle():
     sum(got.values()).backward()
     assert rel_err(c5c.grad, c5r.grad) <= 5e-5
     assert rel_err(fc[0].grad, fr[0].grad) <= 5e-5 and rel_err(fc[1].grad, fr[1].grad) <= 5e-5
+
+
+def test_fused_sgd_matches_torch_sgd_and_refreshes_shadow():
+    from unsupervised_domain_adaptation_object_detection_implementation_b200 import optim
+    torch.manual_seed(0)
+    shapes = [(64, 32, 3, 3), (129,), (40, 70)]
+    ps = [torch.randn(*s, device=DEV).requires_grad_(True) for s in shapes]
+    ps[0].data = ps[0].data.contiguous(memory_format=torch.channels_last)
+    qs = [p.detach().clone().requires_grad_(True) for p in ps]
+    a = optim.FusedSGD(ps, lr=0.05, momentum=0.9, weight_decay=5e-4)
+    b = torch.optim.SGD(qs, lr=0.05, momentum=0.9, weight_decay=5e-4)
+    for it in range(3):
+        for p, q in zip(ps, qs):
+            g = torch.randn_like(q)
+            p.grad, q.grad = g.clone(), g.clone()
+        a.step()
+        b.step()
+    for p, q in zip(ps, qs):
+        assert rel_err(p, q) <= 1e-6
+    sh = F_.bf16_shadow(ps[0])
+    assert sh.dtype == torch.bfloat16 and sh.stride() == ps[0].stride()
+    assert rel_err(sh.float(), ps[0]) <= 4e-3          # refreshed in the update kernel, no re-cast

@@ -1,7 +1,7 @@
 """B200-native domain-adaptation hot path (GRL + domain classifiers + RoIAlign + instance head +
 consistency loss) behind the reference's mmdet-style module surface.  See DESIGN.md."""
 from . import _lib  # noqa: F401  (fails loudly when libda_b200.so is missing)
-from . import functional, ops, da_heads, da_losses, roi_extractors, hotpath, dist  # noqa: F401
+from . import functional, ops, da_heads, da_losses, roi_extractors, hotpath, dist, optim  # noqa: F401
 from .functional import set_engine, get_engine  # noqa: F401
 
 __version__ = "0.1.0"

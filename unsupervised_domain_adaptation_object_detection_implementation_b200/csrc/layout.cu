@@ -56,6 +56,42 @@ __global__ void dropout_mask_kernel(uint64_t seed, int64_t n, uint32_t thr, uint
     keep[i] = drop_hash(seed, (uint64_t)i) >= thr ? 1 : 0;
 }
 
+// torch.optim.SGD (momentum, weight decay, dampening 0, no nesterov) fused with the refresh of the
+// bf16 shadow copy the tensor-core engine reads: one pass over (w, grad, buf) instead of
+// torch's multi-tensor passes plus a separate fp32->bf16 cast of every weight each step.
+__global__ void sgd_step_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ buf,
+                                int64_t n, float lr, float mu, float wd, int first, __nv_bfloat16* __restrict__ shadow) {
+  const int64_t n4 = n >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 wv = reinterpret_cast<float4*>(w)[i];
+    const float4 gv = reinterpret_cast<const float4*>(g)[i];
+    float4 bv = first ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<float4*>(buf)[i];
+    float* wp = &wv.x; const float* gp = &gv.x; float* bp = &bv.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float d = fmaf(wd, wp[j], gp[j]);
+      bp[j] = first ? d : fmaf(mu, bp[j], d);
+      wp[j] = fmaf(-lr, bp[j], wp[j]);
+    }
+    reinterpret_cast<float4*>(w)[i] = wv;
+    reinterpret_cast<float4*>(buf)[i] = bv;
+    if (shadow) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(wv.x, wv.y), b = __floats2bfloat162_rn(wv.z, wv.w);
+      uint2 u;
+      u.x = *reinterpret_cast<unsigned*>(&a); u.y = *reinterpret_cast<unsigned*>(&b);
+      reinterpret_cast<uint2*>(shadow)[i] = u;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {  // tail
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    const float d = fmaf(wd, w[i], g[i]);
+    const float b = first ? d : fmaf(mu, buf[i], d);
+    buf[i] = b;
+    w[i] = fmaf(-lr, b, w[i]);
+    if (shadow) shadow[i] = __float2bfloat16_rn(w[i]);
+  }
+}
+
 static inline int ew_blocks(int64_t n) {
   int64_t b = (n + 255) / 256;
   const int64_t cap = (int64_t)num_sms() * 16;
@@ -128,6 +164,18 @@ extern "C" int da_dropout_mask(uint64_t seed, int64_t n, float drop_p, uint8_t* 
   if (n == 0) return DA_OK;
   DA_REQUIRE(keep_out && n > 0 && drop_p >= 0.f && drop_p < 1.f, DA_ERR_INVALID_ARG, "dropout_mask: bad args");
   dropout_mask_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(seed, n, drop_threshold(drop_p), keep_out);
+  DA_LAUNCH_CHECK();
+  return DA_OK;
+}
+
+extern "C" int da_sgd_step(float* w, const float* grad, float* momentum_buf, int64_t n, float lr, float momentum,
+                           float weight_decay, int first_step, void* w_bf16, da_stream_t stream) {
+  if (n == 0) return DA_OK;
+  DA_REQUIRE(w && grad && momentum_buf && n > 0, DA_ERR_INVALID_ARG, "sgd_step: bad args");
+  DA_REQUIRE((((uintptr_t)w | (uintptr_t)grad | (uintptr_t)momentum_buf) & 15) == 0 && (((uintptr_t)w_bf16) & 7) == 0,
+             DA_ERR_INVALID_ARG, "sgd_step: pointers must be 16-byte aligned");
+  sgd_step_kernel<<<ew_blocks((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(w, grad, momentum_buf, n, lr, momentum, weight_decay,
+                                                                           first_step, (__nv_bfloat16*)w_bf16);
   DA_LAUNCH_CHECK();
   return DA_OK;
 }

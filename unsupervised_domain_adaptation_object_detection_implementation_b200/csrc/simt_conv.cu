@@ -278,11 +278,16 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, int ksplit,
 
 // ---- activation backward (engine independent) --------------------------------------------
 // dz[m,c] = dy[m,c] * scale[c] * relu'(y) * keep/(1-p);  colsum partial of (dy*mask) per block
-constexpr int AB_ROWS = 64;
+// rows per block: enough blocks to fill the machine even for the [1024, C] FC activations
+__host__ __device__ inline int ab_rows(int64_t M) {
+  int64_t r = (M + 591) / 592;
+  return (int)(r < 1 ? 1 : (r > 64 ? 64 : r));
+}
 template <typename T>
 __global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, int64_t M, int C,
                                const float* __restrict__ scale, int relu, float drop_p, uint64_t seed,
                                T* __restrict__ dz, float* __restrict__ partial, float* __restrict__ partial2) {
+  const int AB_ROWS = ab_rows(M);
   const int64_t m0 = (int64_t)blockIdx.x * AB_ROWS;
   const int64_t m1 = (m0 + AB_ROWS < M) ? m0 + AB_ROWS : M;
   const uint32_t thr = drop_threshold(drop_p);
@@ -338,7 +343,7 @@ size_t simt_workspace_bytes(const da_conv_desc* d) {
   const ConvGeom g = make_geom(d);
   const size_t wsz = (size_t)g.Cout * g.KH * g.KW * g.Cin * sizeof(float);
   const int64_t M = (int64_t)g.N * g.OH * g.OW;
-  const size_t act = 2 * (size_t)((M + AB_ROWS - 1) / AB_ROWS) * g.Cout * sizeof(float);
+  const size_t act = 2 * (size_t)((M + ab_rows(M) - 1) / ab_rows(M)) * g.Cout * sizeof(float);
   const size_t a = wsz * simt_wgrad_ksplit(g);
   return (a > act ? a : act) + 256;
 }
@@ -410,7 +415,7 @@ extern "C" int da_conv_act_backward(const da_conv_desc* d, const void* dy, const
   DA_REQUIRE(!relu || y, DA_ERR_INVALID_ARG, "conv_act_backward: relu needs the forward output y");
   const ConvGeom g = make_geom(d);
   const int64_t M = (int64_t)g.N * g.OH * g.OW;
-  const int nb = (int)((M + AB_ROWS - 1) / AB_ROWS);
+  const int nb = (int)((M + ab_rows(M) - 1) / ab_rows(M));
   float* partial = nullptr;
   float* partial2 = nullptr;
   DA_REQUIRE(!dvdot || y, DA_ERR_INVALID_ARG, "conv_act_backward: dvdot needs the forward output y");

@@ -21,48 +21,11 @@
 // BF16X3: fp32 operands are split x = hi + lo (bf16 each) and the kernel accumulates
 // hi*hi + hi*lo + lo*hi into the same TMEM accumulator (3 k-passes), ~2^-16 relative.
 #include "da_common.cuh"
+#include "da_ptx.cuh"
 #include <cuda.h>
 #include <string.h>
 
 namespace da {
-
-// ---------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must surface as a trapped kernel, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) {
-      printf("da_b200: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
@@ -75,6 +38,26 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// commit that arrives on the same barrier offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
 }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
@@ -137,12 +120,19 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
 // ---------------------------------------------------------------------------------------
 // kernel parameters
 // ---------------------------------------------------------------------------------------
-constexpr int BM = 128, BN = 128, BK = 64;
-constexpr int STAGES = 5;
-constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+constexpr int BM = 128, BK = 64;
+constexpr int A_BYTES = BM * BK * 2;
 constexpr int NT_THREADS = 192;
 constexpr int MAX_TAPS = 16;
-constexpr size_t NT_SMEM = 1024 + (size_t)STAGES * (A_BYTES + B_BYTES) + 256;
+// Tile configuration: BN = 256 keeps the per-MMA shared-memory traffic (A 4 KB + B 8 KB per 128 cycles)
+// under the 128 B/clk SMEM port; BN = 128 serves narrow outputs.  Two TMEM accumulators (2*BN
+// columns) let the epilogue of tile i overlap the MMAs of tile i+1 (persistent kernel).
+template <int kBN> struct TileCfg {
+  static constexpr int STAGES = (kBN == 256) ? 4 : 6;
+  static constexpr int B_BYTES = kBN * BK * 2;
+  static constexpr size_t SMEM = 1024 + (size_t)STAGES * (A_BYTES + B_BYTES) + 256;
+  static constexpr int TMEM_COLS = 2 * kBN;
+};
 
 struct TapInfo {
   int map;  // which parity tensor map of A
@@ -157,6 +147,8 @@ struct NtParams {
   int num_taps, kchunks;    // k iterations per term = num_taps * kchunks
   int num_terms;
   int term_a[3], term_b[3];
+  int b_mn_major;           // B tile is [k rows][n contiguous] (weights read untransposed for dgrad)
+  int b_col0;               // MN-major B: column offset of n = 0 inside the B matrix (unused)
   int flat;                 // A is a flat [M,K] matrix (1x1 / FC)
   int BH, BW, bw_shift;     // patch shape (BH*BW == 128, powers of two)
   int TH, TW;               // extent of the tile grid in (class) pixels
@@ -239,126 +231,185 @@ __device__ __forceinline__ void nt_epilogue_row(const NtParams& P, const uint32_
   }
 }
 
-// grid: (pixel tiles, Cout tiles, k-splits)
+// Persistent kernel: grid = min(#tiles, #SMs); tile = (pixel tile, Cout tile, k-split).
+// kCluster == 2: the two CTAs of a cluster work on adjacent pixel tiles of the SAME Cout tile and
+// k-split; each loads half of the shared B (weight) tile and TMA-multicasts it to both, which halves
+// the L2->SM weight traffic (the 128x256 tile is L2-bandwidth bound otherwise).
+template <int kBN, int kCluster>
 __global__ void __launch_bounds__(NT_THREADS, 1)
-umma_nt_kernel(const __grid_constant__ NtParams P) {
+umma_nt_kernel(const __grid_constant__ NtParams P, int pixel_tiles, int n_tiles, int splits) {
+  using Cfg = TileCfg<kBN>;
+  constexpr int STAGES = Cfg::STAGES, B_BYTES = Cfg::B_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_s = base, b_s = base + STAGES * A_BYTES;
-  const uint32_t bars = b_s + STAGES * B_BYTES;  // full[STAGES], empty[STAGES], tmem_full, tmem_slot
-  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull = bars + 16 * STAGES, tslot = tfull + 8;
+  const uint32_t bars = b_s + STAGES * B_BYTES;
+  // full[STAGES] | empty[STAGES] | tmem_full[2] | tmem_empty[2] | tmem slot
+  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 16,
+                 tslot = tempty0 + 16;
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
   volatile uint32_t* tslot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tslot - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  // tile coordinates
-  int n_img = 0, i0 = 0, j0 = 0;
-  long long m0 = 0;
-  if (P.flat) {
-    m0 = (long long)blockIdx.x * BM;
-  } else {
-    const int per_img = P.tiles_h * P.tiles_w;
-    n_img = blockIdx.x / per_img;
-    const int t = blockIdx.x % per_img;
-    i0 = (t / P.tiles_w) * P.BH;
-    j0 = (t % P.tiles_w) * P.BW;
-  }
-  const int c0 = blockIdx.y * BN;
+  // tiles are enumerated per CLUSTER: super pixel tile q covers pixel tiles q*kCluster + rank
+  const int crank = (kCluster > 1) ? (int)cluster_ctarank() : 0;
+  const int super_tiles = (pixel_tiles + kCluster - 1) / kCluster;
+  const int total_tiles = super_tiles * n_tiles * splits;
+  const int tile0 = blockIdx.x / kCluster, tile_step = gridDim.x / kCluster;
   const int total_iters = P.num_terms * P.num_taps * P.kchunks;
-  const int splits = gridDim.z;
   const int per_split = (total_iters + splits - 1) / splits;
-  const int it_begin = blockIdx.z * per_split;
-  const int it_end = min(it_begin + per_split, total_iters);
-  const int n_iters = max(it_end - it_begin, 0);
+  const int per_img = P.tiles_h * P.tiles_w;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-    mbar_init(tfull, 1);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, kCluster); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 4); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tslot, BN);
+  if (warp == 1) tmem_alloc(tslot, Cfg::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  if (kCluster > 1) cluster_sync_all();   // peer barriers are initialised before any multicast lands
   tc_fence_after();
   const uint32_t tmem_base = *tslot_ptr;
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int k = 0; k < n_iters; ++k) {
-        const int it = it_begin + k;
-        const int s = k % STAGES;
-        const uint32_t ph = (k / STAGES) & 1;
-        mbar_wait(empty0 + 8 * s, ph ^ 1);
-        const int per_term = P.num_taps * P.kchunks;
-        const int term = it / per_term, rem = it % per_term;
-        const int tap = rem / P.kchunks, kc = rem % P.kchunks;
-        const TapInfo ti = P.taps[tap];
-        mbar_expect_tx(full0 + 8 * s, A_BYTES + B_BYTES);
-        if (P.flat)
-          tma_load_2d(a_s + s * A_BYTES, &P.a_map[P.term_a[term]][0], full0 + 8 * s, kc * BK, (int)m0);
-        else
-          tma_load_4d(a_s + s * A_BYTES, &P.a_map[P.term_a[term]][ti.map], full0 + 8 * s, kc * BK, j0 + ti.dw, i0 + ti.dh, n_img);
-        tma_load_2d(b_s + s * B_BYTES, &P.b_map[P.term_b[term]], full0 + 8 * s, ti.bk + kc * BK, c0);
+      int kq = 0;
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+        const int sp = tile % splits, nt = (tile / splits) % n_tiles, pt = (tile / (splits * n_tiles)) * kCluster + crank;
+        const int c0 = nt * kBN;
+        int n_img = 0, i0 = 0, j0 = 0, m0 = 0;
+        if (P.flat) {
+          m0 = pt * BM;
+        } else {
+          n_img = pt / per_img;
+          const int t = pt % per_img;
+          i0 = (t / P.tiles_w) * P.BH;
+          j0 = (t % P.tiles_w) * P.BW;
+        }
+        const int it_begin = sp * per_split, it_end = min(it_begin + per_split, total_iters);
+        for (int it = it_begin; it < it_end; ++it, ++kq) {
+          const int s = kq % STAGES;
+          const uint32_t ph = (uint32_t)(kq / STAGES) & 1u;
+          mbar_wait(empty0 + 8 * s, ph ^ 1u);
+          const int per_term = P.num_taps * P.kchunks;
+          const int term = it / per_term, rem = it % per_term;
+          const int tap = rem / P.kchunks, kc = rem % P.kchunks;
+          const TapInfo ti = P.taps[tap];
+          const uint32_t fb = full0 + 8 * s;
+          mbar_expect_tx(fb, A_BYTES + B_BYTES);
+          if (P.flat)
+            tma_load_2d(a_s + s * A_BYTES, &P.a_map[P.term_a[term]][0], fb, kc * BK, m0);
+          else
+            tma_load_4d(a_s + s * A_BYTES, &P.a_map[P.term_a[term]][ti.map], fb, kc * BK, j0 + ti.dw, i0 + ti.dh, n_img);
+          const CUtensorMap* bm = &P.b_map[P.term_b[term]];
+          if (kCluster == 1) {
+            if (P.b_mn_major) {
+              // boxes of (64 n, 64 k-rows): row = output channel chunk kc, column = tap block + n
+#pragma unroll
+              for (int j = 0; j < kBN / 64; ++j)
+                tma_load_2d(b_s + s * B_BYTES + j * (64 * BK * 2), bm, fb, ti.bk + c0 + j * 64, kc * BK);
+            } else {
+              tma_load_2d(b_s + s * B_BYTES, bm, fb, ti.bk + kc * BK, c0);
+            }
+          } else {
+            // this CTA fetches its half of the B tile and multicasts it into both CTAs
+            constexpr uint16_t kMask = (uint16_t)((1u << kCluster) - 1u);
+            constexpr int HALF = kBN / kCluster;
+            if (P.b_mn_major) {
+#pragma unroll
+              for (int j = 0; j < HALF / 64; ++j) {
+                const int jj = crank * (HALF / 64) + j;
+                tma_load_2d_mc(b_s + s * B_BYTES + jj * (64 * BK * 2), bm, fb, ti.bk + c0 + jj * 64, kc * BK, kMask);
+              }
+            } else {
+              tma_load_2d_mc(b_s + s * B_BYTES + crank * (HALF * BK * 2), bm, fb, ti.bk + kc * BK, c0 + crank * HALF, kMask);
+            }
+          }
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN, 0, 0);
-      for (int k = 0; k < n_iters; ++k) {
-        const int s = k % STAGES;
-        const uint32_t ph = (k / STAGES) & 1;
-        mbar_wait(full0 + 8 * s, ph);
+      const uint32_t idesc = make_idesc(BM, kBN, 0, P.b_mn_major ? 1 : 0);
+      int kq = 0, tcount = 0;
+      for (int tile = tile0; tile < total_tiles; tile += tile_step, ++tcount) {
+        const int sp = tile % splits;
+        const int it_begin = sp * per_split, it_end = min(it_begin + per_split, total_iters);
+        const int buf = tcount & 1;
+        const uint32_t use = (uint32_t)(tcount >> 1);
+        mbar_wait(tempty0 + 8 * buf, (use & 1u) ^ 1u);   // epilogue has drained this accumulator
         tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * kBN;
+        for (int it = it_begin; it < it_end; ++it, ++kq) {
+          const int s = kq % STAGES;
+          const uint32_t ph = (uint32_t)(kq / STAGES) & 1u;
+          mbar_wait(full0 + 8 * s, ph);
+          tc_fence_after();
 #pragma unroll
-        for (int kk = 0; kk < BK / 16; ++kk) {
-          const uint64_t ad = desc_kmajor_sw128(a_s + s * A_BYTES + kk * 32);
-          const uint64_t bd = desc_kmajor_sw128(b_s + s * B_BYTES + kk * 32);
-          umma_bf16(tmem_base, ad, bd, idesc, (k > 0 || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t ad = desc_kmajor_sw128(a_s + s * A_BYTES + kk * 32);
+            const uint64_t bd = P.b_mn_major ? desc_mnmajor_sw128(b_s + s * B_BYTES + kk * 2048, 64 * BK * 2)
+                                             : desc_kmajor_sw128(b_s + s * B_BYTES + kk * 32);
+            umma_bf16(d_tmem, ad, bd, idesc, (it > it_begin || kk > 0) ? 1u : 0u);
+          }
+          // the stage is reusable only when BOTH CTAs are done with it (multicast writes into both)
+          if (kCluster == 1) umma_commit(empty0 + 8 * s);
+          else umma_commit_mc(empty0 + 8 * s, (uint16_t)((1u << kCluster) - 1u));
         }
-        umma_commit(empty0 + 8 * s);
+        umma_commit(tfull0 + 8 * buf);
       }
-      umma_commit(tfull);
     }
   } else {
     // epilogue warps 2..5 -> TMEM lane quadrant (warp % 4)
     const int q = warp & 3;
     const int r = q * 32 + lane;  // accumulator row == pixel within the tile
-    bool valid;
-    size_t row_off;
-    if (P.flat) {
-      const long long m = m0 + r;
-      valid = m < P.M_flat;
-      row_off = (size_t)m * P.Cout;
-    } else {
-      const int i = i0 + (r >> P.bw_shift), j = j0 + (r & (P.BW - 1));
-      valid = (i < P.TH) && (j < P.TW);
-      row_off = (((size_t)n_img * P.OHf + (size_t)i * P.os + P.oa) * P.OWf + (size_t)j * P.os + P.ob) * P.Cout;
-    }
-    const bool raw = splits > 1;
-    float* partial = raw ? P.partial + (size_t)blockIdx.z * P.y_numel : nullptr;
-    if (n_iters > 0) {
-      mbar_wait(tfull, 0);
-      tc_fence_after();
-    }
-#pragma unroll 1
-    for (int cc = 0; cc < BN / 32; ++cc) {
-      uint32_t v[32];
-      if (n_iters > 0) {
-        DA_TMEM_LD32(tmem_base + ((uint32_t)(q * 32) << 16) + cc * 32, v);
-        tmem_ld_wait();
+    int tcount = 0;
+    for (int tile = tile0; tile < total_tiles; tile += tile_step, ++tcount) {
+      const int sp = tile % splits, nt = (tile / splits) % n_tiles, pt = (tile / (splits * n_tiles)) * kCluster + crank;
+      const int c0 = nt * kBN;
+      const int it_begin = sp * per_split, it_end = min(it_begin + per_split, total_iters);
+      const bool has_k = it_end > it_begin;
+      bool valid;
+      size_t row_off;
+      if (P.flat) {
+        const long long m = (long long)pt * BM + r;
+        valid = m < P.M_flat;
+        row_off = (size_t)m * P.Cout;
       } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0u;
+        const int n_img = pt / per_img, t = pt % per_img;
+        const int i = (t / P.tiles_w) * P.BH + (r >> P.bw_shift), j = (t % P.tiles_w) * P.BW + (r & (P.BW - 1));
+        valid = (i < P.TH) && (j < P.TW) && (pt < pixel_tiles);   // phantom tile of an odd cluster tail
+        row_off = (((size_t)n_img * P.OHf + (size_t)i * P.os + P.oa) * P.OWf + (size_t)j * P.os + P.ob) * P.Cout;
       }
-      if (valid) nt_epilogue_row(P, v, row_off, c0 + cc * 32, raw, partial);
+      const bool raw = splits > 1;
+      float* partial = raw ? P.partial + (size_t)sp * P.y_numel : nullptr;
+      const int buf = tcount & 1;
+      const uint32_t use = (uint32_t)(tcount >> 1);
+      mbar_wait(tfull0 + 8 * buf, use & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < kBN / 32; ++cc) {
+        uint32_t v[32];
+        if (has_k) {
+          DA_TMEM_LD32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * kBN + cc * 32, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
+        }
+        if (valid) nt_epilogue_row(P, v, row_off, c0 + cc * 32, raw, partial);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
     }
-    tc_fence_before();
   }
   __syncthreads();
+  if (kCluster > 1) cluster_sync_all();   // no CTA exits while its peer may still multicast into it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -386,7 +437,7 @@ __global__ void nt_splitk_finish_kernel(const float* __restrict__ partial, int s
 // weight gradient ("TN"): dW[co, tap, ci] = sum_pix dZ[pix, co] * X[pix_in(tap), ci]
 // ---------------------------------------------------------------------------------------
 constexpr int WK = 64;  // pixels per k-step
-constexpr int W_A_BYTES = BM * WK * 2, W_B_BYTES = BN * WK * 2;
+constexpr int W_A_BYTES = BM * WK * 2;
 
 struct TnParams {
   CUtensorMap a_map[2];     // dZ [hi/lo]: (Cout, OW, OH, N) or flat (Cout, M)
@@ -404,8 +455,12 @@ struct TnParams {
 };
 
 // grid: (Cout tiles, Cin tiles, taps * splits)
+template <int kBN>
 __global__ void __launch_bounds__(NT_THREADS, 1)
 umma_tn_kernel(const __grid_constant__ TnParams P, int splits) {
+  constexpr int STAGES = TileCfg<kBN>::STAGES;
+  constexpr int W_B_BYTES = kBN * WK * 2;
+  constexpr int BN = kBN;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_s = base, b_s = base + STAGES * W_A_BYTES;
@@ -452,16 +507,18 @@ umma_tn_kernel(const __grid_constant__ TnParams P, int splits) {
           const int m = (int)(patch * WK);
           tma_load_2d(ad, &P.a_map[P.term_a[term]], fb, co0, m);
           tma_load_2d(ad + W_A_BYTES / 2, &P.a_map[P.term_a[term]], fb, co0 + 64, m);
-          tma_load_2d(bd, &P.b_map[P.term_b[term]][0], fb, ci0, m);
-          tma_load_2d(bd + W_B_BYTES / 2, &P.b_map[P.term_b[term]][0], fb, ci0 + 64, m);
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_2d(bd + j * (64 * WK * 2), &P.b_map[P.term_b[term]][0], fb, ci0 + j * 64, m);
         } else {
           const int per_img = P.tiles_h * P.tiles_w;
           const int n = (int)(patch / per_img), t = (int)(patch % per_img);
           const int i0 = (t / P.tiles_w) * P.BH, j0 = (t % P.tiles_w) * P.BW;
           tma_load_4d(ad, &P.a_map[P.term_a[term]], fb, co0, j0, i0, n);
           tma_load_4d(ad + W_A_BYTES / 2, &P.a_map[P.term_a[term]], fb, co0 + 64, j0, i0, n);
-          tma_load_4d(bd, &P.b_map[P.term_b[term]][ti.map], fb, ci0, j0 + ti.dw, i0 + ti.dh, n);
-          tma_load_4d(bd + W_B_BYTES / 2, &P.b_map[P.term_b[term]][ti.map], fb, ci0 + 64, j0 + ti.dw, i0 + ti.dh, n);
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_4d(bd + j * (64 * WK * 2), &P.b_map[P.term_b[term]][ti.map], fb, ci0 + j * 64, j0 + ti.dw, i0 + ti.dh, n);
         }
       }
     }
@@ -477,7 +534,7 @@ umma_tn_kernel(const __grid_constant__ TnParams P, int splits) {
         for (int kk = 0; kk < WK / 16; ++kk) {
           // 16 k-rows = 2 swizzle atoms of 1024 B
           const uint64_t adsc = desc_mnmajor_sw128(a_s + s * W_A_BYTES + kk * 2048, W_A_BYTES / 2);
-          const uint64_t bdsc = desc_mnmajor_sw128(b_s + s * W_B_BYTES + kk * 2048, W_B_BYTES / 2);
+          const uint64_t bdsc = desc_mnmajor_sw128(b_s + s * W_B_BYTES + kk * 2048, 64 * WK * 2);
           umma_bf16(tmem_base, adsc, bdsc, idesc, (k > 0 || kk > 0) ? 1u : 0u);
         }
         umma_commit(empty0 + 8 * s);
@@ -677,7 +734,7 @@ static size_t part_bytes(const Geom& g) {
   if (w > m) m = w;
   // split-K only runs when fewer than one wave of 128x128 tiles exists, so the tensor that
   // is split never exceeds ~160 tiles
-  const size_t cap = (size_t)160 * BM * BN;
+  const size_t cap = (size_t)160 * BM * 256;
   if (m > cap) m = cap;
   return align_up(m * 16 * sizeof(float), 256);
 }
@@ -736,20 +793,50 @@ static void set_terms(int engine, int* num_terms, int* ta, int* tb) {
   }
 }
 
-static int launch_nt(NtParams& P, long long pixel_tiles, int k_iters, void* ws_part, size_t part_cap, cudaStream_t st) {
-  const int n_tiles = (P.Cout + BN - 1) / BN;
+static inline int choose_bn(int ncols) { return ncols > 128 ? 256 : 128; }
+
+static int pick_splits_persistent(long long tiles, int k_iters) {
+  // persistent kernel: keep #tile-units <= #SMs (one wave) when splitting
+  const int sms = num_sms();
+  if (tiles >= sms / 2 || k_iters < 16) return 1;
+  int s = (int)(sms / tiles);
+  if (s > k_iters / 8) s = k_iters / 8;
+  if (s > 16) s = 16;
+  return s < 1 ? 1 : s;
+}
+
+template <int kBN, int kCluster>
+static int launch_nt_t(NtParams& P, long long pixel_tiles, int k_iters, void* ws_part, size_t part_cap, cudaStream_t st) {
+  const int n_tiles = (P.Cout + kBN - 1) / kBN;
+  const long long super_tiles = (pixel_tiles + kCluster - 1) / kCluster;
   // split-K partials are indexed like y; a strided (parity-class) launch only owns part of y
-  int splits = (P.os == 1) ? pick_splits(pixel_tiles * n_tiles, k_iters) : 1;
+  int splits = (P.os == 1) ? pick_splits_persistent(super_tiles * kCluster * n_tiles, k_iters) : 1;
   while (splits > 1 && (size_t)splits * P.y_numel * sizeof(float) > part_cap) --splits;
   P.partial = (float*)ws_part;
-  DA_REQUIRE(pixel_tiles <= 0x7fffffffll, DA_ERR_UNSUPPORTED, "umma: too many tiles");
+  const long long total = super_tiles * n_tiles * splits;   // cluster-level tile units
+  DA_REQUIRE(total * kCluster <= 0x7fffffffll, DA_ERR_UNSUPPORTED, "umma: too many tiles");
+  auto kern = umma_nt_kernel<kBN, kCluster>;
   static bool attr_set = false;
   if (!attr_set) {
-    DA_CUDA_OK(cudaFuncSetAttribute(umma_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NT_SMEM));
+    DA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<kBN>::SMEM));
     attr_set = true;
   }
-  dim3 grid((unsigned)pixel_tiles, n_tiles, splits);
-  umma_nt_kernel<<<grid, NT_THREADS, NT_SMEM, st>>>(P);
+  const int max_clusters = num_sms() / kCluster;
+  const int clusters = (int)(total < max_clusters ? total : max_clusters);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(clusters * kCluster);
+  cfg.blockDim = dim3(NT_THREADS);
+  cfg.dynamicSmemBytes = TileCfg<kBN>::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DA_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, P, (int)pixel_tiles, n_tiles, splits));
   DA_LAUNCH_CHECK();
   if (splits > 1) {
     nt_splitk_finish_kernel<<<ew_blocks(P.y_numel), 256, 0, st>>>(P.partial, splits, P.y_numel, P.Cout, P.scale, P.shift,
@@ -757,6 +844,14 @@ static int launch_nt(NtParams& P, long long pixel_tiles, int k_iters, void* ws_p
     DA_LAUNCH_CHECK();
   }
   return DA_OK;
+}
+static int launch_nt(NtParams& P, int bn, long long pixel_tiles, int k_iters, void* ws_part, size_t part_cap, cudaStream_t st) {
+  const bool pair = pixel_tiles >= 2;   // cluster of 2 CTAs sharing the weight tile through TMA multicast
+  if (bn == 256)
+    return pair ? launch_nt_t<256, 2>(P, pixel_tiles, k_iters, ws_part, part_cap, st)
+                : launch_nt_t<256, 1>(P, pixel_tiles, k_iters, ws_part, part_cap, st);
+  return pair ? launch_nt_t<128, 2>(P, pixel_tiles, k_iters, ws_part, part_cap, st)
+              : launch_nt_t<128, 1>(P, pixel_tiles, k_iters, ws_part, part_cap, st);
 }
 
 int umma_conv_forward(const da_conv_desc* d, const void* x, const void* w, const float* scale, const float* shift,
@@ -781,16 +876,10 @@ int umma_conv_forward(const da_conv_desc* d, const void* x, const void* w, const
   P.scale = scale; P.shift = shift; P.relu = relu; P.drop_p = drop_p; P.seed = seed; P.out_scale = 1.f;
   P.y = y; P.y_dtype = d->y_dtype; P.y_numel = (long long)g.N * g.OH * g.OW * g.Cout;
   const int Ktot = g.KH * g.KW * g.Cin;
+  const int bn = choose_bn(g.Cout);
   long long pixel_tiles;
   const __nv_bfloat16* xs[2] = {xh, xl};
   const __nv_bfloat16* wsrc[2] = {wh, wl};
-  for (int t = 0; t < (wl ? 2 : 1); ++t) {
-    const uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)g.Cout};
-    const uint64_t strides[1] = {(uint64_t)Ktot * 2};
-    const uint32_t box[2] = {BK, BN};
-    rc = encode_map(&P.b_map[t], wsrc[t], 2, dims, strides, box);
-    if (rc) return rc;
-  }
   if (is_flat(g)) {
     P.flat = 1;
     P.M_flat = (long long)g.N * g.H * g.W;
@@ -825,7 +914,15 @@ int umma_conv_forward(const da_conv_desc* d, const void* x, const void* w, const
     P.num_taps = nt;
     pixel_tiles = (long long)g.N * P.tiles_h * P.tiles_w;
   }
-  return launch_nt(P, pixel_tiles, P.num_terms * P.num_taps * P.kchunks, ws, part_bytes(g), st);
+  for (int t = 0; t < (wl ? 2 : 1); ++t) {
+    // a 2-CTA cluster (pixel_tiles >= 2, see launch_nt) loads the weight tile as two multicast halves
+    const uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)g.Cout};
+    const uint64_t strides[1] = {(uint64_t)Ktot * 2};
+    const uint32_t box[2] = {BK, (uint32_t)(pixel_tiles >= 2 ? bn / 2 : bn)};
+    rc = encode_map(&P.b_map[t], wsrc[t], 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  return launch_nt(P, bn, pixel_tiles, P.num_terms * P.num_taps * P.kchunks, ws, part_bytes(g), st);
 }
 
 int umma_conv_backward_data(const da_conv_desc* d, const void* dz, const void* w, float out_scale, void* dx, void* ws,
@@ -839,32 +936,27 @@ int umma_conv_backward_data(const da_conv_desc* d, const void* dz, const void* w
   const __nv_bfloat16 *zh, *zl;
   int rc = prep_operand(dz, d->x_dtype, (long long)g.N * g.OH * g.OW * g.Cout, d->engine, stage, &zh, &zl, st);
   if (rc) return rc;
-  // weights re-laid out as Wd[ci][tap][co] (K-major over (tap,co))
-  const size_t wn = (size_t)g.Cout * taps * g.Cin;
-  __nv_bfloat16* wdh = (__nv_bfloat16*)stage; stage += align_up(wn * 2, 256);
-  __nv_bfloat16* wdl = nullptr;
-  if (d->engine == DA_ENGINE_UMMA_BF16X3) { wdl = (__nv_bfloat16*)stage; stage += align_up(wn * 2, 256); }
-  {
-    dim3 grid((g.Cin + 31) / 32, (g.Cout + 31) / 32, taps);
-    if (d->x_dtype == DA_F32) weight_oti_to_ito_kernel<float><<<grid, dim3(32, 8), 0, st>>>((const float*)w, wdh, wdl, g.Cout, taps, g.Cin);
-    else weight_oti_to_ito_kernel<__nv_bfloat16><<<grid, dim3(32, 8), 0, st>>>((const __nv_bfloat16*)w, wdh, wdl, g.Cout, taps, g.Cin);
-    DA_LAUNCH_CHECK();
-  }
+  // B = the weights themselves, read UNtransposed as an MN-major operand: for tap t the B tile is
+  // W[co, t*Cin + ci] viewed as [k = co rows][n = ci contiguous] -> boxes of (64 ci, 64 co)
+  const __nv_bfloat16 *wh, *wl;
+  rc = prep_operand(w, d->x_dtype, (long long)g.Cout * taps * g.Cin, d->engine, stage, &wh, &wl, st);
+  if (rc) return rc;
   NtParams base;
   memset(&base, 0, sizeof(base));
   set_terms(d->engine, &base.num_terms, base.term_a, base.term_b);
+  base.b_mn_major = 1;
   base.kchunks = (g.Cout + BK - 1) / BK;
   base.Cout = g.Cin;  // GEMM N dimension = input channels
   base.OHf = g.H; base.OWf = g.W;
   base.relu = 0; base.drop_p = 0.f; base.out_scale = out_scale;
   base.y = dx; base.y_dtype = d->y_dtype; base.y_numel = (long long)g.N * g.H * g.W * g.Cin;
-  const int Ktot = taps * g.Cout;
-  const __nv_bfloat16* wsrc[2] = {wdh, wdl};
+  const int bn = choose_bn(g.Cin);
+  const __nv_bfloat16* wsrc[2] = {wh, wl};
   const __nv_bfloat16* zs[2] = {zh, zl};
-  for (int t = 0; t < (wdl ? 2 : 1); ++t) {
-    const uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)g.Cin};
-    const uint64_t strides[1] = {(uint64_t)Ktot * 2};
-    const uint32_t box[2] = {BK, BN};
+  for (int t = 0; t < (wl ? 2 : 1); ++t) {
+    const uint64_t dims[2] = {(uint64_t)taps * g.Cin, (uint64_t)g.Cout};
+    const uint64_t strides[1] = {(uint64_t)taps * g.Cin * 2};
+    const uint32_t box[2] = {64, 64};
     rc = encode_map(&base.b_map[t], wsrc[t], 2, dims, strides, box);
     if (rc) return rc;
   }
@@ -879,7 +971,7 @@ int umma_conv_backward_data(const da_conv_desc* d, const void* dz, const void* w
       rc = encode_map(&P.a_map[t][0], zs[t], 2, dims, strides, box);
       if (rc) return rc;
     }
-    return launch_nt(P, (P.M_flat + BM - 1) / BM, P.num_terms * P.kchunks, ws, part_bytes(g), st);
+    return launch_nt(P, bn, (P.M_flat + BM - 1) / BM, P.num_terms * P.kchunks, ws, part_bytes(g), st);
   }
   // one launch per input-pixel parity class (a,b): h = s*i + a, w = s*j + b
   for (int a = 0; a < g.s; ++a)
@@ -902,10 +994,10 @@ int umma_conv_backward_data(const da_conv_desc* d, const void* dz, const void* w
         for (int kw = 0; kw < g.KW; ++kw) {
           const int th = a + g.p - kh, tw = b + g.p - kw;  // oh = i + th/s when s | th
           if (posmod(th, g.s) != 0 || posmod(tw, g.s) != 0) continue;
-          P.taps[nt++] = TapInfo{0, floordiv(th, g.s), floordiv(tw, g.s), (kh * g.KW + kw) * g.Cout};
+          P.taps[nt++] = TapInfo{0, floordiv(th, g.s), floordiv(tw, g.s), (kh * g.KW + kw) * g.Cin};
         }
       P.num_taps = nt;
-      rc = launch_nt(P, (long long)g.N * P.tiles_h * P.tiles_w, P.num_terms * nt * P.kchunks, ws, part_bytes(g), st);
+      rc = launch_nt(P, bn, (long long)g.N * P.tiles_h * P.tiles_w, P.num_terms * nt * P.kchunks, ws, part_bytes(g), st);
       if (rc) return rc;
     }
   return DA_OK;
@@ -971,19 +1063,29 @@ int umma_conv_backward_weight(const da_conv_desc* d, const void* x, const void* 
     P.num_taps = nt;
     patches = (long long)g.N * P.tiles_h * P.tiles_w;
   }
-  const long long tiles = (long long)((g.Cout + BM - 1) / BM) * ((g.Cin + BN - 1) / BN) * P.num_taps;
+  const int bn = choose_bn(g.Cin);
+  const long long tiles = (long long)((g.Cout + BM - 1) / BM) * ((g.Cin + bn - 1) / bn) * P.num_taps;
   long long k_iters = patches * P.num_terms;
   int splits = pick_splits(tiles, (int)(k_iters > 1000000 ? 1000000 : k_iters));
   while (splits > 1 && (size_t)splits * P.dw_numel * sizeof(float) > part_bytes(g)) --splits;
   DA_REQUIRE(P.num_taps * splits <= 65535, DA_ERR_UNSUPPORTED, "umma wgrad: grid too large");
   P.dw = splits > 1 ? (float*)ws : dw;
-  static bool attr_set = false;
-  if (!attr_set) {
-    DA_CUDA_OK(cudaFuncSetAttribute(umma_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NT_SMEM));
-    attr_set = true;
+  dim3 grid((g.Cout + BM - 1) / BM, (g.Cin + bn - 1) / bn, P.num_taps * splits);
+  if (bn == 256) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      DA_CUDA_OK(cudaFuncSetAttribute(umma_tn_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<256>::SMEM));
+      attr_set = true;
+    }
+    umma_tn_kernel<256><<<grid, NT_THREADS, TileCfg<256>::SMEM, st>>>(P, splits);
+  } else {
+    static bool attr_set = false;
+    if (!attr_set) {
+      DA_CUDA_OK(cudaFuncSetAttribute(umma_tn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<128>::SMEM));
+      attr_set = true;
+    }
+    umma_tn_kernel<128><<<grid, NT_THREADS, TileCfg<128>::SMEM, st>>>(P, splits);
   }
-  dim3 grid((g.Cout + BM - 1) / BM, (g.Cin + BN - 1) / BN, P.num_taps * splits);
-  umma_tn_kernel<<<grid, NT_THREADS, NT_SMEM, st>>>(P, splits);
   DA_LAUNCH_CHECK();
   if (splits > 1) {
     sum_splits_kernel<<<ew_blocks(P.dw_numel), 256, 0, st>>>((const float*)ws, splits, P.dw_numel, dw);

@@ -372,6 +372,25 @@ def _conv_desc(N, H, W, Cin, Cout, KH, KW, stride, pad, engine, x_dtype, y_dtype
     return _lib.ConvDesc(N, H, W, Cin, Cout, KH, KW, stride, pad, _lib.ENGINES[engine], _code(x_dtype), _code(y_dtype))
 
 
+def bf16_shadow(w, refresh=False):
+    """bf16 copy of an fp32 weight, cached ON the parameter object together with the version it was
+    made from.  FusedSGD refreshes the copy inside its update kernel (without bumping the version),
+    so the steady-state train step never re-casts; any torch in-place update invalidates it."""
+    hit = getattr(w, "_da_shadow", None)
+    if hit is not None and not refresh and hit[0] == w._version and hit[1].shape == w.shape and hit[1].device == w.device:
+        return hit[1]
+    sh = torch.empty_like(w, dtype=torch.bfloat16)          # preserves strides (channels_last weights)
+    src = w.detach()
+    check(lib.da_cast(_ptr(src), _lib.DA_F32, _ptr(sh), _lib.DA_BF16, src.numel(), _stream()), "cast")
+    w._da_shadow = (w._version, sh)
+    return sh
+
+
+def _dense_memory(t):
+    """True when the tensor occupies one dense block (any permutation of dims)."""
+    return t.is_contiguous() or (t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last))
+
+
 def _w_ohwi(w):
     """Parameter [O,I,KH,KW] (or [O,I]) -> contiguous [O,KH,KW,I] view (zero-copy when the
     parameter is stored channels_last, which DenseConv does at construction)."""
@@ -388,14 +407,17 @@ class DenseLayerFunction(Function):
     is a head input) + wgrad + the two column sums that give d(scale), d(shift)."""
 
     @staticmethod
-    def forward(ctx, x, w, scale, shift, stride, pad, relu, drop_p, seed, engine, grl, out_dtype):
+    def forward(ctx, x, w, scale, shift, stride, pad, relu, drop_p, seed, engine, grl, out_dtype, shadow=None):
         _require_cuda(x, w)
         N, H, W_, Cin = x.shape
-        wv = _w_ohwi(w.detach())
-        Cout, KH, KW, _ = wv.shape
         x = x.contiguous()
-        if wv.dtype != x.dtype:
-            wv = cast(wv, x.dtype)
+        if shadow is not None:
+            wv = _w_ohwi(shadow)
+        else:
+            wv = _w_ohwi(w.detach())
+            if wv.dtype != x.dtype:
+                wv = cast(wv, x.dtype)
+        Cout, KH, KW, _ = wv.shape
         out_dtype = out_dtype or x.dtype
         OH = (H + 2 * pad - KH) // stride + 1
         OW = (W_ + 2 * pad - KW) // stride + 1
@@ -455,7 +477,7 @@ class DenseLayerFunction(Function):
             t = sh if sh is not None else torch.zeros_like(dshift)
             safe = torch.where(sc == 0, torch.ones_like(sc), sc)
             dscale = torch.where(sc == 0, torch.zeros_like(sc), (dvdot - t * dshift) / safe)
-        return dx, dw, dscale, (dshift if need_shift else None), None, None, None, None, None, None, None, None
+        return dx, dw, dscale, (dshift if need_shift else None), None, None, None, None, None, None, None, None, None
 
 
 def _umma_ok(x, w):
@@ -470,7 +492,10 @@ def dense_layer(x, w, scale=None, shift=None, stride=1, pad=0, relu=False, drop_
     engine = engine or get_engine()
     if engine != "simt_f32" and not (_umma_ok(x, w) and stride <= 2):
         engine = "simt_f32"  # shapes the tensor-core tiles cannot express (e.g. the 2-logit FC)
-    return DenseLayerFunction.apply(x, w, scale, shift, stride, pad, relu, drop_p, seed, engine, grl, out_dtype)
+    shadow = None
+    if w.dtype == torch.float32 and x.dtype == torch.bfloat16 and w.is_leaf and _dense_memory(w):
+        shadow = bf16_shadow(w)      # cached on the parameter; refreshed by FusedSGD
+    return DenseLayerFunction.apply(x, w, scale, shift, stride, pad, relu, drop_p, seed, engine, grl, out_dtype, shadow)
 
 
 def dropout_keep_mask(seed, shape, drop_p, device):
