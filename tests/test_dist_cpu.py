@@ -1,0 +1,63 @@
+"""Multi-process logic of the data-parallel path on CPU (gloo, world_size 2): pair sharding, the
+flat-buffer gradient all-reduce and the max-over-ranks timing reduction used by bench.py."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from unsupervised_domain_adaptation_object_detection_implementation_b200 import dist as ddist
+
+
+def test_shard_pairs_is_a_balanced_partition():
+    for pairs in (1, 2, 7, 8, 16, 17):
+        for world in (1, 2, 3, 4, 8):
+            parts = [ddist.shard_pairs(pairs, r, world) for r in range(world)]
+            flat = [p for part in parts for p in part]
+            assert flat == list(range(pairs))                      # complete, ordered, disjoint
+            sizes = [len(p) for p in parts]
+            assert max(sizes) - min(sizes) <= 1                    # balanced; a pair is never split
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    r, l, w = ddist.init_from_env("gloo")
+    assert (r, w) == (rank, world)
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Linear(16, 4), torch.nn.Linear(4, 3))
+    unused = list(model[2].parameters())                            # never receive a gradient (Q9/Q10 analogue)
+    params = ddist.trainable_parameters(model, unused)
+    assert len(params) == 4
+    x = torch.full((5, 8), float(rank + 1))
+    model[1](model[0](x)).sum().backward()
+    local = [p.grad.clone() for p in params]
+    params[3].grad = None                                           # a rank may miss a gradient: treated as zero
+    ddist.FlatGradAllReduce(params)()
+    gathered = [torch.zeros_like(torch.cat([g.reshape(-1) for g in local])) for _ in range(world)]
+    dist.all_gather(gathered, torch.cat([g.reshape(-1) for g in local]))
+    mine = torch.cat([p.grad.reshape(-1) for p in params])
+    tmax = ddist.max_over_ranks(10.0 * (rank + 1), torch.device("cpu"))
+    if rank == 0:
+        torch.save({"mine": mine, "gathered": gathered, "tmax": tmax, "n3": params[3].numel()}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_grad_allreduce_world2_gloo(tmp_path):
+    out = str(tmp_path / "r0.pt")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    rec = torch.load(out)
+    expect = (rec["gathered"][0] + rec["gathered"][1]) / 2
+    n3 = rec["n3"]
+    expect[-n3:] = 0.0                                               # both ranks dropped that gradient
+    assert torch.allclose(rec["mine"], expect, atol=1e-6)
+    assert rec["tmax"] == 20.0
