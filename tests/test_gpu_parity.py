@@ -5,6 +5,8 @@ Tolerances (BASELINE.json north_star): sampling grids / batch indices bit-exact;
 losses and gradients <= 1e-5 relative (to the max magnitude of the reference tensor) on the fp32
 engines; the tcgen05 bf16 engine is stated separately (bf16 inputs, fp32 accumulate: 2e-2).
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -59,13 +61,21 @@ def test_roi_align_layouts_dtypes_and_module_surface(golden):
     # legacy (aligned=False, sampling_ratio=2)
     out2 = F_.roi_align(feat, rois[:24], 7, scale, 2, False)
     assert rel_err(out2, g["out_legacy_sr2"]) <= FP32_TOL
-    # bf16 features: compare with the oracle evaluated on the bf16-rounded map (fp32 accumulation)
+    # bf16 features: compare with the oracle evaluated on the bf16-rounded map
     fb = feat.to(torch.bfloat16)
     ref, _, _ = oracle_roi.roi_align_forward(fb.float().cpu().numpy(), rois.cpu().numpy(), 7, scale)
+    # (a) tensor-core path (default for bf16): interpolation weights rounded to bf16, fp32 accumulate
     ob = F_.roi_align(fb, rois, 7, scale, 0, True, out_dtype=torch.float32)
-    assert rel_err(ob, torch.from_numpy(ref)) <= FP32_TOL
+    assert rel_err(ob, torch.from_numpy(ref)) <= 1e-2
     ob16 = F_.roi_align(fb, rois, 7, scale, 0, True)
     assert ob16.dtype == torch.bfloat16 and rel_err(ob16.float(), torch.from_numpy(ref)) <= 1e-2
+    # (b) CUDA-core path on the same bf16 features: fp32 weights and accumulation
+    os.environ["DA_ROI_NO_TC"] = "1"
+    try:
+        oc = F_.roi_align(fb, rois, 7, scale, 0, True, out_dtype=torch.float32)
+    finally:
+        del os.environ["DA_ROI_NO_TC"]
+    assert rel_err(oc, torch.from_numpy(ref)) <= FP32_TOL
 
 
 def test_roi_align_edge_cases():
@@ -129,6 +139,27 @@ def test_roi_align_full_size_properties():
     ref, _, _ = oracle_roi.roi_align_forward(f1[:1, :64].detach().cpu().numpy(), sub.cpu().numpy(), 7, 1 / 16)
     got = F_.roi_align(f1[:1, :64].detach().contiguous(), sub, 7, 1 / 16)
     assert rel_err(got, torch.from_numpy(ref)) <= FP32_TOL
+
+
+def test_roi_align_tensor_core_path_full_size():
+    """bf16 tensor-core forward at BASELINE config 4 size (+ adversarial RoIs that fall back to the CUDA-core
+    kernel): against the CUDA-core bf16 path everywhere, and against the oracle on a slice."""
+    N, C, H, W, R = 4, 2048, 64, 128, 2048
+    rois = torch.cat([seeded.synthetic_rois(R // N, N, H * 16, W * 16, 0), seeded.adversarial_rois(N, H * 16, W * 16)]).to(DEV)
+    g = torch.Generator(device=DEV).manual_seed(1)
+    f = torch.relu(torch.randn(N, H, W, C, device=DEV, generator=g)).to(torch.bfloat16).permute(0, 3, 1, 2)
+    tc = F_.roi_align(f, rois, 7, 1 / 16)
+    os.environ["DA_ROI_NO_TC"] = "1"
+    try:
+        cc = F_.roi_align(f, rois, 7, 1 / 16)
+    finally:
+        del os.environ["DA_ROI_NO_TC"]
+    assert tc.dtype == torch.bfloat16 and tc.shape == (rois.shape[0], C, 7, 7)
+    assert rel_err(tc.float(), cc.float()) <= 1e-2
+    sub = rois[-40:].clone()
+    ref, _, _ = oracle_roi.roi_align_forward(f[:, :96].float().cpu().numpy(), sub.cpu().numpy(), 7, 1 / 16)
+    got = F_.roi_align(f[:, :96].contiguous(memory_format=torch.channels_last), sub, 7, 1 / 16, out_dtype=torch.float32)
+    assert rel_err(got, torch.from_numpy(ref)) <= 1e-2
 
 
 def test_single_roi_extractor_and_level_mapping():

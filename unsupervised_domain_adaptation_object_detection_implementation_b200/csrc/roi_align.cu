@@ -19,26 +19,10 @@
 //     index order (deterministic), and writes every grad_input element exactly once.
 #include "da_common.cuh"
 #include "da_ptx.cuh"
+#include "roi_common.cuh"
+#include <stdlib.h>
 
 namespace da {
-
-constexpr int P = 7;          // pooled size supported by the register-tiled kernels
-constexpr int PP = P * P;     // 49
-constexpr int WROW = 8;       // floats per weight-table row (7 bins + pad)
-
-struct __align__(16) RoiMeta {
-  int b;        // batch index, -1 when invalid / out of range
-  int gh, gw;   // sampling grid (roi_bin_grid_h / _w)
-  int y_lo, ny; // first footprint row, number of rows (0 = empty)
-  int x_lo, nx;
-  int count;    // max(gh*gw,1)
-};
-
-// workspace layout: int err[4] | RoiMeta[R] | float tables[R][(H+W)*8]
-__host__ __device__ inline size_t ws_meta_off() { return 16; }
-__host__ __device__ inline size_t ws_table_off(int R) {
-  return 16 + ((size_t)R * sizeof(RoiMeta) + 255) / 256 * 256;
-}
 
 // One axis of the reference's sample enumeration.  Thread `bin` (0..6) walks its g samples.
 // Mode 0: return (min low index, max high index) of valid samples through lo/hi.
@@ -416,7 +400,7 @@ __host__ __device__ constexpr size_t fa_smem_bytes(int H, int W) {
 template <typename TIn, typename TOut, int kLayout>
 __global__ void __launch_bounds__(FA_THREADS, 2)
 roi_align_fwd_async_kernel(const TIn* __restrict__ feat, int C, int H, int W, int R,
-                           const unsigned char* __restrict__ ws, TOut* __restrict__ out) {
+                           const unsigned char* __restrict__ ws, TOut* __restrict__ out, int skip_tc) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int NSLOT = fa_slots<TIn>();
   constexpr int SLOT_BYTES = FA_SEG * FWD_CB * (int)sizeof(TIn);
@@ -433,6 +417,9 @@ roi_align_fwd_async_kernel(const TIn* __restrict__ feat, int C, int H, int W, in
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const RoiMeta m = reinterpret_cast<const RoiMeta*>(ws + ws_meta_off())[r];
   const int nch = min(FWD_CB, C - c0);
+  if (skip_tc) {   // this RoI is produced by the tensor-core kernel (roi_align_tc.cu)
+    if (roi_tc_eligible(m)) return;
+  }
 
   if (t == 0) {
     for (int i = 0; i < NSLOT; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, FA_CONSUMERS / 32); }
@@ -756,9 +743,14 @@ static int run_prep(const float* rois, int R, int N, int H, int W, float scale, 
 }
 
 template <typename TIn, typename TOut>
-static int launch_fwd(const void* feat, int C, int H, int W, int R, const void* ws, void* out,
+static int launch_fwd(const void* feat, int N, int C, int H, int W, int R, const void* ws, void* out,
                       int layout, cudaStream_t st) {
   dim3 grid((C + FWD_CB - 1) / FWD_CB, R);
+  // tensor-core path: bf16 features, reference layout, 16-byte granular channel runs
+  if (sizeof(TIn) == 2 && layout == DA_ROI_OUT_RCHW && C % 64 == 0 && ((uintptr_t)feat & 15) == 0 &&
+      ((uintptr_t)out & 15) == 0 && getenv("DA_ROI_NO_TC") == nullptr)
+    return roi_align_fwd_tc(feat, N, C, H, W, R, ws, out, sizeof(TOut) == 2 ? DA_BF16 : DA_F32, st);
+  const int skip_tc = 0;
   // bulk-async path: every per-pixel channel run and the result tile must be 16-byte granular
   const bool async_ok = ((size_t)C * sizeof(TIn)) % 16 == 0 && ((uintptr_t)feat & 15) == 0 &&
                         (layout == DA_ROI_OUT_RHWC || (((size_t)C * sizeof(TOut)) % 16 == 0 && ((uintptr_t)out & 15) == 0)) &&
@@ -768,11 +760,11 @@ static int launch_fwd(const void* feat, int C, int H, int W, int R, const void* 
     if (layout == DA_ROI_OUT_RCHW) {
       auto k = roi_align_fwd_async_kernel<TIn, TOut, DA_ROI_OUT_RCHW>;
       DA_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k<<<grid, FA_THREADS, smem, st>>>((const TIn*)feat, C, H, W, R, (const unsigned char*)ws, (TOut*)out);
+      k<<<grid, FA_THREADS, smem, st>>>((const TIn*)feat, C, H, W, R, (const unsigned char*)ws, (TOut*)out, skip_tc);
     } else {
       auto k = roi_align_fwd_async_kernel<TIn, TOut, DA_ROI_OUT_RHWC>;
       DA_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k<<<grid, FA_THREADS, smem, st>>>((const TIn*)feat, C, H, W, R, (const unsigned char*)ws, (TOut*)out);
+      k<<<grid, FA_THREADS, smem, st>>>((const TIn*)feat, C, H, W, R, (const unsigned char*)ws, (TOut*)out, 0);
     }
     DA_LAUNCH_CHECK();
     return DA_OK;
@@ -805,10 +797,10 @@ extern "C" int da_roi_align_forward(const void* feat, int feat_dtype, int N, int
   cudaStream_t st = (cudaStream_t)stream;
   rc = run_prep(rois, R, N, H, W, spatial_scale, sampling_ratio, aligned, workspace, grid_out, st);
   if (rc) return rc;
-  if (feat_dtype == DA_F32 && out_dtype == DA_F32) return launch_fwd<float, float>(feat, C, H, W, R, workspace, out, out_layout, st);
-  if (feat_dtype == DA_F32 && out_dtype == DA_BF16) return launch_fwd<float, __nv_bfloat16>(feat, C, H, W, R, workspace, out, out_layout, st);
-  if (feat_dtype == DA_BF16 && out_dtype == DA_F32) return launch_fwd<__nv_bfloat16, float>(feat, C, H, W, R, workspace, out, out_layout, st);
-  if (feat_dtype == DA_BF16 && out_dtype == DA_BF16) return launch_fwd<__nv_bfloat16, __nv_bfloat16>(feat, C, H, W, R, workspace, out, out_layout, st);
+  if (feat_dtype == DA_F32 && out_dtype == DA_F32) return launch_fwd<float, float>(feat, N, C, H, W, R, workspace, out, out_layout, st);
+  if (feat_dtype == DA_F32 && out_dtype == DA_BF16) return launch_fwd<float, __nv_bfloat16>(feat, N, C, H, W, R, workspace, out, out_layout, st);
+  if (feat_dtype == DA_BF16 && out_dtype == DA_F32) return launch_fwd<__nv_bfloat16, float>(feat, N, C, H, W, R, workspace, out, out_layout, st);
+  if (feat_dtype == DA_BF16 && out_dtype == DA_BF16) return launch_fwd<__nv_bfloat16, __nv_bfloat16>(feat, N, C, H, W, R, workspace, out, out_layout, st);
   DA_REQUIRE(false, DA_ERR_INVALID_ARG, "roi_align: bad dtype %d/%d", feat_dtype, out_dtype);
 }
 
