@@ -311,16 +311,24 @@ __global__ void pixel_head_bwd_kernel(const T* __restrict__ x, int64_t M, int K,
 
 __global__ void pixel_head_bwd_final_kernel(const float* __restrict__ partial, int nb, int K,
                                             float* __restrict__ dw, float* __restrict__ dbias) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < K && dw) {
-    float acc = 0.f;
-    for (int b = 0; b < nb; ++b) acc += partial[(size_t)b * K + k];
-    dw[k] = acc;
+  // block (32 columns x 32 row lanes); the last block column (k == K) reduces the bias partials
+  __shared__ float red[32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int k = blockIdx.x * 32 + tx;
+  float acc = 0.f;
+  if (k < K) {
+    for (int b = ty; b < nb; b += 32) acc += partial[(size_t)b * K + k];
+  } else if (k == K) {
+    for (int b = ty; b < nb; b += 32) acc += partial[(size_t)nb * K + b];
   }
-  if (k == 0 && dbias) {
-    float acc = 0.f;
-    for (int b = 0; b < nb; ++b) acc += partial[(size_t)nb * K + b];
-    dbias[0] = acc;
+  red[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) t += red[j][tx];
+    if (k < K && dw) dw[k] = t;
+    if (k == K && dbias) dbias[0] = t;
   }
 }
 
@@ -538,7 +546,7 @@ extern "C" int da_pixel_head_backward(const void* x, int x_dtype, int64_t M, int
   else DA_REQUIRE(false, DA_ERR_INVALID_ARG, "pixel_head_backward: bad dtype");
 #undef DA_PH_BWD
   DA_LAUNCH_CHECK();
-  pixel_head_bwd_final_kernel<<<(K + 255) / 256, 256, 0, st>>>(partial, nb, K, dw, dbias);
+  pixel_head_bwd_final_kernel<<<(K + 1 + 31) / 32, dim3(32, 32), 0, st>>>(partial, nb, K, dw, dbias);
   DA_LAUNCH_CHECK();
   return DA_OK;
 }

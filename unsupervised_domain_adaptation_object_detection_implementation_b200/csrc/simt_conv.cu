@@ -311,12 +311,22 @@ __global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y
     if (partial2) partial2[(size_t)blockIdx.x * C + c] = colsum2;
   }
 }
+// out[c] = sum_b partial[b][c]; block (32 columns x 32 row lanes), coalesced rows, smem tree over the lanes
 __global__ void colsum_final_kernel(const float* __restrict__ partial, int nb, int C, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  __shared__ float red[32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int c = blockIdx.x * 32 + tx;
   float acc = 0.f;
-  for (int b = 0; b < nb; ++b) acc += partial[(size_t)b * C + c];
-  out[c] = acc;
+  if (c < C)
+    for (int b = ty; b < nb; b += 32) acc += partial[(size_t)b * C + c];
+  red[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) t += red[j][tx];
+    out[c] = t;
+  }
 }
 
 static inline ConvGeom make_geom(const da_conv_desc* d) {
@@ -430,11 +440,11 @@ extern "C" int da_conv_act_backward(const da_conv_desc* d, const void* dy, const
   else DA_REQUIRE(false, DA_ERR_INVALID_ARG, "conv_act_backward: bad dtype");
   DA_LAUNCH_CHECK();
   if (dshift) {
-    colsum_final_kernel<<<(g.Cout + 255) / 256, 256, 0, st>>>(partial, nb, g.Cout, dshift);
+    colsum_final_kernel<<<(g.Cout + 31) / 32, dim3(32, 32), 0, st>>>(partial, nb, g.Cout, dshift);
     DA_LAUNCH_CHECK();
   }
   if (dvdot) {
-    colsum_final_kernel<<<(g.Cout + 255) / 256, 256, 0, st>>>(partial2, nb, g.Cout, dvdot);
+    colsum_final_kernel<<<(g.Cout + 31) / 32, dim3(32, 32), 0, st>>>(partial2, nb, g.Cout, dvdot);
     DA_LAUNCH_CHECK();
   }
   return DA_OK;

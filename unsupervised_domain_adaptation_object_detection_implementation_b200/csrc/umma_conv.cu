@@ -40,7 +40,7 @@ constexpr int MAX_TAPS = 16;
 template <int kBN> struct TileCfg {
   static constexpr int STAGES = (kBN == 256) ? 4 : 6;
   static constexpr int B_BYTES = kBN * BK * 2;
-  static constexpr size_t SMEM = 1024 + (size_t)STAGES * (A_BYTES + B_BYTES) + 256;
+  static constexpr size_t SMEM = 1024 + (size_t)STAGES * (A_BYTES + B_BYTES) + 256 + 4 * 4096;   // + epilogue staging
   static constexpr int TMEM_COLS = 2 * kBN;
 };
 
@@ -90,55 +90,79 @@ template <> struct Pack<__nv_bfloat16> {
   }
 };
 
-// Fused epilogue of one 32-column chunk of one accumulator row.
-__device__ __forceinline__ void nt_epilogue_row(const NtParams& P, const uint32_t* v, size_t row_off, int c_base,
-                                                bool raw_partial, float* partial) {
-  const int ncols = min(32, P.Cout - c_base);
+// Fused epilogue of one 32-column chunk of a warp's 32 accumulator rows.
+// Phase 1: every lane applies the epilogue to the 32 values of ITS row.  Phase 2: the warp transposes the
+// [32 rows][32 cols] chunk through a private shared-memory tile (16-byte pieces, XOR-swizzled) so that
+// each store instruction writes whole contiguous row segments (64 B bf16 / 128 B fp32 per row) instead
+// of 32 lanes hitting 32 different cache lines with 16 B each.
+__device__ __forceinline__ void nt_epilogue_chunk(const NtParams& P, const uint32_t* v, size_t row_off, bool valid,
+                                                  int c_base, bool raw_partial, float* partial, uint8_t* wstage,
+                                                  int lane) {
+  const int ncols = min(32, P.Cout - c_base);   // warp-uniform
   if (ncols <= 0) return;
   float f[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-  if (raw_partial) {
-    float* o = partial + row_off + c_base;
-    if (ncols == 32 && ((row_off + c_base) & 3) == 0) {
+  const bool out_f32 = raw_partial || P.y_dtype == DA_F32;
+  if (!raw_partial) {
+    const uint32_t thr = drop_threshold(P.drop_p);
+    const float keep_scale = P.drop_p > 0.f ? 1.f / (1.f - P.drop_p) : 1.f;
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-    } else {
-      for (int j = 0; j < ncols; ++j) o[j] = f[j];
+    for (int j = 0; j < 32; ++j) {
+      const int c = c_base + j;
+      float x = f[j] * P.out_scale;
+      if (j < ncols) {
+        if (P.scale) x *= __ldg(P.scale + c);
+        if (P.shift) x += __ldg(P.shift + c);
+      }
+      if (P.relu) x = fmaxf(x, 0.f);
+      if (P.drop_p > 0.f) x = (drop_hash(P.seed, (uint64_t)(row_off + c)) >= thr) ? x * keep_scale : 0.f;
+      f[j] = x;
+    }
+  }
+  uint8_t* gbase = raw_partial ? reinterpret_cast<uint8_t*>(partial) : reinterpret_cast<uint8_t*>(P.y);
+  const int es = out_f32 ? 4 : 2;
+  const bool fast = (ncols == 32) && ((P.Cout * es) % 16 == 0) && ((c_base * es) % 16 == 0) &&
+                    ((reinterpret_cast<uintptr_t>(gbase) & 15) == 0);
+  if (!fast) {   // ragged tail: plain per-row stores
+    if (valid) {
+      if (out_f32) { float* o = reinterpret_cast<float*>(gbase) + row_off + c_base; for (int j = 0; j < ncols; ++j) o[j] = f[j]; }
+      else { __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(gbase) + row_off + c_base; for (int j = 0; j < ncols; ++j) o[j] = __float2bfloat16_rn(f[j]); }
     }
     return;
   }
-  const uint32_t thr = drop_threshold(P.drop_p);
-  const float keep_scale = P.drop_p > 0.f ? 1.f / (1.f - P.drop_p) : 1.f;
+  // phase 2a: own row -> staging, 16-byte piece j at slot (j ^ (row & (npieces-1)))
+  const int npieces = out_f32 ? 8 : 4;          // 16-byte pieces per row
+  const int row_bytes = npieces * 16;
+  uint4* srow = reinterpret_cast<uint4*>(wstage + lane * row_bytes);
+  if (out_f32) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const int c = c_base + j;
-    float x = f[j] * P.out_scale;
-    if (j < ncols) {
-      if (P.scale) x *= __ldg(P.scale + c);
-      if (P.shift) x += __ldg(P.shift + c);
-    }
-    if (P.relu) x = fmaxf(x, 0.f);
-    if (P.drop_p > 0.f) x = (drop_hash(P.seed, (uint64_t)(row_off + c)) >= thr) ? x * keep_scale : 0.f;
-    f[j] = x;
-  }
-  if (P.y_dtype == DA_BF16) {
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(P.y) + row_off + c_base;
-    if (ncols == 32 && ((row_off + c_base) & 7) == 0) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) Pack<__nv_bfloat16>::store8(o + j, f + j);
-    } else {
-      for (int j = 0; j < ncols; ++j) o[j] = __float2bfloat16_rn(f[j]);
-    }
+    for (int j = 0; j < 8; ++j)
+      srow[j ^ (lane & 7)] = make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3]));
   } else {
-    float* o = reinterpret_cast<float*>(P.y) + row_off + c_base;
-    if (ncols == 32 && ((row_off + c_base) & 3) == 0) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-    } else {
-      for (int j = 0; j < ncols; ++j) o[j] = f[j];
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]), b = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
+      __nv_bfloat162 c = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]), d = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+      srow[j ^ (lane & 3)] = make_uint4(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b),
+                                        *reinterpret_cast<uint32_t*>(&c), *reinterpret_cast<uint32_t*>(&d));
     }
   }
+  __syncwarp();
+  // phase 2b: lanes cover contiguous row segments
+  const int rows_per_it = 32 / npieces;
+  const int sub = lane / npieces, piece = lane % npieces;
+  const unsigned long long my_off = valid ? (unsigned long long)row_off : ~0ull;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    if (it * rows_per_it >= 32) break;
+    const int row = it * rows_per_it + sub;
+    const unsigned long long roff = __shfl_sync(0xffffffffu, my_off, row);
+    const uint4 val = *reinterpret_cast<const uint4*>(wstage + row * row_bytes + ((piece ^ (row & (npieces - 1))) << 4));
+    if (roff != ~0ull)
+      *reinterpret_cast<uint4*>(gbase + (roff + c_base) * es + piece * 16) = val;
+  }
+  __syncwarp();
 }
 
 // Persistent kernel: grid = min(#tiles, #SMs); tile = (pixel tile, Cout tile, k-split).
@@ -158,6 +182,7 @@ umma_nt_kernel(const __grid_constant__ NtParams P, int pixel_tiles, int n_tiles,
   const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 16,
                  tslot = tempty0 + 16;
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  uint8_t* epi_stage = gen_base + (bars - base) + 256;   // 4 warps x 4 KB, 16-byte aligned
   volatile uint32_t* tslot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tslot - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -308,7 +333,7 @@ umma_nt_kernel(const __grid_constant__ NtParams P, int pixel_tiles, int n_tiles,
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0u;
         }
-        if (valid) nt_epilogue_row(P, v, row_off, c0 + cc * 32, raw, partial);
+        nt_epilogue_chunk(P, v, row_off, valid, c0 + cc * 32, raw, partial, epi_stage + q * 4096, lane);
       }
       tc_fence_before();
       __syncwarp();
