@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--engine", default="umma_bf16", choices=["umma_bf16", "umma_bf16x3", "simt_f32"])
     ap.add_argument("--pairs-per-gpu", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--cpu-budget-s", type=float, default=20.0)
     return ap.parse_args()
 
@@ -159,8 +160,49 @@ def run_ours(args):
         opt.zero_grad(set_to_none=True)
         return total
 
+    # The whole step (forward, backward, all-reduce excluded, SGD) is captured once into a CUDA graph and
+    # replayed: ~150 kernel launches per step are otherwise CPU-launch bound.  Dropout masks still change
+    # every replay through the device-resident seed counter (functional.dropout_counter).
+    F_.dropout_counter(dev)
+    static_c5 = torch.empty_like(resident[0][0])
+    static_bx = torch.empty_like(resident[0][1])
+    graph, graph_loss, graph_note = None, None, "eager"
+    launches_per_replay = [0]
+
+    def eager_step(c5_dev, boxes_dev):
+        F_.bump_dropout_counter(dev)
+        return step_on(c5_dev, boxes_dev)
+
+    if not args.no_graph and reducer is None:
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                static_c5.copy_(resident[0][0]); static_bx.copy_(resident[0][1])
+                for _ in range(3):
+                    eager_step(static_c5, static_bx)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            _lib.reset_launch_count()
+            with torch.cuda.graph(graph):
+                graph_loss = eager_step(static_c5, static_bx)
+            launches_per_replay[0] = _lib.launch_count()      # libda_b200 kernels inside one replayed step
+            graph_note = "cuda_graph"
+        except Exception as e:  # capture is an optimisation; the eager path is the same kernels
+            graph, graph_note = None, f"eager (graph capture failed: {type(e).__name__}: {str(e)[:120]})"
+            torch.cuda.synchronize()
+
+    def run_step(c5_dev, boxes_dev):
+        if graph is None:
+            return eager_step(c5_dev, boxes_dev)
+        static_c5.copy_(c5_dev, non_blocking=True)       # device->device, 67 MB
+        static_bx.copy_(boxes_dev, non_blocking=True)
+        graph.replay()
+        return graph_loss
+
     def step_resident(i):
-        return step_on(*resident[i % 2])
+        return run_step(*resident[i % 2])
 
     # e2e: every step's inputs come from pinned host memory.  The copy of step i+1 is issued on a side
     # stream into the other device buffer while step i computes (double buffering); the loss of every step
@@ -189,7 +231,7 @@ def run_ours(args):
         prefetch(i + 1)
         cur = torch.cuda.current_stream()
         cur.wait_event(ev_ready[slot])
-        loss = step_on(*dev_in[slot])
+        loss = run_step(*dev_in[slot])
         ev_free[slot].record(cur)
         loss_host.copy_(loss.reshape(1), non_blocking=True)
         cur.synchronize()                                   # the user reads the loss every step
@@ -215,7 +257,7 @@ def run_ours(args):
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
-        launches = _lib.launch_count()
+        launches = _lib.launch_count() if graph is None else launches_per_replay[0] * steps
         clocks = sampler.stop() if sampler else None
         return ddist.max_over_ranks(ms, dev), launches, clocks
 
@@ -237,7 +279,7 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.engine == "umma_bf16" else "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "pairs_per_gpu": pairs, "c5": [2 * pairs, C, H, W], "rois_per_img": ROIS_PER_IMG,
-                   "engine": args.engine, "step": "H1+L1, RoIAlign fwd/bwd, shared FCs, I1+L4, L7, backward, SGD",
+                   "engine": args.engine, "launch": graph_note, "step": "H1+L1, RoIAlign fwd/bwd, shared FCs, I1+L4, L7, backward, SGD",
                    "l2_policy": "inputs_and_weights_exceed_L2 (C5 67MB/pair bf16, FC1 weight 411MB, RoI features 205MB); two input sets alternated"},
         "e2e": {"value": round(e2e_value, 3), "unit": "img-pairs/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4,
                 "ms_per_step": round(ms_e2e / args.steps, 4)},

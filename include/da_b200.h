@@ -216,6 +216,9 @@ int da_conv_backward_weight(const da_conv_desc* d, const void* x, const void* dz
                             float* dw, void* workspace, size_t workspace_bytes,
                             da_stream_t stream);
 int da_dropout_mask(uint64_t seed, int64_t n, float drop_p, uint8_t* keep_out, da_stream_t stream);
+/* Optional device-resident uint64 step counter added to every dropout seed at kernel run time (NULL to
+ * disable): lets a CUDA-graph replay of a captured train step draw fresh masks. */
+int da_set_dropout_counter(const void* counter_dev);
 
 /* global average pool over H*W (F.avg_pool2d(x,(H,W)) at resnet_da_cbam.py:186, resnet_da.py:101):
  * x [N,H,W,C] -> y [N,C] fp32; backward broadcasts dy/(H*W). */

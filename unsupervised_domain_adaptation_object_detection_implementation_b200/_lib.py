@@ -75,6 +75,7 @@ SIGNATURES = {
     "da_conv_backward_data": (I, [CD, P, P, F, P, P, S, P]),
     "da_conv_backward_weight": (I, [CD, P, P, P, P, S, P]),
     "da_dropout_mask": (I, [U64, L, F, P, P]),
+    "da_set_dropout_counter": (I, [P]),
     "da_global_avgpool_workspace_bytes": (S, [I, I]),
     "da_global_avgpool_forward": (I, [P, I, I, I, I, P, P, S, P]),
     "da_global_avgpool_backward": (I, [P, I, I, I, P, I, P]),

@@ -18,6 +18,12 @@ namespace da {
 void set_error(const char* fmt, ...);
 extern std::atomic<int64_t> g_launches;
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+// Device-resident dropout step counter (da_set_dropout_counter): kernels add *counter to their seed, so a
+// CUDA-graph replay of a captured step still draws fresh masks when the host bumps the counter on device.
+extern const unsigned long long* g_seed_counter;
+__device__ __forceinline__ unsigned long long effective_seed(unsigned long long seed, const unsigned long long* ctr) {
+  return ctr ? seed + *ctr : seed;
+}
 
 #define DA_REQUIRE(cond, code, ...)            \
   do {                                         \

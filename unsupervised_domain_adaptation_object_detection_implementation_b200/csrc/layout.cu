@@ -9,6 +9,7 @@ namespace da {
 
 static thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
+const unsigned long long* g_seed_counter = nullptr;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -51,7 +52,8 @@ __global__ void split_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* 
   }
 }
 
-__global__ void dropout_mask_kernel(uint64_t seed, int64_t n, uint32_t thr, uint8_t* __restrict__ keep) {
+__global__ void dropout_mask_kernel(uint64_t seed0, const unsigned long long* ctr, int64_t n, uint32_t thr, uint8_t* __restrict__ keep) {
+  const uint64_t seed = effective_seed(seed0, ctr);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     keep[i] = drop_hash(seed, (uint64_t)i) >= thr ? 1 : 0;
 }
@@ -163,7 +165,7 @@ extern "C" int da_split_bf16(const float* src, void* hi, void* lo, int64_t n, da
 extern "C" int da_dropout_mask(uint64_t seed, int64_t n, float drop_p, uint8_t* keep_out, da_stream_t stream) {
   if (n == 0) return DA_OK;
   DA_REQUIRE(keep_out && n > 0 && drop_p >= 0.f && drop_p < 1.f, DA_ERR_INVALID_ARG, "dropout_mask: bad args");
-  dropout_mask_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(seed, n, drop_threshold(drop_p), keep_out);
+  dropout_mask_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(seed, g_seed_counter, n, drop_threshold(drop_p), keep_out);
   DA_LAUNCH_CHECK();
   return DA_OK;
 }
@@ -177,5 +179,10 @@ extern "C" int da_sgd_step(float* w, const float* grad, float* momentum_buf, int
   sgd_step_kernel<<<ew_blocks((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(w, grad, momentum_buf, n, lr, momentum, weight_decay,
                                                                            first_step, (__nv_bfloat16*)w_bf16);
   DA_LAUNCH_CHECK();
+  return DA_OK;
+}
+
+extern "C" int da_set_dropout_counter(const void* counter_dev) {
+  g_seed_counter = (const unsigned long long*)counter_dev;
   return DA_OK;
 }

@@ -50,7 +50,8 @@ template <typename T, typename TY>
 __global__ void __launch_bounds__(256)
 simt_conv_fwd_kernel(ConvGeom g, const T* __restrict__ x, const T* __restrict__ w,
                      const float* __restrict__ scale, const float* __restrict__ shift, int relu,
-                     float drop_p, uint64_t seed, TY* __restrict__ y) {
+                     float drop_p, uint64_t seed0, const unsigned long long* seed_ctr, TY* __restrict__ y) {
+  const uint64_t seed = effective_seed(seed0, seed_ctr);
   __shared__ __align__(16) float As[TK][LDS_];
   __shared__ __align__(16) float Bs[TK][LDS_];
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
@@ -285,8 +286,10 @@ __host__ __device__ inline int ab_rows(int64_t M) {
 }
 template <typename T>
 __global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, int64_t M, int C,
-                               const float* __restrict__ scale, int relu, float drop_p, uint64_t seed,
+                               const float* __restrict__ scale, int relu, float drop_p, uint64_t seed0,
+                               const unsigned long long* seed_ctr,
                                T* __restrict__ dz, float* __restrict__ partial, float* __restrict__ partial2) {
+  const uint64_t seed = effective_seed(seed0, seed_ctr);
   const int AB_ROWS = ab_rows(M);
   const int64_t m0 = (int64_t)blockIdx.x * AB_ROWS;
   const int64_t m1 = (m0 + AB_ROWS < M) ? m0 + AB_ROWS : M;
@@ -363,7 +366,7 @@ int simt_conv_forward(const da_conv_desc* d, const void* x, const void* w, const
   const ConvGeom g = make_geom(d);
   const int64_t M = (int64_t)g.N * g.OH * g.OW;
   dim3 grid((unsigned)((M + TM - 1) / TM), (g.Cout + TN - 1) / TN);
-#define DA_FWD(T, TY) simt_conv_fwd_kernel<T, TY><<<grid, 256, 0, st>>>(g, (const T*)x, (const T*)w, scale, shift, relu, drop_p, seed, (TY*)y)
+#define DA_FWD(T, TY) simt_conv_fwd_kernel<T, TY><<<grid, 256, 0, st>>>(g, (const T*)x, (const T*)w, scale, shift, relu, drop_p, seed, g_seed_counter, (TY*)y)
   if (d->x_dtype == DA_F32 && d->y_dtype == DA_F32) DA_FWD(float, float);
   else if (d->x_dtype == DA_F32 && d->y_dtype == DA_BF16) DA_FWD(float, __nv_bfloat16);
   else if (d->x_dtype == DA_BF16 && d->y_dtype == DA_F32) DA_FWD(__nv_bfloat16, float);
@@ -435,8 +438,8 @@ extern "C" int da_conv_act_backward(const da_conv_desc* d, const void* dy, const
     partial2 = partial + (size_t)nb * g.Cout;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (d->x_dtype == DA_F32) act_bwd_kernel<float><<<nb, 256, 0, st>>>((const float*)dy, (const float*)y, M, g.Cout, scale, relu, drop_p, drop_seed, (float*)dz, partial, dvdot ? partial2 : nullptr);
-  else if (d->x_dtype == DA_BF16) act_bwd_kernel<__nv_bfloat16><<<nb, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, M, g.Cout, scale, relu, drop_p, drop_seed, (__nv_bfloat16*)dz, partial, dvdot ? partial2 : nullptr);
+  if (d->x_dtype == DA_F32) act_bwd_kernel<float><<<nb, 256, 0, st>>>((const float*)dy, (const float*)y, M, g.Cout, scale, relu, drop_p, drop_seed, g_seed_counter, (float*)dz, partial, dvdot ? partial2 : nullptr);
+  else if (d->x_dtype == DA_BF16) act_bwd_kernel<__nv_bfloat16><<<nb, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, M, g.Cout, scale, relu, drop_p, drop_seed, g_seed_counter, (__nv_bfloat16*)dz, partial, dvdot ? partial2 : nullptr);
   else DA_REQUIRE(false, DA_ERR_INVALID_ARG, "conv_act_backward: bad dtype");
   DA_LAUNCH_CHECK();
   if (dshift) {

@@ -71,6 +71,7 @@ struct NtParams {
   int relu;
   float drop_p;
   unsigned long long seed;
+  const unsigned long long* seed_ctr;
   float out_scale;
   void* y;
   int y_dtype;
@@ -116,7 +117,7 @@ __device__ __forceinline__ void nt_epilogue_chunk(const NtParams& P, const uint3
         if (P.shift) x += __ldg(P.shift + c);
       }
       if (P.relu) x = fmaxf(x, 0.f);
-      if (P.drop_p > 0.f) x = (drop_hash(P.seed, (uint64_t)(row_off + c)) >= thr) ? x * keep_scale : 0.f;
+      if (P.drop_p > 0.f) x = (drop_hash(effective_seed(P.seed, P.seed_ctr), (uint64_t)(row_off + c)) >= thr) ? x * keep_scale : 0.f;
       f[j] = x;
     }
   }
@@ -351,7 +352,9 @@ umma_nt_kernel(const __grid_constant__ NtParams P, int pixel_tiles, int n_tiles,
 // split-K finish: y = epilogue(sum_s partial[s])
 __global__ void nt_splitk_finish_kernel(const float* __restrict__ partial, int splits, long long numel, int Cout,
                                         const float* __restrict__ scale, const float* __restrict__ shift, int relu,
-                                        float drop_p, unsigned long long seed, float out_scale, void* y, int y_dtype) {
+                                        float drop_p, unsigned long long seed0, const unsigned long long* seed_ctr,
+                                        float out_scale, void* y, int y_dtype) {
+  const unsigned long long seed = effective_seed(seed0, seed_ctr);
   const uint32_t thr = drop_threshold(drop_p);
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += (long long)gridDim.x * blockDim.x) {
@@ -775,7 +778,7 @@ static int launch_nt_t(NtParams& P, long long pixel_tiles, int k_iters, void* ws
   DA_LAUNCH_CHECK();
   if (splits > 1) {
     nt_splitk_finish_kernel<<<ew_blocks(P.y_numel), 256, 0, st>>>(P.partial, splits, P.y_numel, P.Cout, P.scale, P.shift,
-                                                                  P.relu, P.drop_p, P.seed, P.out_scale, P.y, P.y_dtype);
+                                                                  P.relu, P.drop_p, P.seed, P.seed_ctr, P.out_scale, P.y, P.y_dtype);
     DA_LAUNCH_CHECK();
   }
   return DA_OK;
@@ -808,7 +811,7 @@ int umma_conv_forward(const da_conv_desc* d, const void* x, const void* w, const
   set_terms(d->engine, &P.num_terms, P.term_a, P.term_b);
   P.kchunks = (g.Cin + BK - 1) / BK;
   P.Cout = g.Cout; P.OHf = g.OH; P.OWf = g.OW; P.os = 1; P.oa = 0; P.ob = 0;
-  P.scale = scale; P.shift = shift; P.relu = relu; P.drop_p = drop_p; P.seed = seed; P.out_scale = 1.f;
+  P.scale = scale; P.shift = shift; P.relu = relu; P.drop_p = drop_p; P.seed = seed; P.seed_ctr = g_seed_counter; P.out_scale = 1.f;
   P.y = y; P.y_dtype = d->y_dtype; P.y_numel = (long long)g.N * g.OH * g.OW * g.Cout;
   const int Ktot = g.KH * g.KW * g.Cin;
   const int bn = choose_bn(g.Cout);

@@ -498,6 +498,26 @@ def dense_layer(x, w, scale=None, shift=None, stride=1, pad=0, relu=False, drop_
     return DenseLayerFunction.apply(x, w, scale, shift, stride, pad, relu, drop_p, seed, engine, grl, out_dtype, shadow)
 
 
+_DROP_COUNTER = {}
+
+
+def dropout_counter(device):
+    """Device-resident uint64 step counter that every dropout kernel adds to its seed at run time.
+    `bump_dropout_counter` (one tiny device op, graph-capturable) advances it once per train step, so a
+    CUDA-graph replay draws fresh masks although the per-layer seeds are baked into the graph."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    t = _DROP_COUNTER.get(idx)
+    if t is None:
+        t = torch.zeros(1, dtype=torch.int64, device=device)
+        _DROP_COUNTER[idx] = t
+        check(lib.da_set_dropout_counter(_ptr(t)), "set_dropout_counter")
+    return t
+
+
+def bump_dropout_counter(device):
+    dropout_counter(device).add_(0x9E3779B97F4A7C15 >> 1)
+
+
 def dropout_keep_mask(seed, shape, drop_p, device):
     """The exact keep-mask the fused epilogues use (exported for the oracle)."""
     n = 1

@@ -18,6 +18,23 @@ from . import da_heads, da_losses, functional as F_
 from .roi_extractors import SingleRoIExtractor, bbox2roi
 
 
+_CONST = {}
+
+
+def domain_tensor(gt_da, device):
+    """Device copy of the per-image domain labels, cached per (labels, device): building it every step
+    would be a pageable host->device copy (a sync the reference pays at DAFaster_rcnn_Orig.py:119-122, and
+    illegal inside CUDA-graph capture)."""
+    if torch.is_tensor(gt_da):
+        return gt_da.to(device=device, dtype=torch.long)
+    key = (tuple(int(d) for d in gt_da), str(device))
+    t = _CONST.get(key)
+    if t is None:
+        t = torch.tensor(key[0], dtype=torch.long, device=device)
+        _CONST[key] = t
+    return t
+
+
 class SharedFCs(nn.Module):
     """Shared2FCBBoxHead's shared_fcs as used by forward_train_da
     (mmdet/models/roi_heads/bbox_heads/convfc_bbox_head.py:198-237): flatten(1) -> FC -> ReLU -> FC -> ReLU.
@@ -59,7 +76,7 @@ class DAFOrgHotPath(nn.Module):
     def forward_train(self, c5, proposal_list, gt_da):
         """c5 [N,C,H,W]; proposal_list: per-image [n_i,4] boxes (image 0 = source, 1 = target);
         gt_da: per-image domain (0/1).  Returns the reference's DA entries of the losses dict."""
-        gt_domain = torch.as_tensor(gt_da, device=c5.device).long()
+        gt_domain = domain_tensor(gt_da, c5.device)
         imgs_feat = self.da_head_top(c5)
         global_loss = da_losses.daf_image_loss(imgs_feat, gt_domain)
         rois = bbox2roi(proposal_list)
@@ -91,7 +108,7 @@ class CBAMHotPath(nn.Module):
         return self.da_head_mid.unused_parameters() + self.da_head_top.unused_parameters()
 
     def forward_train(self, c3, c4, c5, gt_da):
-        gt_domain = torch.as_tensor(gt_da, device=c5.device).long()
+        gt_domain = domain_tensor(gt_da, c5.device)
         local_feat = self.local_da_head_bottom(c3)
         g_mid, _ = da_losses.image_ce_loss(self.da_head_mid(c4), gt_domain, False)
         g_top, _ = da_losses.image_ce_loss(self.da_head_top(c5), gt_domain, False)
@@ -112,7 +129,7 @@ class MAFHotPath(nn.Module):
         self.global_lamda = global_lamda
 
     def forward_train(self, c3, c4, c5, gt_da):
-        gt_domain = torch.as_tensor(gt_da, device=c5.device).long()
+        gt_domain = domain_tensor(gt_da, c5.device)
         total = 0
         for head, feat in ((self.da_head_bottom, c3), (self.da_head_mid, c4), (self.da_head_top, c5)):
             loss, _ = da_losses.image_ce_loss(head.forward_logits(feat), gt_domain, True)
