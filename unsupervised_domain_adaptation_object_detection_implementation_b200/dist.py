@@ -68,6 +68,47 @@ class FlatGradAllReduce:
             off += n
 
 
+class OverlappedGradAllReduce:
+    """Gradient mean over ranks, overlapped with the rest of backward.
+
+    Large parameters (the 411 MB FC1 gradient dominates this path) are all-reduced on a side stream the
+    moment autograd has accumulated them (post-accumulate-grad hook), while RoIAlign backward and the
+    image-head backward still run; everything small goes through one flat buffer at the end.  NCCL's
+    AVG reduction does the division.  Works under CUDA-graph capture (the side stream forks and joins
+    inside the capture)."""
+
+    def __init__(self, params, big_numel=1 << 20):
+        self.params = list(params)
+        self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.big = [p for p in self.params if p.numel() >= big_numel]
+        self.small = [p for p in self.params if p.numel() < big_numel]
+        self.flat = FlatGradAllReduce(self.small) if self.small else None
+        self.comm_stream = None
+        self._handles = []
+        if self.active and self.params and self.params[0].is_cuda:
+            self.comm_stream = torch.cuda.Stream(device=self.params[0].device)
+            for p in self.big:
+                self._handles.append(p.register_post_accumulate_grad_hook(self._hook))
+        self.op = dist.ReduceOp.AVG if (self.params and self.params[0].is_cuda) else dist.ReduceOp.SUM
+
+    def _hook(self, p):
+        cur = torch.cuda.current_stream()
+        self.comm_stream.wait_stream(cur)
+        with torch.cuda.stream(self.comm_stream):
+            dist.all_reduce(p.grad, op=self.op)
+
+    def __call__(self):
+        """Call after backward: reduces the small parameters and joins the side stream."""
+        if not self.active:
+            return
+        if self.comm_stream is None:          # CPU / gloo: no overlap, no AVG
+            FlatGradAllReduce(self.params)()
+            return
+        if self.flat is not None:
+            self.flat()
+        torch.cuda.current_stream().wait_stream(self.comm_stream)
+
+
 def max_over_ranks(value, device):
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return float(value)
