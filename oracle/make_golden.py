@@ -127,9 +127,26 @@ def focal_case(ns):
     print("focal:", float(loss))
 
 
+def state_dict_surface(ns):
+    """Key -> shape of the reference DA backbones (trunk + DA heads) and instance heads: the checkpoint surface
+    (SURVEY.md Appendix C)."""
+    import json
+    common = dict(depth=50, num_stages=4, strides=(1, 2, 2, 1), dilations=(1, 1, 1, 2), out_indices=(3,),
+                  frozen_stages=1, norm_eval=True, style="pytorch")
+    out = {}
+    for name, cls in (("ResNet_DAF", ns.daf_org.ResNet_DAF), ("ResNet_DA", ns.maf.ResNet_DA),
+                      ("ResNet_DA_CBAM", ns.cbam.ResNet_DA_CBAM), ("ResNet_DA_Deep", ns.deep.ResNet_DA_Deep)):
+        out[name] = {k: list(v.shape) for k, v in cls(**common).state_dict().items()}
+    out["InstanceAlignmentHead"] = {k: list(v.shape) for k, v in ns.instance.InstanceAlignmentHead().state_dict().items()}
+    out["InstanceAlignmentHead_DAF"] = {k: list(v.shape) for k, v in ns.instance.InstanceAlignmentHead_DAF().state_dict().items()}
+    json.dump(out, open(os.path.join(OUT, "state_dict_surface.json"), "w"))
+    print("state_dict surface:", {k: len(v) for k, v in out.items()})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_loader.load()
+    state_dict_surface(ns)
     roi_align_case()
     fm = seeded.feature_map
     head_case("img_alignment", ns.daf_org.ImgAlignmentHead(64), fm("x.img", (2, 64, 6, 10)))

@@ -449,3 +449,47 @@ def test_fused_sgd_matches_torch_sgd_and_refreshes_shadow():
     sh = F_.bf16_shadow(ps[0])
     assert sh.dtype == torch.bfloat16 and sh.stride() == ps[0].stride()
     assert rel_err(sh.float(), ps[0]) <= 4e-3          # refreshed in the update kernel, no re-cast
+
+
+# ---------------------------------------------------------------------------- detectors: forward_train surface
+def _det_cfg(det_type, backbone_type):
+    cfg = uda.Config.fromfile(os.path.join(os.path.dirname(os.path.abspath(__file__)), "fixtures", "cfg", "experiment.py"))
+    cfg.model["type"] = det_type
+    cfg.model.backbone["type"] = backbone_type
+    return cfg
+
+
+@pytest.mark.parametrize("det,bb,keys", [
+    ("DAFasterRCNN_Org", "ResNet_DAF", {"local_da_loss", "globle_da_loss", "consistency_loss"}),
+    ("DAFasterRCNN", "ResNet_DA_CBAM", {"local_da_loss", "globle_da_loss", "patch_bottom_loss"}),
+    ("MAFasterRCNN", "ResNet_DA", {"local_da_loss", "globle_da_loss"}),
+    ("DAFasterRCNN_Deep", "ResNet_DA_Deep", {"local_da_loss", "globle_da_loss", "patch_bottom_loss"}),
+])
+def test_detectors_forward_train_losses_dict(det, bb, keys):
+    """build_detector(cfg.model) -> forward_train(img, img_metas, gt_bboxes, gt_labels, gt_da=...) returns the
+    reference's loss keys; train_step gives {loss, log_vars, num_samples}; backward reaches the
+    DA heads and the trunk through the GRL."""
+    torch.manual_seed(0)
+    cfg = _det_cfg(det, bb)
+    model = uda.build_detector(cfg.model)
+    # the reference's N(0, 0.001) head init leaves ReLU-terminated heads with zero gradients (Q17): use O(1) weights
+    seeded.fill_state_(model.backbone.da_head_top, 0, "det.top.")
+    model = model.to(DEV).train()
+    img = torch.randn(2, 3, 128, 192, device=DEV)
+    metas = [dict(img_shape=(128, 192, 3), pad_shape=(128, 192, 3), scale_factor=1.0, flip=False) for _ in range(2)]
+    gtb = [torch.tensor([[20., 30., 90., 100.], [100., 20., 180., 110.]], device=DEV), torch.tensor([[40., 40., 120., 120.]], device=DEV)]
+    gtl = [torch.tensor([0, 2], device=DEV), torch.tensor([1], device=DEV)]
+    losses = model.forward_train(img, metas, gtb, gtl, gt_da=[0, 1])
+    assert keys <= set(losses), set(losses)
+    assert {"loss_rpn_cls", "loss_rpn_bbox", "loss_cls", "loss_bbox", "acc"} <= set(losses)
+    out = model.train_step(dict(img=img, img_metas=metas, gt_bboxes=gtb, gt_labels=gtl, gt_da=[0, 1]), None)
+    assert set(out) == {"loss", "log_vars", "num_samples"} and out["num_samples"] == 2
+    assert torch.isfinite(out["loss"])
+    out["loss"].backward()
+    g = model.backbone.da_head_top.conv1.weight.grad
+    assert g is not None and torch.isfinite(g).all() and float(g.abs().sum()) > 0
+    assert model.backbone.layer4[0].conv1.weight.grad is not None          # reversed gradient reaches the trunk
+    unused = {id(p) for p in model.unused_parameters()}
+    for n, p in model.named_parameters():
+        if id(p) in unused:
+            assert p.grad is None, n
