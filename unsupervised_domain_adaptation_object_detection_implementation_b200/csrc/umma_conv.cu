@@ -32,7 +32,9 @@ namespace da {
 // ---------------------------------------------------------------------------------------
 constexpr int BM = 128, BK = 64;
 constexpr int A_BYTES = BM * BK * 2;
-constexpr int NT_THREADS = 192;
+constexpr int NT_THREADS = 192;      // weight-gradient kernel: TMA, MMA, 4 epilogue warps
+constexpr int NT_EPI_WARPS = 8;      // forward / data-gradient kernel: 8 epilogue warps (2 per TMEM lane quadrant)
+constexpr int NT_FWD_THREADS = 64 + 32 * NT_EPI_WARPS;
 constexpr int MAX_TAPS = 16;
 // Tile configuration: BN = 256 keeps the per-MMA shared-memory traffic (A 4 KB + B 8 KB per 128 cycles)
 // under the 128 B/clk SMEM port; BN = 128 serves narrow outputs.  Two TMEM accumulators (2*BN
@@ -40,7 +42,7 @@ constexpr int MAX_TAPS = 16;
 template <int kBN> struct TileCfg {
   static constexpr int STAGES = (kBN == 256) ? 4 : 6;
   static constexpr int B_BYTES = kBN * BK * 2;
-  static constexpr size_t SMEM = 1024 + (size_t)STAGES * (A_BYTES + B_BYTES) + 256 + 4 * 4096;   // + epilogue staging
+  static constexpr size_t SMEM = 1024 + (size_t)STAGES * (A_BYTES + B_BYTES) + 256 + NT_EPI_WARPS * 4096;   // + epilogue staging
   static constexpr int TMEM_COLS = 2 * kBN;
 };
 
@@ -105,7 +107,12 @@ __device__ __forceinline__ void nt_epilogue_chunk(const NtParams& P, const uint3
 #pragma unroll
   for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
   const bool out_f32 = raw_partial || P.y_dtype == DA_F32;
-  if (!raw_partial) {
+  const bool plain = !P.scale && !P.shift && !P.relu && P.drop_p <= 0.f;   // warp-uniform
+  if (!raw_partial && plain) {
+    const float os = P.out_scale;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] *= os;
+  } else if (!raw_partial) {
     const uint32_t thr = drop_threshold(P.drop_p);
     const float keep_scale = P.drop_p > 0.f ? 1.f / (1.f - P.drop_p) : 1.f;
 #pragma unroll
@@ -171,7 +178,7 @@ __device__ __forceinline__ void nt_epilogue_chunk(const NtParams& P, const uint3
 // k-split; each loads half of the shared B (weight) tile and TMA-multicasts it to both, which halves
 // the L2->SM weight traffic (the 128x256 tile is L2-bandwidth bound otherwise).
 template <int kBN, int kCluster>
-__global__ void __launch_bounds__(NT_THREADS, 1)
+__global__ void __launch_bounds__(NT_FWD_THREADS, 1)
 umma_nt_kernel(const __grid_constant__ NtParams P, int pixel_tiles, int n_tiles, int splits) {
   using Cfg = TileCfg<kBN>;
   constexpr int STAGES = Cfg::STAGES, B_BYTES = Cfg::B_BYTES;
@@ -183,7 +190,7 @@ umma_nt_kernel(const __grid_constant__ NtParams P, int pixel_tiles, int n_tiles,
   const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 16,
                  tslot = tempty0 + 16;
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
-  uint8_t* epi_stage = gen_base + (bars - base) + 256;   // 4 warps x 4 KB, 16-byte aligned
+  uint8_t* epi_stage = gen_base + (bars - base) + 256;   // NT_EPI_WARPS x 4 KB, 16-byte aligned
   volatile uint32_t* tslot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tslot - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -198,7 +205,7 @@ umma_nt_kernel(const __grid_constant__ NtParams P, int pixel_tiles, int n_tiles,
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, kCluster); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, NT_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tslot, Cfg::TMEM_COLS);
@@ -297,8 +304,9 @@ umma_nt_kernel(const __grid_constant__ NtParams P, int pixel_tiles, int n_tiles,
       }
     }
   } else {
-    // epilogue warps 2..5 -> TMEM lane quadrant (warp % 4)
+    // epilogue warps 2..9 -> TMEM lane quadrant (warp % 4); the two warps of a quadrant split the column chunks
     const int q = warp & 3;
+    const int ehalf = (warp - 2) >> 2;
     const int r = q * 32 + lane;  // accumulator row == pixel within the tile
     int tcount = 0;
     for (int tile = tile0; tile < total_tiles; tile += tile_step, ++tcount) {
@@ -325,7 +333,7 @@ umma_nt_kernel(const __grid_constant__ NtParams P, int pixel_tiles, int n_tiles,
       mbar_wait(tfull0 + 8 * buf, use & 1u);
       tc_fence_after();
 #pragma unroll 1
-      for (int cc = 0; cc < kBN / 32; ++cc) {
+      for (int cc = ehalf; cc < kBN / 32; cc += NT_EPI_WARPS / 4) {
         uint32_t v[32];
         if (has_k) {
           DA_TMEM_LD32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * kBN + cc * 32, v);
@@ -334,7 +342,7 @@ umma_nt_kernel(const __grid_constant__ NtParams P, int pixel_tiles, int n_tiles,
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0u;
         }
-        nt_epilogue_chunk(P, v, row_off, valid, c0 + cc * 32, raw, partial, epi_stage + q * 4096, lane);
+        nt_epilogue_chunk(P, v, row_off, valid, c0 + cc * 32, raw, partial, epi_stage + (warp - 2) * 4096, lane);
       }
       tc_fence_before();
       __syncwarp();
@@ -764,7 +772,7 @@ static int launch_nt_t(NtParams& P, long long pixel_tiles, int k_iters, void* ws
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(clusters * kCluster);
-  cfg.blockDim = dim3(NT_THREADS);
+  cfg.blockDim = dim3(NT_FWD_THREADS);
   cfg.dynamicSmemBytes = TileCfg<kBN>::SMEM;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
