@@ -300,13 +300,16 @@ def run_ours(args):
 
 
 def kernel_rooflines(dev, act, step_ms):
-    """Per-kernel timings of the hot kernels, each alone, CUDA events, inputs larger than L2 or L2
-    flushed between launches.  Returns (roofline of the dominant kernel, table)."""
+    """Per-kernel timings of the step's hot kernels AT THE STEP'S SIZES (one pair: 2 images, 1024 RoIs), each
+    alone, CUDA events on the launching stream, L2 flushed between launches.  Algorithmic bytes / flops per
+    launch are the DESIGN.md §4 figures.  Returns (roofline of the dominant kernel, table)."""
+    import ctypes
     from unsupervised_domain_adaptation_object_detection_implementation_b200 import functional as F_
+    from unsupervised_domain_adaptation_object_detection_implementation_b200._lib import lib, check
     pk = peaks()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     g = torch.Generator(device=dev).manual_seed(0)
-    N, R = 4, 2048   # BASELINE config 4: 4 images, 2048 RoIs
+    N, R = 2, 2 * ROIS_PER_IMG
     feat = torch.relu(torch.randn(N, H, W, C, device=dev, generator=g)).to(act).permute(0, 3, 1, 2)
     cpu_g = torch.Generator().manual_seed(1)
     u = torch.rand(R, 4, generator=cpu_g)
@@ -332,33 +335,56 @@ def kernel_rooflines(dev, act, step_ms):
         return sum(ts[:max(1, len(ts) // 2)]) / max(1, len(ts) // 2)
 
     table = {}
+
+    def hbm_row(name, t, nbytes, note=None):
+        table[name] = {"ms": round(t, 4), "bytes": nbytes, "gbs": round(nbytes / t / 1e6, 1),
+                       "frac": round(nbytes / t / 1e6 / pk["hbm_gbs"], 4)}
+        if note:
+            table[name]["note"] = note
+
+    def tensor_row(name, t, fl, note=None):
+        table[name] = {"ms": round(t, 4), "flops": fl, "tflops": round(fl / t / 1e9, 1), "frac": round(fl / t / 1e9 / pk["bf16_tflops"], 4)}
+        if note:
+            table[name]["note"] = note
+
+    # RoIAlign 7x7 forward / backward: pooled tensor + feature map, each touched once
     out = F_.roi_align(feat, rois, 7, 1.0 / STRIDE)
-    fwd_bytes = R * C * 49 * es + N * C * H * W * es + R * 20
-    t = time_it(lambda: F_.roi_align(feat, rois, 7, 1.0 / STRIDE))
-    table["roi_align_fwd"] = {"ms": round(t, 4), "bytes": fwd_bytes, "gbs": round(fwd_bytes / t / 1e6, 1),
-                              "frac": round(fwd_bytes / t / 1e6 / pk["hbm_gbs"], 4), "note": "incl. the RoI prep kernel"}
+    hbm_row("roi_align_fwd", time_it(lambda: F_.roi_align(feat, rois, 7, 1.0 / STRIDE)),
+            R * C * 49 * es + N * C * H * W * es + R * 20, "incl. the RoI prep kernel")
     gout = torch.randn(out.shape, device=dev, generator=g).to(out.dtype)
     fr = feat.detach().requires_grad_(True)
     o2 = F_.roi_align(fr, rois, 7, 1.0 / STRIDE)
-    bwd_bytes = R * C * 49 * es + N * C * H * W * 4 + R * 20
-    t = time_it(lambda: torch.autograd.grad(o2, fr, gout, retain_graph=True))
-    table["roi_align_bwd"] = {"ms": round(t, 4), "bytes": bwd_bytes, "gbs": round(bwd_bytes / t / 1e6, 1),
-                              "frac": round(bwd_bytes / t / 1e6 / pk["hbm_gbs"], 4)}
-    # H1 conv1: 1x1 2048->512 on one pair's C5 (M=16384)
-    x = torch.relu(torch.randn(2, H, W, C, device=dev, generator=g)).to(act)
-    w1 = (torch.randn(512, C, 1, 1, device=dev, generator=g) * C ** -0.5)
-    b1 = torch.zeros(512, device=dev)
-    fl = 2.0 * 2 * H * W * C * 512
-    t = time_it(lambda: F_.dense_layer(x, w1, None, b1, relu=True))
-    table["h1_conv1_fwd"] = {"ms": round(t, 4), "flops": fl, "tflops": round(fl / t / 1e9, 1), "frac": round(fl / t / 1e9 / pk["bf16_tflops"], 4),
-                             "note": "incl. the fp32->bf16 weight cast"}
-    # F1 FC1: [1024,100352] x [100352 -> 1024]
-    a = torch.randn(1024, 1, 1, C * 49, device=dev, generator=g).to(act)
-    wf = torch.randn(FC_OUT, C * 49, device=dev, generator=g) * (C * 49) ** -0.5
-    wf_act = wf.to(act)
-    fl = 2.0 * 1024 * C * 49 * FC_OUT
-    t = time_it(lambda: F_.dense_layer(a, wf_act, None, None, relu=True))
-    table["fc1_fwd"] = {"ms": round(t, 4), "flops": fl, "tflops": round(fl / t / 1e9, 1), "frac": round(fl / t / 1e9 / pk["bf16_tflops"], 4)}
+    hbm_row("roi_align_bwd", time_it(lambda: torch.autograd.grad(o2, fr, gout, retain_graph=True)),
+            R * C * 49 * es + N * C * H * W * es + R * 20, "incl. the RoI prep kernel")
+    del out, o2, gout, fr, feat
+    # FC1 of the shared head: [1024, 100352] x [100352 -> 1024], forward / data gradient / weight gradient
+    K = C * 49
+    x = torch.randn(R, 1, 1, K, device=dev, generator=g).to(torch.bfloat16)
+    w = (torch.randn(FC_OUT, K, device=dev, generator=g) * K ** -0.5).to(torch.bfloat16)
+    dz = torch.randn(R, 1, 1, FC_OUT, device=dev, generator=g).to(torch.bfloat16)
+    y = torch.empty(R, 1, 1, FC_OUT, device=dev, dtype=torch.bfloat16)
+    dx = torch.empty_like(x)
+    dw = torch.empty(FC_OUT, 1, 1, K, device=dev, dtype=torch.float32)
+    desc = F_._conv_desc(R, 1, 1, K, FC_OUT, 1, 1, 1, 0, "umma_bf16", torch.bfloat16, torch.bfloat16)
+    ws = F_.workspace(lib.da_conv_workspace_bytes(ctypes.byref(desc)), torch.device(dev), "conv")
+    P, S = F_._ptr, F_._stream
+    fl = 2.0 * R * K * FC_OUT
+    tensor_row("fc1_fwd", time_it(lambda: check(lib.da_conv_forward(ctypes.byref(desc), P(x), P(w), None, None, 1, 0.0, 0, P(y),
+                                                                     P(ws), ws.numel(), S()), "conv_forward")), fl)
+    tensor_row("fc1_dgrad", time_it(lambda: check(lib.da_conv_backward_data(ctypes.byref(desc), P(dz), P(w), 1.0, P(dx), P(ws),
+                                                                             ws.numel(), S()), "conv_backward_data")), fl)
+    tensor_row("fc1_wgrad", time_it(lambda: check(lib.da_conv_backward_weight(ctypes.byref(desc), P(x), P(dz), P(dw), P(ws),
+                                                                               ws.numel(), S()), "conv_backward_weight")), fl,
+               "incl. the split-K reduction")
+    del x, dx, y, dz
+    # fused SGD + bf16 shadow refresh over the FC1 weight: read w, grad, momentum; write w, momentum, shadow
+    n = FC_OUT * K
+    wf = torch.randn(n, device=dev, generator=g)
+    buf = torch.zeros(n, device=dev)
+    gradf = dw.view(-1)
+    shadow = w.view(-1)
+    hbm_row("sgd_step_fc1", time_it(lambda: check(lib.da_sgd_step(P(wf), P(gradf), P(buf), n, 0.01, 0.9, 1e-4, 0, P(shadow), S()), "sgd_step")),
+            n * (4 * 3 + 4 * 2 + 2))
     dom = max(table, key=lambda k: table[k]["ms"])
     d = table[dom]
     if "bytes" in d:

@@ -106,7 +106,7 @@ int da_roi_align_forward(const void* feat_nhwc, int feat_dtype, int N, int C, in
 int da_roi_align_backward(const void* grad_out, int grad_dtype, int out_layout,
                           const float* rois, int R, int pooled_h, int pooled_w,
                           float spatial_scale, int sampling_ratio, int aligned,
-                          float* grad_in_nhwc, int N, int C, int H, int W,
+                          void* grad_in_nhwc, int grad_in_dtype, int N, int C, int H, int W,
                           void* workspace, size_t workspace_bytes, da_stream_t stream);
 /* FPN level mapping, single_level_roi_extractor.py:36-55. levels_out int32 [R]. */
 int da_map_roi_levels(const float* rois, int R, int num_levels, float finest_scale,

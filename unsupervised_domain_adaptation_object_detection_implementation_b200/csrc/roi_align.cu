@@ -806,10 +806,16 @@ extern "C" int da_roi_align_forward(const void* feat, int feat_dtype, int N, int
 
 template <typename TG>
 static int launch_bwd(const void* g, int layout, int N, int C, int H, int W, int R, const void* ws,
-                      float* gin, cudaStream_t st) {
+                      void* gin_v, int gin_dtype, cudaStream_t st) {
   const int tiles_x = (W + BWD_TX - 1) / BWD_TX, tiles_y = (H + BWD_TY - 1) / BWD_TY;
   dim3 grid(tiles_x * tiles_y, (C + BWD_CB - 1) / BWD_CB, N);
   DA_REQUIRE(grid.y <= 65535 && grid.z <= 65535, DA_ERR_UNSUPPORTED, "roi_align_backward: grid too large");
+  // tensor-core path: bf16 gradients in the reference layout, 16-byte granular channel runs
+  if (sizeof(TG) == 2 && layout == DA_ROI_OUT_RCHW && C % 8 == 0 && ((uintptr_t)g & 15) == 0 && getenv("DA_ROI_NO_TC") == nullptr)
+    return roi_align_bwd_tc(g, N, C, H, W, R, ws, gin_v, gin_dtype, st);
+  DA_REQUIRE(gin_dtype == DA_F32, DA_ERR_UNSUPPORTED,
+             "roi_align_backward: bf16 grad_input needs the tensor-core path (bf16 [R,C,7,7] gradients, C %% 8 == 0)");
+  float* gin = static_cast<float*>(gin_v);
   const bool async_ok = ((size_t)C * sizeof(TG)) % 16 == 0 && ((uintptr_t)g & 15) == 0;
   if (async_ok) {
     const size_t smem = ba_smem_bytes<TG>();
@@ -843,21 +849,22 @@ static int launch_bwd(const void* g, int layout, int N, int C, int H, int W, int
 extern "C" int da_roi_align_backward(const void* grad_out, int grad_dtype, int out_layout,
                                      const float* rois, int R, int pooled_h, int pooled_w,
                                      float spatial_scale, int sampling_ratio, int aligned,
-                                     float* grad_in, int N, int C, int H, int W,
+                                     void* grad_in, int grad_in_dtype, int N, int C, int H, int W,
                                      void* workspace, size_t workspace_bytes, da_stream_t stream) {
   int rc = check_common(N, C, H, W, R, pooled_h, pooled_w, rois, workspace, workspace_bytes);
   if (rc) return rc;
   DA_REQUIRE(grad_in != nullptr, DA_ERR_INVALID_ARG, "roi_align_backward: grad_in is null");
+  DA_REQUIRE(grad_in_dtype == DA_F32 || grad_in_dtype == DA_BF16, DA_ERR_INVALID_ARG, "roi_align_backward: bad grad_in dtype %d", grad_in_dtype);
   cudaStream_t st = (cudaStream_t)stream;
   if (R == 0) {
-    DA_CUDA_OK(cudaMemsetAsync(grad_in, 0, (size_t)N * C * H * W * sizeof(float), st));
+    DA_CUDA_OK(cudaMemsetAsync(grad_in, 0, (size_t)N * C * H * W * (grad_in_dtype == DA_BF16 ? 2 : 4), st));
     return DA_OK;
   }
   DA_REQUIRE(grad_out != nullptr, DA_ERR_INVALID_ARG, "roi_align_backward: grad_out is null");
   rc = run_prep(rois, R, N, H, W, spatial_scale, sampling_ratio, aligned, workspace, nullptr, st);
   if (rc) return rc;
-  if (grad_dtype == DA_F32) return launch_bwd<float>(grad_out, out_layout, N, C, H, W, R, workspace, grad_in, st);
-  if (grad_dtype == DA_BF16) return launch_bwd<__nv_bfloat16>(grad_out, out_layout, N, C, H, W, R, workspace, grad_in, st);
+  if (grad_dtype == DA_F32) return launch_bwd<float>(grad_out, out_layout, N, C, H, W, R, workspace, grad_in, grad_in_dtype, st);
+  if (grad_dtype == DA_BF16) return launch_bwd<__nv_bfloat16>(grad_out, out_layout, N, C, H, W, R, workspace, grad_in, grad_in_dtype, st);
   DA_REQUIRE(false, DA_ERR_INVALID_ARG, "roi_align_backward: bad dtype %d", grad_dtype);
 }
 

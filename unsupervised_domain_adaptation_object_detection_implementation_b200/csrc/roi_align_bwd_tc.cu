@@ -1,0 +1,383 @@
+// RoIAlign backward on the tensor cores (bf16 gradients, [R,C,7,7] layout) — sm_100a.
+//
+//   grad_in[pix, c] = sum_{r touching pix} sum_bin Wt_r[pix, bin] * g[r, c, bin]
+//
+// Gather formulation, no atomics: CTA = (image, 16x16 pixel tile, 256 channels) owns its slice of
+// grad_input as TWO fp32 accumulators D[128 ch x 256 px] in TMEM (512 columns) and walks the RoIs that
+// touch the tile in index order (deterministic).  Per RoI one K = 64 (49 bins, zero padded) contraction:
+//   A = g[r, c0:c0+128, :]   [128 ch x 64 bins]  K-major  (bulk-copied raw, re-laid out to the 128B swizzle)
+//   B = Wt_r^T               [256 px x 64 bins]  K-major  (built from the prep kernel's Wy/Wx tables)
+// Roles: warp 0 = bulk-copy producer (gradient chunks + table slices, 3-deep ring), warp 1 = MMA issuer,
+// warps 2..17 = operand builders (double-buffered operand tiles) and, at the end, the epilogue that streams
+// TMEM to grad_input NHWC (lanes = consecutive channels: 128 B coalesced stores, every element written once).
+// The CUDA-core kernel (roi_align.cu) measured 8 % of HBM peak, issue bound (profiles/r01_roi_align_ncu.md).
+#include <stdlib.h>
+#include "da_common.cuh"
+#include "da_ptx.cuh"
+#include "roi_common.cuh"
+
+namespace da {
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long v;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+  return v;
+}
+
+constexpr int BT_TY = 16, BT_TX = 16, BT_PX = BT_TY * BT_TX;   // 256 pixels = UMMA N
+constexpr int BT_CH = 256;                                      // channels per CTA = 2 accumulators of 128
+constexpr int BT_BUILDERS = 512;                                // warps 2..17: two half-rows per operand row
+constexpr int BT_THREADS = 64 + BT_BUILDERS;
+constexpr int BT_LIST = 1024;
+constexpr int BT_WARPS = BT_THREADS / 32;
+constexpr int BT_ROUNDS = (BT_LIST + BT_THREADS - 1) / BT_THREADS;
+constexpr int BT_A_BYTES = 128 * 128;                           // [128 ch][64 bins] bf16
+constexpr int BT_B_BYTES = BT_PX * 128;                         // [256 px][64 bins] bf16
+constexpr int BT_OPS_BYTES = 2 * BT_A_BYTES + BT_B_BYTES;       // one operand set: 64 KB
+constexpr int BT_RAW_G = BT_CH * PP * 2;                        // 25088 B
+constexpr int BT_RAW_BYTES = 64 + BT_RAW_G + (BT_TY + BT_TX) * WROW * 4 + 64;   // header | g | wy | wx  (26240, 128-multiple)
+constexpr int BT_NRAW = 3;                                     // raw ring depth (copy latency ~3 pair times)
+constexpr size_t BT_SMEM = 1024 + 2 * (size_t)BT_OPS_BYTES + BT_NRAW * (size_t)BT_RAW_BYTES + BT_LIST * 4 + 256;
+
+template <typename TO>
+__global__ void __launch_bounds__(BT_THREADS, 1)
+roi_align_bwd_tc_kernel(const __nv_bfloat16* __restrict__ grad_out, int C, int H, int W, int R,
+                        const unsigned char* __restrict__ ws, TO* __restrict__ grad_in, int tiles_x, int dbg, unsigned long long* trace) {
+  if (dbg & 32) return;
+  unsigned long long tr0 = 0, tr1 = 0, tr2 = 0, tr3 = 0;
+  unsigned long long* ptrace = (trace && blockIdx.x == 13 && blockIdx.y == 1 && blockIdx.z == 1) ? trace + 8 * (size_t)gridDim.x * gridDim.y * gridDim.z : nullptr;
+#define PSTAMP(pair, k) do { if (ptrace && (pair) < 64) ptrace[(pair) * 8 + (k)] = globaltimer_ns(); } while (0)
+  if (trace && threadIdx.x == 64) tr0 = globaltimer_ns();
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t ops0 = base;                                   // [2][A0 | A1 | B]
+  const uint32_t raw0 = ops0 + 2 * BT_OPS_BYTES;                // [2] raw slots
+  int* list = reinterpret_cast<int*>(gen + 2 * BT_OPS_BYTES + BT_NRAW * BT_RAW_BYTES);
+  const uint32_t bars = smem_u32(list + BT_LIST);
+  const uint32_t raw_full0 = bars, raw_empty0 = bars + 32, ops_ready0 = bars + 64, ops_free0 = bars + 80,
+                 tfull = bars + 96, tslot = bars + 104;
+  volatile uint32_t* tslot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tslot - base));
+  __shared__ int s_wcount[BT_ROUNDS * BT_WARPS];
+
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * BT_CH;
+  const int ty0 = (blockIdx.x / tiles_x) * BT_TY, tx0 = (blockIdx.x % tiles_x) * BT_TX;
+  const int ty1 = min(ty0 + BT_TY, H), tx1 = min(tx0 + BT_TX, W);
+  const RoiMeta* metas = reinterpret_cast<const RoiMeta*>(ws + ws_meta_off());
+  const float* tables = reinterpret_cast<const float*>(ws + ws_table_off(R));
+  const int nch = min(BT_CH, C - c0);
+
+  if (t == 0) {
+    for (int i = 0; i < BT_NRAW; ++i) {
+      mbar_init(raw_full0 + 8 * i, 1);
+      mbar_init(raw_empty0 + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(ops_ready0 + 8 * i, 1);
+      mbar_init(ops_free0 + 8 * i, 1);
+    }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tslot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tslot_ptr;
+
+  int seq = 0;  // pairs processed so far (same in every thread)
+  for (int rbase = 0; rbase < R; rbase += BT_LIST) {
+    // ---- ordered compaction of the RoIs of image b that touch this tile: all loads in flight first, then
+    // one ballot per round, a shared prefix over (round, warp) counts, two block barriers per chunk
+    const int rend = min(rbase + BT_LIST, R);
+    bool hit[BT_ROUNDS];
+    unsigned bal[BT_ROUNDS];
+#pragma unroll
+    for (int k = 0; k < BT_ROUNDS; ++k) {
+      const int r = rbase + k * BT_THREADS + t;
+      hit[k] = false;
+      if (r < rend) {
+        const RoiMeta m = metas[r];
+        hit[k] = (m.b == b) && m.ny > 0 && m.y_lo < ty1 && m.y_lo + m.ny > ty0 && m.x_lo < tx1 && m.x_lo + m.nx > tx0;
+      }
+    }
+    __syncthreads();   // previous chunk's list / counts are no longer read
+#pragma unroll
+    for (int k = 0; k < BT_ROUNDS; ++k) {
+      bal[k] = __ballot_sync(0xffffffffu, hit[k]);
+      if (lane == 0) s_wcount[k * BT_WARPS + warp] = __popc(bal[k]);
+    }
+    __syncthreads();
+    int total = 0;
+#pragma unroll
+    for (int k = 0; k < BT_ROUNDS; ++k) {
+      int off = total;
+      for (int w = 0; w < BT_WARPS; ++w) {
+        const int cnt = s_wcount[k * BT_WARPS + w];
+        if (w < warp) off += cnt;
+        total += cnt;
+      }
+      if (hit[k]) list[off + __popc(bal[k] & ((1u << lane) - 1u))] = rbase + k * BT_THREADS + t;
+    }
+    __syncthreads();
+    const int n_list = (dbg & 64) ? 0 : total;
+    if (trace && threadIdx.x == 64 && rbase == 0) tr1 = globaltimer_ns();
+
+    if (warp == 0) {
+      // ------------------------------------------------ producer: raw gradient chunks + table slices
+      int my_r = 0;
+      RoiMeta my_m = {};
+      for (int li = 0; li < n_list; ++li) {
+        const int sq = seq + li, slot = sq % BT_NRAW;
+        const uint32_t par = (uint32_t)(sq / BT_NRAW) & 1u;
+        if ((li & 31) == 0 && li + lane < n_list) {   // 32 metas per L2 round trip, off the ring's critical path
+          my_r = list[li + lane];
+          my_m = metas[my_r];
+        }
+        const int src = li & 31;
+        const int r = __shfl_sync(0xffffffffu, my_r, src);
+        RoiMeta m;
+        m.y_lo = __shfl_sync(0xffffffffu, my_m.y_lo, src);
+        m.ny = __shfl_sync(0xffffffffu, my_m.ny, src);
+        m.x_lo = __shfl_sync(0xffffffffu, my_m.x_lo, src);
+        m.nx = __shfl_sync(0xffffffffu, my_m.nx, src);
+        m.count = __shfl_sync(0xffffffffu, my_m.count, src);
+        const int ya = max(m.y_lo, ty0), yb = min(m.y_lo + m.ny, ty1);
+        const int xa = max(m.x_lo, tx0), xb = min(m.x_lo + m.nx, tx1);
+        mbar_wait(raw_empty0 + 8 * slot, par ^ 1u);
+        if (lane == 0) PSTAMP(sq, 0);
+        uint8_t* sl = gen + 2 * BT_OPS_BYTES + slot * BT_RAW_BYTES;
+        const uint32_t g_bytes = (dbg & 16) ? 16u : (uint32_t)(nch * PP * 2);
+        const uint32_t fb = raw_full0 + 8 * slot;
+        if (lane == 0) {
+          int* hdr = reinterpret_cast<int*>(sl);
+          hdr[0] = ya; hdr[1] = yb; hdr[2] = xa; hdr[3] = xb;
+          reinterpret_cast<float*>(sl)[4] = 1.f / (float)m.count;
+          mbar_expect_tx(fb, g_bytes + (uint32_t)((yb - ya) + (xb - xa)) * WROW * 4);
+        }
+        __syncwarp();
+        const float* tab = tables + (size_t)r * (H + W) * WROW;
+        const uint32_t sbase = raw0 + slot * BT_RAW_BYTES + 64;
+        if (lane == 0) bulk_g2s(sbase, grad_out + ((size_t)r * C + c0) * PP, g_bytes, fb);
+        if (lane == 1) bulk_g2s(sbase + BT_RAW_G, tab + (size_t)(ya - m.y_lo) * WROW, (uint32_t)(yb - ya) * WROW * 4, fb);
+        if (lane == 2) bulk_g2s(sbase + BT_RAW_G + BT_TY * WROW * 4, tab + (size_t)H * WROW + (size_t)(xa - m.x_lo) * WROW,
+                                (uint32_t)(xb - xa) * WROW * 4, fb);
+      }
+    } else if (warp == 1) {
+      // ------------------------------------------------ MMA issuer
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc(128, BT_PX, 0, 0);
+        for (int li = 0; li < n_list; ++li) {
+          const int sq = seq + li, ob = sq & 1;
+          const uint32_t par = (uint32_t)(sq >> 1) & 1u;
+          mbar_wait(ops_ready0 + 8 * ob, par);
+          PSTAMP(sq, 1);
+          tc_fence_after();
+          const uint32_t ops = ops0 + ob * BT_OPS_BYTES;
+          const uint64_t bd = desc_kmajor_sw128(ops + 2 * BT_A_BYTES);
+#pragma unroll
+          for (int cb = 0; cb < 2; ++cb) {
+            const uint64_t ad = desc_kmajor_sw128(ops + cb * BT_A_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              if (!(dbg & 1)) umma_bf16(tmem_base + cb * BT_PX, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc, (sq > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(ops_free0 + 8 * ob);
+          PSTAMP(sq, 2);
+        }
+      }
+    } else {
+      // ------------------------------------------------ operand builders (512 threads)
+      // thread = (operand row, 64-byte half of its 128-byte K row); halves are warp-uniform
+      const int bt = t - 64, half = bt >> 8, row = bt & 255;
+      for (int li = 0; li < n_list; ++li) {
+        const int sq = seq + li, slot = sq % BT_NRAW, ob = sq & 1;
+        mbar_wait(raw_full0 + 8 * slot, (uint32_t)(sq / BT_NRAW) & 1u);
+        if (bt == 0) PSTAMP(sq, 3);
+        mbar_wait(ops_free0 + 8 * ob, ((uint32_t)(sq >> 1) & 1u) ^ 1u);
+        if (bt == 0) PSTAMP(sq, 4);
+        const uint8_t* sl = gen + 2 * BT_OPS_BYTES + slot * BT_RAW_BYTES;
+        const int* hdr = reinterpret_cast<const int*>(sl);
+        const int ya = hdr[0], yb = hdr[1], xa = hdr[2], xb = hdr[3];
+        const float inv_count = reinterpret_cast<const float*>(sl)[4];
+        const float* wy_s = reinterpret_cast<const float*>(sl + 64 + BT_RAW_G);
+        const float* wx_s = wy_s + BT_TY * WROW;
+        uint8_t* ops = gen + ob * BT_OPS_BYTES;
+        // (1) A: 49 bf16 of channel `row` -> 64 (zero padded), 128B-swizzled K-major row.  Rows start on
+        // 2-byte boundaries (98 B pitch): read aligned words and funnel-shift by 0 or 16 bits.
+        {
+          const int cb = row >> 7, mrow = row & 127;
+          uint32_t pk[16];
+          if (row < nch && !(dbg & 2)) {
+            const uint32_t byte0 = (uint32_t)row * (PP * 2) + (uint32_t)half * 64u;
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(sl + 64 + (byte0 & ~3u));
+            const uint32_t sh = (byte0 & 2u) * 8u;
+            if (half == 0) {
+              uint32_t w[17];
+#pragma unroll
+              for (int j = 0; j < 17; ++j) w[j] = src[j];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) pk[j] = __funnelshift_r(w[j], w[j + 1], sh);
+            } else {
+              uint32_t w[10];
+#pragma unroll
+              for (int j = 0; j < 10; ++j) w[j] = src[j];
+#pragma unroll
+              for (int j = 0; j < 9; ++j) pk[j] = __funnelshift_r(w[j], w[j + 1], sh);
+              pk[8] &= 0xFFFFu;  // element 48 | pad
+#pragma unroll
+              for (int j = 9; j < 16; ++j) pk[j] = 0u;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pk[j] = 0u;
+          }
+          uint8_t* arow = ops + cb * BT_A_BYTES + (mrow >> 3) * 1024 + (mrow & 7) * 128;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            *reinterpret_cast<uint4*>(arow + (((half * 4 + k) ^ (mrow & 7)) << 4)) = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+        }
+        // (2) B: Wt[px][bin] = Wy[y][ph] * Wx[x][pw] / count inside the footprint, else 0
+        {
+          const int y = ty0 + (row >> 4), x = tx0 + (row & 15);
+          const bool in = (y >= ya) && (y < yb) && (x >= xa) && (x < xb);
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = 0u;
+          if (in && !(dbg & 4)) {
+            const float4 wa = reinterpret_cast<const float4*>(wy_s)[(y - ya) * 2], wb = reinterpret_cast<const float4*>(wy_s)[(y - ya) * 2 + 1];
+            const float4 xa4 = reinterpret_cast<const float4*>(wx_s)[(x - xa) * 2], xb4 = reinterpret_cast<const float4*>(wx_s)[(x - xa) * 2 + 1];
+            const float wyv[P] = {wa.x * inv_count, wa.y * inv_count, wa.z * inv_count, wa.w * inv_count,
+                                  wb.x * inv_count, wb.y * inv_count, wb.z * inv_count};
+            const float wxv[P] = {xa4.x, xa4.y, xa4.z, xa4.w, xb4.x, xb4.y, xb4.z};
+            if (half == 0) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int n0 = 2 * j, n1 = 2 * j + 1;
+                __nv_bfloat162 v = __floats2bfloat162_rn(wyv[n0 / P] * wxv[n0 % P], wyv[n1 / P] * wxv[n1 % P]);
+                pk[j] = *reinterpret_cast<uint32_t*>(&v);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 9; ++j) {
+                const int n0 = 32 + 2 * j, n1 = 33 + 2 * j;
+                const float v1 = (n1 < PP) ? wyv[(n1 < PP ? n1 : 0) / P] * wxv[n1 % P] : 0.f;
+                __nv_bfloat162 v = __floats2bfloat162_rn(wyv[n0 / P] * wxv[n0 % P], v1);
+                pk[j] = *reinterpret_cast<uint32_t*>(&v);
+              }
+            }
+          }
+          uint8_t* brow = ops + 2 * BT_A_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            *reinterpret_cast<uint4*>(brow + (((half * 4 + k) ^ (row & 7)) << 4)) = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+        }
+        if (bt == 0) PSTAMP(sq, 5);
+        fence_proxy_async();
+        named_bar_sync(2, BT_BUILDERS);
+        if (bt == 0) PSTAMP(sq, 6);
+        if (bt == 0) {
+          mbar_arrive(ops_ready0 + 8 * ob);
+          mbar_arrive(raw_empty0 + 8 * slot);
+        }
+      }
+    }
+    seq += n_list;
+  }
+
+  if (trace && threadIdx.x == 64) tr2 = globaltimer_ns();
+  // ---- epilogue: TMEM -> grad_input (or zeros when no RoI touches the tile)
+  if (warp == 1 && lane == 0 && seq > 0) umma_commit(tfull);
+  if (warp >= 2) {
+    const int q = warp & 3, cb = ((warp - 2) >> 2) & 1, chalf = (warp - 2) >> 3;   // TMEM quadrant, accumulator, pixel half
+    const int c = c0 + cb * 128 + q * 32 + lane;
+    if (seq > 0) {
+      mbar_wait(tfull, 0);
+      tc_fence_after();
+    }
+    if (trace && threadIdx.x == 64) tr3 = globaltimer_ns();
+#pragma unroll 1
+    for (int cc = chalf * (BT_PX / 64); cc < (chalf + 1) * (BT_PX / 64); ++cc) {
+      uint32_t v[32];
+      if (seq > 0) {
+        DA_TMEM_LD32(tmem_base + ((uint32_t)(q * 32) << 16) + cb * BT_PX + cc * 32, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      if constexpr (sizeof(TO) == 2) {
+        // bf16: transpose through the (now idle) operand buffers to stage[px][256 ch]; 64 B conflict-free
+        // warp stores, then one 512 B bulk store per pixel (2-byte scattered stores measured 10 us per CTA)
+        __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(gen);
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          stage[(cc * 32 + j) * BT_CH + cb * 128 + q * 32 + lane] = __float2bfloat16_rn(__uint_as_float(v[j]));
+      } else {
+        if (c < C) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int px = cc * 32 + j;
+            const int y = ty0 + (px >> 4), x = tx0 + (px & 15);
+            if (y < H && x < W && !(dbg & 8)) grad_in[(((size_t)b * H + y) * W + x) * C + c] = from_f32<TO>(__uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+    if constexpr (sizeof(TO) == 2) {
+      fence_proxy_async();
+      named_bar_sync(2, BT_BUILDERS);
+      const int px = t - 64;
+      if (px < BT_PX) {
+        const int y = ty0 + (px >> 4), x = tx0 + (px & 15);
+        if (y < H && x < W && !(dbg & 8)) {
+          bulk_s2g(grad_in + (((size_t)b * H + y) * W + x) * C + c0, base + (uint32_t)px * (BT_CH * 2), (uint32_t)nch * 2u);
+          bulk_commit();
+          bulk_wait_read0();
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (trace && threadIdx.x == 64) {
+    unsigned long long* o = trace + 8 * ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    o[0] = tr0; o[1] = tr1; o[2] = tr2; o[3] = globaltimer_ns(); o[4] = (unsigned long long)seq; o[5] = smid; o[6] = tr3;
+  }
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <typename TO>
+static int launch_bwd_tc(const void* grad_out, int N, int C, int H, int W, int R, const void* ws, void* grad_in, cudaStream_t st) {
+  const int tiles_x = (W + BT_TX - 1) / BT_TX, tiles_y = (H + BT_TY - 1) / BT_TY;
+  dim3 grid(tiles_x * tiles_y, (C + BT_CH - 1) / BT_CH, N);
+  DA_REQUIRE(grid.y <= 65535 && grid.z <= 65535, DA_ERR_UNSUPPORTED, "roi_align_backward tc: grid too large");
+  const char* dbg_env = getenv("DA_ROI_BWD_DBG");
+  const int dbg = dbg_env ? atoi(dbg_env) : 0;   // timing experiments only (results are wrong when set)
+  const char* tr_env = getenv("DA_ROI_BWD_TRACE");   // tools/trace_roi_bwd.py: device address of a [ctas][8] u64 buffer
+  unsigned long long* trace = tr_env ? reinterpret_cast<unsigned long long*>(strtoull(tr_env, nullptr, 0)) : nullptr;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DA_CUDA_OK(cudaFuncSetAttribute(roi_align_bwd_tc_kernel<TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BT_SMEM));
+    attr_set = true;
+  }
+  roi_align_bwd_tc_kernel<TO><<<grid, BT_THREADS, BT_SMEM, st>>>((const __nv_bfloat16*)grad_out, C, H, W, R, (const unsigned char*)ws,
+                                                                   static_cast<TO*>(grad_in), tiles_x, dbg, trace);
+  DA_LAUNCH_CHECK();
+  return DA_OK;
+}
+
+int roi_align_bwd_tc(const void* grad_out, int N, int C, int H, int W, int R, const void* ws, void* grad_in, int grad_in_dtype,
+                     cudaStream_t st) {
+  if (grad_in_dtype == DA_BF16) return launch_bwd_tc<__nv_bfloat16>(grad_out, N, C, H, W, R, ws, grad_in, st);
+  return launch_bwd_tc<float>(grad_out, N, C, H, W, R, ws, grad_in, st);
+}
+
+}  // namespace da

@@ -10,6 +10,7 @@ reference's NCHW tensors (zero-copy when they are channels_last).
 """
 import ctypes
 
+import os
 import torch
 from torch.autograd import Function
 
@@ -199,10 +200,14 @@ class RoIAlignFunction(Function):
         N, C, H, W, ph, pw, scale, sr, aligned, layout, fdtype = ctx.cfg
         R = rois_c.shape[0]
         gout = gout.contiguous()
-        gin = torch.empty((N, H, W, C), dtype=torch.float32, device=gout.device)
+        # bf16 features + bf16 [R,C,7,7] gradients: the tensor-core kernel rounds its fp32 accumulators once and
+        # writes bf16 directly (no fp32 staging tensor, no cast pass)
+        direct = fdtype == torch.bfloat16 and gout.dtype == torch.bfloat16 and layout == 0 and C % 8 == 0 and R > 0 \
+            and os.environ.get("DA_ROI_NO_TC") is None
+        gin = torch.empty((N, H, W, C), dtype=torch.bfloat16 if direct else torch.float32, device=gout.device)
         ws = workspace(lib.da_roi_align_workspace_bytes(R, H, W), gout.device, "roi")
         check(lib.da_roi_align_backward(_ptr(gout), _code(gout.dtype), layout, _ptr(rois_c), R, ph, pw, scale, sr,
-                                        aligned, _ptr(gin), N, C, H, W, _ptr(ws), ws.numel(), _stream()),
+                                        aligned, _ptr(gin), _code(gin.dtype), N, C, H, W, _ptr(ws), ws.numel(), _stream()),
               "roi_align_backward")
         g = nhwc_to_nchw_view(gin)
         if fdtype != torch.float32:
