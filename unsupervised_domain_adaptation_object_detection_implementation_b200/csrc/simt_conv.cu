@@ -277,6 +277,93 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, int ksplit,
   }
 }
 
+// ---- thin outputs (1x1 conv / FC with Cout <= 4: the 2-logit domain classifiers) -------------
+// The 64x64 tile kernels leave 63 of 64 columns empty there (46 us for the [1024,512]x[512,2] logits of the
+// instance head); these are plain reductions.  fp32 accumulation like the tile kernels.
+constexpr int THIN_MAX = 4;
+
+template <typename T, typename TY>
+__global__ void __launch_bounds__(256)
+thin_fwd_kernel(int64_t M, int K, int Cout, const T* __restrict__ x, const T* __restrict__ w,
+                const float* __restrict__ scale, const float* __restrict__ shift, int relu, float drop_p, uint64_t seed0,
+                const unsigned long long* seed_ctr, TY* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // one warp per row
+  if (m >= M) return;
+  float acc[THIN_MAX] = {0.f, 0.f, 0.f, 0.f};
+  for (int k = lane; k < K; k += 32) {
+    const float xv = to_f32<T>(x[(size_t)m * K + k]);
+#pragma unroll
+    for (int n = 0; n < THIN_MAX; ++n)
+      if (n < Cout) acc[n] = fmaf(xv, to_f32<T>(w[(size_t)n * K + k]), acc[n]);
+  }
+#pragma unroll
+  for (int n = 0; n < THIN_MAX; ++n) acc[n] = warp_sum(acc[n]);
+  if (lane == 0) {
+    const uint64_t seed = effective_seed(seed0, seed_ctr);
+    const uint32_t thr = drop_threshold(drop_p);
+    const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+#pragma unroll
+    for (int n = 0; n < THIN_MAX; ++n) {
+      if (n >= Cout) break;
+      float v = acc[n];
+      if (scale) v *= scale[n];
+      if (shift) v += shift[n];
+      if (relu) v = fmaxf(v, 0.f);
+      if (drop_p > 0.f) v = (drop_hash(seed, (uint64_t)m * Cout + n) >= thr) ? v * keep_scale : 0.f;
+      y[(size_t)m * Cout + n] = from_f32<TY>(v);
+    }
+  }
+}
+
+template <typename T, typename TX>
+__global__ void __launch_bounds__(256)
+thin_dgrad_kernel(int64_t M, int K, int Cout, const T* __restrict__ dz, const T* __restrict__ w, float out_scale,
+                  TX* __restrict__ dx) {
+  const int64_t total = M * K;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / K;
+    const int k = (int)(i - m * K);
+    float acc = 0.f;
+    for (int n = 0; n < Cout; ++n) acc = fmaf(to_f32<T>(dz[(size_t)m * Cout + n]), to_f32<T>(w[(size_t)n * K + k]), acc);
+    dx[i] = from_f32<TX>(acc * out_scale);
+  }
+}
+
+// dW[n,k] = sum_m dz[m,n] x[m,k]: block = 32 k-columns, 8 warps stride the rows of one M-split, fixed-order reduce
+template <typename T>
+__global__ void __launch_bounds__(256)
+thin_wgrad_kernel(int64_t M, int K, int Cout, const T* __restrict__ x, const T* __restrict__ dz, float* __restrict__ part,
+                  int msplit) {
+  __shared__ float red[8][THIN_MAX][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = blockIdx.x * 32 + lane;
+  const int64_t per = (M + msplit - 1) / msplit;
+  const int64_t m_lo = (int64_t)blockIdx.y * per, m_hi = m_lo + per < M ? m_lo + per : M;
+  float acc[THIN_MAX] = {0.f, 0.f, 0.f, 0.f};
+  if (k < K) {
+    for (int64_t m = m_lo + warp; m < m_hi; m += 8) {
+      const float xv = to_f32<T>(x[(size_t)m * K + k]);
+#pragma unroll
+      for (int n = 0; n < THIN_MAX; ++n)
+        if (n < Cout) acc[n] = fmaf(to_f32<T>(dz[(size_t)m * Cout + n]), xv, acc[n]);
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < THIN_MAX; ++n) red[warp][n][lane] = acc[n];
+  __syncthreads();
+  if (warp < Cout && k < K) {
+    float v = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) v += red[wv][warp][lane];
+    part[(size_t)blockIdx.y * Cout * K + (size_t)warp * K + k] = v;
+  }
+}
+
+static inline bool thin_ok(const ConvGeom& g) {
+  return g.KH == 1 && g.KW == 1 && g.stride == 1 && g.pad == 0 && g.Cout <= THIN_MAX;
+}
+
 // ---- activation backward (engine independent) --------------------------------------------
 // dz[m,c] = dy[m,c] * scale[c] * relu'(y) * keep/(1-p);  colsum partial of (dy*mask) per block
 // rows per block: enough blocks to fill the machine even for the [1024, C] FC activations
@@ -365,6 +452,18 @@ int simt_conv_forward(const da_conv_desc* d, const void* x, const void* w, const
                       const float* shift, int relu, float drop_p, uint64_t seed, void* y, cudaStream_t st) {
   const ConvGeom g = make_geom(d);
   const int64_t M = (int64_t)g.N * g.OH * g.OW;
+  if (thin_ok(g)) {
+    const unsigned blocks = (unsigned)((M + 7) / 8);
+#define DA_THIN(T, TY) thin_fwd_kernel<T, TY><<<blocks, 256, 0, st>>>(M, g.Cin, g.Cout, (const T*)x, (const T*)w, scale, shift, relu, drop_p, seed, g_seed_counter, (TY*)y)
+    if (d->x_dtype == DA_F32 && d->y_dtype == DA_F32) DA_THIN(float, float);
+    else if (d->x_dtype == DA_F32 && d->y_dtype == DA_BF16) DA_THIN(float, __nv_bfloat16);
+    else if (d->x_dtype == DA_BF16 && d->y_dtype == DA_F32) DA_THIN(__nv_bfloat16, float);
+    else if (d->x_dtype == DA_BF16 && d->y_dtype == DA_BF16) DA_THIN(__nv_bfloat16, __nv_bfloat16);
+    else DA_REQUIRE(false, DA_ERR_INVALID_ARG, "simt conv forward: bad dtype");
+#undef DA_THIN
+    DA_LAUNCH_CHECK();
+    return DA_OK;
+  }
   dim3 grid((unsigned)((M + TM - 1) / TM), (g.Cout + TN - 1) / TN);
 #define DA_FWD(T, TY) simt_conv_fwd_kernel<T, TY><<<grid, 256, 0, st>>>(g, (const T*)x, (const T*)w, scale, shift, relu, drop_p, seed, g_seed_counter, (TY*)y)
   if (d->x_dtype == DA_F32 && d->y_dtype == DA_F32) DA_FWD(float, float);
@@ -381,6 +480,19 @@ int simt_conv_backward_data(const da_conv_desc* d, const void* dz, const void* w
                             cudaStream_t st) {
   const ConvGeom g = make_geom(d);
   const int64_t M = (int64_t)g.N * g.H * g.W;
+  if (thin_ok(g)) {
+    int64_t blocks = (M * g.Cin + 255) / 256;
+    if (blocks > (int64_t)num_sms() * 16) blocks = (int64_t)num_sms() * 16;
+#define DA_THIN(T, TX) thin_dgrad_kernel<T, TX><<<(unsigned)blocks, 256, 0, st>>>(M, g.Cin, g.Cout, (const T*)dz, (const T*)w, out_scale, (TX*)dx)
+    if (d->x_dtype == DA_F32 && d->y_dtype == DA_F32) DA_THIN(float, float);
+    else if (d->x_dtype == DA_F32 && d->y_dtype == DA_BF16) DA_THIN(float, __nv_bfloat16);
+    else if (d->x_dtype == DA_BF16 && d->y_dtype == DA_F32) DA_THIN(__nv_bfloat16, float);
+    else if (d->x_dtype == DA_BF16 && d->y_dtype == DA_BF16) DA_THIN(__nv_bfloat16, __nv_bfloat16);
+    else DA_REQUIRE(false, DA_ERR_INVALID_ARG, "simt conv dgrad: bad dtype");
+#undef DA_THIN
+    DA_LAUNCH_CHECK();
+    return DA_OK;
+  }
   dim3 grid((unsigned)((M + TM - 1) / TM), (g.Cin + TN - 1) / TN);
 #define DA_DG(T, TX) simt_conv_dgrad_kernel<T, TX><<<grid, 256, 0, st>>>(g, (const T*)dz, (const T*)w, out_scale, (TX*)dx)
   if (d->x_dtype == DA_F32 && d->y_dtype == DA_F32) DA_DG(float, float);
@@ -401,6 +513,19 @@ int simt_conv_backward_weight(const da_conv_desc* d, const void* x, const void* 
   const int64_t wn = (int64_t)g.Cout * taps * g.Cin;
   DA_REQUIRE(ks == 1 || (ws && ws_bytes >= (size_t)wn * ks * sizeof(float)), DA_ERR_WORKSPACE, "simt conv wgrad: workspace too small");
   float* part = ks == 1 ? dw : (float*)ws;
+  if (thin_ok(g)) {
+    const int64_t M = (int64_t)g.N * g.OH * g.OW;
+    dim3 tgrid((g.Cin + 31) / 32, ks);
+    if (d->x_dtype == DA_F32) thin_wgrad_kernel<float><<<tgrid, 256, 0, st>>>(M, g.Cin, g.Cout, (const float*)x, (const float*)dz, part, ks);
+    else if (d->x_dtype == DA_BF16) thin_wgrad_kernel<__nv_bfloat16><<<tgrid, 256, 0, st>>>(M, g.Cin, g.Cout, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dz, part, ks);
+    else DA_REQUIRE(false, DA_ERR_INVALID_ARG, "simt conv wgrad: bad dtype");
+    DA_LAUNCH_CHECK();
+    if (ks > 1) {
+      splitk_reduce_kernel<<<(int)((wn + 255) / 256), 256, 0, st>>>(part, ks, wn, dw);
+      DA_LAUNCH_CHECK();
+    }
+    return DA_OK;
+  }
   dim3 grid((g.Cout + TM - 1) / TM, (g.Cin + TN - 1) / TN, taps * ks);
   DA_REQUIRE(grid.y <= 65535 && grid.z <= 65535, DA_ERR_UNSUPPORTED, "simt conv wgrad: grid too large");
   if (d->x_dtype == DA_F32) simt_conv_wgrad_kernel<float><<<grid, 256, 0, st>>>(g, (const float*)x, (const float*)dz, part, ks);

@@ -400,131 +400,186 @@ struct TnParams {
   long long dw_numel;
 };
 
-// grid: (Cout tiles, Cin tiles, taps * splits)
-template <int kBN>
-__global__ void __launch_bounds__(NT_THREADS, 1)
-umma_tn_kernel(const __grid_constant__ TnParams P, int splits) {
+// Persistent kernel, one CTA per SM.  Tile = (Cout tile, Cin tile, tap, pixel split); tiles are enumerated per
+// CLUSTER: the kCluster CTAs of a cluster take adjacent Cout tiles of the SAME (Cin tile, tap, split), so they
+// share the X (B operand) tile: each CTA fetches 1/kCluster of it and TMA-multicasts it to all of them, which
+// cuts the L2->SM traffic of the 128x256 tile from 48 KB to 16 + 32/kCluster KB per k-step (the kernel was
+// L2-bandwidth bound at 505 TFLOP/s).  Two TMEM accumulators: the epilogue of tile t (128 KB of fp32 stores)
+// runs under the main loop of tile t+1.
+template <int kBN, int kCluster>
+__global__ void __launch_bounds__(NT_FWD_THREADS, 1)
+umma_tn_kernel(const __grid_constant__ TnParams P, int co_tiles, int ci_tiles, int splits) {
   constexpr int STAGES = TileCfg<kBN>::STAGES;
   constexpr int W_B_BYTES = kBN * WK * 2;
   constexpr int BN = kBN;
+  constexpr int B_BOXES = BN / 64, B_PER_CTA = B_BOXES / kCluster;
+  static_assert(B_BOXES % kCluster == 0, "cluster size must divide the 64-channel boxes of the B tile");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_s = base, b_s = base + STAGES * W_A_BYTES;
   const uint32_t bars = b_s + STAGES * W_B_BYTES;
-  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull = bars + 16 * STAGES, tslot = tfull + 8;
+  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 16,
+                 tslot = tempty0 + 16;
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
   volatile uint32_t* tslot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tslot - base));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  const int co0 = blockIdx.x * BM, ci0 = blockIdx.y * BN;
-  const int tap = blockIdx.z % P.num_taps, split = blockIdx.z / P.num_taps;
-  const TapInfo ti = P.taps[tap];
+  const int crank = (kCluster > 1) ? (int)cluster_ctarank() : 0;
+  const int co_super = (co_tiles + kCluster - 1) / kCluster;
+  const long long total_tiles = (long long)co_super * ci_tiles * P.num_taps * splits;
+  const int tile0 = blockIdx.x / kCluster, tile_step = gridDim.x / kCluster;
   const long long patches = P.flat ? (P.M_flat + WK - 1) / WK : (long long)P.NB * P.tiles_h * P.tiles_w;
   const long long total_iters = patches * P.num_terms;
   const long long per_split = (total_iters + splits - 1) / splits;
-  const long long it_begin = split * per_split;
-  const long long it_end = (it_begin + per_split < total_iters) ? it_begin + per_split : total_iters;
-  const int n_iters = (int)((it_end > it_begin) ? it_end - it_begin : 0);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-    mbar_init(tfull, 1);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, kCluster); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, NT_EPI_WARPS); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tslot, BN);
+  if (warp == 1) tmem_alloc(tslot, 2 * BN);
   tc_fence_before();
   __syncthreads();
+  if (kCluster > 1) cluster_sync_all();   // peer barriers are initialised before any multicast lands
   tc_fence_after();
   const uint32_t tmem_base = *tslot_ptr;
 
+  // tile index -> (co tile of this CTA, ci tile, tap, split); co is the fastest index so that concurrently
+  // running clusters read the same X tiles (L2 reuse)
+#define DA_TN_DECODE(tile)                                                        \
+  const int cs_ = (int)((tile) % co_super);                                        \
+  const long long r1_ = (tile) / co_super;                                         \
+  const int cit = (int)(r1_ % ci_tiles);                                           \
+  const int z_ = (int)(r1_ / ci_tiles);                                            \
+  const int tap = z_ % P.num_taps, split = z_ / P.num_taps;                        \
+  const int co0 = (cs_ * kCluster + crank) * BM, ci0 = cit * BN;                   \
+  const long long it_begin = split * per_split;                                    \
+  const long long it_end = (it_begin + per_split < total_iters) ? it_begin + per_split : total_iters; \
+  const int n_iters = (int)((it_end > it_begin) ? it_end - it_begin : 0);
+
   if (warp == 0) {
     if (lane == 0) {
-      for (int k = 0; k < n_iters; ++k) {
-        const long long it = it_begin + k;
-        const int s = k % STAGES;
-        const uint32_t ph = (k / STAGES) & 1;
-        mbar_wait(empty0 + 8 * s, ph ^ 1);
-        const int term = (int)(it / patches);
-        const long long patch = it % patches;
-        mbar_expect_tx(full0 + 8 * s, W_A_BYTES + W_B_BYTES);
-        const uint32_t fb = full0 + 8 * s;
-        const uint32_t ad = a_s + s * W_A_BYTES, bd = b_s + s * W_B_BYTES;
-        if (P.flat) {
-          const int m = (int)(patch * WK);
-          tma_load_2d(ad, &P.a_map[P.term_a[term]], fb, co0, m);
-          tma_load_2d(ad + W_A_BYTES / 2, &P.a_map[P.term_a[term]], fb, co0 + 64, m);
+      constexpr uint16_t kMask = (uint16_t)((1u << kCluster) - 1u);
+      int kq = 0;
+      for (long long tile = tile0; tile < total_tiles; tile += tile_step) {
+        DA_TN_DECODE(tile)
+        const TapInfo ti = P.taps[tap];
+        for (int k = 0; k < n_iters; ++k, ++kq) {
+          const long long it = it_begin + k;
+          const int s = kq % STAGES;
+          const uint32_t ph = (uint32_t)(kq / STAGES) & 1u;
+          mbar_wait(empty0 + 8 * s, ph ^ 1u);
+          const int term = (int)(it / patches);
+          const long long patch = it % patches;
+          const uint32_t fb = full0 + 8 * s;
+          mbar_expect_tx(fb, W_A_BYTES + W_B_BYTES);
+          const uint32_t ad = a_s + s * W_A_BYTES, bd = b_s + s * W_B_BYTES;
+          if (P.flat) {
+            const int m = (int)(patch * WK);
+            tma_load_2d(ad, &P.a_map[P.term_a[term]], fb, co0, m);
+            tma_load_2d(ad + W_A_BYTES / 2, &P.a_map[P.term_a[term]], fb, co0 + 64, m);
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j)
-            tma_load_2d(bd + j * (64 * WK * 2), &P.b_map[P.term_b[term]][0], fb, ci0 + j * 64, m);
-        } else {
-          const int per_img = P.tiles_h * P.tiles_w;
-          const int n = (int)(patch / per_img), t = (int)(patch % per_img);
-          const int i0 = (t / P.tiles_w) * P.BH, j0 = (t % P.tiles_w) * P.BW;
-          tma_load_4d(ad, &P.a_map[P.term_a[term]], fb, co0, j0, i0, n);
-          tma_load_4d(ad + W_A_BYTES / 2, &P.a_map[P.term_a[term]], fb, co0 + 64, j0, i0, n);
+            for (int j = 0; j < B_PER_CTA; ++j) {
+              const int jj = crank * B_PER_CTA + j;
+              if (kCluster == 1) tma_load_2d(bd + jj * (64 * WK * 2), &P.b_map[P.term_b[term]][0], fb, ci0 + jj * 64, m);
+              else tma_load_2d_mc(bd + jj * (64 * WK * 2), &P.b_map[P.term_b[term]][0], fb, ci0 + jj * 64, m, kMask);
+            }
+          } else {
+            const int per_img = P.tiles_h * P.tiles_w;
+            const int n = (int)(patch / per_img), t = (int)(patch % per_img);
+            const int i0 = (t / P.tiles_w) * P.BH, j0 = (t % P.tiles_w) * P.BW;
+            tma_load_4d(ad, &P.a_map[P.term_a[term]], fb, co0, j0, i0, n);
+            tma_load_4d(ad + W_A_BYTES / 2, &P.a_map[P.term_a[term]], fb, co0 + 64, j0, i0, n);
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j)
-            tma_load_4d(bd + j * (64 * WK * 2), &P.b_map[P.term_b[term]][ti.map], fb, ci0 + j * 64, j0 + ti.dw, i0 + ti.dh, n);
+            for (int j = 0; j < B_PER_CTA; ++j) {
+              const int jj = crank * B_PER_CTA + j;
+              if (kCluster == 1)
+                tma_load_4d(bd + jj * (64 * WK * 2), &P.b_map[P.term_b[term]][ti.map], fb, ci0 + jj * 64, j0 + ti.dw, i0 + ti.dh, n);
+              else
+                tma_load_4d_mc(bd + jj * (64 * WK * 2), &P.b_map[P.term_b[term]][ti.map], fb, ci0 + jj * 64, j0 + ti.dw, i0 + ti.dh, n, kMask);
+            }
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BM, BN, 1, 1);
-      for (int k = 0; k < n_iters; ++k) {
-        const int s = k % STAGES;
-        const uint32_t ph = (k / STAGES) & 1;
-        mbar_wait(full0 + 8 * s, ph);
+      int kq = 0, tcount = 0;
+      for (long long tile = tile0; tile < total_tiles; tile += tile_step, ++tcount) {
+        DA_TN_DECODE(tile)
+        (void)co0; (void)ci0; (void)tap;
+        const int buf = tcount & 1;
+        mbar_wait(tempty0 + 8 * buf, (((uint32_t)(tcount >> 1)) & 1u) ^ 1u);   // epilogue has drained this accumulator
         tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        for (int k = 0; k < n_iters; ++k, ++kq) {
+          const int s = kq % STAGES;
+          const uint32_t ph = (uint32_t)(kq / STAGES) & 1u;
+          mbar_wait(full0 + 8 * s, ph);
+          tc_fence_after();
 #pragma unroll
-        for (int kk = 0; kk < WK / 16; ++kk) {
-          // 16 k-rows = 2 swizzle atoms of 1024 B
-          const uint64_t adsc = desc_mnmajor_sw128(a_s + s * W_A_BYTES + kk * 2048, W_A_BYTES / 2);
-          const uint64_t bdsc = desc_mnmajor_sw128(b_s + s * W_B_BYTES + kk * 2048, 64 * WK * 2);
-          umma_bf16(tmem_base, adsc, bdsc, idesc, (k > 0 || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < WK / 16; ++kk) {
+            // 16 k-rows = 2 swizzle atoms of 1024 B
+            const uint64_t adsc = desc_mnmajor_sw128(a_s + s * W_A_BYTES + kk * 2048, W_A_BYTES / 2);
+            const uint64_t bdsc = desc_mnmajor_sw128(b_s + s * W_B_BYTES + kk * 2048, 64 * WK * 2);
+            umma_bf16(d_tmem, adsc, bdsc, idesc, (k > 0 || kk > 0) ? 1u : 0u);
+          }
+          // the stage is reusable only when EVERY CTA of the cluster is done with it (multicast writes into all)
+          if (kCluster == 1) umma_commit(empty0 + 8 * s);
+          else umma_commit_mc(empty0 + 8 * s, (uint16_t)((1u << kCluster) - 1u));
         }
-        umma_commit(empty0 + 8 * s);
+        if (n_iters > 0) umma_commit(tfull0 + 8 * buf);
+        else mbar_arrive(tfull0 + 8 * buf);
       }
-      umma_commit(tfull);
     }
   } else {
-    const int q = warp & 3;
-    const int co = co0 + q * 32 + lane;
-    float* out = P.dw + (size_t)split * P.dw_numel;
-    if (n_iters > 0) {
-      mbar_wait(tfull, 0);
+    // epilogue warps 2..9 -> TMEM lane quadrant (warp % 4); the two warps of a quadrant split the column chunks
+    const int q = warp & 3, ehalf = (warp - 2) >> 2;
+    int tcount = 0;
+    for (long long tile = tile0; tile < total_tiles; tile += tile_step, ++tcount) {
+      DA_TN_DECODE(tile)
+      const int buf = tcount & 1;
+      const int co = co0 + q * 32 + lane;
+      float* out = P.dw + (size_t)split * P.dw_numel;
+      mbar_wait(tfull0 + 8 * buf, ((uint32_t)(tcount >> 1)) & 1u);
       tc_fence_after();
-    }
 #pragma unroll 1
-    for (int cc = 0; cc < BN / 32; ++cc) {
-      uint32_t v[32];
-      if (n_iters > 0) {
-        DA_TMEM_LD32(tmem_base + ((uint32_t)(q * 32) << 16) + cc * 32, v);
-        tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0u;
-      }
-      const int cb = ci0 + cc * 32;
-      if (co < P.Cout && cb < P.Cin) {
-        float* o = out + ((size_t)co * P.num_taps + tap) * P.Cin + cb;
-        const int ncols = min(32, P.Cin - cb);
-        if (ncols == 32 && (P.Cin & 3) == 0) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(o + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                            __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+      for (int cc = ehalf; cc < BN / 32; cc += NT_EPI_WARPS / 4) {
+        uint32_t v[32];
+        if (n_iters > 0) {
+          DA_TMEM_LD32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + cc * 32, v);
+          tmem_ld_wait();
         } else {
-          for (int j = 0; j < ncols; ++j) o[j] = __uint_as_float(v[j]);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
+        }
+        const int cb = ci0 + cc * 32;
+        if (co < P.Cout && cb < P.Cin) {
+          float* o = out + ((size_t)co * P.num_taps + tap) * P.Cin + cb;
+          const int ncols = min(32, P.Cin - cb);
+          if (ncols == 32 && (P.Cin & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(o + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                              __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          } else {
+            for (int j = 0; j < ncols; ++j) o[j] = __uint_as_float(v[j]);
+          }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
     }
-    tc_fence_before();
   }
+#undef DA_TN_DECODE
+  tc_fence_before();
   __syncthreads();
+  if (kCluster > 1) cluster_sync_all();   // no CTA exits while a peer may still multicast into it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
@@ -665,7 +720,7 @@ static int pick_splits(long long ctas, int k_iters) {
   const int sms = num_sms();
   if (ctas >= sms || k_iters < 8) return 1;
   int s = (int)((sms + ctas - 1) / ctas);
-  if (s > k_iters / 4) s = k_iters / 4;
+  if (s > k_iters / 16) s = k_iters / 16;
   if (s > 16) s = 16;
   return s < 1 ? 1 : s;
 }
@@ -739,14 +794,20 @@ static void set_terms(int engine, int* num_terms, int* ta, int* tb) {
   }
 }
 
-static inline int choose_bn(int ncols) { return ncols > 128 ? 256 : 128; }
+// 128x256 tiles unless that leaves most SMs idle on a short-K problem (the instance-head FCs: M = N = 1024,
+// K <= 1024): there 128x128 tiles double the CTA count and make split-K (and its finish kernel) unnecessary.
+static inline int choose_bn(int ncols, long long m_rows, long long k_iters) {
+  if (ncols <= 128) return 128;
+  const long long tiles256 = ((m_rows + BM - 1) / BM) * ((ncols + 255) / 256);
+  return (tiles256 >= num_sms() / 2 || k_iters >= 64) ? 256 : 128;
+}
 
 static int pick_splits_persistent(long long tiles, int k_iters) {
   // persistent kernel: keep #tile-units <= #SMs (one wave) when splitting
   const int sms = num_sms();
   if (tiles >= sms / 2 || k_iters < 16) return 1;
   int s = (int)(sms / tiles);
-  if (s > k_iters / 8) s = k_iters / 8;
+  if (s > k_iters / 32) s = k_iters / 32;   // a split must amortise the partial write + finish kernel
   if (s > 16) s = 16;
   return s < 1 ? 1 : s;
 }
@@ -822,7 +883,7 @@ int umma_conv_forward(const da_conv_desc* d, const void* x, const void* w, const
   P.scale = scale; P.shift = shift; P.relu = relu; P.drop_p = drop_p; P.seed = seed; P.seed_ctr = g_seed_counter; P.out_scale = 1.f;
   P.y = y; P.y_dtype = d->y_dtype; P.y_numel = (long long)g.N * g.OH * g.OW * g.Cout;
   const int Ktot = g.KH * g.KW * g.Cin;
-  const int bn = choose_bn(g.Cout);
+  const int bn = choose_bn(g.Cout, (long long)g.N * g.OH * g.OW, (Ktot + BK - 1) / BK);
   long long pixel_tiles;
   const __nv_bfloat16* xs[2] = {xh, xl};
   const __nv_bfloat16* wsrc[2] = {wh, wl};
@@ -896,7 +957,7 @@ int umma_conv_backward_data(const da_conv_desc* d, const void* dz, const void* w
   base.OHf = g.H; base.OWf = g.W;
   base.relu = 0; base.drop_p = 0.f; base.out_scale = out_scale;
   base.y = dx; base.y_dtype = d->y_dtype; base.y_numel = (long long)g.N * g.H * g.W * g.Cin;
-  const int bn = choose_bn(g.Cin);
+  const int bn = choose_bn(g.Cin, (long long)g.N * g.H * g.W, ((long long)taps * g.Cout + BK - 1) / BK);
   const __nv_bfloat16* wsrc[2] = {wh, wl};
   const __nv_bfloat16* zs[2] = {zh, zl};
   for (int t = 0; t < (wl ? 2 : 1); ++t) {
@@ -946,6 +1007,46 @@ int umma_conv_backward_data(const da_conv_desc* d, const void* dz, const void* w
       rc = launch_nt(P, bn, (long long)g.N * P.tiles_h * P.tiles_w, P.num_terms * nt * P.kchunks, ws, part_bytes(g), st);
       if (rc) return rc;
     }
+  return DA_OK;
+}
+
+template <int kBN, int kCluster>
+static int launch_tn_t(const TnParams& P, int co_tiles, int ci_tiles, int splits, cudaStream_t st) {
+  const long long co_super = (co_tiles + kCluster - 1) / kCluster;
+  const long long total = co_super * ci_tiles * P.num_taps * splits;   // cluster-level tile units
+  DA_REQUIRE(total * kCluster <= 0x7fffffffll, DA_ERR_UNSUPPORTED, "umma wgrad: too many tiles");
+  auto kern = umma_tn_kernel<kBN, kCluster>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<kBN>::SMEM));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.blockDim = dim3(NT_FWD_THREADS);
+  cfg.dynamicSmemBytes = TileCfg<kBN>::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // persistent grid = the clusters that are co-resident (GPC sizes need not be multiples of the cluster size)
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    cfg.gridDim = dim3((num_sms() / kCluster) * kCluster);
+    int n = 0;
+    if (kCluster > 1 && cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n > 0) max_clusters = n;
+    else max_clusters = num_sms() / kCluster;
+    (void)cudaGetLastError();
+    if (max_clusters > num_sms() / kCluster) max_clusters = num_sms() / kCluster;
+  }
+  const int clusters = (int)(total < max_clusters ? total : max_clusters);
+  cfg.gridDim = dim3(clusters * kCluster);
+  DA_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, P, co_tiles, ci_tiles, splits));
+  count_launch();
   return DA_OK;
 }
 
@@ -1009,30 +1110,25 @@ int umma_conv_backward_weight(const da_conv_desc* d, const void* x, const void* 
     P.num_taps = nt;
     patches = (long long)g.N * P.tiles_h * P.tiles_w;
   }
-  const int bn = choose_bn(g.Cin);
+  // weight-gradient tiles are [128 Cout x bn Cin] per tap; K runs over the pixels
+  const int bn = (g.Cin > 128 && (long long)((g.Cout + BM - 1) / BM) * ((g.Cin + 255) / 256) * P.num_taps >= num_sms() / 2) ? 256 : 128;
   const long long tiles = (long long)((g.Cout + BM - 1) / BM) * ((g.Cin + bn - 1) / bn) * P.num_taps;
   long long k_iters = patches * P.num_terms;
-  int splits = pick_splits(tiles, (int)(k_iters > 1000000 ? 1000000 : k_iters));
+  int splits = pick_splits_persistent(tiles, (int)(k_iters > 1000000 ? 1000000 : k_iters));
   while (splits > 1 && (size_t)splits * P.dw_numel * sizeof(float) > part_bytes(g)) --splits;
-  DA_REQUIRE(P.num_taps * splits <= 65535, DA_ERR_UNSUPPORTED, "umma wgrad: grid too large");
   P.dw = splits > 1 ? (float*)ws : dw;
-  dim3 grid((g.Cout + BM - 1) / BM, (g.Cin + bn - 1) / bn, P.num_taps * splits);
+  const int co_tiles = (g.Cout + BM - 1) / BM, ci_tiles = (g.Cin + bn - 1) / bn;
+  // Cout tiles that share an X tile form a cluster (TMA multicast of the shared operand)
+  int rc2;
   if (bn == 256) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      DA_CUDA_OK(cudaFuncSetAttribute(umma_tn_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<256>::SMEM));
-      attr_set = true;
-    }
-    umma_tn_kernel<256><<<grid, NT_THREADS, TileCfg<256>::SMEM, st>>>(P, splits);
+    if (co_tiles >= 4) rc2 = launch_tn_t<256, 4>(P, co_tiles, ci_tiles, splits, st);
+    else if (co_tiles >= 2) rc2 = launch_tn_t<256, 2>(P, co_tiles, ci_tiles, splits, st);
+    else rc2 = launch_tn_t<256, 1>(P, co_tiles, ci_tiles, splits, st);
   } else {
-    static bool attr_set = false;
-    if (!attr_set) {
-      DA_CUDA_OK(cudaFuncSetAttribute(umma_tn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<128>::SMEM));
-      attr_set = true;
-    }
-    umma_tn_kernel<128><<<grid, NT_THREADS, TileCfg<128>::SMEM, st>>>(P, splits);
+    if (co_tiles >= 2) rc2 = launch_tn_t<128, 2>(P, co_tiles, ci_tiles, splits, st);
+    else rc2 = launch_tn_t<128, 1>(P, co_tiles, ci_tiles, splits, st);
   }
-  DA_LAUNCH_CHECK();
+  if (rc2) return rc2;
   if (splits > 1) {
     sum_splits_kernel<<<ew_blocks(P.dw_numel), 256, 0, st>>>((const float*)ws, splits, P.dw_numel, dw);
     DA_LAUNCH_CHECK();
