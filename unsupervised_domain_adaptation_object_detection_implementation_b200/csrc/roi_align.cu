@@ -717,7 +717,7 @@ using namespace da;
 
 extern "C" size_t da_roi_align_workspace_bytes(int R, int H, int W) {
   if (R < 0) R = 0;
-  return ws_table_off(R) + (size_t)R * (size_t)(H + W) * WROW * sizeof(float) + 256;
+  return ws_order_off(R, H, W) + (size_t)R * sizeof(int) + 256;
 }
 
 static int check_common(int N, int C, int H, int W, int R, int ph, int pw, const void* rois,

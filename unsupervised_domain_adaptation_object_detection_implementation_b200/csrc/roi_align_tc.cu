@@ -37,7 +37,8 @@ constexpr int TC_ASTAGE = TC_GB * TC_MCH * 16 * 2;   // one quad (16 pixels) x 5
 constexpr int TC_NSTAGE = 6;
 constexpr int TC_BQUAD = TC_NB * 16 * 2;        // weights of one quad: 64 bins x 16 pixels, 2 KB
 constexpr int TC_CHUNK_Q = 32;                  // quads per resident weight chunk (512 pixels)
-constexpr int TC_NACC = 2 * TC_GB;              // TMEM accumulators: two groups ping-pong
+constexpr int TC_NACC = 2 * TC_GB;
+constexpr int TC_NSCHED = 4;                    // depth of the in-CTA work queue (RoI indices broadcast to every role)              // TMEM accumulators: two groups ping-pong
 
 template <typename TOut> __host__ __device__ constexpr int tc_stage_bytes() { return ((TC_MCH * PP * (int)sizeof(TOut) + 127) / 128) * 128; }
 template <typename TOut> __host__ __device__ inline size_t tc_smem_bytes(int H, int W) {
@@ -66,6 +67,48 @@ __device__ __forceinline__ uint64_t desc_kmajor_nosw(uint32_t saddr, uint32_t lb
          ((uint64_t)1 << 46);
 }
 
+// Work queue.  A persistent CTA processes whole RoIs, whose cost (footprint quads) spans 1..64+; a static stride
+// over the RoI index left the slowest CTA with 2x the mean work.  roi_order_kernel counting-sorts the RoIs by
+// decreasing footprint; the TMA producer of every CTA pops the next index with one atomicAdd (list scheduling in
+// LPT order) and broadcasts it to the other roles through a small shared-memory ring.  The order inside a bucket
+// depends on atomics, the results do not: every RoI's output is independent of where and when it is computed.
+__global__ void __launch_bounds__(1024)
+roi_order_kernel(const RoiMeta* __restrict__ metas, int R, int* __restrict__ order) {
+  __shared__ int hist[256];
+  __shared__ int start[256];
+  const int t = threadIdx.x;
+  if (t < 256) hist[t] = 0;
+  __syncthreads();
+  for (int r = t; r < R; r += blockDim.x) {
+    const RoiMeta m = metas[r];
+    const int nq = ((m.ny + 3) >> 2) * ((m.nx + 3) >> 2);
+    atomicAdd(&hist[255 - min(255, nq)], 1);
+  }
+  __syncthreads();
+  if (t == 0) {
+    int acc = 0;
+    for (int k = 0; k < 256; ++k) { start[k] = acc; acc += hist[k]; }
+  }
+  __syncthreads();
+  for (int r = t; r < R; r += blockDim.x) {
+    const RoiMeta m = metas[r];
+    const int nq = ((m.ny + 3) >> 2) * ((m.nx + 3) >> 2);
+    order[atomicAdd(&start[255 - min(255, nq)], 1)] = r;
+  }
+}
+
+// consumer side of the in-CTA queue: returns the next RoI index or -1 (drained); `arrive` = this thread releases the slot
+// kWarp: called by all 32 lanes (lane 0 releases after the whole warp has read); else by one elected thread
+template <bool kWarp>
+__device__ __forceinline__ int sched_pop(uint32_t sfull0, uint32_t sempty0, const volatile int* sched, int qi, bool arrive) {
+  const int slot = qi % TC_NSCHED;
+  mbar_wait(sfull0 + 8 * slot, (uint32_t)(qi / TC_NSCHED) & 1u);
+  const int r = sched[slot];
+  if (kWarp) __syncwarp();
+  if (arrive) mbar_arrive(sempty0 + 8 * slot);
+  return r;
+}
+
 template <typename TOut>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 roi_align_fwd_tc_kernel(const __grid_constant__ CUtensorMap fmap, int C, int H, int W, int R,
@@ -81,8 +124,10 @@ roi_align_fwd_tc_kernel(const __grid_constant__ CUtensorMap fmap, int C, int H, 
   float* wx_s = wy_s + (size_t)(H + 4) * WROW;
   const uint32_t bars = smem_u32(wx_s + (size_t)(W + 4) * WROW);
   const uint32_t full0 = bars, empty0 = bars + 8 * TC_NSTAGE, tfull0 = bars + 16 * TC_NSTAGE,
-                 tempty0 = tfull0 + 8 * TC_NACC, b_ready = tempty0 + 8 * TC_NACC, b_free = b_ready + 8, tslot = b_free + 8;
+                 tempty0 = tfull0 + 8 * TC_NACC, b_ready = tempty0 + 8 * TC_NACC, b_free = b_ready + 8, sfull0 = b_free + 8,
+                 sempty0 = sfull0 + 8 * TC_NSCHED, tslot = sempty0 + 8 * TC_NSCHED, sched_a = tslot + 8;
   volatile uint32_t* tslot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tslot - base));
+  volatile int* sched = reinterpret_cast<volatile int*>(gen + (sched_a - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const RoiMeta* metas = reinterpret_cast<const RoiMeta*>(ws + ws_meta_off());
@@ -95,6 +140,7 @@ roi_align_fwd_tc_kernel(const __grid_constant__ CUtensorMap fmap, int C, int H, 
     for (int b = 0; b < TC_NACC; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 4); }
     mbar_init(b_ready, 1);
     mbar_init(b_free, TC_NISSUE);
+    for (int i = 0; i < TC_NSCHED; ++i) { mbar_init(sfull0 + 8 * i, 1); mbar_init(sempty0 + 8 * i, TC_NISSUE + 4); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tslot, TC_NACC * TC_NB);
@@ -108,8 +154,18 @@ roi_align_fwd_tc_kernel(const __grid_constant__ CUtensorMap fmap, int C, int H, 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer: ONE 16 KB box per stage
     if (lane == 0) {
-      int kq = 0;
-      for (int r = blockIdx.x; r < R; r += gridDim.x) {
+      int kq = 0, qi = 0;
+      int* counter = reinterpret_cast<int*>(const_cast<unsigned char*>(ws)) + 1;
+      const int* order = reinterpret_cast<const int*>(ws + ws_order_off(R, H, W));
+      int nxt_i = atomicAdd(counter, 1);
+      for (;; ++qi) {
+        const int r = nxt_i < R ? order[nxt_i] : -1;
+        if (r >= 0) nxt_i = atomicAdd(counter, 1);   // next index is in flight while this RoI is processed
+        const int sslot = qi % TC_NSCHED;
+        mbar_wait(sempty0 + 8 * sslot, ((uint32_t)(qi / TC_NSCHED) & 1u) ^ 1u);
+        sched[sslot] = r;
+        mbar_arrive(sfull0 + 8 * sslot);
+        if (r < 0) break;
         TcRoi t;
         if (!tc_roi(metas[r], H, t)) continue;
         for (int g = 0; g < ngroups; ++g) {
@@ -136,7 +192,9 @@ roi_align_fwd_tc_kernel(const __grid_constant__ CUtensorMap fmap, int C, int H, 
       const uint64_t ad0 = desc_mnmajor_sw128(a_ring, 2048);
       const uint64_t bd0 = desc_kmajor_nosw(b_base, 128, 256);
       int kq = 0, nbuild = 0, gcount = 0;
-      for (int r = blockIdx.x; r < R; r += gridDim.x) {
+      for (int qi = 0;; ++qi) {
+        const int r = sched_pop<false>(sfull0, sempty0, sched, qi, true);
+        if (r < 0) break;
         TcRoi t;
         if (!tc_roi(metas[r], H, t)) continue;
         for (int g = 0; g < ngroups; ++g, ++gcount) {
@@ -182,7 +240,9 @@ roi_align_fwd_tc_kernel(const __grid_constant__ CUtensorMap fmap, int C, int H, 
     const int ph_n = n / P, pw_n = n - ph_n * P;
     const bool n_ok = n < PP;
     int nbuild = 0, nstore = 0, gcount = 0;
-    for (int r = blockIdx.x; r < R; r += gridDim.x) {
+    for (int qi = 0;; ++qi) {
+      const int r = sched_pop<true>(sfull0, sempty0, sched, qi, lane == 0);
+      if (r < 0) break;
       const RoiMeta m = metas[r];
       TcRoi t;
       if (!tc_roi(m, H, t)) {   // empty footprint (degenerate / outside / bad batch index): zeros, as the reference
@@ -278,6 +338,9 @@ static int launch_tc(const CUtensorMap& fmap, int C, int H, int W, int R, const 
   DA_REQUIRE(smem <= 227 * 1024, DA_ERR_UNSUPPORTED, "roi_align tc: H+W too large for shared memory");
   auto k = roi_align_fwd_tc_kernel<TOut>;
   DA_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  roi_order_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<const RoiMeta*>((const unsigned char*)ws + ws_meta_off()), R,
+                                       reinterpret_cast<int*>((unsigned char*)const_cast<void*>(ws) + ws_order_off(R, H, W)));
+  DA_LAUNCH_CHECK();
   const int grid = R < num_sms() ? R : num_sms();
   k<<<grid, TC_THREADS, smem, st>>>(fmap, C, H, W, R, (const unsigned char*)ws, (TOut*)out);
   DA_LAUNCH_CHECK();

@@ -16,10 +16,14 @@ struct __align__(16) RoiMeta {
   int count;    // max(gh*gw,1)
 };
 
-// workspace layout: int err[4] | RoiMeta[R] | float tables[R][(H+W)*8]
+// workspace layout: int hdr[4] = {error flag, work-queue counter, -, -} | RoiMeta[R] | float tables[R][(H+W)*8] | int order[R]
+// (hdr is zeroed before every prep launch; order = RoIs by decreasing footprint, the tensor-core forward's work queue)
 __host__ __device__ inline size_t ws_meta_off() { return 16; }
 __host__ __device__ inline size_t ws_table_off(int R) {
   return 16 + ((size_t)R * sizeof(RoiMeta) + 255) / 256 * 256;
+}
+__host__ __device__ inline size_t ws_order_off(int R, int H, int W) {
+  return (ws_table_off(R) + (size_t)R * (size_t)(H + W) * WROW * sizeof(float) + 255) / 256 * 256;
 }
 
 

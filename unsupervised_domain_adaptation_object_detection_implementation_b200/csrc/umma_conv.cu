@@ -379,6 +379,27 @@ __global__ void nt_splitk_finish_kernel(const float* __restrict__ partial, int s
   }
 }
 
+// Warp-cooperative store of a [32 rows][32 fp32] accumulator chunk: lane L holds row L.  The chunk is transposed
+// through a private 4 KB shared-memory tile (16-byte pieces, XOR-swizzled) so that every store instruction
+// writes four whole 128-byte row segments instead of 32 lanes hitting 32 different lines with 16 B each.
+// `row_ptr` = this lane's destination row (nullptr: row not stored); must be 16-byte aligned.
+__device__ __forceinline__ void warp_store_rows_f32(const uint32_t* v, float* row_ptr, uint8_t* wstage, int lane) {
+  uint4* srow = reinterpret_cast<uint4*>(wstage + lane * 128);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) srow[j ^ (lane & 7)] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  __syncwarp();
+  const int sub = lane >> 3, piece = lane & 7;
+  const unsigned long long mine = reinterpret_cast<unsigned long long>(row_ptr);
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int row = it * 4 + sub;
+    const unsigned long long dst = __shfl_sync(0xffffffffu, mine, row);
+    const uint4 val = *reinterpret_cast<const uint4*>(wstage + row * 128 + ((piece ^ (row & 7)) << 4));
+    if (dst) *reinterpret_cast<uint4*>(dst + piece * 16) = val;
+  }
+  __syncwarp();
+}
+
 // ---------------------------------------------------------------------------------------
 // weight gradient ("TN"): dW[co, tap, ci] = sum_pix dZ[pix, co] * X[pix_in(tap), ci]
 // ---------------------------------------------------------------------------------------
@@ -421,6 +442,7 @@ umma_tn_kernel(const __grid_constant__ TnParams P, int co_tiles, int ci_tiles, i
   const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 16,
                  tslot = tempty0 + 16;
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  uint8_t* epi_stage = gen_base + (bars - base) + 256;   // NT_EPI_WARPS x 4 KB, 16-byte aligned
   volatile uint32_t* tslot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tslot - base));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -555,15 +577,12 @@ umma_tn_kernel(const __grid_constant__ TnParams P, int co_tiles, int ci_tiles, i
           for (int j = 0; j < 32; ++j) v[j] = 0u;
         }
         const int cb = ci0 + cc * 32;
-        if (co < P.Cout && cb < P.Cin) {
-          float* o = out + ((size_t)co * P.num_taps + tap) * P.Cin + cb;
+        if (cb < P.Cin) {   // warp-uniform
+          float* o = (co < P.Cout) ? out + ((size_t)co * P.num_taps + tap) * P.Cin + cb : nullptr;
           const int ncols = min(32, P.Cin - cb);
-          if (ncols == 32 && (P.Cin & 3) == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(o + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                              __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-          } else {
+          if (ncols == 32 && (P.Cin & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+            warp_store_rows_f32(v, o, epi_stage + (warp - 2) * 4096, lane);
+          } else if (o) {
             for (int j = 0; j < ncols; ++j) o[j] = __uint_as_float(v[j]);
           }
         }
@@ -828,11 +847,8 @@ static int launch_nt_t(NtParams& P, long long pixel_tiles, int k_iters, void* ws
     DA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<kBN>::SMEM));
     attr_set = true;
   }
-  const int max_clusters = num_sms() / kCluster;
-  const int clusters = (int)(total < max_clusters ? total : max_clusters);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(clusters * kCluster);
   cfg.blockDim = dim3(NT_FWD_THREADS);
   cfg.dynamicSmemBytes = TileCfg<kBN>::SMEM;
   cfg.stream = st;
@@ -843,6 +859,18 @@ static int launch_nt_t(NtParams& P, long long pixel_tiles, int k_iters, void* ws
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  // persistent grid = the clusters that are co-resident (GPC sizes need not be multiples of the cluster size)
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    cfg.gridDim = dim3((num_sms() / kCluster) * kCluster);
+    int n = 0;
+    if (kCluster > 1 && cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n > 0) max_clusters = n;
+    else max_clusters = num_sms() / kCluster;
+    (void)cudaGetLastError();
+    if (max_clusters > num_sms() / kCluster) max_clusters = num_sms() / kCluster;
+  }
+  const int clusters = (int)(total < max_clusters ? total : max_clusters);
+  cfg.gridDim = dim3(clusters * kCluster);
   DA_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, P, (int)pixel_tiles, n_tiles, splits));
   DA_LAUNCH_CHECK();
   if (splits > 1) {
@@ -852,13 +880,22 @@ static int launch_nt_t(NtParams& P, long long pixel_tiles, int k_iters, void* ws
   }
   return DA_OK;
 }
+// CTAs per cluster: pixel tiles that share one weight (B) tile.  4 when the pixel tiles divide evenly (a phantom
+// tile of an odd tail would idle a whole SM), else 2.
+static inline int nt_cluster(int bn, long long pixel_tiles) {
+  if (pixel_tiles >= 4 && pixel_tiles % 4 == 0 && bn == 256) return 4;
+  return pixel_tiles >= 2 ? 2 : 1;
+}
+
 static int launch_nt(NtParams& P, int bn, long long pixel_tiles, int k_iters, void* ws_part, size_t part_cap, cudaStream_t st) {
-  const bool pair = pixel_tiles >= 2;   // cluster of 2 CTAs sharing the weight tile through TMA multicast
-  if (bn == 256)
-    return pair ? launch_nt_t<256, 2>(P, pixel_tiles, k_iters, ws_part, part_cap, st)
-                : launch_nt_t<256, 1>(P, pixel_tiles, k_iters, ws_part, part_cap, st);
-  return pair ? launch_nt_t<128, 2>(P, pixel_tiles, k_iters, ws_part, part_cap, st)
-              : launch_nt_t<128, 1>(P, pixel_tiles, k_iters, ws_part, part_cap, st);
+  const int cl = nt_cluster(bn, pixel_tiles);   // CTAs sharing the weight tile through TMA multicast
+  if (bn == 256) {
+    if (cl == 4) return launch_nt_t<256, 4>(P, pixel_tiles, k_iters, ws_part, part_cap, st);
+    return cl == 2 ? launch_nt_t<256, 2>(P, pixel_tiles, k_iters, ws_part, part_cap, st)
+                   : launch_nt_t<256, 1>(P, pixel_tiles, k_iters, ws_part, part_cap, st);
+  }
+  return cl == 2 ? launch_nt_t<128, 2>(P, pixel_tiles, k_iters, ws_part, part_cap, st)
+                 : launch_nt_t<128, 1>(P, pixel_tiles, k_iters, ws_part, part_cap, st);
 }
 
 int umma_conv_forward(const da_conv_desc* d, const void* x, const void* w, const float* scale, const float* shift,
@@ -925,7 +962,7 @@ int umma_conv_forward(const da_conv_desc* d, const void* x, const void* w, const
     // a 2-CTA cluster (pixel_tiles >= 2, see launch_nt) loads the weight tile as two multicast halves
     const uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)g.Cout};
     const uint64_t strides[1] = {(uint64_t)Ktot * 2};
-    const uint32_t box[2] = {BK, (uint32_t)(pixel_tiles >= 2 ? bn / 2 : bn)};
+    const uint32_t box[2] = {BK, (uint32_t)(bn / nt_cluster(bn, pixel_tiles))};
     rc = encode_map(&P.b_map[t], wsrc[t], 2, dims, strides, box);
     if (rc) return rc;
   }
