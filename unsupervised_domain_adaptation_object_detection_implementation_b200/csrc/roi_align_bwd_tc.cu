@@ -36,6 +36,7 @@ constexpr int BT_B_BYTES = BT_PX * 128;                         // [256 px][64 b
 constexpr int BT_OPS_BYTES = 2 * BT_A_BYTES + BT_B_BYTES;       // one operand set: 64 KB
 constexpr int BT_RAW_G = BT_CH * PP * 2;                        // 25088 B
 constexpr int BT_RAW_BYTES = 64 + BT_RAW_G + (BT_TY + BT_TX) * WROW * 4 + 64;   // header | g | wy | wx  (26240, 128-multiple)
+constexpr int BT_PF = 8;                                       // L2 prefetch distance (pairs)
 constexpr int BT_NRAW = 3;                                     // raw ring depth (copy latency ~3 pair times)
 constexpr size_t BT_SMEM = 1024 + 2 * (size_t)BT_OPS_BYTES + BT_NRAW * (size_t)BT_RAW_BYTES + BT_LIST * 4 + 256;
 
@@ -136,6 +137,9 @@ roi_align_bwd_tc_kernel(const __nv_bfloat16* __restrict__ grad_out, int C, int H
           my_r = list[li + lane];
           my_m = metas[my_r];
         }
+        // pull the gradient chunk of the pair BT_PF ring slots ahead into L2 (the ring itself only covers ~3 us)
+        if (lane == 3 && li + BT_PF < n_list && !(dbg & 128))
+          bulk_prefetch_l2(grad_out + ((size_t)list[li + BT_PF] * C + c0) * PP, (uint32_t)(nch * PP * 2));
         const int src = li & 31;
         const int r = __shfl_sync(0xffffffffu, my_r, src);
         RoiMeta m;

@@ -53,6 +53,7 @@ struct TapInfo {
 };
 
 struct NtParams {
+  int dbg;                  // DA_UMMA_DBG timing experiments (results are wrong when set)
   CUtensorMap a_map[2][4];  // [hi/lo term][parity]
   CUtensorMap b_map[2];     // [hi/lo term]
   TapInfo taps[MAX_TAPS];
@@ -134,8 +135,16 @@ __device__ __forceinline__ void nt_epilogue_chunk(const NtParams& P, const uint3
                     ((reinterpret_cast<uintptr_t>(gbase) & 15) == 0);
   if (!fast) {   // ragged tail: plain per-row stores
     if (valid) {
-      if (out_f32) { float* o = reinterpret_cast<float*>(gbase) + row_off + c_base; for (int j = 0; j < ncols; ++j) o[j] = f[j]; }
-      else { __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(gbase) + row_off + c_base; for (int j = 0; j < ncols; ++j) o[j] = __float2bfloat16_rn(f[j]); }
+      // compile-time indices only: a runtime-indexed loop would move f[] (and every access to it) to local memory
+      if (out_f32) {
+        float* o = reinterpret_cast<float*>(gbase) + row_off + c_base;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (j < ncols) o[j] = f[j];
+      } else {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(gbase) + row_off + c_base;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (j < ncols) o[j] = __float2bfloat16_rn(f[j]);
+      }
     }
     return;
   }
@@ -167,7 +176,7 @@ __device__ __forceinline__ void nt_epilogue_chunk(const NtParams& P, const uint3
     const int row = it * rows_per_it + sub;
     const unsigned long long roff = __shfl_sync(0xffffffffu, my_off, row);
     const uint4 val = *reinterpret_cast<const uint4*>(wstage + row * row_bytes + ((piece ^ (row & (npieces - 1))) << 4));
-    if (roff != ~0ull)
+    if (roff != ~0ull && !(P.dbg & 1))
       *reinterpret_cast<uint4*>(gbase + (roff + c_base) * es + piece * 16) = val;
   }
   __syncwarp();
@@ -177,11 +186,17 @@ __device__ __forceinline__ void nt_epilogue_chunk(const NtParams& P, const uint3
 // kCluster == 2: the two CTAs of a cluster work on adjacent pixel tiles of the SAME Cout tile and
 // k-split; each loads half of the shared B (weight) tile and TMA-multicasts it to both, which halves
 // the L2->SM weight traffic (the 128x256 tile is L2-bandwidth bound otherwise).
-template <int kBN, int kCluster>
+// k2SM (CTA pair, kCluster == 2): ONE tcgen05.mma.cta_group::2 per k-step covers the 256 pixel rows of both CTAs.
+// Each CTA stages its own 128 rows of A and HALF of the B tile (16 + 16 KB per k-step instead of 16 + 32 KB), so
+// the bytes every SM has to receive per MMA cycle drop by a third -- the 1-SM 128x256 tile is bound by the ~46 B/clk
+// an SM can take in, not by the tensor pipe.  The leader (cluster rank 0) owns the full barriers and issues the MMAs.
+template <int kBN, int kCluster, bool k2SM>
 __global__ void __launch_bounds__(NT_FWD_THREADS, 1)
 umma_nt_kernel(const __grid_constant__ NtParams P, int pixel_tiles, int n_tiles, int splits) {
   using Cfg = TileCfg<kBN>;
-  constexpr int STAGES = Cfg::STAGES, B_BYTES = Cfg::B_BYTES;
+  static_assert(!k2SM || kCluster == 2, "the CTA-pair mode is a cluster of exactly two CTAs");
+  constexpr int B_BYTES = k2SM ? Cfg::B_BYTES / 2 : Cfg::B_BYTES;                       // bytes of B staged by THIS CTA per k-step
+  constexpr int STAGES = (Cfg::STAGES * (A_BYTES + Cfg::B_BYTES)) / (A_BYTES + B_BYTES);  // same ring bytes, deeper ring
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_s = base, b_s = base + STAGES * A_BYTES;
@@ -204,11 +219,12 @@ umma_nt_kernel(const __grid_constant__ NtParams P, int pixel_tiles, int n_tiles,
   const int per_img = P.tiles_h * P.tiles_w;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, kCluster); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, NT_EPI_WARPS); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, k2SM ? 1 : kCluster); }
+    // pair mode: the epilogue warps of BOTH CTAs release an accumulator to the leader's MMA thread
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, k2SM ? 2 * NT_EPI_WARPS : NT_EPI_WARPS); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tslot, Cfg::TMEM_COLS);
+  if (warp == 1) { if (k2SM) tmem_alloc_2sm(tslot, Cfg::TMEM_COLS); else tmem_alloc(tslot, Cfg::TMEM_COLS); }
   tc_fence_before();
   __syncthreads();
   if (kCluster > 1) cluster_sync_all();   // peer barriers are initialised before any multicast lands
@@ -240,12 +256,29 @@ umma_nt_kernel(const __grid_constant__ NtParams P, int pixel_tiles, int n_tiles,
           const int tap = rem / P.kchunks, kc = rem % P.kchunks;
           const TapInfo ti = P.taps[tap];
           const uint32_t fb = full0 + 8 * s;
+          const CUtensorMap* bm = &P.b_map[P.term_b[term]];
+          if constexpr (k2SM) {
+            // both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of the whole pair
+            if (crank == 0) mbar_expect_tx(fb, 2 * (A_BYTES + B_BYTES));
+            if (P.flat)
+              tma_load_2d_2sm(a_s + s * A_BYTES, &P.a_map[P.term_a[term]][0], fb, kc * BK, m0);
+            else
+              tma_load_4d_2sm(a_s + s * A_BYTES, &P.a_map[P.term_a[term]][ti.map], fb, kc * BK, j0 + ti.dw, i0 + ti.dh, n_img);
+            constexpr int HALF = kBN / 2;   // this CTA stages output channels [crank*HALF, +HALF) of the tile
+            if (P.b_mn_major) {
+#pragma unroll
+              for (int j = 0; j < HALF / 64; ++j)
+                tma_load_2d_2sm(b_s + s * B_BYTES + j * (64 * BK * 2), bm, fb, ti.bk + c0 + crank * HALF + j * 64, kc * BK);
+            } else {
+              tma_load_2d_2sm(b_s + s * B_BYTES, bm, fb, ti.bk + kc * BK, c0 + crank * HALF);
+            }
+            continue;
+          }
           mbar_expect_tx(fb, A_BYTES + B_BYTES);
           if (P.flat)
             tma_load_2d(a_s + s * A_BYTES, &P.a_map[P.term_a[term]][0], fb, kc * BK, m0);
           else
             tma_load_4d(a_s + s * A_BYTES, &P.a_map[P.term_a[term]][ti.map], fb, kc * BK, j0 + ti.dw, i0 + ti.dh, n_img);
-          const CUtensorMap* bm = &P.b_map[P.term_b[term]];
           if (kCluster == 1) {
             if (P.b_mn_major) {
               // boxes of (64 n, 64 k-rows): row = output channel chunk kc, column = tap block + n
@@ -273,8 +306,8 @@ umma_nt_kernel(const __grid_constant__ NtParams P, int pixel_tiles, int n_tiles,
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(BM, kBN, 0, P.b_mn_major ? 1 : 0);
+    if (lane == 0 && (!k2SM || crank == 0)) {
+      const uint32_t idesc = make_idesc(k2SM ? 2 * BM : BM, kBN, 0, P.b_mn_major ? 1 : 0);
       int kq = 0, tcount = 0;
       for (int tile = tile0; tile < total_tiles; tile += tile_step, ++tcount) {
         const int sp = tile % splits;
@@ -294,13 +327,16 @@ umma_nt_kernel(const __grid_constant__ NtParams P, int pixel_tiles, int n_tiles,
             const uint64_t ad = desc_kmajor_sw128(a_s + s * A_BYTES + kk * 32);
             const uint64_t bd = P.b_mn_major ? desc_mnmajor_sw128(b_s + s * B_BYTES + kk * 2048, 64 * BK * 2)
                                              : desc_kmajor_sw128(b_s + s * B_BYTES + kk * 32);
-            umma_bf16(d_tmem, ad, bd, idesc, (it > it_begin || kk > 0) ? 1u : 0u);
+            if (k2SM) umma_bf16_2sm(d_tmem, ad, bd, idesc, (it > it_begin || kk > 0) ? 1u : 0u);
+            else umma_bf16(d_tmem, ad, bd, idesc, (it > it_begin || kk > 0) ? 1u : 0u);
           }
           // the stage is reusable only when BOTH CTAs are done with it (multicast writes into both)
-          if (kCluster == 1) umma_commit(empty0 + 8 * s);
+          if (k2SM) umma_commit_2sm(empty0 + 8 * s, 3);
+          else if (kCluster == 1) umma_commit(empty0 + 8 * s);
           else umma_commit_mc(empty0 + 8 * s, (uint16_t)((1u << kCluster) - 1u));
         }
-        umma_commit(tfull0 + 8 * buf);
+        if (k2SM) umma_commit_2sm(tfull0 + 8 * buf, 3);   // each CTA's epilogue drains its own 128 accumulator rows
+        else umma_commit(tfull0 + 8 * buf);
       }
     }
   } else {
@@ -342,18 +378,19 @@ umma_nt_kernel(const __grid_constant__ NtParams P, int pixel_tiles, int n_tiles,
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0u;
         }
-        nt_epilogue_chunk(P, v, row_off, valid, c0 + cc * 32, raw, partial, epi_stage + (warp - 2) * 4096, lane);
+        if (!(P.dbg & 2)) nt_epilogue_chunk(P, v, row_off, valid, c0 + cc * 32, raw, partial, epi_stage + (warp - 2) * 4096, lane);
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+      if (lane == 0) { if (k2SM) mbar_arrive_cluster(tempty0 + 8 * buf, 0); else mbar_arrive(tempty0 + 8 * buf); }
     }
   }
+  tc_fence_before();
   __syncthreads();
   if (kCluster > 1) cluster_sync_all();   // no CTA exits while its peer may still multicast into it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (k2SM) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -583,7 +620,8 @@ umma_tn_kernel(const __grid_constant__ TnParams P, int co_tiles, int ci_tiles, i
           if (ncols == 32 && (P.Cin & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
             warp_store_rows_f32(v, o, epi_stage + (warp - 2) * 4096, lane);
           } else if (o) {
-            for (int j = 0; j < ncols; ++j) o[j] = __uint_as_float(v[j]);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < ncols) o[j] = __uint_as_float(v[j]);   // compile-time indices keep v[] in registers
           }
         }
       }
@@ -831,7 +869,7 @@ static int pick_splits_persistent(long long tiles, int k_iters) {
   return s < 1 ? 1 : s;
 }
 
-template <int kBN, int kCluster>
+template <int kBN, int kCluster, bool k2SM = false>
 static int launch_nt_t(NtParams& P, long long pixel_tiles, int k_iters, void* ws_part, size_t part_cap, cudaStream_t st) {
   const int n_tiles = (P.Cout + kBN - 1) / kBN;
   const long long super_tiles = (pixel_tiles + kCluster - 1) / kCluster;
@@ -841,7 +879,7 @@ static int launch_nt_t(NtParams& P, long long pixel_tiles, int k_iters, void* ws
   P.partial = (float*)ws_part;
   const long long total = super_tiles * n_tiles * splits;   // cluster-level tile units
   DA_REQUIRE(total * kCluster <= 0x7fffffffll, DA_ERR_UNSUPPORTED, "umma: too many tiles");
-  auto kern = umma_nt_kernel<kBN, kCluster>;
+  auto kern = umma_nt_kernel<kBN, kCluster, k2SM>;
   static bool attr_set = false;
   if (!attr_set) {
     DA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<kBN>::SMEM));
@@ -880,20 +918,24 @@ static int launch_nt_t(NtParams& P, long long pixel_tiles, int k_iters, void* ws
   }
   return DA_OK;
 }
-// CTAs per cluster: pixel tiles that share one weight (B) tile.  4 when the pixel tiles divide evenly (a phantom
-// tile of an odd tail would idle a whole SM), else 2.
+// Cluster shape of the forward / data-gradient GEMM:
+//   pair (2 CTAs, ONE cta_group::2 MMA over 256 pixel rows) when the pixel tiles pair up and the tile is 256 wide;
+//   else 2 CTAs sharing the weight tile through TMA multicast; else single CTAs.
+static inline bool nt_pair_mma(int bn, long long pixel_tiles) {
+  return bn == 256 && pixel_tiles >= 2 && pixel_tiles % 2 == 0 && getenv("DA_UMMA_NO_2SM") == nullptr;
+}
 static inline int nt_cluster(int bn, long long pixel_tiles) {
-  if (pixel_tiles >= 4 && pixel_tiles % 4 == 0 && bn == 256) return 4;
+  (void)bn;
   return pixel_tiles >= 2 ? 2 : 1;
 }
 
 static int launch_nt(NtParams& P, int bn, long long pixel_tiles, int k_iters, void* ws_part, size_t part_cap, cudaStream_t st) {
+  { const char* e = getenv("DA_UMMA_DBG"); P.dbg = e ? atoi(e) : 0; }
+  if (nt_pair_mma(bn, pixel_tiles)) return launch_nt_t<256, 2, true>(P, pixel_tiles, k_iters, ws_part, part_cap, st);
   const int cl = nt_cluster(bn, pixel_tiles);   // CTAs sharing the weight tile through TMA multicast
-  if (bn == 256) {
-    if (cl == 4) return launch_nt_t<256, 4>(P, pixel_tiles, k_iters, ws_part, part_cap, st);
+  if (bn == 256)
     return cl == 2 ? launch_nt_t<256, 2>(P, pixel_tiles, k_iters, ws_part, part_cap, st)
                    : launch_nt_t<256, 1>(P, pixel_tiles, k_iters, ws_part, part_cap, st);
-  }
   return cl == 2 ? launch_nt_t<128, 2>(P, pixel_tiles, k_iters, ws_part, part_cap, st)
                  : launch_nt_t<128, 1>(P, pixel_tiles, k_iters, ws_part, part_cap, st);
 }
