@@ -68,6 +68,11 @@ inline int num_sms() {
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // ---- device helpers --------------------------------------------------------------------
+// Programmatic dependent launch: a kernel launched with the programmatic-serialization attribute may start (and run
+// its prologue: barrier init, TMEM allocation, descriptor prefetch) while its predecessor drains; it must not touch
+// global memory before pdl_wait().  pdl_launch_dependents() lets the successor start early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -21,6 +21,7 @@ void set_error(const char* fmt, ...) {
 // [N][C][HW] -> [N][HW][C] (and the reverse), 32x32 tiles through padded smem
 template <typename TS, typename TD>
 __global__ void transpose_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int rows, int cols) {
+  pdl_launch_dependents();
   // src is [rows][cols] per batch (blockIdx.z), dst is [cols][rows]
   __shared__ float tile[32][33];
   const size_t boff = (size_t)blockIdx.z * rows * cols;
@@ -38,12 +39,14 @@ __global__ void transpose_kernel(const TS* __restrict__ src, TD* __restrict__ ds
 
 template <typename TS, typename TD>
 __global__ void cast_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int64_t n, float mul) {
+  pdl_launch_dependents();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     dst[i] = from_f32<TD>(to_f32<TS>(src[i]) * mul);
 }
 
 __global__ void split_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi,
                                   __nv_bfloat16* __restrict__ lo, int64_t n) {
+  pdl_launch_dependents();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float v = src[i];
     const __nv_bfloat16 h = __float2bfloat16_rn(v);
@@ -63,6 +66,7 @@ __global__ void dropout_mask_kernel(uint64_t seed0, const unsigned long long* ct
 // torch's multi-tensor passes plus a separate fp32->bf16 cast of every weight each step.
 __global__ void sgd_step_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ buf,
                                 int64_t n, float lr, float mu, float wd, int first, __nv_bfloat16* __restrict__ shadow) {
+  pdl_launch_dependents();
   const int64_t n4 = n >> 2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 wv = reinterpret_cast<float4*>(w)[i];

@@ -116,6 +116,7 @@ __global__ void ce2_fwd_kernel(const float* __restrict__ z, const int32_t* __res
 __global__ void ce2_bwd_kernel(const float* __restrict__ z, const int32_t* __restrict__ labels, int R,
                                int on_sigmoid, const float* __restrict__ grad_loss, float scale,
                                const float* __restrict__ grad_pred, float* __restrict__ dz) {
+  pdl_launch_dependents();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= R) return;
   const float g = (grad_loss ? grad_loss[0] : 1.f) * scale / (float)R;
@@ -195,6 +196,7 @@ __global__ void consistency_bwd_kernel(const float* __restrict__ img_logits, int
                                        int R, const float* __restrict__ mean_in,
                                        const float* __restrict__ grad_loss, float scale,
                                        float* __restrict__ d_img, float* __restrict__ d_pred) {
+  pdl_launch_dependents();
   __shared__ float red[33];
   const float g = (grad_loss ? grad_loss[0] : 1.f) * scale;
   const float m = mean_in[0];
@@ -372,6 +374,7 @@ __global__ void avgpool_bwd_kernel(const float* __restrict__ dy, int HW, int C, 
 // softmax over the query axis (dim 0 of s[q,k]); block (32,32): 32 columns x 32 row lanes
 // ---------------------------------------------------------------------------------------
 __global__ void softmax_dim0_fwd_kernel(const float* __restrict__ s, int T, int ld, float* __restrict__ p) {
+  pdl_launch_dependents();
   __shared__ float red[32][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int k = blockIdx.x * 32 + tx;
@@ -394,6 +397,7 @@ __global__ void softmax_dim0_fwd_kernel(const float* __restrict__ s, int T, int 
 }
 __global__ void softmax_dim0_bwd_kernel(const float* __restrict__ p, const float* __restrict__ dp, int T, int ld,
                                         float* __restrict__ ds) {
+  pdl_launch_dependents();
   __shared__ float red[32][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int k = blockIdx.x * 32 + tx;

@@ -270,6 +270,7 @@ simt_conv_wgrad_kernel(ConvGeom g, const T* __restrict__ x, const T* __restrict_
 }
 
 __global__ void splitk_reduce_kernel(const float* __restrict__ part, int ksplit, int64_t n, float* __restrict__ out) {
+  pdl_launch_dependents();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float acc = 0.f;
     for (int s = 0; s < ksplit; ++s) acc += part[(size_t)s * n + i];
@@ -287,6 +288,7 @@ __global__ void __launch_bounds__(256)
 thin_fwd_kernel(int64_t M, int K, int Cout, const T* __restrict__ x, const T* __restrict__ w,
                 const float* __restrict__ scale, const float* __restrict__ shift, int relu, float drop_p, uint64_t seed0,
                 const unsigned long long* seed_ctr, TY* __restrict__ y) {
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // one warp per row
   if (m >= M) return;
@@ -320,6 +322,7 @@ template <typename T, typename TX>
 __global__ void __launch_bounds__(256)
 thin_dgrad_kernel(int64_t M, int K, int Cout, const T* __restrict__ dz, const T* __restrict__ w, float out_scale,
                   TX* __restrict__ dx) {
+  pdl_launch_dependents();
   const int64_t total = M * K;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t m = i / K;
@@ -335,6 +338,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 thin_wgrad_kernel(int64_t M, int K, int Cout, const T* __restrict__ x, const T* __restrict__ dz, float* __restrict__ part,
                   int msplit) {
+  pdl_launch_dependents();
   __shared__ float red[8][THIN_MAX][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = blockIdx.x * 32 + lane;
@@ -376,6 +380,7 @@ __global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y
                                const float* __restrict__ scale, int relu, float drop_p, uint64_t seed0,
                                const unsigned long long* seed_ctr,
                                T* __restrict__ dz, float* __restrict__ partial, float* __restrict__ partial2) {
+  pdl_launch_dependents();
   const uint64_t seed = effective_seed(seed0, seed_ctr);
   const int AB_ROWS = ab_rows(M);
   const int64_t m0 = (int64_t)blockIdx.x * AB_ROWS;
@@ -403,6 +408,7 @@ __global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y
 }
 // out[c] = sum_b partial[b][c]; block (32 columns x 32 row lanes), coalesced rows, smem tree over the lanes
 __global__ void colsum_final_kernel(const float* __restrict__ partial, int nb, int C, float* __restrict__ out) {
+  pdl_launch_dependents();
   __shared__ float red[32][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int c = blockIdx.x * 32 + tx;

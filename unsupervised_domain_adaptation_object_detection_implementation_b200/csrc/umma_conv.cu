@@ -224,12 +224,14 @@ umma_nt_kernel(const __grid_constant__ NtParams P, int pixel_tiles, int n_tiles,
     for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, k2SM ? 2 * NT_EPI_WARPS : NT_EPI_WARPS); }
     fence_barrier_init();
   }
+  pdl_launch_dependents();   // the next kernel of the stream may run its prologue under this one
   if (warp == 1) { if (k2SM) tmem_alloc_2sm(tslot, Cfg::TMEM_COLS); else tmem_alloc(tslot, Cfg::TMEM_COLS); }
   tc_fence_before();
   __syncthreads();
   if (kCluster > 1) cluster_sync_all();   // peer barriers are initialised before any multicast lands
   tc_fence_after();
   const uint32_t tmem_base = *tslot_ptr;
+  pdl_wait();                // everything above overlapped the predecessor; global memory is touched only below
 
   if (warp == 0) {
     if (lane == 0) {
@@ -399,6 +401,7 @@ __global__ void nt_splitk_finish_kernel(const float* __restrict__ partial, int s
                                         const float* __restrict__ scale, const float* __restrict__ shift, int relu,
                                         float drop_p, unsigned long long seed0, const unsigned long long* seed_ctr,
                                         float out_scale, void* y, int y_dtype) {
+  pdl_launch_dependents();
   const unsigned long long seed = effective_seed(seed0, seed_ctr);
   const uint32_t thr = drop_threshold(drop_p);
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
@@ -496,12 +499,14 @@ umma_tn_kernel(const __grid_constant__ TnParams P, int co_tiles, int ci_tiles, i
     for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, NT_EPI_WARPS); }
     fence_barrier_init();
   }
+  pdl_launch_dependents();   // the next kernel of the stream may run its prologue under this one
   if (warp == 1) tmem_alloc(tslot, 2 * BN);
   tc_fence_before();
   __syncthreads();
   if (kCluster > 1) cluster_sync_all();   // peer barriers are initialised before any multicast lands
   tc_fence_after();
   const uint32_t tmem_base = *tslot_ptr;
+  pdl_wait();                // everything above overlapped the predecessor; global memory is touched only below
 
   // tile index -> (co tile of this CTA, ci tile, tap, split); co is the fastest index so that concurrently
   // running clusters read the same X tiles (L2 reuse)
@@ -641,6 +646,7 @@ umma_tn_kernel(const __grid_constant__ TnParams P, int co_tiles, int ci_tiles, i
 }
 
 __global__ void sum_splits_kernel(const float* __restrict__ part, int splits, long long n, float* __restrict__ out) {
+  pdl_launch_dependents();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float acc = 0.f;
     for (int s = 0; s < splits; ++s) acc += part[(size_t)s * n + i];
@@ -890,13 +896,15 @@ static int launch_nt_t(NtParams& P, long long pixel_tiles, int k_iters, void* ws
   cfg.blockDim = dim3(NT_FWD_THREADS);
   cfg.dynamicSmemBytes = TileCfg<kBN>::SMEM;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kCluster;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see pdl_wait() in the kernel
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = getenv("DA_NO_PDL") ? 1 : 2;
   // persistent grid = the clusters that are co-resident (GPC sizes need not be multiples of the cluster size)
   static int max_clusters = 0;
   if (max_clusters == 0) {
@@ -1105,13 +1113,15 @@ static int launch_tn_t(const TnParams& P, int co_tiles, int ci_tiles, int splits
   cfg.blockDim = dim3(NT_FWD_THREADS);
   cfg.dynamicSmemBytes = TileCfg<kBN>::SMEM;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kCluster;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see pdl_wait() in the kernel
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = getenv("DA_NO_PDL") ? 1 : 2;
   // persistent grid = the clusters that are co-resident (GPC sizes need not be multiples of the cluster size)
   static int max_clusters = 0;
   if (max_clusters == 0) {
