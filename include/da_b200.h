@@ -83,6 +83,21 @@ int da_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n,
  * w_bf16 (nullable): bf16 shadow of w refreshed in the same pass (operand of the tcgen05 engine). */
 int da_sgd_step(float* w, const float* grad, float* momentum_buf, int64_t n, float lr, float momentum,
                 float weight_decay, int first_step, void* w_bf16, da_stream_t stream);
+/* The same update for MANY tensors in one launch (torch.optim.SGD's foreach path, mmdet/apis/train.py:127).
+ * `entries` is a DEVICE array of n_entries records; `chunks` a DEVICE array of n_chunks (entry, chunk) pairs that
+ * tiles every tensor in pieces of DA_SGD_CHUNK elements (built once by the caller: sizes do not change). */
+#define DA_SGD_CHUNK 65536
+typedef struct da_sgd_entry {
+  float* w;              /* fp32 weights, 16-byte aligned */
+  const float* grad;     /* fp32 gradient, same memory order */
+  float* momentum_buf;   /* fp32 momentum buffer */
+  void* w_bf16;          /* optional bf16 shadow (NULL = none) */
+  int64_t n;             /* elements */
+  int32_t first_step;    /* 1 = the buffer is uninitialised (torch's first-step rule: buf = d) */
+  int32_t _pad;
+} da_sgd_entry;
+int da_sgd_step_multi(const da_sgd_entry* entries, int n_entries, const int32_t* chunks, int n_chunks,
+                      float lr, float momentum, float weight_decay, da_stream_t stream);
 
 /* ---- RoIAlign ------------------------------------------------------------
  * Replaces mmcv.ops.RoIAlign (ext_module.roi_align_forward / roi_align_backward,

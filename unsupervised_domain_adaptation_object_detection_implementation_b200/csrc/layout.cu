@@ -120,6 +120,47 @@ static int transpose_dispatch(const void* src, int sd, void* dst, int dd, int ba
   DA_REQUIRE(false, DA_ERR_INVALID_ARG, "transpose: bad dtype %d/%d", sd, dd);
 }
 
+// one block per (tensor, 64K-element chunk): the 17 small tensors of a head ride along with the big FC weight
+__global__ void __launch_bounds__(256)
+sgd_step_multi_kernel(const da_sgd_entry* __restrict__ entries, const int32_t* __restrict__ chunks, float lr, float mu, float wd) {
+  pdl_launch_dependents();
+  const da_sgd_entry e = entries[chunks[2 * blockIdx.x]];
+  const int64_t lo = (int64_t)chunks[2 * blockIdx.x + 1] * DA_SGD_CHUNK;
+  const int64_t hi = lo + DA_SGD_CHUNK < e.n ? lo + DA_SGD_CHUNK : e.n;
+  const bool first = e.first_step != 0;
+  __nv_bfloat16* shadow = reinterpret_cast<__nv_bfloat16*>(e.w_bf16);
+  const int64_t hi4 = lo + ((hi - lo) & ~(int64_t)3);
+  for (int64_t i = lo + 4 * (int64_t)threadIdx.x; i < hi4; i += 4 * 256) {
+    float4 wv = *reinterpret_cast<float4*>(e.w + i);
+    const float4 gv = *reinterpret_cast<const float4*>(e.grad + i);
+    float4 bv = first ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<float4*>(e.momentum_buf + i);
+    float* wp = &wv.x; const float* gp = &gv.x; float* bp = &bv.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float d = fmaf(wd, wp[j], gp[j]);
+      bp[j] = first ? d : fmaf(mu, bp[j], d);
+      wp[j] = fmaf(-lr, bp[j], wp[j]);
+    }
+    *reinterpret_cast<float4*>(e.w + i) = wv;
+    *reinterpret_cast<float4*>(e.momentum_buf + i) = bv;
+    if (shadow) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(wv.x, wv.y), b = __floats2bfloat162_rn(wv.z, wv.w);
+      uint2 u;
+      u.x = *reinterpret_cast<unsigned*>(&a); u.y = *reinterpret_cast<unsigned*>(&b);
+      *reinterpret_cast<uint2*>(shadow + i) = u;
+    }
+  }
+  const int64_t i = hi4 + threadIdx.x;   // tail of the tensor (< 4 elements)
+  if (i < hi) {
+    const float d = fmaf(wd, e.w[i], e.grad[i]);
+    const float b = first ? d : fmaf(mu, e.momentum_buf[i], d);
+    e.momentum_buf[i] = b;
+    const float wn = fmaf(-lr, b, e.w[i]);
+    e.w[i] = wn;
+    if (shadow) shadow[i] = __float2bfloat16_rn(wn);
+  }
+}
+
 }  // namespace da
 
 using namespace da;
@@ -182,6 +223,16 @@ extern "C" int da_sgd_step(float* w, const float* grad, float* momentum_buf, int
              DA_ERR_INVALID_ARG, "sgd_step: pointers must be 16-byte aligned");
   sgd_step_kernel<<<ew_blocks((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(w, grad, momentum_buf, n, lr, momentum, weight_decay,
                                                                            first_step, (__nv_bfloat16*)w_bf16);
+  DA_LAUNCH_CHECK();
+  return DA_OK;
+}
+
+extern "C" int da_sgd_step_multi(const da_sgd_entry* entries, int n_entries, const int32_t* chunks, int n_chunks,
+                                 float lr, float momentum, float weight_decay, da_stream_t stream) {
+  DA_REQUIRE(n_entries >= 0 && n_chunks >= 0, DA_ERR_INVALID_ARG, "sgd_step_multi: negative counts");
+  if (n_entries == 0 || n_chunks == 0) return DA_OK;
+  DA_REQUIRE(entries && chunks, DA_ERR_INVALID_ARG, "sgd_step_multi: null table");
+  sgd_step_multi_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(entries, chunks, lr, momentum, weight_decay);
   DA_LAUNCH_CHECK();
   return DA_OK;
 }

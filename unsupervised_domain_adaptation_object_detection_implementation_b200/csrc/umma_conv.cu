@@ -1200,7 +1200,8 @@ int umma_conv_backward_weight(const da_conv_desc* d, const void* x, const void* 
     patches = (long long)g.N * P.tiles_h * P.tiles_w;
   }
   // weight-gradient tiles are [128 Cout x bn Cin] per tap; K runs over the pixels
-  const int bn = (g.Cin > 128 && (long long)((g.Cout + BM - 1) / BM) * ((g.Cin + 255) / 256) * P.num_taps >= num_sms() / 2) ? 256 : 128;
+  const int bn = (g.Cin > 128 && ((long long)((g.Cout + BM - 1) / BM) * ((g.Cin + 255) / 256) * P.num_taps >= num_sms() / 2 ||
+                                   patches * P.num_terms >= 64)) ? 256 : 128;   // short pixel loops: more, narrower tiles instead of split-K
   const long long tiles = (long long)((g.Cout + BM - 1) / BM) * ((g.Cin + bn - 1) / bn) * P.num_taps;
   long long k_iters = patches * P.num_terms;
   int splits = pick_splits_persistent(tiles, (int)(k_iters > 1000000 ? 1000000 : k_iters));

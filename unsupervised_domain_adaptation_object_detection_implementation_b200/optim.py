@@ -7,6 +7,8 @@ import torch
 from . import functional as F_
 from ._lib import lib, check
 
+_CHUNK = 65536   # DA_SGD_CHUNK (include/da_b200.h)
+
 
 class FusedSGD:
     def __init__(self, params, lr=1e-3, momentum=0.9, weight_decay=0.0, shadow_bf16=True):
@@ -15,6 +17,7 @@ class FusedSGD:
         self.shadow_bf16 = shadow_bf16
         self.state = {}
         self.steps = 0
+        self._chunks, self._chunk_key, self._keep, self._host, self._table, self._copied = None, None, None, None, None, None
 
     def zero_grad(self, set_to_none=True):
         for p in self.params:
@@ -25,6 +28,9 @@ class FusedSGD:
 
     @torch.no_grad()
     def step(self):
+        """One launch for all parameters (da_sgd_step_multi): the per-tensor records {w, grad, buf, shadow, n, first}
+        go to the device as one small table; the (tensor, chunk) tiling is built once."""
+        rows, keep = [], []
         for p in self.params:
             g = p.grad
             if g is None:
@@ -35,13 +41,43 @@ class FusedSGD:
                 raise RuntimeError("FusedSGD needs densely stored parameters")
             if g.dtype != torch.float32 or g.stride() != p.stride():
                 g = torch.empty_like(p).copy_(g)      # same memory order as the parameter
+                keep.append(g)
             st = self.state.get(id(p))
             first = st is None
             if first:
                 st = self.state[id(p)] = torch.empty_like(p)
-            shadow = None
-            if self.shadow_bf16 and p.dim() >= 2:
-                shadow = F_.bf16_shadow(p)
-            check(lib.da_sgd_step(F_._ptr(p), F_._ptr(g), F_._ptr(st), p.numel(), self.lr, self.momentum,
-                                  self.weight_decay, int(first), F_._ptr(shadow), F_._stream()), "sgd_step")
+            shadow = F_.bf16_shadow(p) if (self.shadow_bf16 and p.dim() >= 2) else None
+            for t in (p, g, st):
+                if t.data_ptr() % 16:
+                    raise RuntimeError("FusedSGD: tensors must be 16-byte aligned")
+            rows.append((p.data_ptr(), g.data_ptr(), st.data_ptr(), shadow.data_ptr() if shadow is not None else 0,
+                         p.numel(), int(first)))
+        if not rows:
+            self.steps += 1
+            return
+        dev = self.params[0].device
+        sizes = tuple(r[4] for r in rows)
+        if self._chunks is None or self._chunk_key != sizes:
+            ch = [(i, c) for i, n in enumerate(sizes) for c in range((n + _CHUNK - 1) // _CHUNK)]
+            self._chunks = torch.tensor(ch, dtype=torch.int32).reshape(-1, 2).to(dev)
+            self._chunk_key = sizes
+        # table of da_sgd_entry records (6 x int64 each; first_step sits in the low 32 bits of the last word).  The pinned
+        # staging buffer and the device table are allocated once (first eager step), so a captured step only holds a copy node.
+        if self._host is None or self._host[0].shape[0] < len(rows):
+            self._host = [torch.empty((len(self.params), 6), dtype=torch.int64).pin_memory() for _ in range(2)]
+            self._table = torch.empty((len(self.params), 6), dtype=torch.int64, device=dev)
+            self._copied = [None, None]
+        slot = self.steps & 1
+        capturing = torch.cuda.is_current_stream_capturing()
+        if self._copied[slot] is not None and not capturing:
+            self._copied[slot].synchronize()          # the copy that last read this staging buffer has run
+        self._host[slot][:len(rows)] = torch.tensor(rows, dtype=torch.int64)
+        table = self._table
+        table[:len(rows)].copy_(self._host[slot][:len(rows)], non_blocking=True)
+        if not capturing:
+            self._copied[slot] = torch.cuda.Event()
+            self._copied[slot].record()
+        self._keep = keep   # alive until the next step
+        check(lib.da_sgd_step_multi(F_._ptr(table), len(rows), F_._ptr(self._chunks), self._chunks.shape[0], self.lr,
+                                    self.momentum, self.weight_decay, F_._stream()), "sgd_step_multi")
         self.steps += 1
