@@ -40,7 +40,7 @@ constexpr int MAX_TAPS = 16;
 // under the 128 B/clk SMEM port; BN = 128 serves narrow outputs.  Two TMEM accumulators (2*BN
 // columns) let the epilogue of tile i overlap the MMAs of tile i+1 (persistent kernel).
 template <int kBN> struct TileCfg {
-  static constexpr int STAGES = (kBN == 256) ? 4 : 6;
+  static constexpr int STAGES = (kBN == 256) ? 4 : (kBN == 128 ? 6 : 8);
   static constexpr int B_BYTES = kBN * BK * 2;
   static constexpr size_t SMEM = 1024 + (size_t)STAGES * (A_BYTES + B_BYTES) + 256 + NT_EPI_WARPS * 4096;   // + epilogue staging
   static constexpr int TMEM_COLS = 2 * kBN;
@@ -860,9 +860,13 @@ static void set_terms(int engine, int* num_terms, int* ta, int* tb) {
 // 128x256 tiles unless that leaves most SMs idle on a short-K problem (the instance-head FCs: M = N = 1024,
 // K <= 1024): there 128x128 tiles double the CTA count and make split-K (and its finish kernel) unnecessary.
 static inline int choose_bn(int ncols, long long m_rows, long long k_iters) {
-  if (ncols <= 128) return 128;
-  const long long tiles256 = ((m_rows + BM - 1) / BM) * ((ncols + 255) / 256);
-  return (tiles256 >= num_sms() / 2 || k_iters >= 64) ? 256 : 128;
+  if (ncols <= 64) return 64;
+  const long long mt = (m_rows + BM - 1) / BM;
+  const bool short_k = k_iters < 64;
+  if (ncols > 128 && (mt * ((ncols + 255) / 256) >= num_sms() / 2 || !short_k)) return 256;
+  // short-K problems that do not fill the machine with 128-wide tiles: 128x64 tiles (twice the CTAs)
+  if (short_k && mt * ((ncols + 127) / 128) < num_sms() / 2 && getenv("DA_UMMA_NO_BN64") == nullptr) return 64;
+  return 128;
 }
 
 static int pick_splits_persistent(long long tiles, int k_iters) {
@@ -944,6 +948,9 @@ static int launch_nt(NtParams& P, int bn, long long pixel_tiles, int k_iters, vo
   if (bn == 256)
     return cl == 2 ? launch_nt_t<256, 2>(P, pixel_tiles, k_iters, ws_part, part_cap, st)
                    : launch_nt_t<256, 1>(P, pixel_tiles, k_iters, ws_part, part_cap, st);
+  if (bn == 64)   // an MN-major B tile of 64 channels is ONE 64x64 box: nothing to split across a multicast pair
+    return (cl == 2 && !P.b_mn_major) ? launch_nt_t<64, 2>(P, pixel_tiles, k_iters, ws_part, part_cap, st)
+                                      : launch_nt_t<64, 1>(P, pixel_tiles, k_iters, ws_part, part_cap, st);
   return cl == 2 ? launch_nt_t<128, 2>(P, pixel_tiles, k_iters, ws_part, part_cap, st)
                  : launch_nt_t<128, 1>(P, pixel_tiles, k_iters, ws_part, part_cap, st);
 }
@@ -1200,8 +1207,14 @@ int umma_conv_backward_weight(const da_conv_desc* d, const void* x, const void* 
     patches = (long long)g.N * P.tiles_h * P.tiles_w;
   }
   // weight-gradient tiles are [128 Cout x bn Cin] per tap; K runs over the pixels
-  const int bn = (g.Cin > 128 && ((long long)((g.Cout + BM - 1) / BM) * ((g.Cin + 255) / 256) * P.num_taps >= num_sms() / 2 ||
-                                   patches * P.num_terms >= 64)) ? 256 : 128;   // short pixel loops: more, narrower tiles instead of split-K
+  // weight-gradient tiles are [128 Cout x bn Cin] per tap; K runs over the pixels.  Short pixel loops: more, narrower
+  // tiles instead of split-K.
+  const long long co_t = (g.Cout + BM - 1) / BM;
+  const bool short_k = patches * P.num_terms < 64;
+  int bn = 128;
+  if (g.Cin <= 64) bn = 64;
+  else if (g.Cin > 128 && (co_t * ((g.Cin + 255) / 256) * P.num_taps >= num_sms() / 2 || !short_k)) bn = 256;
+  else if (short_k && co_t * ((g.Cin + 127) / 128) * P.num_taps < num_sms() / 2 && getenv("DA_UMMA_NO_BN64") == nullptr) bn = 64;
   const long long tiles = (long long)((g.Cout + BM - 1) / BM) * ((g.Cin + bn - 1) / bn) * P.num_taps;
   long long k_iters = patches * P.num_terms;
   int splits = pick_splits_persistent(tiles, (int)(k_iters > 1000000 ? 1000000 : k_iters));
@@ -1214,6 +1227,8 @@ int umma_conv_backward_weight(const da_conv_desc* d, const void* x, const void* 
     if (co_tiles >= 4) rc2 = launch_tn_t<256, 4>(P, co_tiles, ci_tiles, splits, st);
     else if (co_tiles >= 2) rc2 = launch_tn_t<256, 2>(P, co_tiles, ci_tiles, splits, st);
     else rc2 = launch_tn_t<256, 1>(P, co_tiles, ci_tiles, splits, st);
+  } else if (bn == 64) {
+    rc2 = launch_tn_t<64, 1>(P, co_tiles, ci_tiles, splits, st);
   } else {
     if (co_tiles >= 2) rc2 = launch_tn_t<128, 2>(P, co_tiles, ci_tiles, splits, st);
     else rc2 = launch_tn_t<128, 1>(P, co_tiles, ci_tiles, splits, st);

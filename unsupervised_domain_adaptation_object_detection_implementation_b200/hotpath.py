@@ -35,6 +35,17 @@ def domain_tensor(gt_da, device):
     return t
 
 
+def roi_domain_labels(counts, device):
+    """Per-RoI domain labels (image 0 = source, image 1 = target), cached per (counts, device): a constant of the
+    step, not three fill/cat kernels per iteration."""
+    key = ("roi_labels", counts, str(device))
+    t = _CONST.get(key)
+    if t is None:
+        t = torch.cat([torch.full((n,), d, dtype=torch.long, device=device) for n, d in zip(counts, (0, 1))])
+        _CONST[key] = t
+    return t
+
+
 class SharedFCs(nn.Module):
     """Shared2FCBBoxHead's shared_fcs as used by forward_train_da
     (mmdet/models/roi_heads/bbox_heads/convfc_bbox_head.py:198-237): flatten(1) -> FC -> ReLU -> FC -> ReLU.
@@ -82,8 +93,7 @@ class DAFOrgHotPath(nn.Module):
         rois = bbox2roi(proposal_list)
         roi_feats = self.bbox_roi_extractor([c5], rois)
         bbox_feats = self.bbox_head(roi_feats) if self.bbox_head is not None else roi_feats.flatten(1)
-        label_da = torch.cat([torch.full((len(p),), int(d), dtype=torch.long, device=c5.device)
-                              for p, d in zip(proposal_list, (0, 1))]) if len(proposal_list) == 2 else \
+        label_da = roi_domain_labels(tuple(len(p) for p in proposal_list), c5.device) if len(proposal_list) == 2 else \
             rois[:, 0].long().clamp(max=1)
         ins_loss, ins_preds = da_losses.instance_ce_loss(self.local_da.forward_logits(bbox_feats), label_da)
         consist = da_losses.consistency_loss(imgs_feat, ins_preds, label_da)
@@ -139,7 +149,9 @@ class MAFHotPath(nn.Module):
 
 def parse_losses(losses):
     """mmdet/models/detectors/base.py:176-219: total = sum of every entry whose key contains 'loss'."""
-    log_vars = {k: v.mean() if torch.is_tensor(v) else sum(x.mean() for x in v) for k, v in losses.items()}
+    def _mean(v):   # the DA losses are device scalars already: no reduction kernel for a 0-d tensor
+        return v if v.dim() == 0 else v.mean()
+    log_vars = {k: _mean(v) if torch.is_tensor(v) else sum(_mean(x) for x in v) for k, v in losses.items()}
     loss = sum(v for k, v in log_vars.items() if "loss" in k)
     log_vars["loss"] = loss
     return loss, log_vars
