@@ -63,6 +63,7 @@ struct NtParams {
   int b_mn_major;           // B tile is [k rows][n contiguous] (weights read untransposed for dgrad)
   int b_col0;               // MN-major B: column offset of n = 0 inside the B matrix (unused)
   int flat;                 // A is a flat [M,K] matrix (1x1 / FC)
+  int pix_fast;             // tile order: pixel tiles fastest (the weight operand is the big one and is streamed once)
   int BH, BW, bw_shift;     // patch shape (BH*BW == 128, powers of two)
   int TH, TW;               // extent of the tile grid in (class) pixels
   int tiles_h, tiles_w;
@@ -237,7 +238,9 @@ umma_nt_kernel(const __grid_constant__ NtParams P, int pixel_tiles, int n_tiles,
     if (lane == 0) {
       int kq = 0;
       for (int tile = tile0; tile < total_tiles; tile += tile_step) {
-        const int sp = tile % splits, nt = (tile / splits) % n_tiles, pt = (tile / (splits * n_tiles)) * kCluster + crank;
+        const int sp = tile % splits, rest = tile / splits;
+        const int nt = P.pix_fast ? rest / super_tiles : rest % n_tiles;
+        const int pt = (P.pix_fast ? rest % super_tiles : rest / n_tiles) * kCluster + crank;
         const int c0 = nt * kBN;
         int n_img = 0, i0 = 0, j0 = 0, m0 = 0;
         if (P.flat) {
@@ -348,7 +351,9 @@ umma_nt_kernel(const __grid_constant__ NtParams P, int pixel_tiles, int n_tiles,
     const int r = q * 32 + lane;  // accumulator row == pixel within the tile
     int tcount = 0;
     for (int tile = tile0; tile < total_tiles; tile += tile_step, ++tcount) {
-      const int sp = tile % splits, nt = (tile / splits) % n_tiles, pt = (tile / (splits * n_tiles)) * kCluster + crank;
+      const int sp = tile % splits, rest = tile / splits;
+      const int nt = P.pix_fast ? rest / super_tiles : rest % n_tiles;
+      const int pt = (P.pix_fast ? rest % super_tiles : rest / n_tiles) * kCluster + crank;
       const int c0 = nt * kBN;
       const int it_begin = sp * per_split, it_end = min(it_begin + per_split, total_iters);
       const bool has_k = it_end > it_begin;
@@ -943,6 +948,8 @@ static inline int nt_cluster(int bn, long long pixel_tiles) {
 
 static int launch_nt(NtParams& P, int bn, long long pixel_tiles, int k_iters, void* ws_part, size_t part_cap, cudaStream_t st) {
   { const char* e = getenv("DA_UMMA_DBG"); P.dbg = e ? atoi(e) : 0; }
+  // concurrently running tiles share the operand whose index is NOT the fastest one; stream the bigger operand once
+  P.pix_fast = ((long long)P.Cout > pixel_tiles * BM) ? 1 : 0;
   if (nt_pair_mma(bn, pixel_tiles)) return launch_nt_t<256, 2, true>(P, pixel_tiles, k_iters, ws_part, part_cap, st);
   const int cl = nt_cluster(bn, pixel_tiles);   // CTAs sharing the weight tile through TMA multicast
   if (bn == 256)
@@ -1224,8 +1231,8 @@ int umma_conv_backward_weight(const da_conv_desc* d, const void* x, const void* 
   // Cout tiles that share an X tile form a cluster (TMA multicast of the shared operand)
   int rc2;
   if (bn == 256) {
-    if (co_tiles >= 4) rc2 = launch_tn_t<256, 4>(P, co_tiles, ci_tiles, splits, st);
-    else if (co_tiles >= 2) rc2 = launch_tn_t<256, 2>(P, co_tiles, ci_tiles, splits, st);
+    // clusters of 4 only fit 33 times on the 148 SMs (GPC sizes), pairs fit 74 times
+    if (co_tiles >= 2) rc2 = launch_tn_t<256, 2>(P, co_tiles, ci_tiles, splits, st);
     else rc2 = launch_tn_t<256, 1>(P, co_tiles, ci_tiles, splits, st);
   } else if (bn == 64) {
     rc2 = launch_tn_t<64, 1>(P, co_tiles, ci_tiles, splits, st);
