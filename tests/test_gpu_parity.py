@@ -162,6 +162,36 @@ def test_roi_align_tensor_core_path_full_size():
     assert rel_err(got, torch.from_numpy(ref)) <= 1e-2
 
 
+@pytest.mark.parametrize("N,C,H,W,R", [(3, 328, 37, 53, 1500), (2, 8, 20, 30, 64), (1, 512, 16, 16, 1100)])
+def test_roi_align_tensor_core_backward_vs_oracle(N, C, H, W, R):
+    """bf16 gradients take the tcgen05 gather kernel (TMEM-resident tile accumulators).  Ragged shapes: channel counts
+    that are not a multiple of the 256-channel CTA slice, partial 16x16 pixel tiles, more RoIs than one list chunk
+    (1024), adversarial boxes.  Reference: the fp64 oracle backward on the SAME bf16-rounded cotangent."""
+    stride = 8
+    rois = torch.cat([seeded.synthetic_rois(R // N, N, H * stride, W * stride, 5, 6.0, 300.0),
+                      seeded.adversarial_rois(N, H * stride, W * stride)])
+    feat = seeded.seeded_tensor("tcb.feat", (N, C, H, W), 5).to(torch.bfloat16)
+    f = feat.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    out = F_.roi_align(f, rois.to(DEV), 7, 1.0 / stride)
+    assert out.dtype == torch.bfloat16
+    cot = seeded.seeded_tensor("tcb.cot", tuple(out.shape), 5).to(torch.bfloat16)
+    (g_tc,) = torch.autograd.grad(out, f, cot.to(DEV), retain_graph=True)
+    assert g_tc.dtype == torch.bfloat16 and g_tc.shape == f.shape
+    gref = torch.from_numpy(oracle_roi.roi_align_backward(cot.float().numpy(), rois.numpy(), (N, C, H, W), 7, 1.0 / stride))
+    # bf16 tap weights (2^-9) and one bf16 rounding of the result
+    assert rel_err(g_tc.float(), gref) <= 1e-2
+    os.environ["DA_ROI_NO_TC"] = "1"      # CUDA-core kernel on the same inputs: fp32 weights, fp32 result
+    try:
+        (g_cc,) = torch.autograd.grad(out, f, cot.to(DEV))
+    finally:
+        del os.environ["DA_ROI_NO_TC"]
+    assert rel_err(g_cc.float(), gref) <= 4e-3
+    # pixels no RoI touches are exactly zero in both
+    untouched = gref == 0
+    if bool(untouched.any()):
+        assert float(g_tc.float()[untouched.to(DEV)].abs().max()) == 0.0
+
+
 def test_single_roi_extractor_and_level_mapping():
     ext = SingleRoIExtractor(dict(type="RoIAlign", output_size=7, sampling_ratio=0), out_channels=16, featmap_strides=[4, 8, 16, 32])
     feats = [seeded.seeded_tensor(f"fpn{i}", (2, 16, 128 >> i, 192 >> i), 0).to(DEV) for i in range(4)]
@@ -320,6 +350,28 @@ def test_dense_layer_engines(engine, tol, case):
     assert rel_err(sc.grad, sr.grad) <= tol * 10
 
 
+@pytest.mark.parametrize("M,K,Nc", [(1024, 1024, 1024),   # short K, few tiles: 128x64 tiles
+                                    (300, 192, 72),        # ragged rows and columns, odd pixel-tile count
+                                    (512, 2048, 512),      # CTA-pair MMA (cta_group::2), long K
+                                    (256, 4096, 264),      # pair MMA with a ragged last column tile
+                                    (130, 64, 8)])         # single 128x64 tile + 2 rows
+def test_fc_tile_variants_bf16(M, K, Nc):
+    """Every tile / cluster variant of the tcgen05 GEMM (forward, data gradient, weight gradient) against fp64 on the
+    same bf16-rounded operands."""
+    uda.set_engine("umma_bf16")
+    x = seeded.seeded_tensor("tv.x", (M, K), 3).to(torch.bfloat16)
+    w = seeded.seeded_tensor("tv.w", (Nc, K), 3, scale=K ** -0.5).to(torch.bfloat16)
+    cot = seeded.seeded_tensor("tv.c", (M, Nc), 3).to(torch.bfloat16)
+    xd = x.to(DEV).view(M, 1, 1, K).requires_grad_(True)
+    wd = w.float().to(DEV).requires_grad_(True)          # fp32 master, bf16 shadow inside
+    y = F_.dense_layer(xd, wd).view(M, Nc)
+    y.backward(cot.to(DEV))
+    X, Wm, Cm = x.double(), w.double(), cot.double()
+    assert rel_err(y.float(), (X @ Wm.t()).float()) <= 1e-2
+    assert rel_err(xd.grad.float().view(M, K), (Cm @ Wm).float()) <= 1e-2
+    assert rel_err(wd.grad, (Cm.t() @ X).float()) <= 1e-3      # fp32 result
+
+
 @pytest.mark.parametrize("engine", ["simt_f32", "umma_bf16x3"])
 def test_dense_layer_dropout_mask_is_exported(engine):
     N, H, W, Cin, Cout = 2, 6, 8, 64, 128
@@ -432,7 +484,7 @@ def test_daf_org_composite_losses_vs_oracle():
 def test_fused_sgd_matches_torch_sgd_and_refreshes_shadow():
     from unsupervised_domain_adaptation_object_detection_implementation_b200 import optim
     torch.manual_seed(0)
-    shapes = [(64, 32, 3, 3), (129,), (40, 70)]
+    shapes = [(64, 32, 3, 3), (129,), (40, 70), (2 * 65536 + 3,), (3,)]   # multi-chunk tensor with a tail, tiny tensor
     ps = [torch.randn(*s, device=DEV).requires_grad_(True) for s in shapes]
     ps[0].data = ps[0].data.contiguous(memory_format=torch.channels_last)
     qs = [p.detach().clone().requires_grad_(True) for p in ps]
