@@ -97,6 +97,23 @@ def global_alignment_head(x, sd, masks=(None, None, None, None), q=None):
 
 
 # --------------------------------------------------------------------------------------
+# I3 RoI-conv LocalAlignmentHead — mmdet/models/roi_heads/local_da.py:47-86 (3x3 s2 x3 on the [k,C,7,7] RoI features,
+# BN (eval) + ReLU + dropout, global average pool, FC 512->2, sigmoid)
+# --------------------------------------------------------------------------------------
+def roi_local_alignment_logits(x, sd, masks=(None, None, None), q=None):
+    x = _q(grl(x), q)
+    x = _q(_drop(F.relu(_bn_eval(F.conv2d(x, _q(sd["conv1.weight"], q), None, 2, 1), sd, "bn1")), masks[0]), q)
+    x = _q(_drop(F.relu(_bn_eval(F.conv2d(x, _q(sd["conv2.weight"], q), None, 2, 1), sd, "bn2")), masks[1]), q)
+    x = _q(_drop(F.relu(_bn_eval(F.conv2d(x, _q(sd["conv3.weight"], q), None, 2, 1), sd, "bn3")), masks[2]), q)
+    x = F.avg_pool2d(x, (x.size(2), x.size(3))).view(x.size(0), -1)
+    return F.linear(x, sd["fc.weight"], sd["fc.bias"])
+
+
+def roi_local_alignment_head(x, sd, masks=(None, None, None), q=None):
+    return torch.sigmoid(roi_local_alignment_logits(x, sd, masks, q))
+
+
+# --------------------------------------------------------------------------------------
 # H4 SRM — mmdet/models/backbones/resnet_da.py:83-104 (padding=1 on the 1x1, padding=3 on the 3x3, Q12)
 # --------------------------------------------------------------------------------------
 def srm_logits(x, sd, masks=(None, None), q=None):

@@ -138,6 +138,7 @@ def state_dict_surface(ns):
                       ("ResNet_DA_CBAM", ns.cbam.ResNet_DA_CBAM), ("ResNet_DA_Deep", ns.deep.ResNet_DA_Deep)):
         out[name] = {k: list(v.shape) for k, v in cls(**common).state_dict().items()}
     out["InstanceAlignmentHead"] = {k: list(v.shape) for k, v in ns.instance.InstanceAlignmentHead().state_dict().items()}
+    out["RoILocalAlignmentHead"] = {k: list(v.shape) for k, v in ns.local_da.LocalAlignmentHead(2048).state_dict().items()}
     out["InstanceAlignmentHead_DAF"] = {k: list(v.shape) for k, v in ns.instance.InstanceAlignmentHead_DAF().state_dict().items()}
     json.dump(out, open(os.path.join(OUT, "state_dict_surface.json"), "w"))
     print("state_dict surface:", {k: len(v) for k, v in out.items()})
@@ -156,6 +157,7 @@ def main():
     head_case("srm", ns.maf.SRM(64), fm("x.srm", (2, 64, 6, 10)))
     head_case("non_local_alignment", ns.deep.NonLocalAlignmentHead(64), fm("x.nla", (2, 64, 4, 6)))
     head_case("instance_alignment", ns.instance.InstanceAlignmentHead(), fm("x.ins", (24, 1024)))
+    head_case("roi_local_alignment", ns.local_da.LocalAlignmentHead(64), fm("x.roil", (12, 64, 7, 7)))
     head_case("instance_alignment_daf", ns.instance.InstanceAlignmentHead_DAF(), fm("x.insd", (24, 1024)))
     backbone_loss_cases(ns)
     focal_case(ns)

@@ -85,6 +85,7 @@ def load():
     ns.cbam = _load("mmdet_ref.models.backbones.resnet_da_cbam", "mmdet/models/backbones/resnet_da_cbam.py")
     ns.deep = _load("mmdet_ref.models.backbones.resnet_da_deep", "mmdet/models/backbones/resnet_da_deep.py")
     ns.instance = _load("mmdet_ref.models.roi_heads.instance_da", "mmdet/models/roi_heads/instance_da.py")
+    ns.local_da = _load("mmdet_ref.models.roi_heads.local_da", "mmdet/models/roi_heads/local_da.py")
     ns.loss_utils = _load("mmdet_ref.models.losses.utils", "mmdet/models/losses/utils.py")
     ns.focal = _load("mmdet_ref.models.losses.focal_loss", "mmdet/models/losses/focal_loss.py")
     return ns

@@ -15,6 +15,7 @@ HEADS = {
     "non_local_alignment": (lambda: da_heads.NonLocalAlignmentHead(64), da_oracle.non_local_alignment_head),
     "instance_alignment": (lambda: da_heads.InstanceAlignmentHead(),
                            lambda x, sd, q=None: torch.sigmoid(da_oracle.instance_alignment_logits(x, sd, q=q))),
+    "roi_local_alignment": (lambda: da_heads.RoILocalAlignmentHead(64), da_oracle.roi_local_alignment_head),
     "instance_alignment_daf": (lambda: da_heads.InstanceAlignmentHead_DAF(),
                                lambda x, sd, q=None: torch.sigmoid(da_oracle.instance_alignment_daf_logits(x, sd, q=q))),
 }

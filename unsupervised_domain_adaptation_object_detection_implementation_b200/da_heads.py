@@ -246,6 +246,45 @@ class GlobalAlignmentHeadDeep(GlobalAlignmentHead):
 
 
 # --------------------------------------------------------------------------------------
+# I3  RoI-conv LocalAlignmentHead (roi_heads/local_da.py:47-101)
+# --------------------------------------------------------------------------------------
+class RoILocalAlignmentHead(_HeadBase):
+    """The reference's `roi_heads.local_da.LocalAlignmentHead`: GRL -> three 3x3 stride-2 convs (C -> 1024 -> 512 ->
+    512) with BN (eval) + ReLU + dropout on the [k,C,7,7] RoI features -> global average pool -> FC 512->2 ->
+    sigmoid.  Same state_dict keys; named apart from the backbone `LocalAlignmentHead` it shares a class name with."""
+
+    def __init__(self, in_channel, context=False):
+        super().__init__()
+        self.output_channel = 512
+        self.grl = GradientScalarLayer(weight=-1.0)
+        self.conv1 = conv3x3(in_channel, 1024, stride=2)
+        self.bn1 = nn.BatchNorm2d(1024)
+        self.conv2 = conv3x3(1024, self.output_channel, stride=2)
+        self.bn2 = nn.BatchNorm2d(self.output_channel)
+        self.conv3 = conv3x3(self.output_channel, self.output_channel, stride=2)
+        self.bn3 = nn.BatchNorm2d(self.output_channel)
+        self.fc = nn.Linear(self.output_channel, 2)
+        self.context = context
+
+    def forward_logits(self, x):
+        a = F_.to_nhwc(x, F_.act_dtype())
+        h = self._layer(a, self.conv1, self.bn1, grl=self.grl.weight)
+        h = self._layer(h, self.conv2, self.bn2)
+        h = self._layer(h, self.conv3, self.bn3)
+        feat = F_.global_avgpool(h)
+        z = self._layer(feat.view(feat.shape[0], 1, 1, -1), self.fc, relu=False, drop=False, engine=_tiny_engine(),
+                        out_dtype=torch.float32)
+        return z.view(z.shape[0], 2).float()
+
+    def forward(self, x):
+        return torch.sigmoid(self.forward_logits(x))
+
+    def _init_weights(self):
+        for n in ("conv1", "conv2", "conv3"):
+            normal_init(getattr(self, n), 0, 1)
+
+
+# --------------------------------------------------------------------------------------
 # H4  SRM (MAF head)
 # --------------------------------------------------------------------------------------
 class SRM(_HeadBase):

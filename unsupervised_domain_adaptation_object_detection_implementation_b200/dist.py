@@ -86,7 +86,9 @@ class OverlappedGradAllReduce:
         self.comm_stream = None
         self._handles = []
         if self.active and self.params and self.params[0].is_cuda:
-            self.comm_stream = torch.cuda.Stream(device=self.params[0].device)
+            # high priority: NCCL's CTAs are placed as soon as SMs free up instead of queueing behind the pending CTAs of
+            # the backward kernels they are meant to overlap
+            self.comm_stream = torch.cuda.Stream(device=self.params[0].device, priority=-1)
             for p in self.big:
                 self._handles.append(p.register_post_accumulate_grad_hook(self._hook))
         self.op = dist.ReduceOp.AVG if (self.params and self.params[0].is_cuda) else dist.ReduceOp.SUM
