@@ -164,9 +164,9 @@ def run_ours(args):
     # replayed: ~150 kernel launches per step are otherwise CPU-launch bound.  Dropout masks still change
     # every replay through the device-resident seed counter (functional.dropout_counter).
     F_.dropout_counter(dev)
-    static_c5 = torch.empty_like(resident[0][0])
-    static_bx = torch.empty_like(resident[0][1])
-    graph, graph_loss, graph_note = None, None, "eager"
+    # ONE graph per input buffer: the two resident input sets double as the static inputs of two captures (shared
+    # memory pool), so neither the resident nor the end-to-end loop pays a 67 MB device-to-device staging copy.
+    graphs, graph_losses, graph_note = None, None, "eager"
     launches_per_replay = [0]
 
     def eager_step(c5_dev, boxes_dev):
@@ -178,37 +178,40 @@ def run_ours(args):
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                static_c5.copy_(resident[0][0]); static_bx.copy_(resident[0][1])
-                for _ in range(3):
-                    eager_step(static_c5, static_bx)
+                for i in range(3):
+                    eager_step(*resident[i % 2])
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            _lib.reset_launch_count()
-            with torch.cuda.graph(graph):
-                graph_loss = eager_step(static_c5, static_bx)
+            graphs, graph_losses, pool = [], [], None
+            for slot in range(2):
+                gph = torch.cuda.CUDAGraph()
+                _lib.reset_launch_count()
+                with torch.cuda.graph(gph, pool=pool):
+                    graph_losses.append(eager_step(*resident[slot]))
+                pool = gph.pool()
+                graphs.append(gph)
             launches_per_replay[0] = _lib.launch_count()      # libda_b200 kernels inside one replayed step
             graph_note = "cuda_graph"
         except Exception as e:  # capture is an optimisation; the eager path is the same kernels
-            graph, graph_note = None, f"eager (graph capture failed: {type(e).__name__}: {str(e)[:120]})"
+            graphs, graph_note = None, f"eager (graph capture failed: {type(e).__name__}: {str(e)[:120]})"
             torch.cuda.synchronize()
+    graph = graphs
 
-    def run_step(c5_dev, boxes_dev):
-        if graph is None:
-            return eager_step(c5_dev, boxes_dev)
-        static_c5.copy_(c5_dev, non_blocking=True)       # device->device, 67 MB
-        static_bx.copy_(boxes_dev, non_blocking=True)
-        graph.replay()
-        return graph_loss
+    def run_slot(slot):
+        """One step on input set `slot` (resident[slot] holds the inputs)."""
+        if graphs is None:
+            return eager_step(*resident[slot])
+        graphs[slot].replay()
+        return graph_losses[slot]
 
     def step_resident(i):
-        return run_step(*resident[i % 2])
+        return run_slot(i % 2)
 
     # e2e: every step's inputs come from pinned host memory.  The copy of step i+1 is issued on a side
     # stream into the other device buffer while step i computes (double buffering); the loss of every step
     # is read back to the host.
     copy_stream = torch.cuda.Stream(device=dev)
-    dev_in = [(torch.empty_like(resident[0][0]), torch.empty_like(resident[0][1])) for _ in range(2)]
+    dev_in = resident      # the H2D copies land in the graphs' static input buffers
     ev_ready = [torch.cuda.Event() for _ in range(2)]
     ev_free = [torch.cuda.Event() for _ in range(2)]
     issued = set()
@@ -231,7 +234,7 @@ def run_ours(args):
         prefetch(i + 1)
         cur = torch.cuda.current_stream()
         cur.wait_event(ev_ready[slot])
-        loss = run_step(*dev_in[slot])
+        loss = run_slot(slot)
         ev_free[slot].record(cur)
         loss_host.copy_(loss.reshape(1), non_blocking=True)
         cur.synchronize()                                   # the user reads the loss every step

@@ -18,6 +18,7 @@ class FusedSGD:
         self.state = {}
         self.steps = 0
         self._chunks, self._chunk_key, self._keep, self._host, self._table, self._copied = None, None, None, None, None, None
+        self._spare, self._captured = [], []
 
     def zero_grad(self, set_to_none=True):
         for p in self.params:
@@ -64,16 +65,26 @@ class FusedSGD:
         # table of da_sgd_entry records (6 x int64 each; first_step sits in the low 32 bits of the last word).  The pinned
         # staging buffer and the device table are allocated once (first eager step), so a captured step only holds a copy node.
         if self._host is None or self._host[0].shape[0] < len(rows):
+            # 2 rotating staging buffers for eager steps + spares that a CUDA-graph capture takes for good (a captured
+            # copy node re-reads its host buffer at every replay, so that buffer must never be rewritten)
             self._host = [torch.empty((len(self.params), 6), dtype=torch.int64).pin_memory() for _ in range(2)]
+            self._spare = [torch.empty((len(self.params), 6), dtype=torch.int64).pin_memory() for _ in range(4)]
             self._table = torch.empty((len(self.params), 6), dtype=torch.int64, device=dev)
             self._copied = [None, None]
-        slot = self.steps & 1
         capturing = torch.cuda.is_current_stream_capturing()
-        if self._copied[slot] is not None and not capturing:
-            self._copied[slot].synchronize()          # the copy that last read this staging buffer has run
-        self._host[slot][:len(rows)] = torch.tensor(rows, dtype=torch.int64)
+        if capturing:
+            if not self._spare:
+                raise RuntimeError("FusedSGD: more than 4 graph captures of step(); run one eager step first / raise the spare count")
+            stage = self._spare.pop()
+            self._captured.append(stage)
+        else:
+            slot = self.steps & 1
+            if self._copied[slot] is not None:
+                self._copied[slot].synchronize()          # the copy that last read this staging buffer has run
+            stage = self._host[slot]
+        stage[:len(rows)] = torch.tensor(rows, dtype=torch.int64)
         table = self._table
-        table[:len(rows)].copy_(self._host[slot][:len(rows)], non_blocking=True)
+        table[:len(rows)].copy_(stage[:len(rows)], non_blocking=True)
         if not capturing:
             self._copied[slot] = torch.cuda.Event()
             self._copied[slot].record()
