@@ -282,7 +282,7 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.engine == "umma_bf16" else "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "pairs_per_gpu": pairs, "c5": [2 * pairs, C, H, W], "rois_per_img": ROIS_PER_IMG,
-                   "engine": args.engine, "launch": graph_note, "step": "H1+L1, RoIAlign fwd/bwd, shared FCs, I1+L4, L7, backward, SGD",
+                   "engine": args.engine, "launch": graph_note, "grad_allreduce": ("none (1 GPU)" if world == 1 else "nccl avg fp32, side stream from the weight-gradient kernel on, persistent kernels on SMs-32 meanwhile"), "step": "H1+L1, RoIAlign fwd/bwd, shared FCs, I1+L4, L7, backward, SGD",
                    "l2_policy": "inputs_and_weights_exceed_L2 (C5 67MB/pair bf16, FC1 weight 411MB, RoI features 205MB); two input sets alternated"},
         "e2e": {"value": round(e2e_value, 3), "unit": "img-pairs/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4,
                 "ms_per_step": round(ms_e2e / args.steps, 4)},

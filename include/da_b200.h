@@ -81,6 +81,9 @@ int da_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n,
  * faster_rcnn_r50_daf_c2f.py:8 by mmdet/apis/train.py:127): momentum, weight decay, dampening 0,
  * no nesterov:  d = grad + wd*w;  buf = first_step ? d : mu*buf + d;  w -= lr*buf.
  * w_bf16 (nullable): bf16 shadow of w refreshed in the same pass (operand of the tcgen05 engine). */
+/* SM budget of the persistent kernels (0 = all SMs).  Lower it for launches that overlap a collective holding SMs
+ * (dist.OverlappedGradAllReduce): a persistent grid larger than the free SMs runs in two waves. */
+int da_set_sm_limit(int n);
 int da_sgd_step(float* w, const float* grad, float* momentum_buf, int64_t n, float lr, float momentum,
                 float weight_decay, int first_step, void* w_bf16, da_stream_t stream);
 /* The same update for MANY tensors in one launch (torch.optim.SGD's foreach path, mmdet/apis/train.py:127).

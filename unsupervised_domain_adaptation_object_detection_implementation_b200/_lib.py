@@ -53,6 +53,7 @@ SIGNATURES = {
     "da_split_bf16": (I, [P, P, P, L, P]),
     "da_cast": (I, [P, I, P, I, L, P]),
     "da_sgd_step": (I, [P, P, P, L, F, F, F, I, P, P]),
+    "da_set_sm_limit": (I, [I]),
     "da_sgd_step_multi": (I, [P, I, P, I, F, F, F, P]),
     "da_roi_align_workspace_bytes": (S, [I, I, I]),
     "da_roi_align_forward": (I, [P, I, I, I, I, I, P, I, I, I, F, I, I, P, I, I, P, P, S, P]),

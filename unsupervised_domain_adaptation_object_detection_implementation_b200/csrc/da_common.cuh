@@ -54,7 +54,10 @@ __device__ __forceinline__ unsigned long long effective_seed(unsigned long long 
     }                                                                               \
   } while (0)
 
-inline int num_sms() {
+// SM budget of the persistent kernels (da_set_sm_limit): while a NCCL all-reduce holds some SMs, a persistent grid of
+// one CTA per PHYSICAL SM would run in two waves; the caller lowers the budget for the kernels it overlaps.
+extern int g_sm_limit;
+inline int num_sms_physical() {
   static int n = 0;
   if (n == 0) {
     int dev = 0;
@@ -63,6 +66,10 @@ inline int num_sms() {
     if (n <= 0) n = 148;
   }
   return n;
+}
+inline int num_sms() {
+  const int n = num_sms_physical();
+  return (g_sm_limit > 0 && g_sm_limit < n) ? g_sm_limit : n;
 }
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

@@ -10,6 +10,7 @@ namespace da {
 static thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
 const unsigned long long* g_seed_counter = nullptr;
+int g_sm_limit = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -234,6 +235,11 @@ extern "C" int da_sgd_step_multi(const da_sgd_entry* entries, int n_entries, con
   DA_REQUIRE(entries && chunks, DA_ERR_INVALID_ARG, "sgd_step_multi: null table");
   sgd_step_multi_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(entries, chunks, lr, momentum, weight_decay);
   DA_LAUNCH_CHECK();
+  return DA_OK;
+}
+
+extern "C" int da_set_sm_limit(int n) {
+  g_sm_limit = n > 0 ? n : 0;
   return DA_OK;
 }
 

@@ -915,15 +915,18 @@ static int launch_nt_t(NtParams& P, long long pixel_tiles, int k_iters, void* ws
   cfg.attrs = attr;
   cfg.numAttrs = getenv("DA_NO_PDL") ? 1 : 2;
   // persistent grid = the clusters that are co-resident (GPC sizes need not be multiples of the cluster size)
-  static int max_clusters = 0;
-  if (max_clusters == 0) {
-    cfg.gridDim = dim3((num_sms() / kCluster) * kCluster);
+  static int hw_clusters = 0;
+  if (hw_clusters == 0) {
+    cfg.gridDim = dim3((num_sms_physical() / kCluster) * kCluster);
     int n = 0;
-    if (kCluster > 1 && cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n > 0) max_clusters = n;
-    else max_clusters = num_sms() / kCluster;
+    if (kCluster > 1 && cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n > 0) hw_clusters = n;
+    else hw_clusters = num_sms_physical() / kCluster;
     (void)cudaGetLastError();
-    if (max_clusters > num_sms() / kCluster) max_clusters = num_sms() / kCluster;
+    if (hw_clusters > num_sms_physical() / kCluster) hw_clusters = num_sms_physical() / kCluster;
   }
+  int max_clusters = num_sms() / kCluster;                 // honours da_set_sm_limit
+  if (max_clusters > hw_clusters) max_clusters = hw_clusters;
+  if (max_clusters < 1) max_clusters = 1;
   const int clusters = (int)(total < max_clusters ? total : max_clusters);
   cfg.gridDim = dim3(clusters * kCluster);
   DA_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, P, (int)pixel_tiles, n_tiles, splits));
@@ -1137,15 +1140,18 @@ static int launch_tn_t(const TnParams& P, int co_tiles, int ci_tiles, int splits
   cfg.attrs = attr;
   cfg.numAttrs = getenv("DA_NO_PDL") ? 1 : 2;
   // persistent grid = the clusters that are co-resident (GPC sizes need not be multiples of the cluster size)
-  static int max_clusters = 0;
-  if (max_clusters == 0) {
-    cfg.gridDim = dim3((num_sms() / kCluster) * kCluster);
+  static int hw_clusters = 0;
+  if (hw_clusters == 0) {
+    cfg.gridDim = dim3((num_sms_physical() / kCluster) * kCluster);
     int n = 0;
-    if (kCluster > 1 && cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n > 0) max_clusters = n;
-    else max_clusters = num_sms() / kCluster;
+    if (kCluster > 1 && cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n > 0) hw_clusters = n;
+    else hw_clusters = num_sms_physical() / kCluster;
     (void)cudaGetLastError();
-    if (max_clusters > num_sms() / kCluster) max_clusters = num_sms() / kCluster;
+    if (hw_clusters > num_sms_physical() / kCluster) hw_clusters = num_sms_physical() / kCluster;
   }
+  int max_clusters = num_sms() / kCluster;                 // honours da_set_sm_limit
+  if (max_clusters > hw_clusters) max_clusters = hw_clusters;
+  if (max_clusters < 1) max_clusters = 1;
   const int clusters = (int)(total < max_clusters ? total : max_clusters);
   cfg.gridDim = dim3(clusters * kCluster);
   DA_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, P, co_tiles, ci_tiles, splits));

@@ -58,6 +58,11 @@ def workspace(nbytes, device, tag="default"):
 _ENGINE = ["umma_bf16"]
 
 
+def set_sm_limit(n):
+    """SM budget of the persistent kernels for the launches that follow (0 = all SMs); see da_set_sm_limit."""
+    check(lib.da_set_sm_limit(int(n)), "set_sm_limit")
+
+
 def set_engine(name):
     """'umma_bf16' (tcgen05, default), 'umma_bf16x3' (split-precision tcgen05, fp32 in/out)
     or 'simt_f32' (CUDA-core fp32 parity engine)."""
@@ -405,6 +410,10 @@ def _w_ohwi(w):
     return v if v.is_contiguous() else v.contiguous()
 
 
+# callable(dw) invoked right after a layer's weight-gradient kernel has been enqueued (None = disabled)
+WGRAD_HOOK = None
+
+
 class DenseLayerFunction(Function):
     """y = dropout(relu(conv(x, w) * scale + shift)), NHWC in / NHWC out.
 
@@ -464,11 +473,8 @@ class DenseLayerFunction(Function):
                                            _ptr(dshift), _ptr(dvdot), _ptr(ws), ws.numel(), _stream()), "conv_act_backward")
         dz = cast(dz, x.dtype)
         dx = dw = dscale = None
-        if ctx.needs_input_grad[0]:
-            desc_d = _conv_desc(N, H, W_, Cin, Cout, KH, KW, stride, pad, engine, x.dtype, x.dtype)
-            dx = torch.empty_like(x)
-            check(lib.da_conv_backward_data(ctypes.byref(desc_d), _ptr(dz), _ptr(wv), float(grl), _ptr(dx), _ptr(ws),
-                                            ws.numel(), _stream()), "conv_backward_data")
+        # weight gradient first: a gradient all-reduce can then start while the data gradient of the same layer runs
+        # (WGRAD_HOOK, installed by dist.OverlappedGradAllReduce)
         if ctx.needs_input_grad[1]:
             desc_w = _conv_desc(N, H, W_, Cin, Cout, KH, KW, stride, pad, engine, x.dtype, x.dtype)
             dwv = torch.empty((Cout, KH, KW, Cin), dtype=torch.float32, device=dev)
@@ -477,6 +483,13 @@ class DenseLayerFunction(Function):
             dw = dwv.view(wshape) if len(wshape) == 2 else dwv.permute(0, 3, 1, 2)
             if wdtype != torch.float32:
                 dw = dw.to(wdtype)
+            elif WGRAD_HOOK is not None:
+                WGRAD_HOOK(dwv)
+        if ctx.needs_input_grad[0]:
+            desc_d = _conv_desc(N, H, W_, Cin, Cout, KH, KW, stride, pad, engine, x.dtype, x.dtype)
+            dx = torch.empty_like(x)
+            check(lib.da_conv_backward_data(ctypes.byref(desc_d), _ptr(dz), _ptr(wv), float(grl), _ptr(dx), _ptr(ws),
+                                            ws.numel(), _stream()), "conv_backward_data")
         if need_scale:
             # v = acc*scale + shift  =>  d(scale) = sum dv*acc = (dvdot - shift*dshift) / scale
             t = sh if sh is not None else torch.zeros_like(dshift)

@@ -10,6 +10,11 @@ from ._lib import lib, check
 _CHUNK = 65536   # DA_SGD_CHUNK (include/da_b200.h)
 
 
+def _same_layout(a, b):
+    """Same memory order (strides of size-1 dimensions carry no information)."""
+    return a.shape == b.shape and all(n == 1 or sa == sb for n, sa, sb in zip(a.shape, a.stride(), b.stride()))
+
+
 class FusedSGD:
     def __init__(self, params, lr=1e-3, momentum=0.9, weight_decay=0.0, shadow_bf16=True):
         self.params = [p for p in params if p.requires_grad]
@@ -40,7 +45,7 @@ class FusedSGD:
                 raise RuntimeError("FusedSGD updates fp32 CUDA parameters (no CPU fallback)")
             if not F_._dense_memory(p):
                 raise RuntimeError("FusedSGD needs densely stored parameters")
-            if g.dtype != torch.float32 or g.stride() != p.stride():
+            if g.dtype != torch.float32 or not _same_layout(g, p):
                 g = torch.empty_like(p).copy_(g)      # same memory order as the parameter
                 keep.append(g)
             st = self.state.get(id(p))
