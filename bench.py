@@ -390,12 +390,22 @@ def kernel_rooflines(dev, act, step_ms):
             n * (4 * 3 + 4 * 2 + 2))
     dom = max(table, key=lambda k: table[k]["ms"])
     d = table[dom]
+    # DRAM bytes per launch of the same kernel at the same size, measured once with `ncu --set full` (profiles/)
+    traffic = None
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_hot_kernels_ncu.json")))["kernels"]
+        for k, rec in prof.items():
+            if k in table:
+                table[k]["ncu_dram_bytes"] = rec["dram_bytes"]
+        traffic = prof.get(dom, {}).get("dram_bytes")
+    except (OSError, KeyError, ValueError):
+        pass
     if "bytes" in d:
         roof = {"kernel": dom, "bound": "hbm", "achieved": d["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": d["frac"],
-                "traffic": None, "peak_source": pk["source"], "share_of_step": round(d["ms"] / step_ms, 4)}
+                "traffic": traffic, "peak_source": pk["source"], "share_of_step": round(d["ms"] / step_ms, 4)}
     else:
         roof = {"kernel": dom, "bound": "tensor", "achieved": d["tflops"], "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": d["frac"], "traffic": None, "peak_source": pk["source"], "share_of_step": round(d["ms"] / step_ms, 4)}
+                "frac": d["frac"], "traffic": traffic, "peak_source": pk["source"], "share_of_step": round(d["ms"] / step_ms, 4)}
     return roof, table
 
 
