@@ -51,6 +51,10 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--cpu-budget-s", type=float, default=20.0)
+    ap.add_argument("--grad-sync", default="peer", choices=["peer", "nccl"],
+                    help="N>1: 'peer' = FC1's gradient mean + SGD + operand broadcast in one kernel over NVLink peer memory "
+                         "(peer.PeerShardedSGD), NCCL all-reduce for the small tensors; 'nccl' = NCCL all-reduce for everything")
+    ap.add_argument("--peer-ctas", type=int, default=48)
     return ap.parse_args()
 
 
@@ -122,7 +126,7 @@ def make_host_inputs(pairs, seed, dtype):
 # ----------------------------------------------------------------------------------------------
 def run_ours(args):
     import unsupervised_domain_adaptation_object_detection_implementation_b200 as uda
-    from unsupervised_domain_adaptation_object_detection_implementation_b200 import dist as ddist, functional as F_, hotpath, optim, _lib
+    from unsupervised_domain_adaptation_object_detection_implementation_b200 import dist as ddist, functional as F_, hotpath, optim, peer, _lib
     import torch.distributed as dist
 
     rank, local, world = ddist.init_from_env("nccl")
@@ -136,7 +140,23 @@ def run_ours(args):
     torch.manual_seed(0)
     model = hotpath.DAFOrgHotPath(C, STRIDE, FC_OUT).to(dev).train()
     params = ddist.trainable_parameters(model, model.unused_parameters())
-    opt = optim.FusedSGD(params, lr=1e-3, momentum=0.9, weight_decay=5e-4)    # reference recipe (faster_rcnn_r50_daf_c2f.py:8)
+    sgd = dict(lr=1e-3, momentum=0.9, weight_decay=5e-4)                      # reference recipe (faster_rcnn_r50_daf_c2f.py:8)
+    peer_opt, sync_note = None, "none (1 GPU)"
+    if world > 1:
+        sync_note = "nccl avg fp32, side stream from the weight-gradient kernel on, persistent kernels on SMs-32 meanwhile"
+        if args.grad_sync == "peer" and pairs == 1 and args.engine == "umma_bf16":
+            big = [p for p in params if p.numel() >= (1 << 24)]
+            try:
+                peer_opt = peer.PeerShardedSGD(big, max_ctas=args.peer_ctas, **sgd)
+                params = [p for p in params if all(p is not q for q in big)]
+                sync_note = (f"FC1 ({sum(p.numel() for p in big) / 1e6:.0f} M params): fused gradient-mean + sharded SGD + bf16 operand broadcast "
+                             f"over NVLink peer memory (da_sgd_step_peer, {args.peer_ctas} CTAs, momentum and fp32 master sharded); "
+                             "remaining tensors: nccl avg fp32 + multi-tensor SGD")
+            except Exception as e:    # CUDA IPC unavailable on this box: the all-NCCL path is the same math
+                peer_opt = None
+                F_.MANAGED_WGRAD.clear()
+                sync_note += f" (peer path unavailable: {type(e).__name__}: {str(e)[:100]})"
+    opt = optim.FusedSGD(params, **sgd)
     reducer = ddist.OverlappedGradAllReduce(params) if world > 1 else None
 
     # two input sets (alternated); each is > L2 (C5 alone is 67 MB bf16 per pair, FC1's weight 411 MB)
@@ -158,6 +178,8 @@ def run_ours(args):
             reducer()
         opt.step()
         opt.zero_grad(set_to_none=True)
+        if peer_opt is not None:
+            peer_opt.join()
         return total
 
     # The whole step (forward, backward, all-reduce excluded, SGD) is captured once into a CUDA graph and
@@ -282,12 +304,14 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.engine == "umma_bf16" else "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "pairs_per_gpu": pairs, "c5": [2 * pairs, C, H, W], "rois_per_img": ROIS_PER_IMG,
-                   "engine": args.engine, "launch": graph_note, "grad_allreduce": ("none (1 GPU)" if world == 1 else "nccl avg fp32, side stream from the weight-gradient kernel on, persistent kernels on SMs-32 meanwhile"), "step": "H1+L1, RoIAlign fwd/bwd, shared FCs, I1+L4, L7, backward, SGD",
+                   "engine": args.engine, "launch": graph_note, "grad_allreduce": sync_note, "step": "H1+L1, RoIAlign fwd/bwd, shared FCs, I1+L4, L7, backward, SGD",
                    "l2_policy": "inputs_and_weights_exceed_L2 (C5 67MB/pair bf16, FC1 weight 411MB, RoI features 205MB); two input sets alternated"},
         "e2e": {"value": round(e2e_value, 3), "unit": "img-pairs/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4,
                 "ms_per_step": round(ms_e2e / args.steps, 4)},
         "gpu_launches": int(launches), "clocks": clocks,
     }
+    if peer_opt is not None:
+        peer_opt.check_errors()
     if rank == 0:
         out["roofline"], out["kernels"] = kernel_rooflines(dev, act, ms_res / args.steps)
         if world == 1 and not args.no_cpu_baseline:

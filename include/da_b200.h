@@ -102,6 +102,41 @@ typedef struct da_sgd_entry {
 int da_sgd_step_multi(const da_sgd_entry* entries, int n_entries, const int32_t* chunks, int n_chunks,
                       float lr, float momentum, float weight_decay, da_stream_t stream);
 
+/* ---- gradient mean + SGD + operand broadcast over NVLink peer memory (N GPUs of one box) ------------------
+ * Replaces, for one large tensor, the pair  MMDistributedDataParallel bucket all-reduce (mmdet/apis/train.py:113-121)
+ * -> torch.optim.SGD.step (train.py:127): rank r owns the r-th 1/world slice (slices are multiples of 1024 elements),
+ * reads that slice of EVERY rank's gradient through P2P loads, averages in rank order, applies the SGD rule above to
+ * its slice of the fp32 master (momentum is stored sharded: momentum_shard holds the slice only) and stores the bf16
+ * result into every rank's operand copy (and, when w_f32[r] is given, the fp32 result into every rank's master; with
+ * w_f32[r] == NULL the master of a rank is current on its own slice only, ZeRO-1 style).
+ * Cross-GPU ordering uses flag words in peer memory: the call may start as soon as THIS rank's gradient is complete in
+ * stream order; on return of the second (wait) kernel nobody reads this rank's gradient or writes its operand copy
+ * any more.  Every rank must make the same sequence of calls.  A barrier that does not complete within 4 s sets
+ * local_state[2] (1 = in, 2 = out) instead of hanging.
+ * Memory for grad / w_bf16 / flags must be reachable by every peer: da_peer_alloc (cudaMalloc, zero-filled) +
+ * da_peer_export (64-byte CUDA IPC handle, exchanged by the caller) + da_peer_open on the other ranks. */
+#define DA_MAX_PEERS 8
+#define DA_PEER_HANDLE_BYTES 64
+#define DA_PEER_FLAG_INTS (2 * DA_MAX_PEERS)   /* ready[DA_MAX_PEERS] | done[DA_MAX_PEERS], zero-initialised */
+typedef struct da_peer_sgd_args {
+  float* w;                          /* local fp32 master, full tensor */
+  float* momentum_shard;             /* local fp32 momentum of the own slice (slice-relative index) */
+  const float* grad[DA_MAX_PEERS];   /* gradient buffer of every rank (own entry = local pointer) */
+  void* w_bf16[DA_MAX_PEERS];        /* bf16 operand copy of every rank (NULL = skip) */
+  float* w_f32[DA_MAX_PEERS];        /* fp32 master of every rank (NULL = master stays sharded) */
+  int* flags[DA_MAX_PEERS];          /* flag block (DA_PEER_FLAG_INTS ints) of every rank */
+  int* local_state;                  /* 4 local ints, zero-initialised: epoch, ticket, error, pad */
+  int64_t n;                         /* elements of the tensor */
+  int32_t world, rank;
+} da_peer_sgd_args;
+int da_sgd_step_peer(const da_peer_sgd_args* args, float lr, float momentum, float weight_decay, int first_step,
+                     int max_ctas, da_stream_t stream);
+int da_peer_alloc(size_t bytes, void** out);
+int da_peer_free(void* p);
+int da_peer_export(const void* p, unsigned char* handle64);
+int da_peer_open(const unsigned char* handle64, void** out);
+int da_peer_close(void* p);
+
 /* ---- RoIAlign ------------------------------------------------------------
  * Replaces mmcv.ops.RoIAlign (ext_module.roi_align_forward / roi_align_backward,
  * mmcv-full 1.3.17) as built at mmdet/models/roi_heads/roi_extractors/base_roi_extractor.py:54-60

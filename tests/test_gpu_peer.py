@@ -1,0 +1,108 @@
+"""GPU tests of the peer-memory optimizer kernel (da_sgd_step_peer, csrc/peer_sgd.cu).
+
+The whole cross-rank protocol (flag barriers, slice ownership, gradient mean in rank order, SGD rule, operand
+broadcast) is exercised on ONE device: `world` virtual ranks live in one process, each with its own buffers and its
+own stream, and point at each other's buffers directly (CUDA IPC is only the transport of those pointers between
+processes; tools/peer_check.py covers it under torchrun on >= 2 GPUs and is run by the last test when they exist).
+Expected values: mean of the gradients in rank order, then da_sgd_step (already pinned to torch.optim.SGD by
+test_gpu_parity.py) on the full tensor.  Everything is compared bit for bit.
+"""
+import ctypes
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from unsupervised_domain_adaptation_object_detection_implementation_b200 import _lib, functional as F_, peer  # noqa: E402
+from unsupervised_domain_adaptation_object_detection_implementation_b200._lib import check, lib  # noqa: E402
+
+DEV = "cuda"
+LR, MU, WD = 0.05, 0.9, 5e-4
+
+
+def _expected(w0, grads_per_step, world):
+    """Reference trajectory: (masters per step, bf16 copies per step) from da_sgd_step on the averaged gradient."""
+    w = w0.clone()
+    buf = torch.zeros_like(w)
+    shadow = torch.empty_like(w, dtype=torch.bfloat16)
+    inv = torch.tensor(1.0 / world, dtype=torch.float32, device=DEV)
+    outs = []
+    for s, grads in enumerate(grads_per_step):
+        g = grads[0].clone()
+        for r in range(1, world):
+            g = g + grads[r]
+        g = g * inv
+        check(lib.da_sgd_step(F_._ptr(w), F_._ptr(g), F_._ptr(buf), w.numel(), LR, MU, WD, int(s == 0), F_._ptr(shadow), None), "sgd")
+        torch.cuda.synchronize()
+        outs.append((w.clone(), shadow.clone()))
+    return outs
+
+
+@pytest.mark.parametrize("world,n,share_master", [(1, 8192 + 5, False), (2, 3 * 1024 * 37 + 13, False), (3, 1024 * 50 + 3, True),
+                                                  (4, 1024 * 1024 + 1024, False), (8, 8 * 1024 * 9, True)])
+def test_peer_sgd_virtual_ranks_match_allreduce_plus_sgd(world, n, share_master):
+    g = torch.Generator(device=DEV).manual_seed(world * 1000 + n % 97)
+    w0 = torch.randn(n, device=DEV, generator=g)
+    steps = 3
+    grads_per_step = [[torch.randn(n, device=DEV, generator=g) for _ in range(world)] for _ in range(steps)]
+    exp = _expected(w0, grads_per_step, world)
+
+    masters = [w0.clone() for _ in range(world)]
+    grads = [torch.empty(n, device=DEV) for _ in range(world)]
+    shadows = [torch.zeros(n, device=DEV, dtype=torch.bfloat16) for _ in range(world)]
+    flags = [torch.zeros(_lib.DA_PEER_FLAG_INTS, dtype=torch.int32, device=DEV) for _ in range(world)]
+    states = [torch.zeros(4, dtype=torch.int32, device=DEV) for _ in range(world)]
+    per = peer.slice_bounds(n, world, 0)[2]
+    moms = [torch.zeros(max(per, 8), device=DEV) for _ in range(world)]
+    args = [peer.make_args(masters[r].data_ptr(), moms[r].data_ptr(), [t.data_ptr() for t in grads],
+                           [t.data_ptr() for t in shadows], [t.data_ptr() for t in masters] if share_master else None,
+                           [t.data_ptr() for t in flags], states[r].data_ptr(), n, world, r) for r in range(world)]
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    for s in range(steps):
+        for r in range(world):
+            grads[r].copy_(grads_per_step[s][r])
+        torch.cuda.synchronize()
+        for r in range(world):          # all virtual ranks must be co-resident: 8 x 8 CTAs at most
+            check(lib.da_sgd_step_peer(ctypes.byref(args[r]), LR, MU, WD, int(s == 0), 8,
+                                       ctypes.c_void_p(streams[r].cuda_stream)), "sgd_step_peer")
+        torch.cuda.synchronize()
+        w_exp, sh_exp = exp[s]
+        for r in range(world):
+            assert int(states[r][2]) == 0, "a barrier timed out"
+            assert int(states[r][0]) == s + 1
+            lo, hi, _ = peer.slice_bounds(n, world, r)
+            assert torch.equal(masters[r][lo:hi], w_exp[lo:hi])               # own slice of the master
+            assert torch.equal(shadows[r].view(torch.int16), sh_exp.view(torch.int16))   # every rank's whole operand copy
+            if share_master:
+                assert torch.equal(masters[r], w_exp)
+    # the slices partition the tensor
+    cover = sorted(peer.slice_bounds(n, world, r)[:2] for r in range(world))
+    assert cover[0][0] == 0 and cover[-1][1] == n and all(a[1] == b[0] for a, b in zip(cover, cover[1:]))
+
+
+def test_peer_sgd_rejects_bad_arguments():
+    t = torch.zeros(1024, device=DEV)
+    f = torch.zeros(_lib.DA_PEER_FLAG_INTS, dtype=torch.int32, device=DEV)
+    st = torch.zeros(4, dtype=torch.int32, device=DEV)
+    a = peer.make_args(t.data_ptr(), t.data_ptr(), [t.data_ptr()], [0], None, [f.data_ptr()], st.data_ptr(), 1024, 1, 0)
+    a.world = 9
+    assert lib.da_sgd_step_peer(ctypes.byref(a), LR, MU, WD, 0, 8, None) != 0
+    assert "world" in _lib.last_error()
+    a.world = 1
+    a.w = t.data_ptr() + 4
+    assert lib.da_sgd_step_peer(ctypes.byref(a), LR, MU, WD, 0, 8, None) != 0
+    assert "aligned" in _lib.last_error()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (CUDA IPC between processes)")
+def test_peer_sharded_sgd_two_processes():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "tools", "peer_check.py")]
+    out = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "PEER_CHECK_OK" in out.stdout

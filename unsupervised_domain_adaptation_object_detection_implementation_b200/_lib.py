@@ -27,6 +27,17 @@ class ConvDesc(Structure):
                 ("engine", c_int), ("x_dtype", c_int), ("y_dtype", c_int)]
 
 
+DA_MAX_PEERS, DA_PEER_HANDLE_BYTES, DA_PEER_FLAG_INTS = 8, 64, 16
+
+
+class PeerSgdArgs(Structure):
+    """da_peer_sgd_args (include/da_b200.h)."""
+    _fields_ = [("w", c_void_p), ("momentum_shard", c_void_p),
+                ("grad", c_void_p * DA_MAX_PEERS), ("w_bf16", c_void_p * DA_MAX_PEERS),
+                ("w_f32", c_void_p * DA_MAX_PEERS), ("flags", c_void_p * DA_MAX_PEERS),
+                ("local_state", c_void_p), ("n", c_int64), ("world", c_int32), ("rank", c_int32)]
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -55,6 +66,12 @@ SIGNATURES = {
     "da_sgd_step": (I, [P, P, P, L, F, F, F, I, P, P]),
     "da_set_sm_limit": (I, [I]),
     "da_sgd_step_multi": (I, [P, I, P, I, F, F, F, P]),
+    "da_sgd_step_peer": (I, [P, F, F, F, I, I, P]),
+    "da_peer_alloc": (I, [S, P]),
+    "da_peer_free": (I, [P]),
+    "da_peer_export": (I, [P, P]),
+    "da_peer_open": (I, [P, P]),
+    "da_peer_close": (I, [P]),
     "da_roi_align_workspace_bytes": (S, [I, I, I]),
     "da_roi_align_forward": (I, [P, I, I, I, I, I, P, I, I, I, F, I, I, P, I, I, P, P, S, P]),
     "da_roi_align_backward": (I, [P, I, I, P, I, I, I, F, I, I, P, I, I, I, I, I, P, S, P]),

@@ -412,6 +412,10 @@ def _w_ohwi(w):
 
 # callable(dw) invoked right after a layer's weight-gradient kernel has been enqueued (None = disabled)
 WGRAD_HOOK = None
+# Weights whose gradient is owned by a peer-memory optimizer (peer.PeerShardedSGD): id(weight) -> (flat fp32 buffer the
+# weight-gradient kernel writes into, callable invoked once the layer's backward kernels are enqueued).  Autograd sees
+# such a weight as a constant: no .grad tensor is produced, the optimizer consumes the buffer directly.
+MANAGED_WGRAD = {}
 
 
 class DenseLayerFunction(Function):
@@ -421,8 +425,9 @@ class DenseLayerFunction(Function):
     is a head input) + wgrad + the two column sums that give d(scale), d(shift)."""
 
     @staticmethod
-    def forward(ctx, x, w, scale, shift, stride, pad, relu, drop_p, seed, engine, grl, out_dtype, shadow=None):
+    def forward(ctx, x, w, scale, shift, stride, pad, relu, drop_p, seed, engine, grl, out_dtype, shadow=None, managed=None):
         _require_cuda(x, w)
+        ctx.managed = managed
         N, H, W_, Cin = x.shape
         x = x.contiguous()
         if shadow is not None:
@@ -475,7 +480,12 @@ class DenseLayerFunction(Function):
         dx = dw = dscale = None
         # weight gradient first: a gradient all-reduce can then start while the data gradient of the same layer runs
         # (WGRAD_HOOK, installed by dist.OverlappedGradAllReduce)
-        if ctx.needs_input_grad[1]:
+        managed = ctx.managed
+        if managed is not None:
+            desc_w = _conv_desc(N, H, W_, Cin, Cout, KH, KW, stride, pad, engine, x.dtype, x.dtype)
+            check(lib.da_conv_backward_weight(ctypes.byref(desc_w), _ptr(x), _ptr(dz), _ptr(managed[0]), _ptr(ws), ws.numel(),
+                                              _stream()), "conv_backward_weight")
+        elif ctx.needs_input_grad[1]:
             desc_w = _conv_desc(N, H, W_, Cin, Cout, KH, KW, stride, pad, engine, x.dtype, x.dtype)
             dwv = torch.empty((Cout, KH, KW, Cin), dtype=torch.float32, device=dev)
             check(lib.da_conv_backward_weight(ctypes.byref(desc_w), _ptr(x), _ptr(dz), _ptr(dwv), _ptr(ws), ws.numel(),
@@ -490,12 +500,14 @@ class DenseLayerFunction(Function):
             dx = torch.empty_like(x)
             check(lib.da_conv_backward_data(ctypes.byref(desc_d), _ptr(dz), _ptr(wv), float(grl), _ptr(dx), _ptr(ws),
                                             ws.numel(), _stream()), "conv_backward_data")
+        if managed is not None:
+            managed[1]()     # the layer no longer reads its operand copy and its gradient buffer is complete (stream order)
         if need_scale:
             # v = acc*scale + shift  =>  d(scale) = sum dv*acc = (dvdot - shift*dshift) / scale
             t = sh if sh is not None else torch.zeros_like(dshift)
             safe = torch.where(sc == 0, torch.ones_like(sc), sc)
             dscale = torch.where(sc == 0, torch.zeros_like(sc), (dvdot - t * dshift) / safe)
-        return dx, dw, dscale, (dshift if need_shift else None), None, None, None, None, None, None, None, None, None
+        return dx, dw, dscale, (dshift if need_shift else None), None, None, None, None, None, None, None, None, None, None
 
 
 def _umma_ok(x, w):
@@ -513,7 +525,12 @@ def dense_layer(x, w, scale=None, shift=None, stride=1, pad=0, relu=False, drop_
     shadow = None
     if w.dtype == torch.float32 and x.dtype == torch.bfloat16 and w.is_leaf and _dense_memory(w):
         shadow = bf16_shadow(w)      # cached on the parameter; refreshed by FusedSGD
-    return DenseLayerFunction.apply(x, w, scale, shift, stride, pad, relu, drop_p, seed, engine, grl, out_dtype, shadow)
+    managed = MANAGED_WGRAD.get(id(w)) if (MANAGED_WGRAD and torch.is_grad_enabled()) else None
+    if managed is not None:
+        if shadow is None:
+            raise RuntimeError("a peer-managed weight needs the bf16 tensor-core engine (its operand copy is what the peers refresh)")
+        w = w.detach()
+    return DenseLayerFunction.apply(x, w, scale, shift, stride, pad, relu, drop_p, seed, engine, grl, out_dtype, shadow, managed)
 
 
 _DROP_COUNTER = {}
