@@ -54,7 +54,9 @@ def parse_args():
     ap.add_argument("--grad-sync", default="peer", choices=["peer", "nccl"],
                     help="N>1: 'peer' = FC1's gradient mean + SGD + operand broadcast in one kernel over NVLink peer memory "
                          "(peer.PeerShardedSGD), NCCL all-reduce for the small tensors; 'nccl' = NCCL all-reduce for everything")
-    ap.add_argument("--peer-ctas", type=int, default=48)
+    ap.add_argument("--peer-ctas", type=int, default=0, help="grid cap of the peer kernel (0 = two 128-thread CTAs per SM)")
+    ap.add_argument("--peer-transport", default="copy", choices=["copy", "stores"])
+    ap.add_argument("--peer-reserve-sms", type=int, default=0, help="SMs the persistent kernels leave free while the peer kernel runs")
     return ap.parse_args()
 
 
@@ -147,10 +149,12 @@ def run_ours(args):
         if args.grad_sync == "peer" and pairs == 1 and args.engine == "umma_bf16":
             big = [p for p in params if p.numel() >= (1 << 24)]
             try:
-                peer_opt = peer.PeerShardedSGD(big, max_ctas=args.peer_ctas, **sgd)
+                peer_opt = peer.PeerShardedSGD(big, max_ctas=args.peer_ctas, reserve_sms=args.peer_reserve_sms, transport=args.peer_transport, **sgd)
                 params = [p for p in params if all(p is not q for q in big)]
-                sync_note = (f"FC1 ({sum(p.numel() for p in big) / 1e6:.0f} M params): fused gradient-mean + sharded SGD + bf16 operand broadcast "
-                             f"over NVLink peer memory (da_sgd_step_peer, {args.peer_ctas} CTAs, momentum and fp32 master sharded); "
+                how = ("copy engines push gradient slices to their owner and the refreshed bf16 slices to every rank, all-local update kernel"
+                       if args.peer_transport == "copy" else "one kernel with SM-issued P2P loads/stores")
+                sync_note = (f"FC1 ({sum(p.numel() for p in big) / 1e6:.0f} M params): gradient mean + sharded SGD + bf16 operand broadcast "
+                             f"over NVLink peer memory ({how}; da_sgd_step_peer; momentum and fp32 master sharded); "
                              "remaining tensors: nccl avg fp32 + multi-tensor SGD")
             except Exception as e:    # CUDA IPC unavailable on this box: the all-NCCL path is the same math
                 peer_opt = None
@@ -174,7 +178,7 @@ def run_ours(args):
             loss, _ = hotpath.parse_losses(losses)
             loss.backward()
             total = loss.detach() if total is None else total + loss.detach()
-        if reducer is not None:
+        if reducer is not None and not os.environ.get("DA_DIAG_NOFLAT"):
             reducer()
         opt.step()
         opt.zero_grad(set_to_none=True)

@@ -129,8 +129,19 @@ typedef struct da_peer_sgd_args {
   int64_t n;                         /* elements of the tensor */
   int32_t world, rank;
 } da_peer_sgd_args;
+ /* publish_mode DA_PEER_PUBLISH_STORES: the kernel does all of the above with SM-issued P2P loads and stores, followed by
+ * the wait kernel.  DA_PEER_PUBLISH_BY_CALLER: the copy engines carry the data - before the call the caller pushes slice r
+ * of its gradient into rank r's staging area with da_peer_copy (so grad[r] here are LOCAL pointers biased such that
+ * grad[r] + i addresses element i of the own slice), after the call it pushes the refreshed bf16 slice (w_bf16[rank] is
+ * the local copy, the other entries NULL) to every rank and ends with da_peer_publish_done (done flags + wait). */
+#define DA_PEER_PUBLISH_STORES 0
+#define DA_PEER_PUBLISH_BY_CALLER 1
 int da_sgd_step_peer(const da_peer_sgd_args* args, float lr, float momentum, float weight_decay, int first_step,
-                     int max_ctas, da_stream_t stream);
+                     int max_ctas, int publish_mode, da_stream_t stream);
+/* Stream-ordered copy between any two device pointers this process can address (local or da_peer_open'ed): runs on a
+ * copy engine, no SM involved. */
+int da_peer_copy(void* dst, const void* src, size_t bytes, da_stream_t stream);
+int da_peer_publish_done(const da_peer_sgd_args* args, da_stream_t stream);
 int da_peer_alloc(size_t bytes, void** out);
 int da_peer_free(void* p);
 int da_peer_export(const void* p, unsigned char* handle64);

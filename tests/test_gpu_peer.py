@@ -67,7 +67,7 @@ def test_peer_sgd_virtual_ranks_match_allreduce_plus_sgd(world, n, share_master)
             grads[r].copy_(grads_per_step[s][r])
         torch.cuda.synchronize()
         for r in range(world):          # all virtual ranks must be co-resident: 8 x 8 CTAs at most
-            check(lib.da_sgd_step_peer(ctypes.byref(args[r]), LR, MU, WD, int(s == 0), 8,
+            check(lib.da_sgd_step_peer(ctypes.byref(args[r]), LR, MU, WD, int(s == 0), 8, _lib.DA_PEER_PUBLISH_STORES,
                                        ctypes.c_void_p(streams[r].cuda_stream)), "sgd_step_peer")
         torch.cuda.synchronize()
         w_exp, sh_exp = exp[s]
@@ -84,17 +84,73 @@ def test_peer_sgd_virtual_ranks_match_allreduce_plus_sgd(world, n, share_master)
     assert cover[0][0] == 0 and cover[-1][1] == n and all(a[1] == b[0] for a, b in zip(cover, cover[1:]))
 
 
+@pytest.mark.parametrize("world,n", [(2, 3 * 1024 * 37 + 13), (3, 1024 * 50 + 3), (4, 1024 * 1024 + 1024), (8, 8 * 1024 * 9 + 77)])
+def test_peer_sgd_copy_engine_transport_virtual_ranks(world, n):
+    """transport="copy" of peer.PeerShardedSGD, replayed with raw pointers: push gradient slices into the owners' staging
+    areas (da_peer_copy), all-local update kernel (DA_PEER_PUBLISH_BY_CALLER), push the bf16 slices, da_peer_publish_done."""
+    g = torch.Generator(device=DEV).manual_seed(world * 77 + n % 89)
+    w0 = torch.randn(n, device=DEV, generator=g)
+    steps = 3
+    grads_per_step = [[torch.randn(n, device=DEV, generator=g) for _ in range(world)] for _ in range(steps)]
+    exp = _expected(w0, grads_per_step, world)
+    bounds = [peer.slice_bounds(n, world, r) for r in range(world)]
+    per = bounds[0][2]
+    masters = [w0.clone() for _ in range(world)]
+    grads = [torch.empty(n, device=DEV) for _ in range(world)]
+    staging = [torch.full((world * per,), float("nan"), device=DEV) for _ in range(world)]
+    shadows = [torch.zeros(n, device=DEV, dtype=torch.bfloat16) for _ in range(world)]
+    flags = [torch.zeros(_lib.DA_PEER_FLAG_INTS, dtype=torch.int32, device=DEV) for _ in range(world)]
+    states = [torch.zeros(4, dtype=torch.int32, device=DEV) for _ in range(world)]
+    moms = [torch.zeros(max(per, 8), device=DEV) for _ in range(world)]
+    args = []
+    for r in range(world):
+        lo = bounds[r][0]
+        gp = [grads[r].data_ptr() if q == r else staging[r].data_ptr() + 4 * (q * per - lo) for q in range(world)]
+        sp = [shadows[r].data_ptr() if q == r else 0 for q in range(world)]
+        args.append(peer.make_args(masters[r].data_ptr(), moms[r].data_ptr(), gp, sp, None, [t.data_ptr() for t in flags],
+                                   states[r].data_ptr(), n, world, r))
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    for s in range(steps):
+        for r in range(world):
+            grads[r].copy_(grads_per_step[s][r])
+        torch.cuda.synchronize()
+        for r in range(world):
+            st = ctypes.c_void_p(streams[r].cuda_stream)
+            for q in range(world):
+                if q != r:
+                    lo, hi, _ = bounds[q]
+                    check(lib.da_peer_copy(staging[q].data_ptr() + 4 * r * per, grads[r].data_ptr() + 4 * lo, 4 * (hi - lo), st), "copy")
+        for r in range(world):
+            st = ctypes.c_void_p(streams[r].cuda_stream)
+            lo, hi, _ = bounds[r]
+            check(lib.da_sgd_step_peer(ctypes.byref(args[r]), LR, MU, WD, int(s == 0), 8, _lib.DA_PEER_PUBLISH_BY_CALLER, st), "step")
+            for q in range(world):
+                if q != r:
+                    check(lib.da_peer_copy(shadows[q].data_ptr() + 2 * lo, shadows[r].data_ptr() + 2 * lo, 2 * (hi - lo), st), "copy")
+            check(lib.da_peer_publish_done(ctypes.byref(args[r]), st), "publish_done")
+        torch.cuda.synchronize()
+        w_exp, sh_exp = exp[s]
+        for r in range(world):
+            lo, hi, _ = bounds[r]
+            assert int(states[r][2]) == 0 and int(states[r][0]) == s + 1
+            assert torch.equal(masters[r][lo:hi], w_exp[lo:hi])
+            assert torch.equal(shadows[r].view(torch.int16), sh_exp.view(torch.int16))
+            assert int(flags[r][_lib.DA_MAX_PEERS:_lib.DA_MAX_PEERS + world].min()) == s + 1     # every rank raised done
+
+
 def test_peer_sgd_rejects_bad_arguments():
     t = torch.zeros(1024, device=DEV)
     f = torch.zeros(_lib.DA_PEER_FLAG_INTS, dtype=torch.int32, device=DEV)
     st = torch.zeros(4, dtype=torch.int32, device=DEV)
     a = peer.make_args(t.data_ptr(), t.data_ptr(), [t.data_ptr()], [0], None, [f.data_ptr()], st.data_ptr(), 1024, 1, 0)
     a.world = 9
-    assert lib.da_sgd_step_peer(ctypes.byref(a), LR, MU, WD, 0, 8, None) != 0
+    assert lib.da_sgd_step_peer(ctypes.byref(a), LR, MU, WD, 0, 8, 0, None) != 0
     assert "world" in _lib.last_error()
     a.world = 1
+    assert lib.da_sgd_step_peer(ctypes.byref(a), LR, MU, WD, 0, 8, 7, None) != 0
+    assert "publish_mode" in _lib.last_error()
     a.w = t.data_ptr() + 4
-    assert lib.da_sgd_step_peer(ctypes.byref(a), LR, MU, WD, 0, 8, None) != 0
+    assert lib.da_sgd_step_peer(ctypes.byref(a), LR, MU, WD, 0, 8, 0, None) != 0
     assert "aligned" in _lib.last_error()
 
 

@@ -28,7 +28,9 @@ def main():
     lin_a = torch.nn.Linear(4096, 1024).to(dev)
     lin_b = torch.nn.Linear(4096, 1024).to(dev)
     lin_b.load_state_dict(lin_a.state_dict())
-    popt = peer.PeerShardedSGD([lin_a.weight], lr=LR, momentum=MU, weight_decay=WD, max_ctas=32)
+    transport = "stores" if "--stores" in sys.argv else "copy"
+    popt = peer.PeerShardedSGD([lin_a.weight], lr=LR, momentum=MU, weight_decay=WD, transport=transport,
+                               share_master="--share-master" in sys.argv)
     opt_a = optim.FusedSGD([lin_a.bias], lr=LR, momentum=MU, weight_decay=WD)
     opt_b = optim.FusedSGD(list(lin_b.parameters()), lr=LR, momentum=MU, weight_decay=WD)
     g = torch.Generator(device=dev).manual_seed(100 + rank)
@@ -70,12 +72,13 @@ def main():
     p = torch.nn.Parameter(torch.randn(1 << 22, device=dev, generator=torch.Generator(device=dev).manual_seed(5)))
     q = p.detach().clone()
     qbuf, qsh = torch.zeros_like(q), torch.empty_like(q, dtype=torch.bfloat16)
-    popt2 = peer.PeerShardedSGD([p], lr=LR, momentum=MU, weight_decay=WD, max_ctas=32)
-    gbuf, done = F_.MANAGED_WGRAD[id(p)]
+    popt2 = peer.PeerShardedSGD([p], lr=LR, momentum=MU, weight_decay=WD, transport=transport)
+    gbuf, wgrad_done, done = F_.MANAGED_WGRAD[id(p)]
     src = torch.randn(1 << 22, device=dev, generator=g)
 
     def one_step():
         gbuf.copy_(src)
+        wgrad_done()
         done()
         popt2.join()
 
@@ -107,15 +110,16 @@ def main():
     if "--time" in sys.argv:
         n = 1024 * 100352
         big = torch.nn.Parameter(torch.zeros(n, device=dev))
-        for ctas in (32, 48, 64, 96):
-            po = peer.PeerShardedSGD([big], lr=LR, momentum=MU, weight_decay=WD, max_ctas=ctas)
-            _, done_big = F_.MANAGED_WGRAD[id(big)]
+        for transport, ctas in (("copy", 0), ("copy", 592), ("stores", 296)):
+            po = peer.PeerShardedSGD([big], lr=LR, momentum=MU, weight_decay=WD, max_ctas=ctas, transport=transport)
+            _, wgrad_big, done_big = F_.MANAGED_WGRAD[id(big)]
             ts = []
             for it in range(6):
                 dist.barrier()
                 torch.cuda.synchronize()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
+                wgrad_big()
                 done_big()
                 po.join()
                 e1.record()
@@ -126,7 +130,7 @@ def main():
             if rank == 0:
                 lo, hi, _ = peer.slice_bounds(n, world, 0)
                 remote_in = (world - 1) * (hi - lo) * 4
-                print(f"PEER_TIME world={world} ctas={ctas} ms={t:.4f} remote_in_GBps={remote_in / t / 1e6:.1f} "
+                print(f"PEER_TIME world={world} transport={transport} ctas={ctas} ms={t:.4f} remote_in_GBps={remote_in / t / 1e6:.1f} "
                       f"remote_out_GBps={(world - 1) * (hi - lo) * 2 / t / 1e6:.1f}", flush=True)
             del F_.MANAGED_WGRAD[id(big)]
         grad = torch.zeros(n, device=dev)

@@ -28,6 +28,7 @@ class ConvDesc(Structure):
 
 
 DA_MAX_PEERS, DA_PEER_HANDLE_BYTES, DA_PEER_FLAG_INTS = 8, 64, 16
+DA_PEER_PUBLISH_STORES, DA_PEER_PUBLISH_BY_CALLER = 0, 1
 
 
 class PeerSgdArgs(Structure):
@@ -66,7 +67,9 @@ SIGNATURES = {
     "da_sgd_step": (I, [P, P, P, L, F, F, F, I, P, P]),
     "da_set_sm_limit": (I, [I]),
     "da_sgd_step_multi": (I, [P, I, P, I, F, F, F, P]),
-    "da_sgd_step_peer": (I, [P, F, F, F, I, I, P]),
+    "da_sgd_step_peer": (I, [P, F, F, F, I, I, I, P]),
+    "da_peer_copy": (I, [P, P, S, P]),
+    "da_peer_publish_done": (I, [P, P]),
     "da_peer_alloc": (I, [S, P]),
     "da_peer_free": (I, [P]),
     "da_peer_export": (I, [P, P]),

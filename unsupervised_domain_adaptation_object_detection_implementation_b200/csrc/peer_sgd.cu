@@ -15,6 +15,16 @@
 //                one) holds the stream until every peer's done flag arrived, i.e. until nobody reads this rank's
 //                gradient or writes its operand copy any more.
 //
+// Two transports (publish_mode):
+//   DA_PEER_PUBLISH_STORES     everything above in this one kernel (P2P loads + stores issued by the SMs).
+//   DA_PEER_PUBLISH_BY_CALLER  the COPY ENGINES move the data and the kernel only touches local memory: before the call
+//                              the caller pushes slice r of its gradient into rank r's staging area (da_peer_copy),
+//                              grad[r] of the call points at the local staging slots, w_bf16[r != rank] is NULL; after
+//                              the call it pushes the refreshed bf16 slice to every rank and raises done through
+//                              da_peer_publish_done.  Measured on B200 NVLink (tools/p2p_bw.cu, profiles/): SM-issued
+//                              peer loads reach 14.6 GB/s per SM and collapse to ~370 GB/s per GPU when the same kernel
+//                              also pushes, SM pushes 690 GB/s, the copy engines 800 GB/s with no SM at all - so this is
+//                              the mode the train step uses.
 // Link traffic per rank: (N-1)/N * 4 B in + (N-1)/N * 2 B out per parameter (NCCL ring all-reduce: 2*(N-1)/N*4 B each
 // way) and the optimizer pass shrinks by N.  Flags live in cudaMalloc'ed blocks exchanged through CUDA IPC
 // (da_peer_alloc / da_peer_export / da_peer_open); they carry a monotonically increasing epoch kept on the device, so a
@@ -24,7 +34,7 @@
 
 namespace da {
 
-constexpr int PEER_THREADS = 512;
+constexpr int PEER_THREADS = 128;
 constexpr unsigned long long PEER_TIMEOUT_NS = 4000000000ull;   // 4 s
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -40,7 +50,7 @@ __device__ __forceinline__ int ld_acquire_sys(const int* p) {
 __device__ __forceinline__ void st_release_sys(int* p, int v) {
   asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ float4 ld_cv4(const float* p) {
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
   float4 v;
   // plain weak load, not ld.cv: measured 14.6 GB/s per SM over NVLink against 7.7 for ld.cv / ld.relaxed.sys (tools/p2p_bw.cu).
   // Safe: a gradient word is read once per kernel, after the acquire of its owner's ready flag, and L1 starts a kernel empty.
@@ -61,9 +71,13 @@ __device__ __forceinline__ bool spin_until(const int* flag, int epoch) {
 
 // local_state: [0] epoch of the last completed call, [1] CTA ticket, [2] error (1 = barrier-in timed out, 2 = barrier-out)
 // flags block of a rank: ready[DA_MAX_PEERS] | done[DA_MAX_PEERS]; slot r is written by rank r only.
-template <int W>
-__global__ void __launch_bounds__(PEER_THREADS, 1)
-sgd_step_peer_kernel(const da_peer_sgd_args a, float lr, float mu, float wd, int first) {
+// W = world size (0: run-time), V = float4 per thread, rank and iteration.  Small CTAs (128 threads, <= 96 registers) on
+// purpose: they fit NEXT to the resident CTA of the tensor-core kernels this call overlaps (RoIAlign backward: 576
+// threads x 87 registers; the persistent GEMMs: 320 x 112), so the transfer takes no SM away from them.  NVLink loads are
+// limited per SM (tools/p2p_bw.cu: 14.6 GB/s per SM whatever the unroll), so the grid covers every SM twice.
+template <int W, int V>
+__global__ void __launch_bounds__(PEER_THREADS, 5)
+sgd_step_peer_kernel(const da_peer_sgd_args a, float lr, float mu, float wd, int first, int signal_done) {
   __shared__ int s_epoch;
   const int world = W > 0 ? W : a.world;
   if (threadIdx.x == 0) s_epoch = a.local_state[0] + 1;
@@ -82,82 +96,89 @@ sgd_step_peer_kernel(const da_peer_sgd_args a, float lr, float mu, float wd, int
   const int64_t lo = per * a.rank < a.n ? per * a.rank : a.n;
   const int64_t hi = lo + per < a.n ? lo + per : a.n;
   const float inv = 1.f / (float)world;
-  const int64_t nvec = (hi - lo) >> 3;   // 8 elements per thread and iteration
-  for (int64_t v = (int64_t)blockIdx.x * PEER_THREADS + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * PEER_THREADS) {
-    const int64_t i = lo + (v << 3);
-    float4 g0[W > 0 ? W : 1], g1[W > 0 ? W : 1];
-    float4 s0, s1;
+  constexpr int TILE = PEER_THREADS * 4 * V;             // elements per CTA and iteration; thread t owns float4 t + k*128
+  const int64_t ntile = (hi - lo) / TILE;
+  for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+    const int64_t i0 = lo + tile * TILE + 4 * threadIdx.x;
+    float4 s[V], wv[V], bv[V];
     if (W > 0) {
+      float4 g[W > 0 ? W : 1][V];
 #pragma unroll
-      for (int r = 0; r < W; ++r) { g0[r] = ld_cv4(a.grad[r] + i); g1[r] = ld_cv4(a.grad[r] + i + 4); }
-    }
-    float4 w0 = *reinterpret_cast<const float4*>(a.w + i), w1 = *reinterpret_cast<const float4*>(a.w + i + 4);
-    float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-    if (!first) {
-      b0 = *reinterpret_cast<const float4*>(a.momentum_shard + (i - lo));
-      b1 = *reinterpret_cast<const float4*>(a.momentum_shard + (i - lo) + 4);
-    }
-    if (W > 0) {
-      s0 = g0[0]; s1 = g1[0];
+      for (int r = 0; r < W; ++r)
 #pragma unroll
-      for (int r = 1; r < W; ++r) {
-        s0.x += g0[r].x; s0.y += g0[r].y; s0.z += g0[r].z; s0.w += g0[r].w;
-        s1.x += g1[r].x; s1.y += g1[r].y; s1.z += g1[r].z; s1.w += g1[r].w;
+        for (int k = 0; k < V; ++k) g[r][k] = ld_stream4(a.grad[r] + i0 + k * (4 * PEER_THREADS));
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        wv[k] = *reinterpret_cast<const float4*>(a.w + i0 + k * (4 * PEER_THREADS));
+        bv[k] = first ? make_float4(0.f, 0.f, 0.f, 0.f)
+                      : *reinterpret_cast<const float4*>(a.momentum_shard + (i0 - lo) + k * (4 * PEER_THREADS));
+      }
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        s[k] = g[0][k];
+#pragma unroll
+        for (int r = 1; r < W; ++r) { s[k].x += g[r][k].x; s[k].y += g[r][k].y; s[k].z += g[r][k].z; s[k].w += g[r][k].w; }
       }
     } else {
-      s0 = ld_cv4(a.grad[0] + i); s1 = ld_cv4(a.grad[0] + i + 4);
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        wv[k] = *reinterpret_cast<const float4*>(a.w + i0 + k * (4 * PEER_THREADS));
+        bv[k] = first ? make_float4(0.f, 0.f, 0.f, 0.f)
+                      : *reinterpret_cast<const float4*>(a.momentum_shard + (i0 - lo) + k * (4 * PEER_THREADS));
+        s[k] = ld_stream4(a.grad[0] + i0 + k * (4 * PEER_THREADS));
+      }
       for (int r = 1; r < world; ++r) {
-        const float4 t0 = ld_cv4(a.grad[r] + i), t1 = ld_cv4(a.grad[r] + i + 4);
-        s0.x += t0.x; s0.y += t0.y; s0.z += t0.z; s0.w += t0.w;
-        s1.x += t1.x; s1.y += t1.y; s1.z += t1.z; s1.w += t1.w;
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          const float4 t = ld_stream4(a.grad[r] + i0 + k * (4 * PEER_THREADS));
+          s[k].x += t.x; s[k].y += t.y; s[k].z += t.z; s[k].w += t.w;
+        }
       }
     }
-    float* wp0 = &w0.x; float* wp1 = &w1.x; float* bp0 = &b0.x; float* bp1 = &b1.x;
-    const float* gp0 = &s0.x; const float* gp1 = &s1.x;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float d0 = fmaf(wd, wp0[j], gp0[j] * inv), d1 = fmaf(wd, wp1[j], gp1[j] * inv);
-      bp0[j] = first ? d0 : fmaf(mu, bp0[j], d0);
-      bp1[j] = first ? d1 : fmaf(mu, bp1[j], d1);
-      wp0[j] = fmaf(-lr, bp0[j], wp0[j]);
-      wp1[j] = fmaf(-lr, bp1[j], wp1[j]);
+    for (int k = 0; k < V; ++k) {
+      float* wp = &wv[k].x; float* bp = &bv[k].x; const float* gp = &s[k].x;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float d = fmaf(wd, wp[j], gp[j] * inv);
+        bp[j] = first ? d : fmaf(mu, bp[j], d);
+        wp[j] = fmaf(-lr, bp[j], wp[j]);
+      }
+      const int64_t i = i0 + k * (4 * PEER_THREADS);
+      *reinterpret_cast<float4*>(a.w + i) = wv[k];
+      *reinterpret_cast<float4*>(a.momentum_shard + (i - lo)) = bv[k];
     }
-    *reinterpret_cast<float4*>(a.w + i) = w0;
-    *reinterpret_cast<float4*>(a.w + i + 4) = w1;
-    *reinterpret_cast<float4*>(a.momentum_shard + (i - lo)) = b0;
-    *reinterpret_cast<float4*>(a.momentum_shard + (i - lo) + 4) = b1;
-    __nv_bfloat162 p0 = __floats2bfloat162_rn(w0.x, w0.y), p1 = __floats2bfloat162_rn(w0.z, w0.w);
-    __nv_bfloat162 p2 = __floats2bfloat162_rn(w1.x, w1.y), p3 = __floats2bfloat162_rn(w1.z, w1.w);
-    const uint4 u = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
-                               *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
     // publish, own rank first, then the peers starting at rank+1 (spreads the instantaneous load over the ports)
 #pragma unroll
-    for (int k = 0; k < (W > 0 ? W : DA_MAX_PEERS); ++k) {
-      if (k >= world) break;
-      int r = a.rank + k;
+    for (int q = 0; q < (W > 0 ? W : DA_MAX_PEERS); ++q) {
+      if (q >= world) break;
+      int r = a.rank + q;
       if (r >= world) r -= world;
-      if (a.w_bf16[r]) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.w_bf16[r]) + i) = u;
-      if (k > 0 && a.w_f32[r]) {
-        *reinterpret_cast<float4*>(a.w_f32[r] + i) = w0;
-        *reinterpret_cast<float4*>(a.w_f32[r] + i + 4) = w1;
+      __nv_bfloat16* sh = reinterpret_cast<__nv_bfloat16*>(a.w_bf16[r]);
+      float* mf = q > 0 ? a.w_f32[r] : nullptr;
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        const int64_t i = i0 + k * (4 * PEER_THREADS);
+        if (sh) {
+          __nv_bfloat162 p0 = __floats2bfloat162_rn(wv[k].x, wv[k].y), p1 = __floats2bfloat162_rn(wv[k].z, wv[k].w);
+          *reinterpret_cast<uint2*>(sh + i) = make_uint2(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1));
+        }
+        if (mf) *reinterpret_cast<float4*>(mf + i) = wv[k];
       }
     }
   }
-  // tail of the slice (< 8 elements; only when n is not a multiple of 8)
-  if (blockIdx.x == 0) {
-    const int64_t i = lo + (nvec << 3) + threadIdx.x;
-    if (i < hi) {
-      float g = 0.f;
-      for (int r = 0; r < world; ++r) g += __ldcv(a.grad[r] + i);
-      const float d = fmaf(wd, a.w[i], g * inv);
-      const float b = first ? d : fmaf(mu, a.momentum_shard[i - lo], d);
-      a.momentum_shard[i - lo] = b;
-      const float wn = fmaf(-lr, b, a.w[i]);
-      a.w[i] = wn;
-      for (int r = 0; r < world; ++r) {
-        if (a.w_bf16[r]) reinterpret_cast<__nv_bfloat16*>(a.w_bf16[r])[i] = __float2bfloat16_rn(wn);
-        if (r != a.rank && a.w_f32[r]) a.w_f32[r][i] = wn;
-      }
+  // tail of the slice (< one tile): one element per thread
+  for (int64_t i = lo + ntile * TILE + (int64_t)blockIdx.x * PEER_THREADS + threadIdx.x; i < hi; i += (int64_t)gridDim.x * PEER_THREADS) {
+    float g = 0.f;
+    for (int r = 0; r < world; ++r) g += __ldcv(a.grad[r] + i);
+    const float d = fmaf(wd, a.w[i], g * inv);
+    const float b = first ? d : fmaf(mu, a.momentum_shard[i - lo], d);
+    a.momentum_shard[i - lo] = b;
+    const float wn = fmaf(-lr, b, a.w[i]);
+    a.w[i] = wn;
+    for (int r = 0; r < world; ++r) {
+      if (a.w_bf16[r]) reinterpret_cast<__nv_bfloat16*>(a.w_bf16[r])[i] = __float2bfloat16_rn(wn);
+      if (r != a.rank && a.w_f32[r]) a.w_f32[r][i] = wn;
     }
   }
   // ---- barrier-out, sender side: all stores of this rank are visible system-wide before done[rank] is raised
@@ -169,13 +190,19 @@ sgd_step_peer_kernel(const da_peer_sgd_args a, float lr, float mu, float wd, int
   }
   __syncthreads();
   if (s_epoch) {   // last CTA of this rank
-    if (threadIdx.x < world) st_release_sys(a.flags[threadIdx.x] + DA_MAX_PEERS + a.rank, epoch);
+    if (signal_done && threadIdx.x < world) st_release_sys(a.flags[threadIdx.x] + DA_MAX_PEERS + a.rank, epoch);
     if (threadIdx.x == 0) {
       a.local_state[1] = 0;
       __threadfence();
       a.local_state[0] = epoch;
     }
   }
+}
+
+// done[rank] := epoch of the update in front of this kernel, on every rank (the caller's copies are in front of it too)
+__global__ void peer_signal_done_kernel(const da_peer_sgd_args a) {
+  const int epoch = a.local_state[0];
+  if (threadIdx.x < a.world) st_release_sys(a.flags[threadIdx.x] + DA_MAX_PEERS + a.rank, epoch);
 }
 
 __global__ void peer_wait_kernel(const int* flags_local, int* local_state, int world) {
@@ -220,8 +247,28 @@ extern "C" int da_peer_close(void* p) {
   return DA_OK;
 }
 
+extern "C" int da_peer_copy(void* dst, const void* src, size_t bytes, da_stream_t stream) {
+  if (bytes == 0) return DA_OK;
+  DA_REQUIRE(dst && src, DA_ERR_INVALID_ARG, "peer_copy: null pointer");
+  DA_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+  return DA_OK;
+}
+
+extern "C" int da_peer_publish_done(const da_peer_sgd_args* a, da_stream_t stream) {
+  DA_REQUIRE(a && a->local_state && a->world >= 1 && a->world <= DA_MAX_PEERS && a->rank >= 0 && a->rank < a->world,
+             DA_ERR_INVALID_ARG, "peer_publish_done: bad args");
+  peer_signal_done_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(*a);
+  DA_LAUNCH_CHECK();
+  peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a->flags[a->rank], a->local_state, a->world);
+  DA_LAUNCH_CHECK();
+  return DA_OK;
+}
+
 extern "C" int da_sgd_step_peer(const da_peer_sgd_args* a, float lr, float momentum, float weight_decay, int first_step,
-                                int max_ctas, da_stream_t stream) {
+                                int max_ctas, int publish_mode, da_stream_t stream) {
+  DA_REQUIRE(publish_mode == DA_PEER_PUBLISH_STORES || publish_mode == DA_PEER_PUBLISH_BY_CALLER, DA_ERR_INVALID_ARG,
+             "sgd_step_peer: publish_mode %d", publish_mode);
+  const int sd = publish_mode == DA_PEER_PUBLISH_STORES ? 1 : 0;
   DA_REQUIRE(a && a->w && a->momentum_shard && a->local_state && a->n > 0, DA_ERR_INVALID_ARG, "sgd_step_peer: bad args");
   DA_REQUIRE(a->world >= 1 && a->world <= DA_MAX_PEERS && a->rank >= 0 && a->rank < a->world, DA_ERR_INVALID_ARG,
              "sgd_step_peer: world %d / rank %d out of range (max %d peers)", a->world, a->rank, DA_MAX_PEERS);
@@ -232,19 +279,26 @@ extern "C" int da_sgd_step_peer(const da_peer_sgd_args* a, float lr, float momen
   }
   DA_REQUIRE((bits & 15) == 0, DA_ERR_INVALID_ARG, "sgd_step_peer: pointers must be 16-byte aligned");
   const int64_t per = ((a->n + a->world - 1) / a->world + 1023) / 1024 * 1024;
-  int ctas = (int)((per / 8 + PEER_THREADS - 1) / PEER_THREADS);
-  if (max_ctas <= 0) max_ctas = num_sms_physical();
+  const int v = a->world <= 2 ? 4 : (a->world <= 4 ? 2 : 1);
+  int ctas = (int)((per + PEER_THREADS * 4 * v - 1) / (PEER_THREADS * 4 * v));
+  if (max_ctas <= 0) max_ctas = (sd ? 2 : 16) * num_sms_physical();   // all-local update: enough CTAs to stream HBM
   if (ctas > max_ctas) ctas = max_ctas;
   if (ctas < 1) ctas = 1;
   cudaStream_t st = (cudaStream_t)stream;
   switch (a->world) {
-    case 2: sgd_step_peer_kernel<2><<<ctas, PEER_THREADS, 0, st>>>(*a, lr, momentum, weight_decay, first_step); break;
-    case 4: sgd_step_peer_kernel<4><<<ctas, PEER_THREADS, 0, st>>>(*a, lr, momentum, weight_decay, first_step); break;
-    case 8: sgd_step_peer_kernel<8><<<ctas, PEER_THREADS, 0, st>>>(*a, lr, momentum, weight_decay, first_step); break;
-    default: sgd_step_peer_kernel<0><<<ctas, PEER_THREADS, 0, st>>>(*a, lr, momentum, weight_decay, first_step); break;
+    case 1: sgd_step_peer_kernel<1, 4><<<ctas, PEER_THREADS, 0, st>>>(*a, lr, momentum, weight_decay, first_step, sd); break;
+    case 2: sgd_step_peer_kernel<2, 4><<<ctas, PEER_THREADS, 0, st>>>(*a, lr, momentum, weight_decay, first_step, sd); break;
+    case 4: sgd_step_peer_kernel<4, 2><<<ctas, PEER_THREADS, 0, st>>>(*a, lr, momentum, weight_decay, first_step, sd); break;
+    case 8: sgd_step_peer_kernel<8, 1><<<ctas, PEER_THREADS, 0, st>>>(*a, lr, momentum, weight_decay, first_step, sd); break;
+    default:
+      if (v == 2) sgd_step_peer_kernel<0, 2><<<ctas, PEER_THREADS, 0, st>>>(*a, lr, momentum, weight_decay, first_step, sd);
+      else sgd_step_peer_kernel<0, 1><<<ctas, PEER_THREADS, 0, st>>>(*a, lr, momentum, weight_decay, first_step, sd);
+      break;
   }
   DA_LAUNCH_CHECK();
-  peer_wait_kernel<<<1, 32, 0, st>>>(a->flags[a->rank], a->local_state, a->world);
-  DA_LAUNCH_CHECK();
+  if (sd) {
+    peer_wait_kernel<<<1, 32, 0, st>>>(a->flags[a->rank], a->local_state, a->world);
+    DA_LAUNCH_CHECK();
+  }
   return DA_OK;
 }

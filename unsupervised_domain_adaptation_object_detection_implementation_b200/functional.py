@@ -413,7 +413,8 @@ def _w_ohwi(w):
 # callable(dw) invoked right after a layer's weight-gradient kernel has been enqueued (None = disabled)
 WGRAD_HOOK = None
 # Weights whose gradient is owned by a peer-memory optimizer (peer.PeerShardedSGD): id(weight) -> (flat fp32 buffer the
-# weight-gradient kernel writes into, callable invoked once the layer's backward kernels are enqueued).  Autograd sees
+# weight-gradient kernel writes into, callable invoked right after that kernel is enqueued, callable invoked once all of
+# the layer's backward kernels are enqueued).  Autograd sees
 # such a weight as a constant: no .grad tensor is produced, the optimizer consumes the buffer directly.
 MANAGED_WGRAD = {}
 
@@ -485,6 +486,7 @@ class DenseLayerFunction(Function):
             desc_w = _conv_desc(N, H, W_, Cin, Cout, KH, KW, stride, pad, engine, x.dtype, x.dtype)
             check(lib.da_conv_backward_weight(ctypes.byref(desc_w), _ptr(x), _ptr(dz), _ptr(managed[0]), _ptr(ws), ws.numel(),
                                               _stream()), "conv_backward_weight")
+            managed[1]()     # the gradient buffer is complete in stream order
         elif ctx.needs_input_grad[1]:
             desc_w = _conv_desc(N, H, W_, Cin, Cout, KH, KW, stride, pad, engine, x.dtype, x.dtype)
             dwv = torch.empty((Cout, KH, KW, Cin), dtype=torch.float32, device=dev)
@@ -501,7 +503,7 @@ class DenseLayerFunction(Function):
             check(lib.da_conv_backward_data(ctypes.byref(desc_d), _ptr(dz), _ptr(wv), float(grl), _ptr(dx), _ptr(ws),
                                             ws.numel(), _stream()), "conv_backward_data")
         if managed is not None:
-            managed[1]()     # the layer no longer reads its operand copy and its gradient buffer is complete (stream order)
+            managed[2]()     # the layer no longer reads its operand copy
         if need_scale:
             # v = acc*scale + shift  =>  d(scale) = sum dv*acc = (dvdot - shift*dshift) / scale
             t = sh if sh is not None else torch.zeros_like(dshift)

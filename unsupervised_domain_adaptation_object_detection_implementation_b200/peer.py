@@ -78,24 +78,33 @@ def make_args(w, momentum_shard, grads, shadows, masters, flags, local_state, n,
 
 
 class _Managed:
-    __slots__ = ("param", "n", "grad", "shadow", "flags", "state", "momentum", "args", "calls", "blocks", "pending")
+    __slots__ = ("param", "n", "grad", "shadow", "flags", "state", "momentum", "args", "calls", "blocks", "pending", "ptrs",
+                 "staging", "lo", "hi", "per")
 
 
 class PeerShardedSGD:
     """SGD (momentum, weight decay; the reference recipe) for `params`, fused with the gradient mean over ranks.
 
-    Usage per step:  forward/backward (the managed layers call back into `_layer_done` from their backward, which
-    enqueues the peer kernel on a high-priority side stream) -> `join()` before the next forward.
-    One backward per step: the weight-gradient kernel overwrites the gradient buffer."""
+    Usage per step:  forward/backward (the managed layers call back from their backward: `_after_wgrad` when the
+    weight-gradient kernel is enqueued, `_layer_done` when the layer's last backward kernel is) -> `join()` before
+    the next forward.  One backward per step: the weight-gradient kernel overwrites the gradient buffer.
 
-    def __init__(self, params, lr=1e-3, momentum=0.9, weight_decay=0.0, max_ctas=48, share_master=False, group=None):
+    transport="copy" (default): the copy engines push slice r of the local gradient into rank r's staging area as soon
+    as the weight gradient exists, the update kernel touches local memory only, the copy engines push the refreshed
+    bf16 slice to every rank.  transport="stores": one kernel does everything with SM-issued P2P loads and stores."""
+
+    def __init__(self, params, lr=1e-3, momentum=0.9, weight_decay=0.0, max_ctas=0, reserve_sms=0, share_master=False,
+                 transport="copy", group=None):
         if not (dist.is_available() and dist.is_initialized()):
             raise RuntimeError("PeerShardedSGD needs an initialised torch.distributed process group")
+        if transport not in ("copy", "stores"):
+            raise ValueError("transport must be 'copy' or 'stores'")
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         if self.world > _lib.DA_MAX_PEERS:
             raise RuntimeError(f"PeerShardedSGD: at most {_lib.DA_MAX_PEERS} ranks (one NVSwitch box)")
         self.lr, self.momentum, self.weight_decay = float(lr), float(momentum), float(weight_decay)
         self.max_ctas, self.share_master, self.group = int(max_ctas), bool(share_master), group
+        self.reserve_sms, self.transport = int(reserve_sms), transport
         self.items = []
         params = [p for p in params if p.requires_grad]
         if not params:
@@ -106,26 +115,35 @@ class PeerShardedSGD:
         self._sms = torch.cuda.get_device_properties(dev).multi_processor_count
         self._limited = False
         local_handles = []
+        copy = transport == "copy"
         for p in params:
             if p.dtype != torch.float32 or not p.is_cuda or not F_._dense_memory(p):
                 raise RuntimeError("PeerShardedSGD manages densely stored fp32 CUDA parameters")
             dist.broadcast(p.data, 0, group=group)          # identical masters to start from
             m = _Managed()
             m.param, m.n, m.calls, m.pending = p, p.numel(), 0, False
-            lo, hi, per = slice_bounds(m.n, self.world, self.rank)
-            blocks = [PeerBlock(4 * m.n, dev), PeerBlock(2 * m.n, dev), PeerBlock(4 * _lib.DA_PEER_FLAG_INTS, dev)]
+            m.lo, m.hi, m.per = slice_bounds(m.n, self.world, self.rank)
+            # blocks peers map: [0] gradient (stores) or staging area world x per (copy), [1] bf16 operand copy, [2] flags,
+            # [3] fp32 master (share_master)
+            blocks = [PeerBlock(4 * (self.world * m.per if copy else m.n), dev), PeerBlock(2 * m.n, dev),
+                      PeerBlock(4 * _lib.DA_PEER_FLAG_INTS, dev)]
             if self.share_master:
                 blocks.append(PeerBlock(4 * m.n, dev))
             m.blocks = blocks
-            m.grad = blocks[0].tensor(torch.float32, m.n)
+            if copy:
+                m.staging = blocks[0]
+                m.grad = torch.zeros(m.n, dtype=torch.float32, device=dev)     # local only: peers never read it
+            else:
+                m.staging = None
+                m.grad = blocks[0].tensor(torch.float32, m.n)
             m.shadow = blocks[1].tensor(torch.bfloat16, m.n)
             m.flags = blocks[2].tensor(torch.int32, _lib.DA_PEER_FLAG_INTS)
-            if self.share_master:                            # re-home the master so that peers can store into it
+            if self.share_master:                            # re-home the master so that peers can write into it
                 master = blocks[3].tensor(torch.float32, m.n).as_strided(p.shape, p.stride())
                 master.copy_(p.data)
                 p.data = master
             m.state = torch.zeros(4, dtype=torch.int32, device=dev)
-            m.momentum = torch.zeros(max(per, 8), dtype=torch.float32, device=dev)
+            m.momentum = torch.zeros(max(m.per, 8), dtype=torch.float32, device=dev)
             # the operand copy every layer call will use from now on (functional.bf16_shadow's cache)
             check(lib.da_cast(F_._ptr(p.data), _lib.DA_F32, F_._ptr(m.shadow), _lib.DA_BF16, m.n, F_._stream()), "cast")
             p._da_shadow = (p._version, m.shadow.as_strided(p.shape, p.stride()))
@@ -137,25 +155,62 @@ class PeerShardedSGD:
         for k, m in enumerate(self.items):
             ptrs = [[b.ptr for b in m.blocks] if r == self.rank else [open_peer(h) for h in gathered[r][k]]
                     for r in range(self.world)]
-            m.args = make_args(m.param.data_ptr(), m.momentum.data_ptr(), [q[0] for q in ptrs], [q[1] for q in ptrs],
-                               [q[3] for q in ptrs] if self.share_master else None, [q[2] for q in ptrs],
-                               m.state.data_ptr(), m.n, self.world, self.rank)
-            F_.MANAGED_WGRAD[id(m.param)] = (m.grad, (lambda m=m: self._layer_done(m)))
+            m.ptrs = ptrs
+            flags = [q[2] for q in ptrs]
+            if copy:
+                # grad[r] + i must address element i (absolute index, lo <= i < hi) of what rank r pushed: slot r of the
+                # LOCAL staging area; the own gradient is read in place
+                base = m.blocks[0].ptr
+                grads = [m.grad.data_ptr() if r == self.rank else base + 4 * (r * m.per - m.lo) for r in range(self.world)]
+                shadows = [m.shadow.data_ptr() if r == self.rank else 0 for r in range(self.world)]
+                m.args = make_args(m.param.data_ptr(), m.momentum.data_ptr(), grads, shadows, None, flags,
+                                   m.state.data_ptr(), m.n, self.world, self.rank)
+            else:
+                m.args = make_args(m.param.data_ptr(), m.momentum.data_ptr(), [q[0] for q in ptrs], [q[1] for q in ptrs],
+                                   [q[3] for q in ptrs] if self.share_master else None, flags,
+                                   m.state.data_ptr(), m.n, self.world, self.rank)
+            F_.MANAGED_WGRAD[id(m.param)] = (m.grad, (lambda m=m: self._after_wgrad(m)), (lambda m=m: self._layer_done(m)))
         dist.barrier(group=group)                             # every rank has mapped every block before the first step
 
-    def _layer_done(self, m):
+    def _comm_after_current(self):
+        ev = torch.cuda.Event()
+        ev.record()
+        self.comm_stream.wait_event(ev)
+        return ctypes.c_void_p(self.comm_stream.cuda_stream)
+
+    def _after_wgrad(self, m):
+        """The weight-gradient kernel is enqueued: start pushing the slices the other ranks own (copy engines)."""
         if m.pending:
             raise RuntimeError("PeerShardedSGD: two backward passes through a managed layer in one step "
                                "(gradient accumulation is not supported on the peer path)")
         m.pending = True
-        ev = torch.cuda.Event()
-        ev.record()
-        self.comm_stream.wait_event(ev)
-        check(lib.da_sgd_step_peer(ctypes.byref(m.args), self.lr, self.momentum, self.weight_decay, int(m.calls == 0),
-                                   self.max_ctas, ctypes.c_void_p(self.comm_stream.cuda_stream)), "sgd_step_peer")
+        if self.transport != "copy":
+            return
+        st = self._comm_after_current()
+        for k in range(1, self.world):
+            r = (self.rank + k) % self.world
+            lo, hi, _ = slice_bounds(m.n, self.world, r)
+            check(lib.da_peer_copy(m.ptrs[r][0] + 4 * self.rank * m.per, m.grad.data_ptr() + 4 * lo, 4 * (hi - lo), st), "peer_copy")
+
+    def _layer_done(self, m):
+        """The layer's backward is enqueued (it no longer reads its operand copy): update the own slice and publish it."""
+        st = self._comm_after_current()
+        first = int(m.calls == 0)
+        if self.transport == "copy":
+            check(lib.da_sgd_step_peer(ctypes.byref(m.args), self.lr, self.momentum, self.weight_decay, first, self.max_ctas,
+                                       _lib.DA_PEER_PUBLISH_BY_CALLER, st), "sgd_step_peer")
+            for k in range(1, self.world):
+                r = (self.rank + k) % self.world
+                check(lib.da_peer_copy(m.ptrs[r][1] + 2 * m.lo, m.shadow.data_ptr() + 2 * m.lo, 2 * (m.hi - m.lo), st), "peer_copy")
+                if self.share_master:
+                    check(lib.da_peer_copy(m.ptrs[r][3] + 4 * m.lo, m.param.data_ptr() + 4 * m.lo, 4 * (m.hi - m.lo), st), "peer_copy")
+            check(lib.da_peer_publish_done(ctypes.byref(m.args), st), "peer_publish_done")
+        else:
+            check(lib.da_sgd_step_peer(ctypes.byref(m.args), self.lr, self.momentum, self.weight_decay, first, self.max_ctas,
+                                       _lib.DA_PEER_PUBLISH_STORES, st), "sgd_step_peer")
         m.calls += 1
-        if not self._limited and self.max_ctas > 0:
-            F_.set_sm_limit(self._sms - self.max_ctas)       # persistent kernels leave room for the peer kernel
+        if not self._limited and self.reserve_sms > 0:
+            F_.set_sm_limit(self._sms - self.reserve_sms)    # persistent kernels leave room for the peer kernel
             self._limited = True
 
     def join(self):
