@@ -56,7 +56,10 @@ def main():
         else:
             assert float((wa - wb).abs().max()) <= 1e-6 * float(wb.abs().max())
             assert float((sa.float() - sb.float()).abs().max()) <= 2 ** -7 * float(sb.float().abs().max())
-        assert torch.equal(lin_a.bias.data, lin_b.bias.data)
+        if exact:
+            assert torch.equal(lin_a.bias.data, lin_b.bias.data)
+        else:     # the two weight trajectories differ in the last bits, so do the activations behind them
+            assert float((lin_a.bias.data - lin_b.bias.data).abs().max()) <= 1e-4 * float(lin_b.bias.data.abs().max())
     popt.check_errors()
     popt.gather_master()
     torch.cuda.synchronize()
