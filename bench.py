@@ -55,6 +55,7 @@ def parse_args():
                     help="N>1: 'peer' = FC1's gradient mean + SGD + operand broadcast in one kernel over NVLink peer memory "
                          "(peer.PeerShardedSGD), NCCL all-reduce for the small tensors; 'nccl' = NCCL all-reduce for everything")
     ap.add_argument("--peer-ctas", type=int, default=0, help="grid cap of the peer kernel (0 = two 128-thread CTAs per SM)")
+    ap.add_argument("--no-fused-wgrad-sgd", action="store_true", help="N=1: separate weight-gradient and SGD kernels for FC1")
     ap.add_argument("--peer-transport", default="copy", choices=["copy", "stores"])
     ap.add_argument("--peer-reserve-sms", type=int, default=0, help="SMs the persistent kernels leave free while the peer kernel runs")
     return ap.parse_args()
@@ -146,7 +147,14 @@ def run_ours(args):
     peer_opt, sync_note = None, "none (1 GPU)"
     if world > 1:
         sync_note = "nccl avg fp32, side stream from the weight-gradient kernel on, persistent kernels on SMs-32 meanwhile"
-        if args.grad_sync == "peer" and pairs == 1 and args.engine == "umma_bf16":
+    fuse = []
+    if world == 1 and pairs == 1 and args.engine == "umma_bf16" and not args.no_fused_wgrad_sgd:
+        # one GPU: nothing happens between FC1's weight gradient and its update, so the update rides in the epilogue of the
+        # weight-gradient kernel (da_conv_backward_weight_sgd) and the 411 MB gradient is never written or re-read
+        fuse = [p for p in params if p.numel() >= (1 << 24)]
+        sync_note = "none (1 GPU); FC1's SGD update is applied by the epilogue of its weight-gradient kernel"
+    if world > 1 and args.grad_sync == "peer" and pairs == 1 and args.engine == "umma_bf16":
+        if True:
             big = [p for p in params if p.numel() >= (1 << 24)]
             try:
                 peer_opt = peer.PeerShardedSGD(big, max_ctas=args.peer_ctas, reserve_sms=args.peer_reserve_sms, transport=args.peer_transport, **sgd)
@@ -160,7 +168,7 @@ def run_ours(args):
                 peer_opt = None
                 F_.MANAGED_WGRAD.clear()
                 sync_note += f" (peer path unavailable: {type(e).__name__}: {str(e)[:100]})"
-    opt = optim.FusedSGD(params, **sgd)
+    opt = optim.FusedSGD(params, fuse_wgrad=fuse, **sgd)
     reducer = ddist.OverlappedGradAllReduce(params) if world > 1 else None
 
     # two input sets (alternated); each is > L2 (C5 alone is 67 MB bf16 per pair, FC1's weight 411 MB)

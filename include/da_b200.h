@@ -279,6 +279,21 @@ int da_conv_backward_data(const da_conv_desc* d, const void* dz, const void* w,
 int da_conv_backward_weight(const da_conv_desc* d, const void* x, const void* dz,
                             float* dw, void* workspace, size_t workspace_bytes,
                             da_stream_t stream);
+/* Weight gradient FUSED with the optimizer step of that weight (one GPU: no gradient exchange in between): the
+ * epilogue of the tcgen05 weight-gradient kernel applies the SGD rule of da_sgd_step (same operation order, bit-identical
+ * results) to master / momentum / bf16 operand copy at each tile's addresses; the gradient itself is never written.
+ * Replaces  layer backward (torch autograd) -> torch.optim.SGD.step (mmdet/apis/train.py:127) for one weight: 18 B per
+ * parameter of HBM traffic instead of 4 + 22.  The tensors use the memory order of dw ([Cout,KH,KW,Cin]); Cin % 32 == 0;
+ * call it AFTER the layer's data gradient (the operand copy is rewritten). */
+typedef struct da_sgd_fuse {
+  float* w;              /* fp32 master */
+  float* momentum_buf;   /* fp32 momentum */
+  void* w_bf16;          /* bf16 operand copy (NULL = none) */
+  float lr, momentum, weight_decay;
+  int32_t first_step;    /* 1 = momentum buffer uninitialised */
+} da_sgd_fuse;
+int da_conv_backward_weight_sgd(const da_conv_desc* d, const void* x, const void* dz, const da_sgd_fuse* sgd,
+                                void* workspace, size_t workspace_bytes, da_stream_t stream);
 int da_dropout_mask(uint64_t seed, int64_t n, float drop_p, uint8_t* keep_out, da_stream_t stream);
 /* Optional device-resident uint64 step counter added to every dropout seed at kernel run time (NULL to
  * disable): lets a CUDA-graph replay of a captured train step draw fresh masks. */

@@ -76,7 +76,8 @@ def main():
     q = p.detach().clone()
     qbuf, qsh = torch.zeros_like(q), torch.empty_like(q, dtype=torch.bfloat16)
     popt2 = peer.PeerShardedSGD([p], lr=LR, momentum=MU, weight_decay=WD, transport=transport)
-    gbuf, wgrad_done, done = F_.MANAGED_WGRAD[id(p)]
+    mw = F_.MANAGED_WGRAD[id(p)]
+    gbuf, wgrad_done, done = mw.grad, mw.after_wgrad, mw.layer_done
     src = torch.randn(1 << 22, device=dev, generator=g)
 
     def one_step():
@@ -115,7 +116,7 @@ def main():
         big = torch.nn.Parameter(torch.zeros(n, device=dev))
         for transport, ctas in (("copy", 0), ("copy", 592), ("stores", 296)):
             po = peer.PeerShardedSGD([big], lr=LR, momentum=MU, weight_decay=WD, max_ctas=ctas, transport=transport)
-            _, wgrad_big, done_big = F_.MANAGED_WGRAD[id(big)]
+            wgrad_big, done_big = F_.MANAGED_WGRAD[id(big)].after_wgrad, F_.MANAGED_WGRAD[id(big)].layer_done
             ts = []
             for it in range(6):
                 dist.barrier()

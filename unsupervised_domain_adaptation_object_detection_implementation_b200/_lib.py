@@ -39,6 +39,12 @@ class PeerSgdArgs(Structure):
                 ("local_state", c_void_p), ("n", c_int64), ("world", c_int32), ("rank", c_int32)]
 
 
+class SgdFuse(Structure):
+    """da_sgd_fuse (include/da_b200.h)."""
+    _fields_ = [("w", c_void_p), ("momentum_buf", c_void_p), ("w_bf16", c_void_p),
+                ("lr", c_float), ("momentum", c_float), ("weight_decay", c_float), ("first_step", c_int32)]
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -96,6 +102,7 @@ SIGNATURES = {
     "da_conv_act_backward": (I, [CD, P, P, P, I, F, U64, P, P, P, P, S, P]),
     "da_conv_backward_data": (I, [CD, P, P, F, P, P, S, P]),
     "da_conv_backward_weight": (I, [CD, P, P, P, P, S, P]),
+    "da_conv_backward_weight_sgd": (I, [CD, P, P, P, P, S, P]),
     "da_dropout_mask": (I, [U64, L, F, P, P]),
     "da_set_dropout_counter": (I, [P]),
     "da_global_avgpool_workspace_bytes": (S, [I, I]),

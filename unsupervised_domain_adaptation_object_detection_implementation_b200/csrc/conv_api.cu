@@ -19,7 +19,7 @@ int umma_conv_forward(const da_conv_desc* d, const void* x, const void* w, const
 int umma_conv_backward_data(const da_conv_desc* d, const void* dz, const void* w, float out_scale, void* dx,
                             void* ws, size_t ws_bytes, cudaStream_t st);
 int umma_conv_backward_weight(const da_conv_desc* d, const void* x, const void* dz, float* dw, void* ws,
-                              size_t ws_bytes, cudaStream_t st);
+                              size_t ws_bytes, cudaStream_t st, const da_sgd_fuse* sgd);
 }  // namespace da
 
 using namespace da;
@@ -76,5 +76,15 @@ extern "C" int da_conv_backward_weight(const da_conv_desc* d, const void* x, con
   DA_REQUIRE(x && dz && dw, DA_ERR_INVALID_ARG, "conv_backward_weight: null tensor");
   cudaStream_t st = (cudaStream_t)stream;
   if (d->engine == DA_ENGINE_SIMT_F32) return simt_conv_backward_weight(d, x, dz, dw, workspace, workspace_bytes, st);
-  return umma_conv_backward_weight(d, x, dz, dw, workspace, workspace_bytes, st);
+  return umma_conv_backward_weight(d, x, dz, dw, workspace, workspace_bytes, st, nullptr);
+}
+
+extern "C" int da_conv_backward_weight_sgd(const da_conv_desc* d, const void* x, const void* dz, const da_sgd_fuse* sgd,
+                                           void* workspace, size_t workspace_bytes, da_stream_t stream) {
+  int rc = check_desc(d, "conv_backward_weight_sgd");
+  if (rc) return rc;
+  DA_REQUIRE(x && dz && sgd, DA_ERR_INVALID_ARG, "conv_backward_weight_sgd: null argument");
+  DA_REQUIRE(d->engine != DA_ENGINE_SIMT_F32, DA_ERR_UNSUPPORTED,
+             "conv_backward_weight_sgd: the fused update lives in the tcgen05 weight-gradient kernel (engine umma_*)");
+  return umma_conv_backward_weight(d, x, dz, nullptr, workspace, workspace_bytes, (cudaStream_t)stream, sgd);
 }

@@ -212,12 +212,31 @@ __global__ void peer_wait_kernel(const int* flags_local, int* local_state, int w
   }
 }
 
+// CUDA loads kernels lazily, and loading one can wait for the kernels that are running: a spinning peer kernel in front
+// of the FIRST launch of another peer kernel would stall the host until the time-out.  Load them all up front.
+static void preload_peer_kernels() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  cudaFuncAttributes fa;
+  (void)cudaFuncGetAttributes(&fa, sgd_step_peer_kernel<1, 4>);
+  (void)cudaFuncGetAttributes(&fa, sgd_step_peer_kernel<2, 4>);
+  (void)cudaFuncGetAttributes(&fa, sgd_step_peer_kernel<4, 2>);
+  (void)cudaFuncGetAttributes(&fa, sgd_step_peer_kernel<8, 1>);
+  (void)cudaFuncGetAttributes(&fa, sgd_step_peer_kernel<0, 2>);
+  (void)cudaFuncGetAttributes(&fa, sgd_step_peer_kernel<0, 1>);
+  (void)cudaFuncGetAttributes(&fa, peer_signal_done_kernel);
+  (void)cudaFuncGetAttributes(&fa, peer_wait_kernel);
+  (void)cudaGetLastError();
+}
+
 }  // namespace da
 
 using namespace da;
 
 extern "C" int da_peer_alloc(size_t bytes, void** out) {
   DA_REQUIRE(out && bytes > 0, DA_ERR_INVALID_ARG, "peer_alloc: bad args");
+  preload_peer_kernels();
   DA_CUDA_OK(cudaMalloc(out, bytes));
   DA_CUDA_OK(cudaMemset(*out, 0, bytes));
   DA_CUDA_OK(cudaDeviceSynchronize());
@@ -269,6 +288,7 @@ extern "C" int da_sgd_step_peer(const da_peer_sgd_args* a, float lr, float momen
   DA_REQUIRE(publish_mode == DA_PEER_PUBLISH_STORES || publish_mode == DA_PEER_PUBLISH_BY_CALLER, DA_ERR_INVALID_ARG,
              "sgd_step_peer: publish_mode %d", publish_mode);
   const int sd = publish_mode == DA_PEER_PUBLISH_STORES ? 1 : 0;
+  preload_peer_kernels();
   DA_REQUIRE(a && a->w && a->momentum_shard && a->local_state && a->n > 0, DA_ERR_INVALID_ARG, "sgd_step_peer: bad args");
   DA_REQUIRE(a->world >= 1 && a->world <= DA_MAX_PEERS && a->rank >= 0 && a->rank < a->world, DA_ERR_INVALID_ARG,
              "sgd_step_peer: world %d / rank %d out of range (max %d peers)", a->world, a->rank, DA_MAX_PEERS);

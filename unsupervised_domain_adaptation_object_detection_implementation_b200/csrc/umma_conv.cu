@@ -445,6 +445,57 @@ __device__ __forceinline__ void warp_store_rows_f32(const uint32_t* v, float* ro
   __syncwarp();
 }
 
+// Same data path as warp_store_rows_f32, but the 32x32 gradient chunk never reaches memory: the lanes that would store a
+// 16-byte piece of a row load the matching pieces of the fp32 master and of the momentum buffer (all 16 loads of a lane
+// are issued before the first use: 8 KB in flight per warp), apply torch.optim.SGD's rule with the operation order of
+// sgd_step_kernel (bit-identical results) and store master, momentum and the bf16 operand copy.
+// `w_row` = this lane's row in the master (nullptr: row outside the tensor).
+__device__ __forceinline__ void warp_sgd_rows(const uint32_t* v, float* w_row, uint8_t* wstage, int lane, float* w_base,
+                                              float* buf_base, __nv_bfloat16* shadow_base, float lr, float mu, float wd, int first) {
+  uint4* srow = reinterpret_cast<uint4*>(wstage + lane * 128);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) srow[j ^ (lane & 7)] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  __syncwarp();
+  const int sub = lane >> 3, piece = lane & 7;
+  const unsigned long long mine = reinterpret_cast<unsigned long long>(w_row);
+  float4 wv[8], bv[8];
+  unsigned long long dst[8];
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int row = it * 4 + sub;
+    dst[it] = __shfl_sync(0xffffffffu, mine, row);
+    if (dst[it]) {
+      dst[it] += piece * 16;
+      wv[it] = *reinterpret_cast<const float4*>(dst[it]);
+      bv[it] = first ? make_float4(0.f, 0.f, 0.f, 0.f)
+                     : *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(buf_base) + (dst[it] - reinterpret_cast<unsigned long long>(w_base)));
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int row = it * 4 + sub;
+    const float4 gv = *reinterpret_cast<const float4*>(wstage + row * 128 + ((piece ^ (row & 7)) << 4));
+    if (dst[it]) {
+      float* wp = &wv[it].x; float* bp = &bv[it].x; const float* gp = &gv.x;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float d = fmaf(wd, wp[j], gp[j]);
+        bp[j] = first ? d : fmaf(mu, bp[j], d);
+        wp[j] = fmaf(-lr, bp[j], wp[j]);
+      }
+      const unsigned long long off = dst[it] - reinterpret_cast<unsigned long long>(w_base);
+      *reinterpret_cast<float4*>(dst[it]) = wv[it];
+      *reinterpret_cast<float4*>(reinterpret_cast<char*>(buf_base) + off) = bv[it];
+      if (shadow_base) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(wv[it].x, wv[it].y), b = __floats2bfloat162_rn(wv[it].z, wv[it].w);
+        *reinterpret_cast<uint2*>(reinterpret_cast<char*>(shadow_base) + (off >> 1)) =
+            make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+      }
+    }
+  }
+  __syncwarp();
+}
+
 // ---------------------------------------------------------------------------------------
 // weight gradient ("TN"): dW[co, tap, ci] = sum_pix dZ[pix, co] * X[pix_in(tap), ci]
 // ---------------------------------------------------------------------------------------
@@ -464,6 +515,13 @@ struct TnParams {
   int Cout, Cin;
   float* dw;                // [Cout, taps, Cin] fp32 (or partial [splits][...])
   long long dw_numel;
+  // fused optimizer (da_conv_backward_weight_sgd): when sgd_w != nullptr the epilogue applies the SGD rule to the fp32
+  // master / momentum / bf16 operand copy at the tile's addresses instead of storing the gradient (same memory order as dw)
+  float* sgd_w;
+  float* sgd_buf;
+  __nv_bfloat16* sgd_shadow;
+  float sgd_lr, sgd_mu, sgd_wd;
+  int sgd_first;
 };
 
 // Persistent kernel, one CTA per SM.  Tile = (Cout tile, Cin tile, tap, pixel split); tiles are enumerated per
@@ -625,6 +683,12 @@ umma_tn_kernel(const __grid_constant__ TnParams P, int co_tiles, int ci_tiles, i
         }
         const int cb = ci0 + cc * 32;
         if (cb < P.Cin) {   // warp-uniform
+          if (P.sgd_w) {    // fused optimizer (launcher guarantees Cin % 32 == 0, splits == 1, 16-byte aligned tensors)
+            float* wr = (co < P.Cout) ? P.sgd_w + ((size_t)co * P.num_taps + tap) * P.Cin + cb : nullptr;
+            warp_sgd_rows(v, wr, epi_stage + (warp - 2) * 4096, lane, P.sgd_w, P.sgd_buf, P.sgd_shadow, P.sgd_lr, P.sgd_mu,
+                          P.sgd_wd, P.sgd_first);
+            continue;
+          }
           float* o = (co < P.Cout) ? out + ((size_t)co * P.num_taps + tap) * P.Cin + cb : nullptr;
           const int ncols = min(32, P.Cin - cb);
           if (ncols == 32 && (P.Cin & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
@@ -1160,8 +1224,16 @@ static int launch_tn_t(const TnParams& P, int co_tiles, int ci_tiles, int splits
 }
 
 int umma_conv_backward_weight(const da_conv_desc* d, const void* x, const void* dz, float* dw, void* ws,
-                              size_t ws_bytes, cudaStream_t st) {
+                              size_t ws_bytes, cudaStream_t st, const da_sgd_fuse* sgd) {
   const Geom g = geom_of(d);
+  if (sgd) {
+    DA_REQUIRE(sgd->w && sgd->momentum_buf, DA_ERR_INVALID_ARG, "umma wgrad+sgd: null master / momentum");
+    DA_REQUIRE(g.Cin % 32 == 0, DA_ERR_UNSUPPORTED, "umma wgrad+sgd: Cin must be a multiple of 32");
+    DA_REQUIRE((((uintptr_t)sgd->w | (uintptr_t)sgd->momentum_buf) & 15) == 0 && ((uintptr_t)sgd->w_bf16 & 7) == 0,
+               DA_ERR_INVALID_ARG, "umma wgrad+sgd: tensors must be 16-byte aligned");
+  } else {
+    DA_REQUIRE(dw, DA_ERR_INVALID_ARG, "umma wgrad: null output");
+  }
   DA_REQUIRE(g.Cin % 8 == 0 && g.Cout % 8 == 0, DA_ERR_UNSUPPORTED, "umma wgrad: channels must be multiples of 8");
   DA_REQUIRE(g.KH * g.KW <= MAX_TAPS && g.s <= 2, DA_ERR_UNSUPPORTED, "umma wgrad: unsupported filter/stride");
   DA_REQUIRE(ws && ws_bytes >= umma_workspace_bytes(d), DA_ERR_WORKSPACE, "umma wgrad: workspace too small");
@@ -1232,6 +1304,11 @@ int umma_conv_backward_weight(const da_conv_desc* d, const void* x, const void* 
   long long k_iters = patches * P.num_terms;
   int splits = pick_splits_persistent(tiles, (int)(k_iters > 1000000 ? 1000000 : k_iters));
   while (splits > 1 && (size_t)splits * P.dw_numel * sizeof(float) > part_bytes(g)) --splits;
+  if (sgd) {     // every gradient element must be complete inside one tile: no split-K
+    splits = 1;
+    P.sgd_w = sgd->w; P.sgd_buf = sgd->momentum_buf; P.sgd_shadow = (__nv_bfloat16*)sgd->w_bf16;
+    P.sgd_lr = sgd->lr; P.sgd_mu = sgd->momentum; P.sgd_wd = sgd->weight_decay; P.sgd_first = sgd->first_step;
+  }
   P.dw = splits > 1 ? (float*)ws : dw;
   const int co_tiles = (g.Cout + BM - 1) / BM, ci_tiles = (g.Cin + bn - 1) / bn;
   // Cout tiles that share an X tile form a cluster (TMA multicast of the shared operand)

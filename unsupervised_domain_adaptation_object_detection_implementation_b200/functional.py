@@ -412,11 +412,24 @@ def _w_ohwi(w):
 
 # callable(dw) invoked right after a layer's weight-gradient kernel has been enqueued (None = disabled)
 WGRAD_HOOK = None
-# Weights whose gradient is owned by a peer-memory optimizer (peer.PeerShardedSGD): id(weight) -> (flat fp32 buffer the
-# weight-gradient kernel writes into, callable invoked right after that kernel is enqueued, callable invoked once all of
-# the layer's backward kernels are enqueued).  Autograd sees
-# such a weight as a constant: no .grad tensor is produced, the optimizer consumes the buffer directly.
+# Weights whose gradient never becomes a .grad tensor: id(weight) -> ManagedWeight.  Autograd sees such a weight as a
+# constant; the layer's backward hands the gradient to the optimizer that registered it:
+#   * peer.PeerShardedSGD (N GPUs): the weight-gradient kernel writes `grad`, `after_wgrad` / `layer_done` start the
+#     exchange and the sharded update on a side stream;
+#   * optim.FusedSGD(fuse_wgrad=...) (one GPU): `fuse()` returns the da_sgd_fuse record of this call and the
+#     weight-gradient kernel applies the update in its epilogue (da_conv_backward_weight_sgd); no gradient is stored.
 MANAGED_WGRAD = {}
+
+
+class ManagedWeight:
+    grad = None        # flat fp32 buffer for the weight gradient (None with `fuse`)
+    fuse = None        # callable -> _lib.SgdFuse
+
+    def after_wgrad(self):     # the weight-gradient kernel is enqueued
+        pass
+
+    def layer_done(self):      # every backward kernel of the layer is enqueued (it no longer reads its operand copy)
+        pass
 
 
 class DenseLayerFunction(Function):
@@ -482,12 +495,12 @@ class DenseLayerFunction(Function):
         # weight gradient first: a gradient all-reduce can then start while the data gradient of the same layer runs
         # (WGRAD_HOOK, installed by dist.OverlappedGradAllReduce)
         managed = ctx.managed
-        if managed is not None:
+        if managed is not None and managed.fuse is None:
             desc_w = _conv_desc(N, H, W_, Cin, Cout, KH, KW, stride, pad, engine, x.dtype, x.dtype)
-            check(lib.da_conv_backward_weight(ctypes.byref(desc_w), _ptr(x), _ptr(dz), _ptr(managed[0]), _ptr(ws), ws.numel(),
+            check(lib.da_conv_backward_weight(ctypes.byref(desc_w), _ptr(x), _ptr(dz), _ptr(managed.grad), _ptr(ws), ws.numel(),
                                               _stream()), "conv_backward_weight")
-            managed[1]()     # the gradient buffer is complete in stream order
-        elif ctx.needs_input_grad[1]:
+            managed.after_wgrad()     # the gradient buffer is complete in stream order
+        elif managed is None and ctx.needs_input_grad[1]:
             desc_w = _conv_desc(N, H, W_, Cin, Cout, KH, KW, stride, pad, engine, x.dtype, x.dtype)
             dwv = torch.empty((Cout, KH, KW, Cin), dtype=torch.float32, device=dev)
             check(lib.da_conv_backward_weight(ctypes.byref(desc_w), _ptr(x), _ptr(dz), _ptr(dwv), _ptr(ws), ws.numel(),
@@ -503,7 +516,12 @@ class DenseLayerFunction(Function):
             check(lib.da_conv_backward_data(ctypes.byref(desc_d), _ptr(dz), _ptr(wv), float(grl), _ptr(dx), _ptr(ws),
                                             ws.numel(), _stream()), "conv_backward_data")
         if managed is not None:
-            managed[2]()     # the layer no longer reads its operand copy
+            if managed.fuse is not None:     # data gradient first: the fused kernel rewrites the operand copy it read
+                desc_w = _conv_desc(N, H, W_, Cin, Cout, KH, KW, stride, pad, engine, x.dtype, x.dtype)
+                rec = managed.fuse()
+                check(lib.da_conv_backward_weight_sgd(ctypes.byref(desc_w), _ptr(x), _ptr(dz), ctypes.byref(rec), _ptr(ws),
+                                                      ws.numel(), _stream()), "conv_backward_weight_sgd")
+            managed.layer_done()
         if need_scale:
             # v = acc*scale + shift  =>  d(scale) = sum dv*acc = (dvdot - shift*dshift) / scale
             t = sh if sh is not None else torch.zeros_like(dshift)

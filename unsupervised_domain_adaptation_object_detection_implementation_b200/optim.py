@@ -5,7 +5,7 @@ lr=1e-3, momentum=0.9, weight_decay=5e-4), executed by libda_b200's da_sgd_step:
 import torch
 
 from . import functional as F_
-from ._lib import lib, check
+from ._lib import lib, check, SgdFuse as _lib_SgdFuse
 
 _CHUNK = 65536   # DA_SGD_CHUNK (include/da_b200.h)
 
@@ -16,14 +16,39 @@ def _same_layout(a, b):
 
 
 class FusedSGD:
-    def __init__(self, params, lr=1e-3, momentum=0.9, weight_decay=0.0, shadow_bf16=True):
+    def __init__(self, params, lr=1e-3, momentum=0.9, weight_decay=0.0, shadow_bf16=True, fuse_wgrad=()):
+        """fuse_wgrad: parameters (weights of functional.dense_layer layers on the bf16 tensor-core engine) whose update
+        is applied by the epilogue of their weight-gradient kernel during backward (da_conv_backward_weight_sgd): their
+        gradient is never materialised and `step()` skips them.  One backward per step; one GPU (no gradient exchange)."""
         self.params = [p for p in params if p.requires_grad]
+        self.fused = []
+        for p in fuse_wgrad:
+            self._register_fused(p)
         self.lr, self.momentum, self.weight_decay = float(lr), float(momentum), float(weight_decay)
         self.shadow_bf16 = shadow_bf16
         self.state = {}
         self.steps = 0
         self._chunks, self._chunk_key, self._keep, self._host, self._table, self._copied = None, None, None, None, None, None
         self._spare, self._captured = [], []
+
+    def _register_fused(self, p):
+        if not (p.is_cuda and p.dtype == torch.float32 and F_._dense_memory(p) and p.dim() >= 2):
+            raise RuntimeError("FusedSGD(fuse_wgrad): densely stored fp32 CUDA weights only")
+        self.params = [q for q in self.params if q is not p]
+        buf = torch.zeros_like(p)
+        shadow = F_.bf16_shadow(p)
+        state = {"calls": 0}
+        opt = self
+
+        class _Fused(F_.ManagedWeight):
+            def fuse(self_inner):
+                rec = _lib_SgdFuse(p.data_ptr(), buf.data_ptr(), shadow.data_ptr(), opt.lr, opt.momentum, opt.weight_decay,
+                                   int(state["calls"] == 0))
+                state["calls"] += 1
+                return rec
+
+        F_.MANAGED_WGRAD[id(p)] = _Fused()
+        self.fused.append((p, buf, shadow))
 
     def zero_grad(self, set_to_none=True):
         for p in self.params:

@@ -83,7 +83,10 @@ class _Managed:
 
 
 class PeerShardedSGD:
-    """SGD (momentum, weight decay; the reference recipe) for `params`, fused with the gradient mean over ranks.
+    """SGD (momentum, weight decay; the reference recipe) for `params`, fused with the gradient mean over ranks and
+    launched from INSIDE backward: the update of a layer runs on a side stream as soon as the layer's own backward
+    kernels are enqueued, under the rest of the backward pass (on one GPU that is all it does: the 2.3 GB optimizer
+    pass of FC1 is HBM-bound, the RoIAlign backward it then overlaps is latency-bound).
 
     Usage per step:  forward/backward (the managed layers call back from their backward: `_after_wgrad` when the
     weight-gradient kernel is enqueued, `_layer_done` when the layer's last backward kernel is) -> `join()` before
@@ -95,11 +98,12 @@ class PeerShardedSGD:
 
     def __init__(self, params, lr=1e-3, momentum=0.9, weight_decay=0.0, max_ctas=0, reserve_sms=0, share_master=False,
                  transport="copy", group=None):
-        if not (dist.is_available() and dist.is_initialized()):
-            raise RuntimeError("PeerShardedSGD needs an initialised torch.distributed process group")
         if transport not in ("copy", "stores"):
             raise ValueError("transport must be 'copy' or 'stores'")
-        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if dist.is_available() and dist.is_initialized():
+            self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        else:       # one GPU: no peers, the update still runs on the side stream under the rest of backward
+            self.world, self.rank = 1, 0
         if self.world > _lib.DA_MAX_PEERS:
             raise RuntimeError(f"PeerShardedSGD: at most {_lib.DA_MAX_PEERS} ranks (one NVSwitch box)")
         self.lr, self.momentum, self.weight_decay = float(lr), float(momentum), float(weight_decay)
@@ -119,7 +123,8 @@ class PeerShardedSGD:
         for p in params:
             if p.dtype != torch.float32 or not p.is_cuda or not F_._dense_memory(p):
                 raise RuntimeError("PeerShardedSGD manages densely stored fp32 CUDA parameters")
-            dist.broadcast(p.data, 0, group=group)          # identical masters to start from
+            if self.world > 1:
+                dist.broadcast(p.data, 0, group=group)      # identical masters to start from
             m = _Managed()
             m.param, m.n, m.calls, m.pending = p, p.numel(), 0, False
             m.lo, m.hi, m.per = slice_bounds(m.n, self.world, self.rank)
@@ -151,7 +156,8 @@ class PeerShardedSGD:
             self.items.append(m)
         torch.cuda.synchronize(dev)
         gathered = [None] * self.world
-        dist.all_gather_object(gathered, local_handles, group=group)
+        if self.world > 1:
+            dist.all_gather_object(gathered, local_handles, group=group)
         for k, m in enumerate(self.items):
             ptrs = [[b.ptr for b in m.blocks] if r == self.rank else [open_peer(h) for h in gathered[r][k]]
                     for r in range(self.world)]
@@ -169,8 +175,13 @@ class PeerShardedSGD:
                 m.args = make_args(m.param.data_ptr(), m.momentum.data_ptr(), [q[0] for q in ptrs], [q[1] for q in ptrs],
                                    [q[3] for q in ptrs] if self.share_master else None, flags,
                                    m.state.data_ptr(), m.n, self.world, self.rank)
-            F_.MANAGED_WGRAD[id(m.param)] = (m.grad, (lambda m=m: self._after_wgrad(m)), (lambda m=m: self._layer_done(m)))
-        dist.barrier(group=group)                             # every rank has mapped every block before the first step
+            mw = F_.ManagedWeight()
+            mw.grad = m.grad
+            mw.after_wgrad = (lambda m=m: self._after_wgrad(m))
+            mw.layer_done = (lambda m=m: self._layer_done(m))
+            F_.MANAGED_WGRAD[id(m.param)] = mw
+        if self.world > 1:
+            dist.barrier(group=group)                         # every rank has mapped every block before the first step
 
     def _comm_after_current(self):
         ev = torch.cuda.Event()
@@ -204,7 +215,8 @@ class PeerShardedSGD:
                 check(lib.da_peer_copy(m.ptrs[r][1] + 2 * m.lo, m.shadow.data_ptr() + 2 * m.lo, 2 * (m.hi - m.lo), st), "peer_copy")
                 if self.share_master:
                     check(lib.da_peer_copy(m.ptrs[r][3] + 4 * m.lo, m.param.data_ptr() + 4 * m.lo, 4 * (m.hi - m.lo), st), "peer_copy")
-            check(lib.da_peer_publish_done(ctypes.byref(m.args), st), "peer_publish_done")
+            if self.world > 1:
+                check(lib.da_peer_publish_done(ctypes.byref(m.args), st), "peer_publish_done")
         else:
             check(lib.da_sgd_step_peer(ctypes.byref(m.args), self.lr, self.momentum, self.weight_decay, first, self.max_ctas,
                                        _lib.DA_PEER_PUBLISH_STORES, st), "sgd_step_peer")
@@ -234,7 +246,7 @@ class PeerShardedSGD:
     @torch.no_grad()
     def gather_master(self):
         """Assemble the full fp32 master on every rank (checkpointing); a no-op with share_master."""
-        if self.share_master:
+        if self.share_master or self.world == 1:
             return
         for m in self.items:
             flat = m.param.data.as_strided((m.n,), (1,))
