@@ -279,3 +279,73 @@ def daf_org_da_losses(c5, bbox_feats, gt_domain, sd_img, sd_ins, lam=(0.1, 0.1, 
     c_loss = consistency_loss(img_feat, pred, labels)
     return dict(globle_da_loss=lam[0] * g_loss, local_da_loss=lam[1] * l_loss, consistency_loss=lam[2] * c_loss), \
         img_feat, pred
+
+
+# --------------------------------------------------------------------------------------
+# L5 group_local_da_loss — mmdet/models/detectors/DAFaster_rcnn.py:198-327 (DAF),
+# MAFaster_rcnn.py:204-299 (MAF), DAFaster_rcnn_Deep.py:232-329 (Deep).  Pinned to the reference's own
+# methods run on CPU (oracle/ref_loader.load_group_loss, golden group_local_da_loss.pt).
+# What the reference code actually computes (each point is visible in the cited lines):
+#   * RoI i is "foreground" iff softmax(bbox_cls[d][i])[0] >= 0.5                          (:240, :267)
+#   * DAF only: a group with more than k=20 members is replaced by the k-means "centroids" (:219-223) -
+#     but cluster.forward never writes the updated centroids back (`local = ...` rebinds a loop variable,
+#     models/utils/cluster.py:138-140), so the result is its random initialisation: 10 draws of randn(1024)
+#     (cluster.py:95-98), in the order fg_src, bg_src, fg_tar, bg_tar; a group of exactly 20 is kept; a smaller
+#     one is padded to 20 with copies of the member whose score has the largest softmax over the group (:198-210)
+#   * `len(fg_src)!=0 & len(fg_tar)!=0` parses as `len(fg_src) != (0 & len(fg_tar)) != 0`, which is always
+#     False: the source group is used alone whenever it is non-empty (labels 0), else the target group
+#     (labels 1)                                                                            (:283-305)
+#   * DAF/MAF call the head once per row with a [1,1024] input (:311-313): the NonLocalBlock then attends over a
+#     single token, i.e. y = x + W_mask W_g x; Deep passes the whole batch to the FC-only head (:316-317)
+#   * DAF: FocalLoss(gamma 2, alpha .25, mean) on the sigmoid outputs; MAF/Deep: CrossEntropy on them
+#   * the sum of the two losses is returned through .item(): a Python float, no gradient                (:325)
+# --------------------------------------------------------------------------------------
+def instance_alignment_single_token_logits(x, sd, q=None):
+    """InstanceAlignmentHead applied row by row ([1,1024] inputs): attention over one token is the identity."""
+    x = _q(grl(x), q)
+    g = _q(F.linear(x, _q(sd["nlb.conv_g.weight"].flatten(1), q)), q)
+    x = _q(F.linear(g, _q(sd["nlb.conv_mask.weight"].flatten(1), q)), q) + x
+    x = _q(F.relu(F.linear(x, _q(sd["fc1.weight"], q), sd["fc1.bias"])), q)
+    x = _q(F.relu(F.linear(x, _q(sd["fc2.weight"], q), sd["fc2.bias"])), q)
+    return F.linear(x, _q(sd["fc3.weight"], q), sd["fc3.bias"])
+
+
+def draw_centroids(dim=1024, n=10):
+    """The reference's centroid initialisation (cluster.py:95-98): n separate torch.randn([dim]) draws from the global RNG."""
+    return torch.stack([torch.randn([dim]) for _ in range(n)], 0)
+
+
+def group_features(feats, scores, k=20, draw=draw_centroids):
+    n = feats.shape[0]
+    if n > k:
+        return draw(feats.shape[1]).to(feats)
+    if n == k:
+        return feats
+    top = torch.argmax(torch.softmax(scores, dim=-1), dim=0)
+    return torch.cat([feats, feats[top].unsqueeze(0).expand(k - n, -1)], 0)
+
+
+def group_local_da_loss(bbox_feats, bbox_cls, sd_fore, sd_back, flavour="daf", k=20, draw=draw_centroids, q=None):
+    groups = {}
+    for d in (0, 1):                                     # source first, then target: the order of the RNG draws
+        p = torch.softmax(bbox_cls[d], dim=-1)
+        fg = p[:, 0] >= 0.5
+        for name, m, score in (("fg", fg, p[:, 0]), ("bg", ~fg, p[:, 1])):
+            f = bbox_feats[d][m]
+            if f.shape[0] and flavour == "daf":
+                f = group_features(f, score[m], k, draw)
+            groups[(name, d)] = f
+    total = bbox_feats[0].new_zeros(())
+    for name, sd in (("fg", sd_fore), ("bg", sd_back)):
+        src, tar = groups[(name, 0)], groups[(name, 1)]
+        if src.shape[0]:
+            f, label = src, 0
+        elif tar.shape[0]:
+            f, label = tar, 1
+        else:
+            continue
+        z = instance_alignment_daf_logits(f, sd, q=q) if flavour == "deep" else instance_alignment_single_token_logits(f, sd, q=q)
+        pred = torch.sigmoid(z)
+        labels = torch.full((f.shape[0],), label, dtype=torch.long)
+        total = total + (focal2(pred, labels) if flavour == "daf" else ce2(pred, labels))
+    return total.detach()

@@ -127,6 +127,45 @@ def focal_case(ns):
     print("focal:", float(loss))
 
 
+def group_loss_cases(ns):
+    """L5: the reference's own group_local_da_loss methods (compiled in place, ref_loader.load_group_loss) on CPU.
+    Inputs are a pure function of the case name (seeded); centroid draws come from torch.manual_seed(case seed)."""
+    import types
+    out = {}
+    # (name, flavour, n_src, n_tar, fg fraction src, fg fraction tar)
+    cases = [("daf_big", "daf", 60, 50, 0.5, 0.5), ("daf_pad", "daf", 30, 12, 0.25, 0.5), ("daf_exact20", "daf", 40, 8, 0.5, 0.5),
+             ("daf_src_has_no_fg", "daf", 16, 24, 0.0, 0.5), ("daf_nothing_bg", "daf", 10, 10, 1.0, 1.0),
+             ("maf_mixed", "maf", 48, 32, 0.4, 0.6), ("maf_src_has_no_fg", "maf", 20, 20, 0.0, 0.7),
+             ("deep_mixed", "deep", 64, 64, 0.5, 0.5), ("deep_src_has_no_bg", "deep", 12, 30, 1.0, 0.3)]
+    for idx, (name, flavour, ns_, nt_, fs, ft) in enumerate(cases):
+        fns = ref_loader.load_group_loss(flavour)
+        cls_head = ns.instance.InstanceAlignmentHead_DAF if flavour == "deep" else ns.instance.InstanceAlignmentHead
+        me = types.SimpleNamespace()
+        me.local_da_fore = seeded.fill_state_(cls_head().float().eval(), idx, prefix=f"group.{name}.fore.")
+        me.local_da_back = seeded.fill_state_(cls_head().float().eval(), idx, prefix=f"group.{name}.back.")
+        me.criterion_fl = ns.focal.FocalLoss()
+        me.criterion = torch.nn.CrossEntropyLoss()
+        me.group = types.MethodType(fns["group"], me)
+        me.complete = types.MethodType(fns["complete"], me)
+        feats, cls = [], []
+        for d, (n, frac) in enumerate(((ns_, fs), (nt_, ft))):
+            feats.append(torch.relu(seeded.seeded_tensor(f"group.{name}.feat{d}", (n, 1024), idx)))
+            z = seeded.seeded_tensor(f"group.{name}.cls{d}", (n, 2), idx, scale=2.0)
+            nfg = int(round(frac * n))
+            lo, hi = torch.minimum(z[:, 0], z[:, 1]), torch.maximum(z[:, 0], z[:, 1]) + 0.05
+            z = torch.stack([torch.where(torch.arange(n) < nfg, hi, lo), torch.where(torch.arange(n) < nfg, lo, hi)], 1)
+            cls.append(z[torch.randperm(n, generator=torch.Generator().manual_seed(idx * 10 + d))])
+        if name == "daf_exact20":     # exactly 20 foreground RoIs in the source image
+            assert int((torch.softmax(cls[0], -1)[:, 0] >= 0.5).sum()) == 20
+        torch.manual_seed(1000 + idx)
+        with torch.no_grad():
+            val = fns["group_local_da_loss"](me, feats, 0.2, cls)
+        # features are not stored: relu(seeded_tensor(f"group.{name}.feat{d}", (n, 1024), seed)), see tests/helpers.group_case
+        out[name] = {"flavour": flavour, "seed": idx, "rng_seed": 1000 + idx, "cls": cls, "loss": float(val)}
+        print(f"group_local_da_loss {name}: {val:.6f}")
+    torch.save(out, os.path.join(OUT, "group_local_da_loss.pt"))
+
+
 def state_dict_surface(ns):
     """Key -> shape of the reference DA backbones (trunk + DA heads) and instance heads: the checkpoint surface
     (SURVEY.md Appendix C)."""
@@ -161,6 +200,7 @@ def main():
     head_case("instance_alignment_daf", ns.instance.InstanceAlignmentHead_DAF(), fm("x.insd", (24, 1024)))
     backbone_loss_cases(ns)
     focal_case(ns)
+    group_loss_cases(ns)
     total = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print(f"golden fixtures: {total / 1e6:.2f} MB in {OUT}")
 

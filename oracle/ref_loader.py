@@ -89,3 +89,45 @@ def load():
     ns.loss_utils = _load("mmdet_ref.models.losses.utils", "mmdet/models/losses/utils.py")
     ns.focal = _load("mmdet_ref.models.losses.focal_loss", "mmdet/models/losses/focal_loss.py")
     return ns
+
+
+# ----------------------------------------------------------------------------------------------
+# detector methods of the instance-level "group" loss (L5).  The detector modules cannot be imported
+# (they pull in the whole of mmdet) and hard-code device='cuda'; the METHODS are plain torch.  They are
+# compiled in place from the reference source (ast -> exec, nothing copied into this repo) with a `torch`
+# proxy that drops the device= keyword, so the reference's own code runs on the CPU of the build container.
+# ----------------------------------------------------------------------------------------------
+class _TorchCpu:
+    """Forwards to torch; factory functions ignore device= (the reference passes device='cuda')."""
+
+    def __getattr__(self, name):
+        import torch
+        obj = getattr(torch, name)
+        if name in ("zeros", "ones", "tensor", "randn", "rand", "empty", "full"):
+            def wrapped(*a, **k):
+                k.pop("device", None)
+                return obj(*a, **k)
+            return wrapped
+        return obj
+
+
+def load_group_loss(flavour):
+    """flavour: 'daf' (DAFaster_rcnn.py:198-327), 'maf' (MAFaster_rcnn.py:204-299), 'deep' (DAFaster_rcnn_Deep.py:232-329).
+    Returns a dict of the reference's functions {group_local_da_loss, group?, complete?} taking `self` first."""
+    import ast
+    import torch.nn.functional as F
+    if not available():
+        raise RuntimeError(f"{REF} not present")
+    _install_stubs()
+    cl = _load("mmdet_ref.models.utils.cluster", "mmdet/models/utils/cluster.py")
+    cl.torch = _TorchCpu()                       # cluster.py:98 draws its centroids with device='cuda'
+    path = {"daf": "DAFaster_rcnn.py", "maf": "MAFaster_rcnn.py", "deep": "DAFaster_rcnn_Deep.py"}[flavour]
+    src = open(os.path.join(REF, "mmdet/models/detectors", path)).read()
+    tree = ast.parse(src)
+    wanted = {"group_local_da_loss", "group", "complete"}
+    fns = [f for c in tree.body if isinstance(c, ast.ClassDef) for f in c.body
+           if isinstance(f, ast.FunctionDef) and f.name in wanted]
+    mod = ast.Module(body=fns, type_ignores=[])
+    ns = {"torch": _TorchCpu(), "F": F, "cluster": cl.cluster}
+    exec(compile(mod, os.path.join(REF, "mmdet/models/detectors", path), "exec"), ns)
+    return {f.name: ns[f.name] for f in fns}

@@ -44,3 +44,16 @@ def check_summary(grad, summ, tol):
     e1 = float((g[summ["idx"]] - ref).abs().max()) / scale
     e2 = abs(float(g.norm()) - summ["norm"]) / max(summ["norm"], 1e-30)
     return max(e1, e2)
+
+
+def group_case(rec, name):
+    """Inputs of one golden case of group_local_da_loss.pt: features are regenerated from their seeds."""
+    feats = [torch.relu(seeded.seeded_tensor(f"group.{name}.feat{d}", (rec["cls"][d].shape[0], 1024), rec["seed"])) for d in (0, 1)]
+    return feats, rec["cls"]
+
+
+def group_heads(rec, name):
+    cls_head = da_heads.InstanceAlignmentHead_DAF if rec["flavour"] == "deep" else da_heads.InstanceAlignmentHead
+    fore = seeded.fill_state_(cls_head().float().eval(), rec["seed"], prefix=f"group.{name}.fore.")
+    back = seeded.fill_state_(cls_head().float().eval(), rec["seed"], prefix=f"group.{name}.back.")
+    return fore, back

@@ -549,3 +549,23 @@ def test_detectors_forward_train_losses_dict(det, bb, keys):
     for n, p in model.named_parameters():
         if id(p) in unused:
             assert p.grad is None, n
+
+
+# ---------------------------------------------------------------------------- L5 group_local_da_loss
+@pytest.mark.parametrize("engine,tol", [("simt_f32", 2e-5), ("umma_bf16x3", 3e-4), ("umma_bf16", 3e-2)])
+def test_group_local_da_loss_matches_reference_methods(golden, engine, tol):
+    """da_losses.group_local_da_loss against the values returned by the reference's own detector methods
+    (DAFaster_rcnn.py / MAFaster_rcnn.py / DAFaster_rcnn_Deep.py, run on CPU by oracle/make_golden.group_loss_cases)."""
+    from helpers import group_case, group_heads
+    uda.set_engine(engine)
+    g = golden("group_local_da_loss.pt")
+    for name, rec in g.items():
+        feats, cls = group_case(rec, name)
+        fore, back = group_heads(rec, name)
+        fore, back = fore.to(DEV), back.to(DEV)
+        torch.manual_seed(rec["rng_seed"])          # centroid draws: the reference's order, from the global CPU generator
+        draw = lambda dim, dev: torch.stack([torch.randn([dim]) for _ in range(10)], 0).to(dev)
+        val = da_losses.group_local_da_loss([f.to(DEV) for f in feats], [c.to(DEV) for c in cls], fore, back, rec["flavour"],
+                                            draw_centroids=draw)
+        assert val.dim() == 0 and not val.requires_grad
+        assert abs(float(val) - rec["loss"]) <= tol * max(1.0, abs(rec["loss"])), (name, engine, float(val), rec["loss"])

@@ -188,3 +188,16 @@ def test_product_package_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+
+
+def test_group_local_da_loss_oracle_matches_reference_methods(golden):
+    """L5: the restatement against the values the reference's own methods returned (oracle/make_golden.group_loss_cases)."""
+    from helpers import group_case, group_heads
+    g = golden("group_local_da_loss.pt")
+    assert {r["flavour"] for r in g.values()} == {"daf", "maf", "deep"}
+    for name, rec in g.items():
+        feats, cls = group_case(rec, name)
+        fore, back = group_heads(rec, name)
+        torch.manual_seed(rec["rng_seed"])        # the centroid draws of the DAF flavour come from the global RNG
+        val = da_oracle.group_local_da_loss(feats, cls, fore.state_dict(), back.state_dict(), rec["flavour"])
+        assert abs(float(val) - rec["loss"]) <= 2e-6 * max(1.0, abs(rec["loss"])), (name, float(val), rec["loss"])

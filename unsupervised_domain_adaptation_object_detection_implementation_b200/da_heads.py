@@ -354,6 +354,16 @@ class NonLocalBlock(_HeadBase):
         skip = x if grl == 1.0 else F_.gradient_scalar(x, grl)
         return mask + skip
 
+    def forward_single_tokens(self, x, grl=1.0):
+        """Every row of x [T,C] as its own one-token sequence (the reference calls the block with [1,C] inputs from the
+        per-RoI loops of group_local_da_loss, DAFaster_rcnn.py:311-313): the softmax over one score is 1, so
+        y = x + W_mask W_g x and the phi / theta projections drop out."""
+        T, C = x.shape
+        g = F_.dense_layer(x.view(T, 1, 1, C), self.conv_g.weight, grl=grl)
+        mask = F_.dense_layer(g, self.conv_mask.weight).view(T, C)
+        skip = x if grl == 1.0 else F_.gradient_scalar(x, grl)
+        return mask + skip
+
     def forward(self, x):
         b, c, h, w = x.shape
         a = F_.to_nhwc(x, F_.act_dtype())
@@ -408,10 +418,11 @@ class InstanceAlignmentHead(_HeadBase):
     def unused_parameters(self):
         return list(self.bn1.parameters()) + list(self.bn2.parameters())
 
-    def forward_logits(self, x):
+    def forward_logits(self, x, single_token=False):
+        """single_token: treat every row as a separate [1,1024] call of the reference head (no attention across rows)."""
         k = x.shape[0]
         a = F_.cast(x.contiguous(), F_.act_dtype())
-        t = self.nlb.forward_tokens(a, grl=self.grl.weight)
+        t = (self.nlb.forward_single_tokens if single_token else self.nlb.forward_tokens)(a, grl=self.grl.weight)
         t = self._layer(t.view(k, 1, 1, -1), self.fc1, relu=True, drop=True)
         t = self._layer(t, self.fc2, relu=True, drop=True)
         z = self._layer(t, self.fc3, relu=False, drop=False, engine=_tiny_engine(), out_dtype=torch.float32)

@@ -4,6 +4,7 @@
   patch_loss              L2  mmdet/models/backbones/resnet_da_cbam.py:971-979
   image_ce_loss           L3  resnet_da_cbam.py:966-968 (raw logits), resnet_da.py:846-848 (on sigmoid)
   instance_ce_loss        L4  mmdet/models/detectors/DAFaster_rcnn_Orig.py:177-188
+  group_local_da_loss     L5  DAFaster_rcnn.py:198-327, MAFaster_rcnn.py:204-299, DAFaster_rcnn_Deep.py:232-329
   FocalLoss               L6  mmdet/models/losses/focal_loss.py:106-182
   consistency_loss        L7  DAFaster_rcnn_Orig.py:161-175
 """
@@ -37,6 +38,58 @@ def consistency_loss(imgs_feat, ins_preds, ins_labels):
     """L7.  ins_preds are the sigmoid outputs of the instance head (sigmoid is applied again
     inside, as in the reference)."""
     return F_.consistency_loss(imgs_feat, ins_preds, ins_labels)
+
+
+def _draw_centroids(dim, device):
+    """cluster.py:95-98: ten separate randn([dim]) draws (the reference draws them on the GPU)."""
+    return torch.stack([torch.randn([dim], device=device) for _ in range(10)], 0)
+
+
+@torch.no_grad()
+def group_local_da_loss(bbox_feats, bbox_cls, head_fore, head_back, flavour="daf", k=20, draw_centroids=None):
+    """L5, value-faithful to what the reference code computes (each point is spelled out with file:line in
+    oracle/da_oracle.group_local_da_loss and pinned to the reference's own methods by the golden vectors):
+    fg/bg split by softmax(cls)[0] >= 0.5; DAF: groups of more than k=20 RoIs are replaced by the k-means object's
+    centroids, which the reference never updates (= 10 random normal vectors, `draw_centroids(dim, device)`), smaller
+    groups are padded with their top-scoring member; the source group is used alone when non-empty, else the target
+    group (the `!=0 & ... !=0` test is always False); the InstanceAlignmentHead sees every RoI as a one-token sequence
+    (DAF/MAF), the FC-only head the whole batch (Deep); FocalLoss (DAF) or CrossEntropy (MAF/Deep) on the sigmoid
+    outputs; no gradient (the reference returns .item()).  Returns a 0-dim fp32 tensor instead of a Python float (one
+    sync per group for the data-dependent shapes instead of one per RoI).  Heads in train mode apply dropout, as there."""
+    if flavour not in ("daf", "maf", "deep"):
+        raise ValueError("flavour must be 'daf', 'maf' or 'deep'")
+    draw = draw_centroids or _draw_centroids
+    dev = bbox_feats[0].device
+    groups = {}
+    for d in (0, 1):                                   # source, then target: the order of the reference's RNG draws
+        p = torch.softmax(bbox_cls[d].float(), dim=-1)
+        fg = p[:, 0] >= 0.5
+        for name, m, score in (("fg", fg, p[:, 0]), ("bg", ~fg, p[:, 1])):
+            f = bbox_feats[d][m]
+            n = f.shape[0]
+            if n and flavour == "daf":
+                if n > k:
+                    f = draw(f.shape[1], dev).to(f.dtype)
+                elif n < k:
+                    top = torch.argmax(torch.softmax(score[m], dim=-1), dim=0)
+                    f = torch.cat([f, f[top].unsqueeze(0).expand(k - n, -1)], 0)
+            groups[(name, d)] = f
+    total = torch.zeros((), dtype=torch.float32, device=dev)
+    for name, head in (("fg", head_fore), ("bg", head_back)):
+        src, tar = groups[(name, 0)], groups[(name, 1)]
+        if src.shape[0]:
+            f, label = src, 0
+        elif tar.shape[0]:
+            f, label = tar, 1
+        else:
+            continue
+        z = head.forward_logits(f.contiguous()) if flavour == "deep" else head.forward_logits(f.contiguous(), single_token=True)
+        labels = torch.full((f.shape[0],), label, dtype=torch.long, device=dev)
+        if flavour == "daf":
+            total = total + F_.sigmoid_focal_loss2(torch.sigmoid(z), labels, 2.0, 0.25)
+        else:
+            total = total + F_.ce2(z, labels, True)[0]
+    return total.detach()
 
 
 class FocalLoss(nn.Module):

@@ -108,6 +108,7 @@ class DAFasterRCNN_Org(_DATwoStage):
 
 class _ForeBack(_DATwoStage):
     head_cls = da_heads.InstanceAlignmentHead
+    group_flavour = "maf"
     use_focal = False
     local_lamda = 0.1
     has_patch = True
@@ -122,21 +123,8 @@ class _ForeBack(_DATwoStage):
         self.local_da_back._init_weights()
 
     def group_local_da_loss(self, bbox_feats, lamda, bbox_cls):
-        feats = torch.cat(list(bbox_feats), 0)
-        cls = torch.cat(list(bbox_cls), 0).float()
-        labels = torch.cat([torch.full((len(f),), i, dtype=torch.long, device=f.device) for i, f in enumerate(bbox_feats)])
-        fg = torch.softmax(cls, dim=-1)[:, 0] >= 0.5
-        total = feats.new_zeros((), dtype=torch.float32)
-        for mask, head in ((fg, self.local_da_fore), (~fg, self.local_da_back)):
-            idx = torch.nonzero(mask, as_tuple=False).squeeze(1)
-            if idx.numel() == 0:
-                continue
-            pred = head(feats[idx])
-            if self.use_focal:
-                total = total + self.criterion_fl(pred, labels[idx])
-            else:
-                total = total + da_losses.F_.ce2(pred, labels[idx], False)[0]
-        return total.detach() if self.detach_instance_loss else total
+        """L5 as the reference computes it (da_losses.group_local_da_loss): detached, source group first."""
+        return da_losses.group_local_da_loss(bbox_feats, bbox_cls, self.local_da_fore, self.local_da_back, self.group_flavour)
 
     def forward_train(self, img, img_metas, gt_bboxes, gt_labels, gt_da=None, gt_bboxes_ignore=None, gt_masks=None,
                       proposals=None, **kwargs):
@@ -156,7 +144,7 @@ class _ForeBack(_DATwoStage):
 
 @DETECTORS.register_module()
 class DAFasterRCNN(_ForeBack):
-    use_focal, local_lamda = True, 0.2
+    use_focal, local_lamda, group_flavour = True, 0.2, "daf"
 
 
 @DETECTORS.register_module()
@@ -167,3 +155,5 @@ class MAFasterRCNN(_ForeBack):
 @DETECTORS.register_module()
 class DAFasterRCNN_Deep(_ForeBack):
     head_cls = da_heads.InstanceAlignmentHead_DAF
+    group_flavour = "deep"
+    local_lamda = 0.2      # DAFaster_rcnn_Deep.py:177
