@@ -57,6 +57,9 @@ def parse_args():
     ap.add_argument("--peer-ctas", type=int, default=0, help="grid cap of the peer kernel (0 = two 128-thread CTAs per SM)")
     ap.add_argument("--no-fused-wgrad-sgd", action="store_true", help="N=1: separate weight-gradient and SGD kernels for FC1")
     ap.add_argument("--peer-transport", default="copy", choices=["copy", "stores"])
+    ap.add_argument("--peer-publish", default="deferred", choices=["deferred", "in-step"],
+                    help="deferred: the pushes of the refreshed bf16 slices are enqueued after the step and run under the next step's "
+                         "RoIAlign forward (the next FC1 forward waits for them on the device)")
     ap.add_argument("--peer-reserve-sms", type=int, default=0, help="SMs the persistent kernels leave free while the peer kernel runs")
     return ap.parse_args()
 
@@ -157,7 +160,8 @@ def run_ours(args):
         if True:
             big = [p for p in params if p.numel() >= (1 << 24)]
             try:
-                peer_opt = peer.PeerShardedSGD(big, max_ctas=args.peer_ctas, reserve_sms=args.peer_reserve_sms, transport=args.peer_transport, **sgd)
+                peer_opt = peer.PeerShardedSGD(big, max_ctas=args.peer_ctas, reserve_sms=args.peer_reserve_sms, transport=args.peer_transport,
+                                                deferred_publish=args.peer_publish == "deferred", **sgd)
                 params = [p for p in params if all(p is not q for q in big)]
                 how = ("copy engines push gradient slices to their owner and the refreshed bf16 slices to every rank, all-local update kernel"
                        if args.peer_transport == "copy" else "one kernel with SM-issued P2P loads/stores")
@@ -214,6 +218,8 @@ def run_ours(args):
             with torch.cuda.stream(side):
                 for i in range(3):
                     eager_step(*resident[i % 2])
+                    if peer_opt is not None:
+                        peer_opt.publish()
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             graphs, graph_losses, pool = [], [], None
@@ -234,9 +240,13 @@ def run_ours(args):
     def run_slot(slot):
         """One step on input set `slot` (resident[slot] holds the inputs)."""
         if graphs is None:
-            return eager_step(*resident[slot])
-        graphs[slot].replay()
-        return graph_losses[slot]
+            out = eager_step(*resident[slot])
+        else:
+            graphs[slot].replay()
+            out = graph_losses[slot]
+        if peer_opt is not None:
+            peer_opt.publish()        # deferred pushes of the refreshed FC1 slices (no-op otherwise); part of the timed step
+        return out
 
     def step_resident(i):
         return run_slot(i % 2)

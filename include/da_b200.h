@@ -141,7 +141,13 @@ int da_sgd_step_peer(const da_peer_sgd_args* args, float lr, float momentum, flo
 /* Stream-ordered copy between any two device pointers this process can address (local or da_peer_open'ed): runs on a
  * copy engine, no SM involved. */
 int da_peer_copy(void* dst, const void* src, size_t bytes, da_stream_t stream);
-int da_peer_publish_done(const da_peer_sgd_args* args, da_stream_t stream);
+int da_peer_publish_done(const da_peer_sgd_args* args, da_stream_t stream);   /* = da_peer_signal_done + da_peer_wait_done */
+/* The two halves, for a DEFERRED publish: the pushes of step t and da_peer_signal_done may be enqueued after the step (on a
+ * side stream, outside a captured graph) and run under the beginning of step t+1; da_peer_wait_done then goes in front of
+ * the first kernel of step t+1 that reads the operand copy.  local_state[3] counts this rank's completed publishes; the
+ * update kernel of step t+1 waits for publish t before it rewrites the slice the pushes read (error 3 on time-out). */
+int da_peer_signal_done(const da_peer_sgd_args* args, da_stream_t stream);
+int da_peer_wait_done(const da_peer_sgd_args* args, da_stream_t stream);
 int da_peer_alloc(size_t bytes, void** out);
 int da_peer_free(void* p);
 int da_peer_export(const void* p, unsigned char* handle64);

@@ -64,40 +64,47 @@ def main():
     torch.cuda.synchronize()
     assert torch.equal(lin_a.weight.data.view(-1), w_ref), "gathered master differs"
 
-    # ---- B: CUDA-graph replay of the peer kernel (device-resident epochs) ------------------------------------
-    p = torch.nn.Parameter(torch.randn(1 << 22, device=dev, generator=torch.Generator(device=dev).manual_seed(5)))
-    q = p.detach().clone()
-    qbuf, qsh = torch.zeros_like(q), torch.empty_like(q, dtype=torch.bfloat16)
-    popt2 = peer.PeerShardedSGD([p], lr=LR, momentum=MU, weight_decay=WD, transport=transport)
-    mw = F_.MANAGED_WGRAD[id(p)]
-    gbuf, wgrad_done, done = mw.grad, mw.after_wgrad, mw.layer_done
-    src = torch.randn(1 << 22, device=dev, generator=g)
+    # ---- B: CUDA-graph replay of the peer kernel (device-resident epochs), publish inside the step and deferred ----
+    for deferred in (False, True):
+        p = torch.nn.Parameter(torch.randn(1 << 22, device=dev, generator=torch.Generator(device=dev).manual_seed(5)))
+        q = p.detach().clone()
+        qbuf, qsh = torch.zeros_like(q), torch.empty_like(q, dtype=torch.bfloat16)
+        popt2 = peer.PeerShardedSGD([p], lr=LR, momentum=MU, weight_decay=WD, transport=transport, deferred_publish=deferred)
+        mw = F_.MANAGED_WGRAD[id(p)]
+        gbuf, wgrad_done, done = mw.grad, mw.after_wgrad, mw.layer_done
+        src = torch.randn(1 << 22, device=dev, generator=g)
+        probe = torch.zeros(8, device=dev)
 
-    def one_step():
-        gbuf.copy_(src)
-        wgrad_done()
-        done()
-        popt2.join()
+        def one_step():
+            mw.before_forward()                       # what functional.dense_layer does in front of the layer's forward
+            probe.copy_(F_.bf16_shadow(p).view(-1)[:8].float())    # a "forward" that reads the operand copy
+            gbuf.copy_(src)
+            wgrad_done()
+            done()
+            popt2.join()
 
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        one_step()
-    torch.cuda.current_stream().wait_stream(side)
-    torch.cuda.synchronize()
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
-        one_step()
-    for _ in range(3):
-        graph.replay()
-    torch.cuda.synchronize()
-    popt2.check_errors()
-    gm = rank_order_mean(src)
-    for s in range(4):
-        check(lib.da_sgd_step(F_._ptr(q), F_._ptr(gm), F_._ptr(qbuf), q.numel(), LR, MU, WD, int(s == 0), F_._ptr(qsh), None), "sgd")
-    torch.cuda.synchronize()
-    sh = F_.bf16_shadow(p).view(-1)
-    assert torch.equal(sh.view(torch.int16), qsh.view(torch.int16)), "graph replay: operand copy differs"
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            one_step()
+            popt2.publish()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            one_step()
+        for _ in range(3):
+            graph.replay()
+            popt2.publish()
+        torch.cuda.synchronize()
+        popt2.check_errors()
+        gm = rank_order_mean(src)
+        for s in range(4):
+            check(lib.da_sgd_step(F_._ptr(q), F_._ptr(gm), F_._ptr(qbuf), q.numel(), LR, MU, WD, int(s == 0), F_._ptr(qsh), None), "sgd")
+        torch.cuda.synchronize()
+        sh = F_.bf16_shadow(p).view(-1)
+        assert torch.equal(sh.view(torch.int16), qsh.view(torch.int16)), f"graph replay (deferred={deferred}): operand copy differs"
+        del F_.MANAGED_WGRAD[id(p)]
 
     # ---- C: timing at the FC1 size ----------------------------------------------------------------------------
     if "--time" in sys.argv:

@@ -76,6 +76,8 @@ SIGNATURES = {
     "da_sgd_step_peer": (I, [P, F, F, F, I, I, I, P]),
     "da_peer_copy": (I, [P, P, S, P]),
     "da_peer_publish_done": (I, [P, P]),
+    "da_peer_signal_done": (I, [P, P]),
+    "da_peer_wait_done": (I, [P, P]),
     "da_peer_alloc": (I, [S, P]),
     "da_peer_free": (I, [P]),
     "da_peer_export": (I, [P, P]),

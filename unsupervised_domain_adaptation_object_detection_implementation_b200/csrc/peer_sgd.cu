@@ -89,6 +89,11 @@ sgd_step_peer_kernel(const da_peer_sgd_args a, float lr, float mu, float wd, int
   if (threadIdx.x < world && threadIdx.x != a.rank) {
     if (!spin_until(a.flags[a.rank] + threadIdx.x, epoch)) atomicExch(a.local_state + 2, 1);
   }
+  // caller-published mode: this rank's previous bf16 slice must have left (the copies read what this kernel rewrites);
+  // local_state[3] counts the publishes completed on this rank (peer_signal_done_kernel, behind the copies in stream order)
+  if (!signal_done && world > 1 && threadIdx.x == world) {
+    if (!spin_until(a.local_state + 3, epoch - 1)) atomicExch(a.local_state + 2, 3);
+  }
   __syncthreads();
 
   // ---- own slice [lo, hi): multiples of 1024 elements, the last rank takes the remainder
@@ -199,10 +204,17 @@ sgd_step_peer_kernel(const da_peer_sgd_args a, float lr, float mu, float wd, int
   }
 }
 
-// done[rank] := epoch of the update in front of this kernel, on every rank (the caller's copies are in front of it too)
+// done[rank] := number of publishes this rank has completed, on every rank (the caller's copies are in front of this kernel
+// in stream order).  The count is kept in local_state[3], NOT derived from the update epoch: a deferred publish may run
+// while the next step is already under way.
 __global__ void peer_signal_done_kernel(const da_peer_sgd_args a) {
-  const int epoch = a.local_state[0];
+  const int epoch = a.local_state[3] + 1;
   if (threadIdx.x < a.world) st_release_sys(a.flags[threadIdx.x] + DA_MAX_PEERS + a.rank, epoch);
+  __syncwarp();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.local_state + 3), "r"(epoch) : "memory");
+  }
 }
 
 __global__ void peer_wait_kernel(const int* flags_local, int* local_state, int world) {
@@ -270,6 +282,24 @@ extern "C" int da_peer_copy(void* dst, const void* src, size_t bytes, da_stream_
   if (bytes == 0) return DA_OK;
   DA_REQUIRE(dst && src, DA_ERR_INVALID_ARG, "peer_copy: null pointer");
   DA_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+  return DA_OK;
+}
+
+extern "C" int da_peer_signal_done(const da_peer_sgd_args* a, da_stream_t stream) {
+  DA_REQUIRE(a && a->local_state && a->world >= 1 && a->world <= DA_MAX_PEERS && a->rank >= 0 && a->rank < a->world,
+             DA_ERR_INVALID_ARG, "peer_signal_done: bad args");
+  preload_peer_kernels();
+  peer_signal_done_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(*a);
+  DA_LAUNCH_CHECK();
+  return DA_OK;
+}
+
+extern "C" int da_peer_wait_done(const da_peer_sgd_args* a, da_stream_t stream) {
+  DA_REQUIRE(a && a->local_state && a->world >= 1 && a->world <= DA_MAX_PEERS && a->rank >= 0 && a->rank < a->world,
+             DA_ERR_INVALID_ARG, "peer_wait_done: bad args");
+  preload_peer_kernels();
+  peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a->flags[a->rank], a->local_state, a->world);
+  DA_LAUNCH_CHECK();
   return DA_OK;
 }
 

@@ -425,6 +425,9 @@ class ManagedWeight:
     grad = None        # flat fp32 buffer for the weight gradient (None with `fuse`)
     fuse = None        # callable -> _lib.SgdFuse
 
+    def before_forward(self):  # in front of the layer's forward kernel (it reads the operand copy)
+        pass
+
     def after_wgrad(self):     # the weight-gradient kernel is enqueued
         pass
 
@@ -550,6 +553,7 @@ def dense_layer(x, w, scale=None, shift=None, stride=1, pad=0, relu=False, drop_
         if shadow is None:
             raise RuntimeError("a peer-managed weight needs the bf16 tensor-core engine (its operand copy is what the peers refresh)")
         w = w.detach()
+        managed.before_forward()
     return DenseLayerFunction.apply(x, w, scale, shift, stride, pad, relu, drop_p, seed, engine, grl, out_dtype, shadow, managed)
 
 

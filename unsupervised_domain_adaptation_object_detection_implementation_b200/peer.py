@@ -79,7 +79,7 @@ def make_args(w, momentum_shard, grads, shadows, masters, flags, local_state, n,
 
 class _Managed:
     __slots__ = ("param", "n", "grad", "shadow", "flags", "state", "momentum", "args", "calls", "blocks", "pending", "ptrs",
-                 "staging", "lo", "hi", "per")
+                 "staging", "lo", "hi", "per", "unpublished")
 
 
 class PeerShardedSGD:
@@ -97,7 +97,7 @@ class PeerShardedSGD:
     bf16 slice to every rank.  transport="stores": one kernel does everything with SM-issued P2P loads and stores."""
 
     def __init__(self, params, lr=1e-3, momentum=0.9, weight_decay=0.0, max_ctas=0, reserve_sms=0, share_master=False,
-                 transport="copy", group=None):
+                 transport="copy", deferred_publish=False, group=None):
         if transport not in ("copy", "stores"):
             raise ValueError("transport must be 'copy' or 'stores'")
         if dist.is_available() and dist.is_initialized():
@@ -109,6 +109,11 @@ class PeerShardedSGD:
         self.lr, self.momentum, self.weight_decay = float(lr), float(momentum), float(weight_decay)
         self.max_ctas, self.share_master, self.group = int(max_ctas), bool(share_master), group
         self.reserve_sms, self.transport = int(reserve_sms), transport
+        # deferred publish (copy transport): the pushes of the refreshed bf16 slices are NOT part of the step; the caller
+        # enqueues them with publish() right after the step (outside a captured graph) and they run under the beginning of
+        # the next step, whose first use of the operand copy is preceded by the wait for every peer's pushes
+        # (ManagedWeight.before_forward).  Per step: forward/backward -> join() -> publish().
+        self.deferred = bool(deferred_publish) and transport == "copy"
         self.items = []
         params = [p for p in params if p.requires_grad]
         if not params:
@@ -179,6 +184,8 @@ class PeerShardedSGD:
             mw.grad = m.grad
             mw.after_wgrad = (lambda m=m: self._after_wgrad(m))
             mw.layer_done = (lambda m=m: self._layer_done(m))
+            if self.deferred and self.world > 1:
+                mw.before_forward = (lambda m=m: self._before_forward(m))
             F_.MANAGED_WGRAD[id(m.param)] = mw
         if self.world > 1:
             dist.barrier(group=group)                         # every rank has mapped every block before the first step
@@ -210,13 +217,12 @@ class PeerShardedSGD:
         if self.transport == "copy":
             check(lib.da_sgd_step_peer(ctypes.byref(m.args), self.lr, self.momentum, self.weight_decay, first, self.max_ctas,
                                        _lib.DA_PEER_PUBLISH_BY_CALLER, st), "sgd_step_peer")
-            for k in range(1, self.world):
-                r = (self.rank + k) % self.world
-                check(lib.da_peer_copy(m.ptrs[r][1] + 2 * m.lo, m.shadow.data_ptr() + 2 * m.lo, 2 * (m.hi - m.lo), st), "peer_copy")
-                if self.share_master:
-                    check(lib.da_peer_copy(m.ptrs[r][3] + 4 * m.lo, m.param.data_ptr() + 4 * m.lo, 4 * (m.hi - m.lo), st), "peer_copy")
-            if self.world > 1:
-                check(lib.da_peer_publish_done(ctypes.byref(m.args), st), "peer_publish_done")
+            if self.deferred and self.world > 1:
+                m.unpublished = True
+            else:
+                self._push_slices(m, st)
+                if self.world > 1:
+                    check(lib.da_peer_publish_done(ctypes.byref(m.args), st), "peer_publish_done")
         else:
             check(lib.da_sgd_step_peer(ctypes.byref(m.args), self.lr, self.momentum, self.weight_decay, first, self.max_ctas,
                                        _lib.DA_PEER_PUBLISH_STORES, st), "sgd_step_peer")
@@ -224,6 +230,30 @@ class PeerShardedSGD:
         if not self._limited and self.reserve_sms > 0:
             F_.set_sm_limit(self._sms - self.reserve_sms)    # persistent kernels leave room for the peer kernel
             self._limited = True
+
+    def _push_slices(self, m, st):
+        for k in range(1, self.world):
+            r = (self.rank + k) % self.world
+            check(lib.da_peer_copy(m.ptrs[r][1] + 2 * m.lo, m.shadow.data_ptr() + 2 * m.lo, 2 * (m.hi - m.lo), st), "peer_copy")
+            if self.share_master:
+                check(lib.da_peer_copy(m.ptrs[r][3] + 4 * m.lo, m.param.data_ptr() + 4 * m.lo, 4 * (m.hi - m.lo), st), "peer_copy")
+
+    def _before_forward(self, m):
+        """In front of the layer's forward: every peer's pushes of the previous step have landed in this rank's copy."""
+        check(lib.da_peer_wait_done(ctypes.byref(m.args), F_._stream()), "peer_wait_done")
+
+    def publish(self):
+        """Deferred publish: enqueue the pushes of this step's refreshed slices + the done signal on the side stream, ordered
+        after everything enqueued on the current stream so far (call it right after the step / after replaying its graph;
+        not capturable on purpose: it must not be joined by the step)."""
+        if not (self.deferred and self.world > 1 and self.items):
+            return
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("PeerShardedSGD.publish() belongs outside the captured step")
+        st = self._comm_after_current()
+        for m in self.items:
+            self._push_slices(m, st)
+            check(lib.da_peer_signal_done(ctypes.byref(m.args), st), "peer_signal_done")
 
     def join(self):
         """The step's peer kernels are ordered before whatever the current stream does next."""
@@ -241,7 +271,8 @@ class PeerShardedSGD:
         for m in self.items:
             err = int(m.state[2].item())
             if err:
-                raise RuntimeError(f"PeerShardedSGD: barrier-{'in' if err == 1 else 'out'} timed out on rank {self.rank}")
+                what = {1: "barrier-in", 2: "barrier-out", 3: "wait for the previous publish"}.get(err, str(err))
+                raise RuntimeError(f"PeerShardedSGD: {what} timed out on rank {self.rank}")
 
     @torch.no_grad()
     def gather_master(self):
