@@ -61,3 +61,17 @@ def test_flat_grad_allreduce_world2_gloo(tmp_path):
     expect[-n3:] = 0.0                                               # both ranks dropped that gradient
     assert torch.allclose(rec["mine"], expect, atol=1e-6)
     assert rec["tmax"] == 20.0
+
+
+def test_peer_slice_bounds_partition_the_tensor():
+    """Slice ownership of peer.PeerShardedSGD (same rule as the kernel): contiguous, disjoint, complete, multiples of 1024
+    elements (16-byte aligned for fp32 and bf16), identical `per` on every rank."""
+    from unsupervised_domain_adaptation_object_detection_implementation_b200 import peer
+    for n in (1, 1023, 1024, 1025, 8192 + 5, 1024 * 100352, 3 * 1024 * 37 + 13):
+        for world in (1, 2, 3, 4, 5, 8):
+            b = [peer.slice_bounds(n, world, r) for r in range(world)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(x[1] == y[0] for x, y in zip(b, b[1:]))
+            assert len({x[2] for x in b}) == 1 and b[0][2] % 1024 == 0
+            assert all(x[0] % 1024 == 0 or x[0] == n for x in b)
+            assert all(0 <= x[1] - x[0] <= x[2] for x in b)
