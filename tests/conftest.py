@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# tests/test_gpu_peer.py runs up to 8 "virtual ranks" with two streams each on one device; the kernels of different ranks
+# wait for each other, so their streams must not share a hardware queue (default: 8 connections).  Read at CUDA init.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

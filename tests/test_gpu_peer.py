@@ -138,6 +138,69 @@ def test_peer_sgd_copy_engine_transport_virtual_ranks(world, n):
             assert int(flags[r][_lib.DA_MAX_PEERS:_lib.DA_MAX_PEERS + world].min()) == s + 1     # every rank raised done
 
 
+@pytest.mark.parametrize("world,n", [(2, 1024 * 300 + 5), (4, 1024 * 1024), (8, 8 * 1024 * 33 + 9)])
+def test_peer_sgd_deferred_publish_virtual_ranks(world, n):
+    """The deferred publish of peer.PeerShardedSGD: the pushes of step s and da_peer_signal_done run on a SECOND stream per
+    rank, concurrently with the beginning of step s+1, whose first read of the operand copy sits behind da_peer_wait_done;
+    the update kernel of step s+1 waits for the rank's own publish s (local_state[3]).  No host synchronisation between
+    steps; the operand copy every rank sees at the start of each step is snapshotted in stream order and compared bit for bit."""
+    g = torch.Generator(device=DEV).manual_seed(world * 131 + n % 83)
+    w0 = torch.randn(n, device=DEV, generator=g)
+    steps = 4
+    grads_per_step = [[torch.randn(n, device=DEV, generator=g) for _ in range(world)] for _ in range(steps)]
+    exp = _expected(w0, grads_per_step, world)
+    bounds = [peer.slice_bounds(n, world, r) for r in range(world)]
+    per = bounds[0][2]
+    masters = [w0.clone() for _ in range(world)]
+    staging = [torch.zeros(world * per, device=DEV) for _ in range(world)]
+    shadows = [torch.zeros(n, device=DEV, dtype=torch.bfloat16) for _ in range(world)]
+    snaps = [[torch.zeros(n, device=DEV, dtype=torch.bfloat16) for _ in range(steps)] for _ in range(world)]
+    flags = [torch.zeros(_lib.DA_PEER_FLAG_INTS, dtype=torch.int32, device=DEV) for _ in range(world)]
+    states = [torch.zeros(4, dtype=torch.int32, device=DEV) for _ in range(world)]
+    moms = [torch.zeros(max(per, 8), device=DEV) for _ in range(world)]
+    grads = [[grads_per_step[s][r] for s in range(steps)] for r in range(world)]     # one buffer per step: no host sync needed
+    args = [[None] * steps for _ in range(world)]
+    for r in range(world):
+        lo = bounds[r][0]
+        for s in range(steps):
+            gp = [grads[r][s].data_ptr() if q == r else staging[r].data_ptr() + 4 * (q * per - lo) for q in range(world)]
+            sp = [shadows[r].data_ptr() if q == r else 0 for q in range(world)]
+            args[r][s] = peer.make_args(masters[r].data_ptr(), moms[r].data_ptr(), gp, sp, None, [t.data_ptr() for t in flags],
+                                        states[r].data_ptr(), n, world, r)
+    main = [torch.cuda.Stream() for _ in range(world)]
+    side = [torch.cuda.Stream() for _ in range(world)]
+    torch.cuda.synchronize()
+    for s in range(steps):
+        for r in range(world):
+            st = ctypes.c_void_p(main[r].cuda_stream)
+            check(lib.da_peer_wait_done(ctypes.byref(args[r][s]), st), "wait_done")      # peers' pushes of step s-1 have landed
+            with torch.cuda.stream(main[r]):
+                snaps[r][s].copy_(shadows[r])                                            # the "forward" reads the operand copy
+            for q in range(world):                                                       # gradient slices to their owners
+                if q != r:
+                    lo, hi, _ = bounds[q]
+                    check(lib.da_peer_copy(staging[q].data_ptr() + 4 * r * per, grads[r][s].data_ptr() + 4 * lo, 4 * (hi - lo), st), "copy")
+        for r in range(world):
+            st = ctypes.c_void_p(main[r].cuda_stream)
+            check(lib.da_sgd_step_peer(ctypes.byref(args[r][s]), LR, MU, WD, int(s == 0), 4, _lib.DA_PEER_PUBLISH_BY_CALLER, st), "step")
+            ev = torch.cuda.Event()
+            ev.record(main[r])
+            side[r].wait_event(ev)
+            sst = ctypes.c_void_p(side[r].cuda_stream)
+            lo, hi, _ = bounds[r]
+            for q in range(world):
+                if q != r:
+                    check(lib.da_peer_copy(shadows[q].data_ptr() + 2 * lo, shadows[r].data_ptr() + 2 * lo, 2 * (hi - lo), sst), "copy")
+            check(lib.da_peer_signal_done(ctypes.byref(args[r][s]), sst), "signal_done")
+    torch.cuda.synchronize()
+    for r in range(world):
+        assert int(states[r][2]) == 0, f"time-out code {int(states[r][2])}"
+        assert int(states[r][0]) == steps and int(states[r][3]) == steps
+        assert torch.equal(shadows[r].view(torch.int16), exp[-1][1].view(torch.int16))
+        for s in range(1, steps):
+            assert torch.equal(snaps[r][s].view(torch.int16), exp[s - 1][1].view(torch.int16)), f"rank {r} read a stale copy at step {s}"
+
+
 def test_peer_sgd_rejects_bad_arguments():
     t = torch.zeros(1024, device=DEV)
     f = torch.zeros(_lib.DA_PEER_FLAG_INTS, dtype=torch.int32, device=DEV)
