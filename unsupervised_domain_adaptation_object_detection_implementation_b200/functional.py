@@ -412,6 +412,18 @@ def _w_ohwi(w):
 
 # callable(dw) invoked right after a layer's weight-gradient kernel has been enqueued (None = disabled)
 WGRAD_HOOK = None
+# weight gradient of small layers on a side stream, next to the data gradient (see DenseLayerFunction.backward)
+CONCURRENT_SMALL_WGRAD = not os.environ.get("DA_NO_CONCURRENT_WGRAD")
+SMALL_LAYER_FLOPS = 6e9
+_SIDE = {}
+
+
+def _side_stream(dev):
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    st = _SIDE.get(key)
+    if st is None:
+        st = _SIDE[key] = torch.cuda.Stream(device=dev)
+    return st
 # Weights whose gradient never becomes a .grad tensor: id(weight) -> ManagedWeight.  Autograd sees such a weight as a
 # constant; the layer's backward hands the gradient to the optimizer that registered it:
 #   * peer.PeerShardedSGD (N GPUs): the weight-gradient kernel writes `grad`, `after_wgrad` / `layer_done` start the
@@ -506,18 +518,40 @@ class DenseLayerFunction(Function):
         elif managed is None and ctx.needs_input_grad[1]:
             desc_w = _conv_desc(N, H, W_, Cin, Cout, KH, KW, stride, pad, engine, x.dtype, x.dtype)
             dwv = torch.empty((Cout, KH, KW, Cin), dtype=torch.float32, device=dev)
-            check(lib.da_conv_backward_weight(ctypes.byref(desc_w), _ptr(x), _ptr(dz), _ptr(dwv), _ptr(ws), ws.numel(),
-                                              _stream()), "conv_backward_weight")
+            # Small layers (the 1-2 GFLOP GEMMs of the instance head fill less than half of the SMs each and cost a fixed
+            # ~10 us of latency): weight and data gradient only share dz, so the weight gradient goes to a side stream and
+            # the two run next to each other; joined before this function returns.
+            flops = 2.0 * dz.numel() * KH * KW * Cin
+            join = None
+            if (CONCURRENT_SMALL_WGRAD and ctx.needs_input_grad[0] and engine == "umma_bf16" and wdtype == torch.float32
+                    and flops <= SMALL_LAYER_FLOPS):
+                side = _side_stream(dev)
+                fork = torch.cuda.Event()
+                fork.record()
+                side.wait_event(fork)
+                ws_side = workspace(lib.da_conv_workspace_bytes(ctypes.byref(desc_w)), dev, "conv_side")
+                with torch.cuda.stream(side):
+                    check(lib.da_conv_backward_weight(ctypes.byref(desc_w), _ptr(x), _ptr(dz), _ptr(dwv), _ptr(ws_side), ws_side.numel(),
+                                                      _stream()), "conv_backward_weight")
+                    if WGRAD_HOOK is not None:
+                        WGRAD_HOOK(dwv)
+                    join = torch.cuda.Event()
+                    join.record()
+            else:
+                check(lib.da_conv_backward_weight(ctypes.byref(desc_w), _ptr(x), _ptr(dz), _ptr(dwv), _ptr(ws), ws.numel(),
+                                                  _stream()), "conv_backward_weight")
             dw = dwv.view(wshape) if len(wshape) == 2 else dwv.permute(0, 3, 1, 2)
             if wdtype != torch.float32:
                 dw = dw.to(wdtype)
-            elif WGRAD_HOOK is not None:
+            elif WGRAD_HOOK is not None and join is None:
                 WGRAD_HOOK(dwv)
         if ctx.needs_input_grad[0]:
             desc_d = _conv_desc(N, H, W_, Cin, Cout, KH, KW, stride, pad, engine, x.dtype, x.dtype)
             dx = torch.empty_like(x)
             check(lib.da_conv_backward_data(ctypes.byref(desc_d), _ptr(dz), _ptr(wv), float(grl), _ptr(dx), _ptr(ws),
                                             ws.numel(), _stream()), "conv_backward_data")
+        if managed is None and ctx.needs_input_grad[1] and join is not None:
+            torch.cuda.current_stream().wait_event(join)
         if managed is not None:
             if managed.fuse is not None:     # data gradient first: the fused kernel rewrites the operand copy it read
                 desc_w = _conv_desc(N, H, W_, Cin, Cout, KH, KW, stride, pad, engine, x.dtype, x.dtype)
