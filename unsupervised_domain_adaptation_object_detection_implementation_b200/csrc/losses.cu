@@ -311,6 +311,58 @@ __global__ void pixel_head_bwd_kernel(const T* __restrict__ x, int64_t M, int K,
   }
 }
 
+// bf16 x and dx, K in {64 .. 2048} with 256 % (K/8) == 0: 16-byte accesses, a thread owns 8 consecutive channels and every
+// SUB-th row; partial dw sums meet in shared memory (the scalar kernel: 25 us for [16384, 512]).
+__global__ void __launch_bounds__(256)
+pixel_head_bwd_vec8_kernel(const __nv_bfloat16* __restrict__ x, int64_t M, int K, const float* __restrict__ w,
+                           const float* __restrict__ dlogits, const float* __restrict__ post_relu,
+                           __nv_bfloat16* __restrict__ dx, float* __restrict__ partial, int rows_per_block) {
+  extern __shared__ float ph_red[];   // [SUB][K] when SUB > 1
+  const int64_t m0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t m1 = (m0 + rows_per_block < M) ? m0 + rows_per_block : M;
+  const int G = K >> 3, SUB = 256 / G;
+  const int cg = threadIdx.x % G, sub = threadIdx.x / G, k0 = cg << 3;
+  float wk[8], acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { wk[j] = w[k0 + j]; acc[j] = 0.f; }
+  for (int64_t m = m0 + sub; m < m1; m += SUB) {
+    float dl = dlogits[m];
+    if (post_relu && !(post_relu[m] > 0.f)) dl = 0.f;
+    const uint4 xv = *reinterpret_cast<const uint4*>(x + (size_t)m * K + k0);
+    const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(&xv);
+    uint4 ov;
+    __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(&ov);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[j] = fmaf(dl, __bfloat162float(xp[j]), acc[j]);
+      op[j] = __float2bfloat16_rn(dl * wk[j]);
+    }
+    if (dx) *reinterpret_cast<uint4*>(dx + (size_t)m * K + k0) = ov;
+  }
+  if (SUB > 1) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ph_red[(size_t)sub * K + k0 + j] = acc[j];
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += 256) {
+      float a = 0.f;
+      for (int q = 0; q < SUB; ++q) a += ph_red[(size_t)q * K + k];
+      partial[(size_t)blockIdx.x * K + k] = a;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) partial[(size_t)blockIdx.x * K + k0 + j] = acc[j];
+  }
+  if (threadIdx.x == 0) {
+    float db = 0.f;
+    for (int64_t m = m0; m < m1; ++m) {
+      float dl = dlogits[m];
+      if (post_relu && !(post_relu[m] > 0.f)) dl = 0.f;
+      db += dl;
+    }
+    partial[(size_t)gridDim.x * K + blockIdx.x] = db;
+  }
+}
+
 __global__ void pixel_head_bwd_final_kernel(const float* __restrict__ partial, int nb, int K,
                                             float* __restrict__ dw, float* __restrict__ dbias) {
   // block (32 columns x 32 row lanes); the last block column (k == K) reduces the bias partials
@@ -546,7 +598,12 @@ extern "C" int da_pixel_head_backward(const void* x, int x_dtype, int64_t M, int
   if (x_dtype == DA_F32 && dx_dtype == DA_F32) DA_PH_BWD(float, float);
   else if (x_dtype == DA_F32 && dx_dtype == DA_BF16) DA_PH_BWD(float, __nv_bfloat16);
   else if (x_dtype == DA_BF16 && dx_dtype == DA_F32) DA_PH_BWD(__nv_bfloat16, float);
-  else if (x_dtype == DA_BF16 && dx_dtype == DA_BF16) DA_PH_BWD(__nv_bfloat16, __nv_bfloat16);
+  else if (x_dtype == DA_BF16 && dx_dtype == DA_BF16 && (K & 7) == 0 && (K >> 3) <= 256 && 256 % (K >> 3) == 0 &&
+           ((((uintptr_t)x) | ((uintptr_t)dx)) & 15) == 0) {
+    const int sub = 256 / (K >> 3);
+    pixel_head_bwd_vec8_kernel<<<nb, 256, sub > 1 ? (size_t)sub * K * sizeof(float) : 0, st>>>(
+        (const __nv_bfloat16*)x, M, K, w, dlogits, post_relu_logits, (__nv_bfloat16*)dx, partial, rpb);
+  } else if (x_dtype == DA_BF16 && dx_dtype == DA_BF16) DA_PH_BWD(__nv_bfloat16, __nv_bfloat16);
   else DA_REQUIRE(false, DA_ERR_INVALID_ARG, "pixel_head_backward: bad dtype");
 #undef DA_PH_BWD
   DA_LAUNCH_CHECK();
