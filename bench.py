@@ -157,21 +157,20 @@ def run_ours(args):
         fuse = [p for p in params if p.numel() >= (1 << 24)]
         sync_note = "none (1 GPU); FC1's SGD update is applied by the epilogue of its weight-gradient kernel"
     if world > 1 and args.grad_sync == "peer" and pairs == 1 and args.engine == "umma_bf16":
-        if True:
-            big = [p for p in params if p.numel() >= (1 << 24)]
-            try:
-                peer_opt = peer.PeerShardedSGD(big, max_ctas=args.peer_ctas, reserve_sms=args.peer_reserve_sms, transport=args.peer_transport,
-                                                deferred_publish=args.peer_publish == "deferred", **sgd)
-                params = [p for p in params if all(p is not q for q in big)]
-                how = ("copy engines push gradient slices to their owner and the refreshed bf16 slices to every rank, all-local update kernel"
-                       if args.peer_transport == "copy" else "one kernel with SM-issued P2P loads/stores")
-                sync_note = (f"FC1 ({sum(p.numel() for p in big) / 1e6:.0f} M params): gradient mean + sharded SGD + bf16 operand broadcast "
-                             f"over NVLink peer memory ({how}; da_sgd_step_peer; momentum and fp32 master sharded); "
-                             "remaining tensors: nccl avg fp32 + multi-tensor SGD")
-            except Exception as e:    # CUDA IPC unavailable on this box: the all-NCCL path is the same math
-                peer_opt = None
-                F_.MANAGED_WGRAD.clear()
-                sync_note += f" (peer path unavailable: {type(e).__name__}: {str(e)[:100]})"
+        big = [p for p in params if p.numel() >= (1 << 24)]
+        try:
+            peer_opt = peer.PeerShardedSGD(big, max_ctas=args.peer_ctas, reserve_sms=args.peer_reserve_sms, transport=args.peer_transport,
+                                            deferred_publish=args.peer_publish == "deferred", **sgd)
+            params = [p for p in params if all(p is not q for q in big)]
+            how = ("copy engines push gradient slices to their owner and the refreshed bf16 slices to every rank, all-local update kernel"
+                   if args.peer_transport == "copy" else "one kernel with SM-issued P2P loads/stores")
+            sync_note = (f"FC1 ({sum(p.numel() for p in big) / 1e6:.0f} M params): gradient mean + sharded SGD + bf16 operand broadcast "
+                         f"over NVLink peer memory ({how}; da_sgd_step_peer; momentum and fp32 master sharded); "
+                         "remaining tensors: nccl avg fp32 + multi-tensor SGD")
+        except Exception as e:    # CUDA IPC unavailable on this box: the all-NCCL path is the same math
+            peer_opt = None
+            F_.MANAGED_WGRAD.clear()
+            sync_note += f" (peer path unavailable: {type(e).__name__}: {str(e)[:100]})"
     opt = optim.FusedSGD(params, fuse_wgrad=fuse, **sgd)
     reducer = ddist.OverlappedGradAllReduce(params) if world > 1 else None
 
@@ -190,7 +189,7 @@ def run_ours(args):
             loss, _ = hotpath.parse_losses(losses)
             loss.backward()
             total = loss.detach() if total is None else total + loss.detach()
-        if reducer is not None and not os.environ.get("DA_DIAG_NOFLAT"):
+        if reducer is not None:
             reducer()
         opt.step()
         opt.zero_grad(set_to_none=True)
