@@ -3,9 +3,11 @@
 The reference trains data-parallel through MMDistributedDataParallel + torch.optim.SGD
 (mmdet/apis/train.py:113-127): all-reduce every gradient, then every rank repeats the whole update.  For
 FC1 of the shared bbox head (103 M parameters) that is a 411 MB all-reduce and a 2.26 GB optimizer pass
-per step and rank.  `PeerShardedSGD` replaces both for the tensors it manages with ONE kernel per tensor
-(`da_sgd_step_peer`, csrc/peer_sgd.cu): rank r owns slice r, pulls that slice of every rank's gradient
-over NVLink, applies the SGD rule, and pushes the refreshed bf16 operand copy to every rank.  Momentum is
+per step and rank.  `PeerShardedSGD` replaces both for the tensors it manages (`da_sgd_step_peer`,
+csrc/peer_sgd.cu): rank r owns slice r of the tensor; the copy engines push slice r of every rank's gradient
+into rank r's staging area over NVLink while the backward pass continues, one all-local kernel averages the
+staged slices in rank order and applies the SGD rule, and the copy engines push the refreshed bf16 operand
+slice to every rank (optionally under the beginning of the next step: `deferred_publish`).  Momentum is
 stored sharded; the fp32 master of a rank is current on its own slice only unless `share_master=True`
 (`gather_master()` assembles it for checkpoints).
 
@@ -79,14 +81,15 @@ def make_args(w, momentum_shard, grads, shadows, masters, flags, local_state, n,
 
 class _Managed:
     __slots__ = ("param", "n", "grad", "shadow", "flags", "state", "momentum", "args", "calls", "blocks", "pending", "ptrs",
-                 "staging", "lo", "hi", "per", "unpublished")
+                 "staging", "lo", "hi", "per")
 
 
 class PeerShardedSGD:
     """SGD (momentum, weight decay; the reference recipe) for `params`, fused with the gradient mean over ranks and
-    launched from INSIDE backward: the update of a layer runs on a side stream as soon as the layer's own backward
-    kernels are enqueued, under the rest of the backward pass (on one GPU that is all it does: the 2.3 GB optimizer
-    pass of FC1 is HBM-bound, the RoIAlign backward it then overlaps is latency-bound).
+    launched from INSIDE backward: the exchange starts when the layer's weight gradient exists and the update runs on a
+    side stream as soon as the layer's own backward kernels are enqueued, under the rest of the backward pass.
+    (Without a process group it degenerates to a one-rank update on the side stream; on one GPU that overlap was measured
+    and does not pay - optim.FusedSGD(fuse_wgrad=...) is the one-GPU form.)
 
     Usage per step:  forward/backward (the managed layers call back from their backward: `_after_wgrad` when the
     weight-gradient kernel is enqueued, `_layer_done` when the layer's last backward kernel is) -> `join()` before
@@ -217,9 +220,7 @@ class PeerShardedSGD:
         if self.transport == "copy":
             check(lib.da_sgd_step_peer(ctypes.byref(m.args), self.lr, self.momentum, self.weight_decay, first, self.max_ctas,
                                        _lib.DA_PEER_PUBLISH_BY_CALLER, st), "sgd_step_peer")
-            if self.deferred and self.world > 1:
-                m.unpublished = True
-            else:
+            if not (self.deferred and self.world > 1):      # deferred: publish() enqueues the pushes after the step
                 self._push_slices(m, st)
                 if self.world > 1:
                     check(lib.da_peer_publish_done(ctypes.byref(m.args), st), "peer_publish_done")
