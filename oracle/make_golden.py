@@ -166,6 +166,22 @@ def group_loss_cases(ns):
     torch.save(out, os.path.join(OUT, "group_local_da_loss.pt"))
 
 
+def sampler_cases():
+    """Index streams of the reference's BatchSchedulerSampler for seeded epochs (torch.manual_seed(seed) before iter())."""
+    from torch.utils.data import ConcatDataset, TensorDataset
+    cls = ref_loader.load_batch_sampler()
+    out = []
+    for sizes, spg, seed in [((7, 4), 2, 0), ((5, 9), 4, 1), ((6, 6), 2, 2), ((3, 10), 6, 3)]:
+        ds = ConcatDataset([TensorDataset(torch.zeros(n)) for n in sizes])
+        smp = cls(ds, samples_per_gpu=spg)
+        torch.manual_seed(seed)
+        idx = list(iter(smp))
+        out.append({"sizes": list(sizes), "samples_per_gpu": spg, "seed": seed, "len": len(smp), "indices": idx})
+        print(f"sampler {sizes} spg={spg}: {len(idx)} indices, len()={len(smp)}")
+    import json
+    json.dump(out, open(os.path.join(OUT, "batch_scheduler_sampler.json"), "w"))
+
+
 def state_dict_surface(ns):
     """Key -> shape of the reference DA backbones (trunk + DA heads) and instance heads: the checkpoint surface
     (SURVEY.md Appendix C)."""
@@ -201,6 +217,7 @@ def main():
     backbone_loss_cases(ns)
     focal_case(ns)
     group_loss_cases(ns)
+    sampler_cases()
     total = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print(f"golden fixtures: {total / 1e6:.2f} MB in {OUT}")
 

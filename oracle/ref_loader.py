@@ -131,3 +131,12 @@ def load_group_loss(flavour):
     ns = {"torch": _TorchCpu(), "F": F, "cluster": cl.cluster}
     exec(compile(mod, os.path.join(REF, "mmdet/models/detectors", path), "exec"), ns)
     return {f.name: ns[f.name] for f in fns}
+
+
+def load_batch_sampler():
+    """The reference's BatchSchedulerSampler class (mmdet/datasets/samplers/batch_sampler.py), loaded in place."""
+    if not available():
+        raise RuntimeError(f"{REF} not present")
+    _install_stubs()
+    sys.modules["mmcv.runner"].get_dist_info = lambda: (0, 1)
+    return _load("mmdet_ref.datasets.samplers.batch_sampler", "mmdet/datasets/samplers/batch_sampler.py").BatchSchedulerSampler
