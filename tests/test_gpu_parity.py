@@ -569,3 +569,25 @@ def test_group_local_da_loss_matches_reference_methods(golden, engine, tol):
                                             draw_centroids=draw)
         assert val.dim() == 0 and not val.requires_grad
         assert abs(float(val) - rec["loss"]) <= tol * max(1.0, abs(rec["loss"])), (name, engine, float(val), rec["loss"])
+
+
+# ---------------------------------------------------------------------------- tools/DA_train.py (entry point surface)
+def test_da_train_entry_point_trains_checkpoints_and_resumes(tmp_path):
+    """config -> build_detector -> pair sampler -> train_step -> FusedSGD -> checkpoint, then --resume-from."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = os.path.join(root, "tests", "fixtures", "cfg", "experiment.py")
+    base = [sys.executable, os.path.join(root, "tools", "DA_train.py"), cfg, "--synthetic", "4", "--img-size", "128x192",
+            "--work-dir", str(tmp_path), "--cfg-options", "optimizer.lr=0.0005"]
+    out = subprocess.run(base + ["--iters", "3"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
+    assert "iter 3/3" in out.stdout and "domains [0, 1]" in out.stdout and "globle_da_loss" in out.stdout
+    ck = torch.load(tmp_path / "iter_3.pth", map_location="cpu", weights_only=False)
+    assert ck["meta"]["iter"] == 3 and "backbone.da_head_top.conv1.weight" in ck["state_dict"]
+    assert len(ck["optimizer"]["momentum"]) > 0
+    out = subprocess.run(base + ["--iters", "5", "--resume-from", str(tmp_path / "iter_3.pth")], capture_output=True, text=True,
+                         timeout=600, cwd=root)
+    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
+    assert "iter 4/5" in out.stdout and "iter 5/5" in out.stdout and "iter 3/5" not in out.stdout
+    assert os.path.exists(tmp_path / "iter_5.pth")
