@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--engine", default="umma_bf16", choices=["umma_bf16", "umma_bf16x3", "simt_f32"])
     ap.add_argument("--pairs-per-gpu", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="daf", choices=["daf", "maf"],
+                    help="daf (default, the contract line): DAF-Org hot path; maf: auxiliary line for BASELINE config 3 - the three SRM "
+                         "image-level heads of MAFasterRCNN on C3/C4/C5 of 1024x2048 pairs (tensor-bound), one pair per GPU")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--cpu-budget-s", type=float, default=20.0)
     ap.add_argument("--grad-sync", default="peer", choices=["peer", "nccl"],
@@ -466,6 +469,116 @@ def kernel_rooflines(dev, act, step_ms, fused_step=True):
 
 
 # ----------------------------------------------------------------------------------------------
+# auxiliary workload: MAF image-level heads (BASELINE config 3 shapes, one pair per GPU)
+# ----------------------------------------------------------------------------------------------
+def run_maf(args):
+    """SRM heads (mmdet/models/backbones/resnet_da.py:83-118) on C3/C4/C5 + CE on sigmoid (L3) + backward into the
+    features (reversed gradient) + SGD.  FLOPs: 2*M*N*K per implicit GEMM with the enlarged extents of Q12
+    (1x1 pad 1 -> (H+2)x(W+2); 3x3 pad 3 on that -> (H+6)x(W+6)), forward + data gradient + weight gradient."""
+    import unsupervised_domain_adaptation_object_detection_implementation_b200 as uda
+    from unsupervised_domain_adaptation_object_detection_implementation_b200 import dist as ddist, functional as F_, hotpath, optim, _lib
+    import torch.distributed as dist
+    rank, local, world = ddist.init_from_env("nccl")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    uda.set_engine(args.engine)
+    act = F_.act_dtype()
+    shapes = [(512, 128, 256), (1024, 64, 128), (2048, 64, 128)]
+    torch.manual_seed(0)
+    model = hotpath.MAFHotPath(tuple(c for c, _, _ in shapes)).to(dev).train()
+    params = ddist.trainable_parameters(model, [])
+    opt = optim.FusedSGD(params, lr=1e-3, momentum=0.9, weight_decay=5e-4)
+    reducer = ddist.OverlappedGradAllReduce(params) if world > 1 else None
+    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    feats = [[torch.relu(torch.randn(2, h, w, c, device=dev, generator=g)).to(act) for c, h, w in shapes] for _ in range(2)]
+    flops = 0.0
+    for c, h, w in shapes:
+        flops += 2.0 * (2 * (h + 2) * (w + 2)) * c * (c // 4) + 2.0 * (2 * (h + 6) * (w + 6)) * (9 * c // 4) * (9 * c // 4)
+    flops *= 3.0
+
+    def step(slot):
+        F_.bump_dropout_counter(dev)
+        xs = [t.permute(0, 3, 1, 2).requires_grad_(True) for t in feats[slot]]
+        loss, _ = hotpath.parse_losses(model.forward_train(xs[0], xs[1], xs[2], [0, 1]))
+        loss.backward()
+        if reducer is not None:
+            reducer()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return loss.detach()
+
+    F_.dropout_counter(dev)
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for i in range(3):
+            step(i % 2)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graphs, note = [], "cuda_graph"
+    try:
+        pool = None
+        for slot in range(2):
+            gph = torch.cuda.CUDAGraph()
+            _lib.reset_launch_count()
+            with torch.cuda.graph(gph, pool=pool):
+                step(slot)
+            pool = gph.pool()
+            graphs.append(gph)
+        per_replay = _lib.launch_count()
+    except Exception as e:
+        graphs, note, per_replay = [], f"eager ({type(e).__name__}: {str(e)[:80]})", 0
+        torch.cuda.synchronize()
+
+    def run(i):
+        if graphs:
+            graphs[i % 2].replay()
+        else:
+            step(i % 2)
+
+    for i in range(max(args.warmup, 3)):
+        run(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    _lib.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        run(i)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = ddist.max_over_ranks(e0.elapsed_time(e1), dev)
+    clocks = sampler.stop()
+    launches = per_replay * args.steps if graphs else _lib.launch_count()
+    pk = peaks()
+    tf = flops / (ms / args.steps) / 1e9
+    if rank == 0:
+        print(json.dumps({
+            "metric": "da_train_step_img_pairs_per_s", "value": round(world * args.steps / (ms / 1e3), 3), "unit": "img-pairs/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.engine == "umma_bf16" else "f32",
+            "data": "synthetic",
+            "config": {"workload": "maf_r50dc5_srm_heads_c3c4c5_1024x2048", "pairs_per_gpu": 1, "features": [[2, c, h, w] for c, h, w in shapes],
+                       "engine": args.engine, "launch": note, "step": "SRM x3 + CE-on-sigmoid, backward into the features, SGD",
+                       "l2_policy": "activations exceed L2 (C5 head intermediate 173 MB); two input sets alternated", "auxiliary": True},
+            "e2e": None, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"kernel": "whole step (implicit GEMMs of the three SRM heads)", "bound": "tensor", "achieved": round(tf, 1),
+                         "peak": pk["bf16_tflops_sustained"] or pk["bf16_tflops"], "unit": "TFLOP/s",
+                         "frac": round(tf / (pk["bf16_tflops_sustained"] or pk["bf16_tflops"]), 4), "traffic": None,
+                         "peak_source": pk["source"] + " (sustained: kernels timed inside a long step)", "flops_per_step": flops}}))
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
+
+
+# ----------------------------------------------------------------------------------------------
 # CPU reference arm (oracle port; the one place bench.py may execute oracle/)
 # ----------------------------------------------------------------------------------------------
 def cpu_reference_step(rows, rois_per_img, threads, state):
@@ -583,5 +696,7 @@ if __name__ == "__main__":
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "maf":
+        run_maf(a)
     else:
         run_ours(a)
