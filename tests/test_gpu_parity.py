@@ -591,3 +591,41 @@ def test_da_train_entry_point_trains_checkpoints_and_resumes(tmp_path):
     assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
     assert "iter 4/5" in out.stdout and "iter 5/5" in out.stdout and "iter 3/5" not in out.stdout
     assert os.path.exists(tmp_path / "iter_5.pth")
+
+
+# ---------------------------------------------------------------------------- vectorised bf16 elementwise kernels, wide channels
+@pytest.mark.parametrize("C", [64, 800, 1152, 2304, 4608])
+def test_act_backward_bf16_wide_channels(C):
+    """da_conv_act_backward on bf16 activations takes the 16-byte kernel for every C % 8 == 0: G = C/8 <= 128 column groups
+    (rows split over the block, idle threads when 256 % G != 0) and G > 128 (a thread walks several groups)."""
+    import ctypes
+    g = torch.Generator(device=DEV).manual_seed(C)
+    M = 333
+    dy = torch.randn(M, C, device=DEV, generator=g).to(torch.bfloat16)
+    y = torch.randn(M, C, device=DEV, generator=g).to(torch.bfloat16)
+    scale = torch.rand(C, device=DEV, generator=g) + 0.5
+    dz = torch.empty_like(dy)
+    dshift = torch.empty(C, device=DEV)
+    dvdot = torch.empty(C, device=DEV)
+    desc = F_._conv_desc(M, 1, 1, 8, C, 1, 1, 1, 0, "umma_bf16", torch.bfloat16, torch.bfloat16)
+    ws = F_.workspace(uda._lib.lib.da_conv_workspace_bytes(ctypes.byref(desc)), torch.device(DEV), "conv")
+    uda._lib.check(uda._lib.lib.da_conv_act_backward(ctypes.byref(desc), F_._ptr(dy), F_._ptr(y), F_._ptr(scale), 1, 0.0, 0, F_._ptr(dz),
+                                                     F_._ptr(dshift), F_._ptr(dvdot), F_._ptr(ws), ws.numel(), None), "act_backward")
+    torch.cuda.synchronize()
+    d = dy.float() * (y.float() > 0)
+    assert torch.equal(dz, (d * scale).to(torch.bfloat16))
+    assert rel_err(dshift, d.sum(0)) <= 1e-5
+    assert rel_err(dvdot, (d * y.float()).sum(0)) <= 1e-5
+
+
+@pytest.mark.parametrize("C", [64, 1152, 4608])
+def test_global_avgpool_bf16_vectorised(C):
+    g = torch.Generator(device=DEV).manual_seed(C + 1)
+    x = torch.randn(2, 9, 13, C, device=DEV, generator=g).to(torch.bfloat16).requires_grad_(True)
+    yv = F_.global_avgpool(x)
+    ref = x.detach().float().mean(dim=(1, 2))
+    assert rel_err(yv.float().view(2, C), ref) <= 1e-5
+    cot = torch.randn(yv.shape, device=DEV, generator=g).to(yv.dtype)
+    (dx,) = torch.autograd.grad(yv, x, cot)
+    exp = (cot.float().view(2, 1, 1, C) / (9 * 13)).expand(2, 9, 13, C).to(torch.bfloat16)
+    assert torch.equal(dx, exp)

@@ -406,10 +406,11 @@ __global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y
     if (partial2) partial2[(size_t)blockIdx.x * C + c] = colsum2;
   }
 }
-// bf16 activations, C in {64 .. 2048} with 256 % (C/8) == 0: a thread owns 8 consecutive channels (one 16-byte load of dy and
-// of y, one 16-byte store of dz per row) and every SUB-th row of the block's row range; the SUB partial column sums meet in
-// shared memory.  The scalar kernel above moves 2 bytes per thread and access (ncu: 35 us for the [16384, 512] activation of
-// the image head, 50 MB of traffic).
+// bf16 activations, C % 8 == 0: a thread owns groups of 8 consecutive channels (one 16-byte load of dy and of y, one
+// 16-byte store of dz per row).  With G = C/8 <= 128 column groups the 256 threads also split the block's rows SUB = 256/G
+// ways and the SUB partial column sums meet in shared memory; with more groups a thread walks the rows alone and takes every
+// 256th group.  The scalar kernel above moves 2 bytes per thread and access (ncu: 35 us for the [16384, 512] activation of the
+// image head, 480-510 us for the [18760, 4608] activation of the C5 SRM head).
 __global__ void __launch_bounds__(256)
 act_bwd_vec8_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y, int64_t M, int C,
                     const float* __restrict__ scale, int relu, float drop_p, uint64_t seed0, const unsigned long long* seed_ctr,
@@ -423,42 +424,60 @@ act_bwd_vec8_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
   const uint32_t thr = drop_threshold(drop_p);
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   const float inv_keep = 1.f / keep_scale;
-  const int G = C >> 3, SUB = 256 / G;
-  const int cg = threadIdx.x % G, sub = threadIdx.x / G;
-  const int c0 = cg << 3;
-  float sc[8], cs[8], cs2[8];
+  const int G = C >> 3;
+  const int SUB = G <= 128 ? 256 / G : 1;                 // row-parallel ways (threads beyond G*SUB idle in the main loop)
+  const int sub = G <= 128 ? threadIdx.x / G : 0;
+  const int cg_first = G <= 128 ? threadIdx.x % G : threadIdx.x;
+  const int cg_step = G <= 128 ? G : 256;
+  const bool active = sub < SUB;
+  for (int cg = cg_first; cg < G; cg += cg_step) {
+    const int c0 = cg << 3;
+    float sc[8], cs[8], cs2[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { sc[j] = scale ? scale[c0 + j] : 1.f; cs[j] = 0.f; cs2[j] = 0.f; }
-  for (int64_t m = m0 + sub; m < m1; m += SUB) {
-    const size_t i = (size_t)m * C + c0;
-    const uint4 dv = *reinterpret_cast<const uint4*>(dy + i);
-    uint4 yv4 = make_uint4(0u, 0u, 0u, 0u);
-    if (y) yv4 = *reinterpret_cast<const uint4*>(y + i);
-    const __nv_bfloat16* dp = reinterpret_cast<const __nv_bfloat16*>(&dv);
-    const __nv_bfloat16* yp = reinterpret_cast<const __nv_bfloat16*>(&yv4);
-    uint4 ov;
-    __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(&ov);
+    for (int j = 0; j < 8; ++j) { sc[j] = scale ? scale[c0 + j] : 1.f; cs[j] = 0.f; cs2[j] = 0.f; }
+    if (active) {
+      for (int64_t m = m0 + sub; m < m1; m += SUB) {
+        const size_t i = (size_t)m * C + c0;
+        const uint4 dv = *reinterpret_cast<const uint4*>(dy + i);
+        uint4 yv4 = make_uint4(0u, 0u, 0u, 0u);
+        if (y) yv4 = *reinterpret_cast<const uint4*>(y + i);
+        const __nv_bfloat16* dp = reinterpret_cast<const __nv_bfloat16*>(&dv);
+        const __nv_bfloat16* yp = reinterpret_cast<const __nv_bfloat16*>(&yv4);
+        uint4 ov;
+        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(&ov);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float d = __bfloat162float(dp[j]);
-      const float yv = y ? __bfloat162float(yp[j]) : 0.f;
-      bool on = true;
-      if (relu) on = yv > 0.f;
-      if (drop_p > 0.f) { on = on && (drop_hash(seed, (uint64_t)(i + j)) >= thr); d *= keep_scale; }
-      d = on ? d : 0.f;
-      cs[j] += d;
-      cs2[j] = fmaf(d, yv * inv_keep, cs2[j]);
-      op[j] = __float2bfloat16_rn(d * sc[j]);
+        for (int j = 0; j < 8; ++j) {
+          float d = __bfloat162float(dp[j]);
+          const float yv = y ? __bfloat162float(yp[j]) : 0.f;
+          bool on = true;
+          if (relu) on = yv > 0.f;
+          if (drop_p > 0.f) { on = on && (drop_hash(seed, (uint64_t)(i + j)) >= thr); d *= keep_scale; }
+          d = on ? d : 0.f;
+          cs[j] += d;
+          cs2[j] = fmaf(d, yv * inv_keep, cs2[j]);
+          op[j] = __float2bfloat16_rn(d * sc[j]);
+        }
+        *reinterpret_cast<uint4*>(dz + i) = ov;
+      }
     }
-    *reinterpret_cast<uint4*>(dz + i) = ov;
+    if (!partial && !partial2) continue;
+    if (SUB > 1) {                    // G <= 128: exactly one pass of the cg loop, every thread reaches the barrier
+      if (active) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          ab_red[(size_t)sub * C + c0 + j] = cs[j];
+          ab_red[(size_t)(SUB + sub) * C + c0 + j] = cs2[j];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (partial) partial[(size_t)blockIdx.x * C + c0 + j] = cs[j];
+        if (partial2) partial2[(size_t)blockIdx.x * C + c0 + j] = cs2[j];
+      }
+    }
   }
-  if (!partial && !partial2) return;
-  if (SUB > 1) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      ab_red[(size_t)sub * C + c0 + j] = cs[j];
-      ab_red[(size_t)(SUB + sub) * C + c0 + j] = cs2[j];
-    }
+  if (SUB > 1 && (partial || partial2)) {
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += 256) {
       float a = 0.f, b = 0.f;
@@ -466,18 +485,10 @@ act_bwd_vec8_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
       if (partial) partial[(size_t)blockIdx.x * C + c] = a;
       if (partial2) partial2[(size_t)blockIdx.x * C + c] = b;
     }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (partial) partial[(size_t)blockIdx.x * C + c0 + j] = cs[j];
-      if (partial2) partial2[(size_t)blockIdx.x * C + c0 + j] = cs2[j];
-    }
   }
 }
 static inline bool act_vec8_ok(int C, const void* a, const void* b, const void* c) {
-  const int G = C >> 3;
-  return (C & 7) == 0 && G >= 1 && G <= 256 && 256 % G == 0 &&
-         ((((uintptr_t)a) | ((uintptr_t)b) | ((uintptr_t)c)) & 15) == 0;
+  return (C & 7) == 0 && C >= 8 && ((((uintptr_t)a) | ((uintptr_t)b) | ((uintptr_t)c)) & 15) == 0;
 }
 // out[c] = sum_b partial[b][c]; block (32 columns x 32 row lanes), coalesced rows, smem tree over the lanes
 __global__ void colsum_final_kernel(const float* __restrict__ partial, int nb, int C, float* __restrict__ out) {
@@ -644,7 +655,8 @@ extern "C" int da_conv_act_backward(const da_conv_desc* d, const void* dy, const
   cudaStream_t st = (cudaStream_t)stream;
   if (d->x_dtype == DA_F32) act_bwd_kernel<float><<<nb, 256, 0, st>>>((const float*)dy, (const float*)y, M, g.Cout, scale, relu, drop_p, drop_seed, g_seed_counter, (float*)dz, partial, dvdot ? partial2 : nullptr);
   else if (d->x_dtype == DA_BF16 && act_vec8_ok(g.Cout, dy, y, dz)) {
-    const int sub = 256 / (g.Cout >> 3);
+    const int grp = g.Cout >> 3;
+    const int sub = grp <= 128 ? 256 / grp : 1;
     const size_t smem = sub > 1 ? 2 * (size_t)sub * g.Cout * sizeof(float) : 0;     // <= 2 * 256 * 8 * 4 = 16 KB
     act_bwd_vec8_kernel<<<nb, 256, smem, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, M, g.Cout, scale, relu, drop_p, drop_seed,
                                                g_seed_counter, (__nv_bfloat16*)dz, partial, dvdot ? partial2 : nullptr);
