@@ -75,3 +75,38 @@ def test_peer_slice_bounds_partition_the_tensor():
             assert len({x[2] for x in b}) == 1 and b[0][2] % 1024 == 0
             assert all(x[0] % 1024 == 0 or x[0] == n for x in b)
             assert all(0 <= x[1] - x[0] <= x[2] for x in b)
+
+
+def _sampler_ckpt_worker(rank, world, port, outdir):
+    """world_size-2 gloo: each rank draws its sample stream from DistributedBatchSchedulerSampler (rank/world taken from the
+    process group) and all ranks call checkpoint.save_checkpoint; only rank 0 may write."""
+    from torch.utils.data import ConcatDataset, TensorDataset
+    from unsupervised_domain_adaptation_object_detection_implementation_b200 import checkpoint, data
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    r, _, w = ddist.init_from_env("gloo")
+    ds = ConcatDataset([TensorDataset(torch.zeros(9)), TensorDataset(torch.zeros(5))])
+    smp = data.DistributedBatchSchedulerSampler(ds, samples_per_gpu=2, num_replicas=w, rank=r, seed=3)
+    mine = torch.tensor(list(iter(smp)), dtype=torch.long)
+    streams = [torch.zeros_like(mine) for _ in range(w)]
+    dist.all_gather(streams, mine)                                   # equal length on every rank, or this call fails
+    torch.manual_seed(0)
+    model = torch.nn.Linear(4, 3)
+    path = os.path.join(outdir, "ck.pth")
+    checkpoint.save_checkpoint(model, path, meta={"iter": 7}, rank=r)
+    dist.barrier()
+    if r == 1:
+        torch.save({"streams": streams, "schedule": smp.global_schedule(), "exists": os.path.exists(path)}, os.path.join(outdir, "r1.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_distributed_pair_sampler_and_rank0_checkpoint_world2_gloo(tmp_path):
+    mp.spawn(_sampler_ckpt_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    rec = torch.load(str(tmp_path / "r1.pt"), weights_only=False)
+    s0, s1 = rec["streams"][0].tolist(), rec["streams"][1].tolist()
+    pairs = [tuple(s[k:k + 2]) for s in (s0, s1) for k in range(0, len(s), 2)]
+    assert sorted(pairs) == sorted(tuple(b) for b in rec["schedule"])           # the ranks partition the epoch's pairs
+    assert all(a < 9 <= b for a, b in pairs)                                    # (source, target), never split
+    assert rec["exists"]
+    ck = torch.load(str(tmp_path / "ck.pth"), weights_only=False)
+    assert ck["meta"]["iter"] == 7 and set(ck["state_dict"]) == {"weight", "bias"}
