@@ -52,7 +52,9 @@ enum da_roi_out_layout { DA_ROI_OUT_RCHW = 0, DA_ROI_OUT_RHWC = 1 };
 enum da_engine {
   DA_ENGINE_SIMT_F32 = 0,   /* CUDA-core fp32 FMA: bit-faithful fp32 parity mode          */
   DA_ENGINE_UMMA_BF16 = 1,  /* tcgen05.mma kind::f16 (bf16 in, fp32 TMEM accumulate)      */
-  DA_ENGINE_UMMA_BF16X3 = 2 /* 3-term split bf16 (hi*hi + hi*lo + lo*hi), ~1e-5 relative  */
+  DA_ENGINE_UMMA_BF16X3 = 2, /* 3-term split bf16 (hi*hi + hi*lo + lo*hi), ~2^-16 relative */
+  DA_ENGINE_UMMA_BF16X6 = 3  /* exact 3-way bf16 split of fp32 operands, 6 product terms on tcgen05:
+                                fp32-class (<= 1e-5 parity bar), 1/6 of the bf16 tensor rate (= 3xTF32) */
 };
 
 /* ---- library ------------------------------------------------------------ */
@@ -61,6 +63,12 @@ const char* da_last_error(void);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 int64_t da_launch_count(void);
 void da_launch_count_reset(void);
+/* Debug / test options.  The library reads its DA_* environment variables ONCE, when it is loaded (no getenv on any
+ * launch path); this call changes one afterwards.  Names: "roi_no_tc" (bf16 RoIAlign on the CUDA-core kernels instead of
+ * the tcgen05 ones), "umma_no_bn64", "umma_no_2sm", "no_pdl", "umma_dbg", "roi_bwd_dbg", "roi_bwd_trace".  Process-wide
+ * and not meant to be flipped while other threads launch; defaults (all 0) are what production runs.
+ * Per-DEVICE state (da_set_sm_limit, da_set_dropout_counter) belongs to the calling thread's current CUDA device. */
+int da_set_option(const char* name, long long value);
 
 /* ---- layout + GRL --------------------------------------------------------
  * GRL: mmdet/models/roi_heads/instance_da.py:14-40 (_GradientScalarLayer): forward is the
@@ -148,6 +156,8 @@ int da_peer_publish_done(const da_peer_sgd_args* args, da_stream_t stream);   /*
  * update kernel of step t+1 waits for publish t before it rewrites the slice the pushes read (error 3 on time-out). */
 int da_peer_signal_done(const da_peer_sgd_args* args, da_stream_t stream);
 int da_peer_wait_done(const da_peer_sgd_args* args, da_stream_t stream);
+/* SETUP-TIME ONLY (never on the step path): the one place the library allocates, because a CUDA IPC handle needs a
+ * dedicated cudaMalloc block (a sub-allocation of a caching allocator cannot be exported); zero-fills and synchronises. */
 int da_peer_alloc(size_t bytes, void** out);
 int da_peer_free(void* p);
 int da_peer_export(const void* p, unsigned char* handle64);

@@ -349,3 +349,47 @@ def group_local_da_loss(bbox_feats, bbox_cls, sd_fore, sd_back, flavour="daf", k
         labels = torch.full((f.shape[0],), label, dtype=torch.long)
         total = total + (focal2(pred, labels) if flavour == "daf" else ce2(pred, labels))
     return total.detach()
+
+
+# --------------------------------------------------------------------------------------
+# R3 StandardRoIHeadDA_v5 — mmdet/models/roi_heads/standard_roi_head_da_v5.py:162-227 and the box-head loss it calls
+# (bbox_heads/bbox_head.py:256-315 with the DA configs' CrossEntropyLoss(use_sigmoid=True) + SmoothL1Loss(beta=1),
+# faster_rcnn_r50_torch_daf.py:56-58).  Pinned to the reference's own loss classes by tests/golden/bbox_head_loss.pt.
+# --------------------------------------------------------------------------------------
+def bbox_head_loss(cls_score, bbox_pred, labels, targets, pos_mask, num_classes, beta=1.0, reg_class_agnostic=False):
+    """loss_cls = sum BCEWithLogits(cls_score, onehot_{C+1}(labels)) / R   (weight_reduce_loss with avg_factor = #RoIs,
+    losses/cross_entropy_loss.py:100-114);  loss_bbox = sum SmoothL1(pred[pos, label], target[pos]) / R
+    (avg_factor = bbox_targets.size(0), bbox_head.py:309);  acc = top-1 in percent (losses/accuracy.py)."""
+    R = max(cls_score.shape[0], 1)
+    onehot = F.one_hot(labels, num_classes + 1).to(cls_score.dtype)
+    out = {"loss_cls": F.binary_cross_entropy_with_logits(cls_score, onehot, reduction="sum") / R,
+           "acc": (cls_score.argmax(1) == labels).to(cls_score.dtype).mean() * 100}
+    if bool(pos_mask.any()):
+        pred = bbox_pred[pos_mask] if reg_class_agnostic else bbox_pred.view(bbox_pred.shape[0], -1, 4)[pos_mask, labels[pos_mask]]
+        d = (pred - targets[pos_mask]).abs()
+        out["loss_bbox"] = torch.where(d < beta, 0.5 * d * d / beta, d - 0.5 * beta).sum() / R
+    else:
+        out["loss_bbox"] = bbox_pred.sum() * 0
+    return out
+
+
+def roi_head_da_v5(pooled_per_img, sampled, sd, num_classes, gt_da, q=None):
+    """What _bbox_forward_train returns for a (source, target) pair: per image i the RoI features pooled from image i
+    (`pooled_per_img[i]` [n_i, C, 7, 7]; the RoIAlign itself is oracle/roi_align_ref.c) go through forward_train_da
+    (convfc_bbox_head.py:198-237: flatten, FC+ReLU x2, fc_cls, fc_reg); the box loss is taken on the SOURCE image only
+    (:206-211).  sampled[i] = (boxes, labels, targets, pos_mask) of image i; sd = state_dict of the bbox head.
+    -> (losses, bbox_feats=[feat_src, feat_tar], bbox_cls=[cls_src, cls_tar])."""
+    feats, clss, regs = [], [], []
+    for x in pooled_per_img:
+        t = _q(x.flatten(1), q)
+        t = _q(F.relu(F.linear(t, _q(sd["shared_fcs.0.weight"], q), sd["shared_fcs.0.bias"])), q)
+        t = _q(F.relu(F.linear(t, _q(sd["shared_fcs.1.weight"], q), sd["shared_fcs.1.bias"])), q)
+        feats.append(t)
+        clss.append(F.linear(t, sd["fc_cls.weight"], sd["fc_cls.bias"]))
+        regs.append(F.linear(t, sd["fc_reg.weight"], sd["fc_reg.bias"]))
+    losses = {}
+    src = [i for i, d in enumerate(gt_da) if int(d) == 0]
+    if src:
+        i = src[0]
+        losses = bbox_head_loss(clss[i], regs[i], sampled[i][1], sampled[i][2], sampled[i][3], num_classes)
+    return losses, feats, clss

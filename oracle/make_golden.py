@@ -127,6 +127,32 @@ def focal_case(ns):
     print("focal:", float(loss))
 
 
+def bbox_head_loss_case(ns):
+    """R3: the box-head loss of the source image as BBoxHead.loss computes it (mmdet/models/roi_heads/bbox_heads/bbox_head.py:
+    256-315) with the reference's OWN loss classes: CrossEntropyLoss(use_sigmoid=True) reduced with avg_factor = number of
+    sampled RoIs, SmoothL1Loss(beta=1) over the positives with avg_factor = number of sampled RoIs, top-1 accuracy."""
+    R, C = 48, 3
+    cls_score = seeded.seeded_tensor("bbox.cls", (R, C + 1), 0, scale=2.0).requires_grad_(True)
+    bbox_pred = seeded.seeded_tensor("bbox.reg", (R, 4 * C), 0).requires_grad_(True)
+    labels = (seeded.seeded_tensor("bbox.lab", (R,), 0, "uniform") * 2.7 - 1.2).clamp(0, C).long()    # classes 0..C-1, C = background
+    labels[:4] = torch.tensor([0, 1, 2, C])
+    targets = seeded.seeded_tensor("bbox.tgt", (R, 4), 0, scale=0.7)
+    label_weights = torch.ones(R)
+    pos = (labels >= 0) & (labels < C)
+    bbox_weights = pos.float()[:, None].expand(R, 4).contiguous()
+    avg_factor = max(float((label_weights > 0).sum()), 1.0)
+    loss_cls = ns.ce.CrossEntropyLoss(use_sigmoid=True, loss_weight=1.0)(cls_score, labels, label_weights, avg_factor=avg_factor)
+    acc = ns.accuracy.accuracy(cls_score, labels)
+    pos_pred = bbox_pred.view(R, -1, 4)[pos, labels[pos]]
+    loss_bbox = ns.smooth_l1.SmoothL1Loss(beta=1.0, loss_weight=1.0)(pos_pred, targets[pos], bbox_weights[pos], avg_factor=targets.size(0))
+    (loss_cls + loss_bbox).backward()
+    torch.save({"cls_score": cls_score.detach().clone(), "bbox_pred": bbox_pred.detach().clone(), "labels": labels, "targets": targets,
+                "pos_mask": pos, "num_classes": C, "loss_cls": loss_cls.detach().clone(), "loss_bbox": loss_bbox.detach().clone(),
+                "acc": acc.detach().clone().reshape(()), "dcls": cls_score.grad.clone(), "dreg": bbox_pred.grad.clone()},
+               os.path.join(OUT, "bbox_head_loss.pt"))
+    print(f"bbox_head_loss: cls {float(loss_cls):.6f} bbox {float(loss_bbox):.6f} acc {float(acc):.2f} ({int(pos.sum())} positives of {R})")
+
+
 def group_loss_cases(ns):
     """L5: the reference's own group_local_da_loss methods (compiled in place, ref_loader.load_group_loss) on CPU.
     Inputs are a pure function of the case name (seeded); centroid draws come from torch.manual_seed(case seed)."""
@@ -216,6 +242,7 @@ def main():
     head_case("instance_alignment_daf", ns.instance.InstanceAlignmentHead_DAF(), fm("x.insd", (24, 1024)))
     backbone_loss_cases(ns)
     focal_case(ns)
+    bbox_head_loss_case(ns)
     group_loss_cases(ns)
     sampler_cases()
     total = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))

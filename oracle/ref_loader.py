@@ -88,6 +88,9 @@ def load():
     ns.local_da = _load("mmdet_ref.models.roi_heads.local_da", "mmdet/models/roi_heads/local_da.py")
     ns.loss_utils = _load("mmdet_ref.models.losses.utils", "mmdet/models/losses/utils.py")
     ns.focal = _load("mmdet_ref.models.losses.focal_loss", "mmdet/models/losses/focal_loss.py")
+    ns.ce = _load("mmdet_ref.models.losses.cross_entropy_loss", "mmdet/models/losses/cross_entropy_loss.py")
+    ns.smooth_l1 = _load("mmdet_ref.models.losses.smooth_l1_loss", "mmdet/models/losses/smooth_l1_loss.py")
+    ns.accuracy = _load("mmdet_ref.models.losses.accuracy", "mmdet/models/losses/accuracy.py")
     return ns
 
 

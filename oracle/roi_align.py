@@ -30,6 +30,10 @@ def _lib():
         [ctypes.c_float, ctypes.c_int, ctypes.c_int, fp, ip, ip]
     lib.roi_align_backward_ref.argtypes = [fp, fp] + [ctypes.c_int] * 3 + [ctypes.c_float, ctypes.c_int, ctypes.c_int,
                                                                           ctypes.POINTER(ctypes.c_double)] + [ctypes.c_int] * 4
+    lib.roi_align_backward_ref_range.argtypes = [fp, fp] + [ctypes.c_int] * 3 + [ctypes.c_float, ctypes.c_int, ctypes.c_int,
+                                                                                ctypes.POINTER(ctypes.c_double)] + [ctypes.c_int] * 6
+    lib.roi_align_backward_f32_range.argtypes = [fp, fp] + [ctypes.c_int] * 3 + [ctypes.c_float, ctypes.c_int, ctypes.c_int, fp] + \
+        [ctypes.c_int] * 6
     lib.map_roi_levels_ref.argtypes = [fp, ctypes.c_int, ctypes.c_int, ctypes.c_float, ip]
     return lib
 
@@ -77,15 +81,35 @@ def roi_align_forward(feat, rois, output_size=7, spatial_scale=1.0, sampling_rat
     return out, grid, bidx
 
 
-def roi_align_backward(gout, rois, feat_shape, output_size=7, spatial_scale=1.0, sampling_ratio=0, aligned=True):
-    """gout [R,C,ph,pw] -> grad_input [N,C,H,W] float64 (exact-order-free reference)."""
+def _channel_pool(fn, C, threads):
+    """Run fn(c0, c1) over disjoint channel ranges on a host thread pool (ctypes drops the GIL; every thread owns
+    whole channel planes of the gradient, so no atomics are needed)."""
+    if threads <= 1 or C < 2 * threads:
+        fn(0, C)
+        return
+    step = (C + threads - 1) // threads
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(lambda k: fn(k * step, min(C, (k + 1) * step)), range((C + step - 1) // step)))
+
+
+def roi_align_backward(gout, rois, feat_shape, output_size=7, spatial_scale=1.0, sampling_ratio=0, aligned=True, threads=None,
+                       dtype=np.float64):
+    """gout [R,C,ph,pw] -> grad_input [N,C,H,W].  dtype float64 (default): exact-order-free reference for the parity
+    tests; float32: the reference's own arithmetic (fp32 `+=`), what bench.py's CPU baseline times."""
     gout = np.ascontiguousarray(gout, dtype=np.float32)
     rois = np.ascontiguousarray(rois, dtype=np.float32).reshape(-1, 5)
     N, C, H, W = feat_shape
-    gin = np.zeros((N, C, H, W), np.float64)
-    _get().roi_align_backward_ref(_f(gout), _f(rois), rois.shape[0], int(output_size), int(output_size),
-                                  float(spatial_scale), int(sampling_ratio), int(bool(aligned)),
-                                  gin.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), N, C, H, W)
+    threads = threads or min(os.cpu_count() or 1, 64)
+    gin = np.zeros((N, C, H, W), dtype)
+    lib = _get()
+    args = (_f(gout), _f(rois), rois.shape[0], int(output_size), int(output_size), float(spatial_scale), int(sampling_ratio),
+            int(bool(aligned)))
+    if dtype == np.float64:
+        gp = gin.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+        _channel_pool(lambda c0, c1: lib.roi_align_backward_ref_range(*args, gp, N, C, H, W, c0, c1), C, threads)
+    else:
+        gp = _f(gin)
+        _channel_pool(lambda c0, c1: lib.roi_align_backward_f32_range(*args, gp, N, C, H, W, c0, c1), C, threads)
     return gin
 
 

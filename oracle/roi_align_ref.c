@@ -92,15 +92,15 @@ void roi_align_forward_ref(const float* feat, int N, int C, int H, int W, const 
   roi_align_forward_ref_range(feat, N, C, H, W, rois, 0, R, ph, pw, scale, sr, aligned, out, grid, bidx);
 }
 
-/* gin [N,C,H,W] is zeroed here; accumulation in double then rounded (the reference scatters
- * with float atomics in an unspecified order, so its own result is only defined to rounding). */
-void roi_align_backward_ref(const float* gout, const float* rois, int R, int ph, int pw, float scale,
-                            int sr, int aligned, double* gin, int N, int C, int H, int W) {
-  memset(gin, 0, sizeof(double) * (size_t)N * C * H * W);
+/* gin [N,C,H,W]: accumulation in double then rounded (the reference scatters with float atomics in an
+ * unspecified order, so its own result is only defined to rounding).  [c0,c1): channel range, so that a host
+ * thread pool can split the work without atomics (every thread owns whole channel planes); the caller zeroes gin. */
+void roi_align_backward_ref_range(const float* gout, const float* rois, int R, int ph, int pw, float scale,
+                                  int sr, int aligned, double* gin, int N, int C, int H, int W, int c0, int c1) {
   for (int r = 0; r < R; ++r) {
     roi_geom_t g = roi_geom(rois + 5 * r, ph, pw, scale, sr, aligned);
     if (g.b < 0 || g.b >= N) continue;
-    for (int c = 0; c < C; ++c) {
+    for (int c = c0; c < c1; ++c) {
       double* gi = gin + ((size_t)g.b * C + c) * H * W;
       const float* go = gout + ((size_t)r * C + c) * ph * pw;
       for (int i = 0; i < ph; ++i)
@@ -116,6 +116,42 @@ void roi_align_backward_ref(const float* gout, const float* rois, int R, int ph,
               gi[t.yl * W + t.xh] += (double)(gv * t.w2 / g.count);
               gi[t.yh * W + t.xl] += (double)(gv * t.w3 / g.count);
               gi[t.yh * W + t.xh] += (double)(gv * t.w4 / g.count);
+            }
+          }
+        }
+    }
+  }
+}
+
+void roi_align_backward_ref(const float* gout, const float* rois, int R, int ph, int pw, float scale,
+                            int sr, int aligned, double* gin, int N, int C, int H, int W) {
+  memset(gin, 0, sizeof(double) * (size_t)N * C * H * W);
+  roi_align_backward_ref_range(gout, rois, R, ph, pw, scale, sr, aligned, gin, N, C, H, W, 0, C);
+}
+
+/* The same scatter with fp32 accumulation (what the reference's CPU / CUDA kernels do: `+=` / atomicAdd on float):
+ * the arithmetic bench.py's CPU baseline times.  Channel range as above; the caller zeroes gin. */
+void roi_align_backward_f32_range(const float* gout, const float* rois, int R, int ph, int pw, float scale,
+                                  int sr, int aligned, float* gin, int N, int C, int H, int W, int c0, int c1) {
+  for (int r = 0; r < R; ++r) {
+    roi_geom_t g = roi_geom(rois + 5 * r, ph, pw, scale, sr, aligned);
+    if (g.b < 0 || g.b >= N) continue;
+    for (int c = c0; c < c1; ++c) {
+      float* gi = gin + ((size_t)g.b * C + c) * H * W;
+      const float* go = gout + ((size_t)r * C + c) * ph * pw;
+      for (int i = 0; i < ph; ++i)
+        for (int j = 0; j < pw; ++j) {
+          const float gv = go[i * pw + j];
+          for (int iy = 0; iy < g.gh; ++iy) {
+            const float y = g.y1 + i * g.bin_h + (iy + .5f) * g.bin_h / (float)g.gh;
+            for (int ix = 0; ix < g.gw; ++ix) {
+              const float x = g.x1 + j * g.bin_w + (ix + .5f) * g.bin_w / (float)g.gw;
+              tap_t t = bilinear_taps(y, x, H, W);
+              if (!t.ok) continue;
+              gi[t.yl * W + t.xl] += gv * t.w1 / g.count;
+              gi[t.yl * W + t.xh] += gv * t.w2 / g.count;
+              gi[t.yh * W + t.xl] += gv * t.w3 / g.count;
+              gi[t.yh * W + t.xh] += gv * t.w4 / g.count;
             }
           }
         }

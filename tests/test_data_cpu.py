@@ -94,3 +94,17 @@ def test_save_checkpoint_writes_on_rank_zero_only(tmp_path):
     assert checkpoint.save_checkpoint(head, str(tmp_path / "r1.pth"), rank=1) is None
     assert not os.path.exists(tmp_path / "r1.pth")
     assert ddist.shard_pairs(4, 1, 2) == [2, 3]
+
+
+def test_step_lr_schedule_matches_mmcv_step_updater_with_linear_warmup():
+    """optim.StepLrSchedule against mmcv's StepLrUpdaterHook + linear warm-up formulas for the DAF recipe
+    (da_configs/faster_rcnn/faster_rcnn_r50_daf_c2f.py:13-18: warmup 500 iters from ratio 1e-4, step at epoch 9)."""
+    from unsupervised_domain_adaptation_object_detection_implementation_b200 import optim
+    cfg = dict(policy="step", warmup="linear", warmup_iters=500, warmup_ratio=0.0001, step=[9])
+    sch = optim.StepLrSchedule(1e-3, cfg)
+    assert abs(sch(0, 0) - 1e-3 * 1e-4) < 1e-12                       # k = (1 - 0/500) * (1 - ratio) -> lr * ratio
+    assert abs(sch(250, 0) - 1e-3 * (1 - 0.5 * (1 - 1e-4))) < 1e-12
+    assert sch(500, 0) == 1e-3 and sch(10_000, 8) == 1e-3
+    assert abs(sch(10_000, 9) - 1e-4) < 1e-15 and abs(sch(10_000, 13) - 1e-4) < 1e-15
+    two = optim.StepLrSchedule(0.02, dict(policy="step", step=[6, 8]))
+    assert [round(two(1000, e), 8) for e in (0, 5, 6, 7, 8, 9)] == [0.02, 0.02, 0.002, 0.002, 0.0002, 0.0002]

@@ -40,11 +40,21 @@ def _worker(rank, world, port, out):
     x = torch.full((5, 8), float(rank + 1))
     model[1](model[0](x)).sum().backward()
     local = [p.grad.clone() for p in params]
-    params[3].grad = None                                           # a rank may miss a gradient: treated as zero
-    ddist.FlatGradAllReduce(params)()
+    params[3].grad = None                       # no gradient on ANY rank: skipped, stays None (as on one GPU: no decay/momentum)
+    if rank == 1:
+        params[2].grad = None                   # missing on ONE rank only: that rank contributes zeros and receives the mean
+        local[2] = torch.zeros_like(local[2])
+    red = ddist.FlatGradAllReduce(params)
+    red()
+    assert params[3].grad is None and params[2].grad is not None
+    kept = [p.grad.clone() for p in params[:3]]
+    for p, g in zip(params[:3], local[:3]):     # second step with the same pattern: the cached agreement is reused
+        p.grad = g.clone() if not (rank == 1 and p is params[2]) else None
+    red()
+    assert all(torch.equal(a, p.grad) for a, p in zip(kept, params[:3]))
     gathered = [torch.zeros_like(torch.cat([g.reshape(-1) for g in local])) for _ in range(world)]
     dist.all_gather(gathered, torch.cat([g.reshape(-1) for g in local]))
-    mine = torch.cat([p.grad.reshape(-1) for p in params])
+    mine = torch.cat([p.grad.reshape(-1) for p in params[:3]] + [torch.zeros(params[3].numel())])
     tmax = ddist.max_over_ranks(10.0 * (rank + 1), torch.device("cpu"))
     if rank == 0:
         torch.save({"mine": mine, "gathered": gathered, "tmax": tmax, "n3": params[3].numel()}, out)

@@ -201,3 +201,24 @@ def test_group_local_da_loss_oracle_matches_reference_methods(golden):
         torch.manual_seed(rec["rng_seed"])        # the centroid draws of the DAF flavour come from the global RNG
         val = da_oracle.group_local_da_loss(feats, cls, fore.state_dict(), back.state_dict(), rec["flavour"])
         assert abs(float(val) - rec["loss"]) <= 2e-6 * max(1.0, abs(rec["loss"])), (name, float(val), rec["loss"])
+
+
+def test_bbox_head_loss_matches_reference_loss_classes(golden):
+    """R3's box-head loss: the oracle AND the product's Shared2FCBBoxHead.loss (plain torch, device-agnostic) against the
+    values and gradients of the reference's own CrossEntropyLoss(use_sigmoid=True) / SmoothL1Loss / accuracy
+    (oracle/make_golden.bbox_head_loss_case).  The classification loss is a SUM over the (num_classes+1) channels divided by
+    the number of RoIs -- not a mean over elements."""
+    from unsupervised_domain_adaptation_object_detection_implementation_b200 import detection
+    g = golden("bbox_head_loss.pt")
+    C = g["num_classes"]
+    head = detection.Shared2FCBBoxHead(in_channels=4, fc_out_channels=8, num_classes=C)
+    for fn in (lambda a, b: da_oracle.bbox_head_loss(a, b, g["labels"], g["targets"], g["pos_mask"], C),
+               lambda a, b: head.loss(a, b, g["labels"], g["targets"], g["pos_mask"])):
+        cls = g["cls_score"].clone().requires_grad_(True)
+        reg = g["bbox_pred"].clone().requires_grad_(True)
+        out = fn(cls, reg)
+        assert abs(float(out["loss_cls"]) - float(g["loss_cls"])) <= 1e-6 * float(g["loss_cls"])
+        assert abs(float(out["loss_bbox"]) - float(g["loss_bbox"])) <= 1e-6 * float(g["loss_bbox"])
+        assert abs(float(out["acc"]) - float(g["acc"])) <= 1e-4
+        (out["loss_cls"] + out["loss_bbox"]).backward()
+        assert float((cls.grad - g["dcls"]).abs().max()) <= 1e-7 and float((reg.grad - g["dreg"]).abs().max()) <= 1e-7

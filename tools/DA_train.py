@@ -113,6 +113,7 @@ def main():
     params = ddist.trainable_parameters(model, unused)
     optimizer = optim.FusedSGD(params, lr=ocfg.get("lr", 1e-3), momentum=ocfg.get("momentum", 0.9), weight_decay=ocfg.get("weight_decay", 0.0))
     reducer = ddist.OverlappedGradAllReduce(params) if world > 1 else None
+    schedule = optim.StepLrSchedule(optimizer.lr, cfg.get("lr_config"))      # step decay + linear warm-up (schedule_1x.py)
 
     start_iter, meta = 0, dict(seed=args.seed, config=os.path.abspath(args.config), exp_name=os.path.basename(args.config))
     if args.resume_from or args.load_from:
@@ -123,7 +124,8 @@ def main():
         if args.resume_from:
             start_iter = int(ck.get("meta", {}).get("iter", 0))
             for p, buf in zip(params, ck.get("optimizer", {}).get("momentum", [])):
-                optimizer.state[id(p)] = buf.to(dev)
+                if buf.numel() == p.numel():          # a parameter that never had a gradient has no momentum buffer yet
+                    optimizer.state[id(p)] = buf.to(dev)
             optimizer.steps = start_iter
 
     def save(it):
@@ -147,6 +149,7 @@ def main():
             if it >= args.iters:
                 break
             batch = collate([dataset[i] for i in order[k:k + args.samples_per_gpu]], dev)
+            optimizer.lr = schedule(it, epoch)          # eager loop: the kernels take lr as a launch argument
             out = model.train_step(batch, optimizer)
             out["loss"].backward()
             if reducer is not None:
@@ -157,7 +160,7 @@ def main():
             if rank == 0 and it % args.log_interval == 0:
                 lv = out["log_vars"]
                 da = {k: round(float(v), 5) for k, v in lv.items() if "da_loss" in k or "consistency" in k or "patch" in k}
-                print(f"iter {it}/{args.iters} loss {float(lv['loss']):.4f} DA {da} domains {batch['gt_da']} "
+                print(f"iter {it}/{args.iters} lr {optimizer.lr:.3e} loss {float(lv['loss']):.4f} DA {da} domains {batch['gt_da']} "
                       f"({(time.time() - t0) / max(1, it - start_iter):.2f} s/iter)", flush=True)
             if args.checkpoint_interval and it % args.checkpoint_interval == 0:
                 save(it)

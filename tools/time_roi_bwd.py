@@ -24,12 +24,12 @@ def timeit(tag, n=10):
     print(f"{tag}: {e0.elapsed_time(e1)/n*1000:.0f} us per backward", flush=True)
 g_tc = grad().float()
 timeit("tc")
-os.environ["DA_ROI_NO_TC"] = "1"
+F_.set_option("roi_no_tc", 1)
 g_cc = grad().float()
 timeit("cuda-core")
 err = (g_tc - g_cc).norm() / g_cc.norm()
 print("rel fro err tc vs cuda-core:", float(err), "max abs", float((g_tc - g_cc).abs().max()), "ref max", float(g_cc.abs().max()))
-del os.environ["DA_ROI_NO_TC"]
+F_.set_option("roi_no_tc", 0)
 for d in (15, 32, 64):
-    os.environ["DA_ROI_BWD_DBG"] = str(d)
+    F_.set_option("roi_bwd_dbg", d)
     timeit(f"dbg={d}")

@@ -14,7 +14,7 @@ out = F_.roi_align(feat, rois, 7, 1 / 16)
 for _ in range(3): torch.autograd.grad(out, feat, cot, retain_graph=True)
 ncta = 32 * 8 * N
 buf = torch.zeros(ncta + 64, 8, dtype=torch.int64, device=dev)
-os.environ["DA_ROI_BWD_TRACE"] = str(buf.data_ptr())
+F_.set_option("roi_bwd_trace", buf.data_ptr())
 torch.autograd.grad(out, feat, cot, retain_graph=True)
 torch.cuda.synchronize()
 pt = buf[ncta:].cpu().double()

@@ -16,8 +16,9 @@ LIB_PATH = os.path.join(_HERE, "libda_b200.so")
 # enums of include/da_b200.h
 DA_F32, DA_BF16 = 0, 1
 ROI_OUT_RCHW, ROI_OUT_RHWC = 0, 1
-ENGINE_SIMT_F32, ENGINE_UMMA_BF16, ENGINE_UMMA_BF16X3 = 0, 1, 2
-ENGINES = {"simt_f32": ENGINE_SIMT_F32, "umma_bf16": ENGINE_UMMA_BF16, "umma_bf16x3": ENGINE_UMMA_BF16X3}
+ENGINE_SIMT_F32, ENGINE_UMMA_BF16, ENGINE_UMMA_BF16X3, ENGINE_UMMA_BF16X6 = 0, 1, 2, 3
+ENGINES = {"simt_f32": ENGINE_SIMT_F32, "umma_bf16": ENGINE_UMMA_BF16, "umma_bf16x3": ENGINE_UMMA_BF16X3,
+           "umma_bf16x6": ENGINE_UMMA_BF16X6}
 
 
 class ConvDesc(Structure):
@@ -65,6 +66,7 @@ SIGNATURES = {
     "da_last_error": (c_char_p, []),
     "da_launch_count": (L, []),
     "da_launch_count_reset": (None, []),
+    "da_set_option": (I, [c_char_p, L]),
     "da_grl_backward": (I, [P, P, I, L, F, P]),
     "da_nchw_to_nhwc": (I, [P, I, P, I, I, I, I, I, P]),
     "da_nhwc_to_nchw": (I, [P, I, P, I, I, I, I, I, P]),

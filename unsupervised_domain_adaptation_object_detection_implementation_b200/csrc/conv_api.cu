@@ -1,6 +1,6 @@
 // C-ABI dispatch of the dense contractions (da_conv_*) onto the two engines:
 //   DA_ENGINE_SIMT_F32            -> simt_conv.cu  (fp32 FMA parity engine)
-//   DA_ENGINE_UMMA_BF16 / _BF16X3 -> umma_conv.cu  (tcgen05 + TMEM + TMA implicit GEMM)
+//   DA_ENGINE_UMMA_BF16 / _BF16X3 / _BF16X6 -> umma_conv.cu  (tcgen05 + TMEM + TMA implicit GEMM)
 #include "da_common.cuh"
 
 namespace da {
@@ -32,7 +32,7 @@ static int check_desc(const da_conv_desc* d, const char* who) {
              "%s: bad filter %dx%d stride %d pad %d", who, d->KH, d->KW, d->stride, d->pad);
   DA_REQUIRE(d->H + 2 * d->pad >= d->KH && d->W + 2 * d->pad >= d->KW, DA_ERR_INVALID_ARG,
              "%s: filter larger than padded input", who);
-  DA_REQUIRE(d->engine >= DA_ENGINE_SIMT_F32 && d->engine <= DA_ENGINE_UMMA_BF16X3, DA_ERR_INVALID_ARG,
+  DA_REQUIRE(d->engine >= DA_ENGINE_SIMT_F32 && d->engine <= DA_ENGINE_UMMA_BF16X6, DA_ERR_INVALID_ARG,
              "%s: unknown engine %d", who, d->engine);
   return DA_OK;
 }

@@ -18,9 +18,41 @@ namespace da {
 void set_error(const char* fmt, ...);
 extern std::atomic<int64_t> g_launches;
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
-// Device-resident dropout step counter (da_set_dropout_counter): kernels add *counter to their seed, so a
-// CUDA-graph replay of a captured step still draws fresh masks when the host bumps the counter on device.
-extern const unsigned long long* g_seed_counter;
+// ---- per-device state (indexed by the CURRENT device of the calling thread; one process may drive several GPUs) -----
+// seed_counter: device-resident dropout step counter (da_set_dropout_counter): kernels add *counter to their seed, so a
+//   CUDA-graph replay of a captured step still draws fresh masks when the host bumps the counter on device.
+// sm_limit: SM budget of the persistent kernels (da_set_sm_limit).
+constexpr int kMaxDevices = 64;
+struct DeviceState {
+  const unsigned long long* seed_counter;
+  int sm_limit;
+  int sm_count;   // cached cudaDevAttrMultiProcessorCount (0 = not queried yet)
+};
+extern DeviceState g_dev[kMaxDevices];
+inline int cur_dev() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+inline DeviceState& dev_state() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return g_dev[(dev >= 0 && dev < kMaxDevices) ? dev : 0];
+}
+#define g_seed_counter (da::dev_state().seed_counter)
+
+// ---- debug / test options: read ONCE from the environment when the library is loaded (never in a launch path);
+// da_set_option changes one at run time (test hook: e.g. force the CUDA-core RoIAlign path).
+struct Options {
+  int roi_no_tc;      // DA_ROI_NO_TC      : bf16 RoIAlign on the CUDA-core kernels instead of tcgen05
+  int umma_no_bn64;   // DA_UMMA_NO_BN64   : no 64-wide GEMM tiles
+  int umma_no_2sm;    // DA_UMMA_NO_2SM    : no cta_group::2 pair MMA
+  int no_pdl;         // DA_NO_PDL         : no programmatic dependent launch
+  int umma_dbg;       // DA_UMMA_DBG       : timing experiments (results are wrong when set)
+  int roi_bwd_dbg;    // DA_ROI_BWD_DBG    : timing experiments (results are wrong when set)
+  unsigned long long roi_bwd_trace;   // DA_ROI_BWD_TRACE: device address of a [ctas][8] u64 trace buffer (tools/trace_roi_bwd.py)
+};
+extern Options g_opt;
 __device__ __forceinline__ unsigned long long effective_seed(unsigned long long seed, const unsigned long long* ctr) {
   return ctr ? seed + *ctr : seed;
 }
@@ -56,20 +88,20 @@ __device__ __forceinline__ unsigned long long effective_seed(unsigned long long 
 
 // SM budget of the persistent kernels (da_set_sm_limit): while a NCCL all-reduce holds some SMs, a persistent grid of
 // one CTA per PHYSICAL SM would run in two waves; the caller lowers the budget for the kernels it overlaps.
-extern int g_sm_limit;
 inline int num_sms_physical() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
+  DeviceState& d = dev_state();
+  if (d.sm_count == 0) {
+    int dev = 0, n = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+    d.sm_count = n > 0 ? n : 148;
   }
-  return n;
+  return d.sm_count;
 }
 inline int num_sms() {
   const int n = num_sms_physical();
-  return (g_sm_limit > 0 && g_sm_limit < n) ? g_sm_limit : n;
+  const int lim = dev_state().sm_limit;
+  return (lim > 0 && lim < n) ? lim : n;
 }
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

@@ -4,13 +4,31 @@
 // backward (instance_da.py:20-23) and the exported dropout keep-mask.
 #include "da_common.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 namespace da {
 
 static thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
-const unsigned long long* g_seed_counter = nullptr;
-int g_sm_limit = 0;
+DeviceState g_dev[kMaxDevices] = {};
+
+static int env_int(const char* name) {
+  const char* e = getenv(name);
+  return e ? (e[0] ? atoi(e) ? atoi(e) : 1 : 1) : 0;     // set (even to "" or a non-number) = 1
+}
+static Options read_options() {
+  Options o;
+  memset(&o, 0, sizeof(o));
+  o.roi_no_tc = env_int("DA_ROI_NO_TC");
+  o.umma_no_bn64 = env_int("DA_UMMA_NO_BN64");
+  o.umma_no_2sm = env_int("DA_UMMA_NO_2SM");
+  o.no_pdl = env_int("DA_NO_PDL");
+  { const char* e = getenv("DA_UMMA_DBG"); o.umma_dbg = e ? atoi(e) : 0; }
+  { const char* e = getenv("DA_ROI_BWD_DBG"); o.roi_bwd_dbg = e ? atoi(e) : 0; }
+  { const char* e = getenv("DA_ROI_BWD_TRACE"); o.roi_bwd_trace = e ? strtoull(e, nullptr, 0) : 0ull; }
+  return o;
+}
+Options g_opt = read_options();     // library load time: the launch paths never call getenv
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -238,12 +256,25 @@ extern "C" int da_sgd_step_multi(const da_sgd_entry* entries, int n_entries, con
   return DA_OK;
 }
 
-extern "C" int da_set_sm_limit(int n) {
-  g_sm_limit = n > 0 ? n : 0;
+extern "C" int da_set_sm_limit(int n) {        // applies to the calling thread's CURRENT device
+  dev_state().sm_limit = n > 0 ? n : 0;
   return DA_OK;
 }
 
-extern "C" int da_set_dropout_counter(const void* counter_dev) {
-  g_seed_counter = (const unsigned long long*)counter_dev;
+extern "C" int da_set_dropout_counter(const void* counter_dev) {   // per device, like the counter itself
+  dev_state().seed_counter = (const unsigned long long*)counter_dev;
+  return DA_OK;
+}
+
+extern "C" int da_set_option(const char* name, long long value) {
+  DA_REQUIRE(name != nullptr, DA_ERR_INVALID_ARG, "set_option: null name");
+  if (!strcmp(name, "roi_no_tc")) g_opt.roi_no_tc = (int)value;
+  else if (!strcmp(name, "umma_no_bn64")) g_opt.umma_no_bn64 = (int)value;
+  else if (!strcmp(name, "umma_no_2sm")) g_opt.umma_no_2sm = (int)value;
+  else if (!strcmp(name, "no_pdl")) g_opt.no_pdl = (int)value;
+  else if (!strcmp(name, "umma_dbg")) g_opt.umma_dbg = (int)value;
+  else if (!strcmp(name, "roi_bwd_dbg")) g_opt.roi_bwd_dbg = (int)value;
+  else if (!strcmp(name, "roi_bwd_trace")) g_opt.roi_bwd_trace = (unsigned long long)value;
+  else DA_REQUIRE(false, DA_ERR_INVALID_ARG, "set_option: unknown option '%s'", name);
   return DA_OK;
 }

@@ -748,7 +748,7 @@ static int launch_fwd(const void* feat, int N, int C, int H, int W, int R, const
   dim3 grid((C + FWD_CB - 1) / FWD_CB, R);
   // tensor-core path: bf16 features, reference layout, 16-byte granular channel runs
   if (sizeof(TIn) == 2 && layout == DA_ROI_OUT_RCHW && C % 64 == 0 && ((uintptr_t)feat & 15) == 0 &&
-      ((uintptr_t)out & 15) == 0 && getenv("DA_ROI_NO_TC") == nullptr)
+      ((uintptr_t)out & 15) == 0 && !g_opt.roi_no_tc)
     return roi_align_fwd_tc(feat, N, C, H, W, R, ws, out, sizeof(TOut) == 2 ? DA_BF16 : DA_F32, st);
   const int skip_tc = 0;
   // bulk-async path: every per-pixel channel run and the result tile must be 16-byte granular
@@ -811,7 +811,7 @@ static int launch_bwd(const void* g, int layout, int N, int C, int H, int W, int
   dim3 grid(tiles_x * tiles_y, (C + BWD_CB - 1) / BWD_CB, N);
   DA_REQUIRE(grid.y <= 65535 && grid.z <= 65535, DA_ERR_UNSUPPORTED, "roi_align_backward: grid too large");
   // tensor-core path: bf16 gradients in the reference layout, 16-byte granular channel runs
-  if (sizeof(TG) == 2 && layout == DA_ROI_OUT_RCHW && C % 8 == 0 && ((uintptr_t)g & 15) == 0 && getenv("DA_ROI_NO_TC") == nullptr)
+  if (sizeof(TG) == 2 && layout == DA_ROI_OUT_RCHW && C % 8 == 0 && ((uintptr_t)g & 15) == 0 && !g_opt.roi_no_tc)
     return roi_align_bwd_tc(g, N, C, H, W, R, ws, gin_v, gin_dtype, st);
   DA_REQUIRE(gin_dtype == DA_F32, DA_ERR_UNSUPPORTED,
              "roi_align_backward: bf16 grad_input needs the tensor-core path (bf16 [R,C,7,7] gradients, C %% 8 == 0)");

@@ -363,11 +363,10 @@ static int launch_bwd_tc(const void* grad_out, int N, int C, int H, int W, int R
   const int tiles_x = (W + BT_TX - 1) / BT_TX, tiles_y = (H + BT_TY - 1) / BT_TY;
   dim3 grid(tiles_x * tiles_y, (C + BT_CH - 1) / BT_CH, N);
   DA_REQUIRE(grid.y <= 65535 && grid.z <= 65535, DA_ERR_UNSUPPORTED, "roi_align_backward tc: grid too large");
-  const char* dbg_env = getenv("DA_ROI_BWD_DBG");
-  const int dbg = dbg_env ? atoi(dbg_env) : 0;   // timing experiments only (results are wrong when set)
-  const char* tr_env = getenv("DA_ROI_BWD_TRACE");   // tools/trace_roi_bwd.py: device address of a [ctas][8] u64 buffer
-  unsigned long long* trace = tr_env ? reinterpret_cast<unsigned long long*>(strtoull(tr_env, nullptr, 0)) : nullptr;
-  static bool attr_set = false;
+  const int dbg = g_opt.roi_bwd_dbg;   // timing experiments only (results are wrong when set)
+  unsigned long long* trace = reinterpret_cast<unsigned long long*>(g_opt.roi_bwd_trace);   // tools/trace_roi_bwd.py
+  static bool attr_set_dev[kMaxDevices] = {};     // function attributes are per device
+  bool& attr_set = attr_set_dev[cur_dev()];
   if (!attr_set) {
     DA_CUDA_OK(cudaFuncSetAttribute(roi_align_bwd_tc_kernel<TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BT_SMEM));
     attr_set = true;

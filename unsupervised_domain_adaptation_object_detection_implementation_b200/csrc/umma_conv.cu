@@ -1,5 +1,5 @@
 // tcgen05 / TMEM / TMA implicit-GEMM engine for the domain-classifier convs and FC stacks
-// (DA_ENGINE_UMMA_BF16, DA_ENGINE_UMMA_BF16X3) — sm_100a only.
+// (DA_ENGINE_UMMA_BF16, DA_ENGINE_UMMA_BF16X3, DA_ENGINE_UMMA_BF16X6) — sm_100a only.
 //
 // One warp-specialised kernel serves forward and data-gradient ("NT" form: both operands
 // K-major), a second one the weight gradient ("TN" form: both operands MN-major, the
@@ -20,6 +20,10 @@
 //
 // BF16X3: fp32 operands are split x = hi + lo (bf16 each) and the kernel accumulates
 // hi*hi + hi*lo + lo*hi into the same TMEM accumulator (3 k-passes), ~2^-16 relative.
+// BF16X6: exact 3-way split x = hi + mid + lo, six product terms (everything down to 2^-16 of the
+// product; the dropped mid*lo, lo*mid, lo*lo are <= 2^-23): fp32-class results (<= 1e-5 parity bar)
+// on the tensor cores at 1/6 of the bf16 rate -- the same cost as 3xTF32 (half rate x 3 passes)
+// without a second operand format, swizzle layout and MN-major restriction set.
 #include "da_common.cuh"
 #include "da_ptx.cuh"
 #include <cuda.h>
@@ -54,12 +58,12 @@ struct TapInfo {
 
 struct NtParams {
   int dbg;                  // DA_UMMA_DBG timing experiments (results are wrong when set)
-  CUtensorMap a_map[2][4];  // [hi/lo term][parity]
-  CUtensorMap b_map[2];     // [hi/lo term]
+  CUtensorMap a_map[3][4];  // [split part hi/mid/lo][parity]
+  CUtensorMap b_map[3];     // [split part]
   TapInfo taps[MAX_TAPS];
   int num_taps, kchunks;    // k iterations per term = num_taps * kchunks
   int num_terms;
-  int term_a[3], term_b[3];
+  int term_a[6], term_b[6];
   int b_mn_major;           // B tile is [k rows][n contiguous] (weights read untransposed for dgrad)
   int b_col0;               // MN-major B: column offset of n = 0 inside the B matrix (unused)
   int flat;                 // A is a flat [M,K] matrix (1x1 / FC)
@@ -503,11 +507,11 @@ constexpr int WK = 64;  // pixels per k-step
 constexpr int W_A_BYTES = BM * WK * 2;
 
 struct TnParams {
-  CUtensorMap a_map[2];     // dZ [hi/lo]: (Cout, OW, OH, N) or flat (Cout, M)
-  CUtensorMap b_map[2][4];  // X  [hi/lo][parity]
+  CUtensorMap a_map[3];     // dZ [split part]: (Cout, OW, OH, N) or flat (Cout, M)
+  CUtensorMap b_map[3][4];  // X  [split part][parity]
   TapInfo taps[MAX_TAPS];
   int num_taps, num_terms;
-  int term_a[3], term_b[3];
+  int term_a[6], term_b[6];
   int flat;
   int BH, BW;               // pixel patch per k-step (BH*BW == 64)
   int tiles_h, tiles_w, NB; // patch grid
@@ -762,6 +766,21 @@ __global__ void split_hi_lo_kernel(const float* __restrict__ src, __nv_bfloat16*
   }
 }
 
+// 3-way split x = hi + mid + lo (bf16 each, 8 significant bits apiece: EXACT for every normal fp32 value)
+__global__ void split_hi_mid_lo_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi,
+                                       __nv_bfloat16* __restrict__ mid, __nv_bfloat16* __restrict__ lo, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = src[i];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(h);          // exact
+    const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(m);         // exact
+    hi[i] = h;
+    mid[i] = m;
+    lo[i] = __float2bfloat16_rn(r2);
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
@@ -874,8 +893,8 @@ static size_t part_bytes(const Geom& g) {
 static size_t stage_bytes(const Geom& g) {
   const size_t y = (size_t)g.N * g.OH * g.OW * g.Cout, x = (size_t)g.N * g.H * g.W * g.Cin;
   const size_t w = (size_t)g.Cout * g.KH * g.KW * g.Cin;
-  // worst case (wgrad BF16X3): hi+lo of x and of dz; forward/dgrad: hi+lo of one activation + hi+lo weights
-  return align_up(2 * 2 * (x + y) + 2 * 2 * w + 1024, 256);
+  // worst case (wgrad BF16X6): hi+mid+lo of x and of dz; forward/dgrad: 3 parts of one activation + 3 parts of the weights
+  return align_up(3 * 2 * (x + y) + 3 * 2 * w + 4096, 256);
 }
 size_t umma_workspace_bytes(const da_conv_desc* d) {
   if (d->engine == DA_ENGINE_SIMT_F32) return 0;
@@ -889,40 +908,51 @@ static int ew_blocks(long long n) {
   return (int)(b > cap ? cap : (b < 1 ? 1 : b));
 }
 
-// Prepare bf16 operand(s) from the caller's tensor: returns hi (and lo for BF16X3) pointers.
-static int prep_operand(const void* src, int dtype, long long n, int engine, uint8_t*& stage, const __nv_bfloat16** hi,
-                        const __nv_bfloat16** lo, cudaStream_t st) {
-  *lo = nullptr;
+// Prepare the bf16 operand part(s) of the caller's tensor: parts[0] = hi (BF16), + lo (BF16X3), + mid, lo (BF16X6).
+struct Parts {
+  const __nv_bfloat16* p[3];
+  int n;
+};
+static int prep_operand(const void* src, int dtype, long long n, int engine, uint8_t*& stage, Parts* out, cudaStream_t st) {
+  out->p[0] = out->p[1] = out->p[2] = nullptr;
+  out->n = 1;
   if (dtype == DA_BF16) {
-    DA_REQUIRE(engine == DA_ENGINE_UMMA_BF16, DA_ERR_UNSUPPORTED, "BF16X3 engine needs fp32 operands");
-    *hi = (const __nv_bfloat16*)src;
+    DA_REQUIRE(engine == DA_ENGINE_UMMA_BF16, DA_ERR_UNSUPPORTED, "the split-precision engines need fp32 operands");
+    out->p[0] = (const __nv_bfloat16*)src;
     return DA_OK;
   }
-  __nv_bfloat16* h = (__nv_bfloat16*)stage;
-  stage += align_up((size_t)n * 2, 256);
-  if (engine == DA_ENGINE_UMMA_BF16X3) {
-    __nv_bfloat16* l = (__nv_bfloat16*)stage;
+  const int nparts = engine == DA_ENGINE_UMMA_BF16X6 ? 3 : (engine == DA_ENGINE_UMMA_BF16X3 ? 2 : 1);
+  __nv_bfloat16* part[3] = {nullptr, nullptr, nullptr};
+  for (int i = 0; i < nparts; ++i) {
+    part[i] = (__nv_bfloat16*)stage;
     stage += align_up((size_t)n * 2, 256);
-    split_hi_lo_kernel<<<ew_blocks(n), 256, 0, st>>>((const float*)src, h, l, n);
-    DA_LAUNCH_CHECK();
-    *lo = l;
-  } else {
-    cast_to_bf16_kernel<<<ew_blocks(n), 256, 0, st>>>((const float*)src, h, n);
-    DA_LAUNCH_CHECK();
   }
-  *hi = h;
+  if (nparts == 3) split_hi_mid_lo_kernel<<<ew_blocks(n), 256, 0, st>>>((const float*)src, part[0], part[1], part[2], n);
+  else if (nparts == 2) split_hi_lo_kernel<<<ew_blocks(n), 256, 0, st>>>((const float*)src, part[0], part[1], n);
+  else cast_to_bf16_kernel<<<ew_blocks(n), 256, 0, st>>>((const float*)src, part[0], n);
+  DA_LAUNCH_CHECK();
+  for (int i = 0; i < nparts; ++i) out->p[i] = part[i];
+  out->n = nparts;
   return DA_OK;
 }
 
+// Product terms of the split-precision engines (indices into the operand parts 0 = hi, 1 = mid / lo, 2 = lo).
+//   BF16X3: x = hi + lo (16 bits):  hi*hi + hi*lo + lo*hi                      (dropped: lo*lo ~ 2^-16)
+//   BF16X6: x = hi + mid + lo (24 bits, exact): hh + hm + mh + hl + lh + mm    (dropped: ml, lm, ll ~ 2^-24: fp32 class)
+// Small terms first: they are accumulated before the fp32 sum grows.
 static void set_terms(int engine, int* num_terms, int* ta, int* tb) {
-  if (engine == DA_ENGINE_UMMA_BF16X3) {
+  for (int i = 0; i < 6; ++i) ta[i] = tb[i] = 0;
+  if (engine == DA_ENGINE_UMMA_BF16X6) {
+    *num_terms = 6;
+    const int a[6] = {1, 0, 2, 0, 1, 0}, b[6] = {1, 2, 0, 1, 0, 0};
+    for (int i = 0; i < 6; ++i) { ta[i] = a[i]; tb[i] = b[i]; }
+  } else if (engine == DA_ENGINE_UMMA_BF16X3) {
     *num_terms = 3;
-    ta[0] = 0; tb[0] = 0;  // hi*hi
-    ta[1] = 0; tb[1] = 1;  // hi*lo
-    ta[2] = 1; tb[2] = 0;  // lo*hi
+    ta[0] = 0; tb[0] = 1;  // hi*lo
+    ta[1] = 1; tb[1] = 0;  // lo*hi
+    ta[2] = 0; tb[2] = 0;  // hi*hi
   } else {
     *num_terms = 1;
-    ta[0] = tb[0] = 0; ta[1] = tb[1] = ta[2] = tb[2] = 0;
   }
 }
 
@@ -934,7 +964,7 @@ static inline int choose_bn(int ncols, long long m_rows, long long k_iters) {
   const bool short_k = k_iters < 64;
   if (ncols > 128 && (mt * ((ncols + 255) / 256) >= num_sms() / 2 || !short_k)) return 256;
   // short-K problems that do not fill the machine with 128-wide tiles: 128x64 tiles (twice the CTAs)
-  if (short_k && mt * ((ncols + 127) / 128) < num_sms() / 2 && getenv("DA_UMMA_NO_BN64") == nullptr) return 64;
+  if (short_k && mt * ((ncols + 127) / 128) < num_sms() / 2 && !g_opt.umma_no_bn64) return 64;
   return 128;
 }
 
@@ -959,7 +989,8 @@ static int launch_nt_t(NtParams& P, long long pixel_tiles, int k_iters, void* ws
   const long long total = super_tiles * n_tiles * splits;   // cluster-level tile units
   DA_REQUIRE(total * kCluster <= 0x7fffffffll, DA_ERR_UNSUPPORTED, "umma: too many tiles");
   auto kern = umma_nt_kernel<kBN, kCluster, k2SM>;
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDevices] = {};     // function attributes are per device
+  bool& attr_set = attr_set_dev[cur_dev()];
   if (!attr_set) {
     DA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<kBN>::SMEM));
     attr_set = true;
@@ -977,9 +1008,10 @@ static int launch_nt_t(NtParams& P, long long pixel_tiles, int k_iters, void* ws
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see pdl_wait() in the kernel
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = getenv("DA_NO_PDL") ? 1 : 2;
+  cfg.numAttrs = g_opt.no_pdl ? 1 : 2;
   // persistent grid = the clusters that are co-resident (GPC sizes need not be multiples of the cluster size)
-  static int hw_clusters = 0;
+  static int hw_clusters_dev[kMaxDevices] = {};
+  int& hw_clusters = hw_clusters_dev[cur_dev()];
   if (hw_clusters == 0) {
     cfg.gridDim = dim3((num_sms_physical() / kCluster) * kCluster);
     int n = 0;
@@ -1006,7 +1038,7 @@ static int launch_nt_t(NtParams& P, long long pixel_tiles, int k_iters, void* ws
 //   pair (2 CTAs, ONE cta_group::2 MMA over 256 pixel rows) when the pixel tiles pair up and the tile is 256 wide;
 //   else 2 CTAs sharing the weight tile through TMA multicast; else single CTAs.
 static inline bool nt_pair_mma(int bn, long long pixel_tiles) {
-  return bn == 256 && pixel_tiles >= 2 && pixel_tiles % 2 == 0 && getenv("DA_UMMA_NO_2SM") == nullptr;
+  return bn == 256 && pixel_tiles >= 2 && pixel_tiles % 2 == 0 && !g_opt.umma_no_2sm;
 }
 static inline int nt_cluster(int bn, long long pixel_tiles) {
   (void)bn;
@@ -1014,7 +1046,7 @@ static inline int nt_cluster(int bn, long long pixel_tiles) {
 }
 
 static int launch_nt(NtParams& P, int bn, long long pixel_tiles, int k_iters, void* ws_part, size_t part_cap, cudaStream_t st) {
-  { const char* e = getenv("DA_UMMA_DBG"); P.dbg = e ? atoi(e) : 0; }
+  P.dbg = g_opt.umma_dbg;
   // concurrently running tiles share the operand whose index is NOT the fastest one; stream the bigger operand once
   P.pix_fast = ((long long)P.Cout > pixel_tiles * BM) ? 1 : 0;
   if (nt_pair_mma(bn, pixel_tiles)) return launch_nt_t<256, 2, true>(P, pixel_tiles, k_iters, ws_part, part_cap, st);
@@ -1037,10 +1069,10 @@ int umma_conv_forward(const da_conv_desc* d, const void* x, const void* w, const
   DA_REQUIRE(g.s <= 2, DA_ERR_UNSUPPORTED, "umma conv: stride %d not built (1 or 2)", g.s);
   DA_REQUIRE(ws && ws_bytes >= umma_workspace_bytes(d), DA_ERR_WORKSPACE, "umma conv forward: workspace too small (%zu < %zu)", ws_bytes, umma_workspace_bytes(d));
   uint8_t* stage = (uint8_t*)ws + part_bytes(g);
-  const __nv_bfloat16 *xh, *xl, *wh, *wl;
-  int rc = prep_operand(x, d->x_dtype, (long long)g.N * g.H * g.W * g.Cin, d->engine, stage, &xh, &xl, st);
+  Parts xs, wsrc;
+  int rc = prep_operand(x, d->x_dtype, (long long)g.N * g.H * g.W * g.Cin, d->engine, stage, &xs, st);
   if (rc) return rc;
-  rc = prep_operand(w, d->x_dtype, (long long)g.Cout * g.KH * g.KW * g.Cin, d->engine, stage, &wh, &wl, st);
+  rc = prep_operand(w, d->x_dtype, (long long)g.Cout * g.KH * g.KW * g.Cin, d->engine, stage, &wsrc, st);
   if (rc) return rc;
 
   NtParams P;
@@ -1053,18 +1085,16 @@ int umma_conv_forward(const da_conv_desc* d, const void* x, const void* w, const
   const int Ktot = g.KH * g.KW * g.Cin;
   const int bn = choose_bn(g.Cout, (long long)g.N * g.OH * g.OW, (Ktot + BK - 1) / BK);
   long long pixel_tiles;
-  const __nv_bfloat16* xs[2] = {xh, xl};
-  const __nv_bfloat16* wsrc[2] = {wh, wl};
   if (is_flat(g)) {
     P.flat = 1;
     P.M_flat = (long long)g.N * g.H * g.W;
     P.num_taps = 1;
     P.taps[0] = TapInfo{0, 0, 0, 0};
-    for (int t = 0; t < (xl ? 2 : 1); ++t) {
+    for (int t = 0; t < xs.n; ++t) {
       const uint64_t dims[2] = {(uint64_t)g.Cin, (uint64_t)P.M_flat};
       const uint64_t strides[1] = {(uint64_t)g.Cin * 2};
       const uint32_t box[2] = {BK, BM};
-      rc = encode_map(&P.a_map[t][0], xs[t], 2, dims, strides, box);
+      rc = encode_map(&P.a_map[t][0], xs.p[t], 2, dims, strides, box);
       if (rc) return rc;
     }
     pixel_tiles = (P.M_flat + BM - 1) / BM;
@@ -1075,8 +1105,8 @@ int umma_conv_forward(const da_conv_desc* d, const void* x, const void* w, const
     P.bw_shift = ilog2(P.BW);
     P.tiles_h = (g.OH + P.BH - 1) / P.BH; P.tiles_w = (g.OW + P.BW - 1) / P.BW;
     bool present[4] = {false, false, false, false};
-    for (int t = 0; t < (xl ? 2 : 1); ++t) {
-      rc = make_parity_maps(P.a_map[t], present, xs[t], g.N, g.H, g.W, g.Cin, g.s, P.BH, P.BW);
+    for (int t = 0; t < xs.n; ++t) {
+      rc = make_parity_maps(P.a_map[t], present, xs.p[t], g.N, g.H, g.W, g.Cin, g.s, P.BH, P.BW);
       if (rc) return rc;
     }
     int nt = 0;
@@ -1089,12 +1119,12 @@ int umma_conv_forward(const da_conv_desc* d, const void* x, const void* w, const
     P.num_taps = nt;
     pixel_tiles = (long long)g.N * P.tiles_h * P.tiles_w;
   }
-  for (int t = 0; t < (wl ? 2 : 1); ++t) {
+  for (int t = 0; t < wsrc.n; ++t) {
     // a 2-CTA cluster (pixel_tiles >= 2, see launch_nt) loads the weight tile as two multicast halves
     const uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)g.Cout};
     const uint64_t strides[1] = {(uint64_t)Ktot * 2};
     const uint32_t box[2] = {BK, (uint32_t)(bn / nt_cluster(bn, pixel_tiles))};
-    rc = encode_map(&P.b_map[t], wsrc[t], 2, dims, strides, box);
+    rc = encode_map(&P.b_map[t], wsrc.p[t], 2, dims, strides, box);
     if (rc) return rc;
   }
   return launch_nt(P, bn, pixel_tiles, P.num_terms * P.num_taps * P.kchunks, ws, part_bytes(g), st);
@@ -1108,13 +1138,12 @@ int umma_conv_backward_data(const da_conv_desc* d, const void* dz, const void* w
   DA_REQUIRE(ws && ws_bytes >= umma_workspace_bytes(d), DA_ERR_WORKSPACE, "umma dgrad: workspace too small");
   uint8_t* stage = (uint8_t*)ws + part_bytes(g);
   const int taps = g.KH * g.KW;
-  const __nv_bfloat16 *zh, *zl;
-  int rc = prep_operand(dz, d->x_dtype, (long long)g.N * g.OH * g.OW * g.Cout, d->engine, stage, &zh, &zl, st);
+  Parts zs, wsrc;
+  int rc = prep_operand(dz, d->x_dtype, (long long)g.N * g.OH * g.OW * g.Cout, d->engine, stage, &zs, st);
   if (rc) return rc;
   // B = the weights themselves, read UNtransposed as an MN-major operand: for tap t the B tile is
   // W[co, t*Cin + ci] viewed as [k = co rows][n = ci contiguous] -> boxes of (64 ci, 64 co)
-  const __nv_bfloat16 *wh, *wl;
-  rc = prep_operand(w, d->x_dtype, (long long)g.Cout * taps * g.Cin, d->engine, stage, &wh, &wl, st);
+  rc = prep_operand(w, d->x_dtype, (long long)g.Cout * taps * g.Cin, d->engine, stage, &wsrc, st);
   if (rc) return rc;
   NtParams base;
   memset(&base, 0, sizeof(base));
@@ -1126,24 +1155,22 @@ int umma_conv_backward_data(const da_conv_desc* d, const void* dz, const void* w
   base.relu = 0; base.drop_p = 0.f; base.out_scale = out_scale;
   base.y = dx; base.y_dtype = d->y_dtype; base.y_numel = (long long)g.N * g.H * g.W * g.Cin;
   const int bn = choose_bn(g.Cin, (long long)g.N * g.H * g.W, ((long long)taps * g.Cout + BK - 1) / BK);
-  const __nv_bfloat16* wsrc[2] = {wh, wl};
-  const __nv_bfloat16* zs[2] = {zh, zl};
-  for (int t = 0; t < (wl ? 2 : 1); ++t) {
+  for (int t = 0; t < wsrc.n; ++t) {
     const uint64_t dims[2] = {(uint64_t)taps * g.Cin, (uint64_t)g.Cout};
     const uint64_t strides[1] = {(uint64_t)taps * g.Cin * 2};
     const uint32_t box[2] = {64, 64};
-    rc = encode_map(&base.b_map[t], wsrc[t], 2, dims, strides, box);
+    rc = encode_map(&base.b_map[t], wsrc.p[t], 2, dims, strides, box);
     if (rc) return rc;
   }
   if (is_flat(g)) {
     NtParams P = base;
     P.flat = 1; P.M_flat = (long long)g.N * g.H * g.W; P.num_taps = 1; P.taps[0] = TapInfo{0, 0, 0, 0};
     P.os = 1;
-    for (int t = 0; t < (zl ? 2 : 1); ++t) {
+    for (int t = 0; t < zs.n; ++t) {
       const uint64_t dims[2] = {(uint64_t)g.Cout, (uint64_t)P.M_flat};
       const uint64_t strides[1] = {(uint64_t)g.Cout * 2};
       const uint32_t box[2] = {BK, BM};
-      rc = encode_map(&P.a_map[t][0], zs[t], 2, dims, strides, box);
+      rc = encode_map(&P.a_map[t][0], zs.p[t], 2, dims, strides, box);
       if (rc) return rc;
     }
     return launch_nt(P, bn, (P.M_flat + BM - 1) / BM, P.num_terms * P.kchunks, ws, part_bytes(g), st);
@@ -1160,8 +1187,8 @@ int umma_conv_backward_data(const da_conv_desc* d, const void* dz, const void* w
       P.bw_shift = ilog2(P.BW);
       P.tiles_h = (P.TH + P.BH - 1) / P.BH; P.tiles_w = (P.TW + P.BW - 1) / P.BW;
       bool present[4];
-      for (int t = 0; t < (zl ? 2 : 1); ++t) {
-        rc = make_parity_maps(P.a_map[t], present, zs[t], g.N, g.OH, g.OW, g.Cout, 1, P.BH, P.BW);
+      for (int t = 0; t < zs.n; ++t) {
+        rc = make_parity_maps(P.a_map[t], present, zs.p[t], g.N, g.OH, g.OW, g.Cout, 1, P.BH, P.BW);
         if (rc) return rc;
       }
       int nt = 0;
@@ -1184,7 +1211,8 @@ static int launch_tn_t(const TnParams& P, int co_tiles, int ci_tiles, int splits
   const long long total = co_super * ci_tiles * P.num_taps * splits;   // cluster-level tile units
   DA_REQUIRE(total * kCluster <= 0x7fffffffll, DA_ERR_UNSUPPORTED, "umma wgrad: too many tiles");
   auto kern = umma_tn_kernel<kBN, kCluster>;
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDevices] = {};     // function attributes are per device
+  bool& attr_set = attr_set_dev[cur_dev()];
   if (!attr_set) {
     DA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<kBN>::SMEM));
     attr_set = true;
@@ -1202,9 +1230,10 @@ static int launch_tn_t(const TnParams& P, int co_tiles, int ci_tiles, int splits
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see pdl_wait() in the kernel
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = getenv("DA_NO_PDL") ? 1 : 2;
+  cfg.numAttrs = g_opt.no_pdl ? 1 : 2;
   // persistent grid = the clusters that are co-resident (GPC sizes need not be multiples of the cluster size)
-  static int hw_clusters = 0;
+  static int hw_clusters_dev[kMaxDevices] = {};
+  int& hw_clusters = hw_clusters_dev[cur_dev()];
   if (hw_clusters == 0) {
     cfg.gridDim = dim3((num_sms_physical() / kCluster) * kCluster);
     int n = 0;
@@ -1238,10 +1267,10 @@ int umma_conv_backward_weight(const da_conv_desc* d, const void* x, const void* 
   DA_REQUIRE(g.KH * g.KW <= MAX_TAPS && g.s <= 2, DA_ERR_UNSUPPORTED, "umma wgrad: unsupported filter/stride");
   DA_REQUIRE(ws && ws_bytes >= umma_workspace_bytes(d), DA_ERR_WORKSPACE, "umma wgrad: workspace too small");
   uint8_t* stage = (uint8_t*)ws + part_bytes(g);
-  const __nv_bfloat16 *xh, *xl, *zh, *zl;
-  int rc = prep_operand(x, d->x_dtype, (long long)g.N * g.H * g.W * g.Cin, d->engine, stage, &xh, &xl, st);
+  Parts xs, zs;
+  int rc = prep_operand(x, d->x_dtype, (long long)g.N * g.H * g.W * g.Cin, d->engine, stage, &xs, st);
   if (rc) return rc;
-  rc = prep_operand(dz, d->x_dtype, (long long)g.N * g.OH * g.OW * g.Cout, d->engine, stage, &zh, &zl, st);
+  rc = prep_operand(dz, d->x_dtype, (long long)g.N * g.OH * g.OW * g.Cout, d->engine, stage, &zs, st);
   if (rc) return rc;
 
   TnParams P;
@@ -1249,20 +1278,18 @@ int umma_conv_backward_weight(const da_conv_desc* d, const void* x, const void* 
   set_terms(d->engine, &P.num_terms, P.term_a, P.term_b);
   P.Cout = g.Cout; P.Cin = g.Cin;
   P.dw_numel = (long long)g.Cout * g.KH * g.KW * g.Cin;
-  const __nv_bfloat16* xs[2] = {xh, xl};
-  const __nv_bfloat16* zs[2] = {zh, zl};
   long long patches;
   if (is_flat(g)) {
     P.flat = 1; P.M_flat = (long long)g.N * g.H * g.W; P.num_taps = 1; P.taps[0] = TapInfo{0, 0, 0, 0};
-    for (int t = 0; t < (zl ? 2 : 1); ++t) {
+    for (int t = 0; t < zs.n; ++t) {
       const uint64_t da_[2] = {(uint64_t)g.Cout, (uint64_t)P.M_flat};
       const uint64_t sa[1] = {(uint64_t)g.Cout * 2};
       const uint32_t box[2] = {64, WK};
-      rc = encode_map(&P.a_map[t], zs[t], 2, da_, sa, box);
+      rc = encode_map(&P.a_map[t], zs.p[t], 2, da_, sa, box);
       if (rc) return rc;
       const uint64_t db[2] = {(uint64_t)g.Cin, (uint64_t)P.M_flat};
       const uint64_t sb[1] = {(uint64_t)g.Cin * 2};
-      rc = encode_map(&P.b_map[t][0], xs[t], 2, db, sb, box);
+      rc = encode_map(&P.b_map[t][0], xs.p[t], 2, db, sb, box);
       if (rc) return rc;
     }
     patches = (P.M_flat + WK - 1) / WK;
@@ -1271,12 +1298,12 @@ int umma_conv_backward_weight(const da_conv_desc* d, const void* x, const void* 
     pick_patch(g.OH, g.OW, WK, &P.BH, &P.BW);
     P.tiles_h = (g.OH + P.BH - 1) / P.BH; P.tiles_w = (g.OW + P.BW - 1) / P.BW; P.NB = g.N;
     bool present[4] = {false, false, false, false}, pz[4];
-    for (int t = 0; t < (zl ? 2 : 1); ++t) {
+    for (int t = 0; t < zs.n; ++t) {
       CUtensorMap tmp[4];
-      rc = make_parity_maps(tmp, pz, zs[t], g.N, g.OH, g.OW, g.Cout, 1, P.BH, P.BW);
+      rc = make_parity_maps(tmp, pz, zs.p[t], g.N, g.OH, g.OW, g.Cout, 1, P.BH, P.BW);
       if (rc) return rc;
       P.a_map[t] = tmp[0];
-      rc = make_parity_maps(P.b_map[t], present, xs[t], g.N, g.H, g.W, g.Cin, g.s, P.BH, P.BW);
+      rc = make_parity_maps(P.b_map[t], present, xs.p[t], g.N, g.H, g.W, g.Cin, g.s, P.BH, P.BW);
       if (rc) return rc;
     }
     int nt = 0;
@@ -1299,7 +1326,7 @@ int umma_conv_backward_weight(const da_conv_desc* d, const void* x, const void* 
   int bn = 128;
   if (g.Cin <= 64) bn = 64;
   else if (g.Cin > 128 && (co_t * ((g.Cin + 255) / 256) * P.num_taps >= num_sms() / 2 || !short_k)) bn = 256;
-  else if (short_k && co_t * ((g.Cin + 127) / 128) * P.num_taps < num_sms() / 2 && getenv("DA_UMMA_NO_BN64") == nullptr) bn = 64;
+  else if (short_k && co_t * ((g.Cin + 127) / 128) * P.num_taps < num_sms() / 2 && !g_opt.umma_no_bn64) bn = 64;
   const long long tiles = (long long)((g.Cout + BM - 1) / BM) * ((g.Cin + bn - 1) / bn) * P.num_taps;
   long long k_iters = patches * P.num_terms;
   int splits = pick_splits_persistent(tiles, (int)(k_iters > 1000000 ? 1000000 : k_iters));

@@ -265,11 +265,13 @@ class Shared2FCBBoxHead(nn.Module):
         return cls, reg
 
     def loss(self, cls_score, bbox_pred, labels, bbox_targets, pos_mask):
-        """CrossEntropyLoss(use_sigmoid=True) over num_classes+1 channels + SmoothL1 on positives, both averaged
-        over the number of sampled RoIs (mmdet BBoxHead.loss)."""
+        """CrossEntropyLoss(use_sigmoid=True) over num_classes+1 channels + SmoothL1 on positives.  Both are element SUMS
+        divided by the number of sampled RoIs: mmdet's binary_cross_entropy reduces with weight_reduce_loss(avg_factor =
+        number of RoIs with label_weight > 0) (losses/cross_entropy_loss.py:100-114, bbox_heads/bbox_head.py:268-274), not
+        by the R*(num_classes+1) elements a plain reduction='mean' would use."""
         n = max(cls_score.shape[0], 1)
         onehot = F.one_hot(labels, self.num_classes + 1).to(cls_score.dtype)
-        out = dict(loss_cls=F.binary_cross_entropy_with_logits(cls_score, onehot, reduction="mean") *
+        out = dict(loss_cls=F.binary_cross_entropy_with_logits(cls_score, onehot, reduction="sum") / n *
                    self.loss_cls_cfg.get("loss_weight", 1.0),
                    acc=(cls_score.argmax(1) == labels).float().mean() * 100)
         if pos_mask.any():

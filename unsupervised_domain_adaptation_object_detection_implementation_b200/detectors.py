@@ -122,6 +122,16 @@ class _ForeBack(_DATwoStage):
         self.local_da_fore._init_weights()
         self.local_da_back._init_weights()
 
+    def unused_parameters(self):
+        """The fore/back heads are only ever evaluated without gradient (Q2: the reference adds their loss as a Python
+        float), so EVERY parameter of both heads stays without .grad on every rank and every step: listed statically so
+        the data-parallel reducer and the optimizer skip them (the reference's torch.optim.SGD skips grad=None too)."""
+        out = super().unused_parameters()
+        if self.detach_instance_loss:
+            seen = {id(p) for p in out}
+            out += [p for h in (self.local_da_fore, self.local_da_back) for p in h.parameters() if id(p) not in seen]
+        return out
+
     def group_local_da_loss(self, bbox_feats, lamda, bbox_cls):
         """L5 as the reference computes it (da_losses.group_local_da_loss): detached, source group first."""
         return da_losses.group_local_da_loss(bbox_feats, bbox_cls, self.local_da_fore, self.local_da_back, self.group_flavour)

@@ -44,11 +44,24 @@ class FlatGradAllReduce:
         dev = self.params[0].device if self.params else torch.device("cpu")
         self.flat = torch.zeros(self.numel, dtype=dtype, device=dev)
         self._views = None
+        self._fast_agreed = None
+        self._live = None
 
     def __call__(self):
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
             return
-        if self.flat.is_cuda and all(p.grad is not None and p.grad.dtype == self.flat.dtype for p in self.params):
+        fast = self.flat.is_cuda and all(p.grad is not None and p.grad.dtype == self.flat.dtype and p.grad.is_contiguous()
+                                         for p in self.params)
+        if self._fast_agreed is None:
+            # the two paths issue different collectives: ALL ranks must take the same one.  Agreed once (first step), then
+            # the choice is fixed; a rank that later falls off the fast path raises instead of deadlocking the others.
+            t = torch.tensor([1.0 if fast else 0.0], device=self.flat.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            self._fast_agreed = bool(t.item() > 0)
+        elif self._fast_agreed and not fast:
+            raise RuntimeError("FlatGradAllReduce: a parameter lost its gradient on this rank after the ranks agreed on the "
+                               "all-gradients path; list it in unused_parameters() or rebuild the reducer")
+        if self._fast_agreed:
             # three launches in total: multi-tensor gather, NCCL AVG, multi-tensor scatter
             if self._views is None:
                 self._views, off = [], 0
@@ -61,24 +74,40 @@ class FlatGradAllReduce:
                 dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)
                 torch._foreach_copy_(grads, self._views)
                 return
+        # Slow path (a parameter without gradient on THIS rank, a dtype mismatch, or CPU/gloo).  A parameter whose gradient
+        # is None on EVERY rank is skipped, exactly like on one GPU (torch.optim.SGD and FusedSGD skip grad=None, so no
+        # weight decay / momentum is applied to it); a parameter that has a gradient on SOME rank gets zeros on the others.
+        # Every rank runs the same collectives in the same order with the same op.
+        world = dist.get_world_size()
+        if self._live is None:      # agreed once, outside any graph capture (first eager step); static afterwards
+            has = torch.tensor([0.0 if p.grad is None else 1.0 for p in self.params], dtype=torch.float32, device=self.flat.device)
+            if len(self.params):
+                dist.all_reduce(has, op=dist.ReduceOp.SUM)
+            self._live = (has > 0).tolist()
+        anywhere = self._live
+        for p, live in zip(self.params, anywhere):
+            if p.grad is not None and not live:
+                raise RuntimeError("FlatGradAllReduce: a parameter that had no gradient on any rank at the first step has one now; "
+                                   "rebuild the reducer")
         off = 0
-        for p in self.params:
+        for p, live in zip(self.params, anywhere):
             n = p.numel()
-            if p.grad is None:
+            if p.grad is None or not live:
                 self.flat[off:off + n].zero_()
             else:
                 self.flat[off:off + n].copy_(p.grad.reshape(-1))
             off += n
-        dist.all_reduce(self.flat)
-        self.flat.div_(dist.get_world_size())
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+        self.flat.div_(world)
         off = 0
-        for p in self.params:
+        for p, live in zip(self.params, anywhere):
             n = p.numel()
-            g = self.flat[off:off + n].view(p.shape)
-            if p.grad is None:
-                p.grad = g.clone().to(p.dtype)
-            else:
-                p.grad.copy_(g.view_as(p.grad))
+            if live:
+                g = self.flat[off:off + n].view(p.shape)
+                if p.grad is None:
+                    p.grad = g.clone().to(p.dtype)
+                else:
+                    p.grad.copy_(g.view_as(p.grad))
             off += n
 
 

@@ -63,9 +63,19 @@ def set_sm_limit(n):
     check(lib.da_set_sm_limit(int(n)), "set_sm_limit")
 
 
+def set_option(name, value):
+    """Debug / test switch of the library (da_set_option): e.g. set_option("roi_no_tc", 1) forces the CUDA-core RoIAlign
+    kernels for bf16 tensors.  The DA_* environment variables are read once, when the library is loaded."""
+    check(lib.da_set_option(name.encode(), int(value)), "set_option")
+    _OPTIONS[name] = int(value)
+
+
+_OPTIONS = {"roi_no_tc": 1 if os.environ.get("DA_ROI_NO_TC") else 0}
+
+
 def set_engine(name):
-    """'umma_bf16' (tcgen05, default), 'umma_bf16x3' (split-precision tcgen05, fp32 in/out)
-    or 'simt_f32' (CUDA-core fp32 parity engine)."""
+    """'umma_bf16' (tcgen05, default), 'umma_bf16x6' (fp32-class tcgen05: exact 3-way bf16 split, six product
+    terms, fp32 in/out, <= 1e-5), 'umma_bf16x3' (2-way split, ~2^-16) or 'simt_f32' (CUDA-core fp32 parity engine)."""
     if name not in _lib.ENGINES:
         raise ValueError(f"unknown engine {name!r}; choose from {sorted(_lib.ENGINES)}")
     _ENGINE[0] = name
@@ -208,7 +218,7 @@ class RoIAlignFunction(Function):
         # bf16 features + bf16 [R,C,7,7] gradients: the tensor-core kernel rounds its fp32 accumulators once and
         # writes bf16 directly (no fp32 staging tensor, no cast pass)
         direct = fdtype == torch.bfloat16 and gout.dtype == torch.bfloat16 and layout == 0 and C % 8 == 0 and R > 0 \
-            and os.environ.get("DA_ROI_NO_TC") is None
+            and not _OPTIONS.get("roi_no_tc")
         gin = torch.empty((N, H, W, C), dtype=torch.bfloat16 if direct else torch.float32, device=gout.device)
         ws = workspace(lib.da_roi_align_workspace_bytes(R, H, W), gout.device, "roi")
         check(lib.da_roi_align_backward(_ptr(gout), _code(gout.dtype), layout, _ptr(rois_c), R, ph, pw, scale, sr,

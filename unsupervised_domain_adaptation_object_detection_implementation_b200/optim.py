@@ -15,6 +15,39 @@ def _same_layout(a, b):
     return a.shape == b.shape and all(n == 1 or sa == sb for n, sa, sb in zip(a.shape, a.stride(), b.stride()))
 
 
+class StepLrSchedule:
+    """mmcv's StepLrUpdaterHook with linear warm-up, as the DA configs use it (da_configs/_base_/schedules/schedule_1x.py:
+    lr_config = dict(policy='step', warmup='linear', warmup_iters=500, warmup_ratio=0.0001, step=[6, 8]); the DAF recipe
+    overrides step=[9], faster_rcnn_r50_daf_c2f.py:13-18).  lr(iter, epoch) =
+        base * gamma ** #{s in step : epoch >= s}                         regular
+        regular * (1 - (1 - iter / warmup_iters) * (1 - warmup_ratio))    while iter < warmup_iters (linear warm-up)
+    Hyper-parameters reach the kernels as launch arguments: assign `optimizer.lr` every iteration of an EAGER loop; a
+    captured CUDA graph or the peer optimizer bakes the value in, so re-capture when the schedule changes it."""
+
+    def __init__(self, base_lr, lr_config=None):
+        cfg = dict(lr_config or {})
+        if cfg.get("policy", "step") != "step":
+            raise NotImplementedError("the DA configs use policy='step' (da_configs/_base_/schedules/schedule_1x.py)")
+        self.base_lr = float(base_lr)
+        step = cfg.get("step", [])
+        self.steps = [int(step)] if isinstance(step, int) else [int(s) for s in step]
+        self.gamma = float(cfg.get("gamma", 0.1))
+        self.warmup = cfg.get("warmup")
+        if self.warmup not in (None, "linear", "constant"):
+            raise NotImplementedError(f"warmup={self.warmup!r} (mmcv supports constant/linear/exp; the DA configs use linear)")
+        self.warmup_iters = int(cfg.get("warmup_iters", 0))
+        self.warmup_ratio = float(cfg.get("warmup_ratio", 0.1))
+
+    def __call__(self, it, epoch):
+        """Learning rate of iteration `it` (0-based, global) in epoch `epoch` (0-based)."""
+        lr = self.base_lr * self.gamma ** sum(1 for s in self.steps if epoch >= s)
+        if self.warmup is not None and it < self.warmup_iters:
+            if self.warmup == "constant":
+                return lr * self.warmup_ratio
+            return lr * (1.0 - (1.0 - it / self.warmup_iters) * (1.0 - self.warmup_ratio))
+        return lr
+
+
 class FusedSGD:
     def __init__(self, params, lr=1e-3, momentum=0.9, weight_decay=0.0, shadow_bf16=True, fuse_wgrad=()):
         """fuse_wgrad: parameters (weights of functional.dense_layer layers on the bf16 tensor-core engine) whose update
