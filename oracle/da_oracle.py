@@ -65,10 +65,13 @@ def _drop(x, mask):
 # --------------------------------------------------------------------------------------
 # H1 ImgAlignmentHead — mmdet/models/backbones/resnet_da_daf_org.py:120-133
 # --------------------------------------------------------------------------------------
-def img_alignment_head(x, sd, q=None):
+def img_alignment_head(x, sd, q=None, relu=F.relu):
+    """`relu`: the activation (default F.relu).  ReLU has no derivative at 0: a test that compares GRADIENTS of a large
+    tensor passes a callable that takes the CUDA path's on/off decision for pre-activations within rounding of 0
+    (tests/helpers.ReluLikeCuda) -- either subgradient is valid there, and one flipped unit moves whole gradient rows."""
     x = _q(grl(x), q)
-    x = _q(F.relu(F.conv2d(x, _q(sd["conv1.weight"], q), sd["conv1.bias"])), q)
-    return F.relu(F.conv2d(x, sd["conv2.weight"], sd["conv2.bias"]))
+    x = _q(relu(F.conv2d(x, _q(sd["conv1.weight"], q), sd["conv1.bias"])), q)
+    return relu(F.conv2d(x, sd["conv2.weight"], sd["conv2.bias"]))
 
 
 # --------------------------------------------------------------------------------------
@@ -152,13 +155,13 @@ def non_local_alignment_head(x, sd, mask=None, q=None):
 # --------------------------------------------------------------------------------------
 # I1 InstanceAlignmentHead — instance_da.py:42-86 ; I2 InstanceAlignmentHead_DAF — :103-131
 # --------------------------------------------------------------------------------------
-def instance_alignment_logits(x, sd, masks=(None, None), q=None):
+def instance_alignment_logits(x, sd, masks=(None, None), q=None, relu=F.relu):
     x = _q(grl(x), q)
     x = x.unsqueeze(0).permute(0, 2, 1).contiguous().unsqueeze(2)  # [1,C,1,k]
     x = non_local_block(x, sd, "nlb.", q)
     x = x.permute(3, 1, 0, 2).contiguous().squeeze(-1).squeeze(-1)  # [k,C]
-    x = _q(_drop(F.relu(F.linear(x, _q(sd["fc1.weight"], q), sd["fc1.bias"])), masks[0]), q)
-    x = _q(_drop(F.relu(F.linear(x, _q(sd["fc2.weight"], q), sd["fc2.bias"])), masks[1]), q)
+    x = _q(_drop(relu(F.linear(x, _q(sd["fc1.weight"], q), sd["fc1.bias"])), masks[0]), q)
+    x = _q(_drop(relu(F.linear(x, _q(sd["fc2.weight"], q), sd["fc2.bias"])), masks[1]), q)
     return F.linear(x, _q(sd["fc3.weight"], q), sd["fc3.bias"])
 
 

@@ -57,3 +57,27 @@ def group_heads(rec, name):
     fore = seeded.fill_state_(cls_head().float().eval(), rec["seed"], prefix=f"group.{name}.fore.")
     back = seeded.fill_state_(cls_head().float().eval(), rec["seed"], prefix=f"group.{name}.back.")
     return fore, back
+
+
+class ReluLikeCuda:
+    """ReLU for the ORACLE side of a gradient comparison at large sizes.  The function is evaluated exactly; only where a
+    pre-activation lies within `delta` (relative to the tensor's max magnitude) of 0 -- where the two sides' rounding decides
+    whether the unit is on, and either subgradient of ReLU is valid -- the oracle takes the on/off decision the CUDA path
+    made (`cuda_acts`: the CUDA path's post-activation tensors, in call order, already in the oracle's layout).
+    `flips` counts the near-zero units where that changed the mask; `outside` counts disagreements OUTSIDE the delta band
+    (must be 0: that would be a real error, and the test asserts it)."""
+
+    def __init__(self, cuda_acts, delta):
+        self.acts, self.delta, self.i, self.flips, self.outside, self.near = list(cuda_acts), delta, 0, 0, 0, 0
+
+    def __call__(self, z):
+        on_cuda = (self.acts[self.i].to(z.device) > 0)
+        self.i += 1
+        assert on_cuda.shape == z.shape, (on_cuda.shape, z.shape)
+        zd = z.detach()
+        near = zd.abs() <= self.delta * zd.abs().max()
+        on_self = zd > 0
+        self.near += int(near.sum())
+        self.flips += int((near & (on_cuda != on_self)).sum())
+        self.outside += int((~near & (on_cuda != on_self)).sum())
+        return z * torch.where(near, on_cuda, on_self).to(z.dtype)

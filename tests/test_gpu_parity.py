@@ -654,10 +654,16 @@ def test_daf_org_hot_path_at_bench_shape_vs_oracle(engine):
       * the three losses of the dict                                    (all RoIs, all pixels)
       * d loss / d C5                                                    (whole tensor, max-norm relative)
       * d loss / d FC1.weight on 8 output rows x all 100352 columns      (slice: the oracle forms dz^T X for those rows only)
-      * d loss / d of every instance-head / image-head weight            (whole tensors)
+      * d loss / d of every instance-head weight                         (whole tensors)
     umma_bf16x6 (tcgen05, fp32-class) is held to the fp32 bar; umma_bf16 is compared with the oracle evaluated at the same
-    bf16 storage points (q='bf16') and stated separately."""
+    bf16 storage points (q='bf16') and stated separately.
+    ReLU subgradients: the path has ~11 M ReLU units; a unit whose pre-activation is within rounding of 0 is switched on by
+    one side and off by the other, and ONE such unit of FC1 moves the gradient of a whole RoI by ~1/sqrt(#active units)
+    (measured without this provision: fp32-class engine, ~40 such units, dC5 max-norm error 1.5e-2 with all losses <= 4e-6).
+    The oracle therefore takes the CUDA path's on/off decision inside a band |z| <= delta*max|z| (delta = 4e-5 for the
+    fp32-class engine, 1e-2 for bf16) and its own decision outside; the test asserts that NO disagreement lies outside the band."""
     from unsupervised_domain_adaptation_object_detection_implementation_b200 import hotpath
+    from helpers import ReluLikeCuda
     import torch.nn.functional as tF
     uda.set_engine(engine)
     bf16 = engine == "umma_bf16"
@@ -671,24 +677,49 @@ def test_daf_org_hot_path_at_bench_shape_vs_oracle(engine):
     rois = torch.cat([torch.cat([torch.full((512, 1), float(i)), boxes[i]], 1) for i in range(2)])
     labels = (torch.arange(1024) >= 512).long()
     gt = torch.tensor([0, 1])
+    sd = {k: v.detach().double() for k, v in model.state_dict().items()}
+
+    # ---- CUDA path (first: the oracle needs its ReLU decisions)
+    model = model.to(DEV)
+    acts, orig = [], F_.dense_layer
+
+    def recording_dense_layer(*a, **k):
+        y = orig(*a, **k)
+        if k.get("relu"):
+            acts.append(y.detach())
+        return y
+
+    x = c5_nhwc.to(DEV).to(F_.act_dtype()).permute(0, 3, 1, 2).requires_grad_(True)
+    F_.dense_layer = recording_dense_layer
+    try:
+        losses = model.forward_train(x, [boxes[0].to(DEV), boxes[1].to(DEV)], [0, 1])
+    finally:
+        F_.dense_layer = orig
+    total, _ = hotpath.parse_losses(losses)
+    total.backward()
+    assert len(acts) == 5                                                   # H1 conv1, shared FC1, FC2, instance fc1, fc2
+    with torch.no_grad():
+        img_feat_cuda = model.da_head_top(x.detach())
+    cuda_acts = [acts[0].permute(0, 3, 1, 2).float().cpu(), img_feat_cuda.float().cpu()] + \
+        [a.reshape(1024, -1).float().cpu() for a in acts[1:]]
 
     # ---- oracle (CPU)
+    vtol = BF16_TOL if bf16 else FP32_TOL
+    relu = ReluLikeCuda(cuda_acts, 1e-2 if bf16 else 4e-5)        # band: a few x the rounding noise of a pre-activation
     torch.set_num_threads(os.cpu_count() or 8)
     Q = (lambda t: da_oracle._q(t, q))
-    sd = {k: v.detach().double() for k, v in model.state_dict().items()}
     sub = lambda p: {k[len(p):]: v for k, v in sd.items() if k.startswith(p)}
     c5r = c5_nhwc.permute(0, 3, 1, 2).double().requires_grad_(True)
-    img_feat = da_oracle.img_alignment_head(c5r, sub("da_head_top."), q=q)
+    img_feat = da_oracle.img_alignment_head(c5r, sub("da_head_top."), q=q, relu=relu)
     pooled_np, grid_ref, _ = oracle_roi.roi_align_forward(c5_nhwc.permute(0, 3, 1, 2).contiguous().numpy(), rois.numpy(), 7, 1 / 16,
                                                           threads=os.cpu_count() or 8)
     pooled = torch.from_numpy(pooled_np).double().requires_grad_(True)
-    w1 = sd["bbox_head.shared_fcs.0.weight"].requires_grad_(False)
-    z1 = tF.linear(Q(pooled.flatten(1)), Q(w1), sd["bbox_head.shared_fcs.0.bias"])
+    z1 = tF.linear(Q(pooled.flatten(1)), Q(sd["bbox_head.shared_fcs.0.weight"]), sd["bbox_head.shared_fcs.0.bias"])
     z1.retain_grad()
-    f1 = Q(torch.relu(z1))
-    f2 = Q(torch.relu(tF.linear(f1, Q(sd["bbox_head.shared_fcs.1.weight"]), sd["bbox_head.shared_fcs.1.bias"])))
+    f1 = Q(relu(z1))
+    f2 = Q(relu(tF.linear(f1, Q(sd["bbox_head.shared_fcs.1.weight"]), sd["bbox_head.shared_fcs.1.bias"])))
     sd_ins = {k: v.requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sub("local_da.").items()}
-    pred = torch.sigmoid(da_oracle.instance_alignment_logits(f2, sd_ins, q=q))
+    pred = torch.sigmoid(da_oracle.instance_alignment_logits(f2, sd_ins, q=q, relu=relu))
     ref = dict(globle_da_loss=0.1 * da_oracle.daf_image_loss(img_feat, gt), local_da_loss=0.1 * da_oracle.ce2(pred, labels),
                consistency_loss=0.1 * da_oracle.consistency_loss(img_feat, pred, labels))
     sum(ref.values()).backward()
@@ -696,24 +727,29 @@ def test_daf_org_hot_path_at_bench_shape_vs_oracle(engine):
                                                                             (2, 2048, 64, 128), 7, 1 / 16))
     rows = torch.tensor([0, 1, 127, 128, 511, 640, 1000, 1023])
     dw1_ref = z1.grad[:, rows].t() @ Q(pooled.detach().flatten(1))          # [8, 100352]
+    # L7 is |m - s_r|: well-posed for a gradient comparison only while no RoI sits at the kink
+    margin = (torch.sigmoid(img_feat.detach()).mean() - torch.sigmoid(pred.detach()[torch.arange(1024), labels])).abs()
+    assert float(margin.min()) > (1e-2 if bf16 else 1e-4)
 
-    # ---- CUDA path
-    model = model.to(DEV)
-    x = c5_nhwc.to(DEV).to(F_.act_dtype()).permute(0, 3, 1, 2).requires_grad_(True)
-    losses = model.forward_train(x, [boxes[0].to(DEV), boxes[1].to(DEV)], [0, 1])
-    total, _ = hotpath.parse_losses(losses)
-    total.backward()
+    # ---- compare
     ltol, gtol, wtol = (BF16_TOL, 2 * BF16_TOL, 5e-2) if bf16 else (FP32_TOL, 5e-5, 5e-5)
+    gx = x.grad.double().cpu()
+    e_max, e_fro = rel_err(gx, c5_grad_ref), float((gx - c5_grad_ref).norm() / c5_grad_ref.norm())
+    print(f"\n[bench-shape {engine}] losses " + ", ".join(f"{k}: {abs(float(losses[k]) - float(ref[k])) / abs(float(ref[k])):.2e}" for k in ref) +
+          f" | dC5 max-norm {e_max:.3e} frobenius {e_fro:.3e} | ReLU units near 0: {relu.near}, decided by the CUDA path: {relu.flips}, "
+          f"disagreements outside the band: {relu.outside}")
+    assert relu.outside == 0
     for k in ref:
         assert abs(float(losses[k]) - float(ref[k])) <= ltol * abs(float(ref[k])), (k, float(losses[k]), float(ref[k]))
-    assert rel_err(x.grad.float(), c5_grad_ref) <= gtol
+    assert e_max <= gtol
     dw1 = model.bbox_head.shared_fcs[0].weight.grad[rows.to(DEV)]
     assert float((dw1.double().cpu() - dw1_ref).norm() / dw1_ref.norm()) <= wtol
     for k, v in sd_ins.items():
         if v.grad is not None and v.dim() >= 2:
             got = dict(model.local_da.named_parameters())[k].grad
             assert got is not None, k
-            assert float((got.double().cpu() - v.grad).norm() / v.grad.norm().clamp_min(1e-30)) <= wtol, k
+            e = float((got.double().cpu() - v.grad).norm() / v.grad.norm().clamp_min(1e-30))
+            assert e <= wtol, (k, e)
 
 
 def test_roi_align_tensor_core_backward_at_bench_size_vs_oracle():

@@ -195,11 +195,19 @@ __device__ __forceinline__ void nt_epilogue_chunk(const NtParams& P, const uint3
 // Each CTA stages its own 128 rows of A and HALF of the B tile (16 + 16 KB per k-step instead of 16 + 32 KB), so
 // the bytes every SM has to receive per MMA cycle drop by a third -- the 1-SM 128x256 tile is bound by the ~46 B/clk
 // an SM can take in, not by the tensor pipe.  The leader (cluster rank 0) owns the full barriers and issues the MMAs.
-template <int kBN, int kCluster, bool k2SM>
+// kChunked (fp32-class engine, BN = 128): the fp32 accumulator in TMEM is updated with TRUNCATION, so the error of an
+// accumulation chain is a bias of ~2^-24 of the running sum per tcgen05.mma (tools/probe_precision.py,
+// profiles/r02_precision_probe.txt: K = 100352 -> 1.9e-4 on same-sign data).  In this mode a chain is cut after kChunkIters
+// k-steps (32 MMAs): the two TMEM buffers ping-pong per CHUNK instead of per tile, and the epilogue warps add every finished
+// chunk into fp32 REGISTER accumulators (64 per thread) with round-to-nearest adds; the fused epilogue then runs from registers.
+constexpr int kChunkIters = 8;
+
+template <int kBN, int kCluster, bool k2SM, bool kChunked = false>
 __global__ void __launch_bounds__(NT_FWD_THREADS, 1)
 umma_nt_kernel(const __grid_constant__ NtParams P, int pixel_tiles, int n_tiles, int splits) {
   using Cfg = TileCfg<kBN>;
   static_assert(!k2SM || kCluster == 2, "the CTA-pair mode is a cluster of exactly two CTAs");
+  static_assert(!kChunked || (kBN == 128 && !k2SM), "chunked accumulation: 128-wide tiles, one CTA per MMA");
   constexpr int B_BYTES = k2SM ? Cfg::B_BYTES / 2 : Cfg::B_BYTES;                       // bytes of B staged by THIS CTA per k-step
   constexpr int STAGES = (Cfg::STAGES * (A_BYTES + Cfg::B_BYTES)) / (A_BYTES + B_BYTES);  // same ring bytes, deeper ring
   extern __shared__ uint8_t smem_raw[];
@@ -318,15 +326,25 @@ umma_nt_kernel(const __grid_constant__ NtParams P, int pixel_tiles, int n_tiles,
     if (lane == 0 && (!k2SM || crank == 0)) {
       const uint32_t idesc = make_idesc(k2SM ? 2 * BM : BM, kBN, 0, P.b_mn_major ? 1 : 0);
       int kq = 0, tcount = 0;
-      for (int tile = tile0; tile < total_tiles; tile += tile_step, ++tcount) {
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         const int sp = tile % splits;
         const int it_begin = sp * per_split, it_end = min(it_begin + per_split, total_iters);
-        const int buf = tcount & 1;
-        const uint32_t use = (uint32_t)(tcount >> 1);
-        mbar_wait(tempty0 + 8 * buf, (use & 1u) ^ 1u);   // epilogue has drained this accumulator
+        // one accumulator hand-over per tile -- or, chunked, per kChunkIters k-steps (tcount counts hand-overs)
+        int buf = tcount & 1;
+        mbar_wait(tempty0 + 8 * buf, (((uint32_t)(tcount >> 1)) & 1u) ^ 1u);   // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * kBN;
+        uint32_t d_tmem = tmem_base + buf * kBN;
         for (int it = it_begin; it < it_end; ++it, ++kq) {
+          const int rel = it - it_begin;
+          if (kChunked && rel > 0 && rel % kChunkIters == 0) {     // hand the finished chunk over, start the next chain at zero
+            umma_commit(tfull0 + 8 * buf);
+            ++tcount;
+            buf = tcount & 1;
+            mbar_wait(tempty0 + 8 * buf, (((uint32_t)(tcount >> 1)) & 1u) ^ 1u);
+            tc_fence_after();
+            d_tmem = tmem_base + buf * kBN;
+          }
+          const bool fresh = kChunked ? (rel % kChunkIters == 0) : (it == it_begin);
           const int s = kq % STAGES;
           const uint32_t ph = (uint32_t)(kq / STAGES) & 1u;
           mbar_wait(full0 + 8 * s, ph);
@@ -336,8 +354,8 @@ umma_nt_kernel(const __grid_constant__ NtParams P, int pixel_tiles, int n_tiles,
             const uint64_t ad = desc_kmajor_sw128(a_s + s * A_BYTES + kk * 32);
             const uint64_t bd = P.b_mn_major ? desc_mnmajor_sw128(b_s + s * B_BYTES + kk * 2048, 64 * BK * 2)
                                              : desc_kmajor_sw128(b_s + s * B_BYTES + kk * 32);
-            if (k2SM) umma_bf16_2sm(d_tmem, ad, bd, idesc, (it > it_begin || kk > 0) ? 1u : 0u);
-            else umma_bf16(d_tmem, ad, bd, idesc, (it > it_begin || kk > 0) ? 1u : 0u);
+            if (k2SM) umma_bf16_2sm(d_tmem, ad, bd, idesc, (!fresh || kk > 0) ? 1u : 0u);
+            else umma_bf16(d_tmem, ad, bd, idesc, (!fresh || kk > 0) ? 1u : 0u);
           }
           // the stage is reusable only when BOTH CTAs are done with it (multicast writes into both)
           if (k2SM) umma_commit_2sm(empty0 + 8 * s, 3);
@@ -346,6 +364,7 @@ umma_nt_kernel(const __grid_constant__ NtParams P, int pixel_tiles, int n_tiles,
         }
         if (k2SM) umma_commit_2sm(tfull0 + 8 * buf, 3);   // each CTA's epilogue drains its own 128 accumulator rows
         else umma_commit(tfull0 + 8 * buf);
+        ++tcount;
       }
     }
   } else {
@@ -354,7 +373,7 @@ umma_nt_kernel(const __grid_constant__ NtParams P, int pixel_tiles, int n_tiles,
     const int ehalf = (warp - 2) >> 2;
     const int r = q * 32 + lane;  // accumulator row == pixel within the tile
     int tcount = 0;
-    for (int tile = tile0; tile < total_tiles; tile += tile_step, ++tcount) {
+    for (int tile = tile0; tile < total_tiles; tile += tile_step) {
       const int sp = tile % splits, rest = tile / splits;
       const int nt = P.pix_fast ? rest / super_tiles : rest % n_tiles;
       const int pt = (P.pix_fast ? rest % super_tiles : rest / n_tiles) * kCluster + crank;
@@ -375,8 +394,42 @@ umma_nt_kernel(const __grid_constant__ NtParams P, int pixel_tiles, int n_tiles,
       }
       const bool raw = splits > 1;
       float* partial = raw ? P.partial + (size_t)sp * P.y_numel : nullptr;
+      if constexpr (kChunked) {
+        // this warp owns columns [ehalf*32, +32) and [(ehalf+2)*32, +32) of its 32 rows: 64 fp32 register accumulators
+        float a0[32], a1[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { a0[j] = 0.f; a1[j] = 0.f; }
+        const int nchunks = has_k ? (it_end - it_begin + kChunkIters - 1) / kChunkIters : 1;
+#pragma unroll 1
+        for (int c = 0; c < nchunks; ++c, ++tcount) {
+          const int buf = tcount & 1;
+          mbar_wait(tfull0 + 8 * buf, ((uint32_t)(tcount >> 1)) & 1u);
+          tc_fence_after();
+          if (has_k) {
+            uint32_t v0[32], v1[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * kBN;
+            DA_TMEM_LD32(taddr + ehalf * 32, v0);
+            DA_TMEM_LD32(taddr + (ehalf + 2) * 32, v1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { a0[j] = __fadd_rn(a0[j], __uint_as_float(v0[j])); a1[j] = __fadd_rn(a1[j], __uint_as_float(v1[j])); }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+        }
+        uint32_t u[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) u[j] = __float_as_uint(a0[j]);
+        nt_epilogue_chunk(P, u, row_off, valid, c0 + ehalf * 32, raw, partial, epi_stage + (warp - 2) * 4096, lane);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) u[j] = __float_as_uint(a1[j]);
+        nt_epilogue_chunk(P, u, row_off, valid, c0 + (ehalf + 2) * 32, raw, partial, epi_stage + (warp - 2) * 4096, lane);
+        continue;
+      }
       const int buf = tcount & 1;
       const uint32_t use = (uint32_t)(tcount >> 1);
+      ++tcount;
       mbar_wait(tfull0 + 8 * buf, use & 1u);
       tc_fence_after();
 #pragma unroll 1
@@ -978,17 +1031,24 @@ static int pick_splits_persistent(long long tiles, int k_iters) {
   return s < 1 ? 1 : s;
 }
 
-template <int kBN, int kCluster, bool k2SM = false>
+// Weight-gradient kernel of the fp32-class engine: its accumulation chains (pixels) are cut by split-K instead of in-kernel
+// chunking (see kChunked above for why chains must be short): at most kX6ChainIters k-steps per chain, partials summed in
+// fp32 round-to-nearest by sum_splits_kernel.
+constexpr int kX6ChainIters = 32;
+constexpr int kMaxSplits = 64;
+
+template <int kBN, int kCluster, bool k2SM = false, bool kChunked = false>
 static int launch_nt_t(NtParams& P, long long pixel_tiles, int k_iters, void* ws_part, size_t part_cap, cudaStream_t st) {
   const int n_tiles = (P.Cout + kBN - 1) / kBN;
   const long long super_tiles = (pixel_tiles + kCluster - 1) / kCluster;
   // split-K partials are indexed like y; a strided (parity-class) launch only owns part of y
   int splits = (P.os == 1) ? pick_splits_persistent(super_tiles * kCluster * n_tiles, k_iters) : 1;
+
   while (splits > 1 && (size_t)splits * P.y_numel * sizeof(float) > part_cap) --splits;
   P.partial = (float*)ws_part;
   const long long total = super_tiles * n_tiles * splits;   // cluster-level tile units
   DA_REQUIRE(total * kCluster <= 0x7fffffffll, DA_ERR_UNSUPPORTED, "umma: too many tiles");
-  auto kern = umma_nt_kernel<kBN, kCluster, k2SM>;
+  auto kern = umma_nt_kernel<kBN, kCluster, k2SM, kChunked>;
   static bool attr_set_dev[kMaxDevices] = {};     // function attributes are per device
   bool& attr_set = attr_set_dev[cur_dev()];
   if (!attr_set) {
@@ -1049,6 +1109,9 @@ static int launch_nt(NtParams& P, int bn, long long pixel_tiles, int k_iters, vo
   P.dbg = g_opt.umma_dbg;
   // concurrently running tiles share the operand whose index is NOT the fastest one; stream the bigger operand once
   P.pix_fast = ((long long)P.Cout > pixel_tiles * BM) ? 1 : 0;
+  if (P.num_terms == 6)   // fp32-class engine: chunked accumulation (short TMEM chains, fp32 register sums), 128-wide tiles
+    return nt_cluster(128, pixel_tiles) == 2 ? launch_nt_t<128, 2, false, true>(P, pixel_tiles, k_iters, ws_part, part_cap, st)
+                                             : launch_nt_t<128, 1, false, true>(P, pixel_tiles, k_iters, ws_part, part_cap, st);
   if (nt_pair_mma(bn, pixel_tiles)) return launch_nt_t<256, 2, true>(P, pixel_tiles, k_iters, ws_part, part_cap, st);
   const int cl = nt_cluster(bn, pixel_tiles);   // CTAs sharing the weight tile through TMA multicast
   if (bn == 256)
@@ -1083,7 +1146,7 @@ int umma_conv_forward(const da_conv_desc* d, const void* x, const void* w, const
   P.scale = scale; P.shift = shift; P.relu = relu; P.drop_p = drop_p; P.seed = seed; P.seed_ctr = g_seed_counter; P.out_scale = 1.f;
   P.y = y; P.y_dtype = d->y_dtype; P.y_numel = (long long)g.N * g.OH * g.OW * g.Cout;
   const int Ktot = g.KH * g.KW * g.Cin;
-  const int bn = choose_bn(g.Cout, (long long)g.N * g.OH * g.OW, (Ktot + BK - 1) / BK);
+  const int bn = d->engine == DA_ENGINE_UMMA_BF16X6 ? 128 : choose_bn(g.Cout, (long long)g.N * g.OH * g.OW, (Ktot + BK - 1) / BK);
   long long pixel_tiles;
   if (is_flat(g)) {
     P.flat = 1;
@@ -1154,7 +1217,7 @@ int umma_conv_backward_data(const da_conv_desc* d, const void* dz, const void* w
   base.OHf = g.H; base.OWf = g.W;
   base.relu = 0; base.drop_p = 0.f; base.out_scale = out_scale;
   base.y = dx; base.y_dtype = d->y_dtype; base.y_numel = (long long)g.N * g.H * g.W * g.Cin;
-  const int bn = choose_bn(g.Cin, (long long)g.N * g.H * g.W, ((long long)taps * g.Cout + BK - 1) / BK);
+  const int bn = d->engine == DA_ENGINE_UMMA_BF16X6 ? 128 : choose_bn(g.Cin, (long long)g.N * g.H * g.W, ((long long)taps * g.Cout + BK - 1) / BK);
   for (int t = 0; t < wsrc.n; ++t) {
     const uint64_t dims[2] = {(uint64_t)taps * g.Cin, (uint64_t)g.Cout};
     const uint64_t strides[1] = {(uint64_t)taps * g.Cin * 2};
@@ -1330,6 +1393,10 @@ int umma_conv_backward_weight(const da_conv_desc* d, const void* x, const void* 
   const long long tiles = (long long)((g.Cout + BM - 1) / BM) * ((g.Cin + bn - 1) / bn) * P.num_taps;
   long long k_iters = patches * P.num_terms;
   int splits = pick_splits_persistent(tiles, (int)(k_iters > 1000000 ? 1000000 : k_iters));
+  if (P.num_terms == 6) {   // fp32-class engine: bounded accumulation chains (see kX6ChainIters)
+    const long long need = (k_iters + kX6ChainIters - 1) / kX6ChainIters;
+    if (need > splits) splits = (int)(need > kMaxSplits ? kMaxSplits : need);
+  }
   while (splits > 1 && (size_t)splits * P.dw_numel * sizeof(float) > part_bytes(g)) --splits;
   if (sgd) {     // every gradient element must be complete inside one tile: no split-K
     splits = 1;
