@@ -330,6 +330,56 @@ int da_softmax_dim0_forward(const float* s, int T, int ldk, float* p, da_stream_
 int da_softmax_dim0_backward(const float* p, const float* dp, int T, int ldk, float* ds,
                              da_stream_t stream);
 
+/* ---- instance-level domain classifier + its loss as ONE persistent kernel (forward) / ONE (backward) ----------------------
+ * InstanceAlignmentHead (nlb = 1: GRL -> NonLocalBlock over the R RoIs -> FC C-H1-H2-2 -> sigmoid, mmdet/models/roi_heads/
+ * instance_da.py:42-101,150-192) or InstanceAlignmentHead_DAF (nlb = 0, :103-148) fused with the CE-on-sigmoid instance loss
+ * (detectors/DAFaster_rcnn_Orig.py:177-188): north_star kernel (3).  bf16 operands (the tcgen05 engine), fp32 accumulation,
+ * fp32 logits / predictions / loss / weight gradients.  The kernel is a program of GEMM tiles and elementwise ops separated
+ * by grid-wide barriers (csrc/chain.cu); every tensor, saved activation and scratch buffer belongs to the caller.
+ * Dropout (p after fc1 and fc2) uses the same counter hash as da_conv_forward (keep(seed, row*width + col)); backward takes
+ * the ReLU/dropout derivative from the stored post-activation (a clamped or dropped unit stored exactly 0). */
+typedef struct da_instance_fc_desc {
+  int R, C, I, H1, H2;   /* RoIs; feature width (1024); NonLocalBlock inner width (C/2, ignored when !nlb); FC widths */
+  int nlb;               /* 1: NonLocalBlock in front of the FC stack */
+  float drop_p;          /* 0 = eval */
+  uint64_t seed1, seed2; /* dropout seeds of fc1 / fc2 */
+  float grl;             /* gradient-reversal weight folded into dx (backward), instance_da.py:20-23 */
+} da_instance_fc_desc;
+typedef struct da_instance_fc_tensors {
+  const void* x;         /* bf16 [R,C] */
+  const void* w_proj;    /* bf16 [3I,C]: conv_theta | conv_phi | conv_g weights in ONE buffer (nlb) */
+  const void* w_mask;    /* bf16 [C,I] (nlb) */
+  const void* w1; const float* b1;   /* bf16 [H1,C], f32 [H1] */
+  const void* w2; const float* b2;   /* bf16 [H2,H1], f32 [H2] */
+  const void* w3; const float* b3;   /* bf16 [2,H2], f32 [2] */
+  const int32_t* labels; /* [R], 0 = source, 1 = target */
+  /* saved activations: written by forward, read by backward */
+  void* proj;            /* bf16 [R,3I]  theta | phi | g (nlb) */
+  void* attn;            /* bf16 [R, (R+7)&~7] softmax over the QUERY axis (nlb) */
+  void* y;               /* bf16 [R,I] (nlb) */
+  void* t;               /* bf16 [R,C] NonLocalBlock output (nlb) */
+  void* h1; void* h2;    /* bf16 [R,H1], [R,H2], after ReLU and dropout */
+  float* z;              /* f32 [R,2] raw logits of fc3 */
+  float* pred;           /* f32 [R,2] sigmoid(z): what the reference head returns */
+  float* loss;           /* f32 scalar: mean CE(pred, labels) */
+} da_instance_fc_tensors;
+typedef struct da_instance_fc_grads {
+  const float* grad_loss;   /* device scalar (NULL = 1) */
+  float loss_scale;         /* host scalar multiplied in (lambda) */
+  const float* grad_pred;   /* f32 [R,2] gradient w.r.t. pred from other consumers (the consistency loss), or NULL */
+  void* dx;                 /* bf16 [R,C], already multiplied by desc.grl */
+  float* dw_proj;           /* f32 [3I,C] (nlb) */
+  float* dw_mask;           /* f32 [C,I] (nlb) */
+  float* dw1; float* db1; float* dw2; float* db2; float* dw3; float* db3;
+  void* dz2; void* dz1;     /* scratch bf16 [R,H2], [R,H1] */
+  void* dt; void* dy; void* dproj;   /* scratch bf16 [R,C], [R,I], [R,3I] (nlb) */
+} da_instance_fc_grads;
+size_t da_instance_fc_workspace_bytes(int R);
+int da_instance_fc_forward(const da_instance_fc_desc* d, const da_instance_fc_tensors* t, void* workspace, size_t workspace_bytes,
+                           da_stream_t stream);
+int da_instance_fc_backward(const da_instance_fc_desc* d, const da_instance_fc_tensors* t, const da_instance_fc_grads* g,
+                            void* workspace, size_t workspace_bytes, da_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

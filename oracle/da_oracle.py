@@ -142,7 +142,9 @@ def non_local_block(x, sd, p="", q=None):
     x_g = _q(F.conv2d(x, _q(sd[p + "conv_g.weight"], q)), q).view(b, ic, -1).permute(0, 2, 1)
     att = _q(torch.softmax(torch.matmul(x_theta, x_phi), dim=1), q)
     y = _q(torch.matmul(att, x_g), q).permute(0, 2, 1).contiguous().view(b, ic, h, w)
-    return _q(F.conv2d(y, _q(sd[p + "conv_mask.weight"], q)), q) + x
+    # q='bf16': the residual SUM is the stored bf16 activation on the CUDA path (the fused epilogue adds x to the fp32
+    # accumulator and rounds once; it feeds the next GEMM as an operand)
+    return _q(F.conv2d(y, _q(sd[p + "conv_mask.weight"], q)) + x, q)
 
 
 # H5 NonLocalAlignmentHead — mmdet/models/backbones/resnet_da_deep.py:122-164

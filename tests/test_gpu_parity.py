@@ -689,12 +689,20 @@ def test_daf_org_hot_path_at_bench_shape_vs_oracle(engine):
             acts.append(y.detach())
         return y
 
+    chain_orig = F_.instance_head_chain
+
+    def recording_chain(*a, **k):         # bf16 engine: the instance head is ONE kernel; its stored activations h1, h2
+        loss_c, pred_c = chain_orig(*a, **k)
+        sv = loss_c.grad_fn.keep[2]
+        acts.extend([sv["h1"].detach(), sv["h2"].detach()])
+        return loss_c, pred_c
+
     x = c5_nhwc.to(DEV).to(F_.act_dtype()).permute(0, 3, 1, 2).requires_grad_(True)
-    F_.dense_layer = recording_dense_layer
+    F_.dense_layer, F_.instance_head_chain = recording_dense_layer, recording_chain
     try:
         losses = model.forward_train(x, [boxes[0].to(DEV), boxes[1].to(DEV)], [0, 1])
     finally:
-        F_.dense_layer = orig
+        F_.dense_layer, F_.instance_head_chain = orig, chain_orig
     total, _ = hotpath.parse_losses(losses)
     total.backward()
     assert len(acts) == 5                                                   # H1 conv1, shared FC1, FC2, instance fc1, fc2
@@ -820,3 +828,134 @@ def test_roi_head_da_v5_values_vs_oracle(engine, tol):
     for k, p in head.bbox_head.named_parameters():
         assert p.grad is not None, k
         assert rel_err(p.grad, sd[k].grad) <= 5 * tol, k
+
+
+# ---------------------------------------------------------------------------- instance head + CE as one kernel (csrc/chain.cu)
+def _chain_case(name, R, seed=0):
+    from unsupervised_domain_adaptation_object_detection_implementation_b200 import da_heads
+    m = build_head(name, seed)
+    x = seeded.feature_map(f"chain.{name}.x", (R, 1024), seed).bfloat16().float()
+    labels = (torch.arange(R) >= R // 2).long()
+    gpred = seeded.seeded_tensor(f"chain.{name}.gp", (R, 2), seed, scale=0.3 / R)
+    return m, x, labels, gpred
+
+
+@pytest.mark.parametrize("name", ["instance_alignment", "instance_alignment_daf"])
+@pytest.mark.parametrize("R", [24, 300, 1024])
+def test_instance_head_chain_vs_oracle_and_layerwise(name, R):
+    """da_instance_fc_forward/backward (ONE persistent kernel each: NonLocalBlock projections, query-axis softmax, attention,
+    FC stack, sigmoid + CE; data / weight / bias gradients with the GRL folded in) against
+      (a) the oracle evaluated at the same bf16 storage points (q='bf16'), loss + pred + dx + every parameter gradient,
+      (b) the layer-by-layer CUDA path (same kernels as the goldens pin), eval mode.
+    R = 24 (golden size, one partial tile), 300 (ragged: rows, attention columns and the K of P*g all have tails), 1024 (bench)."""
+    from unsupervised_domain_adaptation_object_detection_implementation_b200 import da_heads
+    uda.set_engine("umma_bf16")
+    m, x, labels, gpred = _chain_case(name, R)
+    # (a) oracle
+    sd = {k: v.detach().double().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in m.state_dict().items()}
+    xr = x.double().requires_grad_(True)
+    logits = (da_oracle.instance_alignment_logits if name == "instance_alignment" else da_oracle.instance_alignment_daf_logits)(xr, sd, q="bf16")
+    pred_r = torch.sigmoid(logits)
+    loss_r = da_oracle.ce2(pred_r, labels)
+    (0.1 * loss_r + (pred_r * gpred.double()).sum()).backward()
+    # chain
+    m = m.to(DEV)
+    xc = x.to(DEV).requires_grad_(True)
+    loss, pred = m.forward_loss(xc, labels.to(DEV))
+    assert pred.shape == (R, 2) and loss.dim() == 0
+    (0.1 * loss + (pred * gpred.to(DEV)).sum()).backward()
+    assert abs(float(loss) - float(loss_r)) <= BF16_TOL * abs(float(loss_r))
+    assert rel_err(pred, pred_r) <= BF16_TOL
+    # every gradient of the backward chain (dz, dz2, dz1, dt, dY, dS, dtheta|dphi|dg) is stored in bf16: bounded in the
+    # Frobenius norm (3e-2) and, looser, element-wise against the max magnitude
+    e_fro = float((xc.grad.double().cpu() - xr.grad).norm() / xr.grad.norm())
+    print(f"\n[chain {name} R={R}] loss {abs(float(loss) - float(loss_r)) / abs(float(loss_r)):.2e} pred {rel_err(pred, pred_r):.2e} "
+          f"dx max-norm {rel_err(xc.grad, xr.grad):.2e} frobenius {e_fro:.2e}")
+    chain_grads, errs = {}, {}
+    for k, p in m.named_parameters():
+        if sd[k].grad is None:
+            assert p.grad is None, k
+            continue
+        assert p.grad is not None and p.grad.shape == p.shape, k
+        a, b = p.grad.double().cpu(), sd[k].grad
+        errs[k] = float((a - b).norm() / b.norm().clamp_min(1e-30))
+        chain_grads[k] = p.grad.clone()
+        p.grad = None
+    print("   param grad frobenius errors:", {k: f"{v:.1e}" for k, v in errs.items()})
+    assert e_fro <= BF16_TOL and rel_err(xc.grad, xr.grad) <= 0.12
+    assert all(v <= 5e-2 for v in errs.values()), errs
+    # (b) layer-by-layer path
+    da_heads.USE_CHAIN = False
+    try:
+        xl = x.to(DEV).requires_grad_(True)
+        loss_l, pred_l = m.forward_loss(xl, labels.to(DEV))
+        (0.1 * loss_l + (pred_l * gpred.to(DEV)).sum()).backward()
+    finally:
+        da_heads.USE_CHAIN = True
+    # two bf16 paths with different rounding points (the layer-wise path rounds the NonLocalBlock output twice, keeps fc3 and
+    # dz in fp32, ...): a sanity bound in the Frobenius norm, the parity statement is (a)
+    fro = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+    assert abs(float(loss) - float(loss_l)) <= 2e-3 * abs(float(loss_l)) and rel_err(pred, pred_l) <= 2e-2
+    assert fro(xc.grad, xl.grad) <= 0.1
+    for k, p in m.named_parameters():
+        if k in chain_grads:
+            assert fro(chain_grads[k], p.grad) <= 0.12, k
+
+
+def test_instance_head_chain_dropout_matches_layerwise_masks():
+    """Training mode: the chain draws its two dropout seeds in the same order as the layer-by-layer path and hashes the same
+    element index (row * width + column), so both paths drop the SAME units; the stored activations double as the ReLU/dropout
+    derivative mask in the chain's backward."""
+    from unsupervised_domain_adaptation_object_detection_implementation_b200 import da_heads
+    uda.set_engine("umma_bf16")
+    m, x, labels, gpred = _chain_case("instance_alignment", 256, seed=2)
+    m = m.to(DEV).train()
+    outs = []
+    for use in (True, False):
+        da_heads.USE_CHAIN = use
+        try:
+            torch.manual_seed(1234)
+            xc = x.to(DEV).requires_grad_(True)
+            loss, pred = m.forward_loss(xc, labels.to(DEV))
+            (loss + (pred * gpred.to(DEV)).sum()).backward()
+            outs.append((float(loss), pred.detach().clone(), xc.grad.clone(), {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}))
+            for p in m.parameters():
+                p.grad = None
+        finally:
+            da_heads.USE_CHAIN = True
+    (la, pa, ga, wa), (lb, pb, gb, wb) = outs
+    fro = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+    assert abs(la - lb) <= 3e-3 * abs(lb) and rel_err(pa, pb) <= 2e-2
+    assert fro(ga, gb) <= 0.1               # different masks would give O(1)
+    assert set(wa) == set(wb)
+    for k in wa:
+        assert fro(wa[k], wb[k]) <= 0.12, k
+    torch.manual_seed(99)                                             # another seed: other masks
+    xc = x.to(DEV)
+    _, p2 = m.forward_loss(xc.requires_grad_(True), labels.to(DEV))
+    assert float((p2 - pa).abs().max()) > 0
+
+
+def test_instance_head_chain_golden_and_packed_projection_state(golden):
+    """pred of the chain against the reference class's golden output; the packed theta|phi|g storage keeps parameter names,
+    shapes and values, survives load_state_dict and is re-packed after .to()."""
+    uda.set_engine("umma_bf16")
+    g = golden("head_instance_alignment.pt")
+    m = build_head("instance_alignment", g["seed"]).to(DEV)
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    x = g["x"].to(DEV).requires_grad_(True)
+    _, pred = m.forward_loss(x, torch.zeros(x.shape[0], dtype=torch.long, device=DEV))
+    assert rel_err(pred, g["out"][0]) <= BF16_TOL
+    nlb = m.nlb
+    ws = [nlb.conv_theta.weight, nlb.conv_phi.weight, nlb.conv_g.weight]
+    n = ws[0].numel() * 4
+    assert ws[1].data_ptr() == ws[0].data_ptr() + n and ws[2].data_ptr() == ws[0].data_ptr() + 2 * n      # one buffer
+    after = m.state_dict()
+    assert set(after) == set(before) and all(torch.equal(after[k], before[k]) for k in before)
+    m.load_state_dict({k: v * 0.5 if "conv_phi" in k else v for k, v in before.items()})
+    assert ws[1].data_ptr() == ws[0].data_ptr() + n                                                       # in-place load keeps it
+    _, pred2 = m.forward_loss(x, torch.zeros(x.shape[0], dtype=torch.long, device=DEV))
+    assert float((pred2 - pred).abs().max()) > 0                                                          # operand copy refreshed
+    m2 = m.float().cpu().to(DEV)                                                                          # storages separated
+    _, pred3 = m2.forward_loss(x, torch.zeros(x.shape[0], dtype=torch.long, device=DEV))
+    assert rel_err(pred3, pred2) <= 1e-6

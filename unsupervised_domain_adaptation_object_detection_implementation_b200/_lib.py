@@ -46,6 +46,25 @@ class SgdFuse(Structure):
                 ("lr", c_float), ("momentum", c_float), ("weight_decay", c_float), ("first_step", c_int32)]
 
 
+class InstanceFcDesc(Structure):
+    """da_instance_fc_desc (include/da_b200.h)."""
+    _fields_ = [("R", c_int), ("C", c_int), ("I", c_int), ("H1", c_int), ("H2", c_int), ("nlb", c_int), ("drop_p", c_float),
+                ("seed1", c_uint64), ("seed2", c_uint64), ("grl", c_float)]
+
+
+class InstanceFcTensors(Structure):
+    """da_instance_fc_tensors."""
+    _fields_ = [(n, c_void_p) for n in ("x", "w_proj", "w_mask", "w1", "b1", "w2", "b2", "w3", "b3", "labels", "proj", "attn", "y", "t",
+                                        "h1", "h2", "z", "pred", "loss")]
+
+
+class InstanceFcGrads(Structure):
+    """da_instance_fc_grads."""
+    _fields_ = [("grad_loss", c_void_p), ("loss_scale", c_float), ("grad_pred", c_void_p), ("dx", c_void_p), ("dw_proj", c_void_p),
+                ("dw_mask", c_void_p), ("dw1", c_void_p), ("db1", c_void_p), ("dw2", c_void_p), ("db2", c_void_p), ("dw3", c_void_p),
+                ("db3", c_void_p), ("dz2", c_void_p), ("dz1", c_void_p), ("dt", c_void_p), ("dy", c_void_p), ("dproj", c_void_p)]
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -114,6 +133,9 @@ SIGNATURES = {
     "da_global_avgpool_backward": (I, [P, I, I, I, P, I, P]),
     "da_softmax_dim0_forward": (I, [P, I, I, P, P]),
     "da_softmax_dim0_backward": (I, [P, P, I, I, P, P]),
+    "da_instance_fc_workspace_bytes": (S, [I]),
+    "da_instance_fc_forward": (I, [POINTER(InstanceFcDesc), POINTER(InstanceFcTensors), P, S, P]),
+    "da_instance_fc_backward": (I, [POINTER(InstanceFcDesc), POINTER(InstanceFcTensors), POINTER(InstanceFcGrads), P, S, P]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

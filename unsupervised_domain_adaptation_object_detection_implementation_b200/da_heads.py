@@ -400,6 +400,14 @@ class NonLocalAlignmentHead(_HeadBase):
         return F_.nhwc_to_nchw_view(y).float()
 
 
+USE_CHAIN = True      # functional.instance_head_chain for the instance heads on the bf16 engine (False: layer by layer)
+
+
+def _chain_ok(x):
+    return USE_CHAIN and x.is_cuda and x.dim() == 2 and x.shape[0] > 0 and F_.get_engine() == "umma_bf16" and x.shape[1] % 64 == 0 \
+        and torch.is_grad_enabled()
+
+
 class InstanceAlignmentHead(_HeadBase):
     """I1: GRL -> NonLocalBlock over the k RoIs -> FC 1024-512-512-2 -> sigmoid."""
 
@@ -431,6 +439,20 @@ class InstanceAlignmentHead(_HeadBase):
     def forward(self, x):
         return torch.sigmoid(self.forward_logits(x))
 
+    def forward_loss(self, x, labels):
+        """(mean CE(sigmoid(fc3(...)), labels), pred = sigmoid(fc3(...))): the head AND the instance loss built on it
+        (DAFaster_rcnn_Orig.py:177-188).  On the bf16 tensor-core engine this is ONE kernel forward and ONE backward
+        (functional.instance_head_chain -> da_instance_fc_forward/backward); the other engines run layer by layer."""
+        if _chain_ok(x):
+            p = self._p()
+            seeds = (_draw_seed(self.training, p), _draw_seed(self.training, p))
+            nlb = self.nlb
+            return F_.instance_head_chain(F_.cast(x.contiguous(), torch.bfloat16), labels,
+                                          (nlb.conv_theta.weight, nlb.conv_phi.weight, nlb.conv_g.weight), nlb.conv_mask.weight,
+                                          ((self.fc1.weight, self.fc1.bias), (self.fc2.weight, self.fc2.bias), (self.fc3.weight, self.fc3.bias)),
+                                          p, seeds, self.grl.weight)
+        return F_.ce2(self.forward_logits(x), labels, True)
+
     def _init_weights(self):
         normal_init(self.fc1, 0, 0.01)
         normal_init(self.fc2, 0, 0.01)
@@ -458,6 +480,16 @@ class InstanceAlignmentHead_DAF(_HeadBase):
 
     def forward(self, x):
         return torch.sigmoid(self.forward_logits(x))
+
+    def forward_loss(self, x, labels):
+        """See InstanceAlignmentHead.forward_loss (same kernel without the NonLocalBlock part)."""
+        if _chain_ok(x):
+            p = self._p()
+            seeds = (_draw_seed(self.training, p), _draw_seed(self.training, p))
+            return F_.instance_head_chain(F_.cast(x.contiguous(), torch.bfloat16), labels, None, None,
+                                          ((self.fc1.weight, self.fc1.bias), (self.fc2.weight, self.fc2.bias), (self.fc3.weight, self.fc3.bias)),
+                                          p, seeds, self.grl.weight)
+        return F_.ce2(self.forward_logits(x), labels, True)
 
     def _init_weights(self):
         normal_init(self.fc1, 0, 0.01)

@@ -99,7 +99,7 @@ class DAFasterRCNN_Org(_DATwoStage):
 
     def local_da_loss(self, bbox_feats, lamda):
         labels = torch.cat([torch.full((len(f),), i, dtype=torch.long, device=f.device) for i, f in enumerate(bbox_feats)])
-        loss, pred = da_losses.instance_ce_loss(self.local_da.forward_logits(torch.cat(list(bbox_feats), 0)), labels)
+        loss, pred = self.local_da.forward_loss(torch.cat(list(bbox_feats), 0), labels)
         return loss, pred, labels
 
     def consist_loss(self, imgs_feat, ins_preds, ins_labels):

@@ -724,3 +724,135 @@ class SoftmaxDim0Function(Function):
 
 def softmax_dim0(s):
     return SoftmaxDim0Function.apply(s)
+
+
+# --------------------------------------------------------------------------------------
+# instance-level domain classifier + CE as one persistent kernel (csrc/chain.cu)
+# --------------------------------------------------------------------------------------
+def pack_projection(weights):
+    """The three 1x1 projection weights of a NonLocalBlock (theta | phi | g, each [I,C,1,1]) as ONE [3I,C] buffer, and their
+    bf16 operand copies as one [3I,C] buffer: the chain kernel runs the three projections (and their data / weight gradients)
+    as single GEMMs.  The parameters keep their identity, names and shapes; only their storage is re-seated (once; again after
+    a .to()/.cuda() that separated them).  Returns (fp32 [3I,C] view of the masters, bf16 [3I,C] operand copy)."""
+    I_, C = weights[0].shape[0], weights[0].shape[1]
+    n = I_ * C
+    base = weights[0].data_ptr()
+    packed = all(w.dtype == torch.float32 and w.data_ptr() == base + 4 * n * i and _dense_memory(w) for i, w in enumerate(weights))
+    hit = getattr(weights[0], "_da_pack", None)
+    if not packed or hit is None or hit[0].data_ptr() != base:
+        with torch.no_grad():
+            buf = torch.empty((3 * I_, C), dtype=torch.float32, device=weights[0].device)
+            for i, w in enumerate(weights):
+                buf[i * I_:(i + 1) * I_].copy_(w.detach().reshape(I_, C))
+                w.data = buf[i * I_:(i + 1) * I_].view(I_, C, 1, 1)
+            sh = torch.empty((3 * I_, C), dtype=torch.bfloat16, device=buf.device)
+            check(lib.da_cast(_ptr(buf), _lib.DA_F32, _ptr(sh), _lib.DA_BF16, buf.numel(), _stream()), "cast")
+            for i, w in enumerate(weights):
+                w._da_shadow = (w._version, sh[i * I_:(i + 1) * I_].view(I_, C, 1, 1))
+            weights[0]._da_pack = (buf, sh)
+        hit = weights[0]._da_pack
+    buf, sh = hit
+    for i, w in enumerate(weights):      # a torch in-place update of a master invalidates its operand copy: refresh
+        cur = getattr(w, "_da_shadow", None)
+        if cur is None or cur[0] != w._version or cur[1].data_ptr() != sh.data_ptr() + 2 * n * i:
+            with torch.no_grad():
+                view = sh[i * I_:(i + 1) * I_].view(I_, C, 1, 1)
+                check(lib.da_cast(_ptr(w.detach()), _lib.DA_F32, _ptr(view), _lib.DA_BF16, n, _stream()), "cast")
+                w._da_shadow = (w._version, view)
+    return buf, sh
+
+
+class InstanceHeadChainFunction(Function):
+    """(loss, pred) = CE-on-sigmoid( FC stack ( [NonLocalBlock]( GRL(x) ) ) ) in one kernel; backward in one kernel."""
+
+    @staticmethod
+    def forward(ctx, x, labels, nlb_w, w_mask, w1, b1, w2, b2, w3, b3, ops, cfg):
+        # nlb_w: packed fp32 [3I,C] view of the projection masters (or None); ops: bf16 operand copies in the same order
+        _require_cuda(x)
+        R, C = x.shape
+        drop_p, seed1, seed2, grl = cfg
+        nlb = nlb_w is not None
+        I_ = nlb_w.shape[0] // 3 if nlb else 0
+        H1, H2 = w1.shape[0], w2.shape[0]
+        dev = x.device
+        x = x.contiguous()
+        lab = _as_i32(labels, dev)
+        bf, f32 = torch.bfloat16, torch.float32
+        ldp = (R + 7) // 8 * 8
+        sv = dict(h1=torch.empty((R, H1), dtype=bf, device=dev), h2=torch.empty((R, H2), dtype=bf, device=dev),
+                  z=torch.empty((R, 2), dtype=f32, device=dev))
+        if nlb:
+            sv.update(proj=torch.empty((R, 3 * I_), dtype=bf, device=dev), attn=torch.empty((R, ldp), dtype=bf, device=dev),
+                      y=torch.empty((R, I_), dtype=bf, device=dev), t=torch.empty((R, C), dtype=bf, device=dev))
+        pred = torch.empty((R, 2), dtype=f32, device=dev)
+        loss = torch.empty((), dtype=f32, device=dev)
+        op_proj, op_mask, op1, op2, op3 = ops
+        b1c, b2c, b3c = (b.detach().float().contiguous() for b in (b1, b2, b3))
+        desc = _lib.InstanceFcDesc(R, C, I_, H1, H2, int(nlb), float(drop_p), int(seed1), int(seed2), float(grl))
+        g = lambda t_: None if t_ is None else t_.data_ptr()
+        ten = _lib.InstanceFcTensors(g(x), g(op_proj), g(op_mask), g(op1), g(b1c), g(op2), g(b2c), g(op3), g(b3c), g(lab), g(sv.get("proj")),
+                                     g(sv.get("attn")), g(sv.get("y")), g(sv.get("t")), g(sv["h1"]), g(sv["h2"]), g(sv["z"]), g(pred), g(loss))
+        ws = workspace(lib.da_instance_fc_workspace_bytes(R), dev, "chain")
+        check(lib.da_instance_fc_forward(ctypes.byref(desc), ctypes.byref(ten), _ptr(ws), ws.numel(), _stream()), "instance_fc_forward")
+        ctx.desc, ctx.ten, ctx.keep = desc, ten, (x, lab, sv, ops, b1c, b2c, b3c, pred)
+        ctx.shapes = (None if not nlb else nlb_w.shape, None if w_mask is None else w_mask.shape, w1.shape, w2.shape, w3.shape)
+        return loss, pred
+
+    @staticmethod
+    def backward(ctx, g_loss, g_pred):
+        x, lab, sv, ops, b1c, b2c, b3c, pred = ctx.keep
+        desc = ctx.desc
+        R, C, I_, H1, H2, nlb = desc.R, desc.C, desc.I, desc.H1, desc.H2, bool(desc.nlb)
+        dev = x.device
+        bf, f32 = torch.bfloat16, torch.float32
+        gl = None if g_loss is None else g_loss.contiguous().float()
+        gp = None if g_pred is None else g_pred.contiguous().float()
+        dx = torch.empty((R, C), dtype=bf, device=dev)
+        dw1, db1 = torch.empty((H1, C), dtype=f32, device=dev), torch.empty((H1,), dtype=f32, device=dev)
+        dw2, db2 = torch.empty((H2, H1), dtype=f32, device=dev), torch.empty((H2,), dtype=f32, device=dev)
+        dw3, db3 = torch.empty((2, H2), dtype=f32, device=dev), torch.empty((2,), dtype=f32, device=dev)
+        dz2, dz1 = torch.empty((R, H2), dtype=bf, device=dev), torch.empty((R, H1), dtype=bf, device=dev)
+        dwp = dwm = dt = dy = dproj = None
+        if nlb:
+            dwp, dwm = torch.empty((3 * I_, C), dtype=f32, device=dev), torch.empty((C, I_), dtype=f32, device=dev)
+            dt, dy = torch.empty((R, C), dtype=bf, device=dev), torch.empty((R, I_), dtype=bf, device=dev)
+            dproj = torch.empty((R, 3 * I_), dtype=bf, device=dev)
+        g = lambda t_: None if t_ is None else t_.data_ptr()
+        gr = _lib.InstanceFcGrads(g(gl), 1.0, g(gp), g(dx), g(dwp), g(dwm), g(dw1), g(db1), g(dw2), g(db2), g(dw3), g(db3), g(dz2), g(dz1),
+                                  g(dt), g(dy), g(dproj))
+        ws = workspace(lib.da_instance_fc_workspace_bytes(R), dev, "chain")
+        check(lib.da_instance_fc_backward(ctypes.byref(desc), ctypes.byref(ctx.ten), ctypes.byref(gr), _ptr(ws), ws.numel(), _stream()),
+              "instance_fc_backward")
+        s_proj, s_mask, s1, s2, s3 = ctx.shapes
+        return (dx, None, dwp, None if dwm is None else dwm.view(s_mask), dw1.view(s1), db1, dw2.view(s2), db2, dw3.view(s3), db3,
+                None, None)
+
+
+class _SplitPacked(Function):
+    """Identity bridge between the three projection parameters and their packed [3I,C] view: backward hands each parameter
+    its slice of the packed gradient (views of one buffer, no copies)."""
+
+    @staticmethod
+    def forward(ctx, packed_view, w_theta, w_phi, w_g):
+        ctx.shapes = (w_theta.shape, w_phi.shape, w_g.shape)
+        return packed_view.detach()
+
+    @staticmethod
+    def backward(ctx, d):
+        I_ = d.shape[0] // 3
+        parts = [d[i * I_:(i + 1) * I_].view(s) for i, s in enumerate(ctx.shapes)]
+        return (None, *parts)
+
+
+def instance_head_chain(x, labels, nlb_weights, w_mask, fcs, drop_p, seeds, grl):
+    """x [R,C] bf16; nlb_weights: (theta, phi, g) conv weights or None; w_mask: conv_mask weight or None;
+    fcs: ((w1,b1),(w2,b2),(w3,b3)).  -> (loss = mean CE(sigmoid(fc3), labels), pred = sigmoid(fc3) [R,2])."""
+    (w1, b1), (w2, b2), (w3, b3) = fcs
+    if nlb_weights is not None:
+        buf, sh = pack_projection(list(nlb_weights))
+        nlb_w = _SplitPacked.apply(buf, *nlb_weights)
+        op_proj, op_mask = sh, bf16_shadow(w_mask)
+    else:
+        nlb_w, op_proj, op_mask = None, None, None
+    ops = (op_proj, op_mask, bf16_shadow(w1), bf16_shadow(w2), bf16_shadow(w3))
+    return InstanceHeadChainFunction.apply(x, labels, nlb_w, w_mask, w1, b1, w2, b2, w3, b3, ops, (drop_p, seeds[0], seeds[1], grl))

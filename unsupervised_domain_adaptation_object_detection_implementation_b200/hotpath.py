@@ -95,7 +95,7 @@ class DAFOrgHotPath(nn.Module):
         bbox_feats = self.bbox_head(roi_feats) if self.bbox_head is not None else roi_feats.flatten(1)
         label_da = roi_domain_labels(tuple(len(p) for p in proposal_list), c5.device) if len(proposal_list) == 2 else \
             rois[:, 0].long().clamp(max=1)
-        ins_loss, ins_preds = da_losses.instance_ce_loss(self.local_da.forward_logits(bbox_feats), label_da)
+        ins_loss, ins_preds = self.local_da.forward_loss(bbox_feats, label_da)
         consist = da_losses.consistency_loss(imgs_feat, ins_preds, label_da)
         return dict(local_da_loss=self.local_lamda * ins_loss,
                     globle_da_loss=self.global_lamda * global_loss,
