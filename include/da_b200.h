@@ -330,6 +330,48 @@ int da_softmax_dim0_forward(const float* s, int T, int ldk, float* p, da_stream_
 int da_softmax_dim0_backward(const float* p, const float* dp, int T, int ldk, float* ds,
                              da_stream_t stream);
 
+/* ---- pixel-level domain classifier: producing conv -> terminal 1-channel conv -> per-pixel loss -> mean (north_star kernel 1) ----
+ * ImgAlignmentHead (resnet_da_daf_org.py:120-146) + L1 (:816-822); LocalAlignmentHead (resnet_da_cbam.py:77-115) + L2 (:971-979);
+ * plus the plain per-pixel sigmoid-BCE / focal modes north_star names (parity: F.binary_cross_entropy_with_logits,
+ * py_sigmoid_focal_loss losses/focal_loss.py:12-57).  The producing conv is the implicit GEMM of da_conv_forward (GRL, bias /
+ * folded BN, ReLU, dropout in its epilogue); the TAIL is one kernel: logit[m] = act(y[m,:].w + b), per-pixel loss term by
+ * `mode`, deterministic mean (per-block partials, the last block sums them in block order) -> loss scalar on the device.
+ * Backward tail = one kernel + one small reduction: d loss / d logit (times grad_loss * loss_scale, plus grad_logits from
+ * other consumers of the logits, e.g. the consistency loss), ReLU mask of the logit, terminal conv's weight / bias gradient,
+ * AND the activation derivative of the producing layer (ReLU / dropout taken from the stored y, folded-BN scale): it writes
+ * dz = d loss / d accumulator of the producing conv, ready for da_conv_backward_weight / _data (GRL weight = out_scale). */
+enum da_pixel_loss_mode {
+  DA_PIXEL_LOSS_DAF_SQ_BATCH = 0,  /* L1: 0.5*mean(sigmoid(p)^2) | 0.5*mean(sigmoid(1-p)^2), means over the WHOLE batch per slot (Q5) */
+  DA_PIXEL_LOSS_DAF_SQ_IMAGE = 1,  /* L2: the same integrands, mean per image */
+  DA_PIXEL_LOSS_BCE = 2,           /* sigmoid BCE against the image's domain label, mean over all pixels */
+  DA_PIXEL_LOSS_FOCAL = 3          /* sigmoid focal loss (gamma, alpha) against the domain label, mean over all pixels */
+};
+typedef struct da_pixel_tail {
+  const float* w;         /* [K] fp32 weights of the terminal 1-channel conv (K = Cout of the producing conv) */
+  const float* bias;      /* [1] or NULL */
+  int relu;               /* ReLU on the logit (ImgAlignmentHead: resnet_da_daf_org.py:131) */
+  int mode;               /* enum da_pixel_loss_mode */
+  float gamma, alpha;     /* focal */
+  const int32_t* domain;  /* [N] 0 = source, 1 = target */
+} da_pixel_tail;
+/* `d` describes the PRODUCING conv (x -> y); logits [N,OH,OW] fp32; loss fp32 scalar. */
+size_t da_grl_conv_loss_workspace_bytes(const da_conv_desc* d);
+int da_pixel_tail_forward(const da_conv_desc* d, const void* y, const da_pixel_tail* tail, float* logits, float* loss,
+                          void* workspace, size_t workspace_bytes, da_stream_t stream);
+int da_pixel_tail_backward(const da_conv_desc* d, const void* y, const da_pixel_tail* tail, const float* logits,
+                           const float* grad_loss, float loss_scale, const float* grad_logits, const float* scale, int act_relu,
+                           float drop_p, void* dz, float* dw_tail, float* dbias_tail, float* dshift, float* dvdot,
+                           void* workspace, size_t workspace_bytes, da_stream_t stream);
+/* Composite: conv (+ fused epilogue) -> tail; tail -> weight gradient -> data gradient * grl.  dx / dw nullable. */
+int da_grl_conv_loss_forward(const da_conv_desc* d, const void* x, const void* w, const float* scale, const float* shift,
+                             int relu, float drop_p, uint64_t drop_seed, void* y, const da_pixel_tail* tail, float* logits,
+                             float* loss, void* workspace, size_t workspace_bytes, da_stream_t stream);
+int da_grl_conv_loss_backward(const da_conv_desc* d, const void* x, const void* w, const float* scale, int relu, float drop_p,
+                              const void* y, const da_pixel_tail* tail, const float* logits, const float* grad_loss,
+                              float loss_scale, const float* grad_logits, float grl, void* dx, float* dw, float* dshift,
+                              float* dvdot, float* dw_tail, float* dbias_tail, void* dz_scratch, void* workspace,
+                              size_t workspace_bytes, da_stream_t stream);
+
 /* ---- instance-level domain classifier + its loss as ONE persistent kernel (forward) / ONE (backward) ----------------------
  * InstanceAlignmentHead (nlb = 1: GRL -> NonLocalBlock over the R RoIs -> FC C-H1-H2-2 -> sigmoid, mmdet/models/roi_heads/
  * instance_da.py:42-101,150-192) or InstanceAlignmentHead_DAF (nlb = 0, :103-148) fused with the CE-on-sigmoid instance loss

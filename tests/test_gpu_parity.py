@@ -959,3 +959,86 @@ def test_instance_head_chain_golden_and_packed_projection_state(golden):
     m2 = m.float().cpu().to(DEV)                                                                          # storages separated
     _, pred3 = m2.forward_loss(x, torch.zeros(x.shape[0], dtype=torch.long, device=DEV))
     assert rel_err(pred3, pred2) <= 1e-6
+
+
+# ---------------------------------------------------------------------------- fused pixel tail (north_star kernel 1) + BCE / focal modes
+def _tail_reference(mode, p, gt, gamma=2.0, alpha=0.25):
+    """Per-pixel loss on logits p [N,1,H,W] (double) against the image's domain label."""
+    if mode == "daf_sq_batch":
+        return da_oracle.daf_image_loss(p, gt)
+    if mode == "daf_sq_image":
+        return da_oracle.patch_loss(p, gt)
+    t = gt.to(p.dtype).view(-1, 1, 1, 1).expand_as(p)
+    if mode == "bce":
+        return torch.nn.functional.binary_cross_entropy_with_logits(p, t)                  # mean over all pixels
+    # py_sigmoid_focal_loss (mmdet/models/losses/focal_loss.py:12-57), reduction='mean'
+    s = p.sigmoid()
+    pt = (1 - s) * t + s * (1 - t)
+    fw = (alpha * t + (1 - alpha) * (1 - t)) * pt.pow(gamma)
+    return (torch.nn.functional.binary_cross_entropy_with_logits(p, t, reduction="none") * fw).mean()
+
+
+@pytest.mark.parametrize("engine,tol", [("simt_f32", FP32_TOL), ("umma_bf16x6", FP32_TOL), ("umma_bf16", BF16_TOL)])
+@pytest.mark.parametrize("mode", ["daf_sq_batch", "daf_sq_image", "bce", "focal"])
+@pytest.mark.parametrize("head", ["img_alignment", "local_alignment"])
+def test_pixel_head_fused_loss_modes_vs_oracle(golden, head, mode, engine, tol):
+    """da_grl_conv_loss_forward/backward: the pixel-level heads with their loss fused into the tail kernel, all four per-pixel
+    modes (the reference's L1 / L2 and the plain sigmoid-BCE / focal modes, against F.binary_cross_entropy_with_logits and the
+    py_sigmoid_focal_loss formula), loss + logits + input gradient (GRL folded) + every parameter gradient, plus a second
+    consumer of the logits (as the consistency loss is)."""
+    uda.set_engine(engine)
+    g = golden(f"head_{head}.pt")
+    m = build_head(head, g["seed"])
+    q = "bf16" if engine == "umma_bf16" else None
+    x = g["x"].bfloat16().float() if q else g["x"]
+    gt = torch.tensor([0, 1])
+    cot = g["cot"][0] * 0.05
+    sd = {k: v.detach().double().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in m.state_dict().items()}
+    xr = x.double().requires_grad_(True)
+    pr = HEADS[head][1](xr, sd, q=q)
+    lr_ = _tail_reference(mode, pr, gt)
+    (0.3 * lr_ + (pr * cot.double()).sum()).backward()
+    m = m.to(DEV)
+    xc = x.to(DEV).requires_grad_(True)
+    loss, feat = m.forward_loss(xc, gt.to(DEV), mode=mode)
+    assert feat.shape == pr.shape
+    assert rel_err(feat, pr) <= tol
+    assert abs(float(loss) - float(lr_)) <= tol * abs(float(lr_)), (float(loss), float(lr_))
+    (0.3 * loss + (feat * cot.to(DEV)).sum()).backward()
+    gtol = 2 * tol if q else 5 * tol
+    assert rel_err(xc.grad, xr.grad) <= gtol
+    for k, p in m.named_parameters():
+        if sd[k].grad is None:
+            continue
+        assert p.grad is not None, k
+        a, b = p.grad.double().cpu(), sd[k].grad
+        assert float((a - b).norm() / b.norm().clamp_min(1e-30)) <= (5e-2 if q else 5 * tol), k
+
+
+def test_pixel_tail_matches_unfused_path_at_bench_size():
+    """H1 + L1 at the benchmarked size (C5 [2,2048,64,128]): fused tail vs the separate pixel_head / pixel_domain_loss kernels
+    (same GEMM in front): identical logits, loss to 1e-6, gradients to bf16 rounding of dz."""
+    uda.set_engine("umma_bf16")
+    from unsupervised_domain_adaptation_object_detection_implementation_b200 import da_heads
+    torch.manual_seed(0)
+    m = da_heads.ImgAlignmentHead(2048)
+    seeded.fill_state_(m, 5, "tailbench.")
+    m = m.to(DEV)
+    g = torch.Generator(device=DEV).manual_seed(3)
+    x = torch.relu(torch.randn(2, 64, 128, 2048, device=DEV, generator=g)).to(torch.bfloat16).permute(0, 3, 1, 2)
+    gt = torch.tensor([0, 1], device=DEV)
+    xa = x.detach().requires_grad_(True)
+    la, fa = m.forward_loss(xa, gt)
+    la.backward()
+    ga = {k: p.grad.clone() for k, p in m.named_parameters()}
+    for p in m.parameters():
+        p.grad = None
+    xb = x.detach().requires_grad_(True)
+    fb = m(xb)
+    lb = da_losses.daf_image_loss(fb, gt)
+    lb.backward()
+    assert torch.equal(fa, fb) or rel_err(fa, fb) <= 1e-6
+    assert abs(float(la) - float(lb)) <= 1e-6 * abs(float(lb))
+    assert rel_err(xa.grad.float(), xb.grad.float()) <= 2e-2
+    for k, p in m.named_parameters():
+        assert float((ga[k] - p.grad).norm() / p.grad.norm().clamp_min(1e-30)) <= 2e-2, k

@@ -65,6 +65,15 @@ class InstanceFcGrads(Structure):
                 ("db3", c_void_p), ("dz2", c_void_p), ("dz1", c_void_p), ("dt", c_void_p), ("dy", c_void_p), ("dproj", c_void_p)]
 
 
+class PixelTail(Structure):
+    """da_pixel_tail."""
+    _fields_ = [("w", c_void_p), ("bias", c_void_p), ("relu", c_int), ("mode", c_int), ("gamma", c_float), ("alpha", c_float),
+                ("domain", c_void_p)]
+
+
+PIXEL_LOSS_MODES = {"daf_sq_batch": 0, "daf_sq_image": 1, "bce": 2, "focal": 3}
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -133,6 +142,11 @@ SIGNATURES = {
     "da_global_avgpool_backward": (I, [P, I, I, I, P, I, P]),
     "da_softmax_dim0_forward": (I, [P, I, I, P, P]),
     "da_softmax_dim0_backward": (I, [P, P, I, I, P, P]),
+    "da_grl_conv_loss_workspace_bytes": (S, [CD]),
+    "da_pixel_tail_forward": (I, [CD, P, POINTER(PixelTail), P, P, P, S, P]),
+    "da_pixel_tail_backward": (I, [CD, P, POINTER(PixelTail), P, P, F, P, P, I, F, P, P, P, P, P, P, S, P]),
+    "da_grl_conv_loss_forward": (I, [CD, P, P, P, P, I, F, U64, P, POINTER(PixelTail), P, P, P, S, P]),
+    "da_grl_conv_loss_backward": (I, [CD, P, P, P, I, F, P, POINTER(PixelTail), P, P, F, P, F, P, P, P, P, P, P, P, P, S, P]),
     "da_instance_fc_workspace_bytes": (S, [I]),
     "da_instance_fc_forward": (I, [POINTER(InstanceFcDesc), POINTER(InstanceFcTensors), P, S, P]),
     "da_instance_fc_backward": (I, [POINTER(InstanceFcDesc), POINTER(InstanceFcTensors), POINTER(InstanceFcGrads), P, S, P]),

@@ -137,14 +137,13 @@ class ResNet_DAF(_ResNetTrunk):
         self.da_outs_idx = (3,)
 
     def forward_train(self, x, gt_domain):
-        outs, patch_feat = [], None
+        outs, patch_feat, loss = [], None, None
         for i, f in self._stages(x):
             if i in self.da_outs_idx:
                 if i in self.out_indices:
                     outs.append(f)
                 if i == 3:
-                    patch_feat = self.da_head_top(f)
-        loss = da_losses.daf_image_loss(patch_feat, gt_domain)
+                    loss, patch_feat = self.da_head_top.forward_loss(f, gt_domain)      # H1 + L1: GEMM + fused tail kernel
         return tuple(outs), loss, patch_feat
 
 
@@ -182,7 +181,9 @@ class _GlobalLocal(_ResNetTrunk):
                 if i in self.out_indices:
                     outs.append(f)
                 if i in local_heads:
-                    patch = patch + da_losses.patch_loss(local_heads[i](f), gt_domain)
+                    head = local_heads[i]
+                    patch = patch + (head.forward_loss(f, gt_domain)[0] if hasattr(head, "forward_loss") else
+                                     da_losses.patch_loss(head(f), gt_domain))
                 if i == 2:
                     glob.append(da_losses.image_ce_loss(self.da_head_mid(f), gt_domain, False)[0])
                 elif i == 3:

@@ -77,6 +77,7 @@ struct ChainParams {
   int group_begin[CH_MAX_GROUPS + 1];
   unsigned int* barrier;                    // zeroed by the host before the launch
   const unsigned long long* seed_ctr;
+  unsigned long long* trace;                // debug (da_set_option("chain_trace", ptr)): globaltimer stamps of CTA 0
   ChainOp ops[CH_MAX_OPS];
 };
 
@@ -205,30 +206,57 @@ __device__ __forceinline__ void ch_epilogue_chunk(const ChainOp& o, const uint32
 
 // ---- elementwise ops: executed by ALL threads of every CTA after the group's GEMM tiles ------------------------------
 // Column-wise (query-axis) softmax of S [R rows (q), R columns (k)]: a CTA owns 8 columns at a time, its threads are
-// (row group, column) pairs; three passes over an L2-resident slab (max, sum of exp, normalise).
+// (row group, column) pairs.  One read pass: a thread keeps its (up to CH_SM_ROWS) values of the column in registers, the 40
+// row groups of the CTA are combined through shared memory in a fixed order (deterministic), then the registers are
+// normalised and written.  Columns taller than 40 * CH_SM_ROWS rows take the three-pass form.
+constexpr int CH_SM_ROWS = 26;      // 40 row groups x 26 = 1040 rows: covers the 1024 RoIs of a pair
 __device__ void ch_softmax_col_fwd(const ChainOp& o, float* red) {
   const float* S = reinterpret_cast<const float*>(o.p0);
   __nv_bfloat16* Pm = reinterpret_cast<__nv_bfloat16*>(o.q0);
   const int R = o.i0, ldS = o.i1, ldP = o.i2;
   const int col = threadIdx.x & 7, rg = threadIdx.x >> 3, nrg = CH_THREADS / 8;   // 40 row groups
+  const bool in_regs = R <= nrg * CH_SM_ROWS;
   for (int c0 = blockIdx.x * 8; c0 < R; c0 += gridDim.x * 8) {
     const int c = c0 + col;
     const bool ok = c < R;
+    float v[CH_SM_ROWS];
     float mx = -INFINITY;
-    if (ok) for (int r = rg; r < R; r += nrg) mx = fmaxf(mx, S[(size_t)r * ldS + c]);
+    if (in_regs) {
+#pragma unroll
+      for (int i = 0; i < CH_SM_ROWS; ++i) {
+        const int r = rg + i * nrg;
+        v[i] = (ok && r < R) ? S[(size_t)r * ldS + c] : -INFINITY;
+        mx = fmaxf(mx, v[i]);
+      }
+    } else if (ok) {
+      for (int r = rg; r < R; r += nrg) mx = fmaxf(mx, S[(size_t)r * ldS + c]);
+    }
     red[rg * 8 + col] = mx;
     __syncthreads();
     for (int g = 0; g < nrg; ++g) mx = fmaxf(mx, red[g * 8 + col]);
     __syncthreads();
     float sum = 0.f;
-    if (ok) for (int r = rg; r < R; r += nrg) sum += expf(S[(size_t)r * ldS + c] - mx);
+    if (in_regs) {
+#pragma unroll
+      for (int i = 0; i < CH_SM_ROWS; ++i) { v[i] = ok ? expf(v[i] - mx) : 0.f; sum += v[i]; }     // exp(-inf) = 0 for the padding rows
+    } else if (ok) {
+      for (int r = rg; r < R; r += nrg) sum += expf(S[(size_t)r * ldS + c] - mx);
+    }
     red[rg * 8 + col] = sum;
     __syncthreads();
     sum = 0.f;
     for (int g = 0; g < nrg; ++g) sum += red[g * 8 + col];     // fixed order: deterministic
     __syncthreads();
     const float inv = 1.f / sum;
-    if (ok) for (int r = rg; r < R; r += nrg) Pm[(size_t)r * ldP + c] = __float2bfloat16_rn(expf(S[(size_t)r * ldS + c] - mx) * inv);
+    if (in_regs) {
+#pragma unroll
+      for (int i = 0; i < CH_SM_ROWS; ++i) {
+        const int r = rg + i * nrg;
+        if (ok && r < R) Pm[(size_t)r * ldP + c] = __float2bfloat16_rn(v[i] * inv);
+      }
+    } else if (ok) {
+      for (int r = rg; r < R; r += nrg) Pm[(size_t)r * ldP + c] = __float2bfloat16_rn(expf(S[(size_t)r * ldS + c] - mx) * inv);
+    }
   }
 }
 
@@ -238,19 +266,40 @@ __device__ void ch_softmax_col_bwd(const ChainOp& o, float* red) {
   __nv_bfloat16* dS = reinterpret_cast<__nv_bfloat16*>(o.q0);
   const int R = o.i0, ldP = o.i1, ldD = o.i2, ldO = o.i3;
   const int col = threadIdx.x & 7, rg = threadIdx.x >> 3, nrg = CH_THREADS / 8;
+  const bool in_regs = R <= nrg * CH_SM_ROWS;
   for (int c0 = blockIdx.x * 8; c0 < R; c0 += gridDim.x * 8) {
     const int c = c0 + col;
     const bool ok = c < R;
+    float p[CH_SM_ROWS], d[CH_SM_ROWS];
     float dot = 0.f;
-    if (ok) for (int r = rg; r < R; r += nrg) dot += __bfloat162float(Pm[(size_t)r * ldP + c]) * dP[(size_t)r * ldD + c];
+    if (in_regs) {
+#pragma unroll
+      for (int i = 0; i < CH_SM_ROWS; ++i) {
+        const int r = rg + i * nrg;
+        const bool in = ok && r < R;
+        p[i] = in ? __bfloat162float(Pm[(size_t)r * ldP + c]) : 0.f;
+        d[i] = in ? dP[(size_t)r * ldD + c] : 0.f;
+        dot += p[i] * d[i];
+      }
+    } else if (ok) {
+      for (int r = rg; r < R; r += nrg) dot += __bfloat162float(Pm[(size_t)r * ldP + c]) * dP[(size_t)r * ldD + c];
+    }
     red[rg * 8 + col] = dot;
     __syncthreads();
     dot = 0.f;
     for (int g = 0; g < nrg; ++g) dot += red[g * 8 + col];
     __syncthreads();
-    if (ok) for (int r = rg; r < R; r += nrg) {
-      const float p = __bfloat162float(Pm[(size_t)r * ldP + c]);
-      dS[(size_t)r * ldO + c] = __float2bfloat16_rn(p * (dP[(size_t)r * ldD + c] - dot));
+    if (in_regs) {
+#pragma unroll
+      for (int i = 0; i < CH_SM_ROWS; ++i) {
+        const int r = rg + i * nrg;
+        if (ok && r < R) dS[(size_t)r * ldO + c] = __float2bfloat16_rn(p[i] * (d[i] - dot));
+      }
+    } else if (ok) {
+      for (int r = rg; r < R; r += nrg) {
+        const float pv = __bfloat162float(Pm[(size_t)r * ldP + c]);
+        dS[(size_t)r * ldO + c] = __float2bfloat16_rn(pv * (dP[(size_t)r * ldD + c] - dot));
+      }
     }
   }
 }
@@ -355,6 +404,16 @@ chain_kernel(const __grid_constant__ ChainParams P) {
   const unsigned long long seed_add = P.seed_ctr ? *P.seed_ctr : 0ull;
 
   int kq = 0, tcount = 0;       // ring position (producer / MMA thread), accumulator hand-overs (MMA thread / epilogue warps)
+  int tr = 0;
+#define CH_STAMP()                                                                                        \
+  do {                                                                                                    \
+    if (P.trace && blockIdx.x == 0 && threadIdx.x == 0) {                                                 \
+      unsigned long long t_;                                                                              \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                              \
+      P.trace[tr++] = t_;                                                                                 \
+    }                                                                                                     \
+  } while (0)
+  CH_STAMP();
   for (int g = 0; g < P.ngroups; ++g) {
     const int ob = P.group_begin[g], oe = P.group_begin[g + 1];
     int total = 0;
@@ -439,6 +498,7 @@ chain_kernel(const __grid_constant__ ChainParams P) {
     // the operand ring doubles as scratch of the elementwise ops: every MMA that read it has completed (the epilogue
     // warps waited for the last accumulator) once all warps are here
     __syncthreads();
+    CH_STAMP();        // GEMM tiles of the group done (this CTA)
     for (int o = ob; o < oe; ++o) {
       const ChainOp& e = P.ops[o];
       switch (e.kind) {
@@ -450,11 +510,17 @@ chain_kernel(const __grid_constant__ ChainParams P) {
         default: break;
       }
     }
+    CH_STAMP();        // elementwise ops done
     if (g + 1 < P.ngroups) grid_sync(P.barrier, (unsigned int)(g + 1) * gridDim.x);
+    // after the LAST grid barrier nothing in this grid waits for another CTA any more: the dependent grid may start its
+    // prologue now (its CTAs only get an SM when one of ours exits)
+    if (g + 2 == P.ngroups) pdl_launch_dependents();
+    CH_STAMP();        // barrier passed
   }
+#undef CH_STAMP
   tc_fence_before();
   __syncthreads();
-  pdl_launch_dependents();
+  if (P.ngroups < 2) pdl_launch_dependents();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 2 * CH_BN);
@@ -518,6 +584,7 @@ static int launch_chain(Builder& b, unsigned int* barrier, cudaStream_t st) {
   if (rc) return rc;
   b.P.barrier = barrier;
   b.P.seed_ctr = g_seed_counter;
+  b.P.trace = reinterpret_cast<unsigned long long*>(g_opt.chain_trace);
   int max_tiles = 1;
   for (int g = 0; g < b.P.ngroups; ++g) {
     int t = 0;

@@ -275,6 +275,7 @@ extern "C" int da_set_option(const char* name, long long value) {
   else if (!strcmp(name, "umma_dbg")) g_opt.umma_dbg = (int)value;
   else if (!strcmp(name, "roi_bwd_dbg")) g_opt.roi_bwd_dbg = (int)value;
   else if (!strcmp(name, "roi_bwd_trace")) g_opt.roi_bwd_trace = (unsigned long long)value;
+  else if (!strcmp(name, "chain_trace")) g_opt.chain_trace = (unsigned long long)value;
   else DA_REQUIRE(false, DA_ERR_INVALID_ARG, "set_option: unknown option '%s'", name);
   return DA_OK;
 }

@@ -129,6 +129,19 @@ class ImgAlignmentHead(_HeadBase):
         logits = F_.pixel_head(h, self.conv2.weight, self.conv2.bias, relu=True)  # [N,H,W]
         return logits.unsqueeze(1)
 
+    def forward_loss(self, x, gt_domain, mode="daf_sq_batch", gamma=2.0, alpha=0.25):
+        """(loss, img_feat [N,1,H,W]): the head AND its per-pixel domain loss (L1 by default: resnet_da_daf_org.py:816-822; 'bce' /
+        'focal' are the plain per-pixel modes) as conv1 (tcgen05 GEMM, GRL folded into its data gradient) + ONE tail kernel
+        (conv2 + bias + ReLU + loss + mean); backward = one tail kernel (loss', conv2 gradients, ReLU mask of conv1) + the
+        weight / data gradient GEMMs (functional.conv_pixel_loss -> da_grl_conv_loss_forward/backward)."""
+        if not USE_FUSED_TAIL:
+            feat = self.forward(x)
+            return F_.pixel_domain_loss(feat, gt_domain, True), feat
+        a = F_.to_nhwc(x, F_.act_dtype())
+        loss, logits = F_.conv_pixel_loss(a, self.conv1.weight, None, self.conv1.bias, self.conv2.weight, self.conv2.bias, gt_domain,
+                                          relu=True, grl=self.grl.weight, tail_relu=True, mode=mode, gamma=gamma, alpha=alpha)
+        return loss, logits.unsqueeze(1)
+
     def _init_weights(self):
         normal_init(self.conv1, 0, 0.001)
         normal_init(self.conv2, 0, 0.001)
@@ -155,6 +168,17 @@ class LocalAlignmentHead(_HeadBase):
         normal_init(self.conv1, 0, 0.01)
         normal_init(self.conv2, 0, 0.01)
         normal_init(self.conv3, 0, 0.01)
+
+    def forward_loss(self, x, gt_domain, mode="daf_sq_image", gamma=2.0, alpha=0.25):
+        """(loss, local_feat [N,1,H,W]): the head AND its per-pixel loss (L2 by default: resnet_da_cbam.py:971-979).  conv1 is
+        a plain fused layer; conv2 (+BN+ReLU+dropout) -> conv3 -> loss -> mean run as GEMM + one tail kernel."""
+        a = F_.to_nhwc(x, F_.act_dtype())
+        h = self._layer(a, self.conv1, self.bn1, grl=self.grl.weight)
+        scale, shift = bn_affine(self.bn2, self.conv2.bias)
+        p = self._p()
+        loss, logits = F_.conv_pixel_loss(h, self.conv2.weight, scale, shift, self.conv3.weight, None, gt_domain, relu=True, drop_p=p,
+                                          seed=_draw_seed(self.training, p), tail_relu=False, mode=mode, gamma=gamma, alpha=alpha)
+        return loss, logits.unsqueeze(1)
 
     def forward(self, x):
         a = F_.to_nhwc(x, F_.act_dtype())
@@ -401,6 +425,7 @@ class NonLocalAlignmentHead(_HeadBase):
 
 
 USE_CHAIN = True      # functional.instance_head_chain for the instance heads on the bf16 engine (False: layer by layer)
+USE_FUSED_TAIL = True # functional.conv_pixel_loss for the pixel-level heads (False: separate pixel_head / loss kernels)
 
 
 def _chain_ok(x):

@@ -856,3 +856,101 @@ def instance_head_chain(x, labels, nlb_weights, w_mask, fcs, drop_p, seeds, grl)
         nlb_w, op_proj, op_mask = None, None, None
     ops = (op_proj, op_mask, bf16_shadow(w1), bf16_shadow(w2), bf16_shadow(w3))
     return InstanceHeadChainFunction.apply(x, labels, nlb_w, w_mask, w1, b1, w2, b2, w3, b3, ops, (drop_p, seeds[0], seeds[1], grl))
+
+
+# --------------------------------------------------------------------------------------
+# pixel-level domain classifier tail: producing conv -> 1-channel conv -> per-pixel loss -> mean (csrc/pixel_tail.cu)
+# --------------------------------------------------------------------------------------
+class ConvPixelLossFunction(Function):
+    """(loss, logits) = tail(act(conv(x, w) * scale + shift)): the last two layers of a pixel-level domain classifier and its
+    loss (da_grl_conv_loss_forward / _backward).  `grl` multiplies the gradient into x (first layer of a head) -- pass 1.0
+    for an inner layer."""
+
+    @staticmethod
+    def forward(ctx, x, w, scale, shift, w_tail, b_tail, domain, cfg, shadow):
+        stride, pad, relu, drop_p, seed, engine, grl, tail_relu, mode, gamma, alpha = cfg
+        _require_cuda(x, w)
+        N, H, W_, Cin = x.shape
+        x = x.contiguous()
+        if shadow is not None:
+            wv = _w_ohwi(shadow)
+        else:
+            wv = _w_ohwi(w.detach())
+            if wv.dtype != x.dtype:
+                wv = cast(wv, x.dtype)
+        Cout, KH, KW, _ = wv.shape
+        OH, OW = (H + 2 * pad - KH) // stride + 1, (W_ + 2 * pad - KW) // stride + 1
+        dev = x.device
+        y = torch.empty((N, OH, OW, Cout), dtype=x.dtype, device=dev)
+        logits = torch.empty((N, OH, OW), dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        desc = _conv_desc(N, H, W_, Cin, Cout, KH, KW, stride, pad, engine, x.dtype, x.dtype)
+        ws = workspace(lib.da_grl_conv_loss_workspace_bytes(ctypes.byref(desc)), dev, "conv_tail")
+        sc = None if scale is None else scale.detach().float().contiguous()
+        sh = None if shift is None else shift.detach().float().contiguous()
+        wt = w_tail.detach().reshape(-1).float().contiguous()
+        bt = None if b_tail is None else b_tail.detach().reshape(-1).float().contiguous()
+        dom = _as_i32(domain, dev)
+        tail = _lib.PixelTail(wt.data_ptr(), None if bt is None else bt.data_ptr(), int(tail_relu), _lib.PIXEL_LOSS_MODES[mode],
+                              float(gamma), float(alpha), dom.data_ptr())
+        check(lib.da_grl_conv_loss_forward(ctypes.byref(desc), _ptr(x), _ptr(wv), _ptr(sc), _ptr(sh), int(relu), float(drop_p), int(seed),
+                                           _ptr(y), ctypes.byref(tail), _ptr(logits), _ptr(loss), _ptr(ws), ws.numel(), _stream()),
+              "grl_conv_loss_forward")
+        ctx.save_for_backward(x, wv, y, sc, sh, wt, bt, dom, logits)
+        ctx.cfg, ctx.desc = cfg, desc
+        ctx.meta = (w.shape, w.dtype, w_tail.shape, b_tail is not None)
+        return loss, logits
+
+    @staticmethod
+    def backward(ctx, g_loss, g_logits):
+        x, wv, y, sc, sh, wt, bt, dom, logits = ctx.saved_tensors
+        stride, pad, relu, drop_p, seed, engine, grl, tail_relu, mode, gamma, alpha = ctx.cfg
+        wshape, wdtype, wt_shape, has_bt = ctx.meta
+        dev = x.device
+        Cout, KH, KW, Cin = wv.shape
+        gl = None if g_loss is None else g_loss.contiguous().float()
+        gq = None if g_logits is None else g_logits.contiguous().float()
+        need_x, need_w, need_scale, need_shift = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2], ctx.needs_input_grad[3]
+        dx = torch.empty_like(x) if need_x else None
+        dwv = torch.empty((Cout, KH, KW, Cin), dtype=torch.float32, device=dev) if need_w else None
+        dshift = torch.empty((Cout,), dtype=torch.float32, device=dev)
+        dvdot = torch.empty((Cout,), dtype=torch.float32, device=dev)
+        dwt = torch.empty((Cout,), dtype=torch.float32, device=dev)
+        dbt = torch.empty((1,), dtype=torch.float32, device=dev)
+        dz = torch.empty_like(y)
+        tail = _lib.PixelTail(wt.data_ptr(), None if bt is None else bt.data_ptr(), int(tail_relu), _lib.PIXEL_LOSS_MODES[mode],
+                              float(gamma), float(alpha), dom.data_ptr())
+        ws = workspace(lib.da_grl_conv_loss_workspace_bytes(ctypes.byref(ctx.desc)), dev, "conv_tail")
+        check(lib.da_grl_conv_loss_backward(ctypes.byref(ctx.desc), _ptr(x), _ptr(wv), _ptr(sc), int(relu), float(drop_p), _ptr(y),
+                                            ctypes.byref(tail), _ptr(logits), _ptr(gl), 1.0, _ptr(gq), float(grl), _ptr(dx), _ptr(dwv),
+                                            _ptr(dshift), _ptr(dvdot), _ptr(dwt), _ptr(dbt), _ptr(dz), _ptr(ws), ws.numel(), _stream()),
+              "grl_conv_loss_backward")
+        dw = None
+        if need_w:
+            dw = dwv.view(wshape) if len(wshape) == 2 else dwv.permute(0, 3, 1, 2)
+            if wdtype != torch.float32:
+                dw = dw.to(wdtype)
+            elif WGRAD_HOOK is not None:
+                WGRAD_HOOK(dwv)
+        dscale = None
+        if need_scale:
+            t = sh if sh is not None else torch.zeros_like(dshift)
+            safe = torch.where(sc == 0, torch.ones_like(sc), sc)
+            dscale = torch.where(sc == 0, torch.zeros_like(sc), (dvdot - t * dshift) / safe)
+        return (dx, dw, dscale, dshift if need_shift else None, dwt.view(wt_shape), dbt if has_bt else None, None, None, None)
+
+
+def conv_pixel_loss(x, w, scale, shift, w_tail, b_tail, domain, stride=1, pad=0, relu=True, drop_p=0.0, seed=0, engine=None, grl=1.0,
+                    tail_relu=False, mode="daf_sq_batch", gamma=2.0, alpha=0.25):
+    """x [N,H,W,Cin] NHWC; w the producing conv's weight; (scale, shift): bias / folded BN; w_tail [1,Cout,1,1], b_tail [1] or None;
+    domain [N].  -> (loss scalar, logits [N,OH,OW] fp32).  mode: 'daf_sq_batch' (L1), 'daf_sq_image' (L2), 'bce', 'focal'."""
+    engine = engine or get_engine()
+    if engine != "simt_f32" and not (_umma_ok(x, w) and stride <= 2):
+        engine = "simt_f32"
+    if mode not in _lib.PIXEL_LOSS_MODES:
+        raise ValueError(f"unknown pixel loss mode {mode!r}; choose from {sorted(_lib.PIXEL_LOSS_MODES)}")
+    shadow = None
+    if w.dtype == torch.float32 and x.dtype == torch.bfloat16 and w.is_leaf and _dense_memory(w):
+        shadow = bf16_shadow(w)
+    cfg = (stride, pad, int(relu), float(drop_p), int(seed), engine, float(grl), int(tail_relu), mode, float(gamma), float(alpha))
+    return ConvPixelLossFunction.apply(x, w, scale, shift, w_tail, b_tail, domain, cfg, shadow)

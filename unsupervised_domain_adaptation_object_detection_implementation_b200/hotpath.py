@@ -88,8 +88,7 @@ class DAFOrgHotPath(nn.Module):
         """c5 [N,C,H,W]; proposal_list: per-image [n_i,4] boxes (image 0 = source, 1 = target);
         gt_da: per-image domain (0/1).  Returns the reference's DA entries of the losses dict."""
         gt_domain = domain_tensor(gt_da, c5.device)
-        imgs_feat = self.da_head_top(c5)
-        global_loss = da_losses.daf_image_loss(imgs_feat, gt_domain)
+        global_loss, imgs_feat = self.da_head_top.forward_loss(c5, gt_domain)      # H1 + L1: GEMM + one fused tail kernel
         rois = bbox2roi(proposal_list)
         roi_feats = self.bbox_roi_extractor([c5], rois)
         bbox_feats = self.bbox_head(roi_feats) if self.bbox_head is not None else roi_feats.flatten(1)
@@ -119,10 +118,9 @@ class CBAMHotPath(nn.Module):
 
     def forward_train(self, c3, c4, c5, gt_da):
         gt_domain = domain_tensor(gt_da, c5.device)
-        local_feat = self.local_da_head_bottom(c3)
+        patch, local_feat = self.local_da_head_bottom.forward_loss(c3, gt_domain)   # H2 + L2: fused tail
         g_mid, _ = da_losses.image_ce_loss(self.da_head_mid(c4), gt_domain, False)
         g_top, _ = da_losses.image_ce_loss(self.da_head_top(c5), gt_domain, False)
-        patch = da_losses.patch_loss(local_feat, gt_domain)
         return dict(globle_da_loss=self.global_lamda * (g_mid + g_top), patch_bottom_loss=self.patch_lamda * patch)
 
 
