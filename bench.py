@@ -218,7 +218,6 @@ def measure_engine(args, engine, rank, local, world, sample_clocks):
     host = [make_host_inputs(pairs, 1000 * rank + s, act) for s in range(2)]
     resident = [(c5.to(dev), bx.to(dev)) for c5, bx in host]
     h2d_bytes = host[0][0].numel() * host[0][0].element_size() + host[0][1].numel() * 4
-    loss_host = torch.zeros(1).pin_memory()
 
     def step_on(c5_dev, boxes_dev):
         total = None
@@ -311,7 +310,14 @@ def measure_engine(args, engine, rank, local, world, sample_clocks):
             dev_in[slot][1].copy_(bx_h, non_blocking=True)
             ev_ready[slot].record(copy_stream)
 
+    loss_ring = [torch.zeros(1).pin_memory() for _ in range(2)]
+    ev_loss = [torch.cuda.Event() for _ in range(2)]
+    seen = [0.0]
+
     def step_e2e(i):
+        """Step i from HOST inputs; the loss of EVERY step is copied to pinned host memory and read by the host -- one step
+        late (while step i runs the host waits for, and reads, the loss of step i-1; the closing synchronize of the timed
+        region delivers the last one), so the GPU never idles on the host's read."""
         slot = i % 2
         prefetch(i)
         prefetch(i + 1)
@@ -319,9 +325,12 @@ def measure_engine(args, engine, rank, local, world, sample_clocks):
         cur.wait_event(ev_ready[slot])
         loss = run_slot(slot)
         ev_free[slot].record(cur)
-        loss_host.copy_(loss.reshape(1), non_blocking=True)
-        cur.synchronize()                                   # the user reads the loss every step
-        return loss_host
+        loss_ring[slot].copy_(loss.reshape(1), non_blocking=True)
+        ev_loss[slot].record(cur)
+        if i > 0:
+            ev_loss[1 - slot].synchronize()                 # step i-1 has finished: its loss is on the host
+            seen[0] = float(loss_ring[1 - slot][0])         # the user reads the loss of every step
+        return loss_ring[slot]
 
     def barrier():
         if world > 1:

@@ -330,6 +330,16 @@ int da_softmax_dim0_forward(const float* s, int T, int ldk, float* p, da_stream_
 int da_softmax_dim0_backward(const float* p, const float* dp, int T, int ldk, float* ds,
                              da_stream_t stream);
 
+/* W1: the lambda-weighted DA loss entries AND their total in one launch (detectors/DAFaster_rcnn_Orig.py:143-157 weights,
+ * detectors/base.py:176-219 sum): scaled[i] = w[i] * *losses[i], total = sum_i scaled[i] (fixed order).  `losses_host` is a HOST
+ * array of n device pointers, `weights_host` a host array of n floats (n <= DA_MAX_WEIGHTED).  Backward: d losses[i] =
+ * w[i] * (grad_total + grad_scaled[i]) (either gradient nullable). */
+#define DA_MAX_WEIGHTED 8
+int da_weighted_sum_forward(const float* const* losses_host, const float* weights_host, int n, float* scaled, float* total,
+                            da_stream_t stream);
+int da_weighted_sum_backward(const float* weights_host, int n, const float* grad_total, const float* grad_scaled, float* d_losses,
+                             da_stream_t stream);
+
 /* ---- pixel-level domain classifier: producing conv -> terminal 1-channel conv -> per-pixel loss -> mean (north_star kernel 1) ----
  * ImgAlignmentHead (resnet_da_daf_org.py:120-146) + L1 (:816-822); LocalAlignmentHead (resnet_da_cbam.py:77-115) + L2 (:971-979);
  * plus the plain per-pixel sigmoid-BCE / focal modes north_star names (parity: F.binary_cross_entropy_with_logits,

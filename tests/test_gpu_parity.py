@@ -697,12 +697,19 @@ def test_daf_org_hot_path_at_bench_shape_vs_oracle(engine):
         acts.extend([sv["h1"].detach(), sv["h2"].detach()])
         return loss_c, pred_c
 
+    tail_orig = F_.conv_pixel_loss
+
+    def recording_tail(*a, **k):          # H1: conv1 + fused tail; its stored conv1 activation
+        loss_t, logits_t = tail_orig(*a, **k)
+        acts.insert(0, loss_t.grad_fn.saved_tensors[2].detach())
+        return loss_t, logits_t
+
     x = c5_nhwc.to(DEV).to(F_.act_dtype()).permute(0, 3, 1, 2).requires_grad_(True)
-    F_.dense_layer, F_.instance_head_chain = recording_dense_layer, recording_chain
+    F_.dense_layer, F_.instance_head_chain, F_.conv_pixel_loss = recording_dense_layer, recording_chain, recording_tail
     try:
         losses = model.forward_train(x, [boxes[0].to(DEV), boxes[1].to(DEV)], [0, 1])
     finally:
-        F_.dense_layer, F_.instance_head_chain = orig, chain_orig
+        F_.dense_layer, F_.instance_head_chain, F_.conv_pixel_loss = orig, chain_orig, tail_orig
     total, _ = hotpath.parse_losses(losses)
     total.backward()
     assert len(acts) == 5                                                   # H1 conv1, shared FC1, FC2, instance fc1, fc2

@@ -5,7 +5,7 @@ sys.path.insert(0, ".")
 from unsupervised_domain_adaptation_object_detection_implementation_b200 import functional as F_
 from oracle import seeded
 dev = "cuda"
-N, C, H, W, R = 4, 2048, 64, 128, 2048
+N, C, H, W, R = 2, 2048, 64, 128, 1024
 g = torch.Generator(device=dev).manual_seed(0)
 feat = torch.relu(torch.randn(N, H, W, C, device=dev, generator=g)).to(torch.bfloat16).permute(0, 3, 1, 2).requires_grad_(True)
 rois = seeded.synthetic_rois(R // N, N, H * 16, W * 16, 0).to(dev)

@@ -142,6 +142,8 @@ SIGNATURES = {
     "da_global_avgpool_backward": (I, [P, I, I, I, P, I, P]),
     "da_softmax_dim0_forward": (I, [P, I, I, P, P]),
     "da_softmax_dim0_backward": (I, [P, P, I, I, P, P]),
+    "da_weighted_sum_forward": (I, [POINTER(c_void_p), POINTER(c_float), I, P, P, P]),
+    "da_weighted_sum_backward": (I, [POINTER(c_float), I, P, P, P, P]),
     "da_grl_conv_loss_workspace_bytes": (S, [CD]),
     "da_pixel_tail_forward": (I, [CD, P, POINTER(PixelTail), P, P, P, S, P]),
     "da_pixel_tail_backward": (I, [CD, P, POINTER(PixelTail), P, P, F, P, P, I, F, P, P, P, P, P, P, S, P]),

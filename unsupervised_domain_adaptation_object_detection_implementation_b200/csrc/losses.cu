@@ -508,6 +508,26 @@ __global__ void softmax_dim0_bwd_kernel(const float* __restrict__ p, const float
 
 using namespace da;
 
+// ---------------------------------------------------------------------------------------
+// W1: lambda-weighting of the DA losses and their total (DAFaster_rcnn_Orig.py:143-157, base.py:176-219) in one launch
+// ---------------------------------------------------------------------------------------
+struct ScalarPtrs { const float* p[DA_MAX_WEIGHTED]; float w[DA_MAX_WEIGHTED]; };
+__global__ void weighted_sum_fwd_kernel(ScalarPtrs a, int n, float* __restrict__ scaled, float* __restrict__ total) {
+  pdl_launch_dependents();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < n; ++i) { const float v = a.w[i] * a.p[i][0]; scaled[i] = v; t += v; }    // fixed order
+    total[0] = t;
+  }
+}
+// d loss_i = w_i * (g_total + g_scaled[i])
+__global__ void weighted_sum_bwd_kernel(ScalarPtrs a, int n, const float* __restrict__ g_total, const float* __restrict__ g_scaled,
+                                        float* __restrict__ d_in) {
+  pdl_launch_dependents();
+  const int i = threadIdx.x;
+  if (i < n) d_in[i] = a.w[i] * ((g_total ? g_total[0] : 0.f) + (g_scaled ? g_scaled[i] : 0.f));
+}
+
 extern "C" size_t da_pixel_loss_workspace_bytes(int N, int64_t L) {
   return (size_t)(N > 0 ? N : 0) * pl_blocks(L) * 2 * sizeof(float) + 64;
 }
@@ -697,6 +717,25 @@ extern "C" int da_softmax_dim0_forward(const float* s, int T, int ldk, float* p,
 extern "C" int da_softmax_dim0_backward(const float* p, const float* dp, int T, int ldk, float* ds, da_stream_t stream) {
   DA_REQUIRE(T > 0 && ldk >= T && p && dp && ds, DA_ERR_INVALID_ARG, "softmax_dim0_backward: bad args");
   softmax_dim0_bwd_kernel<<<(T + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream>>>(p, dp, T, ldk, ds);
+  DA_LAUNCH_CHECK();
+  return DA_OK;
+}
+
+extern "C" int da_weighted_sum_forward(const float* const* losses_host, const float* weights_host, int n, float* scaled, float* total,
+                                       da_stream_t stream) {
+  DA_REQUIRE(n > 0 && n <= DA_MAX_WEIGHTED && losses_host && weights_host && scaled && total, DA_ERR_INVALID_ARG, "weighted_sum_forward: bad args (n=%d)", n);
+  ScalarPtrs a;
+  for (int i = 0; i < DA_MAX_WEIGHTED; ++i) { a.p[i] = i < n ? losses_host[i] : nullptr; a.w[i] = i < n ? weights_host[i] : 0.f; }
+  weighted_sum_fwd_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a, n, scaled, total);
+  DA_LAUNCH_CHECK();
+  return DA_OK;
+}
+extern "C" int da_weighted_sum_backward(const float* weights_host, int n, const float* grad_total, const float* grad_scaled, float* d_losses,
+                                        da_stream_t stream) {
+  DA_REQUIRE(n > 0 && n <= DA_MAX_WEIGHTED && weights_host && d_losses, DA_ERR_INVALID_ARG, "weighted_sum_backward: bad args (n=%d)", n);
+  ScalarPtrs a;
+  for (int i = 0; i < DA_MAX_WEIGHTED; ++i) { a.p[i] = nullptr; a.w[i] = i < n ? weights_host[i] : 0.f; }
+  weighted_sum_bwd_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a, n, grad_total, grad_scaled, d_losses);
   DA_LAUNCH_CHECK();
   return DA_OK;
 }

@@ -40,15 +40,17 @@ constexpr int BT_PF = 8;                                       // L2 prefetch di
 constexpr int BT_NRAW = 3;                                     // raw ring depth (copy latency ~3 pair times)
 constexpr size_t BT_SMEM = 1024 + 2 * (size_t)BT_OPS_BYTES + BT_NRAW * (size_t)BT_RAW_BYTES + BT_LIST * 4 + 256;
 
-template <typename TO>
+template <typename TO, bool kTrace>
 __global__ void __launch_bounds__(BT_THREADS, 1)
 roi_align_bwd_tc_kernel(const __nv_bfloat16* __restrict__ grad_out, int C, int H, int W, int R,
                         const unsigned char* __restrict__ ws, TO* __restrict__ grad_in, int tiles_x, int dbg, unsigned long long* trace) {
   if (dbg & 32) return;
   unsigned long long tr0 = 0, tr1 = 0, tr2 = 0, tr3 = 0;
-  unsigned long long* ptrace = (trace && blockIdx.x == 13 && blockIdx.y == 1 && blockIdx.z == 1) ? trace + 8 * (size_t)gridDim.x * gridDim.y * gridDim.z : nullptr;
-#define PSTAMP(pair, k) do { if (ptrace && (pair) < 64) ptrace[(pair) * 8 + (k)] = globaltimer_ns(); } while (0)
-  if (trace && threadIdx.x == 64) tr0 = globaltimer_ns();
+  unsigned long long* ptrace = (kTrace && trace && blockIdx.x == 13 && blockIdx.y == 1 && blockIdx.z == 1) ? trace + 8 * (size_t)gridDim.x * gridDim.y * gridDim.z : nullptr;
+  // per-pair stamps (tools/trace_roi_bwd.py) exist only in the kTrace instantiation: even predicated off they were ~4 % of the
+  // builder warps' issue slots (ncu source page, profiles/r02_roi_align_ncu.md)
+#define PSTAMP(pair, k) do { if (kTrace && ptrace && (pair) < 64) ptrace[(pair) * 8 + (k)] = globaltimer_ns(); } while (0)
+  if (kTrace && trace && threadIdx.x == 64) tr0 = globaltimer_ns();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -60,6 +62,7 @@ roi_align_bwd_tc_kernel(const __nv_bfloat16* __restrict__ grad_out, int C, int H
                  tfull = bars + 96, tslot = bars + 104;
   volatile uint32_t* tslot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tslot - base));
   __shared__ int s_wcount[BT_ROUNDS * BT_WARPS];
+  __shared__ int s_rows[2];     // per operand buffer: first tile row | (end tile row << 8) of the RoI's footprint in this tile
 
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int b = blockIdx.z;
@@ -124,7 +127,7 @@ roi_align_bwd_tc_kernel(const __nv_bfloat16* __restrict__ grad_out, int C, int H
     }
     __syncthreads();
     const int n_list = (dbg & 64) ? 0 : total;
-    if (trace && threadIdx.x == 64 && rbase == 0) tr1 = globaltimer_ns();
+    if (kTrace && trace && threadIdx.x == 64 && rbase == 0) tr1 = globaltimer_ns();
 
     if (warp == 0) {
       // ------------------------------------------------ producer: raw gradient chunks + table slices
@@ -180,13 +183,23 @@ roi_align_bwd_tc_kernel(const __nv_bfloat16* __restrict__ grad_out, int C, int H
           PSTAMP(sq, 1);
           tc_fence_after();
           const uint32_t ops = ops0 + ob * BT_OPS_BYTES;
-          const uint64_t bd = desc_kmajor_sw128(ops + 2 * BT_A_BYTES);
+          // Only the tile rows the RoI touches take part: N = 16 px x (rows touched) instead of the whole 16x16 tile (the
+          // weight rows of the other pixels are zero, and are not even built any more).  The very first pair of the CTA runs
+          // the full N = 256 with accumulate = 0: it is what initialises both TMEM accumulators.
+          int r0 = 0, nrows = BT_TY;
+          if (sq > 0) {
+            const int rr = *reinterpret_cast<volatile int*>(&s_rows[ob]);
+            r0 = rr & 255;
+            nrows = (rr >> 8) - r0;
+          }
+          const uint32_t idesc_n = sq > 0 ? make_idesc(128, BT_TX * nrows, 0, 0) : idesc;
+          const uint64_t bd = desc_kmajor_sw128(ops + 2 * BT_A_BYTES + (uint32_t)r0 * (BT_TX * 128));
 #pragma unroll
           for (int cb = 0; cb < 2; ++cb) {
             const uint64_t ad = desc_kmajor_sw128(ops + cb * BT_A_BYTES);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
-              if (!(dbg & 1)) umma_bf16(tmem_base + cb * BT_PX, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc, (sq > 0 || kk > 0) ? 1u : 0u);
+              if (!(dbg & 1)) umma_bf16(tmem_base + cb * BT_PX + r0 * BT_TX, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc_n, (sq > 0 || kk > 0) ? 1u : 0u);
           }
           umma_commit(ops_free0 + 8 * ob);
           PSTAMP(sq, 2);
@@ -243,8 +256,9 @@ roi_align_bwd_tc_kernel(const __nv_bfloat16* __restrict__ grad_out, int C, int H
           for (int k = 0; k < 4; ++k)
             *reinterpret_cast<uint4*>(arow + (((half * 4 + k) ^ (mrow & 7)) << 4)) = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
         }
-        // (2) B: Wt[px][bin] = Wy[y][ph] * Wx[x][pw] / count inside the footprint, else 0
-        {
+        // (2) B: Wt[px][bin] = Wy[y][ph] * Wx[x][pw] / count inside the footprint, else 0.  Tile rows the RoI does not
+        // touch are skipped (the MMA only reads rows [ya, yb)); the first pair of the CTA still writes all 256 rows.
+        if (sq == 0 || ((ty0 + (row >> 4)) >= ya && (ty0 + (row >> 4)) < yb)) {
           const int y = ty0 + (row >> 4), x = tx0 + (row & 15);
           const bool in = (y >= ya) && (y < yb) && (x >= xa) && (x < xb);
           uint32_t pk[16];
@@ -283,6 +297,7 @@ roi_align_bwd_tc_kernel(const __nv_bfloat16* __restrict__ grad_out, int C, int H
         named_bar_sync(2, BT_BUILDERS);
         if (bt == 0) PSTAMP(sq, 6);
         if (bt == 0) {
+          s_rows[ob] = (ya - ty0) | ((yb - ty0) << 8);     // read by the MMA thread after it has seen ops_ready (release/acquire)
           mbar_arrive(ops_ready0 + 8 * ob);
           mbar_arrive(raw_empty0 + 8 * slot);
         }
@@ -291,7 +306,7 @@ roi_align_bwd_tc_kernel(const __nv_bfloat16* __restrict__ grad_out, int C, int H
     seq += n_list;
   }
 
-  if (trace && threadIdx.x == 64) tr2 = globaltimer_ns();
+  if (kTrace && trace && threadIdx.x == 64) tr2 = globaltimer_ns();
   // ---- epilogue: TMEM -> grad_input (or zeros when no RoI touches the tile)
   if (warp == 1 && lane == 0 && seq > 0) umma_commit(tfull);
   if (warp >= 2) {
@@ -301,7 +316,7 @@ roi_align_bwd_tc_kernel(const __nv_bfloat16* __restrict__ grad_out, int C, int H
       mbar_wait(tfull, 0);
       tc_fence_after();
     }
-    if (trace && threadIdx.x == 64) tr3 = globaltimer_ns();
+    if (kTrace && trace && threadIdx.x == 64) tr3 = globaltimer_ns();
 #pragma unroll 1
     for (int cc = chalf * (BT_PX / 64); cc < (chalf + 1) * (BT_PX / 64); ++cc) {
       uint32_t v[32];
@@ -346,7 +361,7 @@ roi_align_bwd_tc_kernel(const __nv_bfloat16* __restrict__ grad_out, int C, int H
     tc_fence_before();
   }
   __syncthreads();
-  if (trace && threadIdx.x == 64) {
+  if (kTrace && trace && threadIdx.x == 64) {
     unsigned long long* o = trace + 8 * ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -368,11 +383,16 @@ static int launch_bwd_tc(const void* grad_out, int N, int C, int H, int W, int R
   static bool attr_set_dev[kMaxDevices] = {};     // function attributes are per device
   bool& attr_set = attr_set_dev[cur_dev()];
   if (!attr_set) {
-    DA_CUDA_OK(cudaFuncSetAttribute(roi_align_bwd_tc_kernel<TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BT_SMEM));
+    DA_CUDA_OK(cudaFuncSetAttribute(roi_align_bwd_tc_kernel<TO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BT_SMEM));
+    DA_CUDA_OK(cudaFuncSetAttribute(roi_align_bwd_tc_kernel<TO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BT_SMEM));
     attr_set = true;
   }
-  roi_align_bwd_tc_kernel<TO><<<grid, BT_THREADS, BT_SMEM, st>>>((const __nv_bfloat16*)grad_out, C, H, W, R, (const unsigned char*)ws,
-                                                                   static_cast<TO*>(grad_in), tiles_x, dbg, trace);
+  if (trace)
+    roi_align_bwd_tc_kernel<TO, true><<<grid, BT_THREADS, BT_SMEM, st>>>((const __nv_bfloat16*)grad_out, C, H, W, R, (const unsigned char*)ws,
+                                                                           static_cast<TO*>(grad_in), tiles_x, dbg, trace);
+  else
+    roi_align_bwd_tc_kernel<TO, false><<<grid, BT_THREADS, BT_SMEM, st>>>((const __nv_bfloat16*)grad_out, C, H, W, R, (const unsigned char*)ws,
+                                                                            static_cast<TO*>(grad_in), tiles_x, dbg, trace);
   DA_LAUNCH_CHECK();
   return DA_OK;
 }

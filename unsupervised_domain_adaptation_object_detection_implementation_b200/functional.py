@@ -954,3 +954,38 @@ def conv_pixel_loss(x, w, scale, shift, w_tail, b_tail, domain, stride=1, pad=0,
         shadow = bf16_shadow(w)
     cfg = (stride, pad, int(relu), float(drop_p), int(seed), engine, float(grl), int(tail_relu), mode, float(gamma), float(alpha))
     return ConvPixelLossFunction.apply(x, w, scale, shift, w_tail, b_tail, domain, cfg, shadow)
+
+
+# --------------------------------------------------------------------------------------
+# W1: lambda-weighted loss entries + their total in one launch
+# --------------------------------------------------------------------------------------
+class WeightedLossesFunction(Function):
+    @staticmethod
+    def forward(ctx, weights, *losses):
+        n = len(losses)
+        dev = losses[0].device
+        ls = [l.detach().float().contiguous() for l in losses]
+        ptrs = (ctypes.c_void_p * n)(*[l.data_ptr() for l in ls])
+        w = (ctypes.c_float * n)(*[float(x) for x in weights])
+        scaled = torch.empty((n,), dtype=torch.float32, device=dev)
+        total = torch.empty((), dtype=torch.float32, device=dev)
+        check(lib.da_weighted_sum_forward(ptrs, w, n, _ptr(scaled), _ptr(total), _stream()), "weighted_sum_forward")
+        ctx.weights, ctx.n = tuple(float(x) for x in weights), n
+        return scaled, total
+
+    @staticmethod
+    def backward(ctx, g_scaled, g_total):
+        n = ctx.n
+        dev = (g_total if g_total is not None else g_scaled).device
+        w = (ctypes.c_float * n)(*ctx.weights)
+        d = torch.empty((n,), dtype=torch.float32, device=dev)
+        gs = None if g_scaled is None else g_scaled.contiguous().float()
+        gt = None if g_total is None else g_total.contiguous().float()
+        check(lib.da_weighted_sum_backward(w, n, _ptr(gt), _ptr(gs), _ptr(d), _stream()), "weighted_sum_backward")
+        return (None, *[d[i] for i in range(n)])
+
+
+def weighted_losses(losses, weights):
+    """-> (scaled [n] with scaled[i] = weights[i] * losses[i], total = scaled.sum()), one kernel forward, one backward."""
+    _require_cuda(*losses)
+    return WeightedLossesFunction.apply(tuple(weights), *losses)

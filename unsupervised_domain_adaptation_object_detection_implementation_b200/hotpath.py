@@ -26,11 +26,11 @@ def domain_tensor(gt_da, device):
     would be a pageable host->device copy (a sync the reference pays at DAFaster_rcnn_Orig.py:119-122, and
     illegal inside CUDA-graph capture)."""
     if torch.is_tensor(gt_da):
-        return gt_da.to(device=device, dtype=torch.long)
+        return gt_da.to(device=device, dtype=torch.int32)
     key = (tuple(int(d) for d in gt_da), str(device))
     t = _CONST.get(key)
     if t is None:
-        t = torch.tensor(key[0], dtype=torch.long, device=device)
+        t = torch.tensor(key[0], dtype=torch.int32, device=device)      # int32: what the kernels read (no per-step cast)
         _CONST[key] = t
     return t
 
@@ -41,9 +41,17 @@ def roi_domain_labels(counts, device):
     key = ("roi_labels", counts, str(device))
     t = _CONST.get(key)
     if t is None:
-        t = torch.cat([torch.full((n,), d, dtype=torch.long, device=device) for n, d in zip(counts, (0, 1))])
+        t = torch.cat([torch.full((n,), d, dtype=torch.int32, device=device) for n, d in zip(counts, (0, 1))])
         _CONST[key] = t
     return t
+
+
+class LossDict(dict):
+    """The reference's losses dict (same keys) that also carries the already computed sum of its entries."""
+
+    def __init__(self, total, **entries):
+        super().__init__(**entries)
+        self.total = total
 
 
 class SharedFCs(nn.Module):
@@ -93,12 +101,12 @@ class DAFOrgHotPath(nn.Module):
         roi_feats = self.bbox_roi_extractor([c5], rois)
         bbox_feats = self.bbox_head(roi_feats) if self.bbox_head is not None else roi_feats.flatten(1)
         label_da = roi_domain_labels(tuple(len(p) for p in proposal_list), c5.device) if len(proposal_list) == 2 else \
-            rois[:, 0].long().clamp(max=1)
+            rois[:, 0].to(torch.int32).clamp(max=1)
         ins_loss, ins_preds = self.local_da.forward_loss(bbox_feats, label_da)
         consist = da_losses.consistency_loss(imgs_feat, ins_preds, label_da)
-        return dict(local_da_loss=self.local_lamda * ins_loss,
-                    globle_da_loss=self.global_lamda * global_loss,
-                    consistency_loss=self.consist_lamda * consist)
+        # lambda weights (DAFaster_rcnn_Orig.py:143-157) and the total of the dict in ONE launch; parse_losses picks the total up
+        scaled, total = F_.weighted_losses([ins_loss, global_loss, consist], [self.local_lamda, self.global_lamda, self.consist_lamda])
+        return LossDict(total, local_da_loss=scaled[0], globle_da_loss=scaled[1], consistency_loss=scaled[2])
 
 
 class CBAMHotPath(nn.Module):
@@ -150,6 +158,9 @@ def parse_losses(losses):
     def _mean(v):   # the DA losses are device scalars already: no reduction kernel for a 0-d tensor
         return v if v.dim() == 0 else v.mean()
     log_vars = {k: _mean(v) if torch.is_tensor(v) else sum(_mean(x) for x in v) for k, v in losses.items()}
-    loss = sum(v for k, v in log_vars.items() if "loss" in k)
+    if isinstance(losses, LossDict) and all("loss" in k for k in losses):
+        loss = losses.total            # summed by the same kernel that applied the lambda weights
+    else:
+        loss = sum(v for k, v in log_vars.items() if "loss" in k)
     log_vars["loss"] = loss
     return loss, log_vars
