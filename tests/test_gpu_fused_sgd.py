@@ -17,7 +17,11 @@ LR, MU, WD = 0.05, 0.9, 5e-4
 
 
 @pytest.mark.parametrize("N,H,W,Cin,Cout,K,stride,pad", [
-    (300, 1, 1, 2048, 256, 1, 1, 0),       # FC-shaped (flat), bn 256, Cout tiles in cluster pairs, ragged pixel count
+    (300, 1, 1, 2048, 256, 1, 1, 0),       # FC-shaped (flat), bn 256, Cout tiles in cluster pairs (TMA-slab epilogue), ragged pixel count
+    (1024, 1, 1, 4096, 1024, 1, 1, 0),     # 64 cluster tiles
+    (64, 1, 1, 76800, 256, 1, 1, 0),       # 300 cluster tiles on 74 clusters: the slab ring wraps across tiles and accumulators
+    (130, 1, 1, 2336, 320, 1, 1, 0),       # TMA-slab epilogue with a partial last Cin tile (2336 = 9*256 + 32) and a partial Cout tile
+    (2, 9, 11, 256, 256, 3, 1, 1),         # 3x3, 9 taps, bn 256, cluster pairs: slab columns = tap*Cin + ci
     (64, 1, 1, 96, 136, 1, 1, 0),          # Cin not a multiple of the tile, Cout not a multiple of 128
     (2, 12, 20, 64, 64, 3, 2, 1),          # 3x3 stride 2 (parity maps, 9 taps), bn 64
     (2, 16, 16, 160, 128, 3, 1, 1),        # 3x3 stride 1, Cin = 160 (partial 256-wide tile)
