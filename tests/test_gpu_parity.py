@@ -1049,3 +1049,68 @@ def test_pixel_tail_matches_unfused_path_at_bench_size():
     assert rel_err(xa.grad.float(), xb.grad.float()) <= 2e-2
     for k, p in m.named_parameters():
         assert float((ga[k] - p.grad).norm() / p.grad.norm().clamp_min(1e-30)) <= 2e-2, k
+
+
+# ---------------------------------------------------------------------------- hot-path modules beyond DAF-Org
+def test_fpn_hot_path_runs_under_cuda_graph_and_matches_eager():
+    """FPNHotPath (BASELINE config 2b: heads + multi-level RoIAlign + shared FCs + instance head on P2..P5): the multi-level
+    extractor partitions the RoIs on the device (no nonzero / host sync), so the whole forward+backward is CUDA-graph
+    capturable; the replay reproduces the eager losses and input gradients bit for bit (eval: no dropout)."""
+    from unsupervised_domain_adaptation_object_detection_implementation_b200 import hotpath
+    uda.set_engine("umma_bf16")
+    torch.manual_seed(0)
+    m = hotpath.FPNHotPath(64, (4, 8, 16, 32), 1024).to(DEV).eval()        # the instance head is 1024 wide (instance_da.py:50)
+    seeded.fill_state_(m, 1, "fpn.")
+    feats = [seeded.feature_map(f"fpn.f{i}", (2, 64, 64 >> i, 96 >> i), 1).to(DEV).to(torch.bfloat16) for i in range(4)]
+    props = [seeded.synthetic_rois(40, 1, 256, 384, s, 8.0, 300.0)[:, 1:].to(DEV) for s in (0, 1)]
+
+    def step(_unused=None):
+        xs = [f.detach().clone().requires_grad_(True) for f in feats]     # leaves live on the stream that runs the step (as in bench.py)
+        losses = m.forward_train(xs, props, [0, 1])
+        total, log = hotpath.parse_losses(losses)
+        grads = torch.autograd.grad(total, xs)
+        return total.detach(), [g.detach() for g in grads]
+
+    xs = None
+    for _ in range(2):
+        t_eager, g_eager = step(xs)
+    assert torch.isfinite(t_eager) and all(torch.isfinite(g.float()).all() and float(g.float().abs().sum()) > 0 for g in g_eager)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        step(xs)
+    torch.cuda.current_stream().wait_stream(side)
+    gph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gph):
+        t_cap, g_cap = step(xs)
+    gph.replay()
+    torch.cuda.synchronize()
+    assert float(t_cap) == float(t_eager)
+    for a, b in zip(g_cap, g_eager):
+        assert torch.equal(a, b)
+    losses = m.forward_train(feats, props, [0, 1])
+    assert set(losses) == {"local_da_loss", "consistency_loss", "globle_da_loss"} and len(losses["globle_da_loss"]) == 4
+
+
+def test_deep_hot_path_losses_vs_oracle():
+    """DeepHotPath (DAFasterRCNN_Deep's DA part): Global heads (Deep flavour) + NonLocalAlignmentHead patch loss +
+    InstanceAlignmentHead_DAF CE against the oracle heads / losses, fp32 engine."""
+    from unsupervised_domain_adaptation_object_detection_implementation_b200 import hotpath
+    uda.set_engine("simt_f32")
+    m = hotpath.DeepHotPath((64, 64, 64), 1024).eval()
+    seeded.fill_state_(m, 4, "deep.")
+    c3, c4, c5 = (seeded.feature_map(f"deep.c{i}", (2, 64, h, w), 4) for i, (h, w) in enumerate(((8, 12), (12, 20), (13, 19))))
+    feats = seeded.feature_map("deep.roi", (48, 1024), 4)
+    gt = torch.tensor([0, 1])
+    sd = {k: v.detach().double() for k, v in m.state_dict().items()}
+    sub = lambda p: {k[len(p):]: v for k, v in sd.items() if k.startswith(p)}
+    labels = (torch.arange(48) >= 24).long()
+    ref = dict(
+        globle_da_loss=0.1 * (da_oracle.ce2(da_oracle.global_alignment_head(c4.double(), sub("da_head_mid.")), gt) +
+                              da_oracle.ce2(da_oracle.global_alignment_head(c5.double(), sub("da_head_top.")), gt)),
+        patch_bottom_loss=0.1 * da_oracle.patch_loss(da_oracle.non_local_alignment_head(c3.double(), sub("local_da_head_bottom.")), gt),
+        local_da_loss=0.2 * da_oracle.ce2(torch.sigmoid(da_oracle.instance_alignment_daf_logits(feats.double(), sub("local_da."))), labels))
+    m = m.to(DEV)
+    got = m.forward_train(c3.to(DEV), c4.to(DEV), c5.to(DEV), feats.to(DEV), [0, 1])
+    for k in ref:
+        assert abs(float(got[k]) - float(ref[k])) <= 2e-5 * abs(float(ref[k])), (k, float(got[k]), float(ref[k]))

@@ -848,6 +848,11 @@ def instance_head_chain(x, labels, nlb_weights, w_mask, fcs, drop_p, seeds, grl)
     """x [R,C] bf16; nlb_weights: (theta, phi, g) conv weights or None; w_mask: conv_mask weight or None;
     fcs: ((w1,b1),(w2,b2),(w3,b3)).  -> (loss = mean CE(sigmoid(fc3), labels), pred = sigmoid(fc3) [R,2])."""
     (w1, b1), (w2, b2), (w3, b3) = fcs
+    C = x.shape[1]
+    if nlb_weights is not None and (any(w.shape[1] != C for w in nlb_weights) or w_mask.shape[0] != C or w1.shape[1] != C):
+        raise RuntimeError(f"instance_head_chain: features are {C} wide, the NonLocalBlock / fc1 expect {nlb_weights[0].shape[1]} / {w1.shape[1]}")
+    if w1.shape[1] != C or w2.shape[1] != w1.shape[0] or w3.shape[1] != w2.shape[0] or w3.shape[0] != 2:
+        raise RuntimeError("instance_head_chain: FC shapes do not chain (C -> H1 -> H2 -> 2)")
     if nlb_weights is not None:
         buf, sh = pack_projection(list(nlb_weights))
         nlb_w = _SplitPacked.apply(buf, *nlb_weights)

@@ -164,3 +164,83 @@ def parse_losses(losses):
         loss = sum(v for k, v in log_vars.items() if "loss" in k)
     log_vars["loss"] = loss
     return loss, log_vars
+
+
+class DeepHotPath(nn.Module):
+    """Image-level + instance-level part of DAFasterRCNN_Deep / ResNet_DA_Deep (detectors/DAFaster_rcnn_Deep.py:78-196,
+    backbones/resnet_da_deep.py:1120-1175): Global heads without the dead branch on C4/C5 (CE on raw logits, L3),
+    NonLocalAlignmentHead on C3 (and C4 when `patch_mid`) with the per-image patch loss L2 over all C*H*W values, and the
+    FC-only InstanceAlignmentHead_DAF on the RoI features (one chain kernel).  The T x T attention of the NonLocalBlock is
+    materialised (T = H*W of the level): fine at the reference's 512x1024 scale (C3: T = 8192), not at 1024x2048
+    (T = 32768 -> 4.3 GB per image; the blocked two-pass kernel is SURVEY 8f rank 2, not built)."""
+
+    def __init__(self, channels=(512, 1024, 2048), fc_out_channels=1024, lambdas=(0.1, 0.1, 0.2), patch_mid=False):
+        super().__init__()
+        self.da_head_mid = da_heads.GlobalAlignmentHeadDeep(channels[1])
+        self.da_head_top = da_heads.GlobalAlignmentHeadDeep(channels[2])
+        self.local_da_head_bottom = da_heads.NonLocalAlignmentHead(channels[0])
+        self.local_da_head_mid = da_heads.NonLocalAlignmentHead(channels[1]) if patch_mid else None
+        self.da_head_mid._init_weights()
+        self.da_head_top._init_weights()
+        self.local_da = da_heads.InstanceAlignmentHead_DAF()
+        self.local_da._init_weights()
+        self.global_lamda, self.patch_lamda, self.local_lamda = lambdas
+
+    def unused_parameters(self):
+        return []
+
+    def forward_train(self, c3, c4, c5, bbox_feats, gt_da):
+        """bbox_feats: [R_src + R_tgt, fc_out] features of the shared FCs (source RoIs first); -> losses dict."""
+        gt_domain = domain_tensor(gt_da, c5.device)
+        g_mid, _ = da_losses.image_ce_loss(self.da_head_mid(c4), gt_domain, False)
+        g_top, _ = da_losses.image_ce_loss(self.da_head_top(c5), gt_domain, False)
+        patch = da_losses.patch_loss(self.local_da_head_bottom(c3), gt_domain)
+        if self.local_da_head_mid is not None:
+            patch = patch + da_losses.patch_loss(self.local_da_head_mid(c4), gt_domain)
+        half = bbox_feats.shape[0] // 2
+        labels = roi_domain_labels((half, bbox_feats.shape[0] - half), c5.device)
+        ins_loss, _ = self.local_da.forward_loss(bbox_feats, labels)
+        return dict(globle_da_loss=self.global_lamda * (g_mid + g_top), patch_bottom_loss=self.patch_lamda * patch,
+                    local_da_loss=self.local_lamda * ins_loss)
+
+
+class FPNHotPath(nn.Module):
+    """The DAF hot path on FPN levels (BASELINE config 2b; SURVEY 8d: an EXTENSION -- no DA config of the reference has a
+    neck).  One ImgAlignmentHead per level with its per-level mean loss (fused tail kernel), RoIAlign through the multi-level
+    SingleRoIExtractor (FPN level map, single_level_roi_extractor.py:36-55; device-side partition, CUDA-graph capturable),
+    shared FCs (channels*49 -> fc_out -> fc_out), InstanceAlignmentHead + CE (chain kernel), consistency against the
+    stride-16 level."""
+
+    def __init__(self, channels=256, featmap_strides=(4, 8, 16, 32), fc_out_channels=1024, lambdas=(0.1, 0.1, 0.1)):
+        super().__init__()
+        self.featmap_strides = list(featmap_strides)
+        self.da_heads = nn.ModuleList([da_heads.ImgAlignmentHead(channels) for _ in self.featmap_strides])
+        for h in self.da_heads:
+            h._init_weights()
+        self.bbox_roi_extractor = SingleRoIExtractor(dict(type="RoIAlign", output_size=7, sampling_ratio=0),
+                                                     out_channels=channels, featmap_strides=self.featmap_strides)
+        self.bbox_head = SharedFCs(channels, 7, fc_out_channels)
+        self.local_da = da_heads.InstanceAlignmentHead()
+        self.local_da._init_weights()
+        self.global_lamda, self.local_lamda, self.consist_lamda = lambdas
+        self.consist_level = self.featmap_strides.index(16) if 16 in self.featmap_strides else len(self.featmap_strides) - 1
+
+    def unused_parameters(self):
+        return self.local_da.unused_parameters()
+
+    def forward_train(self, feats, proposal_list, gt_da):
+        gt_domain = domain_tensor(gt_da, feats[0].device)
+        level_losses, level_feats = zip(*[h.forward_loss(f, gt_domain) for h, f in zip(self.da_heads, feats)])
+        rois = bbox2roi(proposal_list)
+        roi_feats = self.bbox_roi_extractor(list(feats), rois)
+        bbox_feats = self.bbox_head(roi_feats)
+        label_da = roi_domain_labels(tuple(len(p) for p in proposal_list), feats[0].device) if len(proposal_list) == 2 else \
+            rois[:, 0].to(torch.int32).clamp(max=1)
+        ins_loss, ins_preds = self.local_da.forward_loss(bbox_feats, label_da)
+        consist = da_losses.consistency_loss(level_feats[self.consist_level], ins_preds, label_da)
+        n = len(level_losses)
+        scaled, total = F_.weighted_losses(list(level_losses) + [ins_loss, consist],
+                                           [self.global_lamda] * n + [self.local_lamda, self.consist_lamda])
+        out = LossDict(total, local_da_loss=scaled[n], consistency_loss=scaled[n + 1])
+        out["globle_da_loss"] = [scaled[i] for i in range(n)]     # one entry per level; _parse_losses sums a list (base.py:196-197)
+        return out

@@ -82,12 +82,18 @@ class SingleRoIExtractor(nn.Module):
             if len(rois) == 0:
                 return feats[0].new_zeros(0, self.out_channels, *out_size)
             return self.roi_layers[0](feats[0], rois)
-        roi_feats = feats[0].new_zeros(rois.size(0), self.out_channels, *out_size)
+        if len(rois) == 0:
+            return feats[0].new_zeros(0, self.out_channels, *out_size)
+        # FPN path (single_level_roi_extractor.py:81-104).  The reference gathers the RoIs of each level with nonzero() -- a
+        # host sync per level, and not capturable in a CUDA graph.  Here every level sees the WHOLE RoI list with the batch
+        # index of the RoIs that belong to another level set to -1: the kernels treat such a RoI as empty (zero footprint,
+        # zeros written, no feature read), so the per-level outputs have disjoint supports and their sum is the reference's
+        # scatter -- same values, no host round trip, fixed launch sequence.
         target_lvls = self.map_roi_levels(rois, num_levels)
+        roi_feats = None
         for i in range(num_levels):
-            inds = (target_lvls == i).nonzero(as_tuple=False).squeeze(1)
-            if inds.numel() > 0:
-                roi_feats[inds] = self.roi_layers[i](feats[i], rois[inds])
-            else:
-                roi_feats = roi_feats + feats[i].sum() * 0.0
+            masked = rois.clone()
+            masked[:, 0] = torch.where(target_lvls == i, rois[:, 0], rois.new_full((), -1.0))
+            out_i = self.roi_layers[i](feats[i], masked)
+            roi_feats = out_i if roi_feats is None else roi_feats + out_i
         return roi_feats
