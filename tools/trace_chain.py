@@ -15,7 +15,7 @@ for _ in range(3):
     loss, pred = m.forward_loss(x, labels)
     (loss + pred.sum() * 1e-3).backward()
 torch.cuda.synchronize()
-buf = torch.zeros(128, dtype=torch.int64, device=dev)
+buf = torch.zeros(256, dtype=torch.int64, device=dev)
 names_f = ["proj", "S", "softmax", "P*g", "mask+res", "fc1", "fc2", "fc3", "CE"]
 names_b = ["ce_bwd", "fc3 bwd", "fc2 bwd", "fc1 bwd", "mask bwd", "dP,dg", "softmax bwd", "dtheta,dphi", "dWproj,dx"]
 for which, names in (("forward", names_f), ("backward", names_b)):
@@ -31,9 +31,11 @@ for which, names in (("forward", names_f), ("backward", names_b)):
     F_.set_option("chain_trace", 0)
     t = buf.cpu().tolist()
     t0 = t[0]
-    print(f"{which}: total {(max(t) - t0) / 1e3:.1f} us")
+    print(f"{which}: total {(max(t[:128]) - t0) / 1e3:.1f} us")
     for g, n in enumerate(names):
         a, gemm, ew, bar = t[3 * g], t[3 * g + 1], t[3 * g + 2], t[3 * g + 3]
         if gemm == 0:
             break
-        print(f"  {n:12s} gemm {(gemm - a) / 1e3:6.2f}  elementwise {(ew - gemm) / 1e3:6.2f}  barrier {(bar - ew) / 1e3:6.2f} us")
+        roles = [(t[128 + 4 * g + k] - a) / 1e3 for k in range(4)]
+        print(f"  {n:12s} gemm {(gemm - a) / 1e3:6.2f}  elementwise {(ew - gemm) / 1e3:6.2f}  barrier {(bar - ew) / 1e3:6.2f} us"
+              f"   role done at: tma {roles[0]:5.2f} mma {roles[1]:5.2f} epi-first {roles[2]:5.2f} epi-last {roles[3]:5.2f}")

@@ -31,7 +31,7 @@ constexpr int CH_STAGES = 8;
 constexpr int CH_THREADS = 320;                    // TMA warp, MMA warp, 8 epilogue warps
 constexpr int CH_MAX_OPS = 28;
 constexpr int CH_MAX_GROUPS = 16;
-constexpr size_t CH_SMEM = 1024 + (size_t)CH_STAGES * (CH_A_BYTES + CH_B_BYTES) + 512;
+constexpr size_t CH_SMEM_FIXED = 1024 + (size_t)CH_STAGES * (CH_A_BYTES + CH_B_BYTES) + 512;   // + the program copy (see CH_SMEM)
 
 enum ChainKind {
   CH_GEMM = 0,
@@ -81,6 +81,11 @@ struct ChainParams {
   ChainOp ops[CH_MAX_OPS];
 };
 
+constexpr size_t CH_SMEM = CH_SMEM_FIXED + sizeof(ChainOp) * CH_MAX_OPS;
+
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
+}
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   unsigned int v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -108,13 +113,13 @@ __device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int target
   fence_proxy_async_all();
 }
 
-__device__ __forceinline__ void ch_tile_of(const ChainParams& P, int ob, int oe, int t, int& op, int& m0, int& n0) {
+__device__ __forceinline__ void ch_tile_of(const ChainOp* ops, int ob, int oe, int t, int& op, int& m0, int& n0) {
   // tiles of the group's GEMM ops, op after op; inside an op n is the fastest index (neighbouring CTAs share the A tile)
   op = -1;
   for (int o = ob; o < oe; ++o) {
-    if (P.ops[o].kind != CH_GEMM) continue;
-    const int n = P.ops[o].tiles_m * P.ops[o].tiles_n;
-    if (t < n) { op = o; m0 = (t / P.ops[o].tiles_n) * CH_BM; n0 = (t % P.ops[o].tiles_n) * CH_BN; return; }
+    if (ops[o].kind != CH_GEMM) continue;
+    const int n = ops[o].tiles_m * ops[o].tiles_n;
+    if (t < n) { op = o; m0 = (t / ops[o].tiles_n) * CH_BM; n0 = (t % ops[o].tiles_n) * CH_BN; return; }
     t -= n;
   }
 }
@@ -389,6 +394,18 @@ chain_kernel(const __grid_constant__ ChainParams P) {
   volatile uint32_t* tslot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tslot - base));
   float* red = reinterpret_cast<float*>(gen_base);      // elementwise scratch: the operand ring is idle while they run
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // The program lives in the kernel-parameter space (14 KB: beyond what the constant cache keeps warm, and every group touches
+  // op records no SM has read yet: ~1 us of cold misses per role and group in the first build).  Its scalar fields are read from
+  // a shared-memory copy; only the TMA engine reads the tensor maps in place (prefetched into its descriptor cache here).
+  ChainOp* ops = reinterpret_cast<ChainOp*>(gen_base + (bars - base) + 512);
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(&P.ops[0]);
+    uint4* dst = reinterpret_cast<uint4*>(ops);
+    const int n16 = (int)(sizeof(ChainOp) * P.nops / 16);
+    for (int i = threadIdx.x; i < n16; i += CH_THREADS) dst[i] = src[i];
+    for (int o = threadIdx.x; o < P.nops; o += CH_THREADS)
+      if (P.ops[o].kind == CH_GEMM) { prefetch_tensormap(&P.ops[o].a_map); prefetch_tensormap(&P.ops[o].b_map); }
+  }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < CH_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
@@ -409,7 +426,7 @@ chain_kernel(const __grid_constant__ ChainParams P) {
   do {                                                                                                    \
     if (P.trace && blockIdx.x == 0 && threadIdx.x == 0) {                                                 \
       unsigned long long t_;                                                                              \
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                              \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)::"memory");                                    \
       P.trace[tr++] = t_;                                                                                 \
     }                                                                                                     \
   } while (0)
@@ -417,13 +434,15 @@ chain_kernel(const __grid_constant__ ChainParams P) {
   for (int g = 0; g < P.ngroups; ++g) {
     const int ob = P.group_begin[g], oe = P.group_begin[g + 1];
     int total = 0;
-    for (int o = ob; o < oe; ++o) if (P.ops[o].kind == CH_GEMM) total += P.ops[o].tiles_m * P.ops[o].tiles_n;
+    for (int o = ob; o < oe; ++o) if (ops[o].kind == CH_GEMM) total += ops[o].tiles_m * ops[o].tiles_n;
     if (warp == 0) {
       if (lane == 0) {
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
           int op, m0, n0;
-          ch_tile_of(P, ob, oe, t, op, m0, n0);
-          const ChainOp& o = P.ops[op];
+          ch_tile_of(ops, ob, oe, t, op, m0, n0);
+          const ChainOp& o = ops[op];
+          const CUtensorMap* amap = &P.ops[op].a_map;     // the TMA engine reads descriptors from the parameter space
+          const CUtensorMap* bmap = &P.ops[op].b_map;
           const int kchunks = (o.K + CH_BK - 1) / CH_BK;
           for (int kc = 0; kc < kchunks; ++kc, ++kq) {
             const int s = kq % CH_STAGES;
@@ -432,13 +451,13 @@ chain_kernel(const __grid_constant__ ChainParams P) {
             mbar_expect_tx(fb, CH_A_BYTES + CH_B_BYTES);
             const uint32_t ad = a_s + s * CH_A_BYTES, bd = b_s + s * CH_B_BYTES;
             if (o.a_mn) {
-              tma_load_2d(ad, &o.a_map, fb, m0, kc * CH_BK);
-              tma_load_2d(ad + CH_A_BYTES / 2, &o.a_map, fb, m0 + 64, kc * CH_BK);
+              tma_load_2d(ad, amap, fb, m0, kc * CH_BK);
+              tma_load_2d(ad + CH_A_BYTES / 2, amap, fb, m0 + 64, kc * CH_BK);
             } else {
-              tma_load_2d(ad, &o.a_map, fb, kc * CH_BK, m0);
+              tma_load_2d(ad, amap, fb, kc * CH_BK, m0);
             }
-            if (o.b_mn) tma_load_2d(bd, &o.b_map, fb, n0, kc * CH_BK);
-            else tma_load_2d(bd, &o.b_map, fb, kc * CH_BK, n0);
+            if (o.b_mn) tma_load_2d(bd, bmap, fb, n0, kc * CH_BK);
+            else tma_load_2d(bd, bmap, fb, kc * CH_BK, n0);
           }
         }
       }
@@ -446,8 +465,8 @@ chain_kernel(const __grid_constant__ ChainParams P) {
       if (lane == 0) {
         for (int t = blockIdx.x; t < total; t += gridDim.x, ++tcount) {
           int op, m0, n0;
-          ch_tile_of(P, ob, oe, t, op, m0, n0);
-          const ChainOp& o = P.ops[op];
+          ch_tile_of(ops, ob, oe, t, op, m0, n0);
+          const ChainOp& o = ops[op];
           const int kchunks = (o.K + CH_BK - 1) / CH_BK;
           const uint32_t idesc = make_idesc(CH_BM, CH_BN, o.a_mn, o.b_mn);
           const int buf = tcount & 1;
@@ -476,8 +495,8 @@ chain_kernel(const __grid_constant__ ChainParams P) {
       const int q = warp & 3, chunk = (warp - 2) >> 2;
       for (int t = blockIdx.x; t < total; t += gridDim.x, ++tcount) {
         int op, m0, n0;
-        ch_tile_of(P, ob, oe, t, op, m0, n0);
-        const ChainOp& o = P.ops[op];
+        ch_tile_of(ops, ob, oe, t, op, m0, n0);
+        const ChainOp& o = ops[op];
         const int buf = tcount & 1;
         mbar_wait(tfull0 + 8 * buf, ((uint32_t)(tcount >> 1)) & 1u);
         tc_fence_after();
@@ -495,12 +514,17 @@ chain_kernel(const __grid_constant__ ChainParams P) {
         ch_epilogue_chunk(o, v, m0 + q * 32 + lane, n0 + chunk * 32, o.seed + seed_add);
       }
     }
+    if (P.trace && blockIdx.x == 0 && lane == 0 && (warp < 3 || warp == 9)) {     // per-role "done" stamps of the group
+      unsigned long long t_;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)::"memory");
+      P.trace[128 + 4 * g + (warp == 9 ? 3 : warp)] = t_;
+    }
     // the operand ring doubles as scratch of the elementwise ops: every MMA that read it has completed (the epilogue
     // warps waited for the last accumulator) once all warps are here
     __syncthreads();
     CH_STAMP();        // GEMM tiles of the group done (this CTA)
     for (int o = ob; o < oe; ++o) {
-      const ChainOp& e = P.ops[o];
+      const ChainOp& e = ops[o];
       switch (e.kind) {
         case CH_SOFTMAX_COL_FWD: ch_softmax_col_fwd(e, red); break;
         case CH_SOFTMAX_COL_BWD: ch_softmax_col_bwd(e, red); break;

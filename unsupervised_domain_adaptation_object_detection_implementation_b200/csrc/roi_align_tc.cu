@@ -29,20 +29,22 @@
 namespace da {
 
 constexpr int TC_NISSUE = 2;                    // MMA issuer warps: block j of a stage is issued by issuer j % 2
-constexpr int TC_THREADS = 192 + 32 * (TC_NISSUE - 1);   // warp 0: TMA, warp 1 + warps 6..: MMA, warps 2..5: weights + epilogue
+constexpr int TC_BUILD_WARP0 = 5 + TC_NISSUE;   // first of the 4 weight-builder warps
+constexpr int TC_THREADS = 32 * (TC_BUILD_WARP0 + 4);    // warp 0: TMA, warp 1 + warps 6..: MMA, warps 2..5: epilogue, last 4: weights
 constexpr int TC_MCH = 128;                     // channels per accumulator (UMMA M)
 constexpr int TC_NB = 64;                       // 49 bins padded to the UMMA N
 constexpr int TC_GB = 4;                        // channel blocks per group (512 channels share one TMA box)
 constexpr int TC_ASTAGE = TC_GB * TC_MCH * 16 * 2;   // one quad (16 pixels) x 512 channels x bf16 = 16 KB
 constexpr int TC_NSTAGE = 6;
 constexpr int TC_BQUAD = TC_NB * 16 * 2;        // weights of one quad: 64 bins x 16 pixels, 2 KB
-constexpr int TC_CHUNK_Q = 32;                  // quads per resident weight chunk (512 pixels)
+constexpr int TC_CHUNK_Q = 16;                  // quads per weight chunk (256 pixels); two chunk buffers: the builders run one ahead
+constexpr int TC_BBUF = TC_CHUNK_Q * TC_BQUAD;  // 32 KB
 constexpr int TC_NACC = 2 * TC_GB;
 constexpr int TC_NSCHED = 4;                    // depth of the in-CTA work queue (RoI indices broadcast to every role)              // TMEM accumulators: two groups ping-pong
 
 template <typename TOut> __host__ __device__ constexpr int tc_stage_bytes() { return ((TC_MCH * PP * (int)sizeof(TOut) + 127) / 128) * 128; }
 template <typename TOut> __host__ __device__ inline size_t tc_smem_bytes(int H, int W) {
-  return 1024 + (size_t)TC_NSTAGE * TC_ASTAGE + (size_t)TC_CHUNK_Q * TC_BQUAD + 2 * tc_stage_bytes<TOut>() +
+  return 1024 + (size_t)TC_NSTAGE * TC_ASTAGE + 2 * (size_t)TC_BBUF + 2 * tc_stage_bytes<TOut>() +
          (size_t)(H + W + 8) * WROW * 4 + 512;
 }
 
@@ -118,13 +120,13 @@ roi_align_fwd_tc_kernel(const __grid_constant__ CUtensorMap fmap, int C, int H, 
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t a_ring = base;
   const uint32_t b_base = a_ring + TC_NSTAGE * TC_ASTAGE;
-  const uint32_t stage0 = b_base + TC_CHUNK_Q * TC_BQUAD;
+  const uint32_t stage0 = b_base + 2 * TC_BBUF;
   constexpr int STG = tc_stage_bytes<TOut>();
   float* wy_s = reinterpret_cast<float*>(gen + (stage0 - base) + 2 * STG);
   float* wx_s = wy_s + (size_t)(H + 4) * WROW;
   const uint32_t bars = smem_u32(wx_s + (size_t)(W + 4) * WROW);
   const uint32_t full0 = bars, empty0 = bars + 8 * TC_NSTAGE, tfull0 = bars + 16 * TC_NSTAGE,
-                 tempty0 = tfull0 + 8 * TC_NACC, b_ready = tempty0 + 8 * TC_NACC, b_free = b_ready + 8, sfull0 = b_free + 8,
+                 tempty0 = tfull0 + 8 * TC_NACC, b_ready = tempty0 + 8 * TC_NACC, b_free = b_ready + 16, sfull0 = b_free + 16,
                  sempty0 = sfull0 + 8 * TC_NSCHED, tslot = sempty0 + 8 * TC_NSCHED, sched_a = tslot + 8;
   volatile uint32_t* tslot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tslot - base));
   volatile int* sched = reinterpret_cast<volatile int*>(gen + (sched_a - base));
@@ -138,9 +140,8 @@ roi_align_fwd_tc_kernel(const __grid_constant__ CUtensorMap fmap, int C, int H, 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_NSTAGE; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, TC_NISSUE); }
     for (int b = 0; b < TC_NACC; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 4); }
-    mbar_init(b_ready, 1);
-    mbar_init(b_free, TC_NISSUE);
-    for (int i = 0; i < TC_NSCHED; ++i) { mbar_init(sfull0 + 8 * i, 1); mbar_init(sempty0 + 8 * i, TC_NISSUE + 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(b_ready + 8 * b, 1); mbar_init(b_free + 8 * b, TC_NISSUE); }
+    for (int i = 0; i < TC_NSCHED; ++i) { mbar_init(sfull0 + 8 * i, 1); mbar_init(sempty0 + 8 * i, TC_NISSUE + 8); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tslot, TC_NACC * TC_NB);
@@ -183,7 +184,7 @@ roi_align_fwd_tc_kernel(const __grid_constant__ CUtensorMap fmap, int C, int H, 
         }
       }
     }
-  } else if (warp == 1 || warp >= 6) {
+  } else if (warp == 1 || (warp >= 6 && warp < TC_BUILD_WARP0)) {
     // ------------------------------------------------------------------ MMA issuers (one elected lane each)
     if (lane == 0) {
       const int me = (warp == 1) ? 0 : warp - 5;
@@ -191,7 +192,7 @@ roi_align_fwd_tc_kernel(const __grid_constant__ CUtensorMap fmap, int C, int H, 
       // A: per block j the two 64-channel groups are 2048 B apart (LBO), the two 8-pixel atoms 1024 B (SBO)
       const uint64_t ad0 = desc_mnmajor_sw128(a_ring, 2048);
       const uint64_t bd0 = desc_kmajor_nosw(b_base, 128, 256);
-      int kq = 0, nbuild = 0, gcount = 0;
+      int kq = 0, nbuild = 0, gcount = 0, bb = 0;
       for (int qi = 0;; ++qi) {
         const int r = sched_pop<false>(sfull0, sempty0, sched, qi, true);
         if (r < 0) break;
@@ -209,7 +210,8 @@ roi_align_fwd_tc_kernel(const __grid_constant__ CUtensorMap fmap, int C, int H, 
             const bool built = (t.nchunks > 1) || (g == 0);           // a fresh weight chunk was built for (g, ch)
             const bool last_use = (t.nchunks > 1) || (g == ngroups - 1);
             if (built) {
-              mbar_wait(b_ready, (uint32_t)nbuild & 1u);
+              bb = nbuild & 1;
+              mbar_wait(b_ready + 8 * bb, (uint32_t)(nbuild >> 1) & 1u);
               tc_fence_after();
               ++nbuild;
             }
@@ -220,53 +222,50 @@ roi_align_fwd_tc_kernel(const __grid_constant__ CUtensorMap fmap, int C, int H, 
               mbar_wait(full0 + 8 * slot, ph);
               tc_fence_after();
               const uint64_t ad = ad0 + (uint64_t)((slot * TC_ASTAGE) >> 4);
-              const uint64_t bd = bd0 + (uint64_t)((ql * TC_BQUAD) >> 4);
+              const uint64_t bd = bd0 + (uint64_t)((bb * TC_BBUF + ql * TC_BQUAD) >> 4);
               const uint32_t accf = (ch > 0 || ql > 0) ? 1u : 0u;
               for (int j = me; j < nb_g; j += TC_NISSUE)
                 umma_bf16(tmem_base + (accb + j) * TC_NB, ad + (uint64_t)(j * 256), bd, idesc, accf);
               umma_commit(empty0 + 8 * slot);
             }
-            if (last_use) umma_commit(b_free);   // all of THIS issuer's MMAs reading the weight chunk have completed
+            if (last_use) umma_commit(b_free + 8 * bb);   // all of THIS issuer's MMAs reading the weight chunk have completed
           }
           for (int j = me; j < nb_g; j += TC_NISSUE) umma_commit(tfull0 + 8 * (accb + j));
         }
       }
     }
-  } else {
-    // ------------------------------------------------------------------ weight builder + epilogue (128 threads)
-    const int tid = threadIdx.x - 64;
-    const int q = warp & 3;
+  } else if (warp >= TC_BUILD_WARP0) {
+    // ------------------------------------------------------------------ weight builders (128 threads), one chunk ahead of the MMAs
+    // r01 had the epilogue warps build the weights: at every RoI boundary the tensor pipe (and behind it the TMA ring) waited for
+    // the last group's epilogue + the table loads + the build.  A dedicated team with two chunk buffers takes all of that off
+    // the critical path, and for footprints of several chunks build(ch+1) overlaps the MMAs of chunk ch.
+    const int tid = threadIdx.x - 32 * TC_BUILD_WARP0;
     const int n = tid & 63, part = tid >> 6;
     const int ph_n = n / P, pw_n = n - ph_n * P;
     const bool n_ok = n < PP;
-    int nbuild = 0, nstore = 0, gcount = 0;
+    int nbuild = 0;
     for (int qi = 0;; ++qi) {
       const int r = sched_pop<true>(sfull0, sempty0, sched, qi, lane == 0);
       if (r < 0) break;
       const RoiMeta m = metas[r];
       TcRoi t;
-      if (!tc_roi(m, H, t)) {   // empty footprint (degenerate / outside / bad batch index): zeros, as the reference
-        TOut* o = out + (size_t)r * C * PP;
-        for (int i = tid; i < C * PP; i += 128) o[i] = from_f32<TOut>(0.f);
-        continue;
-      }
+      if (!tc_roi(m, H, t)) continue;
       const int nrg = (m.ny + 3) >> 2;
-      bool tables_loaded = false;
-      for (int g = 0; g < ngroups; ++g, ++gcount) {
-        const int nb_g = min(TC_GB, nblk - g * TC_GB);
+      {   // tables -> smem (1/count folded into Wy; both zero-padded to whole quads); the previous RoI's builds are behind a barrier
+        const float* tab = tables + (size_t)r * (H + W) * WROW;
+        const float inv = 1.f / (float)m.count;
+        for (int i = tid; i < nrg * 4 * WROW; i += 128) wy_s[i] = (i < m.ny * WROW) ? tab[i] * inv : 0.f;
+        for (int i = tid; i < t.ncg * 4 * WROW; i += 128) wx_s[i] = (i < m.nx * WROW) ? tab[(size_t)H * WROW + i] : 0.f;
+        named_bar_sync(3, 128);
+      }
+      for (int g = 0; g < ngroups; ++g) {
         for (int ch = 0; ch < t.nchunks; ++ch) {
           const bool built = (t.nchunks > 1) || (g == 0);
           if (!built) continue;
-          mbar_wait(b_free, ((uint32_t)nbuild & 1u) ^ 1u);
+          const int bb = nbuild & 1;
+          mbar_wait(b_free + 8 * bb, ((uint32_t)(nbuild >> 1) & 1u) ^ 1u);
           ++nbuild;
-          if (!tables_loaded) {   // tables -> smem (1/count folded into Wy; both zero-padded to whole quads)
-            const float* tab = tables + (size_t)r * (H + W) * WROW;
-            const float inv = 1.f / (float)m.count;
-            for (int i = tid; i < nrg * 4 * WROW; i += 128) wy_s[i] = (i < m.ny * WROW) ? tab[i] * inv : 0.f;
-            for (int i = tid; i < t.ncg * 4 * WROW; i += 128) wx_s[i] = (i < m.nx * WROW) ? tab[(size_t)H * WROW + i] : 0.f;
-            tables_loaded = true;
-            named_bar_sync(2, 128);
-          }
+          uint8_t* bdst = gen + (b_base - base) + bb * TC_BBUF;
           const int q0 = ch * TC_CHUNK_Q, nq_ch = min(TC_CHUNK_Q, t.NQ - q0);
           // one 16-byte chunk (8 pixels of one bin row) per (atom, n): atom = 2*quad + (rows 0-1 | rows 2-3)
           for (int atom = part; atom < nq_ch * 2; atom += 2) {
@@ -281,14 +280,32 @@ roi_align_fwd_tc_kernel(const __grid_constant__ CUtensorMap fmap, int C, int H, 
             __nv_bfloat162 v0 = __floats2bfloat162_rn(wy0 * x0, wy0 * x1), v1 = __floats2bfloat162_rn(wy0 * x2, wy0 * x3);
             __nv_bfloat162 v2 = __floats2bfloat162_rn(wy1 * x0, wy1 * x1), v3 = __floats2bfloat162_rn(wy1 * x2, wy1 * x3);
             const uint32_t off = (uint32_t)ql * TC_BQUAD + (uint32_t)(n >> 3) * 256u + (uint32_t)(atom & 1) * 128u + (uint32_t)(n & 7) * 16u;
-            *reinterpret_cast<uint4*>(gen + (b_base - base) + off) =
+            *reinterpret_cast<uint4*>(bdst + off) =
                 make_uint4(*reinterpret_cast<uint32_t*>(&v0), *reinterpret_cast<uint32_t*>(&v1),
                            *reinterpret_cast<uint32_t*>(&v2), *reinterpret_cast<uint32_t*>(&v3));
           }
           fence_proxy_async();
-          named_bar_sync(2, 128);
-          if (tid == 0) mbar_arrive(b_ready);
+          named_bar_sync(3, 128);
+          if (tid == 0) mbar_arrive(b_ready + 8 * bb);
         }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (128 threads)
+    const int tid = threadIdx.x - 64;
+    const int q = warp & 3;
+    int nstore = 0, gcount = 0;
+    for (int qi = 0;; ++qi) {
+      const int r = sched_pop<true>(sfull0, sempty0, sched, qi, lane == 0);
+      if (r < 0) break;
+      TcRoi t;
+      if (!tc_roi(metas[r], H, t)) {   // empty footprint (degenerate / outside / bad batch index): zeros, as the reference
+        TOut* o = out + (size_t)r * C * PP;
+        for (int i = tid; i < C * PP; i += 128) o[i] = from_f32<TOut>(0.f);
+        continue;
+      }
+      for (int g = 0; g < ngroups; ++g, ++gcount) {
+        const int nb_g = min(TC_GB, nblk - g * TC_GB);
         // epilogue of the group's channel blocks
         const int accb = (gcount & 1) * TC_GB;
         const uint32_t use = (uint32_t)(gcount >> 1);
