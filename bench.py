@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--engine", default="umma_bf16", choices=["umma_bf16", "umma_bf16x6", "umma_bf16x3", "simt_f32"])
     ap.add_argument("--repeats", type=int, default=0, help="how many times the K-step timed region is repeated (0 = enough for ~1.5 s under load)")
     ap.add_argument("--no-chain", action="store_true", help="A/B: instance head layer by layer instead of the chain kernel")
+    ap.add_argument("--no-chain-feed", action="store_true", help="A/B: the last shared FC as its own launches, not inside the chain kernel")
     ap.add_argument("--no-fused-tail", action="store_true", help="A/B: separate pixel-head / pixel-loss kernels instead of the fused tail")
     ap.add_argument("--no-f32-line", action="store_true", help="skip the nested line on the fp32-class engine (umma_bf16x6)")
     ap.add_argument("--pairs-per-gpu", type=int, default=1)
@@ -179,6 +180,7 @@ def measure_engine(args, engine, rank, local, world, sample_clocks):
     uda.set_engine(engine)
     from unsupervised_domain_adaptation_object_detection_implementation_b200 import da_heads as _dh
     _dh.USE_CHAIN, _dh.USE_FUSED_TAIL = not args.no_chain, not args.no_fused_tail
+    _dh.USE_CHAIN_FEED = not args.no_chain_feed
     F_.MANAGED_WGRAD.clear()          # optimizer hooks of a previous measurement are keyed by id(weight)
     act = F_.act_dtype()
     pairs = args.pairs_per_gpu

@@ -65,7 +65,7 @@ int64_t da_launch_count(void);
 void da_launch_count_reset(void);
 /* Debug / test options.  The library reads its DA_* environment variables ONCE, when it is loaded (no getenv on any
  * launch path); this call changes one afterwards.  Names: "roi_no_tc" (bf16 RoIAlign on the CUDA-core kernels instead of
- * the tcgen05 ones), "umma_no_bn64", "umma_no_2sm", "no_pdl", "umma_dbg", "roi_bwd_dbg", "roi_bwd_trace".  Process-wide
+ * the tcgen05 ones), "umma_no_bn64", "umma_no_2sm", "no_pdl", "umma_dbg", "roi_bwd_dbg", "roi_fwd_dbg", "roi_bwd_trace", "chain_trace".  Process-wide
  * and not meant to be flipped while other threads launch; defaults (all 0) are what production runs.
  * Per-DEVICE state (da_set_sm_limit, da_set_dropout_counter) belongs to the calling thread's current CUDA device. */
 int da_set_option(const char* name, long long value);
@@ -396,9 +396,14 @@ typedef struct da_instance_fc_desc {
   float drop_p;          /* 0 = eval */
   uint64_t seed1, seed2; /* dropout seeds of fc1 / fc2 */
   float grl;             /* gradient-reversal weight folded into dx (backward), instance_da.py:20-23 */
+  /* Optional feeding layer in the same kernel (the last shared FC of the bbox head, convfc_bbox_head.py:229-237, which produces
+   * the features the head reads): x = relu(xin * w0^T + b0).  C0 = width of xin, 0 = no such layer (x is an input).
+   * gate_in = 1: xin is itself a post-ReLU activation of the caller's previous layer; backward then emits dxin already
+   * multiplied by that layer's ReLU derivative (xin > 0) and its bias gradient db_in = colsum(dxin). */
+  int C0, gate_in;
 } da_instance_fc_desc;
 typedef struct da_instance_fc_tensors {
-  const void* x;         /* bf16 [R,C] */
+  const void* x;         /* bf16 [R,C]; an OUTPUT of forward (saved activation) when desc.C0 > 0 */
   const void* w_proj;    /* bf16 [3I,C]: conv_theta | conv_phi | conv_g weights in ONE buffer (nlb) */
   const void* w_mask;    /* bf16 [C,I] (nlb) */
   const void* w1; const float* b1;   /* bf16 [H1,C], f32 [H1] */
@@ -414,6 +419,7 @@ typedef struct da_instance_fc_tensors {
   float* z;              /* f32 [R,2] raw logits of fc3 */
   float* pred;           /* f32 [R,2] sigmoid(z): what the reference head returns */
   float* loss;           /* f32 scalar: mean CE(pred, labels) */
+  const void* xin; const void* w0; const float* b0;   /* feeding layer (desc.C0 > 0): bf16 [R,C0], bf16 [C,C0], f32 [C] */
 } da_instance_fc_tensors;
 typedef struct da_instance_fc_grads {
   const float* grad_loss;   /* device scalar (NULL = 1) */
@@ -425,6 +431,10 @@ typedef struct da_instance_fc_grads {
   float* dw1; float* db1; float* dw2; float* db2; float* dw3; float* db3;
   void* dz2; void* dz1;     /* scratch bf16 [R,H2], [R,H1] */
   void* dt; void* dy; void* dproj;   /* scratch bf16 [R,C], [R,I], [R,3I] (nlb) */
+  /* feeding layer (desc.C0 > 0): dx then holds the gradient w.r.t. the layer's PRE-activation (dx * (x > 0)) */
+  void* dxin;               /* bf16 [R,C0] */
+  float* dw0; float* db0;   /* f32 [C,C0], [C] */
+  float* db_in;             /* f32 [C0] (gate_in) */
 } da_instance_fc_grads;
 size_t da_instance_fc_workspace_bytes(int R);
 int da_instance_fc_forward(const da_instance_fc_desc* d, const da_instance_fc_tensors* t, void* workspace, size_t workspace_bytes,

@@ -694,6 +694,8 @@ def test_daf_org_hot_path_at_bench_shape_vs_oracle(engine):
     def recording_chain(*a, **k):         # bf16 engine: the instance head is ONE kernel; its stored activations h1, h2
         loss_c, pred_c = chain_orig(*a, **k)
         sv = loss_c.grad_fn.keep[2]
+        if k.get("pre") is not None:      # the last shared FC ran inside the kernel: its output is the kernel's stored x
+            acts.append(loss_c.grad_fn.keep[0].detach())
         acts.extend([sv["h1"].detach(), sv["h2"].detach()])
         return loss_c, pred_c
 
@@ -907,6 +909,53 @@ def test_instance_head_chain_vs_oracle_and_layerwise(name, R):
     for k, p in m.named_parameters():
         if k in chain_grads:
             assert fro(chain_grads[k], p.grad) <= 0.12, k
+
+
+@pytest.mark.parametrize("name", ["instance_alignment", "instance_alignment_daf"])
+@pytest.mark.parametrize("R", [300, 1024])
+def test_instance_head_chain_feeding_layer_matches_separate_layers(name, R):
+    """desc.C0 > 0: the last shared FC of the bbox head (convfc_bbox_head.py:229-237) runs INSIDE the chain kernel, forward and
+    backward, and the kernel applies the ReLU derivative of the FC before it and returns that layer's bias gradient
+    (hotpath.SharedFCs.split + dense_layer(preact_grad=True)).  Same storage points (bf16 activations) as the separate
+    launches, so loss, pred, the gradient into the RoI features and EVERY parameter gradient of both FCs and of the head agree
+    to accumulation-order noise."""
+    from unsupervised_domain_adaptation_object_detection_implementation_b200 import da_heads, hotpath
+    uda.set_engine("umma_bf16")
+    torch.manual_seed(0)
+    fcs = hotpath.SharedFCs(64, 2, 1024).to(DEV)
+    seeded.fill_state_(fcs, 3, "feed.")
+    with torch.no_grad():
+        for fc in fcs.shared_fcs:
+            fc.bias.add_(0.05)            # non-trivial biases (the module initialises them to 0)
+    head = build_head(name, 1).to(DEV).eval()
+    roi = seeded.feature_map("feed.roi", (R, 64, 2, 2), 0).to(DEV).to(torch.bfloat16)
+    labels = (torch.arange(R, device=DEV) >= R // 2).long()
+    gpred = seeded.seeded_tensor("feed.gp", (R, 2), 0, scale=0.3 / R).to(DEV)
+    outs = []
+    for feed in (True, False):
+        x = roi.clone().requires_grad_(True)
+        if feed:
+            assert fcs.can_feed_chain(x)
+            xin, pre = fcs.split(x)
+            loss, pred = head.forward_loss(None, labels, pre=(xin,) + pre)
+        else:
+            loss, pred = head.forward_loss(fcs(x), labels)
+        (0.1 * loss + (pred * gpred).sum()).backward()
+        grads = {"x": x.grad.float().clone()}
+        for mod, pfx in ((fcs, "fcs."), (head, "head.")):
+            for k, p in mod.named_parameters():
+                if p.grad is not None:
+                    grads[pfx + k] = p.grad.clone()
+                    p.grad = None
+        outs.append((float(loss), pred.detach().clone(), grads))
+    (la, pa, ga), (lb, pb, gb) = outs
+    fro = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+    assert abs(la - lb) <= 1e-4 * abs(lb) and rel_err(pa, pb) <= 1e-3
+    assert set(ga) == set(gb), set(ga) ^ set(gb)
+    errs = {k: fro(ga[k], gb[k]) for k in ga}
+    print(f"\n[chain feed {name} R={R}]", {k: f"{v:.1e}" for k, v in errs.items()})
+    assert all(v <= 2e-2 for v in errs.values()), errs
+    assert "fcs.shared_fcs.0.bias" in ga and "fcs.shared_fcs.1.weight" in ga
 
 
 def test_instance_head_chain_dropout_matches_layerwise_masks():

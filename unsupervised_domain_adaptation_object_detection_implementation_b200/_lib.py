@@ -49,20 +49,21 @@ class SgdFuse(Structure):
 class InstanceFcDesc(Structure):
     """da_instance_fc_desc (include/da_b200.h)."""
     _fields_ = [("R", c_int), ("C", c_int), ("I", c_int), ("H1", c_int), ("H2", c_int), ("nlb", c_int), ("drop_p", c_float),
-                ("seed1", c_uint64), ("seed2", c_uint64), ("grl", c_float)]
+                ("seed1", c_uint64), ("seed2", c_uint64), ("grl", c_float), ("C0", c_int), ("gate_in", c_int)]
 
 
 class InstanceFcTensors(Structure):
     """da_instance_fc_tensors."""
     _fields_ = [(n, c_void_p) for n in ("x", "w_proj", "w_mask", "w1", "b1", "w2", "b2", "w3", "b3", "labels", "proj", "attn", "y", "t",
-                                        "h1", "h2", "z", "pred", "loss")]
+                                        "h1", "h2", "z", "pred", "loss", "xin", "w0", "b0")]
 
 
 class InstanceFcGrads(Structure):
     """da_instance_fc_grads."""
     _fields_ = [("grad_loss", c_void_p), ("loss_scale", c_float), ("grad_pred", c_void_p), ("dx", c_void_p), ("dw_proj", c_void_p),
                 ("dw_mask", c_void_p), ("dw1", c_void_p), ("db1", c_void_p), ("dw2", c_void_p), ("db2", c_void_p), ("dw3", c_void_p),
-                ("db3", c_void_p), ("dz2", c_void_p), ("dz1", c_void_p), ("dt", c_void_p), ("dy", c_void_p), ("dproj", c_void_p)]
+                ("db3", c_void_p), ("dz2", c_void_p), ("dz1", c_void_p), ("dt", c_void_p), ("dy", c_void_p), ("dproj", c_void_p),
+                ("dxin", c_void_p), ("dw0", c_void_p), ("db0", c_void_p), ("db_in", c_void_p)]
 
 
 class PixelTail(Structure):

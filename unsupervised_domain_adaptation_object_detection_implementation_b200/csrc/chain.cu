@@ -661,6 +661,7 @@ static int check_desc(const da_instance_fc_desc* d, const char* who) {
   DA_REQUIRE(d->C % 64 == 0 && d->H1 % 64 == 0 && d->H2 % 64 == 0 && (!d->nlb || (d->I > 0 && d->I % 64 == 0)), DA_ERR_UNSUPPORTED,
              "%s: channel counts must be multiples of 64 (C=%d I=%d H1=%d H2=%d)", who, d->C, d->I, d->H1, d->H2);
   DA_REQUIRE(d->drop_p >= 0.f && d->drop_p < 1.f, DA_ERR_INVALID_ARG, "%s: drop_p out of [0,1)", who);
+  DA_REQUIRE(d->C0 >= 0 && d->C0 % 64 == 0, DA_ERR_UNSUPPORTED, "%s: C0=%d must be a multiple of 64 (0 = no feeding layer)", who, d->C0);
   return DA_OK;
 }
 
@@ -677,8 +678,12 @@ extern "C" int da_instance_fc_forward(const da_instance_fc_desc* d, const da_ins
   uint8_t* ws = (uint8_t*)workspace;
   unsigned int* barrier = (unsigned int*)ws;
   float* S = (float*)(ws + 256);
+  DA_REQUIRE(d->C0 == 0 || (t->xin && t->w0), DA_ERR_INVALID_ARG, "instance_fc_forward: null feeding-layer tensor");
   Builder b;
   int g = 0;
+  // feeding layer: x = relu(xin W0^T + b0)                                                (convfc_bbox_head.py:229-237)
+  if (d->C0 > 0)
+    if (ChainOp* o = b.gemm(g++, t->xin, 0, d->C0, t->w0, 0, d->C0, R, C, d->C0, const_cast<void*>(t->x), 0, C)) { o->bias = t->b0; o->relu = 1; }
   const void* feat = t->x;      // input of FC1
   if (d->nlb) {
     const __nv_bfloat16* proj = (const __nv_bfloat16*)t->proj;
@@ -712,6 +717,8 @@ extern "C" int da_instance_fc_backward(const da_instance_fc_desc* d, const da_in
              "instance_fc_backward: null gradient buffer");
   DA_REQUIRE(!d->nlb || (t->w_proj && t->w_mask && t->proj && t->attn && t->y && t->t && gr->dw_proj && gr->dw_mask && gr->dt && gr->dy && gr->dproj),
              DA_ERR_INVALID_ARG, "instance_fc_backward: null NonLocalBlock tensor");
+  DA_REQUIRE(d->C0 == 0 || (t->xin && t->w0 && gr->dxin && gr->dw0 && gr->db0 && (!d->gate_in || gr->db_in)), DA_ERR_INVALID_ARG,
+             "instance_fc_backward: null feeding-layer tensor");
   DA_REQUIRE(workspace && workspace_bytes >= da_instance_fc_workspace_bytes(d->R), DA_ERR_WORKSPACE, "instance_fc_backward: workspace too small");
   const int R = d->R, C = d->C, I = d->I, H1 = d->H1, H2 = d->H2, ldp = pad8(R);
   uint8_t* ws = (uint8_t*)workspace;
@@ -740,7 +747,10 @@ extern "C" int da_instance_fc_backward(const da_instance_fc_desc* d, const da_in
   if (d->nlb) {
     b.gemm(g, gr->dz1, 0, H1, t->w1, 1, C, R, C, H1, gr->dt, 0, C);
   } else {
-    if (ChainOp* o = b.gemm(g, gr->dz1, 0, H1, t->w1, 1, C, R, C, H1, gr->dx, 0, C)) o->alpha = d->grl;   // reversed gradient leaves here
+    if (ChainOp* o = b.gemm(g, gr->dz1, 0, H1, t->w1, 1, C, R, C, H1, gr->dx, 0, C)) {
+      o->alpha = d->grl;   // reversed gradient leaves here
+      if (d->C0 > 0) { o->gate = (const __nv_bfloat16*)t->x; o->ld_gate = C; }
+    }
   }
   if (ChainOp* o = b.add(CH_COLSUM, g++)) { o->p0 = gr->dz1; o->q0 = gr->db1; o->i0 = R; o->i1 = H1; o->i2 = H1; }
   if (d->nlb) {
@@ -761,7 +771,18 @@ extern "C" int da_instance_fc_backward(const da_instance_fc_desc* d, const da_in
     b.gemm(g, dproj, 1, 3 * I, t->x, 1, C, 3 * I, C, R, gr->dw_proj, 1, C);
     if (ChainOp* o = b.gemm(g++, dproj, 0, 3 * I, t->w_proj, 1, C, R, C, 3 * I, gr->dx, 0, C)) {
       o->res = (const __nv_bfloat16*)gr->dt; o->ld_res = C; o->alpha = d->grl;
+      if (d->C0 > 0) { o->gate = (const __nv_bfloat16*)t->x; o->ld_gate = C; }
     }
+  }
+  if (d->C0 > 0) {
+    // feeding layer: dx now holds dz0 = grl * d(x) * (x > 0); dW0 = dz0^T xin, db0 = colsum(dz0), dxin = dz0 W0 [* (xin > 0)]
+    const int C0 = d->C0;
+    b.gemm(g, gr->dx, 1, C, t->xin, 1, C0, C, C0, R, gr->dw0, 1, C0);
+    if (ChainOp* o = b.gemm(g, gr->dx, 0, C, t->w0, 1, C0, R, C0, C, gr->dxin, 0, C0))
+      if (d->gate_in) { o->gate = (const __nv_bfloat16*)t->xin; o->ld_gate = C0; }
+    if (ChainOp* o = b.add(CH_COLSUM, g++)) { o->p0 = gr->dx; o->q0 = gr->db0; o->i0 = R; o->i1 = C; o->i2 = C; }
+    if (d->gate_in)
+      if (ChainOp* o = b.add(CH_COLSUM, g++)) { o->p0 = gr->dxin; o->q0 = gr->db_in; o->i0 = R; o->i1 = C0; o->i2 = C0; }
   }
   return launch_chain(b, barrier, (cudaStream_t)stream);
 }

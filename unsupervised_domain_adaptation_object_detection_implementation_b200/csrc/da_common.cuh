@@ -50,6 +50,7 @@ struct Options {
   int no_pdl;         // DA_NO_PDL         : no programmatic dependent launch
   int umma_dbg;       // DA_UMMA_DBG       : timing experiments (results are wrong when set)
   int roi_bwd_dbg;    // DA_ROI_BWD_DBG    : timing experiments (results are wrong when set)
+  int roi_fwd_dbg;    // DA_ROI_FWD_DBG    : timing experiments (bit 0: no MMAs, bit 1: no output stores; results are wrong when set)
   unsigned long long chain_trace;     // device address of a u64 buffer: per-group globaltimer stamps of the chain kernel (tools/trace_chain.py)
   unsigned long long roi_bwd_trace;   // DA_ROI_BWD_TRACE: device address of a [ctas][8] u64 trace buffer (tools/trace_roi_bwd.py)
 };

@@ -25,6 +25,7 @@ static Options read_options() {
   o.no_pdl = env_int("DA_NO_PDL");
   { const char* e = getenv("DA_UMMA_DBG"); o.umma_dbg = e ? atoi(e) : 0; }
   { const char* e = getenv("DA_ROI_BWD_DBG"); o.roi_bwd_dbg = e ? atoi(e) : 0; }
+  { const char* e = getenv("DA_ROI_FWD_DBG"); o.roi_fwd_dbg = e ? atoi(e) : 0; }
   { const char* e = getenv("DA_ROI_BWD_TRACE"); o.roi_bwd_trace = e ? strtoull(e, nullptr, 0) : 0ull; }
   return o;
 }
@@ -274,6 +275,7 @@ extern "C" int da_set_option(const char* name, long long value) {
   else if (!strcmp(name, "no_pdl")) g_opt.no_pdl = (int)value;
   else if (!strcmp(name, "umma_dbg")) g_opt.umma_dbg = (int)value;
   else if (!strcmp(name, "roi_bwd_dbg")) g_opt.roi_bwd_dbg = (int)value;
+  else if (!strcmp(name, "roi_fwd_dbg")) g_opt.roi_fwd_dbg = (int)value;
   else if (!strcmp(name, "roi_bwd_trace")) g_opt.roi_bwd_trace = (unsigned long long)value;
   else if (!strcmp(name, "chain_trace")) g_opt.chain_trace = (unsigned long long)value;
   else DA_REQUIRE(false, DA_ERR_INVALID_ARG, "set_option: unknown option '%s'", name);

@@ -114,7 +114,7 @@ __device__ __forceinline__ int sched_pop(uint32_t sfull0, uint32_t sempty0, cons
 template <typename TOut>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 roi_align_fwd_tc_kernel(const __grid_constant__ CUtensorMap fmap, int C, int H, int W, int R,
-                        const unsigned char* __restrict__ ws, TOut* __restrict__ out) {
+                        const unsigned char* __restrict__ ws, TOut* __restrict__ out, int dbg) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -224,8 +224,9 @@ roi_align_fwd_tc_kernel(const __grid_constant__ CUtensorMap fmap, int C, int H, 
               const uint64_t ad = ad0 + (uint64_t)((slot * TC_ASTAGE) >> 4);
               const uint64_t bd = bd0 + (uint64_t)((bb * TC_BBUF + ql * TC_BQUAD) >> 4);
               const uint32_t accf = (ch > 0 || ql > 0) ? 1u : 0u;
-              for (int j = me; j < nb_g; j += TC_NISSUE)
-                umma_bf16(tmem_base + (accb + j) * TC_NB, ad + (uint64_t)(j * 256), bd, idesc, accf);
+              if (!(dbg & 1))
+                for (int j = me; j < nb_g; j += TC_NISSUE)
+                  umma_bf16(tmem_base + (accb + j) * TC_NB, ad + (uint64_t)(j * 256), bd, idesc, accf);
               umma_commit(empty0 + 8 * slot);
             }
             if (last_use) umma_commit(b_free + 8 * bb);   // all of THIS issuer's MMAs reading the weight chunk have completed
@@ -331,7 +332,7 @@ roi_align_fwd_tc_kernel(const __grid_constant__ CUtensorMap fmap, int C, int H, 
           for (int k = 32; k < PP; ++k) stg[k] = from_f32<TOut>(__uint_as_float(v1[k - 32]));
           fence_proxy_async();
           named_bar_sync(2, 128);
-          if (tid == 0) {
+          if (tid == 0 && !(dbg & 2)) {
             const int c0 = mb * TC_MCH;
             const int nch = min(TC_MCH, C - c0);
             bulk_s2g(out + ((size_t)r * C + c0) * PP, stage0 + sb * STG, (uint32_t)(nch * PP * sizeof(TOut)));
@@ -359,7 +360,7 @@ static int launch_tc(const CUtensorMap& fmap, int C, int H, int W, int R, const 
                                        reinterpret_cast<int*>((unsigned char*)const_cast<void*>(ws) + ws_order_off(R, H, W)));
   DA_LAUNCH_CHECK();
   const int grid = R < num_sms() ? R : num_sms();
-  k<<<grid, TC_THREADS, smem, st>>>(fmap, C, H, W, R, (const unsigned char*)ws, (TOut*)out);
+  k<<<grid, TC_THREADS, smem, st>>>(fmap, C, H, W, R, (const unsigned char*)ws, (TOut*)out, g_opt.roi_fwd_dbg);
   DA_LAUNCH_CHECK();
   return DA_OK;
 }

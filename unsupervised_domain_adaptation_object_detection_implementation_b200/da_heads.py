@@ -428,9 +428,17 @@ USE_CHAIN = True      # functional.instance_head_chain for the instance heads on
 USE_FUSED_TAIL = True # functional.conv_pixel_loss for the pixel-level heads (False: separate pixel_head / loss kernels)
 
 
+USE_CHAIN_FEED = True # let the chain kernel also run the FC that produces the RoI features (hotpath.SharedFCs.split)
+
+
 def _chain_ok(x):
     return USE_CHAIN and x.is_cuda and x.dim() == 2 and x.shape[0] > 0 and F_.get_engine() == "umma_bf16" and x.shape[1] % 64 == 0 \
         and torch.is_grad_enabled()
+
+
+def chain_feed_ok(xin):
+    """The instance heads can take `pre=(xin, w0, b0, b_in)` (the layer producing their input runs inside the chain kernel)."""
+    return USE_CHAIN_FEED and _chain_ok(xin) and xin.dtype == torch.bfloat16
 
 
 class InstanceAlignmentHead(_HeadBase):
@@ -464,18 +472,19 @@ class InstanceAlignmentHead(_HeadBase):
     def forward(self, x):
         return torch.sigmoid(self.forward_logits(x))
 
-    def forward_loss(self, x, labels):
+    def forward_loss(self, x, labels, pre=None):
         """(mean CE(sigmoid(fc3(...)), labels), pred = sigmoid(fc3(...))): the head AND the instance loss built on it
         (DAFaster_rcnn_Orig.py:177-188).  On the bf16 tensor-core engine this is ONE kernel forward and ONE backward
-        (functional.instance_head_chain -> da_instance_fc_forward/backward); the other engines run layer by layer."""
-        if _chain_ok(x):
+        (functional.instance_head_chain -> da_instance_fc_forward/backward); the other engines run layer by layer.
+        pre=(xin, w0, b0, b_in) with x=None: the FC producing the features joins the kernel (see chain_feed_ok)."""
+        if pre is not None or _chain_ok(x):
             p = self._p()
             seeds = (_draw_seed(self.training, p), _draw_seed(self.training, p))
             nlb = self.nlb
-            return F_.instance_head_chain(F_.cast(x.contiguous(), torch.bfloat16), labels,
+            return F_.instance_head_chain(None if pre is not None else F_.cast(x.contiguous(), torch.bfloat16), labels,
                                           (nlb.conv_theta.weight, nlb.conv_phi.weight, nlb.conv_g.weight), nlb.conv_mask.weight,
                                           ((self.fc1.weight, self.fc1.bias), (self.fc2.weight, self.fc2.bias), (self.fc3.weight, self.fc3.bias)),
-                                          p, seeds, self.grl.weight)
+                                          p, seeds, self.grl.weight, pre=pre)
         return F_.ce2(self.forward_logits(x), labels, True)
 
     def _init_weights(self):
@@ -506,14 +515,14 @@ class InstanceAlignmentHead_DAF(_HeadBase):
     def forward(self, x):
         return torch.sigmoid(self.forward_logits(x))
 
-    def forward_loss(self, x, labels):
+    def forward_loss(self, x, labels, pre=None):
         """See InstanceAlignmentHead.forward_loss (same kernel without the NonLocalBlock part)."""
-        if _chain_ok(x):
+        if pre is not None or _chain_ok(x):
             p = self._p()
             seeds = (_draw_seed(self.training, p), _draw_seed(self.training, p))
-            return F_.instance_head_chain(F_.cast(x.contiguous(), torch.bfloat16), labels, None, None,
+            return F_.instance_head_chain(None if pre is not None else F_.cast(x.contiguous(), torch.bfloat16), labels, None, None,
                                           ((self.fc1.weight, self.fc1.bias), (self.fc2.weight, self.fc2.bias), (self.fc3.weight, self.fc3.bias)),
-                                          p, seeds, self.grl.weight)
+                                          p, seeds, self.grl.weight, pre=pre)
         return F_.ce2(self.forward_logits(x), labels, True)
 
     def _init_weights(self):

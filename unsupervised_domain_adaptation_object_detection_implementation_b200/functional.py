@@ -464,9 +464,11 @@ class DenseLayerFunction(Function):
     is a head input) + wgrad + the two column sums that give d(scale), d(shift)."""
 
     @staticmethod
-    def forward(ctx, x, w, scale, shift, stride, pad, relu, drop_p, seed, engine, grl, out_dtype, shadow=None, managed=None):
+    def forward(ctx, x, w, scale, shift, stride, pad, relu, drop_p, seed, engine, grl, out_dtype, shadow=None, managed=None,
+                preact_grad=False):
         _require_cuda(x, w)
         ctx.managed = managed
+        ctx.preact_grad = preact_grad
         N, H, W_, Cin = x.shape
         x = x.contiguous()
         if shadow is not None:
@@ -504,6 +506,12 @@ class DenseLayerFunction(Function):
         dy = cast(dy.contiguous(), out_dtype)
         need_scale, need_shift = ctx.needs_input_grad[2], ctx.needs_input_grad[3]
         trivial = (not relu) and drop_p == 0.0 and sc is None and not (need_scale or need_shift)
+        if ctx.preact_grad:
+            # the consumer (functional.instance_head_chain with a feeding layer) already applied this layer's ReLU derivative
+            # and produced the bias gradient: dy IS dz
+            if need_scale or need_shift or sc is not None or drop_p != 0.0:
+                raise RuntimeError("dense_layer(preact_grad=True): pass a detached shift, no scale, no dropout")
+            trivial = True
         dshift = dvdot = None
         if trivial:
             dz = dy
@@ -574,7 +582,7 @@ class DenseLayerFunction(Function):
             t = sh if sh is not None else torch.zeros_like(dshift)
             safe = torch.where(sc == 0, torch.ones_like(sc), sc)
             dscale = torch.where(sc == 0, torch.zeros_like(sc), (dvdot - t * dshift) / safe)
-        return dx, dw, dscale, (dshift if need_shift else None), None, None, None, None, None, None, None, None, None, None
+        return dx, dw, dscale, (dshift if need_shift else None), None, None, None, None, None, None, None, None, None, None, None
 
 
 def _umma_ok(x, w):
@@ -585,7 +593,9 @@ def _umma_ok(x, w):
 
 
 def dense_layer(x, w, scale=None, shift=None, stride=1, pad=0, relu=False, drop_p=0.0, seed=0, engine=None,
-                grl=1.0, out_dtype=None):
+                grl=1.0, out_dtype=None, preact_grad=False):
+    """preact_grad=True: the gradient that will arrive for the output is already the PRE-activation gradient (its consumer
+    applied relu' and owns the bias gradient): backward skips the activation pass; `shift` must not require grad."""
     engine = engine or get_engine()
     if engine != "simt_f32" and not (_umma_ok(x, w) and stride <= 2):
         engine = "simt_f32"  # shapes the tensor-core tiles cannot express (e.g. the 2-logit FC)
@@ -598,7 +608,8 @@ def dense_layer(x, w, scale=None, shift=None, stride=1, pad=0, relu=False, drop_
             raise RuntimeError("a peer-managed weight needs the bf16 tensor-core engine (its operand copy is what the peers refresh)")
         w = w.detach()
         managed.before_forward()
-    return DenseLayerFunction.apply(x, w, scale, shift, stride, pad, relu, drop_p, seed, engine, grl, out_dtype, shadow, managed)
+    return DenseLayerFunction.apply(x, w, scale, shift, stride, pad, relu, drop_p, seed, engine, grl, out_dtype, shadow, managed,
+                                    preact_grad)
 
 
 _DROP_COUNTER = {}
@@ -766,10 +777,21 @@ class InstanceHeadChainFunction(Function):
     """(loss, pred) = CE-on-sigmoid( FC stack ( [NonLocalBlock]( GRL(x) ) ) ) in one kernel; backward in one kernel."""
 
     @staticmethod
-    def forward(ctx, x, labels, nlb_w, w_mask, w1, b1, w2, b2, w3, b3, ops, cfg):
+    def forward(ctx, x, labels, nlb_w, w_mask, w1, b1, w2, b2, w3, b3, ops, cfg, xin=None, w0=None, b0=None, b_in=None, op0=None):
         # nlb_w: packed fp32 [3I,C] view of the projection masters (or None); ops: bf16 operand copies in the same order
-        _require_cuda(x)
-        R, C = x.shape
+        # feeding layer (x is None): x = relu(xin w0^T + b0) inside the kernel; b_in = bias of the layer that produced xin
+        # (a post-ReLU activation) when that layer runs with preact_grad=True: its gradient is returned through b_in
+        pre = xin is not None
+        if pre:
+            _require_cuda(xin)
+            xin = xin.contiguous()
+            R, C0 = xin.shape
+            C = w0.shape[0]
+            x = torch.empty((R, C), dtype=torch.bfloat16, device=xin.device)
+        else:
+            _require_cuda(x)
+            R, C = x.shape
+            C0 = 0
         drop_p, seed1, seed2, grl = cfg
         nlb = nlb_w is not None
         I_ = nlb_w.shape[0] // 3 if nlb else 0
@@ -788,21 +810,25 @@ class InstanceHeadChainFunction(Function):
         loss = torch.empty((), dtype=f32, device=dev)
         op_proj, op_mask, op1, op2, op3 = ops
         b1c, b2c, b3c = (b.detach().float().contiguous() for b in (b1, b2, b3))
-        desc = _lib.InstanceFcDesc(R, C, I_, H1, H2, int(nlb), float(drop_p), int(seed1), int(seed2), float(grl))
+        b0c = b0.detach().float().contiguous() if pre else None
+        desc = _lib.InstanceFcDesc(R, C, I_, H1, H2, int(nlb), float(drop_p), int(seed1), int(seed2), float(grl), C0, int(b_in is not None))
         g = lambda t_: None if t_ is None else t_.data_ptr()
         ten = _lib.InstanceFcTensors(g(x), g(op_proj), g(op_mask), g(op1), g(b1c), g(op2), g(b2c), g(op3), g(b3c), g(lab), g(sv.get("proj")),
-                                     g(sv.get("attn")), g(sv.get("y")), g(sv.get("t")), g(sv["h1"]), g(sv["h2"]), g(sv["z"]), g(pred), g(loss))
+                                     g(sv.get("attn")), g(sv.get("y")), g(sv.get("t")), g(sv["h1"]), g(sv["h2"]), g(sv["z"]), g(pred), g(loss),
+                                     g(xin), g(op0), g(b0c))
         ws = workspace(lib.da_instance_fc_workspace_bytes(R), dev, "chain")
         check(lib.da_instance_fc_forward(ctypes.byref(desc), ctypes.byref(ten), _ptr(ws), ws.numel(), _stream()), "instance_fc_forward")
-        ctx.desc, ctx.ten, ctx.keep = desc, ten, (x, lab, sv, ops, b1c, b2c, b3c, pred)
-        ctx.shapes = (None if not nlb else nlb_w.shape, None if w_mask is None else w_mask.shape, w1.shape, w2.shape, w3.shape)
+        ctx.desc, ctx.ten, ctx.keep = desc, ten, (x, lab, sv, ops, b1c, b2c, b3c, pred, xin, op0, b0c)
+        ctx.shapes = (None if not nlb else nlb_w.shape, None if w_mask is None else w_mask.shape, w1.shape, w2.shape, w3.shape,
+                      None if not pre else w0.shape)
         return loss, pred
 
     @staticmethod
     def backward(ctx, g_loss, g_pred):
-        x, lab, sv, ops, b1c, b2c, b3c, pred = ctx.keep
+        x, lab, sv, ops, b1c, b2c, b3c, pred, xin, op0, b0c = ctx.keep
         desc = ctx.desc
         R, C, I_, H1, H2, nlb = desc.R, desc.C, desc.I, desc.H1, desc.H2, bool(desc.nlb)
+        C0, gate_in = desc.C0, bool(desc.gate_in)
         dev = x.device
         bf, f32 = torch.bfloat16, torch.float32
         gl = None if g_loss is None else g_loss.contiguous().float()
@@ -817,15 +843,21 @@ class InstanceHeadChainFunction(Function):
             dwp, dwm = torch.empty((3 * I_, C), dtype=f32, device=dev), torch.empty((C, I_), dtype=f32, device=dev)
             dt, dy = torch.empty((R, C), dtype=bf, device=dev), torch.empty((R, I_), dtype=bf, device=dev)
             dproj = torch.empty((R, 3 * I_), dtype=bf, device=dev)
+        dxin = dw0 = db0 = db_in = None
+        if C0:
+            dxin = torch.empty((R, C0), dtype=bf, device=dev)
+            dw0, db0 = torch.empty((C, C0), dtype=f32, device=dev), torch.empty((C,), dtype=f32, device=dev)
+            if gate_in:
+                db_in = torch.empty((C0,), dtype=f32, device=dev)
         g = lambda t_: None if t_ is None else t_.data_ptr()
         gr = _lib.InstanceFcGrads(g(gl), 1.0, g(gp), g(dx), g(dwp), g(dwm), g(dw1), g(db1), g(dw2), g(db2), g(dw3), g(db3), g(dz2), g(dz1),
-                                  g(dt), g(dy), g(dproj))
+                                  g(dt), g(dy), g(dproj), g(dxin), g(dw0), g(db0), g(db_in))
         ws = workspace(lib.da_instance_fc_workspace_bytes(R), dev, "chain")
         check(lib.da_instance_fc_backward(ctypes.byref(desc), ctypes.byref(ctx.ten), ctypes.byref(gr), _ptr(ws), ws.numel(), _stream()),
               "instance_fc_backward")
-        s_proj, s_mask, s1, s2, s3 = ctx.shapes
-        return (dx, None, dwp, None if dwm is None else dwm.view(s_mask), dw1.view(s1), db1, dw2.view(s2), db2, dw3.view(s3), db3,
-                None, None)
+        s_proj, s_mask, s1, s2, s3, s0 = ctx.shapes
+        return (None if C0 else dx, None, dwp, None if dwm is None else dwm.view(s_mask), dw1.view(s1), db1, dw2.view(s2), db2,
+                dw3.view(s3), db3, None, None, dxin, None if dw0 is None else dw0.view(s0), db0, db_in, None)
 
 
 class _SplitPacked(Function):
@@ -844,11 +876,20 @@ class _SplitPacked(Function):
         return (None, *parts)
 
 
-def instance_head_chain(x, labels, nlb_weights, w_mask, fcs, drop_p, seeds, grl):
+def instance_head_chain(x, labels, nlb_weights, w_mask, fcs, drop_p, seeds, grl, pre=None):
     """x [R,C] bf16; nlb_weights: (theta, phi, g) conv weights or None; w_mask: conv_mask weight or None;
-    fcs: ((w1,b1),(w2,b2),(w3,b3)).  -> (loss = mean CE(sigmoid(fc3), labels), pred = sigmoid(fc3) [R,2])."""
+    fcs: ((w1,b1),(w2,b2),(w3,b3)).  -> (loss = mean CE(sigmoid(fc3), labels), pred = sigmoid(fc3) [R,2]).
+    pre = (xin [R,C0] bf16, w0 [C,C0], b0 [C], b_in or None): the layer that PRODUCES the features runs inside the kernel
+    (x = relu(xin w0^T + b0); pass x=None); with b_in (the bias of the layer that produced xin, itself called with
+    dense_layer(..., preact_grad=True)) the kernel also applies that layer's ReLU derivative and returns its bias gradient."""
     (w1, b1), (w2, b2), (w3, b3) = fcs
-    C = x.shape[1]
+    if pre is not None:
+        xin, w0, b0, b_in = pre
+        if x is not None or xin.dim() != 2 or w0.shape[1] != xin.shape[1] or xin.shape[1] % 64 or (b_in is not None and b_in.shape[0] != xin.shape[1]):
+            raise RuntimeError("instance_head_chain: bad feeding layer (x must be None, xin [R,C0], w0 [C,C0], C0 % 64 == 0)")
+        C = w0.shape[0]
+    else:
+        C = x.shape[1]
     if nlb_weights is not None and (any(w.shape[1] != C for w in nlb_weights) or w_mask.shape[0] != C or w1.shape[1] != C):
         raise RuntimeError(f"instance_head_chain: features are {C} wide, the NonLocalBlock / fc1 expect {nlb_weights[0].shape[1]} / {w1.shape[1]}")
     if w1.shape[1] != C or w2.shape[1] != w1.shape[0] or w3.shape[1] != w2.shape[0] or w3.shape[0] != 2:
@@ -860,7 +901,11 @@ def instance_head_chain(x, labels, nlb_weights, w_mask, fcs, drop_p, seeds, grl)
     else:
         nlb_w, op_proj, op_mask = None, None, None
     ops = (op_proj, op_mask, bf16_shadow(w1), bf16_shadow(w2), bf16_shadow(w3))
-    return InstanceHeadChainFunction.apply(x, labels, nlb_w, w_mask, w1, b1, w2, b2, w3, b3, ops, (drop_p, seeds[0], seeds[1], grl))
+    cfg = (drop_p, seeds[0], seeds[1], grl)
+    if pre is not None:
+        return InstanceHeadChainFunction.apply(None, labels, nlb_w, w_mask, w1, b1, w2, b2, w3, b3, ops, cfg, xin, w0, b0, b_in,
+                                               bf16_shadow(w0))
+    return InstanceHeadChainFunction.apply(x, labels, nlb_w, w_mask, w1, b1, w2, b2, w3, b3, ops, cfg, None, None, None, None, None)
 
 
 # --------------------------------------------------------------------------------------

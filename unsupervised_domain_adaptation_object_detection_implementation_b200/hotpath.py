@@ -75,6 +75,27 @@ class SharedFCs(nn.Module):
             x = F_.dense_layer(x, fc.weight, None, fc.bias, relu=True)
         return x.view(k, -1)
 
+    def can_feed_chain(self, x):
+        fcs = self.shared_fcs
+        return (len(fcs) >= 2 and da_heads.USE_CHAIN and da_heads.USE_CHAIN_FEED and F_.get_engine() == "umma_bf16"
+                and torch.is_grad_enabled() and x.is_cuda and x.shape[0] > 0
+                and fcs[-1].in_features % 64 == 0 and fcs[-1].out_features % 64 == 0)
+
+    def split(self, x):
+        """All layers but the last, and the last one as the `pre` tuple of InstanceAlignmentHead*.forward_loss: the instance
+        head's chain kernel runs it (forward and backward), applies the ReLU derivative of the layer before it and returns
+        that layer's bias gradient, so the layer before runs with preact_grad=True (no activation-backward / bias-sum kernels).
+        Only for callers whose ONLY consumer of the shared features is the instance head (the hot path)."""
+        x = F_.cast(x.flatten(1), F_.act_dtype())
+        k = x.shape[0]
+        x = x.view(k, 1, 1, -1)
+        fcs = list(self.shared_fcs)
+        for i, fc in enumerate(fcs[:-1]):
+            last = i == len(fcs) - 2
+            x = F_.dense_layer(x, fc.weight, None, fc.bias.detach() if last else fc.bias, relu=True, preact_grad=last)
+        b_in = fcs[-2].bias if len(fcs) >= 2 else None
+        return x.view(k, -1), (fcs[-1].weight, fcs[-1].bias, b_in)
+
 
 class DAFOrgHotPath(nn.Module):
     def __init__(self, in_channels=2048, featmap_stride=16, fc_out_channels=1024,
@@ -99,10 +120,16 @@ class DAFOrgHotPath(nn.Module):
         global_loss, imgs_feat = self.da_head_top.forward_loss(c5, gt_domain)      # H1 + L1: GEMM + one fused tail kernel
         rois = bbox2roi(proposal_list)
         roi_feats = self.bbox_roi_extractor([c5], rois)
-        bbox_feats = self.bbox_head(roi_feats) if self.bbox_head is not None else roi_feats.flatten(1)
         label_da = roi_domain_labels(tuple(len(p) for p in proposal_list), c5.device) if len(proposal_list) == 2 else \
             rois[:, 0].to(torch.int32).clamp(max=1)
-        ins_loss, ins_preds = self.local_da.forward_loss(bbox_feats, label_da)
+        ins_loss = None
+        if self.bbox_head is not None and self.bbox_head.can_feed_chain(roi_feats):
+            # the last shared FC, the instance head and its loss in one kernel per direction
+            xin, (w0, b0, b_in) = self.bbox_head.split(roi_feats)
+            ins_loss, ins_preds = self.local_da.forward_loss(None, label_da, pre=(xin, w0, b0, b_in))
+        if ins_loss is None:
+            bbox_feats = self.bbox_head(roi_feats) if self.bbox_head is not None else roi_feats.flatten(1)
+            ins_loss, ins_preds = self.local_da.forward_loss(bbox_feats, label_da)
         consist = da_losses.consistency_loss(imgs_feat, ins_preds, label_da)
         # lambda weights (DAFaster_rcnn_Orig.py:143-157) and the total of the dict in ONE launch; parse_losses picks the total up
         scaled, total = F_.weighted_losses([ins_loss, global_loss, consist], [self.local_lamda, self.global_lamda, self.consist_lamda])
