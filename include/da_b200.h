@@ -97,7 +97,7 @@ int da_sgd_step(float* w, const float* grad, float* momentum_buf, int64_t n, flo
 /* The same update for MANY tensors in one launch (torch.optim.SGD's foreach path, mmdet/apis/train.py:127).
  * `entries` is a DEVICE array of n_entries records; `chunks` a DEVICE array of n_chunks (entry, chunk) pairs that
  * tiles every tensor in pieces of DA_SGD_CHUNK elements (built once by the caller: sizes do not change). */
-#define DA_SGD_CHUNK 65536
+#define DA_SGD_CHUNK 8192
 typedef struct da_sgd_entry {
   float* w;              /* fp32 weights, 16-byte aligned */
   const float* grad;     /* fp32 gradient, same memory order */

@@ -7,7 +7,7 @@ import torch
 from . import functional as F_
 from ._lib import lib, check, SgdFuse as _lib_SgdFuse
 
-_CHUNK = 65536   # DA_SGD_CHUNK (include/da_b200.h)
+_CHUNK = 8192    # DA_SGD_CHUNK (include/da_b200.h)
 
 
 def _same_layout(a, b):
