@@ -12,8 +12,9 @@
 //     ones) were bound by the per-op overhead.  Per 64-channel group the box is two 128B-swizzle atoms of
 //     the canonical MN-major UMMA layout; a block's second group sits 2048 B further (descriptor LBO).
 //   * B operand = Wt as bf16, K-major (no-swizzle core-matrix layout, 2 KB per quad), built in shared
-//     memory by the epilogue warps from the prep kernel's (Wy, Wx) tables, once per RoI (chunks of 32
-//     quads = 512 pixels for larger footprints) and reused by all channel groups.
+//     memory by a dedicated 4-warp builder team from the prep kernel's (Wy, Wx) tables, once per RoI (chunks of 16
+//     quads = 256 pixels for larger footprints, two chunk buffers so that the builders run one chunk ahead of the
+//     MMAs) and reused by all channel groups.
 //   * D = [128 channels x 64 (49 bins)] fp32 in TMEM; the 4 accumulators of a channel group stay live
 //     while its quads stream through, two groups ping-pong (8 accumulators, 512 columns) so the
 //     epilogue of group g overlaps the MMAs of group g+1; the epilogue writes the [128][49] tile to a
