@@ -587,11 +587,17 @@ struct TnParams {
 // cuts the L2->SM traffic of the 128x256 tile from 48 KB to 16 + 32/kCluster KB per k-step (the kernel was
 // L2-bandwidth bound at 505 TFLOP/s).  Two TMEM accumulators: the epilogue of tile t (128 KB of fp32 stores)
 // runs under the main loop of tile t+1.
-template <int kBN, int kCluster>
+// k2SM (r02): the two CTAs of a cluster form ONE cta_group::2 MMA over 256 output channels: each stages its own 128 Cout rows of
+// dZ and HALF of the X tile (16 + 16 KB per k-step instead of 16 + 32 KB received through multicast), so the bytes every SM
+// has to take in per MMA drop by a third -- the same reasoning as the forward kernel's pair mode.  Same tile assignment as the
+// multicast cluster (two Cout tiles sharing one X tile); the leader owns the full barriers and issues.
+template <int kBN, int kCluster, bool k2SM = false>
 __global__ void __launch_bounds__(NT_FWD_THREADS, 1)
 umma_tn_kernel(const __grid_constant__ TnParams P, int co_tiles, int ci_tiles, int splits) {
-  constexpr int STAGES = TileCfg<kBN>::STAGES;
-  constexpr int W_B_BYTES = kBN * WK * 2;
+  static_assert(!k2SM || kCluster == 2, "the CTA-pair mode is a cluster of exactly two CTAs");
+  constexpr int W_B_FULL = kBN * WK * 2;
+  constexpr int W_B_BYTES = k2SM ? W_B_FULL / 2 : W_B_FULL;          // bytes of X staged in THIS CTA per k-step
+  constexpr int STAGES = (TileCfg<kBN>::STAGES * (W_A_BYTES + W_B_FULL)) / (W_A_BYTES + W_B_BYTES);   // same ring bytes, deeper ring
   constexpr int BN = kBN;
   constexpr int B_BOXES = BN / 64, B_PER_CTA = B_BOXES / kCluster;
   static_assert(B_BOXES % kCluster == 0, "cluster size must divide the 64-channel boxes of the B tile");
@@ -615,12 +621,13 @@ umma_tn_kernel(const __grid_constant__ TnParams P, int co_tiles, int ci_tiles, i
   const long long per_split = (total_iters + splits - 1) / splits;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, kCluster); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, NT_EPI_WARPS); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, k2SM ? 1 : kCluster); }
+    // pair mode: the epilogue warps of BOTH CTAs release an accumulator to the leader's MMA thread
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, k2SM ? 2 * NT_EPI_WARPS : NT_EPI_WARPS); }
     fence_barrier_init();
   }
   pdl_launch_dependents();   // the next kernel of the stream may run its prologue under this one
-  if (warp == 1) tmem_alloc(tslot, 2 * BN);
+  if (warp == 1) { if (k2SM) tmem_alloc_2sm(tslot, 2 * BN); else tmem_alloc(tslot, 2 * BN); }
   tc_fence_before();
   __syncthreads();
   if (kCluster > 1) cluster_sync_all();   // peer barriers are initialised before any multicast lands
@@ -656,8 +663,31 @@ umma_tn_kernel(const __grid_constant__ TnParams P, int co_tiles, int ci_tiles, i
           const int term = (int)(it / patches);
           const long long patch = it % patches;
           const uint32_t fb = full0 + 8 * s;
-          mbar_expect_tx(fb, W_A_BYTES + W_B_BYTES);
           const uint32_t ad = a_s + s * W_A_BYTES, bd = b_s + s * W_B_BYTES;
+          if constexpr (k2SM) {
+            // both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of the whole pair
+            if (crank == 0) mbar_expect_tx(fb, 2 * (W_A_BYTES + W_B_BYTES));
+            if (P.flat) {
+              const int m = (int)(patch * WK);
+              tma_load_2d_2sm(ad, &P.a_map[P.term_a[term]], fb, co0, m);
+              tma_load_2d_2sm(ad + W_A_BYTES / 2, &P.a_map[P.term_a[term]], fb, co0 + 64, m);
+#pragma unroll
+              for (int j = 0; j < B_PER_CTA; ++j)
+                tma_load_2d_2sm(bd + j * (64 * WK * 2), &P.b_map[P.term_b[term]][0], fb, ci0 + (crank * B_PER_CTA + j) * 64, m);
+            } else {
+              const int per_img = P.tiles_h * P.tiles_w;
+              const int n = (int)(patch / per_img), t = (int)(patch % per_img);
+              const int i0 = (t / P.tiles_w) * P.BH, j0 = (t % P.tiles_w) * P.BW;
+              tma_load_4d_2sm(ad, &P.a_map[P.term_a[term]], fb, co0, j0, i0, n);
+              tma_load_4d_2sm(ad + W_A_BYTES / 2, &P.a_map[P.term_a[term]], fb, co0 + 64, j0, i0, n);
+#pragma unroll
+              for (int j = 0; j < B_PER_CTA; ++j)
+                tma_load_4d_2sm(bd + j * (64 * WK * 2), &P.b_map[P.term_b[term]][ti.map], fb, ci0 + (crank * B_PER_CTA + j) * 64,
+                                j0 + ti.dw, i0 + ti.dh, n);
+            }
+            continue;
+          }
+          mbar_expect_tx(fb, W_A_BYTES + W_B_BYTES);
           if (P.flat) {
             const int m = (int)(patch * WK);
             tma_load_2d(ad, &P.a_map[P.term_a[term]], fb, co0, m);
@@ -687,8 +717,8 @@ umma_tn_kernel(const __grid_constant__ TnParams P, int co_tiles, int ci_tiles, i
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN, 1, 1);
+    if (lane == 0 && (!k2SM || crank == 0)) {
+      constexpr uint32_t idesc = make_idesc(k2SM ? 2 * BM : BM, BN, 1, 1);
       int kq = 0, tcount = 0;
       for (long long tile = tile0; tile < total_tiles; tile += tile_step, ++tcount) {
         DA_TN_DECODE(tile)
@@ -707,14 +737,22 @@ umma_tn_kernel(const __grid_constant__ TnParams P, int co_tiles, int ci_tiles, i
             // 16 k-rows = 2 swizzle atoms of 1024 B
             const uint64_t adsc = desc_mnmajor_sw128(a_s + s * W_A_BYTES + kk * 2048, W_A_BYTES / 2);
             const uint64_t bdsc = desc_mnmajor_sw128(b_s + s * W_B_BYTES + kk * 2048, 64 * WK * 2);
-            umma_bf16(d_tmem, adsc, bdsc, idesc, (k > 0 || kk > 0) ? 1u : 0u);
+            if (k2SM) umma_bf16_2sm(d_tmem, adsc, bdsc, idesc, (k > 0 || kk > 0) ? 1u : 0u);
+            else umma_bf16(d_tmem, adsc, bdsc, idesc, (k > 0 || kk > 0) ? 1u : 0u);
           }
-          // the stage is reusable only when EVERY CTA of the cluster is done with it (multicast writes into all)
-          if (kCluster == 1) umma_commit(empty0 + 8 * s);
+          // the stage is reusable only when EVERY CTA of the cluster is done with it (multicast writes into all / the pair
+          // MMA reads both CTAs' shared memory)
+          if (k2SM) umma_commit_2sm(empty0 + 8 * s, 3);
+          else if (kCluster == 1) umma_commit(empty0 + 8 * s);
           else umma_commit_mc(empty0 + 8 * s, (uint16_t)((1u << kCluster) - 1u));
         }
-        if (n_iters > 0) umma_commit(tfull0 + 8 * buf);
-        else mbar_arrive(tfull0 + 8 * buf);
+        if (n_iters > 0) {
+          if (k2SM) umma_commit_2sm(tfull0 + 8 * buf, 3);   // each CTA's epilogue drains its own 128 accumulator rows
+          else umma_commit(tfull0 + 8 * buf);
+        } else {
+          mbar_arrive(tfull0 + 8 * buf);
+          if (k2SM) mbar_arrive_cluster(tfull0 + 8 * buf, 1);
+        }
       }
     }
   } else {
@@ -758,7 +796,7 @@ umma_tn_kernel(const __grid_constant__ TnParams P, int co_tiles, int ci_tiles, i
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+      if (lane == 0) { if (k2SM) mbar_arrive_cluster(tempty0 + 8 * buf, 0); else mbar_arrive(tempty0 + 8 * buf); }
     }
   }
 #undef DA_TN_DECODE
@@ -767,7 +805,7 @@ umma_tn_kernel(const __grid_constant__ TnParams P, int co_tiles, int ci_tiles, i
   if (kCluster > 1) cluster_sync_all();   // no CTA exits while a peer may still multicast into it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN);
+    if (k2SM) tmem_dealloc_2sm(tmem_base, 2 * BN); else tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
@@ -1268,12 +1306,12 @@ int umma_conv_backward_data(const da_conv_desc* d, const void* dz, const void* w
   return DA_OK;
 }
 
-template <int kBN, int kCluster>
+template <int kBN, int kCluster, bool k2SM = false>
 static int launch_tn_t(const TnParams& P, int co_tiles, int ci_tiles, int splits, cudaStream_t st) {
   const long long co_super = (co_tiles + kCluster - 1) / kCluster;
   const long long total = co_super * ci_tiles * P.num_taps * splits;   // cluster-level tile units
   DA_REQUIRE(total * kCluster <= 0x7fffffffll, DA_ERR_UNSUPPORTED, "umma wgrad: too many tiles");
-  auto kern = umma_tn_kernel<kBN, kCluster>;
+  auto kern = umma_tn_kernel<kBN, kCluster, k2SM>;
   static bool attr_set_dev[kMaxDevices] = {};     // function attributes are per device
   bool& attr_set = attr_set_dev[cur_dev()];
   if (!attr_set) {
@@ -1409,7 +1447,8 @@ int umma_conv_backward_weight(const da_conv_desc* d, const void* x, const void* 
   int rc2;
   if (bn == 256) {
     // clusters of 4 only fit 33 times on the 148 SMs (GPC sizes), pairs fit 74 times
-    if (co_tiles >= 2) rc2 = launch_tn_t<256, 2>(P, co_tiles, ci_tiles, splits, st);
+    if (co_tiles >= 2 && co_tiles % 2 == 0 && !g_opt.umma_no_2sm) rc2 = launch_tn_t<256, 2, true>(P, co_tiles, ci_tiles, splits, st);   // CTA pair
+    else if (co_tiles >= 2) rc2 = launch_tn_t<256, 2>(P, co_tiles, ci_tiles, splits, st);
     else rc2 = launch_tn_t<256, 1>(P, co_tiles, ci_tiles, splits, st);
   } else if (bn == 64) {
     rc2 = launch_tn_t<64, 1>(P, co_tiles, ci_tiles, splits, st);
