@@ -552,10 +552,20 @@ def kernel_rooflines(dev, act, step_ms, fused_step=True):
     # DRAM bytes per launch of the same kernel at the same size, measured once with `ncu --set full` (profiles/)
     traffic = None
     try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_hot_kernels_ncu.json")))["kernels"]
+        # round-2 capture (tools/prof_r02.py under ncu --set full, summarised by tools/ncu_summary.py): launches in program order
+        launches = json.load(open(os.path.join(ROOT, "profiles", "r02_hot_kernels_ncu.json")))["launches"]
+        pick = {"roi_align_fwd": ("roi_align_fwd_tc_kernel", 0), "roi_align_bwd": ("roi_align_bwd_tc_kernel", 0),
+                "fc1_fwd": ("umma_nt_kernel<256, 2, 1, 0>", 0), "fc1_dgrad": ("umma_nt_kernel<256, 2, 1, 0>", 1),
+                "fc1_wgrad_sgd": ("umma_tn_kernel<256, 2, 1>", 0)}
+        prof = {}
+        for name, (prefix, inst) in pick.items():
+            for rec in launches:
+                if rec["kernel"].startswith(prefix) and rec["instance"] == inst:
+                    prof[name] = rec
         for k, rec in prof.items():
             if k in table:
                 table[k]["ncu_dram_bytes"] = rec["dram_bytes"]
+                table[k]["ncu_l2_to_sm_bytes"] = rec["l2_to_sm_bytes"]
         traffic = prof.get(dom, {}).get("dram_bytes")
     except (OSError, KeyError, ValueError):
         pass
