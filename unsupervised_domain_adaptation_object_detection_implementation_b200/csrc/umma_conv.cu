@@ -43,11 +43,16 @@ constexpr int MAX_TAPS = 16;
 // Tile configuration: BN = 256 keeps the per-MMA shared-memory traffic (A 4 KB + B 8 KB per 128 cycles)
 // under the 128 B/clk SMEM port; BN = 128 serves narrow outputs.  Two TMEM accumulators (2*BN
 // columns) let the epilogue of tile i overlap the MMAs of tile i+1 (persistent kernel).
+// BN = 512 (r02, CTA-pair mode only): ONE accumulator of 512 columns fills the TMEM, so the epilogue is not overlapped with the
+// next tile -- worth it for long-K problems (FC1 forward: every operand byte is delivered to the SMs 3x instead of 4x; the
+// 256-wide kernel moves 9.3 TB/s L2 -> SM at 64 % tensor-pipe activity, profiles/r02_hot_kernels_ncu.md).  The pair MMA is
+// still N = 256: two instructions per k-substep share the A operand.
 template <int kBN> struct TileCfg {
-  static constexpr int STAGES = (kBN == 256) ? 4 : (kBN == 128 ? 6 : 8);
+  static constexpr int STAGES = (kBN == 512) ? 4 : (kBN == 256) ? 4 : (kBN == 128 ? 6 : 8);   // 512: stages of the PAIR layout (A + B/2)
   static constexpr int B_BYTES = kBN * BK * 2;
-  static constexpr size_t SMEM = 1024 + (size_t)STAGES * (A_BYTES + B_BYTES) + 256 + NT_EPI_WARPS * 4096;   // + epilogue staging
-  static constexpr int TMEM_COLS = 2 * kBN;
+  static constexpr size_t SMEM = 1024 + (size_t)STAGES * (A_BYTES + (kBN == 512 ? B_BYTES / 2 : B_BYTES)) + 256 + NT_EPI_WARPS * 4096;   // + epilogue staging
+  static constexpr int TMEM_COLS = (kBN == 512) ? 512 : 2 * kBN;
+  static constexpr int NBUF = (kBN == 512) ? 1 : 2;
 };
 
 struct TapInfo {
@@ -207,9 +212,11 @@ __global__ void __launch_bounds__(NT_FWD_THREADS, 1)
 umma_nt_kernel(const __grid_constant__ NtParams P, int pixel_tiles, int n_tiles, int splits) {
   using Cfg = TileCfg<kBN>;
   static_assert(!k2SM || kCluster == 2, "the CTA-pair mode is a cluster of exactly two CTAs");
+  static_assert(kBN != 512 || k2SM, "512-wide tiles exist in the CTA-pair mode only");
   static_assert(!kChunked || (kBN == 128 && !k2SM), "chunked accumulation: 128-wide tiles, one CTA per MMA");
+  constexpr int NBUF = Cfg::NBUF;
   constexpr int B_BYTES = k2SM ? Cfg::B_BYTES / 2 : Cfg::B_BYTES;                       // bytes of B staged by THIS CTA per k-step
-  constexpr int STAGES = (Cfg::STAGES * (A_BYTES + Cfg::B_BYTES)) / (A_BYTES + B_BYTES);  // same ring bytes, deeper ring
+  constexpr int STAGES = (kBN == 512) ? Cfg::STAGES : (Cfg::STAGES * (A_BYTES + Cfg::B_BYTES)) / (A_BYTES + B_BYTES);  // same ring bytes, deeper ring
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_s = base, b_s = base + STAGES * A_BYTES;
@@ -281,13 +288,16 @@ umma_nt_kernel(const __grid_constant__ NtParams P, int pixel_tiles, int n_tiles,
               tma_load_2d_2sm(a_s + s * A_BYTES, &P.a_map[P.term_a[term]][0], fb, kc * BK, m0);
             else
               tma_load_4d_2sm(a_s + s * A_BYTES, &P.a_map[P.term_a[term]][ti.map], fb, kc * BK, j0 + ti.dw, i0 + ti.dh, n_img);
-            constexpr int HALF = kBN / 2;   // this CTA stages output channels [crank*HALF, +HALF) of the tile
-            if (P.b_mn_major) {
+            // per 256-column MMA this CTA stages output channels [h2*256 + crank*128, +128) of the tile
 #pragma unroll
-              for (int j = 0; j < HALF / 64; ++j)
-                tma_load_2d_2sm(b_s + s * B_BYTES + j * (64 * BK * 2), bm, fb, ti.bk + c0 + crank * HALF + j * 64, kc * BK);
-            } else {
-              tma_load_2d_2sm(b_s + s * B_BYTES, bm, fb, ti.bk + kc * BK, c0 + crank * HALF);
+            for (int h2 = 0; h2 < kBN / 256; ++h2) {
+              if (P.b_mn_major) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                  tma_load_2d_2sm(b_s + s * B_BYTES + (h2 * 2 + j) * (64 * BK * 2), bm, fb, ti.bk + c0 + h2 * 256 + crank * 128 + j * 64, kc * BK);
+              } else {
+                tma_load_2d_2sm(b_s + s * B_BYTES + h2 * (128 * BK * 2), bm, fb, ti.bk + kc * BK, c0 + h2 * 256 + crank * 128);
+              }
             }
             continue;
           }
@@ -324,14 +334,14 @@ umma_nt_kernel(const __grid_constant__ NtParams P, int pixel_tiles, int n_tiles,
     }
   } else if (warp == 1) {
     if (lane == 0 && (!k2SM || crank == 0)) {
-      const uint32_t idesc = make_idesc(k2SM ? 2 * BM : BM, kBN, 0, P.b_mn_major ? 1 : 0);
+      const uint32_t idesc = make_idesc(k2SM ? 2 * BM : BM, kBN == 512 ? 256 : kBN, 0, P.b_mn_major ? 1 : 0);
       int kq = 0, tcount = 0;
       for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         const int sp = tile % splits;
         const int it_begin = sp * per_split, it_end = min(it_begin + per_split, total_iters);
         // one accumulator hand-over per tile -- or, chunked, per kChunkIters k-steps (tcount counts hand-overs)
-        int buf = tcount & 1;
-        mbar_wait(tempty0 + 8 * buf, (((uint32_t)(tcount >> 1)) & 1u) ^ 1u);   // epilogue has drained this accumulator
+        int buf = tcount % NBUF;
+        mbar_wait(tempty0 + 8 * buf, (((uint32_t)(tcount / NBUF)) & 1u) ^ 1u);   // epilogue has drained this accumulator
         tc_fence_after();
         uint32_t d_tmem = tmem_base + buf * kBN;
         for (int it = it_begin; it < it_end; ++it, ++kq) {
@@ -354,7 +364,12 @@ umma_nt_kernel(const __grid_constant__ NtParams P, int pixel_tiles, int n_tiles,
             const uint64_t ad = desc_kmajor_sw128(a_s + s * A_BYTES + kk * 32);
             const uint64_t bd = P.b_mn_major ? desc_mnmajor_sw128(b_s + s * B_BYTES + kk * 2048, 64 * BK * 2)
                                              : desc_kmajor_sw128(b_s + s * B_BYTES + kk * 32);
-            if (k2SM) umma_bf16_2sm(d_tmem, ad, bd, idesc, (!fresh || kk > 0) ? 1u : 0u);
+            if (kBN == 512) {     // two N = 256 pair MMAs share the A operand
+              umma_bf16_2sm(d_tmem, ad, bd, idesc, (!fresh || kk > 0) ? 1u : 0u);
+              const uint64_t bd2 = P.b_mn_major ? desc_mnmajor_sw128(b_s + s * B_BYTES + 2 * (64 * BK * 2) + kk * 2048, 64 * BK * 2)
+                                                : desc_kmajor_sw128(b_s + s * B_BYTES + 128 * BK * 2 + kk * 32);
+              umma_bf16_2sm(d_tmem + 256, ad, bd2, idesc, (!fresh || kk > 0) ? 1u : 0u);
+            } else if (k2SM) umma_bf16_2sm(d_tmem, ad, bd, idesc, (!fresh || kk > 0) ? 1u : 0u);
             else umma_bf16(d_tmem, ad, bd, idesc, (!fresh || kk > 0) ? 1u : 0u);
           }
           // the stage is reusable only when BOTH CTAs are done with it (multicast writes into both)
@@ -427,8 +442,8 @@ umma_nt_kernel(const __grid_constant__ NtParams P, int pixel_tiles, int n_tiles,
         nt_epilogue_chunk(P, u, row_off, valid, c0 + (ehalf + 2) * 32, raw, partial, epi_stage + (warp - 2) * 4096, lane);
         continue;
       }
-      const int buf = tcount & 1;
-      const uint32_t use = (uint32_t)(tcount >> 1);
+      const int buf = tcount % NBUF;
+      const uint32_t use = (uint32_t)(tcount / NBUF);
       ++tcount;
       mbar_wait(tfull0 + 8 * buf, use & 1u);
       tc_fence_after();
@@ -1150,6 +1165,7 @@ static int launch_nt(NtParams& P, int bn, long long pixel_tiles, int k_iters, vo
   if (P.num_terms == 6)   // fp32-class engine: chunked accumulation (short TMEM chains, fp32 register sums), 128-wide tiles
     return nt_cluster(128, pixel_tiles) == 2 ? launch_nt_t<128, 2, false, true>(P, pixel_tiles, k_iters, ws_part, part_cap, st)
                                              : launch_nt_t<128, 1, false, true>(P, pixel_tiles, k_iters, ws_part, part_cap, st);
+  if (bn == 512) return launch_nt_t<512, 2, true>(P, pixel_tiles, k_iters, ws_part, part_cap, st);
   if (nt_pair_mma(bn, pixel_tiles)) return launch_nt_t<256, 2, true>(P, pixel_tiles, k_iters, ws_part, part_cap, st);
   const int cl = nt_cluster(bn, pixel_tiles);   // CTAs sharing the weight tile through TMA multicast
   if (bn == 256)
@@ -1184,7 +1200,7 @@ int umma_conv_forward(const da_conv_desc* d, const void* x, const void* w, const
   P.scale = scale; P.shift = shift; P.relu = relu; P.drop_p = drop_p; P.seed = seed; P.seed_ctr = g_seed_counter; P.out_scale = 1.f;
   P.y = y; P.y_dtype = d->y_dtype; P.y_numel = (long long)g.N * g.OH * g.OW * g.Cout;
   const int Ktot = g.KH * g.KW * g.Cin;
-  const int bn = d->engine == DA_ENGINE_UMMA_BF16X6 ? 128 : choose_bn(g.Cout, (long long)g.N * g.OH * g.OW, (Ktot + BK - 1) / BK);
+  int bn = d->engine == DA_ENGINE_UMMA_BF16X6 ? 128 : choose_bn(g.Cout, (long long)g.N * g.OH * g.OW, (Ktot + BK - 1) / BK);
   long long pixel_tiles;
   if (is_flat(g)) {
     P.flat = 1;
@@ -1220,11 +1236,15 @@ int umma_conv_forward(const da_conv_desc* d, const void* x, const void* w, const
     P.num_taps = nt;
     pixel_tiles = (long long)g.N * P.tiles_h * P.tiles_w;
   }
+  // long-K problems whose tiles pair up: 512-wide tiles (one TMEM accumulator, two N = 256 pair MMAs per k-substep)
+  if (bn == 256 && d->engine == DA_ENGINE_UMMA_BF16 && nt_pair_mma(bn, pixel_tiles) && g.Cout % 512 == 0 &&
+      (long long)P.num_taps * P.kchunks >= 256 && !g_opt.umma_no_bn512)
+    bn = 512;
   for (int t = 0; t < wsrc.n; ++t) {
     // a 2-CTA cluster (pixel_tiles >= 2, see launch_nt) loads the weight tile as two multicast halves
     const uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)g.Cout};
     const uint64_t strides[1] = {(uint64_t)Ktot * 2};
-    const uint32_t box[2] = {BK, (uint32_t)(bn / nt_cluster(bn, pixel_tiles))};
+    const uint32_t box[2] = {BK, (uint32_t)(bn == 512 ? 128 : bn / nt_cluster(bn, pixel_tiles))};
     rc = encode_map(&P.b_map[t], wsrc.p[t], 2, dims, strides, box);
     if (rc) return rc;
   }
