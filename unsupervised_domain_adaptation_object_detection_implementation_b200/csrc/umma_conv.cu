@@ -1151,7 +1151,9 @@ static int launch_nt_t(NtParams& P, long long pixel_tiles, int k_iters, void* ws
 //   pair (2 CTAs, ONE cta_group::2 MMA over 256 pixel rows) when the pixel tiles pair up and the tile is 256 wide;
 //   else 2 CTAs sharing the weight tile through TMA multicast; else single CTAs.
 static inline bool nt_pair_mma(int bn, long long pixel_tiles) {
-  return bn == 256 && pixel_tiles >= 2 && pixel_tiles % 2 == 0 && !g_opt.umma_no_2sm;
+  // an odd tile count leaves one phantom tile in the last pair (its A rows are TMA zero fill, its rows are not stored):
+  // accepted when that is < 7 % of the work
+  return bn == 256 && pixel_tiles >= 2 && (pixel_tiles % 2 == 0 || pixel_tiles >= 15) && !g_opt.umma_no_2sm;
 }
 static inline int nt_cluster(int bn, long long pixel_tiles) {
   (void)bn;
@@ -1275,7 +1277,15 @@ int umma_conv_backward_data(const da_conv_desc* d, const void* dz, const void* w
   base.OHf = g.H; base.OWf = g.W;
   base.relu = 0; base.drop_p = 0.f; base.out_scale = out_scale;
   base.y = dx; base.y_dtype = d->y_dtype; base.y_numel = (long long)g.N * g.H * g.W * g.Cin;
-  const int bn = d->engine == DA_ENGINE_UMMA_BF16X6 ? 128 : choose_bn(g.Cin, (long long)g.N * g.H * g.W, ((long long)taps * g.Cout + BK - 1) / BK);
+  int bn = d->engine == DA_ENGINE_UMMA_BF16X6 ? 128 : choose_bn(g.Cin, (long long)g.N * g.H * g.W, ((long long)taps * g.Cout + BK - 1) / BK);
+  // long-K stride-1 data gradients whose pixel tiles pair up: 512-wide tiles (see TileCfg)
+  if (bn == 256 && d->engine == DA_ENGINE_UMMA_BF16 && g.s == 1 && g.Cin % 512 == 0 && (long long)taps * base.kchunks >= 256 &&
+      !g_opt.umma_no_bn512) {
+    long long ptiles;
+    if (is_flat(g)) ptiles = ((long long)g.N * g.H * g.W + BM - 1) / BM;
+    else { int bh, bw; pick_patch(g.H, g.W, BM, &bh, &bw); ptiles = (long long)g.N * ((g.H + bh - 1) / bh) * ((g.W + bw - 1) / bw); }
+    if (nt_pair_mma(bn, ptiles)) bn = 512;
+  }
   for (int t = 0; t < wsrc.n; ++t) {
     const uint64_t dims[2] = {(uint64_t)taps * g.Cin, (uint64_t)g.Cout};
     const uint64_t strides[1] = {(uint64_t)taps * g.Cin * 2};
