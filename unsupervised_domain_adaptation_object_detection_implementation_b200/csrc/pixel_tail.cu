@@ -81,6 +81,29 @@ __device__ __forceinline__ float tail_dot<__nv_bfloat16>(const __nv_bfloat16* __
   return warp_sum(acc);
 }
 
+// two rows at once: both rows' loads are in flight before the first FMA (the per-pixel chain load -> dot -> shuffle tree is
+// latency bound)
+__device__ __forceinline__ void tail_dot2_bf16(const __nv_bfloat16* __restrict__ x0, const __nv_bfloat16* __restrict__ x1,
+                                               const float* __restrict__ w_s, int K, int lane, float& p0, float& p1) {
+  float a0 = 0.f, a1 = 0.f;
+#pragma unroll 2
+  for (int i = lane * 8; i < K; i += 256) {
+    const uint4 u0 = *reinterpret_cast<const uint4*>(x0 + i);
+    const uint4 u1 = *reinterpret_cast<const uint4*>(x1 + i);
+    const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&u0);
+    const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&u1);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f0 = __bfloat1622float2(h0[e]), f1 = __bfloat1622float2(h1[e]);
+      const float w0 = w_s[i + 2 * e], w1 = w_s[i + 2 * e + 1];
+      a0 = fmaf(f0.x, w0, a0); a0 = fmaf(f0.y, w1, a0);
+      a1 = fmaf(f1.x, w0, a1); a1 = fmaf(f1.y, w1, a1);
+    }
+  }
+  p0 = warp_sum(a0);
+  p1 = warp_sum(a1);
+}
+
 // grid (blocks per image, N).  partial[(n*nb + blk)*2 + {0,1}]; ticket: last block reduces.
 template <typename T>
 __global__ void __launch_bounds__(PT_THREADS)
@@ -98,9 +121,9 @@ pixel_tail_fwd_kernel(const T* __restrict__ h, TailArgs a, float* __restrict__ l
   const int d = a.domain[n];
   const float t = d == 1 ? 1.f : 0.f;
   float s0 = 0.f, s1 = 0.f;
-  for (long long i = (long long)blockIdx.x * PT_WARPS + wid; i < a.L; i += (long long)nb * PT_WARPS) {
-    const long long m = (long long)n * a.L + i;
-    float p = tail_dot<T>(h + (size_t)m * a.K, w_s, a.K, lane) + bv;
+  const long long stride = (long long)nb * PT_WARPS;
+  auto account = [&](long long m, float p) {
+    p += bv;
     if (a.relu) p = fmaxf(p, 0.f);
     if (lane == 0) {
       logits[m] = p;
@@ -112,6 +135,21 @@ pixel_tail_fwd_kernel(const T* __restrict__ h, TailArgs a, float* __restrict__ l
         s0 += a.mode == 2 ? bce_term(p, t) : focal_term(p, t, a.gamma, a.alpha);
       }
     }
+  };
+  long long i = (long long)blockIdx.x * PT_WARPS + wid;
+  if (sizeof(T) == 2 && (a.K & 7) == 0) {
+    for (; i + stride < a.L; i += 2 * stride) {      // same per-pixel order of the partial sums as the one-row loop
+      const long long m0 = (long long)n * a.L + i, m1 = m0 + stride;
+      float p0, p1;
+      tail_dot2_bf16(reinterpret_cast<const __nv_bfloat16*>(h) + (size_t)m0 * a.K, reinterpret_cast<const __nv_bfloat16*>(h) + (size_t)m1 * a.K,
+                     w_s, a.K, lane, p0, p1);
+      account(m0, p0);
+      account(m1, p1);
+    }
+  }
+  for (; i < a.L; i += stride) {
+    const long long m = (long long)n * a.L + i;
+    account(m, tail_dot<T>(h + (size_t)m * a.K, w_s, a.K, lane));
   }
   s0 = block_sum<false>(s0, red);
   s1 = block_sum<false>(s1, red);
@@ -219,6 +257,7 @@ pixel_tail_bwd_kernel(const T* __restrict__ y, TailArgs a, const float* __restri
       sc[j] = (scale && j < nk) ? scale[k0 + j] : 1.f;
       aw[j] = as[j] = ad[j] = 0.f;
     }
+#pragma unroll 2
     for (long long m = m0 + sub; m < m1; m += SUB) {
       const float dl = dl_s[m - m0];
       if (cg == 0) dbias += dl;
@@ -289,26 +328,29 @@ pixel_tail_bwd_kernel(const T* __restrict__ y, TailArgs a, const float* __restri
 
 // out[0..3K) = sum over blocks of partial[blk][0..3K); out[3K] = sum of the bias partials.  Block = 32 columns x 8 block
 // lanes; the 8 lane sums meet in shared memory in a fixed order (deterministic).
-__global__ void __launch_bounds__(256)
+constexpr int PT_FINAL_LANES = 32;      // block lanes per column (1024 threads): ~9 partials per thread, four loads in flight
+__global__ void __launch_bounds__(32 * PT_FINAL_LANES)
 pixel_tail_final_kernel(const float* __restrict__ partial, int nb, int K, float* __restrict__ dw_tail,
                         float* __restrict__ dshift, float* __restrict__ dvdot, float* __restrict__ dbias) {
-  __shared__ float red[8][33];
+  __shared__ float red[PT_FINAL_LANES][33];
   pdl_wait();
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + tx;
   float s = 0.f;
   if (i < 3 * K) {
     const int which = i / K, k = i - which * K;
-    for (int b = ty; b < nb; b += 8) s += partial[(size_t)b * 4 * K + which * K + k];
+#pragma unroll 4
+    for (int b = ty; b < nb; b += PT_FINAL_LANES) s += partial[(size_t)b * 4 * K + which * K + k];
   } else if (i == 3 * K) {
-    for (int b = ty; b < nb; b += 8) s += partial[(size_t)nb * 4 * K + b];
+#pragma unroll 4
+    for (int b = ty; b < nb; b += PT_FINAL_LANES) s += partial[(size_t)nb * 4 * K + b];
   }
   red[ty][tx] = s;
   __syncthreads();
   if (ty == 0) {
     float t = 0.f;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) t += red[q][tx];
+    for (int q = 0; q < PT_FINAL_LANES; ++q) t += red[q][tx];
     if (i < 3 * K) {
       const int which = i / K, k = i - which * K;
       float* dst = which == 0 ? dw_tail : (which == 1 ? dshift : dvdot);
@@ -439,7 +481,7 @@ extern "C" int da_pixel_tail_backward(const da_conv_desc* d, const void* y, cons
   const float* cpartial = partial;
   int K = a.K, nbv = nb;
   void* fargs[] = {(void*)&cpartial, (void*)&nbv, (void*)&K, (void*)&dw_tail, (void*)&dshift, (void*)&dvdot, (void*)&dbias_tail};
-  return launch_pdl(pixel_tail_final_kernel, dim3((3 * a.K + 1 + 31) / 32), dim3(256), 0, st, fargs);
+  return launch_pdl(pixel_tail_final_kernel, dim3((3 * a.K + 1 + 31) / 32), dim3(32 * PT_FINAL_LANES), 0, st, fargs);
 }
 
 // Composite entry points: producing conv (tcgen05 implicit GEMM, fused BN/bias + ReLU + dropout epilogue) -> tail.
