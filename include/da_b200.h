@@ -65,7 +65,7 @@ int64_t da_launch_count(void);
 void da_launch_count_reset(void);
 /* Debug / test options.  The library reads its DA_* environment variables ONCE, when it is loaded (no getenv on any
  * launch path); this call changes one afterwards.  Names: "roi_no_tc" (bf16 RoIAlign on the CUDA-core kernels instead of
- * the tcgen05 ones), "umma_no_bn64", "umma_no_2sm", "umma_no_bn512", "no_pdl", "umma_dbg", "roi_bwd_dbg", "roi_fwd_dbg", "roi_bwd_trace", "chain_trace".  Process-wide
+ * the tcgen05 ones), "umma_no_bn64", "umma_no_2sm", "umma_no_bn512", "chain_no_bn128", "no_pdl", "umma_dbg", "roi_bwd_dbg", "roi_fwd_dbg", "roi_bwd_trace", "chain_trace".  Process-wide
  * and not meant to be flipped while other threads launch; defaults (all 0) are what production runs.
  * Per-DEVICE state (da_set_sm_limit, da_set_dropout_counter) belongs to the calling thread's current CUDA device. */
 int da_set_option(const char* name, long long value);

@@ -24,14 +24,19 @@
 
 namespace da {
 
-constexpr int CH_BM = 128, CH_BN = 64, CH_BK = 64;
-constexpr int CH_A_BYTES = CH_BM * CH_BK * 2;      // 16 KB
-constexpr int CH_B_BYTES = CH_BN * CH_BK * 2;      //  8 KB
-constexpr int CH_STAGES = 8;
+// Tile width per op: 64 (more tiles: the small GEMMs are latency sized) or 128 (groups whose tiles fill the machine anyway:
+// with every SM pulling operands the L2 fabric, not the SM port, is the limit, and a 128-wide tile needs 1/3 fewer operand
+// bytes per FLOP).  The 192 KB operand ring is cut per GROUP: 8 stages of 16 + 8 KB, or 6 stages of 16 + 16 KB when the group
+// has a 128-wide op (everything is drained at a group boundary; mbarrier phases are tracked per stage, not per ring turn).
+constexpr int CH_BM = 128, CH_BN_MAX = 128, CH_BK = 64;
+constexpr int CH_A_BYTES = CH_BM * CH_BK * 2;          // 16 KB
+constexpr int CH_B_BYTES = CH_BN_MAX * CH_BK * 2;      // 16 KB (wide stage)
+constexpr int CH_STAGES = 8;                           // barriers; a wide group uses 6 of them
+constexpr int CH_RING_BYTES = 8 * (CH_A_BYTES + CH_B_BYTES / 2);   // 192 KB = 6 * (16 + 16) KB
 constexpr int CH_THREADS = 320;                    // TMA warp, MMA warp, 8 epilogue warps
 constexpr int CH_MAX_OPS = 28;
 constexpr int CH_MAX_GROUPS = 16;
-constexpr size_t CH_SMEM_FIXED = 1024 + (size_t)CH_STAGES * (CH_A_BYTES + CH_B_BYTES) + 512;   // + the program copy (see CH_SMEM)
+constexpr size_t CH_SMEM_FIXED = 1024 + (size_t)CH_RING_BYTES + 512;   // + the program copy (see CH_SMEM)
 
 enum ChainKind {
   CH_GEMM = 0,
@@ -48,6 +53,7 @@ struct __align__(128) ChainOp {
   // ---- GEMM: out[M,N] = epilogue(A[M,K] * B[N,K]^T)
   int a_mn, b_mn;            // 0 = K-major ([rows, K] row-major), 1 = MN-major ([K, rows] row-major)
   int M, N, K;
+  int bn;                    // tile width: 64 or 128
   int tiles_m, tiles_n;
   float alpha;               // v = alpha * (acc + res) + bias
   const float* bias;         // [N] or null
@@ -119,7 +125,7 @@ __device__ __forceinline__ void ch_tile_of(const ChainOp* ops, int ob, int oe, i
   for (int o = ob; o < oe; ++o) {
     if (ops[o].kind != CH_GEMM) continue;
     const int n = ops[o].tiles_m * ops[o].tiles_n;
-    if (t < n) { op = o; m0 = (t / ops[o].tiles_n) * CH_BM; n0 = (t % ops[o].tiles_n) * CH_BN; return; }
+    if (t < n) { op = o; m0 = (t / ops[o].tiles_n) * CH_BM; n0 = (t % ops[o].tiles_n) * ops[o].bn; return; }
     t -= n;
   }
 }
@@ -387,8 +393,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
 chain_kernel(const __grid_constant__ ChainParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t a_s = base, b_s = base + CH_STAGES * CH_A_BYTES;
-  const uint32_t bars = b_s + CH_STAGES * CH_B_BYTES;
+  const uint32_t bars = base + CH_RING_BYTES;
   const uint32_t full0 = bars, empty0 = bars + 8 * CH_STAGES, tfull0 = bars + 16 * CH_STAGES, tempty0 = tfull0 + 16, tslot = tempty0 + 16;
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
   volatile uint32_t* tslot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (tslot - base));
@@ -412,7 +417,7 @@ chain_kernel(const __grid_constant__ ChainParams P) {
     for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, 8); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tslot, 2 * CH_BN);
+  if (warp == 1) tmem_alloc(tslot, 2 * CH_BN_MAX);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -420,7 +425,8 @@ chain_kernel(const __grid_constant__ ChainParams P) {
   pdl_wait();      // NO early griddepcontrol.launch_dependents: a dependent grid's CTAs must not take SMs this grid barrier needs
   const unsigned long long seed_add = P.seed_ctr ? *P.seed_ctr : 0ull;
 
-  int kq = 0, tcount = 0;       // ring position (producer / MMA thread), accumulator hand-overs (MMA thread / epilogue warps)
+  int tcount = 0;               // accumulator hand-overs (MMA thread / epilogue warps)
+  uint32_t ring_bits = 0;       // producer: uses of empty[s] mod 2; MMA thread: uses of full[s] mod 2
   int tr = 0;
 #define CH_STAMP()                                                                                        \
   do {                                                                                                    \
@@ -434,7 +440,12 @@ chain_kernel(const __grid_constant__ ChainParams P) {
   for (int g = 0; g < P.ngroups; ++g) {
     const int ob = P.group_begin[g], oe = P.group_begin[g + 1];
     int total = 0;
-    for (int o = ob; o < oe; ++o) if (ops[o].kind == CH_GEMM) total += ops[o].tiles_m * ops[o].tiles_n;
+    bool wide_g = false;
+    for (int o = ob; o < oe; ++o)
+      if (ops[o].kind == CH_GEMM) { total += ops[o].tiles_m * ops[o].tiles_n; wide_g |= (ops[o].bn == 128); }
+    const int nstages = wide_g ? 6 : 8;
+    const uint32_t stage_bytes = CH_A_BYTES + (wide_g ? CH_B_BYTES : CH_B_BYTES / 2);
+    int rs = 0;                   // ring stage (producer / MMA thread); the ring is empty at a group boundary
     if (warp == 0) {
       if (lane == 0) {
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
@@ -444,20 +455,26 @@ chain_kernel(const __grid_constant__ ChainParams P) {
           const CUtensorMap* amap = &P.ops[op].a_map;     // the TMA engine reads descriptors from the parameter space
           const CUtensorMap* bmap = &P.ops[op].b_map;
           const int kchunks = (o.K + CH_BK - 1) / CH_BK;
-          for (int kc = 0; kc < kchunks; ++kc, ++kq) {
-            const int s = kq % CH_STAGES;
-            mbar_wait(empty0 + 8 * s, (((uint32_t)(kq / CH_STAGES)) & 1u) ^ 1u);
+          for (int kc = 0; kc < kchunks; ++kc) {
+            const int s = rs;
+            rs = (rs + 1 == nstages) ? 0 : rs + 1;
+            mbar_wait(empty0 + 8 * s, ((ring_bits >> s) & 1u) ^ 1u);
+            ring_bits ^= 1u << s;
             const uint32_t fb = full0 + 8 * s;
-            mbar_expect_tx(fb, CH_A_BYTES + CH_B_BYTES);
-            const uint32_t ad = a_s + s * CH_A_BYTES, bd = b_s + s * CH_B_BYTES;
+            mbar_expect_tx(fb, CH_A_BYTES + o.bn * CH_BK * 2);
+            const uint32_t ad = base + s * stage_bytes, bd = ad + CH_A_BYTES;
             if (o.a_mn) {
               tma_load_2d(ad, amap, fb, m0, kc * CH_BK);
               tma_load_2d(ad + CH_A_BYTES / 2, amap, fb, m0 + 64, kc * CH_BK);
             } else {
               tma_load_2d(ad, amap, fb, kc * CH_BK, m0);
             }
-            if (o.b_mn) tma_load_2d(bd, bmap, fb, n0, kc * CH_BK);
-            else tma_load_2d(bd, bmap, fb, kc * CH_BK, n0);
+            if (o.b_mn) {
+              tma_load_2d(bd, bmap, fb, n0, kc * CH_BK);
+              if (o.bn == 128) tma_load_2d(bd + CH_B_BYTES / 2, bmap, fb, n0 + 64, kc * CH_BK);
+            } else {
+              tma_load_2d(bd, bmap, fb, kc * CH_BK, n0);      // box rows = o.bn (encoded per op)
+            }
           }
         }
       }
@@ -468,21 +485,22 @@ chain_kernel(const __grid_constant__ ChainParams P) {
           ch_tile_of(ops, ob, oe, t, op, m0, n0);
           const ChainOp& o = ops[op];
           const int kchunks = (o.K + CH_BK - 1) / CH_BK;
-          const uint32_t idesc = make_idesc(CH_BM, CH_BN, o.a_mn, o.b_mn);
+          const uint32_t idesc = make_idesc(CH_BM, o.bn, o.a_mn, o.b_mn);
           const int buf = tcount & 1;
           mbar_wait(tempty0 + 8 * buf, (((uint32_t)(tcount >> 1)) & 1u) ^ 1u);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + buf * CH_BN;
-          for (int kc = 0; kc < kchunks; ++kc, ++kq) {
-            const int s = kq % CH_STAGES;
-            mbar_wait(full0 + 8 * s, ((uint32_t)(kq / CH_STAGES)) & 1u);
+          const uint32_t d_tmem = tmem_base + buf * CH_BN_MAX;
+          for (int kc = 0; kc < kchunks; ++kc) {
+            const int s = rs;
+            rs = (rs + 1 == nstages) ? 0 : rs + 1;
+            mbar_wait(full0 + 8 * s, (ring_bits >> s) & 1u);
+            ring_bits ^= 1u << s;
+            const uint32_t a_st = base + s * stage_bytes, b_st = a_st + CH_A_BYTES;
             tc_fence_after();
 #pragma unroll
             for (int kk = 0; kk < CH_BK / 16; ++kk) {
-              const uint64_t adsc = o.a_mn ? desc_mnmajor_sw128(a_s + s * CH_A_BYTES + kk * 2048, CH_A_BYTES / 2)
-                                           : desc_kmajor_sw128(a_s + s * CH_A_BYTES + kk * 32);
-              const uint64_t bdsc = o.b_mn ? desc_mnmajor_sw128(b_s + s * CH_B_BYTES + kk * 2048, CH_B_BYTES)
-                                           : desc_kmajor_sw128(b_s + s * CH_B_BYTES + kk * 32);
+              const uint64_t adsc = o.a_mn ? desc_mnmajor_sw128(a_st + kk * 2048, CH_A_BYTES / 2) : desc_kmajor_sw128(a_st + kk * 32);
+              const uint64_t bdsc = o.b_mn ? desc_mnmajor_sw128(b_st + kk * 2048, CH_B_BYTES / 2) : desc_kmajor_sw128(b_st + kk * 32);
               umma_bf16(d_tmem, adsc, bdsc, idesc, (kc > 0 || kk > 0) ? 1u : 0u);
             }
             umma_commit(empty0 + 8 * s);
@@ -501,17 +519,24 @@ chain_kernel(const __grid_constant__ ChainParams P) {
         mbar_wait(tfull0 + 8 * buf, ((uint32_t)(tcount >> 1)) & 1u);
         tc_fence_after();
         uint32_t v[32];
-        if (o.K > 0) {
-          DA_TMEM_LD32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * CH_BN + chunk * 32, v);
-          tmem_ld_wait();
-        } else {
+        const int nch = o.bn == 128 ? 2 : 1;               // 32-column chunks of this warp: chunk, chunk + 2
+#pragma unroll 1
+        for (int ci = 0; ci < nch; ++ci) {
+          const int cc = chunk + 2 * ci;
+          if (o.K > 0) {
+            DA_TMEM_LD32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * CH_BN_MAX + cc * 32, v);
+            tmem_ld_wait();
+          } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0u;
+            for (int j = 0; j < 32; ++j) v[j] = 0u;
+          }
+          if (ci == nch - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * buf);      // the accumulator is in registers: the next tile may start
+          }
+          ch_epilogue_chunk(o, v, m0 + q * 32 + lane, n0 + cc * 32, o.seed + seed_add);
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty0 + 8 * buf);      // the accumulator is in registers: the next tile may start
-        ch_epilogue_chunk(o, v, m0 + q * 32 + lane, n0 + chunk * 32, o.seed + seed_add);
       }
     }
     if (P.trace && blockIdx.x == 0 && lane == 0 && (warp < 3 || warp == 9)) {     // per-role "done" stamps of the group
@@ -547,7 +572,7 @@ chain_kernel(const __grid_constant__ ChainParams P) {
   if (P.ngroups < 2) pdl_launch_dependents();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * CH_BN);
+    tmem_dealloc(tmem_base, 2 * CH_BN_MAX);
   }
 }
 
@@ -557,8 +582,10 @@ chain_kernel(const __grid_constant__ ChainParams P) {
 struct Builder {
   ChainParams P;
   int rc;
+  struct Operands { const void* A; const void* B; int lda, ldb; } raw[CH_MAX_OPS];   // tensor maps are encoded in finish()
   Builder() : rc(DA_OK) {
     memset(&P, 0, sizeof(P));
+    memset(raw, 0, sizeof(raw));
   }
   ChainOp* add(int kind, int group) {
     if (P.nops >= CH_MAX_OPS || group >= CH_MAX_GROUPS) { set_error("chain: program too long"); rc = DA_ERR_UNSUPPORTED; return nullptr; }
@@ -582,15 +609,35 @@ struct Builder {
     ChainOp* o = add(CH_GEMM, group);
     if (!o) return nullptr;
     o->a_mn = a_mn; o->b_mn = b_mn; o->M = M; o->N = N; o->K = K;
-    o->tiles_m = (M + CH_BM - 1) / CH_BM; o->tiles_n = (N + CH_BN - 1) / CH_BN;
+    o->bn = 64;
     o->out = out; o->out_f32 = out_f32; o->ld_out = ld_out;
-    int r = encode(&o->a_map, A, a_mn, M, K, lda, CH_BM);
-    if (!r) r = encode(&o->b_map, B, b_mn, N, K, ldb, CH_BN);
-    if (r) rc = r;
+    raw[P.nops - 1] = Operands{A, B, lda, ldb};
     return o;
   }
   int finish() {
     if (rc) return rc;
+    // tile width per group: 128 when the group's wide-eligible GEMMs still give (nearly) every SM a tile, else 64
+    for (int g = 0; g < P.ngroups; ++g) {
+      int wide_tiles = 0, narrow_other = 0;
+      for (int i = 0; i < P.nops; ++i) {
+        const ChainOp& o = P.ops[i];
+        if (o.group != g || o.kind != CH_GEMM) continue;
+        const int tm = (o.M + CH_BM - 1) / CH_BM;
+        if (o.N % 128 == 0 && o.K >= 256) wide_tiles += tm * (o.N / 128);
+        else narrow_other += tm * ((o.N + 63) / 64);
+      }
+      const bool wide = !g_opt.chain_no_bn128 && wide_tiles + narrow_other >= (num_sms() * 5) / 8;
+      for (int i = 0; i < P.nops; ++i) {
+        ChainOp& o = P.ops[i];
+        if (o.group != g || o.kind != CH_GEMM) continue;
+        o.bn = (wide && o.N % 128 == 0 && o.K >= 256) ? 128 : 64;
+        o.tiles_m = (o.M + CH_BM - 1) / CH_BM;
+        o.tiles_n = (o.N + o.bn - 1) / o.bn;
+        int r = encode(&o.a_map, raw[i].A, o.a_mn, o.M, o.K, raw[i].lda, CH_BM);
+        if (!r) r = encode(&o.b_map, raw[i].B, o.b_mn, o.N, o.K, raw[i].ldb, o.bn);
+        if (r) return r;
+      }
+    }
     // ops were appended group by group, in order
     int g = 0;
     P.group_begin[0] = 0;

@@ -50,6 +50,7 @@ struct Options {
   int no_pdl;         // DA_NO_PDL         : no programmatic dependent launch
   int umma_dbg;       // DA_UMMA_DBG       : timing experiments (results are wrong when set)
   int umma_no_bn512;  // DA_UMMA_NO_BN512  : no 512-wide pair tiles for long-K forward GEMMs
+  int chain_no_bn128; // DA_CHAIN_NO_BN128  : instance-head chain kernel with 64-wide tiles only (A/B)
   int roi_bwd_dbg;    // DA_ROI_BWD_DBG    : timing experiments (results are wrong when set)
   int roi_fwd_dbg;    // DA_ROI_FWD_DBG    : timing experiments (bit 0: no MMAs, bit 1: no output stores; results are wrong when set)
   unsigned long long chain_trace;     // device address of a u64 buffer: per-group globaltimer stamps of the chain kernel (tools/trace_chain.py)

@@ -25,6 +25,7 @@ static Options read_options() {
   o.no_pdl = env_int("DA_NO_PDL");
   { const char* e = getenv("DA_UMMA_DBG"); o.umma_dbg = e ? atoi(e) : 0; }
   o.umma_no_bn512 = getenv("DA_UMMA_NO_BN512") != nullptr;
+  o.chain_no_bn128 = getenv("DA_CHAIN_NO_BN128") != nullptr;
   { const char* e = getenv("DA_ROI_BWD_DBG"); o.roi_bwd_dbg = e ? atoi(e) : 0; }
   { const char* e = getenv("DA_ROI_FWD_DBG"); o.roi_fwd_dbg = e ? atoi(e) : 0; }
   { const char* e = getenv("DA_ROI_BWD_TRACE"); o.roi_bwd_trace = e ? strtoull(e, nullptr, 0) : 0ull; }
@@ -275,6 +276,7 @@ extern "C" int da_set_option(const char* name, long long value) {
   else if (!strcmp(name, "umma_no_bn64")) g_opt.umma_no_bn64 = (int)value;
   else if (!strcmp(name, "umma_no_2sm")) g_opt.umma_no_2sm = (int)value;
   else if (!strcmp(name, "umma_no_bn512")) g_opt.umma_no_bn512 = (int)value;
+  else if (!strcmp(name, "chain_no_bn128")) g_opt.chain_no_bn128 = (int)value;
   else if (!strcmp(name, "no_pdl")) g_opt.no_pdl = (int)value;
   else if (!strcmp(name, "umma_dbg")) g_opt.umma_dbg = (int)value;
   else if (!strcmp(name, "roi_bwd_dbg")) g_opt.roi_bwd_dbg = (int)value;
