@@ -188,6 +188,14 @@ int da_roi_align_backward(const void* grad_out, int grad_dtype, int out_layout,
                           float spatial_scale, int sampling_ratio, int aligned,
                           void* grad_in_nhwc, int grad_in_dtype, int N, int C, int H, int W,
                           void* workspace, size_t workspace_bytes, da_stream_t stream);
+/* Same, for a workspace that still holds the preparation of THIS RoI set: the last call that wrote `workspace` was
+ * da_roi_align_forward (or da_roi_align_backward) with the same rois, R, N, H, W, spatial_scale, sampling_ratio and aligned,
+ * on the same stream.  Skips the preparation launch (tap tables, footprints) -- the caller keeps track (functional.py does). */
+int da_roi_align_backward_prepared(const void* grad_out, int grad_dtype, int out_layout,
+                          const float* rois, int R, int pooled_h, int pooled_w,
+                          float spatial_scale, int sampling_ratio, int aligned,
+                          void* grad_in_nhwc, int grad_in_dtype, int N, int C, int H, int W,
+                          void* workspace, size_t workspace_bytes, da_stream_t stream);
 /* FPN level mapping, single_level_roi_extractor.py:36-55. levels_out int32 [R]. */
 int da_map_roi_levels(const float* rois, int R, int num_levels, float finest_scale,
                       int32_t* levels_out, da_stream_t stream);

@@ -117,6 +117,7 @@ SIGNATURES = {
     "da_roi_align_workspace_bytes": (S, [I, I, I]),
     "da_roi_align_forward": (I, [P, I, I, I, I, I, P, I, I, I, F, I, I, P, I, I, P, P, S, P]),
     "da_roi_align_backward": (I, [P, I, I, P, I, I, I, F, I, I, P, I, I, I, I, I, P, S, P]),
+    "da_roi_align_backward_prepared": (I, [P, I, I, P, I, I, I, F, I, I, P, I, I, I, I, I, P, S, P]),
     "da_map_roi_levels": (I, [P, I, I, F, P, P]),
     "da_pixel_loss_workspace_bytes": (S, [I, L]),
     "da_pixel_domain_loss_forward": (I, [P, I, L, P, I, P, P, S, P]),

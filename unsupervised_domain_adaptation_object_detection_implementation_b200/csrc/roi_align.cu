@@ -105,6 +105,7 @@ __global__ void roi_prep_kernel(const float* __restrict__ rois, int R, int N, in
     if (lane < P) axis_samples(x1, bw, gw_s, lane, W, 1, x_lo, wx, d0, d1);
     else if (lane >= 8 && lane < 8 + P) axis_samples(y1, bh, gh_s, lane - 8, H, 1, y_lo, wy, d0, d1);
   }
+  int last = 0;
   if (lane == 0) {
     RoiMeta m;
     m.b = b; m.gh = gh; m.gw = gw;
@@ -112,6 +113,45 @@ __global__ void roi_prep_kernel(const float* __restrict__ rois, int R, int N, in
     m.count = max(gh * gw, 1);
     metas[r] = m;
     if (grid_out) { grid_out[2 * r] = gh; grid_out[2 * r + 1] = gw; }
+    __threadfence();
+    last = atomicAdd(&err[2], 1) == R - 1;      // hdr[2]: blocks done (zeroed by the host with the rest of the header)
+  }
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (!last) return;
+  // The LAST block orders the RoIs by decreasing footprint (work queue of the tensor-core forward, roi_align_tc.cu): counting
+  // sort over 256 buckets of quad counts by one warp -- a separate single-block kernel cost a launch and 8 us for this.
+  // The order inside a bucket depends on atomics, the results do not (every RoI's output is independent of when it is computed).
+  __threadfence();
+  __shared__ int hist[256];
+  int* order = reinterpret_cast<int*>(ws + ws_order_off(R, H, W));
+  for (int k = lane; k < 256; k += 32) hist[k] = 0;
+  __syncwarp();
+  for (int i = lane; i < R; i += 32) {
+    const RoiMeta m = metas[i];
+    const int nq = ((m.ny + 3) >> 2) * ((m.nx + 3) >> 2);
+    atomicAdd(&hist[255 - min(255, nq)], 1);
+  }
+  __syncwarp();
+  {   // exclusive prefix: lane l owns buckets [8l, 8l+8)
+    int loc[8], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { loc[j] = sum; sum += hist[8 * lane + j]; }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int base = incl - sum;
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) hist[8 * lane + j] = base + loc[j];
+  }
+  __syncwarp();
+  for (int i = lane; i < R; i += 32) {
+    const RoiMeta m = metas[i];
+    const int nq = ((m.ny + 3) >> 2) * ((m.nx + 3) >> 2);
+    order[atomicAdd(&hist[255 - min(255, nq)], 1)] = i;
   }
 }
 
@@ -846,11 +886,11 @@ static int launch_bwd(const void* g, int layout, int N, int C, int H, int W, int
   return DA_OK;
 }
 
-extern "C" int da_roi_align_backward(const void* grad_out, int grad_dtype, int out_layout,
-                                     const float* rois, int R, int pooled_h, int pooled_w,
-                                     float spatial_scale, int sampling_ratio, int aligned,
-                                     void* grad_in, int grad_in_dtype, int N, int C, int H, int W,
-                                     void* workspace, size_t workspace_bytes, da_stream_t stream) {
+static int roi_backward_impl(bool prepared, const void* grad_out, int grad_dtype, int out_layout,
+                             const float* rois, int R, int pooled_h, int pooled_w,
+                             float spatial_scale, int sampling_ratio, int aligned,
+                             void* grad_in, int grad_in_dtype, int N, int C, int H, int W,
+                             void* workspace, size_t workspace_bytes, da_stream_t stream) {
   int rc = check_common(N, C, H, W, R, pooled_h, pooled_w, rois, workspace, workspace_bytes);
   if (rc) return rc;
   DA_REQUIRE(grad_in != nullptr, DA_ERR_INVALID_ARG, "roi_align_backward: grad_in is null");
@@ -861,11 +901,30 @@ extern "C" int da_roi_align_backward(const void* grad_out, int grad_dtype, int o
     return DA_OK;
   }
   DA_REQUIRE(grad_out != nullptr, DA_ERR_INVALID_ARG, "roi_align_backward: grad_out is null");
-  rc = run_prep(rois, R, N, H, W, spatial_scale, sampling_ratio, aligned, workspace, nullptr, st);
-  if (rc) return rc;
+  if (!prepared) {
+    rc = run_prep(rois, R, N, H, W, spatial_scale, sampling_ratio, aligned, workspace, nullptr, st);
+    if (rc) return rc;
+  }
   if (grad_dtype == DA_F32) return launch_bwd<float>(grad_out, out_layout, N, C, H, W, R, workspace, grad_in, grad_in_dtype, st);
   if (grad_dtype == DA_BF16) return launch_bwd<__nv_bfloat16>(grad_out, out_layout, N, C, H, W, R, workspace, grad_in, grad_in_dtype, st);
   DA_REQUIRE(false, DA_ERR_INVALID_ARG, "roi_align_backward: bad dtype %d", grad_dtype);
+}
+
+extern "C" int da_roi_align_backward(const void* grad_out, int grad_dtype, int out_layout,
+                                     const float* rois, int R, int pooled_h, int pooled_w,
+                                     float spatial_scale, int sampling_ratio, int aligned,
+                                     void* grad_in, int grad_in_dtype, int N, int C, int H, int W,
+                                     void* workspace, size_t workspace_bytes, da_stream_t stream) {
+  return roi_backward_impl(false, grad_out, grad_dtype, out_layout, rois, R, pooled_h, pooled_w, spatial_scale, sampling_ratio, aligned,
+                           grad_in, grad_in_dtype, N, C, H, W, workspace, workspace_bytes, stream);
+}
+extern "C" int da_roi_align_backward_prepared(const void* grad_out, int grad_dtype, int out_layout,
+                                              const float* rois, int R, int pooled_h, int pooled_w,
+                                              float spatial_scale, int sampling_ratio, int aligned,
+                                              void* grad_in, int grad_in_dtype, int N, int C, int H, int W,
+                                              void* workspace, size_t workspace_bytes, da_stream_t stream) {
+  return roi_backward_impl(true, grad_out, grad_dtype, out_layout, rois, R, pooled_h, pooled_w, spatial_scale, sampling_ratio, aligned,
+                           grad_in, grad_in_dtype, N, C, H, W, workspace, workspace_bytes, stream);
 }
 
 extern "C" int da_map_roi_levels(const float* rois, int R, int num_levels, float finest_scale,

@@ -71,35 +71,10 @@ __device__ __forceinline__ uint64_t desc_kmajor_nosw(uint32_t saddr, uint32_t lb
 }
 
 // Work queue.  A persistent CTA processes whole RoIs, whose cost (footprint quads) spans 1..64+; a static stride
-// over the RoI index left the slowest CTA with 2x the mean work.  roi_order_kernel counting-sorts the RoIs by
+// over the RoI index left the slowest CTA with 2x the mean work.  The last block of roi_prep_kernel counting-sorts the RoIs by
 // decreasing footprint; the TMA producer of every CTA pops the next index with one atomicAdd (list scheduling in
 // LPT order) and broadcasts it to the other roles through a small shared-memory ring.  The order inside a bucket
 // depends on atomics, the results do not: every RoI's output is independent of where and when it is computed.
-__global__ void __launch_bounds__(1024)
-roi_order_kernel(const RoiMeta* __restrict__ metas, int R, int* __restrict__ order) {
-  __shared__ int hist[256];
-  __shared__ int start[256];
-  const int t = threadIdx.x;
-  if (t < 256) hist[t] = 0;
-  __syncthreads();
-  for (int r = t; r < R; r += blockDim.x) {
-    const RoiMeta m = metas[r];
-    const int nq = ((m.ny + 3) >> 2) * ((m.nx + 3) >> 2);
-    atomicAdd(&hist[255 - min(255, nq)], 1);
-  }
-  __syncthreads();
-  if (t == 0) {
-    int acc = 0;
-    for (int k = 0; k < 256; ++k) { start[k] = acc; acc += hist[k]; }
-  }
-  __syncthreads();
-  for (int r = t; r < R; r += blockDim.x) {
-    const RoiMeta m = metas[r];
-    const int nq = ((m.ny + 3) >> 2) * ((m.nx + 3) >> 2);
-    order[atomicAdd(&start[255 - min(255, nq)], 1)] = r;
-  }
-}
-
 // consumer side of the in-CTA queue: returns the next RoI index or -1 (drained); `arrive` = this thread releases the slot
 // kWarp: called by all 32 lanes (lane 0 releases after the whole warp has read); else by one elected thread
 template <bool kWarp>
@@ -357,9 +332,7 @@ static int launch_tc(const CUtensorMap& fmap, int C, int H, int W, int R, const 
   DA_REQUIRE(smem <= 227 * 1024, DA_ERR_UNSUPPORTED, "roi_align tc: H+W too large for shared memory");
   auto k = roi_align_fwd_tc_kernel<TOut>;
   DA_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  roi_order_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<const RoiMeta*>((const unsigned char*)ws + ws_meta_off()), R,
-                                       reinterpret_cast<int*>((unsigned char*)const_cast<void*>(ws) + ws_order_off(R, H, W)));
-  DA_LAUNCH_CHECK();
+  // the footprint-sorted RoI order was left in the workspace by the last block of roi_prep_kernel
   const int grid = R < num_sms() ? R : num_sms();
   k<<<grid, TC_THREADS, smem, st>>>(fmap, C, H, W, R, (const unsigned char*)ws, (TOut*)out, g_opt.roi_fwd_dbg);
   DA_LAUNCH_CHECK();

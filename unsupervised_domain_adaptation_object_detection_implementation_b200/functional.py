@@ -174,6 +174,13 @@ def gradient_scalar(x, weight):
 # --------------------------------------------------------------------------------------
 # RoIAlign
 # --------------------------------------------------------------------------------------
+_ROI_PREP = {}      # device index -> what the shared "roi" workspace currently holds the preparation of
+
+
+def _roi_prep_token(ws, rois_c, R, N, H, W, scale, sr, aligned):
+    return (ws.data_ptr(), rois_c.data_ptr(), rois_c._version, R, N, H, W, float(scale), int(sr), int(aligned), _stream().value)
+
+
 class RoIAlignFunction(Function):
     """mmcv.ops.roi_align.RoIAlignFunction replacement (avg pooling, 7x7)."""
 
@@ -199,6 +206,7 @@ class RoIAlignFunction(Function):
                                        float(spatial_scale), int(sampling_ratio), int(bool(aligned)),
                                        _ptr(out), _code(out_dtype), layout, _ptr(grid), _ptr(ws), ws.numel(),
                                        _stream()), "roi_align_forward")
+        _ROI_PREP[feat.device.index] = _roi_prep_token(ws, rois_c, R, N, H, W, spatial_scale, sampling_ratio, bool(aligned))
         if validate and R > 0:
             flag = ws[:4].view(torch.int32)[0].item()
             if flag != 0:
@@ -221,8 +229,12 @@ class RoIAlignFunction(Function):
             and not _OPTIONS.get("roi_no_tc")
         gin = torch.empty((N, H, W, C), dtype=torch.bfloat16 if direct else torch.float32, device=gout.device)
         ws = workspace(lib.da_roi_align_workspace_bytes(R, H, W), gout.device, "roi")
-        check(lib.da_roi_align_backward(_ptr(gout), _code(gout.dtype), layout, _ptr(rois_c), R, ph, pw, scale, sr,
-                                        aligned, _ptr(gin), _code(gin.dtype), N, C, H, W, _ptr(ws), ws.numel(), _stream()),
+        # the forward's preparation (tap tables, footprints) is still in the workspace unless another roi_align call used it since
+        token = _roi_prep_token(ws, rois_c, R, N, H, W, scale, sr, aligned)
+        fn = lib.da_roi_align_backward_prepared if (R > 0 and _ROI_PREP.get(gout.device.index) == token) else lib.da_roi_align_backward
+        _ROI_PREP[gout.device.index] = token
+        check(fn(_ptr(gout), _code(gout.dtype), layout, _ptr(rois_c), R, ph, pw, scale, sr,
+                 aligned, _ptr(gin), _code(gin.dtype), N, C, H, W, _ptr(ws), ws.numel(), _stream()),
               "roi_align_backward")
         g = nhwc_to_nchw_view(gin)
         if fdtype != torch.float32:
