@@ -555,7 +555,7 @@ def kernel_rooflines(dev, act, step_ms, fused_step=True):
         # round-2 capture (tools/prof_r02.py under ncu --set full, summarised by tools/ncu_summary.py): launches in program order
         launches = json.load(open(os.path.join(ROOT, "profiles", "r02_hot_kernels_ncu.json")))["launches"]
         pick = {"roi_align_fwd": ("roi_align_fwd_tc_kernel", 0), "roi_align_bwd": ("roi_align_bwd_tc_kernel", 0),
-                "fc1_fwd": ("umma_nt_kernel<256, 2, 1, 0>", 0), "fc1_dgrad": ("umma_nt_kernel<256, 2, 1, 0>", 1),
+                "fc1_fwd": ("umma_nt_kernel<512, 2, 1, 0>", 0), "fc1_dgrad": ("umma_nt_kernel<256, 2, 1, 0>", 0),
                 "fc1_wgrad_sgd": ("umma_tn_kernel<256, 2, 1>", 0)}
         prof = {}
         for name, (prefix, inst) in pick.items():
