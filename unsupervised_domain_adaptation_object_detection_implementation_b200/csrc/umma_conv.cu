@@ -109,34 +109,54 @@ template <> struct Pack<__nv_bfloat16> {
 // [32 rows][32 cols] chunk through a private shared-memory tile (16-byte pieces, XOR-swizzled) so that
 // each store instruction writes whole contiguous row segments (64 B bf16 / 128 B fp32 per row) instead
 // of 32 lanes hitting 32 different cache lines with 16 B each.
+// Per-channel scale / shift of a 32-column chunk, one column per lane (column c_base + lane): ONE coalesced load per chunk,
+// issued early by the caller (32 broadcast loads per lane inside the epilogue stalled every chunk on the first L1 miss).
+struct LaneAffine { float scale, shift; };
+__device__ __forceinline__ LaneAffine nt_lane_affine(const NtParams& P, int c_base, int lane) {
+  LaneAffine a{1.f, 0.f};
+  const int c = c_base + lane;
+  if (c < P.Cout) {
+    if (P.scale) a.scale = __ldg(P.scale + c);
+    if (P.shift) a.shift = __ldg(P.shift + c);
+  }
+  return a;
+}
+
 __device__ __forceinline__ void nt_epilogue_chunk(const NtParams& P, const uint32_t* v, size_t row_off, bool valid,
                                                   int c_base, bool raw_partial, float* partial, uint8_t* wstage,
-                                                  int lane) {
+                                                  int lane, LaneAffine aff) {
   const int ncols = min(32, P.Cout - c_base);   // warp-uniform
   if (ncols <= 0) return;
   float f[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
   const bool out_f32 = raw_partial || P.y_dtype == DA_F32;
-  const bool plain = !P.scale && !P.shift && !P.relu && P.drop_p <= 0.f;   // warp-uniform
-  if (!raw_partial && plain) {
+  // Every optional step is ONE warp-uniform branch around its own unrolled loop.  (r01 had them as per-element `if`s inside one
+  // loop; the compiler if-converted the ~45-instruction dropout hash, so every conv with a bias / BN / ReLU epilogue issued
+  // 1500 predicated-off instructions per chunk: +12 us per tile, tools/probe_mk.py.)
+  if (!raw_partial) {
     const float os = P.out_scale;
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] *= os;
-  } else if (!raw_partial) {
-    const uint32_t thr = drop_threshold(P.drop_p);
-    const float keep_scale = P.drop_p > 0.f ? 1.f / (1.f - P.drop_p) : 1.f;
+    if (P.scale) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int c = c_base + j;
-      float x = f[j] * P.out_scale;
-      if (j < ncols) {
-        if (P.scale) x *= __ldg(P.scale + c);
-        if (P.shift) x += __ldg(P.shift + c);
-      }
-      if (P.relu) x = fmaxf(x, 0.f);
-      if (P.drop_p > 0.f) x = (drop_hash(effective_seed(P.seed, P.seed_ctr), (uint64_t)(row_off + c)) >= thr) ? x * keep_scale : 0.f;
-      f[j] = x;
+      for (int j = 0; j < 32; ++j) f[j] *= __shfl_sync(0xffffffffu, aff.scale, j);
+    }
+    if (P.shift) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] += __shfl_sync(0xffffffffu, aff.shift, j);
+    }
+    if (P.relu) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+    if (P.drop_p > 0.f) {
+      const uint32_t thr = drop_threshold(P.drop_p);
+      const float keep_scale = 1.f / (1.f - P.drop_p);
+      const unsigned long long seed = effective_seed(P.seed, P.seed_ctr);
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        f[j] = (drop_hash(seed, (uint64_t)(row_off + c_base + j)) >= thr) ? f[j] * keep_scale : 0.f;
     }
   }
   uint8_t* gbase = raw_partial ? reinterpret_cast<uint8_t*>(partial) : reinterpret_cast<uint8_t*>(P.y);
@@ -436,19 +456,23 @@ umma_nt_kernel(const __grid_constant__ NtParams P, int pixel_tiles, int n_tiles,
         uint32_t u[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) u[j] = __float_as_uint(a0[j]);
-        nt_epilogue_chunk(P, u, row_off, valid, c0 + ehalf * 32, raw, partial, epi_stage + (warp - 2) * 4096, lane);
+        nt_epilogue_chunk(P, u, row_off, valid, c0 + ehalf * 32, raw, partial, epi_stage + (warp - 2) * 4096, lane,
+                          nt_lane_affine(P, c0 + ehalf * 32, lane));
 #pragma unroll
         for (int j = 0; j < 32; ++j) u[j] = __float_as_uint(a1[j]);
-        nt_epilogue_chunk(P, u, row_off, valid, c0 + (ehalf + 2) * 32, raw, partial, epi_stage + (warp - 2) * 4096, lane);
+        nt_epilogue_chunk(P, u, row_off, valid, c0 + (ehalf + 2) * 32, raw, partial, epi_stage + (warp - 2) * 4096, lane,
+                          nt_lane_affine(P, c0 + (ehalf + 2) * 32, lane));
         continue;
       }
       const int buf = tcount % NBUF;
       const uint32_t use = (uint32_t)(tcount / NBUF);
       ++tcount;
+      LaneAffine aff = nt_lane_affine(P, c0 + ehalf * 32, lane);      // first chunk's scale / shift: in flight during the wait
       mbar_wait(tfull0 + 8 * buf, use & 1u);
       tc_fence_after();
 #pragma unroll 1
       for (int cc = ehalf; cc < kBN / 32; cc += NT_EPI_WARPS / 4) {
+        const LaneAffine aff_next = nt_lane_affine(P, c0 + (cc + NT_EPI_WARPS / 4) * 32, lane);   // next chunk's, under this chunk's work
         uint32_t v[32];
         if (has_k) {
           DA_TMEM_LD32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * kBN + cc * 32, v);
@@ -457,7 +481,8 @@ umma_nt_kernel(const __grid_constant__ NtParams P, int pixel_tiles, int n_tiles,
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0u;
         }
-        if (!(P.dbg & 2)) nt_epilogue_chunk(P, v, row_off, valid, c0 + cc * 32, raw, partial, epi_stage + (warp - 2) * 4096, lane);
+        if (!(P.dbg & 2)) nt_epilogue_chunk(P, v, row_off, valid, c0 + cc * 32, raw, partial, epi_stage + (warp - 2) * 4096, lane, aff);
+        aff = aff_next;
       }
       tc_fence_before();
       __syncwarp();
