@@ -521,6 +521,42 @@ __global__ void nt_splitk_finish_kernel(const float* __restrict__ partial, int s
   }
 }
 
+// four outputs per thread (numel % 4 == 0, Cout % 4 == 0, 16-byte aligned buffers): 16-byte loads of every split's partial
+__global__ void nt_splitk_finish_vec4_kernel(const float4* __restrict__ partial, int splits, long long n4, int Cout,
+                                             const float* __restrict__ scale, const float* __restrict__ shift, int relu,
+                                             float drop_p, unsigned long long seed0, const unsigned long long* seed_ctr,
+                                             float out_scale, void* y, int y_dtype) {
+  pdl_launch_dependents();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < splits; ++s) {
+      const float4 p = partial[(size_t)s * n4 + i];
+      acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+    }
+    float x[4] = {acc.x * out_scale, acc.y * out_scale, acc.z * out_scale, acc.w * out_scale};
+    const int c = (int)((i * 4) % Cout);
+    if (scale) { const float4 v = *reinterpret_cast<const float4*>(scale + c); x[0] *= v.x; x[1] *= v.y; x[2] *= v.z; x[3] *= v.w; }
+    if (shift) { const float4 v = *reinterpret_cast<const float4*>(shift + c); x[0] += v.x; x[1] += v.y; x[2] += v.z; x[3] += v.w; }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], 0.f);
+    }
+    if (drop_p > 0.f) {      // one uniform branch (see nt_epilogue_chunk)
+      const unsigned long long seed = effective_seed(seed0, seed_ctr);
+      const uint32_t thr = drop_threshold(drop_p);
+      const float keep_scale = 1.f / (1.f - drop_p);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) x[j] = (drop_hash(seed, (uint64_t)(i * 4 + j)) >= thr) ? x[j] * keep_scale : 0.f;
+    }
+    if (y_dtype == DA_BF16) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(x[0], x[1]), b = __floats2bfloat162_rn(x[2], x[3]);
+      reinterpret_cast<uint2*>(y)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+    } else {
+      reinterpret_cast<float4*>(y)[i] = make_float4(x[0], x[1], x[2], x[3]);
+    }
+  }
+}
+
 // Warp-cooperative store of a [32 rows][32 fp32] accumulator chunk: lane L holds row L.  The chunk is transposed
 // through a private 4 KB shared-memory tile (16-byte pieces, XOR-swizzled) so that every store instruction
 // writes four whole 128-byte row segments instead of 32 lanes hitting 32 different lines with 16 B each.
@@ -849,6 +885,17 @@ umma_tn_kernel(const __grid_constant__ TnParams P, int co_tiles, int ci_tiles, i
   }
 }
 
+__global__ void sum_splits_vec4_kernel(const float4* __restrict__ part, int splits, long long n4, float4* __restrict__ out) {
+  pdl_launch_dependents();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < splits; ++s) {
+      const float4 p = part[(size_t)s * n4 + i];
+      acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+    }
+    out[i] = acc;
+  }
+}
 __global__ void sum_splits_kernel(const float* __restrict__ part, int splits, long long n, float* __restrict__ out) {
   pdl_launch_dependents();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -1166,8 +1213,15 @@ static int launch_nt_t(NtParams& P, long long pixel_tiles, int k_iters, void* ws
   DA_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, P, (int)pixel_tiles, n_tiles, splits));
   DA_LAUNCH_CHECK();
   if (splits > 1) {
-    nt_splitk_finish_kernel<<<ew_blocks(P.y_numel), 256, 0, st>>>(P.partial, splits, P.y_numel, P.Cout, P.scale, P.shift,
-                                                                  P.relu, P.drop_p, P.seed, P.seed_ctr, P.out_scale, P.y, P.y_dtype);
+    const bool vec4 = P.y_numel % 4 == 0 && P.Cout % 4 == 0 && ((reinterpret_cast<uintptr_t>(P.y) | reinterpret_cast<uintptr_t>(P.partial) |
+                       reinterpret_cast<uintptr_t>(P.scale) | reinterpret_cast<uintptr_t>(P.shift)) & 15) == 0;
+    if (vec4)
+      nt_splitk_finish_vec4_kernel<<<ew_blocks(P.y_numel / 4), 256, 0, st>>>(reinterpret_cast<const float4*>(P.partial), splits, P.y_numel / 4,
+                                                                             P.Cout, P.scale, P.shift, P.relu, P.drop_p, P.seed, P.seed_ctr,
+                                                                             P.out_scale, P.y, P.y_dtype);
+    else
+      nt_splitk_finish_kernel<<<ew_blocks(P.y_numel), 256, 0, st>>>(P.partial, splits, P.y_numel, P.Cout, P.scale, P.shift,
+                                                                    P.relu, P.drop_p, P.seed, P.seed_ctr, P.out_scale, P.y, P.y_dtype);
     DA_LAUNCH_CHECK();
   }
   return DA_OK;
@@ -1513,7 +1567,10 @@ int umma_conv_backward_weight(const da_conv_desc* d, const void* x, const void* 
   }
   if (rc2) return rc2;
   if (splits > 1) {
-    sum_splits_kernel<<<ew_blocks(P.dw_numel), 256, 0, st>>>((const float*)ws, splits, P.dw_numel, dw);
+    if (P.dw_numel % 4 == 0 && ((reinterpret_cast<uintptr_t>(ws) | reinterpret_cast<uintptr_t>(dw)) & 15) == 0)
+      sum_splits_vec4_kernel<<<ew_blocks(P.dw_numel / 4), 256, 0, st>>>((const float4*)ws, splits, P.dw_numel / 4, (float4*)dw);
+    else
+      sum_splits_kernel<<<ew_blocks(P.dw_numel), 256, 0, st>>>((const float*)ws, splits, P.dw_numel, dw);
     DA_LAUNCH_CHECK();
   }
   return DA_OK;
