@@ -308,8 +308,9 @@ def measure_engine(args, engine, rank, local, world, sample_clocks):
         c5_h, bx_h = host[i % 2]
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(ev_free[slot])          # the step that last used this buffer has finished
-            dev_in[slot][0].copy_(c5_h, non_blocking=True)
-            dev_in[slot][1].copy_(bx_h, non_blocking=True)
+            if not os.environ.get("DA_E2E_NOCOPY"):      # attribution experiment only
+                dev_in[slot][0].copy_(c5_h, non_blocking=True)
+                dev_in[slot][1].copy_(bx_h, non_blocking=True)
             ev_ready[slot].record(copy_stream)
 
     loss_ring = [torch.zeros(1).pin_memory() for _ in range(2)]
