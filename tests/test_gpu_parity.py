@@ -769,6 +769,31 @@ def test_daf_org_hot_path_at_bench_shape_vs_oracle(engine):
             assert e <= wtol, (k, e)
 
 
+def test_roi_align_backward_reuses_forward_preparation_only_when_valid():
+    """da_roi_align_backward_prepared: the backward skips the preparation launch when the shared workspace still holds the
+    forward's tap tables for the SAME RoI set (functional._ROI_PREP token); any roi_align call in between (other RoIs, other
+    map) invalidates the token and the backward prepares again.  All three routes give bit-identical gradients, for the
+    tensor-core (bf16) and the CUDA-core (fp32) kernels."""
+    for dtype in (torch.bfloat16, torch.float32):
+        feat = seeded.feature_map("prep.f", (2, 128, 24, 40), 0).to(DEV).to(dtype).contiguous(memory_format=torch.channels_last)
+        rois = seeded.synthetic_rois(48, 2, 24 * 16, 40 * 16, 1).to(DEV)
+        other = seeded.synthetic_rois(16, 2, 24 * 16, 40 * 16, 2).to(DEV)
+        cot = seeded.seeded_tensor("prep.c", (96, 128, 7, 7), 0).to(DEV).to(dtype)
+        grads, routes = [], []
+        for interleave in (False, True, False):
+            x = feat.clone(memory_format=torch.preserve_format).requires_grad_(True)
+            out = F_.roi_align(x, rois, 7, 1 / 16)
+            if interleave:
+                F_.roi_align(feat, other, 7, 1 / 16)          # overwrites the workspace: the token must not match any more
+            tok = F_._ROI_PREP.get(x.device.index)
+            routes.append(tok is not None and tok[1] == out.grad_fn.saved_tensors[0].data_ptr())   # what the backward will find
+            (g,) = torch.autograd.grad(out, x, cot)
+            grads.append(g.clone())
+        assert routes == [True, False, True]
+        assert torch.equal(grads[0], grads[1]) and torch.equal(grads[0], grads[2])
+        assert float(grads[0].float().abs().max()) > 0
+
+
 def test_roi_align_tensor_core_backward_at_bench_size_vs_oracle():
     """bf16 tcgen05 RoIAlign backward at the benchmarked size (C=2048, 64x128, 1024 RoIs over 2 images): the whole
     [2,2048,64,128] gradient against the fp64 oracle backward on the same bf16-rounded cotangent.  Tolerance: the
