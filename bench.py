@@ -54,7 +54,7 @@ def parse_args():
     ap.add_argument("--no-f32-line", action="store_true", help="skip the nested line on the fp32-class engine (umma_bf16x6)")
     ap.add_argument("--pairs-per-gpu", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="daf", choices=["daf", "maf"],
+    ap.add_argument("--workload", default="daf", choices=["daf", "maf", "fpn"],
                     help="daf (default, the contract line): DAF-Org hot path; maf: auxiliary line for BASELINE config 3 - the three SRM "
                          "image-level heads of MAFasterRCNN on C3/C4/C5 of 1024x2048 pairs (tensor-bound), one pair per GPU")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
@@ -582,8 +582,8 @@ def kernel_rooflines(dev, act, step_ms, fused_step=True):
 # ----------------------------------------------------------------------------------------------
 # auxiliary workload: MAF image-level heads (BASELINE config 3 shapes, one pair per GPU)
 # ----------------------------------------------------------------------------------------------
-def run_maf(args):
-    """SRM heads (mmdet/models/backbones/resnet_da.py:83-118) on C3/C4/C5 + CE on sigmoid (L3) + backward into the
+def run_maf(args, kind="maf"):
+    """kind == "maf": SRM heads (mmdet/models/backbones/resnet_da.py:83-118) on C3/C4/C5 + CE on sigmoid (L3) + backward into the
     features (reversed gradient) + SGD.  FLOPs: 2*M*N*K per implicit GEMM with the enlarged extents of Q12
     (1x1 pad 1 -> (H+2)x(W+2); 3x3 pad 3 on that -> (H+6)x(W+6)), forward + data gradient + weight gradient."""
     import unsupervised_domain_adaptation_object_detection_implementation_b200 as uda
@@ -594,23 +594,45 @@ def run_maf(args):
     torch.cuda.set_device(dev)
     uda.set_engine(args.engine)
     act = F_.act_dtype()
-    shapes = [(512, 128, 256), (1024, 64, 128), (2048, 64, 128)]
+    # kind == "fpn" (BASELINE config 2b, an extension: no DA config of the reference has a neck): hotpath.FPNHotPath on P2..P5 of a
+    # 1024x2048 pair (256 channels, strides 4..32): one image-level head + L1 per level, multi-level RoIAlign of 2x512 RoIs with
+    # the device-side level partition, shared FCs, instance head (chain kernel), consistency, backward into every level, SGD.
+    fpn = kind == "fpn"
+    shapes = [(256, 256, 512), (256, 128, 256), (256, 64, 128), (256, 32, 64)] if fpn else [(512, 128, 256), (1024, 64, 128), (2048, 64, 128)]
     torch.manual_seed(0)
-    model = hotpath.MAFHotPath(tuple(c for c, _, _ in shapes)).to(dev).train()
+    if fpn:
+        model = hotpath.FPNHotPath(256, (4, 8, 16, 32), 1024).to(dev).train()
+        gb = torch.Generator().manual_seed(10 + rank)      # boxes as in make_host_inputs: log-uniform 16..512 px on 1024x2048
+        u = torch.rand(2, 512, 4, generator=gb)
+        bx1, by1 = u[..., 0] * (2048 - 33), u[..., 1] * (1024 - 33)
+        lo, hi = torch.log(torch.tensor(16.0)), torch.log(torch.tensor(512.0))
+        bw, bh = torch.exp(lo + u[..., 2] * (hi - lo)), torch.exp(lo + u[..., 3] * (hi - lo))
+        bxs = torch.stack([bx1, by1, torch.clamp(bx1 + bw, max=2048.0), torch.clamp(by1 + bh, max=1024.0)], -1)
+        props = [bxs[i].contiguous().to(dev) for i in range(2)]
+    else:
+        model = hotpath.MAFHotPath(tuple(c for c, _, _ in shapes)).to(dev).train()
     params = ddist.trainable_parameters(model, [])
     opt = optim.FusedSGD(params, lr=1e-3, momentum=0.9, weight_decay=5e-4)
     reducer = ddist.OverlappedGradAllReduce(params) if world > 1 else None
     g = torch.Generator(device=dev).manual_seed(1 + rank)
     feats = [[torch.relu(torch.randn(2, h, w, c, device=dev, generator=g)).to(act) for c, h, w in shapes] for _ in range(2)]
     flops = 0.0
-    for c, h, w in shapes:
-        flops += 2.0 * (2 * (h + 2) * (w + 2)) * c * (c // 4) + 2.0 * (2 * (h + 6) * (w + 6)) * (9 * c // 4) * (9 * c // 4)
+    if fpn:       # image heads (C -> 512 1x1 per level) + FC 12544 -> 1024 on 1024 RoIs; forward + data + weight gradient
+        for c, h, w in shapes:
+            flops += 2.0 * (2 * h * w) * c * 512
+        flops += 2.0 * 1024 * (256 * 49) * 1024
+    else:
+        for c, h, w in shapes:
+            flops += 2.0 * (2 * (h + 2) * (w + 2)) * c * (c // 4) + 2.0 * (2 * (h + 6) * (w + 6)) * (9 * c // 4) * (9 * c // 4)
     flops *= 3.0
 
     def step(slot):
         F_.bump_dropout_counter(dev)
         xs = [t.permute(0, 3, 1, 2).requires_grad_(True) for t in feats[slot]]
-        loss, _ = hotpath.parse_losses(model.forward_train(xs[0], xs[1], xs[2], [0, 1]))
+        if fpn:
+            loss, _ = hotpath.parse_losses(model.forward_train(xs, props, [0, 1]))
+        else:
+            loss, _ = hotpath.parse_losses(model.forward_train(xs[0], xs[1], xs[2], [0, 1]))
         loss.backward()
         if reducer is not None:
             reducer()
@@ -674,11 +696,16 @@ def run_maf(args):
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.engine == "umma_bf16" else "f32",
             "data": "synthetic",
-            "config": {"workload": "maf_r50dc5_srm_heads_c3c4c5_1024x2048", "pairs_per_gpu": 1, "features": [[2, c, h, w] for c, h, w in shapes],
-                       "engine": args.engine, "launch": note, "step": "SRM x3 + CE-on-sigmoid, backward into the features, SGD",
-                       "l2_policy": "activations exceed L2 (C5 head intermediate 173 MB); two input sets alternated", "auxiliary": True},
+            "config": {"workload": "daf_fpn_p2p5_heads_multilevel_roialign_1024x2048" if fpn else "maf_r50dc5_srm_heads_c3c4c5_1024x2048",
+                       "pairs_per_gpu": 1, "features": [[2, c, h, w] for c, h, w in shapes],
+                       "engine": args.engine, "launch": note,
+                       "step": ("image head + L1 on P2..P5, multi-level RoIAlign (2x512 RoIs, device-side level partition), shared FCs, "
+                                "instance head + L4 (chain kernel), L7, backward into every level, SGD") if fpn else
+                               "SRM x3 + CE-on-sigmoid, backward into the features, SGD",
+                       "l2_policy": "activations exceed L2; two input sets alternated", "auxiliary": True},
             "e2e": None, "gpu_launches": int(launches), "clocks": clocks,
-            "roofline": {"kernel": "whole step (implicit GEMMs of the three SRM heads)", "bound": "tensor", "achieved": round(tf, 1),
+            "roofline": {"kernel": "whole step (GEMM FLOPs only; the FPN step is dominated by memory-bound head tails and RoIAlign)" if fpn
+                         else "whole step (implicit GEMMs of the three SRM heads)", "bound": "tensor", "achieved": round(tf, 1),
                          "peak": pk["bf16_tflops_sustained"] or pk["bf16_tflops"], "unit": "TFLOP/s",
                          "frac": round(tf / (pk["bf16_tflops_sustained"] or pk["bf16_tflops"]), 4), "traffic": None,
                          "peak_source": pk["source"] + " (sustained: kernels timed inside a long step)", "flops_per_step": flops}}))
@@ -817,6 +844,8 @@ if __name__ == "__main__":
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "fpn":
+        run_maf(a, "fpn")
     elif a.workload == "maf":
         run_maf(a)
     else:

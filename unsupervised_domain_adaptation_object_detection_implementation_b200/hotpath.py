@@ -97,6 +97,16 @@ class SharedFCs(nn.Module):
         return x.view(k, -1), (fcs[-1].weight, fcs[-1].bias, b_in)
 
 
+def instance_branch(bbox_head, local_da, roi_feats, label_da):
+    """RoI features -> shared FCs -> instance head + its CE loss.  When the shared features have no other consumer and the
+    shapes allow it, the LAST shared FC runs inside the instance head's chain kernel (one kernel per direction)."""
+    if bbox_head is not None and bbox_head.can_feed_chain(roi_feats):
+        xin, (w0, b0, b_in) = bbox_head.split(roi_feats)
+        return local_da.forward_loss(None, label_da, pre=(xin, w0, b0, b_in))
+    bbox_feats = bbox_head(roi_feats) if bbox_head is not None else roi_feats.flatten(1)
+    return local_da.forward_loss(bbox_feats, label_da)
+
+
 class DAFOrgHotPath(nn.Module):
     def __init__(self, in_channels=2048, featmap_stride=16, fc_out_channels=1024,
                  lambdas=(0.1, 0.1, 0.1), with_shared_fcs=True):
@@ -122,14 +132,7 @@ class DAFOrgHotPath(nn.Module):
         roi_feats = self.bbox_roi_extractor([c5], rois)
         label_da = roi_domain_labels(tuple(len(p) for p in proposal_list), c5.device) if len(proposal_list) == 2 else \
             rois[:, 0].to(torch.int32).clamp(max=1)
-        ins_loss = None
-        if self.bbox_head is not None and self.bbox_head.can_feed_chain(roi_feats):
-            # the last shared FC, the instance head and its loss in one kernel per direction
-            xin, (w0, b0, b_in) = self.bbox_head.split(roi_feats)
-            ins_loss, ins_preds = self.local_da.forward_loss(None, label_da, pre=(xin, w0, b0, b_in))
-        if ins_loss is None:
-            bbox_feats = self.bbox_head(roi_feats) if self.bbox_head is not None else roi_feats.flatten(1)
-            ins_loss, ins_preds = self.local_da.forward_loss(bbox_feats, label_da)
+        ins_loss, ins_preds = instance_branch(self.bbox_head, self.local_da, roi_feats, label_da)
         consist = da_losses.consistency_loss(imgs_feat, ins_preds, label_da)
         # lambda weights (DAFaster_rcnn_Orig.py:143-157) and the total of the dict in ONE launch; parse_losses picks the total up
         scaled, total = F_.weighted_losses([ins_loss, global_loss, consist], [self.local_lamda, self.global_lamda, self.consist_lamda])
@@ -260,10 +263,9 @@ class FPNHotPath(nn.Module):
         level_losses, level_feats = zip(*[h.forward_loss(f, gt_domain) for h, f in zip(self.da_heads, feats)])
         rois = bbox2roi(proposal_list)
         roi_feats = self.bbox_roi_extractor(list(feats), rois)
-        bbox_feats = self.bbox_head(roi_feats)
         label_da = roi_domain_labels(tuple(len(p) for p in proposal_list), feats[0].device) if len(proposal_list) == 2 else \
             rois[:, 0].to(torch.int32).clamp(max=1)
-        ins_loss, ins_preds = self.local_da.forward_loss(bbox_feats, label_da)
+        ins_loss, ins_preds = instance_branch(self.bbox_head, self.local_da, roi_feats, label_da)
         consist = da_losses.consistency_loss(level_feats[self.consist_level], ins_preds, label_da)
         n = len(level_losses)
         scaled, total = F_.weighted_losses(list(level_losses) + [ins_loss, consist],
