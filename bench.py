@@ -650,6 +650,8 @@ def run_maf(args, kind="maf"):
     torch.cuda.synchronize()
     graphs, note = [], "cuda_graph"
     try:
+        if args.no_graph:
+            raise RuntimeError("--no-graph")
         pool = None
         for slot in range(2):
             gph = torch.cuda.CUDAGraph()

@@ -50,12 +50,18 @@ __device__ __forceinline__ void axis_samples(float start, float bin_size, int g,
   }
 }
 
-// grid = R blocks of 32 threads.
-__global__ void roi_prep_kernel(const float* __restrict__ rois, int R, int N, int H, int W,
-                                float spatial_scale, int sampling_ratio, int aligned,
-                                unsigned char* __restrict__ ws, int32_t* __restrict__ grid_out) {
-  const int r = blockIdx.x;
-  const int lane = threadIdx.x;
+// grid = ceil(R / PREP_WARPS) blocks of PREP_WARPS warps: one warp per RoI.  want_order: the last block to finish also sorts the
+// RoIs by decreasing footprint (work queue of the tensor-core forward).
+constexpr int PREP_WARPS = 8;
+__global__ void __launch_bounds__(32 * PREP_WARPS)
+roi_prep_kernel(const float* __restrict__ rois, int R, int N, int H, int W,
+                float spatial_scale, int sampling_ratio, int aligned,
+                unsigned char* __restrict__ ws, int32_t* __restrict__ grid_out, int want_order) {
+  const int r = blockIdx.x * PREP_WARPS + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  __shared__ int s_last;
+  __shared__ int hist[256];
+  if (r < R) {
   int* err = reinterpret_cast<int*>(ws);
   RoiMeta* metas = reinterpret_cast<RoiMeta*>(ws + ws_meta_off());
   float* tab = reinterpret_cast<float*>(ws + ws_table_off(R)) + (size_t)r * (H + W) * WROW;
@@ -105,7 +111,6 @@ __global__ void roi_prep_kernel(const float* __restrict__ rois, int R, int N, in
     if (lane < P) axis_samples(x1, bw, gw_s, lane, W, 1, x_lo, wx, d0, d1);
     else if (lane >= 8 && lane < 8 + P) axis_samples(y1, bh, gh_s, lane - 8, H, 1, y_lo, wy, d0, d1);
   }
-  int last = 0;
   if (lane == 0) {
     RoiMeta m;
     m.b = b; m.gh = gh; m.gw = gw;
@@ -113,43 +118,48 @@ __global__ void roi_prep_kernel(const float* __restrict__ rois, int R, int N, in
     m.count = max(gh * gw, 1);
     metas[r] = m;
     if (grid_out) { grid_out[2 * r] = gh; grid_out[2 * r + 1] = gw; }
-    __threadfence();
-    last = atomicAdd(&err[2], 1) == R - 1;      // hdr[2]: blocks done (zeroed by the host with the rest of the header)
   }
-  last = __shfl_sync(0xffffffffu, last, 0);
-  if (!last) return;
-  // The LAST block orders the RoIs by decreasing footprint (work queue of the tensor-core forward, roi_align_tc.cu): counting
-  // sort over 256 buckets of quad counts by one warp -- a separate single-block kernel cost a launch and 8 us for this.
-  // The order inside a bucket depends on atomics, the results do not (every RoI's output is independent of when it is computed).
+  }   // r < R
+  if (!want_order) return;
+  // The LAST block orders the RoIs by decreasing footprint: counting sort over 256 buckets of quad counts (a separate
+  // single-block kernel cost a launch and 8 us for this).  The order inside a bucket depends on atomics, the results do not
+  // (every RoI's output is independent of when it is computed).
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(reinterpret_cast<int*>(ws) + 2, 1) == (int)gridDim.x - 1;   // hdr[2]: blocks done (zeroed with the header)
+  }
+  __syncthreads();
+  if (!s_last) return;
   __threadfence();
-  __shared__ int hist[256];
+  const RoiMeta* all = reinterpret_cast<const RoiMeta*>(ws + ws_meta_off());
   int* order = reinterpret_cast<int*>(ws + ws_order_off(R, H, W));
-  for (int k = lane; k < 256; k += 32) hist[k] = 0;
-  __syncwarp();
-  for (int i = lane; i < R; i += 32) {
-    const RoiMeta m = metas[i];
+  const int t = threadIdx.x, nt = blockDim.x;
+  for (int k = t; k < 256; k += nt) hist[k] = 0;
+  __syncthreads();
+  for (int i = t; i < R; i += nt) {
+    const RoiMeta m = all[i];
     const int nq = ((m.ny + 3) >> 2) * ((m.nx + 3) >> 2);
     atomicAdd(&hist[255 - min(255, nq)], 1);
   }
-  __syncwarp();
-  {   // exclusive prefix: lane l owns buckets [8l, 8l+8)
+  __syncthreads();
+  if (t < 32) {   // exclusive prefix: lane l owns buckets [8l, 8l+8)
     int loc[8], sum = 0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { loc[j] = sum; sum += hist[8 * lane + j]; }
+    for (int j = 0; j < 8; ++j) { loc[j] = sum; sum += hist[8 * t + j]; }
     int incl = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
+      if (t >= o) incl += v;
     }
     const int base = incl - sum;
-    __syncwarp();
 #pragma unroll
-    for (int j = 0; j < 8; ++j) hist[8 * lane + j] = base + loc[j];
+    for (int j = 0; j < 8; ++j) hist[8 * t + j] = base + loc[j];
   }
-  __syncwarp();
-  for (int i = lane; i < R; i += 32) {
-    const RoiMeta m = metas[i];
+  __syncthreads();
+  for (int i = t; i < R; i += nt) {
+    const RoiMeta m = all[i];
     const int nq = ((m.ny + 3) >> 2) * ((m.nx + 3) >> 2);
     order[atomicAdd(&hist[255 - min(255, nq)], 1)] = i;
   }
@@ -775,9 +785,10 @@ static int check_common(int N, int C, int H, int W, int R, int ph, int pw, const
 }
 
 static int run_prep(const float* rois, int R, int N, int H, int W, float scale, int sr, int aligned,
-                    void* ws, int32_t* grid_out, cudaStream_t st) {
+                    void* ws, int32_t* grid_out, cudaStream_t st, int want_order = 0) {
   DA_CUDA_OK(cudaMemsetAsync(ws, 0, 16, st));
-  roi_prep_kernel<<<R, 32, 0, st>>>(rois, R, N, H, W, scale, sr, aligned, (unsigned char*)ws, grid_out);
+  roi_prep_kernel<<<(R + PREP_WARPS - 1) / PREP_WARPS, 32 * PREP_WARPS, 0, st>>>(rois, R, N, H, W, scale, sr, aligned, (unsigned char*)ws,
+                                                                                grid_out, want_order);
   DA_LAUNCH_CHECK();
   return DA_OK;
 }
@@ -835,7 +846,9 @@ extern "C" int da_roi_align_forward(const void* feat, int feat_dtype, int N, int
   DA_REQUIRE(feat && out, DA_ERR_INVALID_ARG, "roi_align: null feature/output pointer");
   DA_REQUIRE(feat_dtype != DA_BF16 || (C % 2 == 0), DA_ERR_UNSUPPORTED, "roi_align: bf16 features need even C");
   cudaStream_t st = (cudaStream_t)stream;
-  rc = run_prep(rois, R, N, H, W, spatial_scale, sampling_ratio, aligned, workspace, grid_out, st);
+  // the footprint order is only read by the tensor-core forward (launch_fwd's first branch)
+  const int want_order = feat_dtype == DA_BF16 && out_layout == DA_ROI_OUT_RCHW && C % 64 == 0 && !g_opt.roi_no_tc;
+  rc = run_prep(rois, R, N, H, W, spatial_scale, sampling_ratio, aligned, workspace, grid_out, st, want_order);
   if (rc) return rc;
   if (feat_dtype == DA_F32 && out_dtype == DA_F32) return launch_fwd<float, float>(feat, N, C, H, W, R, workspace, out, out_layout, st);
   if (feat_dtype == DA_F32 && out_dtype == DA_BF16) return launch_fwd<float, __nv_bfloat16>(feat, N, C, H, W, R, workspace, out, out_layout, st);
