@@ -355,6 +355,9 @@ def test_dense_layer_engines(engine, tol, case):
                                     (300, 192, 72),        # ragged rows and columns, odd pixel-tile count
                                     (512, 2048, 512),      # CTA-pair MMA (cta_group::2), long K
                                     (256, 4096, 264),      # pair MMA with a ragged last column tile
+                                    (256, 16384, 1024),    # 512-wide pair tiles in the forward (>= 256 k-steps), split-K
+                                    (1920, 16384, 512),    # ... with an ODD pixel-tile count (phantom tile in the last pair)
+                                    (8192, 512, 256),      # 512-wide pair tiles in the weight gradient (>= 128 pixel steps)
                                     (130, 64, 8)])         # single 128x64 tile + 2 rows
 def test_fc_tile_variants_bf16(M, K, Nc):
     """Every tile / cluster variant of the tcgen05 GEMM (forward, data gradient, weight gradient) against fp64 on the
@@ -371,6 +374,31 @@ def test_fc_tile_variants_bf16(M, K, Nc):
     assert rel_err(y.float(), (X @ Wm.t()).float()) <= 1e-2
     assert rel_err(xd.grad.float().view(M, K), (Cm @ Wm).float()) <= 1e-2
     assert rel_err(wd.grad, (Cm.t() @ X).float()) <= 1e-3      # fp32 result
+
+
+@pytest.mark.parametrize("case", [(2, 64, 64, 512, 256, 3, 1, 1),     # weight gradient: 512-wide pair tiles through the 4-D (tap) loads
+                                  (1, 32, 48, 512, 2048, 3, 1, 1),    # data gradient: 512-wide pair tiles, MN-major weights, 288 k-steps
+                                  (1, 40, 48, 512, 2048, 3, 1, 1)])   # ... with an odd pixel-tile count (15)
+def test_conv_wide_pair_tiles_bf16(case):
+    """The 512-wide CTA-pair tiles (one TMEM accumulator, two N = 256 pair MMAs per k-substep) of the forward / data-gradient
+    kernel and of the weight-gradient kernel on 3x3 convolutions, against fp64 on the same bf16-rounded operands."""
+    N, H, W, Cin, Cout, k, stride, pad = case
+    uda.set_engine("umma_bf16")
+    x = seeded.seeded_tensor("wt.x", (N, Cin, H, W), 0).bfloat16().float()
+    w = seeded.seeded_tensor("wt.w", (Cout, Cin, k, k), 0, scale=(Cin * k * k) ** -0.5).bfloat16().float()
+    xr, wr = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    torch.set_num_threads(os.cpu_count() or 8)
+    yr = _conv_ref(xr, wr, stride, pad)
+    cot = seeded.seeded_tensor("wt.c", tuple(yr.shape), 0).bfloat16().float()
+    (yr * cot.double()).sum().backward()
+    xc = x.to(DEV).requires_grad_(True)
+    wc = w.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    y = F_.dense_layer(F_.to_nhwc(xc, torch.bfloat16), wc, None, None, stride=stride, pad=pad, relu=False, engine="umma_bf16")
+    y_nchw = y.permute(0, 3, 1, 2).float()
+    assert rel_err(y_nchw, yr) <= 1e-2
+    (y_nchw * cot.to(DEV)).sum().backward()
+    assert rel_err(xc.grad, xr.grad) <= 1e-2
+    assert rel_err(wc.grad, wr.grad) <= 2e-3
 
 
 @pytest.mark.parametrize("engine", ["simt_f32", "umma_bf16x6", "umma_bf16x3"])

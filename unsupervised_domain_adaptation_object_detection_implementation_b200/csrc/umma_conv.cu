@@ -671,9 +671,12 @@ template <int kBN, int kCluster, bool k2SM = false>
 __global__ void __launch_bounds__(NT_FWD_THREADS, 1)
 umma_tn_kernel(const __grid_constant__ TnParams P, int co_tiles, int ci_tiles, int splits) {
   static_assert(!k2SM || kCluster == 2, "the CTA-pair mode is a cluster of exactly two CTAs");
+  static_assert(kBN != 512 || k2SM, "512-wide tiles exist in the CTA-pair mode only");
+  constexpr int NBUF = TileCfg<kBN>::NBUF;                           // 512-wide: ONE accumulator fills the TMEM (no epilogue overlap)
   constexpr int W_B_FULL = kBN * WK * 2;
   constexpr int W_B_BYTES = k2SM ? W_B_FULL / 2 : W_B_FULL;          // bytes of X staged in THIS CTA per k-step
-  constexpr int STAGES = (TileCfg<kBN>::STAGES * (W_A_BYTES + W_B_FULL)) / (W_A_BYTES + W_B_BYTES);   // same ring bytes, deeper ring
+  constexpr int STAGES = (kBN == 512) ? TileCfg<kBN>::STAGES
+                                      : (TileCfg<kBN>::STAGES * (W_A_BYTES + W_B_FULL)) / (W_A_BYTES + W_B_BYTES);   // same ring bytes, deeper ring
   constexpr int BN = kBN;
   constexpr int B_BOXES = BN / 64, B_PER_CTA = B_BOXES / kCluster;
   static_assert(B_BOXES % kCluster == 0, "cluster size must divide the 64-channel boxes of the B tile");
@@ -703,7 +706,7 @@ umma_tn_kernel(const __grid_constant__ TnParams P, int co_tiles, int ci_tiles, i
     fence_barrier_init();
   }
   pdl_launch_dependents();   // the next kernel of the stream may run its prologue under this one
-  if (warp == 1) { if (k2SM) tmem_alloc_2sm(tslot, 2 * BN); else tmem_alloc(tslot, 2 * BN); }
+  if (warp == 1) { if (k2SM) tmem_alloc_2sm(tslot, TileCfg<kBN>::TMEM_COLS); else tmem_alloc(tslot, 2 * BN); }
   tc_fence_before();
   __syncthreads();
   if (kCluster > 1) cluster_sync_all();   // peer barriers are initialised before any multicast lands
@@ -748,8 +751,8 @@ umma_tn_kernel(const __grid_constant__ TnParams P, int co_tiles, int ci_tiles, i
               tma_load_2d_2sm(ad, &P.a_map[P.term_a[term]], fb, co0, m);
               tma_load_2d_2sm(ad + W_A_BYTES / 2, &P.a_map[P.term_a[term]], fb, co0 + 64, m);
 #pragma unroll
-              for (int j = 0; j < B_PER_CTA; ++j)
-                tma_load_2d_2sm(bd + j * (64 * WK * 2), &P.b_map[P.term_b[term]][0], fb, ci0 + (crank * B_PER_CTA + j) * 64, m);
+              for (int j = 0; j < B_PER_CTA; ++j)   // box j: 256-column MMA j/2, this CTA's 128 columns of it, 64-column half j%2
+                tma_load_2d_2sm(bd + j * (64 * WK * 2), &P.b_map[P.term_b[term]][0], fb, ci0 + (j >> 1) * 256 + crank * 128 + (j & 1) * 64, m);
             } else {
               const int per_img = P.tiles_h * P.tiles_w;
               const int n = (int)(patch / per_img), t = (int)(patch % per_img);
@@ -758,7 +761,7 @@ umma_tn_kernel(const __grid_constant__ TnParams P, int co_tiles, int ci_tiles, i
               tma_load_4d_2sm(ad + W_A_BYTES / 2, &P.a_map[P.term_a[term]], fb, co0 + 64, j0, i0, n);
 #pragma unroll
               for (int j = 0; j < B_PER_CTA; ++j)
-                tma_load_4d_2sm(bd + j * (64 * WK * 2), &P.b_map[P.term_b[term]][ti.map], fb, ci0 + (crank * B_PER_CTA + j) * 64,
+                tma_load_4d_2sm(bd + j * (64 * WK * 2), &P.b_map[P.term_b[term]][ti.map], fb, ci0 + (j >> 1) * 256 + crank * 128 + (j & 1) * 64,
                                 j0 + ti.dw, i0 + ti.dh, n);
             }
             continue;
@@ -794,13 +797,13 @@ umma_tn_kernel(const __grid_constant__ TnParams P, int co_tiles, int ci_tiles, i
     }
   } else if (warp == 1) {
     if (lane == 0 && (!k2SM || crank == 0)) {
-      constexpr uint32_t idesc = make_idesc(k2SM ? 2 * BM : BM, BN, 1, 1);
+      constexpr uint32_t idesc = make_idesc(k2SM ? 2 * BM : BM, kBN == 512 ? 256 : BN, 1, 1);
       int kq = 0, tcount = 0;
       for (long long tile = tile0; tile < total_tiles; tile += tile_step, ++tcount) {
         DA_TN_DECODE(tile)
         (void)co0; (void)ci0; (void)tap;
-        const int buf = tcount & 1;
-        mbar_wait(tempty0 + 8 * buf, (((uint32_t)(tcount >> 1)) & 1u) ^ 1u);   // epilogue has drained this accumulator
+        const int buf = tcount % NBUF;
+        mbar_wait(tempty0 + 8 * buf, (((uint32_t)(tcount / NBUF)) & 1u) ^ 1u);   // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * BN;
         for (int k = 0; k < n_iters; ++k, ++kq) {
@@ -813,7 +816,11 @@ umma_tn_kernel(const __grid_constant__ TnParams P, int co_tiles, int ci_tiles, i
             // 16 k-rows = 2 swizzle atoms of 1024 B
             const uint64_t adsc = desc_mnmajor_sw128(a_s + s * W_A_BYTES + kk * 2048, W_A_BYTES / 2);
             const uint64_t bdsc = desc_mnmajor_sw128(b_s + s * W_B_BYTES + kk * 2048, 64 * WK * 2);
-            if (k2SM) umma_bf16_2sm(d_tmem, adsc, bdsc, idesc, (k > 0 || kk > 0) ? 1u : 0u);
+            if (kBN == 512) {   // two N = 256 pair MMAs share the dZ operand; the second reads boxes 2, 3 of this CTA's X stage
+              umma_bf16_2sm(d_tmem, adsc, bdsc, idesc, (k > 0 || kk > 0) ? 1u : 0u);
+              const uint64_t bdsc2 = desc_mnmajor_sw128(b_s + s * W_B_BYTES + 2 * (64 * WK * 2) + kk * 2048, 64 * WK * 2);
+              umma_bf16_2sm(d_tmem + 256, adsc, bdsc2, idesc, (k > 0 || kk > 0) ? 1u : 0u);
+            } else if (k2SM) umma_bf16_2sm(d_tmem, adsc, bdsc, idesc, (k > 0 || kk > 0) ? 1u : 0u);
             else umma_bf16(d_tmem, adsc, bdsc, idesc, (k > 0 || kk > 0) ? 1u : 0u);
           }
           // the stage is reusable only when EVERY CTA of the cluster is done with it (multicast writes into all / the pair
@@ -837,10 +844,10 @@ umma_tn_kernel(const __grid_constant__ TnParams P, int co_tiles, int ci_tiles, i
     int tcount = 0;
     for (long long tile = tile0; tile < total_tiles; tile += tile_step, ++tcount) {
       DA_TN_DECODE(tile)
-      const int buf = tcount & 1;
+      const int buf = tcount % NBUF;
       const int co = co0 + q * 32 + lane;
       float* out = P.dw + (size_t)split * P.dw_numel;
-      mbar_wait(tfull0 + 8 * buf, ((uint32_t)(tcount >> 1)) & 1u);
+      mbar_wait(tfull0 + 8 * buf, ((uint32_t)(tcount / NBUF)) & 1u);
       tc_fence_after();
 #pragma unroll 1
       for (int cc = ehalf; cc < BN / 32; cc += NT_EPI_WARPS / 4) {
@@ -881,7 +888,7 @@ umma_tn_kernel(const __grid_constant__ TnParams P, int co_tiles, int ci_tiles, i
   if (kCluster > 1) cluster_sync_all();   // no CTA exits while a peer may still multicast into it
   if (warp == 1) {
     tc_fence_after();
-    if (k2SM) tmem_dealloc_2sm(tmem_base, 2 * BN); else tmem_dealloc(tmem_base, 2 * BN);
+    if (k2SM) tmem_dealloc_2sm(tmem_base, TileCfg<kBN>::TMEM_COLS); else tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
@@ -1537,6 +1544,11 @@ int umma_conv_backward_weight(const da_conv_desc* d, const void* x, const void* 
   if (g.Cin <= 64) bn = 64;
   else if (g.Cin > 128 && (co_t * ((g.Cin + 255) / 256) * P.num_taps >= num_sms() / 2 || !short_k)) bn = 256;
   else if (short_k && co_t * ((g.Cin + 127) / 128) * P.num_taps < num_sms() / 2 && !g_opt.umma_no_bn64) bn = 64;
+  // long pixel loops, Cout tiles that pair up, no fused optimizer (its epilogue needs the overlap): 512-wide pair tiles
+  // (one TMEM accumulator, two N = 256 pair MMAs per k-substep share the dZ operand: operand bytes per FLOP -25 %)
+  if (bn == 256 && !sgd && d->engine == DA_ENGINE_UMMA_BF16 && g.Cin % 512 == 0 && co_t >= 2 && co_t % 2 == 0 &&
+      patches * P.num_terms >= 128 && !g_opt.umma_no_2sm && !g_opt.umma_no_bn512)
+    bn = 512;
   const long long tiles = (long long)((g.Cout + BM - 1) / BM) * ((g.Cin + bn - 1) / bn) * P.num_taps;
   long long k_iters = patches * P.num_terms;
   int splits = pick_splits_persistent(tiles, (int)(k_iters > 1000000 ? 1000000 : k_iters));
@@ -1554,7 +1566,9 @@ int umma_conv_backward_weight(const da_conv_desc* d, const void* x, const void* 
   const int co_tiles = (g.Cout + BM - 1) / BM, ci_tiles = (g.Cin + bn - 1) / bn;
   // Cout tiles that share an X tile form a cluster (TMA multicast of the shared operand)
   int rc2;
-  if (bn == 256) {
+  if (bn == 512) {
+    rc2 = launch_tn_t<512, 2, true>(P, co_tiles, ci_tiles, splits, st);
+  } else if (bn == 256) {
     // clusters of 4 only fit 33 times on the 148 SMs (GPC sizes), pairs fit 74 times
     if (co_tiles >= 2 && co_tiles % 2 == 0 && !g_opt.umma_no_2sm) rc2 = launch_tn_t<256, 2, true>(P, co_tiles, ci_tiles, splits, st);   // CTA pair
     else if (co_tiles >= 2) rc2 = launch_tn_t<256, 2>(P, co_tiles, ci_tiles, splits, st);
