@@ -378,7 +378,9 @@ def test_fc_tile_variants_bf16(M, K, Nc):
 
 @pytest.mark.parametrize("case", [(2, 64, 64, 512, 256, 3, 1, 1),     # weight gradient: 512-wide pair tiles through the 4-D (tap) loads
                                   (1, 32, 48, 512, 2048, 3, 1, 1),    # data gradient: 512-wide pair tiles, MN-major weights, 288 k-steps
-                                  (1, 40, 48, 512, 2048, 3, 1, 1)])   # ... with an odd pixel-tile count (15)
+                                  (1, 40, 48, 512, 2048, 3, 1, 1),    # ... with an odd pixel-tile count (15)
+                                  (2, 64, 96, 512, 1024, 3, 2, 1),    # stride 2: forward + per-parity-class data gradients on wide tiles
+                                  (2, 64, 64, 2048, 512, 1, 1, 0)])   # image-head shape: 32 k-steps in the forward
 def test_conv_wide_pair_tiles_bf16(case):
     """The 512-wide CTA-pair tiles (one TMEM accumulator, two N = 256 pair MMAs per k-substep) of the forward / data-gradient
     kernel and of the weight-gradient kernel on 3x3 convolutions, against fp64 on the same bf16-rounded operands."""

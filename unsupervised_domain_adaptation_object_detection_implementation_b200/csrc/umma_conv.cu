@@ -44,7 +44,7 @@ constexpr int MAX_TAPS = 16;
 // under the 128 B/clk SMEM port; BN = 128 serves narrow outputs.  Two TMEM accumulators (2*BN
 // columns) let the epilogue of tile i overlap the MMAs of tile i+1 (persistent kernel).
 // BN = 512 (r02, CTA-pair mode only): ONE accumulator of 512 columns fills the TMEM, so the epilogue is not overlapped with the
-// next tile -- worth it for long-K problems (FC1 forward: every operand byte is delivered to the SMs 3x instead of 4x; the
+// next tile -- worth it from ~24 k-steps per tile on (measured; FC1 forward: every operand byte is delivered to the SMs 3x instead of 4x; the
 // 256-wide kernel moves 9.3 TB/s L2 -> SM at 64 % tensor-pipe activity, profiles/r02_hot_kernels_ncu.md).  The pair MMA is
 // still N = 256: two instructions per k-substep share the A operand.
 template <int kBN> struct TileCfg {
@@ -1326,7 +1326,7 @@ int umma_conv_forward(const da_conv_desc* d, const void* x, const void* w, const
   }
   // long-K problems whose tiles pair up: 512-wide tiles (one TMEM accumulator, two N = 256 pair MMAs per k-substep)
   if (bn == 256 && d->engine == DA_ENGINE_UMMA_BF16 && nt_pair_mma(bn, pixel_tiles) && g.Cout % 512 == 0 &&
-      (long long)P.num_taps * P.kchunks >= 256 && !g_opt.umma_no_bn512)
+      (long long)P.num_taps * P.kchunks >= 24 && !g_opt.umma_no_bn512)
     bn = 512;
   for (int t = 0; t < wsrc.n; ++t) {
     // a 2-CTA cluster (pixel_tiles >= 2, see launch_nt) loads the weight tile as two multicast halves
@@ -1364,13 +1364,23 @@ int umma_conv_backward_data(const da_conv_desc* d, const void* dz, const void* w
   base.relu = 0; base.drop_p = 0.f; base.out_scale = out_scale;
   base.y = dx; base.y_dtype = d->y_dtype; base.y_numel = (long long)g.N * g.H * g.W * g.Cin;
   int bn = d->engine == DA_ENGINE_UMMA_BF16X6 ? 128 : choose_bn(g.Cin, (long long)g.N * g.H * g.W, ((long long)taps * g.Cout + BK - 1) / BK);
-  // long-K stride-1 data gradients whose pixel tiles pair up: 512-wide tiles (see TileCfg)
-  if (bn == 256 && d->engine == DA_ENGINE_UMMA_BF16 && g.s == 1 && g.Cin % 512 == 0 && (long long)taps * base.kchunks >= 256 &&
+  // data gradients with >= 24 k-steps per launch whose pixel tiles pair up: 512-wide tiles (see TileCfg)
+  if (bn == 256 && d->engine == DA_ENGINE_UMMA_BF16 && g.Cin % 512 == 0 && (long long)taps * base.kchunks / (g.s * g.s) >= 24 &&
       !g_opt.umma_no_bn512) {
     long long ptiles;
-    if (is_flat(g)) ptiles = ((long long)g.N * g.H * g.W + BM - 1) / BM;
-    else { int bh, bw; pick_patch(g.H, g.W, BM, &bh, &bw); ptiles = (long long)g.N * ((g.H + bh - 1) / bh) * ((g.W + bw - 1) / bw); }
-    if (nt_pair_mma(bn, ptiles)) bn = 512;
+    // every launch of this call (one per input-parity class for stride 2) must pair up
+    bool ok = true;
+    if (is_flat(g)) ok = nt_pair_mma(bn, ((long long)g.N * g.H * g.W + BM - 1) / BM);
+    else
+      for (int a = 0; a < g.s && ok; ++a)
+        for (int b = 0; b < g.s && ok; ++b) {
+          const int th = (g.H - a + g.s - 1) / g.s, tw = (g.W - b + g.s - 1) / g.s;
+          if (th <= 0 || tw <= 0) continue;
+          int bh, bw;
+          pick_patch(th, tw, BM, &bh, &bw);
+          ok = nt_pair_mma(bn, (long long)g.N * ((th + bh - 1) / bh) * ((tw + bw - 1) / bw));
+        }
+    if (ok) bn = 512;
   }
   for (int t = 0; t < wsrc.n; ++t) {
     const uint64_t dims[2] = {(uint64_t)taps * g.Cin, (uint64_t)g.Cout};
@@ -1547,7 +1557,7 @@ int umma_conv_backward_weight(const da_conv_desc* d, const void* x, const void* 
   // long pixel loops, Cout tiles that pair up, no fused optimizer (its epilogue needs the overlap): 512-wide pair tiles
   // (one TMEM accumulator, two N = 256 pair MMAs per k-substep share the dZ operand: operand bytes per FLOP -25 %)
   if (bn == 256 && !sgd && d->engine == DA_ENGINE_UMMA_BF16 && g.Cin % 512 == 0 && co_t >= 2 && co_t % 2 == 0 &&
-      patches * P.num_terms >= 128 && !g_opt.umma_no_2sm && !g_opt.umma_no_bn512)
+      patches * P.num_terms >= 32 && !g_opt.umma_no_2sm && !g_opt.umma_no_bn512)
     bn = 512;
   const long long tiles = (long long)((g.Cout + BM - 1) / BM) * ((g.Cin + bn - 1) / bn) * P.num_taps;
   long long k_iters = patches * P.num_terms;
