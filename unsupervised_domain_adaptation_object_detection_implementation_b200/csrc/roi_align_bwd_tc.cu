@@ -40,13 +40,45 @@ constexpr int BT_PF = 8;                                       // L2 prefetch di
 constexpr int BT_NRAW = 3;                                     // raw ring depth (copy latency ~3 pair times)
 constexpr size_t BT_SMEM = 1024 + 2 * (size_t)BT_OPS_BYTES + BT_NRAW * (size_t)BT_RAW_BYTES + BT_LIST * 4 + 256;
 
+// Work items = (image, pixel tile) x channel chunk; their cost is the number of RoIs touching the tile (0 ... 54 pairs at the bench
+// size), and the hardware hands CTAs out in index order: with tiles in raster order the last CTAs to start were heavy ones and
+// the SMs were busy 151 us of a 184 us kernel (tools/trace_roi_bwd.py).  roi_tile_order_kernel sorts the (image, tile) items
+// by decreasing RoI count; CTA L takes item order[L / chunks], channel chunk L % chunks (longest processing time first).
+__global__ void __launch_bounds__(1024)
+roi_tile_order_kernel(const unsigned char* __restrict__ ws, int R, int N, int H, int W, int tiles_x, int tiles_y, int* __restrict__ order) {
+  __shared__ int cnt[1024];
+  const RoiMeta* metas = reinterpret_cast<const RoiMeta*>(ws + ws_meta_off());
+  const int tiles = tiles_x * tiles_y, n_items = N * tiles, t = threadIdx.x;
+  if (t < n_items) cnt[t] = 0;
+  __syncthreads();
+  for (int r = t; r < R; r += blockDim.x) {
+    const RoiMeta m = metas[r];
+    if (m.b < 0 || m.b >= N || m.ny <= 0 || m.nx <= 0) continue;
+    const int ty_a = m.y_lo / BT_TY, ty_b = min((m.y_lo + m.ny - 1) / BT_TY, tiles_y - 1);
+    const int tx_a = m.x_lo / BT_TX, tx_b = min((m.x_lo + m.nx - 1) / BT_TX, tiles_x - 1);
+    for (int ty = ty_a; ty <= ty_b; ++ty)
+      for (int tx = tx_a; tx <= tx_b; ++tx) atomicAdd(&cnt[m.b * tiles + ty * tiles_x + tx], 1);
+  }
+  __syncthreads();
+  if (t < n_items) {     // rank by counting (n_items <= 1024): stable, deterministic
+    const int mine = cnt[t];
+    int rank = 0;
+    for (int j = 0; j < n_items; ++j) rank += (cnt[j] > mine) || (cnt[j] == mine && j < t);
+    order[rank] = t;
+  }
+}
+
 template <typename TO, bool kTrace>
 __global__ void __launch_bounds__(BT_THREADS, 1)
 roi_align_bwd_tc_kernel(const __nv_bfloat16* __restrict__ grad_out, int C, int H, int W, int R,
-                        const unsigned char* __restrict__ ws, TO* __restrict__ grad_in, int tiles_x, int dbg, unsigned long long* trace) {
+                        const unsigned char* __restrict__ ws, TO* __restrict__ grad_in, int tiles_x, int dbg, unsigned long long* trace,
+                        const int* __restrict__ item_order, int tiles, int chunks) {
   if (dbg & 32) return;
   unsigned long long tr0 = 0, tr1 = 0, tr2 = 0, tr3 = 0;
-  unsigned long long* ptrace = (kTrace && trace && blockIdx.x == 13 && blockIdx.y == 1 && blockIdx.z == 1) ? trace + 8 * (size_t)gridDim.x * gridDim.y * gridDim.z : nullptr;
+  const int item_l = (int)blockIdx.x / chunks, chunk_l = (int)blockIdx.x % chunks;
+  const int item = item_order ? item_order[item_l] : item_l;
+  const int blk_b = item / tiles, blk_tile = item % tiles;
+  unsigned long long* ptrace = (kTrace && trace && blockIdx.x == 3 * chunks + 1) ? trace + 8 * (size_t)gridDim.x : nullptr;
   // per-pair stamps (tools/trace_roi_bwd.py) exist only in the kTrace instantiation: even predicated off they were ~4 % of the
   // builder warps' issue slots (ncu source page, profiles/r02_roi_align_ncu.md)
 #define PSTAMP(pair, k) do { if (kTrace && ptrace && (pair) < 64) ptrace[(pair) * 8 + (k)] = globaltimer_ns(); } while (0)
@@ -65,9 +97,9 @@ roi_align_bwd_tc_kernel(const __nv_bfloat16* __restrict__ grad_out, int C, int H
   __shared__ int s_rows[2];     // per operand buffer: first tile row | (end tile row << 8) of the RoI's footprint in this tile
 
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int b = blockIdx.z;
-  const int c0 = blockIdx.y * BT_CH;
-  const int ty0 = (blockIdx.x / tiles_x) * BT_TY, tx0 = (blockIdx.x % tiles_x) * BT_TX;
+  const int b = blk_b;
+  const int c0 = chunk_l * BT_CH;
+  const int ty0 = (blk_tile / tiles_x) * BT_TY, tx0 = (blk_tile % tiles_x) * BT_TX;
   const int ty1 = min(ty0 + BT_TY, H), tx1 = min(tx0 + BT_TX, W);
   const RoiMeta* metas = reinterpret_cast<const RoiMeta*>(ws + ws_meta_off());
   const float* tables = reinterpret_cast<const float*>(ws + ws_table_off(R));
@@ -362,7 +394,7 @@ roi_align_bwd_tc_kernel(const __nv_bfloat16* __restrict__ grad_out, int C, int H
   }
   __syncthreads();
   if (kTrace && trace && threadIdx.x == 64) {
-    unsigned long long* o = trace + 8 * ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
+    unsigned long long* o = trace + 8 * (size_t)blockIdx.x;
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     o[0] = tr0; o[1] = tr1; o[2] = tr2; o[3] = globaltimer_ns(); o[4] = (unsigned long long)seq; o[5] = smid; o[6] = tr3;
@@ -376,8 +408,17 @@ roi_align_bwd_tc_kernel(const __nv_bfloat16* __restrict__ grad_out, int C, int H
 template <typename TO>
 static int launch_bwd_tc(const void* grad_out, int N, int C, int H, int W, int R, const void* ws, void* grad_in, cudaStream_t st) {
   const int tiles_x = (W + BT_TX - 1) / BT_TX, tiles_y = (H + BT_TY - 1) / BT_TY;
-  dim3 grid(tiles_x * tiles_y, (C + BT_CH - 1) / BT_CH, N);
-  DA_REQUIRE(grid.y <= 65535 && grid.z <= 65535, DA_ERR_UNSUPPORTED, "roi_align_backward tc: grid too large");
+  const int tiles = tiles_x * tiles_y, chunks = (C + BT_CH - 1) / BT_CH;
+  DA_REQUIRE((long long)N * tiles * chunks <= 0x7fffffffll, DA_ERR_UNSUPPORTED, "roi_align_backward tc: grid too large");
+  dim3 grid((unsigned)(N * tiles * chunks));
+  // longest-processing-time-first order of the (image, tile) items; the list lives in the workspace's RoI-order region (only the
+  // forward reads that one, and every forward rewrites it)
+  int* item_order = nullptr;
+  if ((long long)N * tiles <= 1024 && (long long)N * tiles <= R && !(g_opt.roi_bwd_dbg & 512)) {
+    item_order = reinterpret_cast<int*>(const_cast<unsigned char*>((const unsigned char*)ws) + ws_order_off(R, H, W));
+    roi_tile_order_kernel<<<1, 1024, 0, st>>>((const unsigned char*)ws, R, N, H, W, tiles_x, tiles_y, item_order);
+    DA_LAUNCH_CHECK();
+  }
   const int dbg = g_opt.roi_bwd_dbg;   // timing experiments only (results are wrong when set)
   unsigned long long* trace = reinterpret_cast<unsigned long long*>(g_opt.roi_bwd_trace);   // tools/trace_roi_bwd.py
   static bool attr_set_dev[kMaxDevices] = {};     // function attributes are per device
@@ -389,10 +430,10 @@ static int launch_bwd_tc(const void* grad_out, int N, int C, int H, int W, int R
   }
   if (trace)
     roi_align_bwd_tc_kernel<TO, true><<<grid, BT_THREADS, BT_SMEM, st>>>((const __nv_bfloat16*)grad_out, C, H, W, R, (const unsigned char*)ws,
-                                                                           static_cast<TO*>(grad_in), tiles_x, dbg, trace);
+                                                                           static_cast<TO*>(grad_in), tiles_x, dbg, trace, item_order, tiles, chunks);
   else
     roi_align_bwd_tc_kernel<TO, false><<<grid, BT_THREADS, BT_SMEM, st>>>((const __nv_bfloat16*)grad_out, C, H, W, R, (const unsigned char*)ws,
-                                                                            static_cast<TO*>(grad_in), tiles_x, dbg, trace);
+                                                                            static_cast<TO*>(grad_in), tiles_x, dbg, trace, item_order, tiles, chunks);
   DA_LAUNCH_CHECK();
   return DA_OK;
 }
