@@ -96,3 +96,47 @@ def test_fused_sgd_option_matches_plain_fused_sgd_through_the_layer():
             assert torch.equal(F_.bf16_shadow(lin_a.weight).view(torch.int16), F_.bf16_shadow(lin_b.weight).view(torch.int16))
     finally:
         F_.MANAGED_WGRAD.clear()
+
+
+def test_fused_sgd_state_dict_has_the_torch_sgd_layout_and_moves_both_ways():
+    """FusedSGD.state_dict() / load_state_dict() use torch.optim.SGD's layout ({'state': {i: {'momentum_buffer'}}, 'param_groups'}),
+    the 'optimizer' section mmcv's save_checkpoint writes for the reference (mmdet/apis/train.py:127): after the same two
+    steps both optimizers hold the same momentum; a FusedSGD restored from either state_dict continues exactly like the
+    uninterrupted one; a parameter that never received a gradient has no entry (and none is invented on load)."""
+    torch.manual_seed(0)
+    shapes = [(64, 32), (48,), (16, 8, 3, 3), (5,)]
+    base = [torch.randn(*s, device=DEV) for s in shapes]
+    grads = [[torch.randn(*s, device=DEV) for s in shapes] for _ in range(4)]
+
+    def make(cls, **kw):
+        ps = [torch.nn.Parameter(b.clone()) for b in base]
+        return ps, cls(ps, lr=LR, momentum=MU, weight_decay=WD, **kw)
+
+    def run(ps, opt, steps):
+        for k in steps:
+            for i, p in enumerate(ps):
+                p.grad = None if i == 3 else grads[k][i].clone()      # parameter 3 never gets a gradient
+            opt.step()
+
+    ps_f, fused = make(optim.FusedSGD, shadow_bf16=False)
+    ps_t, ref = make(torch.optim.SGD)
+    run(ps_f, fused, (0, 1))
+    run(ps_t, ref, (0, 1))
+    sd_f, sd_t = fused.state_dict(), ref.state_dict()
+    assert set(sd_f) == set(sd_t) == {"state", "param_groups"}
+    assert sorted(sd_f["state"]) == sorted(sd_t["state"]) == [0, 1, 2]          # no entry for the parameter without gradients
+    for i in sd_t["state"]:
+        assert torch.allclose(sd_f["state"][i]["momentum_buffer"], sd_t["state"][i]["momentum_buffer"], rtol=1e-6, atol=1e-7)
+    g_f, g_t = sd_f["param_groups"][0], sd_t["param_groups"][0]
+    assert g_f["params"] == g_t["params"] and all(g_f[k] == g_t[k] for k in ("lr", "momentum", "weight_decay", "dampening", "nesterov"))
+    run(ps_f, fused, (2, 3))                                                     # the uninterrupted run
+    for source in (sd_f, sd_t):                                                  # ... and two resumed ones
+        ps_r, resumed = make(optim.FusedSGD, shadow_bf16=False)
+        with torch.no_grad():
+            for p, q in zip(ps_r, ps_t if source is sd_t else ps_t):             # weights after two steps (the torch run's)
+                p.copy_(q)
+        resumed.load_state_dict(source)
+        assert id(ps_r[3]) not in resumed.state
+        run(ps_r, resumed, (2, 3))
+        for p, q in zip(ps_r, ps_f):
+            assert torch.allclose(p, q, rtol=2e-6, atol=1e-6)

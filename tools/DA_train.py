@@ -115,6 +115,7 @@ def main():
     reducer = ddist.OverlappedGradAllReduce(params) if world > 1 else None
     schedule = optim.StepLrSchedule(optimizer.lr, cfg.get("lr_config"))      # step decay + linear warm-up (schedule_1x.py)
 
+    start_epoch = 0
     start_iter, meta = 0, dict(seed=args.seed, config=os.path.abspath(args.config), exp_name=os.path.basename(args.config))
     if args.resume_from or args.load_from:
         ck = checkpoint.load_checkpoint(model, args.resume_from or args.load_from, strict=False)
@@ -123,25 +124,21 @@ def main():
             print(f"load: missing {rep['missing_keys'][:5]} unexpected {rep['unexpected_keys'][:5]}", flush=True)
         if args.resume_from:
             start_iter = int(ck.get("meta", {}).get("iter", 0))
-            for p, buf in zip(params, ck.get("optimizer", {}).get("momentum", [])):
-                if buf.numel() == p.numel():          # a parameter that never had a gradient has no momentum buffer yet
-                    optimizer.state[id(p)] = buf.to(dev)
+            start_epoch = int(ck.get("meta", {}).get("epoch", 0))
+            osd = ck.get("optimizer", {})
+            if "momentum" in osd:                     # checkpoints of round 1: a bare list of buffers in parameter order
+                osd = {"state": {i: {"momentum_buffer": b} for i, b in enumerate(osd["momentum"]) if b.numel()}, "param_groups": []}
+            optimizer.load_state_dict(osd)            # torch.optim.SGD layout (FusedSGD.state_dict)
             optimizer.steps = start_iter
 
-    def save(it):
-        state = {"momentum": [optimizer.state[id(p)].cpu() if id(p) in optimizer.state else torch.zeros(0) for p in params]}
-
-        class _Opt:            # the momentum buffers in parameter order (FusedSGD keeps them keyed by parameter identity)
-            def state_dict(self_inner):
-                return state
-
+    def save(it, epoch):
         path = os.path.join(work_dir, f"iter_{it}.pth")
-        checkpoint.save_checkpoint(model, path, optimizer=_Opt(), meta=dict(meta, iter=it), rank=rank)
+        checkpoint.save_checkpoint(model, path, optimizer=optimizer, meta=dict(meta, iter=it, epoch=epoch), rank=rank)
         if rank == 0:
             print(f"checkpoint: {path}", flush=True)
 
     it, t0 = start_iter, time.time()
-    epoch = 0
+    epoch = start_epoch                                   # the sampler's seeded schedule resumes in the epoch it stopped in
     while it < args.iters:
         sampler.set_epoch(epoch)
         order = list(iter(sampler))
@@ -163,9 +160,9 @@ def main():
                 print(f"iter {it}/{args.iters} lr {optimizer.lr:.3e} loss {float(lv['loss']):.4f} DA {da} domains {batch['gt_da']} "
                       f"({(time.time() - t0) / max(1, it - start_iter):.2f} s/iter)", flush=True)
             if args.checkpoint_interval and it % args.checkpoint_interval == 0:
-                save(it)
+                save(it, epoch)
         epoch += 1
-    save(it)
+    save(it, epoch)
     if world > 1:
         torch.distributed.barrier()
         torch.cuda.synchronize()

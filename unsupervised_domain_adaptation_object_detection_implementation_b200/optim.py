@@ -54,6 +54,7 @@ class FusedSGD:
         is applied by the epilogue of their weight-gradient kernel during backward (da_conv_backward_weight_sgd): their
         gradient is never materialised and `step()` skips them.  One backward per step; one GPU (no gradient exchange)."""
         self.params = [p for p in params if p.requires_grad]
+        self._order = list(self.params)           # constructor order = the index space of state_dict() (torch.optim.SGD layout)
         self.fused = []
         for p in fuse_wgrad:
             self._register_fused(p)
@@ -82,6 +83,50 @@ class FusedSGD:
 
         F_.MANAGED_WGRAD[id(p)] = _Fused()
         self.fused.append((p, buf, shadow))
+        self._fused_state = getattr(self, "_fused_state", {})
+        self._fused_state[id(p)] = state
+        if all(q is not p for q in self._order):
+            self._order.append(p)
+
+    # ---- checkpointing: the layout of torch.optim.SGD.state_dict() (what mmcv's save_checkpoint stores for the reference,
+    # mmdet/apis/train.py:127 + mmcv/runner/checkpoint.py), so that optimizer state moves both ways
+    def state_dict(self):
+        state = {}
+        fused = {id(p): (buf, self._fused_state[id(p)]) for p, buf, _ in self.fused}
+        for i, p in enumerate(self._order):
+            if id(p) in fused:
+                buf, st = fused[id(p)]
+                if st["calls"] > 0:
+                    state[i] = {"momentum_buffer": buf.detach().clone()}
+            elif id(p) in self.state:
+                state[i] = {"momentum_buffer": self.state[id(p)].detach().clone()}
+        group = {"lr": self.lr, "momentum": self.momentum, "dampening": 0, "weight_decay": self.weight_decay, "nesterov": False,
+                 "maximize": False, "foreach": None, "differentiable": False, "params": list(range(len(self._order)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        groups = sd.get("param_groups", [])
+        if groups:
+            g = groups[0]
+            self.lr, self.momentum = float(g.get("lr", self.lr)), float(g.get("momentum", self.momentum))
+            self.weight_decay = float(g.get("weight_decay", self.weight_decay))
+        fused = {id(p): (buf, self._fused_state[id(p)]) for p, buf, _ in self.fused}
+        for i, st in sd.get("state", {}).items():
+            i = int(i)
+            buf = st.get("momentum_buffer") if isinstance(st, dict) else None
+            if buf is None or i >= len(self._order):
+                continue                                  # a parameter that never had a gradient has no momentum yet
+            p = self._order[i]
+            if buf.numel() != p.numel():
+                raise RuntimeError(f"FusedSGD.load_state_dict: momentum of parameter {i} has {buf.numel()} elements, expected {p.numel()}")
+            if id(p) in fused:
+                fused[id(p)][0].copy_(buf.to(p.device).view_as(p))
+                fused[id(p)][1]["calls"] = max(1, fused[id(p)][1]["calls"])
+            else:
+                tgt = self.state.get(id(p))
+                if tgt is None:
+                    tgt = self.state[id(p)] = torch.empty_like(p)
+                tgt.copy_(buf.to(p.device).reshape(p.shape))
 
     def zero_grad(self, set_to_none=True):
         for p in self.params:
