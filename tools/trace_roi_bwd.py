@@ -5,16 +5,17 @@ sys.path.insert(0, ".")
 from unsupervised_domain_adaptation_object_detection_implementation_b200 import functional as F_
 from oracle import seeded
 dev = "cuda"
-N, C, H, W, R = 2, 2048, 64, 128, 1024
+N, C, H, W, R = 2, int(os.environ.get('TRACE_C', 2048)), 64, 128, 1024
 g = torch.Generator(device=dev).manual_seed(0)
 feat = torch.relu(torch.randn(N, H, W, C, device=dev, generator=g)).to(torch.bfloat16).permute(0, 3, 1, 2).requires_grad_(True)
 rois = seeded.synthetic_rois(R // N, N, H * 16, W * 16, 0).to(dev)
 cot = torch.randn(R, C, 7, 7, device=dev, generator=g).to(torch.bfloat16)
 out = F_.roi_align(feat, rois, 7, 1 / 16)
 for _ in range(3): torch.autograd.grad(out, feat, cot, retain_graph=True)
-ncta = 32 * 8 * N
+ncta = 32 * (C // 256) * N
 buf = torch.zeros(ncta + 64, 8, dtype=torch.int64, device=dev)
 F_.set_option("roi_bwd_trace", buf.data_ptr())
+if len(sys.argv) > 1: F_.set_option("roi_bwd_dbg", int(sys.argv[1]))
 torch.autograd.grad(out, feat, cot, retain_graph=True)
 torch.cuda.synchronize()
 pt = buf[ncta:].cpu().double()
@@ -27,12 +28,12 @@ pp = (loop - comp) / pairs.clamp(min=1)
 print(f"per-pair (pair phase / pairs): mean {pp[pairs>8].mean():.0f} ns, p10 {pp[pairs>8].quantile(0.1):.0f}, p90 {pp[pairs>8].quantile(0.9):.0f}")
 busy = torch.zeros(148)
 for i in range(ncta): busy[int(smid[i]) % 148] += (end[i] - start[i])
-print(f"SM busy: mean {busy.mean()/1e3:.1f} us, min {busy.min()/1e3:.1f}, max {busy.max()/1e3:.1f}; first CTA start spread {start.sort().values[147]/1e3:.1f} us")
+print(f"SM busy: mean {busy.mean()/1e3:.1f} us, min {busy.min()/1e3:.1f}, max {busy.max()/1e3:.1f}; first CTA start spread {start.sort().values[min(147, ncta - 1)]/1e3:.1f} us")
 last_start = start.max(); print(f"last CTA starts at {last_start/1e3:.1f} us; its duration {(end-start)[start.argmax()]/1e3:.1f}")
 
 print(f"epilogue: tfull wait mean {(t[:,6]-t[:,2])[pairs>0].mean()/1e3:.2f} us; TMEM->global mean {(t[:,3]-t[:,6])[pairs>0].mean()/1e3:.2f} us")
 base = pt[0, 0]
-print("pair | prod:slot free | bld:raw here  ops free  built  synced | mma:ops ready  committed   (ns from first)")
+print("pair | prod:slot free | bld:raw here  ops free  built  synced | mma:ops ready  committed   (SM cycles from first)")
 for i in range(24):
     r = pt[i] - base
     print(f"{i:3d} | {r[0]:8.0f} | {r[3]:8.0f} {r[4]:8.0f} {r[5]:8.0f} {r[6]:8.0f} | {r[1]:8.0f} {r[2]:8.0f}")

@@ -81,7 +81,7 @@ roi_align_bwd_tc_kernel(const __nv_bfloat16* __restrict__ grad_out, int C, int H
   unsigned long long* ptrace = (kTrace && trace && blockIdx.x == 3 * chunks + 1) ? trace + 8 * (size_t)gridDim.x : nullptr;
   // per-pair stamps (tools/trace_roi_bwd.py) exist only in the kTrace instantiation: even predicated off they were ~4 % of the
   // builder warps' issue slots (ncu source page, profiles/r02_roi_align_ncu.md)
-#define PSTAMP(pair, k) do { if (kTrace && ptrace && (pair) < 64) ptrace[(pair) * 8 + (k)] = globaltimer_ns(); } while (0)
+#define PSTAMP(pair, k) do { if (kTrace && ptrace && (pair) < 64) ptrace[(pair) * 8 + (k)] = (unsigned long long)clock64(); } while (0)   /* SM cycles: globaltimer ticks every 256 ns here */
   if (kTrace && trace && threadIdx.x == 64) tr0 = globaltimer_ns();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
