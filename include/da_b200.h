@@ -338,6 +338,21 @@ int da_softmax_dim0_forward(const float* s, int T, int ldk, float* p, da_stream_
 int da_softmax_dim0_backward(const float* p, const float* dp, int T, int ldk, float* ds,
                              da_stream_t stream);
 
+/* Blocked form of the same normalisation (NonLocalAlignmentHead at 1024x2048, T = 32768 tokens,
+ * resnet_da_deep.py:122-164,402-445): the softmax runs over the QUERY axis, so every key column is independent and the
+ * T x T matrix is processed one KEY BLOCK at a time.  s [Tq,Tk] fp32 row-major (row stride ld) = theta . phi_block^T.
+ *   forward : stats[0:Tk] = column max, stats[Tk:2Tk] = 1 / column sum of exp(s - max) (computed unless have_stats != 0, in
+ *             which case they are read: the backward re-creates p from a recomputed s without a second statistics pass);
+ *             p[q,k] = exp(s[q,k] - max_k) / sum_k  in p_dtype (DA_F32 | DA_BF16 = the next GEMM's operand dtype), same ld.
+ *   backward: ds[q,k] = p[q,k] * (dp[q,k] - sum_q' p[q',k] dp[q',k]),  dp fp32, ds in ds_dtype.
+ * Two passes over the block each (per-row-chunk partials merged in a fixed order: deterministic, no atomics).
+ * Workspace: da_colsoftmax_workspace_bytes(Tq,Tk), caller-owned. */
+size_t da_colsoftmax_workspace_bytes(int Tq, int Tk);
+int da_colsoftmax_forward(const float* s, int Tq, int Tk, int ld, void* p, int p_dtype, float* stats, int have_stats,
+                          void* workspace, size_t workspace_bytes, da_stream_t stream);
+int da_colsoftmax_backward(const void* p, int p_dtype, const float* dp, int Tq, int Tk, int ld, void* ds, int ds_dtype,
+                           void* workspace, size_t workspace_bytes, da_stream_t stream);
+
 /* W1: the lambda-weighted DA loss entries AND their total in one launch (detectors/DAFaster_rcnn_Orig.py:143-157 weights,
  * detectors/base.py:176-219 sum): scaled[i] = w[i] * *losses[i], total = sum_i scaled[i] (fixed order).  `losses_host` is a HOST
  * array of n device pointers, `weights_host` a host array of n floats (n <= DA_MAX_WEIGHTED).  Backward: d losses[i] =

@@ -144,6 +144,9 @@ SIGNATURES = {
     "da_global_avgpool_backward": (I, [P, I, I, I, P, I, P]),
     "da_softmax_dim0_forward": (I, [P, I, I, P, P]),
     "da_softmax_dim0_backward": (I, [P, P, I, I, P, P]),
+    "da_colsoftmax_workspace_bytes": (S, [I, I]),
+    "da_colsoftmax_forward": (I, [P, I, I, I, P, I, P, I, P, S, P]),
+    "da_colsoftmax_backward": (I, [P, I, P, I, I, I, P, I, P, S, P]),
     "da_weighted_sum_forward": (I, [POINTER(c_void_p), POINTER(c_float), I, P, P, P]),
     "da_weighted_sum_backward": (I, [POINTER(c_float), I, P, P, P, P]),
     "da_grl_conv_loss_workspace_bytes": (S, [CD]),

@@ -349,6 +349,9 @@ class NonLocalBlock(_HeadBase):
     `forward_tokens` works on [T,C] token matrices (NHWC rows); `forward` keeps the reference's
     [b,C,h,w] signature."""
 
+    BLOCK_TOKENS = 4096   # more tokens than this: functional.nonlocal_attention_blocked (the T x T scores are never materialised)
+    BLOCK_K = 2048        # keys per block
+
     def __init__(self, channel):
         super().__init__()
         self.inter_channel = channel // 2
@@ -368,6 +371,12 @@ class NonLocalBlock(_HeadBase):
         xin = x.view(T, 1, 1, C)
         lay = lambda conv, g: F_.dense_layer(xin, conv.weight, grl=g).view(T, -1)
         phi, theta, g = lay(self.conv_phi, grl), lay(self.conv_theta, grl), lay(self.conv_g, grl)
+        if T > self.BLOCK_TOKENS:
+            # key-block by key-block, two-pass query-axis softmax, recompute in backward: no T x T matrix
+            y = F_.nonlocal_attention_blocked(theta, phi, g, self.BLOCK_K)
+            mask = F_.dense_layer(y.view(T, 1, 1, -1), self.conv_mask.weight).view(T, C)
+            skip = x if grl == 1.0 else F_.gradient_scalar(x, grl)
+            return mask + skip
         # S[q,k] = theta[q,:].phi[k,:]  (theta as activations, phi as the "weight")
         s = F_.dense_layer(theta.view(T, 1, 1, -1), phi, out_dtype=torch.float32).view(T, T)
         p = F_.softmax_dim0(s)

@@ -750,6 +750,125 @@ def softmax_dim0(s):
 
 
 # --------------------------------------------------------------------------------------
+# blocked NonLocalBlock attention: key blocks, two-pass query-axis softmax, recompute in backward
+# --------------------------------------------------------------------------------------
+def _gemm_nt(a, b, out, engine):
+    """out[M,N] = a[M,K] . b[N,K]^T   (forward form of the 1x1 implicit GEMM: x = a, w = b)."""
+    M, K = a.shape
+    N = b.shape[0]
+    desc = _conv_desc(M, 1, 1, K, N, 1, 1, 1, 0, engine, a.dtype, out.dtype)
+    ws = workspace(lib.da_conv_workspace_bytes(ctypes.byref(desc)), a.device, "conv")
+    check(lib.da_conv_forward(ctypes.byref(desc), _ptr(a), _ptr(b), None, None, 0, 0.0, 0, _ptr(out), _ptr(ws), ws.numel(),
+                              _stream()), "conv_forward")
+    return out
+
+
+def _gemm_nn(a, b, out, engine):
+    """out[M,N] = a[M,K] . b[K,N]   (data-gradient form: dz = a, w = b as [Cout=K, Cin=N]; b is read where it lies)."""
+    M, K = a.shape
+    N = b.shape[1]
+    desc = _conv_desc(M, 1, 1, N, K, 1, 1, 1, 0, engine, a.dtype, out.dtype)
+    ws = workspace(lib.da_conv_workspace_bytes(ctypes.byref(desc)), a.device, "conv")
+    check(lib.da_conv_backward_data(ctypes.byref(desc), _ptr(a), _ptr(b), 1.0, _ptr(out), _ptr(ws), ws.numel(), _stream()),
+          "conv_backward_data")
+    return out
+
+
+def _gemm_tn(a, b, out, engine):
+    """out[K1,K2] (fp32) = a[M,K1]^T . b[M,K2]   (weight-gradient form: dz = a, x = b)."""
+    M, K1 = a.shape
+    K2 = b.shape[1]
+    desc = _conv_desc(M, 1, 1, K2, K1, 1, 1, 1, 0, engine, a.dtype, a.dtype)
+    ws = workspace(lib.da_conv_workspace_bytes(ctypes.byref(desc)), a.device, "conv")
+    check(lib.da_conv_backward_weight(ctypes.byref(desc), _ptr(b), _ptr(a), _ptr(out), _ptr(ws), ws.numel(), _stream()),
+          "conv_backward_weight")
+    return out
+
+
+class BlockedNonLocalAttention(Function):
+    """y[q,:] = sum_k P[q,k] g[k,:],  P = softmax over the QUERY axis of theta.phi^T  (NonLocalBlock,
+    mmdet/models/backbones/resnet_da_deep.py:402-445, roi_heads/instance_da.py:150-192; Q11), without the T x T matrix.
+
+    Key columns normalise independently, so the keys are walked in blocks of `block_k`: per block one score GEMM
+    [T x block_k] (fp32), the two-pass column softmax of csrc/colsoftmax.cu (statistics kept: 2 floats per key), one
+    P.g GEMM accumulated in fp32.  Backward recomputes the block's scores and P from the saved statistics (no second
+    statistics pass) and runs the five gradient GEMMs of the block; only theta, phi, g and 2T floats are saved, against
+    T^2 floats for the unblocked form (4.3 GB per image at T = 32768, C3 of a 1024x2048 input)."""
+
+    @staticmethod
+    def forward(ctx, theta, phi, g, block_k, engine):
+        _require_cuda(theta, phi, g)
+        theta, phi, g = theta.contiguous(), phi.contiguous(), g.contiguous()
+        T, I = theta.shape
+        dt, dev = theta.dtype, theta.device
+        bk = min(int(block_k), T)
+        stats = torch.empty((2 * T,), dtype=torch.float32, device=dev)
+        s_buf = torch.empty((T * bk,), dtype=torch.float32, device=dev)
+        p_buf = torch.empty((T * bk,), dtype=dt, device=dev)
+        y = torch.empty((T, I), dtype=torch.float32, device=dev)
+        yb = torch.empty((T, I), dtype=torch.float32, device=dev) if T > bk else None
+        ws = workspace(lib.da_colsoftmax_workspace_bytes(T, bk), dev, "colsoftmax")
+        for k0 in range(0, T, bk):
+            tk = min(bk, T - k0)
+            s = _gemm_nt(theta, phi[k0:k0 + tk], s_buf[:T * tk].view(T, tk), engine)
+            p = p_buf[:T * tk].view(T, tk)
+            check(lib.da_colsoftmax_forward(_ptr(s), T, tk, tk, _ptr(p), _code(dt), _ptr(stats[2 * k0:]), 0, _ptr(ws), ws.numel(),
+                                            _stream()), "colsoftmax_forward")
+            if k0 == 0:
+                _gemm_nn(p, g[k0:k0 + tk], y, engine)
+            else:
+                y += _gemm_nn(p, g[k0:k0 + tk], yb, engine)
+        ctx.save_for_backward(theta, phi, g, stats)
+        ctx.cfg = (bk, engine)
+        return y.to(dt)
+
+    @staticmethod
+    def backward(ctx, dy):
+        theta, phi, g, stats = ctx.saved_tensors
+        bk, engine = ctx.cfg
+        T, I = theta.shape
+        dt, dev = theta.dtype, theta.device
+        dy = cast(dy.contiguous(), dt)
+        s_buf = torch.empty((T * bk,), dtype=torch.float32, device=dev)
+        dp_buf = torch.empty((T * bk,), dtype=torch.float32, device=dev)
+        p_buf = torch.empty((T * bk,), dtype=dt, device=dev)
+        ds_buf = torch.empty((T * bk,), dtype=dt, device=dev)
+        dtheta = torch.empty((T, I), dtype=torch.float32, device=dev)
+        dtb = torch.empty((T, I), dtype=torch.float32, device=dev) if T > bk else None
+        dphi = torch.empty((T, I), dtype=torch.float32, device=dev)
+        dg = torch.empty((T, I), dtype=torch.float32, device=dev)
+        ws = workspace(lib.da_colsoftmax_workspace_bytes(T, bk), dev, "colsoftmax")
+        for k0 in range(0, T, bk):
+            tk = min(bk, T - k0)
+            phi_b, g_b = phi[k0:k0 + tk], g[k0:k0 + tk]
+            s = _gemm_nt(theta, phi_b, s_buf[:T * tk].view(T, tk), engine)
+            p = p_buf[:T * tk].view(T, tk)
+            check(lib.da_colsoftmax_forward(_ptr(s), T, tk, tk, _ptr(p), _code(dt), _ptr(stats[2 * k0:]), 1, None, 0, _stream()),
+                  "colsoftmax_forward")
+            dp = _gemm_nt(dy, g_b, dp_buf[:T * tk].view(T, tk), engine)
+            _gemm_tn(p, dy, dg[k0:k0 + tk], engine)                       # dg_b = P_b^T . dy
+            ds = ds_buf[:T * tk].view(T, tk)
+            check(lib.da_colsoftmax_backward(_ptr(p), _code(dt), _ptr(dp), T, tk, tk, _ptr(ds), _code(dt), _ptr(ws), ws.numel(),
+                                             _stream()), "colsoftmax_backward")
+            if k0 == 0:
+                _gemm_nn(ds, phi_b, dtheta, engine)                       # dtheta += dS_b . phi_b
+            else:
+                dtheta += _gemm_nn(ds, phi_b, dtb, engine)
+            _gemm_tn(ds, theta, dphi[k0:k0 + tk], engine)                 # dphi_b = dS_b^T . theta
+        return dtheta.to(dt), dphi.to(dt), dg.to(dt), None, None
+
+
+def nonlocal_attention_blocked(theta, phi, g, block_k=2048, engine=None):
+    """theta, phi, g: [T,I] token projections in the activation dtype -> y [T,I].  T and I must be multiples of 8 (tile
+    granularity of the tensor-core engines; the CUDA-core engine takes any size)."""
+    engine = engine or get_engine()
+    T, I = theta.shape
+    if engine != "simt_f32" and (T % 8 or I % 8 or int(block_k) % 8):
+        raise RuntimeError(f"nonlocal_attention_blocked: T={T}, I={I}, block_k={block_k} must be multiples of 8 on engine {engine}")
+    return BlockedNonLocalAttention.apply(theta, phi, g, int(block_k), engine)
+
+
+# --------------------------------------------------------------------------------------
 # instance-level domain classifier + CE as one persistent kernel (csrc/chain.cu)
 # --------------------------------------------------------------------------------------
 def pack_projection(weights):
