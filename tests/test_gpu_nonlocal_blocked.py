@@ -142,6 +142,7 @@ def test_nonlocal_alignment_head_at_full_c3_size():
     assert rel_err(y, ref) <= BF16_TOL
     assert torch.cuda.max_memory_allocated() < 6 * (1 << 30)          # nowhere near T*T*4 = 4.3 GB per live matrix (x3 in autograd)
     head = da_heads.NonLocalAlignmentHead(512).to(DEV)
+    head.bn1.eval()          # frozen statistics, as in the reference (norm_eval=True)
     x = torch.relu(seeded.seeded_tensor("nlb.full.x", (1, 512, 128, 256), 0)).to(DEV).requires_grad_(True)
     out = head(x)
     assert out.shape == (1, 512, 128, 256) and bool(torch.isfinite(out).all())

@@ -858,7 +858,7 @@ class BlockedNonLocalAttention(Function):
         return dtheta.to(dt), dphi.to(dt), dg.to(dt), None, None
 
 
-def nonlocal_attention_blocked(theta, phi, g, block_k=2048, engine=None):
+def nonlocal_attention_blocked(theta, phi, g, block_k=4096, engine=None):
     """theta, phi, g: [T,I] token projections in the activation dtype -> y [T,I].  T and I must be multiples of 8 (tile
     granularity of the tensor-core engines; the CUDA-core engine takes any size)."""
     engine = engine or get_engine()
