@@ -200,6 +200,29 @@ int da_roi_align_backward_prepared(const void* grad_out, int grad_dtype, int out
 int da_map_roi_levels(const float* rois, int R, int num_levels, float finest_scale,
                       int32_t* levels_out, da_stream_t stream);
 
+/* ---- RPN proposal stage ------------------------------
+ * Replaces RPNHeadDA._get_bboxes_single + _bbox_post_process (mmdet/models/dense_heads/rpn_head_da.py:170-303) for one image
+ * and one level: sigmoid scores in the reference's (H,W,A) order, DeltaXYWHBBoxCoder.decode = delta2bbox
+ * (mmdet/core/bbox/coder/delta_xywh_bbox_coder.py:224-259), the min_bbox_size filter, mmcv.ops.batched_nms (single level =
+ * plain NMS: a box is dropped when its IoU with a kept, higher-ranked box is > iou_thr) and the first max_out survivors.
+ *   da_rpn_scores    cls [A,H*W] fp32 logits (the conv output as it lies) -> scores [H*W*A], index = cell*A + a.
+ *   (ranking: the caller sorts scores descending, stable, and passes the first n = min(nms_pre, H*W*A) indices + scores)
+ *   da_rpn_proposals reg [4A,H,W] fp32 deltas as they lie; base_anchors [A,4] (AnchorGenerator.base_anchors of the level),
+ *                    anchor(idx) = base[idx % A] + stride * (cell % W, cell / W, ...) is computed, never stored;
+ *                    means4 / stds4 / max_ratio = |log(wh_ratio_clip)| / (img_h, img_w) = max_shape / min_size < 0 disables
+ *                    the size filter.  dets [max_out,5] = (x1,y1,x2,y2,score) in rank order, zero padded; *count (device
+ *                    int32) = number of valid rows; keep_idx (nullable, int32 [max_out]) = rank of each kept box, -1 padded.
+ * Nothing is read back by the host.  Workspace: da_rpn_proposals_workspace_bytes(n) (decoded boxes, validity flags and the
+ * n x ceil(n/64) suppression bitmap); da_rpn_proposals_peek copies the decoded boxes / flags of the last call out of it. */
+int da_rpn_scores(const float* cls, int A, int HW, float* scores, da_stream_t stream);
+size_t da_rpn_proposals_workspace_bytes(int n);
+int da_rpn_proposals(const float* reg, int A, int H, int W, const float* base_anchors, float stride,
+                     const int64_t* top_idx, const float* top_scores, int n,
+                     const float* means4, const float* stds4, float max_ratio, float img_h, float img_w, float min_size,
+                     float iou_thr, int max_out, float* dets, int32_t* count, int32_t* keep_idx,
+                     void* workspace, size_t workspace_bytes, da_stream_t stream);
+int da_rpn_proposals_peek(const void* workspace, int n, float* boxes_out, unsigned char* valid_out, da_stream_t stream);
+
 /* ---- domain losses -------------------------------
  * Every forward writes fp32 scalars on the device; every backward takes the upstream
  * gradient as a DEVICE scalar pointer (nullable = 1) times a host scalar `scale`

@@ -222,3 +222,49 @@ def test_bbox_head_loss_matches_reference_loss_classes(golden):
         assert abs(float(out["acc"]) - float(g["acc"])) <= 1e-4
         (out["loss_cls"] + out["loss_bbox"]).backward()
         assert float((cls.grad - g["dcls"]).abs().max()) <= 1e-7 and float((reg.grad - g["dreg"]).abs().max()) <= 1e-7
+
+
+# ---------------------------------------------------------------------------- RPN proposal stage
+def _rpn_inputs(name, g):
+    from oracle import seeded
+    cls = seeded.seeded_tensor(f"rpn.{name}.cls", (g["A"], g["H"], g["W"]), 0, scale=g["cls_scale"])
+    reg = seeded.seeded_tensor(f"rpn.{name}.reg", (4 * g["A"], g["H"], g["W"]), 0, scale=g["reg_scale"])
+    return cls, reg
+
+
+def test_rpn_oracle_vs_reference_golden(golden):
+    """oracle/rpn_oracle.py against the fixture produced by the reference's AnchorGenerator + delta2bbox run in place
+    (oracle/make_golden_rpn.py) and torchvision's NMS: bit-exact anchors, ranking, decoded boxes and proposals."""
+    from oracle import rpn_oracle
+    rec = golden("rpn_proposals.pt")
+    d = rec["docstring"]
+    out = rpn_oracle.delta2bbox(d["rois"], d["deltas"], max_shape=d["max_shape"])
+    assert torch.equal(out, d["reference_output"])
+    assert torch.allclose(out, d["expected"], atol=5e-5)          # the known-answer example of delta_xywh_bbox_coder.py:210-222
+    for name in ("small", "min_size", "dc5_s"):
+        g = rec[name]
+        cls, reg = _rpn_inputs(name, g)
+        base = rpn_oracle.base_anchors(g["stride"], [0.5, 1.0, 2.0], [2, 4, 8, 16, 32])
+        assert torch.equal(base, g["base_anchors"])
+        anchors = rpn_oracle.grid_anchors(base, g["H"], g["W"], g["stride"])
+        assert torch.equal(anchors[:32], g["anchors_first"]) and torch.equal(anchors[-32:], g["anchors_last"])
+        s, idx = rpn_oracle.rank(cls.permute(1, 2, 0).reshape(-1).sigmoid(), g["nms_pre"])
+        assert torch.equal(idx[:64], g["top_idx_head"]) and idx.numel() == g["n_decoded"]
+        decoded = rpn_oracle.delta2bbox(anchors[idx], reg.permute(1, 2, 0).reshape(-1, 4)[idx], max_shape=g["img_shape"])
+        assert torch.equal(decoded[:256], g["decoded_head"])
+        dets = rpn_oracle.proposals(cls, reg, base, g["stride"], g["img_shape"], g["nms_pre"], g["max_per_img"], g["iou_thr"], g["min_size"])
+        assert dets.shape == g["dets"].shape and torch.equal(dets, g["dets"]), name
+
+
+def test_rpn_oracle_nms_vs_torchvision():
+    """The greedy NMS loop against torchvision.ops.nms (the stand-in for mmcv.ops.nms) on clustered random boxes."""
+    from torchvision.ops import nms
+    from oracle import rpn_oracle
+    g = torch.Generator().manual_seed(3)
+    ctr = torch.rand(40, 2, generator=g) * 400
+    xy = (ctr[torch.randint(0, 40, (3000,), generator=g)] + torch.randn(3000, 2, generator=g) * 12)
+    wh = torch.rand(3000, 2, generator=g) * 80 + 4
+    boxes = torch.cat([xy - wh / 2, xy + wh / 2], -1)
+    scores = torch.sort(torch.rand(3000, generator=g), descending=True).values
+    for thr in (0.3, 0.7):
+        assert torch.equal(rpn_oracle.greedy_nms(boxes, thr), nms(boxes, scores, thr))

@@ -144,6 +144,10 @@ SIGNATURES = {
     "da_global_avgpool_backward": (I, [P, I, I, I, P, I, P]),
     "da_softmax_dim0_forward": (I, [P, I, I, P, P]),
     "da_softmax_dim0_backward": (I, [P, P, I, I, P, P]),
+    "da_rpn_scores": (I, [P, I, I, P, P]),
+    "da_rpn_proposals_workspace_bytes": (S, [I]),
+    "da_rpn_proposals": (I, [P, I, I, I, P, F, P, P, I, POINTER(c_float), POINTER(c_float), F, F, F, F, F, I, P, P, P, P, S, P]),
+    "da_rpn_proposals_peek": (I, [P, I, P, P, P]),
     "da_colsoftmax_workspace_bytes": (S, [I, I]),
     "da_colsoftmax_forward": (I, [P, I, I, I, P, I, P, I, P, S, P]),
     "da_colsoftmax_backward": (I, [P, I, P, I, I, I, P, I, P, S, P]),

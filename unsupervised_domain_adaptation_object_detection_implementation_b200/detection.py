@@ -164,6 +164,15 @@ class RPNHeadDA(nn.Module):
         return cls, reg
 
     def _proposals(self, cls, reg, anchors, img_shape, cfg):
+        if cls.is_cuda:
+            # native proposal stage (csrc/rpn_proposals.cu): scores, analytic anchors, decode, NMS, top max_per_img on the
+            # device; the ONE host read is the survivor count, to hand back the reference's variable-length [n,5] tensor
+            from . import functional as F_
+            dets, count = F_.rpn_proposals(cls, reg, self.anchor_generator.base[0], self.anchor_generator.strides[0], img_shape,
+                                           nms_pre=cfg.get("nms_pre", 2000), max_per_img=cfg.get("max_per_img", 1000),
+                                           iou_thr=cfg.get("nms", {}).get("iou_threshold", 0.7),
+                                           min_size=cfg.get("min_bbox_size", 0), means=self.bbox_coder.means, stds=self.bbox_coder.stds)
+            return dets[:int(count)]
         scores = cls.permute(1, 2, 0).reshape(-1).sigmoid()
         deltas = reg.permute(1, 2, 0).reshape(-1, 4)
         nms_pre = cfg.get("nms_pre", 2000)

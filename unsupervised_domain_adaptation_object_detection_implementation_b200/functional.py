@@ -9,6 +9,7 @@ Activation layout inside the DA heads is NHWC ([N,H,W,C] contiguous); `to_nhwc` 
 reference's NCHW tensors (zero-copy when they are channels_last).
 """
 import ctypes
+import math
 
 import os
 import torch
@@ -747,6 +748,50 @@ class SoftmaxDim0Function(Function):
 
 def softmax_dim0(s):
     return SoftmaxDim0Function.apply(s)
+
+
+# --------------------------------------------------------------------------------------
+# RPN proposal stage: scores, decode, NMS, top max_per_img -- no host round trip
+# --------------------------------------------------------------------------------------
+def rpn_proposals(cls, reg, base_anchors, stride, img_shape, nms_pre=12000, max_per_img=2000, iou_thr=0.7, min_size=0.0,
+                  means=(0., 0., 0., 0.), stds=(1., 1., 1., 1.), wh_ratio_clip=16 / 1000, return_keep=False):
+    """One image, one level of RPNHeadDA._get_bboxes_single + _bbox_post_process (rpn_head_da.py:170-303).
+    cls [A,H,W] logits, reg [4A,H,W] deltas (the conv outputs as they lie), base_anchors [A,4] ->
+    (dets [max_per_img,5] zero padded, count: 0-dim int32 DEVICE tensor[, keep ranks int32 [max_per_img]]).
+    The ranking is torch.sort(stable, descending) on the device; everything else is csrc/rpn_proposals.cu."""
+    _require_cuda(cls, reg)
+    A, H, W = cls.shape
+    if reg.shape != (4 * A, H, W):
+        raise RuntimeError(f"rpn_proposals: reg {tuple(reg.shape)} does not match cls {tuple(cls.shape)}")
+    dev = cls.device
+    cls = cls.detach().contiguous().float()
+    reg = reg.detach().contiguous().float()
+    base = base_anchors.detach().to(device=dev, dtype=torch.float32).contiguous()
+    total = A * H * W
+    scores = torch.empty((total,), dtype=torch.float32, device=dev)
+    check(lib.da_rpn_scores(_ptr(cls), A, H * W, _ptr(scores), _stream()), "rpn_scores")
+    top_scores, top_idx = torch.sort(scores, descending=True, stable=True)
+    n = int(nms_pre) if 0 < int(nms_pre) < total else total
+    top_scores, top_idx = top_scores[:n].contiguous(), top_idx[:n].contiguous()
+    dets = torch.empty((int(max_per_img), 5), dtype=torch.float32, device=dev)
+    count = torch.empty((), dtype=torch.int32, device=dev)
+    keep = torch.empty((int(max_per_img),), dtype=torch.int32, device=dev) if return_keep else None
+    ws = workspace(lib.da_rpn_proposals_workspace_bytes(n), dev, "rpn")
+    f4 = ctypes.c_float * 4
+    check(lib.da_rpn_proposals(_ptr(reg), A, H, W, _ptr(base), float(stride), _ptr(top_idx), _ptr(top_scores), n,
+                               f4(*[float(v) for v in means]), f4(*[float(v) for v in stds]), abs(math.log(wh_ratio_clip)),
+                               float(img_shape[0]), float(img_shape[1]), float(min_size), float(iou_thr), int(max_per_img),
+                               _ptr(dets), _ptr(count), _ptr(keep), _ptr(ws), ws.numel(), _stream()), "rpn_proposals")
+    return (dets, count, keep) if return_keep else (dets, count)
+
+
+def rpn_decoded_boxes(n, device):
+    """Decoded boxes [n,4] and validity flags [n] of the last rpn_proposals call on this device (pre-NMS set, rank order)."""
+    ws = workspace(lib.da_rpn_proposals_workspace_bytes(n), device, "rpn")
+    boxes = torch.empty((n, 4), dtype=torch.float32, device=device)
+    valid = torch.empty((n,), dtype=torch.uint8, device=device)
+    check(lib.da_rpn_proposals_peek(_ptr(ws), n, _ptr(boxes), _ptr(valid), _stream()), "rpn_proposals_peek")
+    return boxes, valid.bool()
 
 
 # --------------------------------------------------------------------------------------
