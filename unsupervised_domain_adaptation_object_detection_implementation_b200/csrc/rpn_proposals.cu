@@ -105,23 +105,32 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned char
   extern __shared__ unsigned long long remv[];          // [words]
   __shared__ unsigned long long diag[64];
   __shared__ unsigned long long s_kept;
+  __shared__ unsigned s_valid[2];
   __shared__ int s_count;
   const int t = threadIdx.x;
   for (int w = t; w < words; w += SCAN_THREADS) remv[w] = 0ull;
   if (t == 0) s_count = 0;
   __syncthreads();
+  const int warp = t >> 5, lane = t & 31;
   for (int b = 0; b < words; ++b) {
     if (s_count >= max_out) break;                       // uniform: s_count is only written between barriers
     const int i0 = b * 64, nb = min(64, n - i0);
-    if (t < 64) diag[t] = (t < nb) ? mask[(size_t)(i0 + t) * words + b] : 0ull;
+    if (t < 64) {
+      diag[t] = (t < nb) ? mask[(size_t)(i0 + t) * words + b] : 0ull;
+      const unsigned vb = __ballot_sync(0xffffffffu, t < nb && valid[i0 + t] != 0);      // validity of the 64 boxes as two words
+      if (lane == 0) s_valid[warp] = vb;
+    }
     __syncthreads();
     if (t == 0) {
       unsigned long long cur = remv[b], kept = 0ull;
-      for (int j = 0; j < nb; ++j) {
-        if (!((cur >> j) & 1ull) && valid[i0 + j]) {
-          kept |= 1ull << j;
-          cur |= diag[j];
-        }
+      const unsigned long long vmask = (unsigned long long)s_valid[0] | ((unsigned long long)s_valid[1] << 32);
+      unsigned long long cand = vmask & ~cur;            // boxes of this block still alive; a kept box may clear later ones
+      while (cand) {
+        const int j = __ffsll((long long)cand) - 1;
+        kept |= 1ull << j;
+        cur |= diag[j];
+        cand &= ~cur;
+        cand &= ~((2ull << j) - 1ull);                   // strictly after j
       }
       s_kept = kept;
     }
@@ -138,15 +147,21 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const unsigned char
         if (keep_idx) keep_idx[pos] = i0 + t;
       }
     }
-    // every later word: OR the rows of the kept boxes into the removed bitmap
-    for (int w = b + 1 + t; w < words; w += SCAN_THREADS) {
-      unsigned long long acc = remv[w], k = kept;
+    // every later word: OR the rows of the kept boxes into the removed bitmap.  One warp per kept row (coalesced row reads, all of a
+    // row's loads in flight at once), shared-memory atomicOr: OR commutes, so the result does not depend on the order.
+    {
+      unsigned long long k = kept;
+      int r = 0;
       while (k) {
         const int j = __ffsll((long long)k) - 1;
         k &= k - 1;
-        acc |= mask[(size_t)(i0 + j) * words + w];
+        if ((r++ & (SCAN_THREADS / 32 - 1)) != warp) continue;
+        const unsigned long long* row = mask + (size_t)(i0 + j) * words;
+        for (int w = b + 1 + lane; w < words; w += 32) {
+          const unsigned long long v = row[w];
+          if (v) atomicOr(&remv[w], v);
+        }
       }
-      remv[w] = acc;
     }
     __syncthreads();
     if (t == 0) s_count = base_count + __popcll(kept);
