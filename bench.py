@@ -543,10 +543,42 @@ def kernel_rooflines(dev, act, step_ms, fused_step=True):
     gradf = dw.view(-1)
     hbm_row("sgd_step_fc1", time_it(lambda: check(lib.da_sgd_step(P(wf), P(gradf), P(buf), n, 0.01, 0.9, 1e-4, 0, P(shadow), S()), "sgd_step")),
             n * (4 * 3 + 4 * 2 + 2))
+    # "next" rows of SURVEY 8f, measured beside the step (not launched by it): the query-axis softmax kernels of the blocked
+    # NonLocalBlock on one [32768 x 4096] key block (C3 of a 1024x2048 input), the blocked attention as a whole, and the RPN
+    # proposal stage of one image at the train configuration (122880 candidates -> 12000 ranked -> NMS -> 2000)
+    del wf, gradf, buf, shadow, dw
+    torch.cuda.empty_cache()
+    Tq, Tk, Inl = 32768, 4096, 256
+    s_blk = torch.randn(Tq, Tk, device=dev, generator=g) * 3
+    p_blk = torch.empty(Tq, Tk, dtype=torch.bfloat16, device=dev)
+    stats = torch.empty(2 * Tk, device=dev)
+    cws = torch.empty(lib.da_colsoftmax_workspace_bytes(Tq, Tk), dtype=torch.uint8, device=dev)
+    hbm_row("nlb_colsoftmax_fwd", time_it(lambda: check(lib.da_colsoftmax_forward(P(s_blk), Tq, Tk, Tk, P(p_blk), 1, P(stats), 0, P(cws), cws.numel(), S()),
+                                                   "colsoftmax_forward"), 6), Tq * Tk * 10, "key block [32768 x 4096]: S fp32 read twice, P bf16 written")
+    dp_blk = torch.randn(Tq, Tk, device=dev, generator=g)
+    ds_blk = torch.empty_like(p_blk)
+    hbm_row("nlb_colsoftmax_bwd", time_it(lambda: check(lib.da_colsoftmax_backward(P(p_blk), 1, P(dp_blk), Tq, Tk, Tk, P(ds_blk), 1, P(cws), cws.numel(), S()),
+                                                   "colsoftmax_backward"), 6), Tq * Tk * 14, "P bf16 + dP fp32 read twice, dS bf16 written")
+    del s_blk, p_blk, dp_blk, ds_blk
+    mk = lambda sc: (torch.randn(Tq, Inl, device=dev, generator=g) * sc).to(torch.bfloat16)
+    th, ph, gg = mk(0.2), mk(0.2), mk(1.0)
+    with torch.no_grad():
+        t_nlb = time_it(lambda: F_.nonlocal_attention_blocked(th, ph, gg, Tk), 4)
+    tensor_row("nlb_blocked_attention_fwd", t_nlb, 4.0 * Tq * Tq * Inl, "T = 32768 tokens, I = 256, 8 key blocks: 2 GEMMs + the softmax passes (HBM-bound on the fp32 score blocks)")
+    del th, ph, gg
+    A_r, H_r, W_r = 15, 64, 128
+    cls_r = torch.randn(A_r, H_r, W_r, device=dev, generator=g) * 2
+    reg_r = torch.randn(4 * A_r, H_r, W_r, device=dev, generator=g) * 0.5
+    from unsupervised_domain_adaptation_object_detection_implementation_b200.detection import AnchorGenerator
+    base_r = AnchorGenerator(strides=[16], ratios=[0.5, 1.0, 2.0], scales=[2, 4, 8, 16, 32]).base[0]
+    t_rpn = time_it(lambda: F_.rpn_proposals(cls_r, reg_r, base_r, 16, (1024, 2048), 12000, 2000, 0.7, 0.0), 6)
+    table["rpn_proposals_per_image"] = {"ms": round(t_rpn, 4), "note": "122880 candidates -> 12000 ranked -> NMS 0.7 -> 2000; 4 of our launches + torch.sort; "
+                                        "latency-sized (one-CTA scan), no roofline row"}
     # the dominant kernel is picked among the kernels the timed step actually launches
     not_in_step = {"fc1_wgrad", "sgd_step_fc1"} if fused_step else {"fc1_wgrad_sgd", "sgd_step_fc1"}
     for k in table:
-        table[k]["in_step"] = k not in not_in_step and not k.startswith("da_conv_") and not k.endswith("_config4")
+        table[k]["in_step"] = (k not in not_in_step and not k.startswith("da_conv_") and not k.endswith("_config4")
+                               and not k.startswith("nlb_") and not k.startswith("rpn_"))
     table["da_conv_h1_1x1_c5_fwd"]["in_step"] = table["da_conv_h1_1x1_c5_dgrad"]["in_step"] = table["da_conv_h1_1x1_c5_wgrad"]["in_step"] = True
     dom = max((k for k in table if table[k]["in_step"]), key=lambda k: table[k]["ms"])
     d = table[dom]
