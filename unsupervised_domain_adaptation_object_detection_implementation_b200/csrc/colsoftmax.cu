@@ -5,7 +5,7 @@
 // its own max and its own sum over the T queries.  Key columns are therefore independent, and the T x T matrix (4.3 GB per image
 // in fp32 at T = 32768, a 1024x2048 input on C3) never has to exist: functional.nonlocal_attention_blocked walks the keys in
 // blocks of Tk columns; per block S_b = theta.phi_b^T is [Tq x Tk] and these kernels normalise it in two passes:
-//   pass 1  per (row chunk, column): running max m and sum of exp(s - m), one read of S_b        (colstats_partial)
+//   pass 1  per (row chunk, column): running max m and sum of exp(s - m), rescaled once per 4 rows    (colstats_partial)
 //           per column: merge the chunks -> stats = (max, 1 / sum)                               (colstats_combine)
 //   pass 2  p = exp(s - max) / sum, written once in the GEMM operand dtype (bf16 or fp32)         (col_apply)
 // The backward of the block, ds = p * (dp - sum_q p*dp), has the same shape: per-chunk column dots, merge, apply.
@@ -44,11 +44,6 @@ template <> struct Ld2<__nv_bfloat16> {
   static __device__ __forceinline__ void st(__nv_bfloat16* p, float a, float b) { *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b); }
 };
 
-// running (max, sum of exp(v - max)); one exp per element unless the max moves
-__device__ __forceinline__ void online(float v, float& m, float& z) {
-  if (v > m) { z = z * expf(m - v) + 1.f; m = v; }
-  else z += expf(v - m);
-}
 __device__ __forceinline__ void merge(float m2, float z2, float& m, float& z) {
   if (z2 == 0.f) return;
   if (z == 0.f) { m = m2; z = z2; return; }
@@ -83,11 +78,20 @@ colstats_partial_kernel(const float* __restrict__ s, int Tq, int Tk, int ld, int
           for (int v = 0; v < VEC; ++v) x[u][v] = -INFINITY;
         }
       }
+      // one rescale per CS_UNROLL rows and no data-dependent branch: ncu of the per-element form (rescale only when the max
+      // moves) showed the kernel issue-bound at 40 % of DRAM -- both sides of the divergent branch ran, two exps per element
 #pragma unroll
-      for (int u = 0; u < CS_UNROLL; ++u)
+      for (int v = 0; v < VEC; ++v) {
+        float mx = x[0][v];
 #pragma unroll
-        for (int v = 0; v < VEC; ++v)
-          if (x[u][v] != -INFINITY) online(x[u][v], m[v], z[v]);
+        for (int u = 1; u < CS_UNROLL; ++u) mx = fmaxf(mx, x[u][v]);
+        const float mn = fmaxf(m[v], mx);                 // finite: row u = 0 of the group is always in range
+        float acc = z[v] * expf(m[v] - mn);               // first group: 0 * exp(-inf) = 0
+#pragma unroll
+        for (int u = 0; u < CS_UNROLL; ++u) acc += expf(x[u][v] - mn);    // masked rows: exp(-inf) = 0
+        z[v] = acc;
+        m[v] = mn;
+      }
     }
   }
 #pragma unroll
