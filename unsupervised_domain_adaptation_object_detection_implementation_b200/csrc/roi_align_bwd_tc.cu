@@ -24,6 +24,9 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return v;
 }
 
+__constant__ unsigned char kRowPerm[64] = {0, 1, 34, 19, 4, 5, 38, 23, 8, 9, 42, 27, 12, 13, 46, 31, 16, 49, 50, 35, 20, 53, 54, 39, 24, 57, 58, 43, 28, 61, 62, 47,
+                                           32, 17, 2, 3, 36, 21, 6, 7, 40, 25, 10, 11, 44, 29, 14, 15, 48, 33, 18, 51, 52, 37, 22, 55, 56, 41, 26, 59, 60, 45, 30, 63};
+
 constexpr int BT_TY = 16, BT_TX = 16, BT_PX = BT_TY * BT_TX;   // 256 pixels = UMMA N
 constexpr int BT_CH = 256;                                      // channels per CTA = 2 accumulators of 128
 constexpr int BT_BUILDERS = 512;                                // warps 2..17: two half-rows per operand row
@@ -240,7 +243,12 @@ roi_align_bwd_tc_kernel(const __nv_bfloat16* __restrict__ grad_out, int C, int H
     } else {
       // ------------------------------------------------ operand builders (512 threads)
       // thread = (operand row, 64-byte half of its 128-byte K row); halves are warp-uniform
-      const int bt = t - 64, half = bt >> 8, row = bt & 255;
+      // Lane -> operand row: the raw gradient rows have a 98-byte pitch, so 32 CONSECUTIVE rows put 8 of the 32 lanes of every
+      // relayout LDS.32 on an already used bank (2 passes per load: ~430 of the ~1600 shared-memory-port cycles per pair,
+      // profiles/r02_roi_bwd_pipeline_study.md).  Within each group of 64 rows the two warps take the row sets below instead:
+      // floor(24.5 r) mod 32 is distinct over a warp (conflict-free loads) and every aligned octet of lanes holds all residues
+      // r mod 8 (conflict-free 128B-swizzled STS.128, as before).  Pure re-assignment of work: results are bit-identical.
+      const int bt = t - 64, half = bt >> 8, row = (dbg & 256) ? (bt & 255) : ((bt & 192) | kRowPerm[bt & 63]);
       for (int li = 0; li < n_list; ++li) {
         const int sq = seq + li, slot = sq % BT_NRAW, ob = sq & 1;
         mbar_wait(raw_full0 + 8 * slot, (uint32_t)(sq / BT_NRAW) & 1u);
