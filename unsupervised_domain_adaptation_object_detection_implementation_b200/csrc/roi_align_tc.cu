@@ -302,10 +302,29 @@ roi_align_fwd_tc_kernel(const __grid_constant__ CUtensorMap fmap, int C, int H, 
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty0 + 8 * (accb + j));
           TOut* stg = reinterpret_cast<TOut*>(gen + (stage0 - base) + sb * STG) + (size_t)(q * 32 + lane) * PP;
+          bool packed = false;
+          if constexpr (sizeof(TOut) == 2) packed = !(dbg & 4);       // bit 2 of roi_fwd_dbg: the old 2-byte stores (A/B)
+          if (packed) {
+            // 98-byte rows: 4-byte aligned for even channels, 2 mod 4 for odd ones.  One 2-byte store (element 48 resp. 0) and 24
+            // packed 4-byte stores per row instead of 49 2-byte ones: the epilogue's conflicted stores were the largest single user
+            // of the shared-memory port in this kernel (2 passes x 49 per warp and block), the port the TMA ingest competes for.
+#define TC_V(k) __uint_as_float((k) < 32 ? v0[(k) & 31] : v1[((k) - 32) & 31])
+            const bool odd = (lane & 1) != 0;
+            stg[odd ? 0 : PP - 1] = from_f32<TOut>(odd ? TC_V(0) : TC_V(PP - 1));     // (only instantiated paths with 2-byte TOut get here)
+            uint32_t* stg32 = reinterpret_cast<uint32_t*>(stg + (odd ? 1 : 0));
 #pragma unroll
-          for (int k = 0; k < 32; ++k) stg[k] = from_f32<TOut>(__uint_as_float(v0[k]));
+            for (int i = 0; i < (PP - 1) / 2; ++i) {
+              const float lo = odd ? TC_V(2 * i + 1) : TC_V(2 * i), hi = odd ? TC_V(2 * i + 2) : TC_V(2 * i + 1);
+              const __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
+              stg32[i] = *reinterpret_cast<const uint32_t*>(&pk);
+            }
+#undef TC_V
+          } else {
 #pragma unroll
-          for (int k = 32; k < PP; ++k) stg[k] = from_f32<TOut>(__uint_as_float(v1[k - 32]));
+            for (int k = 0; k < 32; ++k) stg[k] = from_f32<TOut>(__uint_as_float(v0[k]));
+#pragma unroll
+            for (int k = 32; k < PP; ++k) stg[k] = from_f32<TOut>(__uint_as_float(v1[k - 32]));
+          }
           fence_proxy_async();
           named_bar_sync(2, 128);
           if (tid == 0 && !(dbg & 2)) {
