@@ -38,6 +38,7 @@ WORKLOAD = "daf_org_r50dc5_da_hot_path_1024x2048"
 C, H, W, STRIDE = 2048, 64, 128, 16
 ROIS_PER_IMG = 512
 FC_OUT = 1024
+ROI_LAYOUT_DEFAULT = "rchw"      # memory order of the RoI features in the timed step (see --roi-layout)
 
 
 def parse_args():
@@ -52,6 +53,8 @@ def parse_args():
     ap.add_argument("--no-chain-feed", action="store_true", help="A/B: the last shared FC as its own launches, not inside the chain kernel")
     ap.add_argument("--no-fused-tail", action="store_true", help="A/B: separate pixel-head / pixel-loss kernels instead of the fused tail")
     ap.add_argument("--no-f32-line", action="store_true", help="skip the nested line on the fp32-class engine (umma_bf16x6)")
+    ap.add_argument("--roi-layout", default=ROI_LAYOUT_DEFAULT, choices=["rchw", "rhwc"],
+                    help="memory order of the RoI features between RoIAlign and the first shared FC (rhwc = bin-major, [R,7,7,C])")
     ap.add_argument("--pairs-per-gpu", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="daf", choices=["daf", "maf", "fpn"],
@@ -148,7 +151,7 @@ def run_ours(args):
     torch.cuda.set_device(dev)
     out, act, step_ms, fused = measure_engine(args, args.engine, rank, local, world, sample_clocks=True)
     if rank == 0:
-        out["roofline"], out["kernels"] = kernel_rooflines(dev, act, step_ms, fused_step=fused)
+        out["roofline"], out["kernels"] = kernel_rooflines(dev, act, step_ms, fused_step=fused, roi_layout=args.roi_layout)
     if world == 1 and args.engine == "umma_bf16" and not args.no_f32_line:
         # second line of the same workload on the fp32-class tensor-core engine (exact 3-way bf16 split, 6 product terms on
         # tcgen05; the engine that meets the <= 1e-5 parity bar, tests/test_gpu_parity.py) -- nested, ONE JSON line is printed
@@ -186,7 +189,7 @@ def measure_engine(args, engine, rank, local, world, sample_clocks):
     pairs = args.pairs_per_gpu
 
     torch.manual_seed(0)
-    model = hotpath.DAFOrgHotPath(C, STRIDE, FC_OUT).to(dev).train()
+    model = hotpath.DAFOrgHotPath(C, STRIDE, FC_OUT, roi_layout=args.roi_layout).to(dev).train()
     params = ddist.trainable_parameters(model, model.unused_parameters())
     sgd = dict(lr=1e-3, momentum=0.9, weight_decay=5e-4)                      # reference recipe (faster_rcnn_r50_daf_c2f.py:8)
     peer_opt, sync_note = None, "none (1 GPU)"
@@ -395,7 +398,7 @@ def measure_engine(args, engine, rank, local, world, sample_clocks):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if engine == "umma_bf16" else "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "pairs_per_gpu": pairs, "c5": [2 * pairs, C, H, W], "rois_per_img": ROIS_PER_IMG,
-                   "engine": engine, "launch": graph_note, "grad_allreduce": sync_note, "step": "H1+L1, RoIAlign fwd/bwd, shared FCs, I1+L4, L7, backward, SGD",
+                   "engine": engine, "roi_layout": args.roi_layout, "launch": graph_note, "grad_allreduce": sync_note, "step": "H1+L1, RoIAlign fwd/bwd, shared FCs, I1+L4, L7, backward, SGD",
                    "l2_policy": "inputs_and_weights_exceed_L2 (C5 67MB/pair bf16, FC1 weight 411MB, RoI features 205MB); two input sets alternated"},
         "e2e": {"value": round(e2e_value, 3), "unit": "img-pairs/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4,
                 "ms_per_step": round(ms_e2e / args.steps, 4),
@@ -408,7 +411,7 @@ def measure_engine(args, engine, rank, local, world, sample_clocks):
     return out, act, ms_res / args.steps, bool(fuse)
 
 
-def kernel_rooflines(dev, act, step_ms, fused_step=True):
+def kernel_rooflines(dev, act, step_ms, fused_step=True, roi_layout=ROI_LAYOUT_DEFAULT):
     """Per-kernel timings of the step's hot kernels AT THE STEP'S SIZES (one pair: 2 images, 1024 RoIs), each
     alone, CUDA events on the launching stream, L2 flushed between launches.  Algorithmic bytes / flops per
     launch are the DESIGN.md §4 figures.  Returns (roofline of the dominant kernel, table)."""
@@ -457,15 +460,20 @@ def kernel_rooflines(dev, act, step_ms, fused_step=True):
             table[name]["note"] = note
 
     # RoIAlign 7x7 forward / backward: pooled tensor + feature map, each touched once
-    out = F_.roi_align(feat, rois, 7, 1.0 / STRIDE)
-    hbm_row("roi_align_fwd", time_it(lambda: F_.roi_align(feat, rois, 7, 1.0 / STRIDE)),
-            R * C * 49 * es + N * C * H * W * es + R * 20, "incl. the RoI prep kernel")
-    gout = torch.randn(out.shape, device=dev, generator=g).to(out.dtype)
-    fr = feat.detach().requires_grad_(True)
-    o2 = F_.roi_align(fr, rois, 7, 1.0 / STRIDE)
-    hbm_row("roi_align_bwd", time_it(lambda: torch.autograd.grad(o2, fr, gout, retain_graph=True)),
-            R * C * 49 * es + N * C * H * W * es + R * 20, "incl. the RoI prep kernel")
-    del out, o2, gout, fr, feat
+    for lay in (roi_layout, "rhwc" if roi_layout == "rchw" else "rchw"):
+        in_step = lay == roi_layout
+        sfx = "" if in_step else "_" + lay
+        note = "incl. the RoI prep kernel" + ("" if in_step else f"; RoI tensor in {lay} order (not the step's layout)")
+        out = F_.roi_align(feat, rois, 7, 1.0 / STRIDE, out_layout=lay)
+        hbm_row("roi_align_fwd" + sfx, time_it(lambda: F_.roi_align(feat, rois, 7, 1.0 / STRIDE, out_layout=lay)),
+                R * C * 49 * es + N * C * H * W * es + R * 20, note)
+        gout = torch.randn(out.shape, device=dev, generator=g).to(out.dtype)
+        fr = feat.detach().requires_grad_(True)
+        o2 = F_.roi_align(fr, rois, 7, 1.0 / STRIDE, out_layout=lay)
+        hbm_row("roi_align_bwd" + sfx, time_it(lambda: torch.autograd.grad(o2, fr, gout, retain_graph=True)),
+                R * C * 49 * es + N * C * H * W * es + R * 20, note)
+        del out, o2, gout, fr
+    del feat
     # FC1 of the shared head: [1024, 100352] x [100352 -> 1024], forward / data gradient / weight gradient
     K = C * 49
     x = torch.randn(R, 1, 1, K, device=dev, generator=g).to(torch.bfloat16)
@@ -533,9 +541,10 @@ def kernel_rooflines(dev, act, step_ms, fused_step=True):
     rois4 = torch.stack([(torch.arange(R4) // ROIS_PER_IMG).float(), x14, y14, torch.clamp(x14 + wh4[:, 0], max=W * STRIDE),
                          torch.clamp(y14 + wh4[:, 1], max=H * STRIDE)], 1).to(dev)
     b4 = R4 * C * 49 * es + N4 * C * H * W * es + R4 * 20
-    hbm_row("roi_align_fwd_config4", time_it(lambda: F_.roi_align(feat4, rois4, 7, 1.0 / STRIDE), 6), b4, "4 images, 2048 RoIs (BASELINE config 4)")
+    lay4 = roi_layout
+    hbm_row("roi_align_fwd_config4", time_it(lambda: F_.roi_align(feat4, rois4, 7, 1.0 / STRIDE, out_layout=lay4), 6), b4, "4 images, 2048 RoIs (BASELINE config 4)")
     fr4 = feat4.detach().requires_grad_(True)
-    o4 = F_.roi_align(fr4, rois4, 7, 1.0 / STRIDE)
+    o4 = F_.roi_align(fr4, rois4, 7, 1.0 / STRIDE, out_layout=lay4)
     go4 = torch.randn(o4.shape, device=dev, generator=g).to(o4.dtype)
     hbm_row("roi_align_bwd_config4", time_it(lambda: torch.autograd.grad(o4, fr4, go4, retain_graph=True), 6), b4, "4 images, 2048 RoIs (BASELINE config 4)")
     del feat4, fr4, o4, go4
@@ -578,7 +587,8 @@ def kernel_rooflines(dev, act, step_ms, fused_step=True):
     not_in_step = {"fc1_wgrad", "sgd_step_fc1"} if fused_step else {"fc1_wgrad_sgd", "sgd_step_fc1"}
     for k in table:
         table[k]["in_step"] = (k not in not_in_step and not k.startswith("da_conv_") and not k.endswith("_config4")
-                               and not k.startswith("nlb_") and not k.startswith("rpn_"))
+                               and not k.startswith("nlb_") and not k.startswith("rpn_")
+                               and not k.endswith("_rhwc") and not k.endswith("_rchw"))
     table["da_conv_h1_1x1_c5_fwd"]["in_step"] = table["da_conv_h1_1x1_c5_dgrad"]["in_step"] = table["da_conv_h1_1x1_c5_wgrad"]["in_step"] = True
     dom = max((k for k in table if table[k]["in_step"]), key=lambda k: table[k]["ms"])
     d = table[dom]

@@ -78,6 +78,70 @@ def test_roi_align_layouts_dtypes_and_module_surface(golden):
     assert rel_err(oc, torch.from_numpy(ref)) <= FP32_TOL
 
 
+@pytest.mark.parametrize("C,H,W,R,N", [(320, 33, 47, 300, 3), (256, 64, 128, 512, 2), (64, 20, 30, 63, 1), (2048, 64, 128, 1024, 2)])
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
+def test_roi_align_tensor_core_bin_major_layout_is_bit_identical(C, H, W, R, N, out_dtype):
+    """DA_ROI_OUT_RHWC on the tensor-core kernels ([R,7,7,C] RoI tensor: forward leaves through one tensor store per [49][128]
+    tile, backward fetches its gradient operand MN-major by TMA with the 15 pad bins zero-filled): the products and their
+    order are those of the [R,C,7,7] mode, so values and gradients must be BIT-identical to it (which the other tests pin to
+    the oracle), including ragged channel counts (C % 256 != 0), adversarial / empty RoIs and the bench size."""
+    if C == 2048 and out_dtype is torch.float32:
+        pytest.skip("bench size is covered in bf16")
+    stride = 16
+    feat = torch.relu(torch.randn(N, H, W, C, generator=torch.Generator().manual_seed(5))).to(DEV).bfloat16().permute(0, 3, 1, 2)
+    rois = torch.cat([seeded.synthetic_rois(R // N, N, H * stride, W * stride, 3),
+                      seeded.adversarial_rois(N, H * stride, W * stride)]).to(DEV)
+    rois = torch.cat([rois, torch.tensor([[-1.0, 0, 0, 64, 64], [float(N), 8, 8, 99, 99]], device=DEV)])   # not on any image: zeros
+    cot = torch.randn(rois.shape[0], C, 7, 7, generator=torch.Generator().manual_seed(6)).to(DEV).bfloat16()
+    res = {}
+    for layout in ("rchw", "rhwc"):
+        x = feat.detach().clone(memory_format=torch.preserve_format).requires_grad_(True)
+        out = F_.roi_align(x, rois, 7, 1.0 / stride, out_dtype=out_dtype, out_layout=layout)
+        g_in = cot if layout == "rchw" else cot.permute(0, 2, 3, 1).contiguous()
+        if layout == "rhwc":
+            assert out.shape == (rois.shape[0], 7, 7, C) and out.is_contiguous()
+        # bf16 cotangent in the layout of the output -> the tensor-core backward in both cases (fp32 outputs: forward only)
+        g = torch.autograd.grad(out, x, g_in)[0] if out_dtype is torch.bfloat16 else None
+        res[layout] = (out if layout == "rchw" else out.permute(0, 3, 1, 2), g)
+    assert res["rhwc"][0].dtype == out_dtype and float(res["rchw"][0].float().abs().max()) > 0
+    assert torch.equal(res["rchw"][0], res["rhwc"][0])
+    assert float(res["rchw"][0][-2:].float().abs().max()) == 0.0           # RoIs of no image: zeros in both layouts
+    if out_dtype is torch.bfloat16:
+        assert res["rchw"][1].dtype == torch.bfloat16 and float(res["rchw"][1].float().abs().max()) > 0
+        assert torch.equal(res["rchw"][1], res["rhwc"][1])
+
+
+def test_bin_major_hot_path_matches_reference_order_hot_path():
+    """hotpath.DAFOrgHotPath(roi_layout="rhwc") against the default layout on the same reference-order state_dict: same losses
+    and gradients up to the summation order of the first shared FC; load_state_dict / state_dict speak the reference's
+    (channel, bin) column order in both (convfc_bbox_head.py:229), the held weight is the (bin, channel) permutation."""
+    uda.set_engine("umma_bf16")
+    C, Hf, Wf = 256, 24, 40
+    ref_model = hotpath.DAFOrgHotPath(C, 16, 128).eval()
+    seeded.fill_state_(ref_model, 11, "binmajor.")
+    sd = ref_model.state_dict()
+    alt = hotpath.DAFOrgHotPath(C, 16, 128, roi_layout="rhwc").eval()
+    alt.load_state_dict(sd)
+    w_ref, w_alt = sd["bbox_head.shared_fcs.0.weight"], alt.bbox_head.shared_fcs[0].weight.detach()
+    assert torch.equal(w_alt.view(128, 49, C), w_ref.view(128, C, 49).transpose(1, 2))
+    assert all(torch.equal(v, alt.state_dict()[k]) for k, v in sd.items())
+    c5 = torch.relu(torch.randn(2, Hf, Wf, C, generator=torch.Generator().manual_seed(1))).to(DEV).bfloat16().permute(0, 3, 1, 2)
+    boxes = [seeded.synthetic_rois(96, 1, Hf * 16, Wf * 16, s)[:, 1:].to(DEV) for s in (1, 2)]
+    got = {}
+    for name, m in (("rchw", ref_model), ("rhwc", alt)):
+        m = m.to(DEV)
+        x = c5.detach().clone(memory_format=torch.preserve_format).requires_grad_(True)
+        losses = m.forward_train(x, boxes, [0, 1])
+        total, _ = hotpath.parse_losses(losses)
+        total.backward()
+        got[name] = ({k: float(v) for k, v in losses.items()}, x.grad.float(),
+                     m.bbox_head.to_reference_order(m.bbox_head.shared_fcs[0].weight.grad).float())
+    for k, v in got["rchw"][0].items():
+        assert abs(got["rhwc"][0][k] - v) <= 2e-3 * abs(v) + 1e-6, (k, v, got["rhwc"][0][k])
+    assert rel_err(got["rhwc"][1], got["rchw"][1]) <= BF16_TOL
+    assert float((got["rhwc"][2] - got["rchw"][2]).norm() / got["rchw"][2].norm()) <= BF16_TOL
+
+
 def test_roi_align_edge_cases():
     feat = seeded.seeded_tensor("edge.feat", (2, 6, 9, 11), 0).to(DEV)
     empty = F_.roi_align(feat, torch.zeros(0, 5, device=DEV), 7, 0.25)
@@ -677,8 +741,8 @@ def _bench_shape_inputs():
     return c5, boxes
 
 
-@pytest.mark.parametrize("engine", ["umma_bf16", "umma_bf16x6"])
-def test_daf_org_hot_path_at_bench_shape_vs_oracle(engine):
+@pytest.mark.parametrize("engine,roi_layout", [("umma_bf16", "rchw"), ("umma_bf16x6", "rchw"), ("umma_bf16", "rhwc")])
+def test_daf_org_hot_path_at_bench_shape_vs_oracle(engine, roi_layout):
     """The configuration bench.py times (hotpath.DAFOrgHotPath, C5 [2,2048,64,128], 2x512 RoIs, shared FC 100352 -> 1024 ->
     1024, InstanceAlignmentHead over the 1024 RoIs, L1 + L4 + L7, full backward) against the CPU oracle AT FULL SIZE:
     fp64 torch for heads / FCs / losses, oracle/roi_align_ref.c for RoIAlign forward and its transposed map.  Dropout off
@@ -701,8 +765,9 @@ def test_daf_org_hot_path_at_bench_shape_vs_oracle(engine):
     bf16 = engine == "umma_bf16"
     q = "bf16" if bf16 else None
     torch.manual_seed(0)
-    model = hotpath.DAFOrgHotPath(2048, 16, 1024).eval()
+    model = hotpath.DAFOrgHotPath(2048, 16, 1024, roi_layout=roi_layout).eval()
     seeded.fill_state_(model, 7, "bench.")                                  # O(1) activations everywhere (Q17)
+    # (roi_layout="rhwc": the first shared FC holds its columns in (bin, channel) order; state_dict() below is in the reference's)
     c5_nhwc, boxes = _bench_shape_inputs()
     if bf16:
         c5_nhwc = c5_nhwc.bfloat16().float()
@@ -791,7 +856,7 @@ def test_daf_org_hot_path_at_bench_shape_vs_oracle(engine):
     for k in ref:
         assert abs(float(losses[k]) - float(ref[k])) <= ltol * abs(float(ref[k])), (k, float(losses[k]), float(ref[k]))
     assert e_max <= gtol
-    dw1 = model.bbox_head.shared_fcs[0].weight.grad[rows.to(DEV)]
+    dw1 = model.bbox_head.to_reference_order(model.bbox_head.shared_fcs[0].weight.grad[rows.to(DEV)])
     assert float((dw1.double().cpu() - dw1_ref).norm() / dw1_ref.norm()) <= wtol
     for k, v in sd_ins.items():
         if v.grad is not None and v.dim() >= 2:

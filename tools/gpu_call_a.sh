@@ -1,0 +1,20 @@
+#!/bin/bash
+# one GPU call: the bin-major RoIAlign tests, then the step in both RoI layouts
+set -x
+cd "$GRAFT_REPO_ROOT" || exit 1
+mkdir -p gpurun_out
+timeout -s KILL 420 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "bin_major or roi_align" > gpurun_out/t_roi.log 2>&1; echo "rc=$?" >> gpurun_out/t_roi.log
+tail -5 gpurun_out/t_roi.log
+timeout -s KILL 200 python bench.py --no-cpu-baseline --no-f32-line --roi-layout rchw > gpurun_out/b_rchw.json 2> gpurun_out/b_rchw.err; echo "rc=$?"
+timeout -s KILL 200 python bench.py --no-cpu-baseline --no-f32-line --roi-layout rhwc > gpurun_out/b_rhwc.json 2> gpurun_out/b_rhwc.err; echo "rc=$?"
+python - <<'P'
+import json
+for n in ("rchw","rhwc"):
+    try:
+        d=json.loads(open(f"gpurun_out/b_{n}.json").read().strip().splitlines()[-1])
+        k=d["kernels"]
+        print(n, d["ms_per_step"], d["e2e"]["ms_per_step"], {x:(k[x]["ms"],k[x]["frac"]) for x in k if x.startswith("roi_align")})
+    except Exception as e:
+        print(n, "failed", e)
+P
+tail -3 gpurun_out/b_rhwc.err

@@ -73,6 +73,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// tensor store shared -> global (bulk async-group completion); out-of-bounds parts of the box are not written
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -230,5 +235,8 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
 // host: bf16 tensor map (rank 2..4, innermost dim first, 128B swizzle, zero OOB fill); umma_conv.cu
 int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                const uint32_t* box);
+// host: un-swizzled tensor map of 2-byte (bf16) or 4-byte (fp32) elements: dense shared-memory boxes (store side of RoIAlign)
+int encode_map_plain(CUtensorMap* m, const void* base, int elem_bytes, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box);
 
 }  // namespace da

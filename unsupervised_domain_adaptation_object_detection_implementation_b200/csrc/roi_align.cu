@@ -798,9 +798,9 @@ static int launch_fwd(const void* feat, int N, int C, int H, int W, int R, const
                       int layout, cudaStream_t st) {
   dim3 grid((C + FWD_CB - 1) / FWD_CB, R);
   // tensor-core path: bf16 features, reference layout, 16-byte granular channel runs
-  if (sizeof(TIn) == 2 && layout == DA_ROI_OUT_RCHW && C % 64 == 0 && ((uintptr_t)feat & 15) == 0 &&
+  if (sizeof(TIn) == 2 && C % 64 == 0 && ((uintptr_t)feat & 15) == 0 &&
       ((uintptr_t)out & 15) == 0 && !g_opt.roi_no_tc)
-    return roi_align_fwd_tc(feat, N, C, H, W, R, ws, out, sizeof(TOut) == 2 ? DA_BF16 : DA_F32, st);
+    return roi_align_fwd_tc(feat, N, C, H, W, R, ws, out, sizeof(TOut) == 2 ? DA_BF16 : DA_F32, layout, st);
   const int skip_tc = 0;
   // bulk-async path: every per-pixel channel run and the result tile must be 16-byte granular
   const bool async_ok = ((size_t)C * sizeof(TIn)) % 16 == 0 && ((uintptr_t)feat & 15) == 0 &&
@@ -847,7 +847,7 @@ extern "C" int da_roi_align_forward(const void* feat, int feat_dtype, int N, int
   DA_REQUIRE(feat_dtype != DA_BF16 || (C % 2 == 0), DA_ERR_UNSUPPORTED, "roi_align: bf16 features need even C");
   cudaStream_t st = (cudaStream_t)stream;
   // the footprint order is only read by the tensor-core forward (launch_fwd's first branch)
-  const int want_order = feat_dtype == DA_BF16 && out_layout == DA_ROI_OUT_RCHW && C % 64 == 0 && !g_opt.roi_no_tc;
+  const int want_order = feat_dtype == DA_BF16 && C % 64 == 0 && !g_opt.roi_no_tc;
   rc = run_prep(rois, R, N, H, W, spatial_scale, sampling_ratio, aligned, workspace, grid_out, st, want_order);
   if (rc) return rc;
   if (feat_dtype == DA_F32 && out_dtype == DA_F32) return launch_fwd<float, float>(feat, N, C, H, W, R, workspace, out, out_layout, st);
@@ -864,8 +864,9 @@ static int launch_bwd(const void* g, int layout, int N, int C, int H, int W, int
   dim3 grid(tiles_x * tiles_y, (C + BWD_CB - 1) / BWD_CB, N);
   DA_REQUIRE(grid.y <= 65535 && grid.z <= 65535, DA_ERR_UNSUPPORTED, "roi_align_backward: grid too large");
   // tensor-core path: bf16 gradients in the reference layout, 16-byte granular channel runs
-  if (sizeof(TG) == 2 && layout == DA_ROI_OUT_RCHW && C % 8 == 0 && ((uintptr_t)g & 15) == 0 && !g_opt.roi_no_tc)
-    return roi_align_bwd_tc(g, N, C, H, W, R, ws, gin_v, gin_dtype, st);
+  // ([R,7,7,C] gradients: the operand is fetched by TMA as it lies in memory, C % 64 == 0)
+  if (sizeof(TG) == 2 && C % (layout == DA_ROI_OUT_RCHW ? 8 : 64) == 0 && ((uintptr_t)g & 15) == 0 && !g_opt.roi_no_tc)
+    return roi_align_bwd_tc(g, layout, N, C, H, W, R, ws, gin_v, gin_dtype, st);
   DA_REQUIRE(gin_dtype == DA_F32, DA_ERR_UNSUPPORTED,
              "roi_align_backward: bf16 grad_input needs the tensor-core path (bf16 [R,C,7,7] gradients, C %% 8 == 0)");
   float* gin = static_cast<float*>(gin_v);

@@ -11,7 +11,14 @@
 // warps 2..17 = operand builders (double-buffered operand tiles) and, at the end, the epilogue that streams
 // TMEM to grad_input NHWC (lanes = consecutive channels: 128 B coalesced stores, every element written once).
 // The CUDA-core kernel (roi_align.cu) measured 8 % of HBM peak, issue bound (profiles/r01_roi_align_ncu.md).
+//
+// kRHWC = gradients in [R,7,7,C] order (DA_ROI_OUT_RHWC): the A operand is then MN-major AS IT LIES IN MEMORY.  One rank-4 TMA
+// box (64 ch, 64 bins of which 15 are out-of-bounds zero fill, 4 channel groups, 1 RoI) = 32 KB lands 128B-swizzled in a 4-deep
+// operand ring, no raw gradient ring and no relayout by the builders (the relayout's reads of 98-byte-pitch rows and its swizzled
+// stores were ~690 of the ~1600 shared-memory-port cycles per (RoI, tile) pair; profiles/r02_roi_bwd_pipeline_study.md).  The
+// builders only build the weight tile; the products and their order are the same as in the [R,C,7,7] mode: bit-identical results.
 #include <stdlib.h>
+#include <string.h>
 #include "da_common.cuh"
 #include "da_ptx.cuh"
 #include "roi_common.cuh"
@@ -42,6 +49,11 @@ constexpr int BT_RAW_BYTES = 64 + BT_RAW_G + (BT_TY + BT_TX) * WROW * 4 + 64;   
 constexpr int BT_PF = 8;                                       // L2 prefetch distance (pairs)
 constexpr int BT_NRAW = 3;                                     // raw ring depth (copy latency ~3 pair times)
 constexpr size_t BT_SMEM = 1024 + 2 * (size_t)BT_OPS_BYTES + BT_NRAW * (size_t)BT_RAW_BYTES + BT_LIST * 4 + 256;
+// kRHWC layout: [BT_NA][A 32 KB] | [2][B 32 KB] | [BT_NRAW][header | wy | wx] | list | barriers
+constexpr int BT_NA = 4;                                       // A (gradient) ring depth: TMA latency ~2 pair times inside the kernel
+constexpr int BT_RAWT_BYTES = 64 + (BT_TY + BT_TX) * WROW * 4 + 64;    // 1152 (128-multiple)
+constexpr size_t BT_SMEM_RHWC = 1024 + (size_t)BT_NA * 2 * BT_A_BYTES + 2 * (size_t)BT_B_BYTES + BT_NRAW * (size_t)BT_RAWT_BYTES + BT_LIST * 4 + 256;
+static_assert(BT_SMEM_RHWC <= 227 * 1024 && BT_NA * 2 * BT_A_BYTES >= BT_PX * BT_CH * 2, "epilogue staging overlays the A ring");
 
 // Work items = (image, pixel tile) x channel chunk; their cost is the number of RoIs touching the tile (0 ... 54 pairs at the bench
 // size), and the hardware hands CTAs out in index order: with tiles in raster order the last CTAs to start were heavy ones and
@@ -71,9 +83,9 @@ roi_tile_order_kernel(const unsigned char* __restrict__ ws, int R, int N, int H,
   }
 }
 
-template <typename TO, bool kTrace>
+template <typename TO, bool kTrace, bool kRHWC>
 __global__ void __launch_bounds__(BT_THREADS, 1)
-roi_align_bwd_tc_kernel(const __nv_bfloat16* __restrict__ grad_out, int C, int H, int W, int R,
+roi_align_bwd_tc_kernel(const __grid_constant__ CUtensorMap gmap, const __nv_bfloat16* __restrict__ grad_out, int C, int H, int W, int R,
                         const unsigned char* __restrict__ ws, TO* __restrict__ grad_in, int tiles_x, int dbg, unsigned long long* trace,
                         const int* __restrict__ item_order, int tiles, int chunks) {
   if (dbg & 32) return;
@@ -89,12 +101,15 @@ roi_align_bwd_tc_kernel(const __nv_bfloat16* __restrict__ grad_out, int C, int H
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t ops0 = base;                                   // [2][A0 | A1 | B]
-  const uint32_t raw0 = ops0 + 2 * BT_OPS_BYTES;                // [2] raw slots
-  int* list = reinterpret_cast<int*>(gen + 2 * BT_OPS_BYTES + BT_NRAW * BT_RAW_BYTES);
+  const uint32_t ops0 = base;                                   // [2][A0 | A1 | B]   (kRHWC: A ring, then the two B tiles)
+  constexpr int RAW_OFF = kRHWC ? BT_NA * 2 * BT_A_BYTES + 2 * BT_B_BYTES : 2 * BT_OPS_BYTES;
+  constexpr int RAW_PITCH = kRHWC ? BT_RAWT_BYTES : BT_RAW_BYTES;
+  constexpr int RAW_TAB = kRHWC ? 0 : BT_RAW_G;                 // offset of the table slices behind a slot's 64-byte header
+  const uint32_t raw0 = ops0 + RAW_OFF;                         // [BT_NRAW] raw slots
+  int* list = reinterpret_cast<int*>(gen + RAW_OFF + BT_NRAW * RAW_PITCH);
   const uint32_t bars = smem_u32(list + BT_LIST);
   const uint32_t raw_full0 = bars, raw_empty0 = bars + 32, ops_ready0 = bars + 64, ops_free0 = bars + 80,
-                 tfull = bars + 96, tslot = bars + 104;
+                 tfull = bars + 96, tslot = bars + 104, a_full0 = bars + 112, a_empty0 = bars + 144;
   volatile uint32_t* tslot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tslot - base));
   __shared__ int s_wcount[BT_ROUNDS * BT_WARPS];
   __shared__ int s_rows[2];     // per operand buffer: first tile row | (end tile row << 8) of the RoI's footprint in this tile
@@ -118,6 +133,11 @@ roi_align_bwd_tc_kernel(const __nv_bfloat16* __restrict__ grad_out, int C, int H
       mbar_init(ops_free0 + 8 * i, 1);
     }
     mbar_init(tfull, 1);
+    if (kRHWC)
+      for (int i = 0; i < BT_NA; ++i) {
+        mbar_init(a_full0 + 8 * i, 1);
+        mbar_init(a_empty0 + 8 * i, 1);
+      }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tslot, 512);
@@ -176,7 +196,7 @@ roi_align_bwd_tc_kernel(const __nv_bfloat16* __restrict__ grad_out, int C, int H
           my_m = metas[my_r];
         }
         // pull the gradient chunk of the pair BT_PF ring slots ahead into L2 (the ring itself only covers ~3 us)
-        if (lane == 3 && li + BT_PF < n_list && !(dbg & 128))
+        if (!kRHWC && lane == 3 && li + BT_PF < n_list && !(dbg & 128))
           bulk_prefetch_l2(grad_out + ((size_t)list[li + BT_PF] * C + c0) * PP, (uint32_t)(nch * PP * 2));
         const int src = li & 31;
         const int r = __shfl_sync(0xffffffffu, my_r, src);
@@ -190,8 +210,8 @@ roi_align_bwd_tc_kernel(const __nv_bfloat16* __restrict__ grad_out, int C, int H
         const int xa = max(m.x_lo, tx0), xb = min(m.x_lo + m.nx, tx1);
         mbar_wait(raw_empty0 + 8 * slot, par ^ 1u);
         if (lane == 0) PSTAMP(sq, 0);
-        uint8_t* sl = gen + 2 * BT_OPS_BYTES + slot * BT_RAW_BYTES;
-        const uint32_t g_bytes = (dbg & 16) ? 16u : (uint32_t)(nch * PP * 2);
+        uint8_t* sl = gen + RAW_OFF + slot * RAW_PITCH;
+        const uint32_t g_bytes = kRHWC ? 0u : (dbg & 16) ? 16u : (uint32_t)(nch * PP * 2);
         const uint32_t fb = raw_full0 + 8 * slot;
         if (lane == 0) {
           int* hdr = reinterpret_cast<int*>(sl);
@@ -201,23 +221,35 @@ roi_align_bwd_tc_kernel(const __nv_bfloat16* __restrict__ grad_out, int C, int H
         }
         __syncwarp();
         const float* tab = tables + (size_t)r * (H + W) * WROW;
-        const uint32_t sbase = raw0 + slot * BT_RAW_BYTES + 64;
-        if (lane == 0) bulk_g2s(sbase, grad_out + ((size_t)r * C + c0) * PP, g_bytes, fb);
-        if (lane == 1) bulk_g2s(sbase + BT_RAW_G, tab + (size_t)(ya - m.y_lo) * WROW, (uint32_t)(yb - ya) * WROW * 4, fb);
-        if (lane == 2) bulk_g2s(sbase + BT_RAW_G + BT_TY * WROW * 4, tab + (size_t)H * WROW + (size_t)(xa - m.x_lo) * WROW,
+        const uint32_t sbase = raw0 + slot * RAW_PITCH + 64;
+        if (!kRHWC && lane == 0) bulk_g2s(sbase, grad_out + ((size_t)r * C + c0) * PP, g_bytes, fb);
+        if (lane == 1) bulk_g2s(sbase + RAW_TAB, tab + (size_t)(ya - m.y_lo) * WROW, (uint32_t)(yb - ya) * WROW * 4, fb);
+        if (lane == 2) bulk_g2s(sbase + RAW_TAB + BT_TY * WROW * 4, tab + (size_t)H * WROW + (size_t)(xa - m.x_lo) * WROW,
                                 (uint32_t)(xb - xa) * WROW * 4, fb);
+        if (kRHWC) {
+          // the gradient chunk of the pair: box (64 ch, 64 bins, 4 channel groups, 1 RoI) -> smem [grp][bin][64 ch], swizzled;
+          // bins 49..63 and channel groups past C/64 are out of bounds = zero fill (counted in the transaction bytes)
+          const int aslot = sq % BT_NA;
+          mbar_wait(a_empty0 + 8 * aslot, ((uint32_t)(sq / BT_NA) & 1u) ^ 1u);
+          if (lane == 0) {
+            mbar_expect_tx(a_full0 + 8 * aslot, 2 * BT_A_BYTES);
+            tma_load_4d(ops0 + aslot * (2 * BT_A_BYTES), &gmap, a_full0 + 8 * aslot, 0, 0, c0 >> 6, r);
+          }
+        }
       }
     } else if (warp == 1) {
       // ------------------------------------------------ MMA issuer
       if (lane == 0) {
-        constexpr uint32_t idesc = make_idesc(128, BT_PX, 0, 0);
         for (int li = 0; li < n_list; ++li) {
           const int sq = seq + li, ob = sq & 1;
           const uint32_t par = (uint32_t)(sq >> 1) & 1u;
           mbar_wait(ops_ready0 + 8 * ob, par);
+          if (kRHWC) mbar_wait(a_full0 + 8 * (sq % BT_NA), (uint32_t)(sq / BT_NA) & 1u);
           PSTAMP(sq, 1);
           tc_fence_after();
           const uint32_t ops = ops0 + ob * BT_OPS_BYTES;
+          const uint32_t a_tile = kRHWC ? ops0 + (sq % BT_NA) * (2 * BT_A_BYTES) : ops;
+          const uint32_t b_tile = kRHWC ? ops0 + BT_NA * 2 * BT_A_BYTES + ob * BT_B_BYTES : ops + 2 * BT_A_BYTES;
           // Only the tile rows the RoI touches take part: N = 16 px x (rows touched) instead of the whole 16x16 tile (the
           // weight rows of the other pixels are zero, and are not even built any more).  The very first pair of the CTA runs
           // the full N = 256 with accumulate = 0: it is what initialises both TMEM accumulators.
@@ -227,16 +259,18 @@ roi_align_bwd_tc_kernel(const __nv_bfloat16* __restrict__ grad_out, int C, int H
             r0 = rr & 255;
             nrows = (rr >> 8) - r0;
           }
-          const uint32_t idesc_n = sq > 0 ? make_idesc(128, BT_TX * nrows, 0, 0) : idesc;
-          const uint64_t bd = desc_kmajor_sw128(ops + 2 * BT_A_BYTES + (uint32_t)r0 * (BT_TX * 128));
+          // kRHWC: A is MN-major (channels contiguous): 64-channel groups 8 KB apart (LBO), 8-bin atoms 1 KB apart, 16 bins = 2 KB per k-step
+          const uint32_t idesc_n = make_idesc(128, sq > 0 ? BT_TX * nrows : BT_PX, kRHWC ? 1 : 0, 0);
+          const uint64_t bd = desc_kmajor_sw128(b_tile + (uint32_t)r0 * (BT_TX * 128));
 #pragma unroll
           for (int cb = 0; cb < 2; ++cb) {
-            const uint64_t ad = desc_kmajor_sw128(ops + cb * BT_A_BYTES);
+            const uint64_t ad = kRHWC ? desc_mnmajor_sw128(a_tile + cb * BT_A_BYTES, 8192) : desc_kmajor_sw128(a_tile + cb * BT_A_BYTES);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
-              if (!(dbg & 1)) umma_bf16(tmem_base + cb * BT_PX + r0 * BT_TX, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc_n, (sq > 0 || kk > 0) ? 1u : 0u);
+              if (!(dbg & 1)) umma_bf16(tmem_base + cb * BT_PX + r0 * BT_TX, ad + (uint64_t)(kk * (kRHWC ? 128 : 2)), bd + (uint64_t)(kk * 2), idesc_n, (sq > 0 || kk > 0) ? 1u : 0u);
           }
           umma_commit(ops_free0 + 8 * ob);
+          if (kRHWC) umma_commit(a_empty0 + 8 * (sq % BT_NA));
           PSTAMP(sq, 2);
         }
       }
@@ -255,16 +289,17 @@ roi_align_bwd_tc_kernel(const __nv_bfloat16* __restrict__ grad_out, int C, int H
         if (bt == 0) PSTAMP(sq, 3);
         mbar_wait(ops_free0 + 8 * ob, ((uint32_t)(sq >> 1) & 1u) ^ 1u);
         if (bt == 0) PSTAMP(sq, 4);
-        const uint8_t* sl = gen + 2 * BT_OPS_BYTES + slot * BT_RAW_BYTES;
+        const uint8_t* sl = gen + RAW_OFF + slot * RAW_PITCH;
         const int* hdr = reinterpret_cast<const int*>(sl);
         const int ya = hdr[0], yb = hdr[1], xa = hdr[2], xb = hdr[3];
         const float inv_count = reinterpret_cast<const float*>(sl)[4];
-        const float* wy_s = reinterpret_cast<const float*>(sl + 64 + BT_RAW_G);
+        const float* wy_s = reinterpret_cast<const float*>(sl + 64 + RAW_TAB);
         const float* wx_s = wy_s + BT_TY * WROW;
         uint8_t* ops = gen + ob * BT_OPS_BYTES;
+        uint8_t* b_ops = kRHWC ? gen + BT_NA * 2 * BT_A_BYTES + ob * BT_B_BYTES : ops + 2 * BT_A_BYTES;
         // (1) A: 49 bf16 of channel `row` -> 64 (zero padded), 128B-swizzled K-major row.  Rows start on
         // 2-byte boundaries (98 B pitch): read aligned words and funnel-shift by 0 or 16 bits.
-        {
+        if constexpr (!kRHWC) {
           const int cb = row >> 7, mrow = row & 127;
           uint32_t pk[16];
           if (row < nch && !(dbg & 2)) {
@@ -327,7 +362,7 @@ roi_align_bwd_tc_kernel(const __nv_bfloat16* __restrict__ grad_out, int C, int H
               }
             }
           }
-          uint8_t* brow = ops + 2 * BT_A_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
+          uint8_t* brow = b_ops + (row >> 3) * 1024 + (row & 7) * 128;
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             *reinterpret_cast<uint4*>(brow + (((half * 4 + k) ^ (row & 7)) << 4)) = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
@@ -413,12 +448,23 @@ roi_align_bwd_tc_kernel(const __nv_bfloat16* __restrict__ grad_out, int C, int H
   }
 }
 
-template <typename TO>
+template <typename TO, bool kRHWC>
 static int launch_bwd_tc(const void* grad_out, int N, int C, int H, int W, int R, const void* ws, void* grad_in, cudaStream_t st) {
   const int tiles_x = (W + BT_TX - 1) / BT_TX, tiles_y = (H + BT_TY - 1) / BT_TY;
   const int tiles = tiles_x * tiles_y, chunks = (C + BT_CH - 1) / BT_CH;
   DA_REQUIRE((long long)N * tiles * chunks <= 0x7fffffffll, DA_ERR_UNSUPPORTED, "roi_align_backward tc: grid too large");
   dim3 grid((unsigned)(N * tiles * chunks));
+  CUtensorMap gmap;
+  memset(&gmap, 0, sizeof(gmap));
+  if (kRHWC) {
+    // grad_out [R][49][C] viewed as (64 ch, 49 bins, C/64 groups, R): one box = the [64 bins][256 ch] chunk of a (RoI, CTA) pair
+    DA_REQUIRE(C % 64 == 0, DA_ERR_UNSUPPORTED, "roi_align_backward tc ([R,7,7,C] gradients): C must be a multiple of 64");
+    const uint64_t dims[4] = {64, (uint64_t)PP, (uint64_t)(C / 64), (uint64_t)R};
+    const uint64_t strides[3] = {(uint64_t)C * 2, 128, (uint64_t)PP * C * 2};
+    const uint32_t box[4] = {64, 64, BT_CH / 64, 1};
+    int rc = encode_map(&gmap, grad_out, 4, dims, strides, box);
+    if (rc) return rc;
+  }
   // longest-processing-time-first order of the (image, tile) items; the list lives in the workspace's RoI-order region (only the
   // forward reads that one, and every forward rewrites it)
   int* item_order = nullptr;
@@ -429,27 +475,32 @@ static int launch_bwd_tc(const void* grad_out, int N, int C, int H, int W, int R
   }
   const int dbg = g_opt.roi_bwd_dbg;   // timing experiments only (results are wrong when set)
   unsigned long long* trace = reinterpret_cast<unsigned long long*>(g_opt.roi_bwd_trace);   // tools/trace_roi_bwd.py
-  static bool attr_set_dev[kMaxDevices] = {};     // function attributes are per device
+  constexpr size_t smem = kRHWC ? BT_SMEM_RHWC : BT_SMEM;
+  static bool attr_set_dev[kMaxDevices] = {};     // function attributes are per device (one flag array per instantiation)
   bool& attr_set = attr_set_dev[cur_dev()];
   if (!attr_set) {
-    DA_CUDA_OK(cudaFuncSetAttribute(roi_align_bwd_tc_kernel<TO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BT_SMEM));
-    DA_CUDA_OK(cudaFuncSetAttribute(roi_align_bwd_tc_kernel<TO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BT_SMEM));
+    DA_CUDA_OK(cudaFuncSetAttribute(roi_align_bwd_tc_kernel<TO, false, kRHWC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DA_CUDA_OK(cudaFuncSetAttribute(roi_align_bwd_tc_kernel<TO, true, kRHWC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   if (trace)
-    roi_align_bwd_tc_kernel<TO, true><<<grid, BT_THREADS, BT_SMEM, st>>>((const __nv_bfloat16*)grad_out, C, H, W, R, (const unsigned char*)ws,
-                                                                           static_cast<TO*>(grad_in), tiles_x, dbg, trace, item_order, tiles, chunks);
+    roi_align_bwd_tc_kernel<TO, true, kRHWC><<<grid, BT_THREADS, smem, st>>>(gmap, (const __nv_bfloat16*)grad_out, C, H, W, R, (const unsigned char*)ws,
+                                                                                 static_cast<TO*>(grad_in), tiles_x, dbg, trace, item_order, tiles, chunks);
   else
-    roi_align_bwd_tc_kernel<TO, false><<<grid, BT_THREADS, BT_SMEM, st>>>((const __nv_bfloat16*)grad_out, C, H, W, R, (const unsigned char*)ws,
-                                                                            static_cast<TO*>(grad_in), tiles_x, dbg, trace, item_order, tiles, chunks);
+    roi_align_bwd_tc_kernel<TO, false, kRHWC><<<grid, BT_THREADS, smem, st>>>(gmap, (const __nv_bfloat16*)grad_out, C, H, W, R, (const unsigned char*)ws,
+                                                                                  static_cast<TO*>(grad_in), tiles_x, dbg, trace, item_order, tiles, chunks);
   DA_LAUNCH_CHECK();
   return DA_OK;
 }
 
-int roi_align_bwd_tc(const void* grad_out, int N, int C, int H, int W, int R, const void* ws, void* grad_in, int grad_in_dtype,
+int roi_align_bwd_tc(const void* grad_out, int layout, int N, int C, int H, int W, int R, const void* ws, void* grad_in, int grad_in_dtype,
                      cudaStream_t st) {
-  if (grad_in_dtype == DA_BF16) return launch_bwd_tc<__nv_bfloat16>(grad_out, N, C, H, W, R, ws, grad_in, st);
-  return launch_bwd_tc<float>(grad_out, N, C, H, W, R, ws, grad_in, st);
+  if (layout == DA_ROI_OUT_RHWC) {
+    if (grad_in_dtype == DA_BF16) return launch_bwd_tc<__nv_bfloat16, true>(grad_out, N, C, H, W, R, ws, grad_in, st);
+    return launch_bwd_tc<float, true>(grad_out, N, C, H, W, R, ws, grad_in, st);
+  }
+  if (grad_in_dtype == DA_BF16) return launch_bwd_tc<__nv_bfloat16, false>(grad_out, N, C, H, W, R, ws, grad_in, st);
+  return launch_bwd_tc<float, false>(grad_out, N, C, H, W, R, ws, grad_in, st);
 }
 
 }  // namespace da

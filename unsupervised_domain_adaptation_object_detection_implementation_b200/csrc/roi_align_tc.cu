@@ -26,6 +26,7 @@
 #include "da_ptx.cuh"
 #include "roi_common.cuh"
 #include <stdlib.h>
+#include <string.h>
 
 namespace da {
 
@@ -87,9 +88,11 @@ __device__ __forceinline__ int sched_pop(uint32_t sfull0, uint32_t sempty0, cons
   return r;
 }
 
-template <typename TOut>
+// kRHWC: out is [R,7,7,C] (DA_ROI_OUT_RHWC): the [49][128] result tile is staged bin-major and leaves through ONE tensor store
+// (box 128 ch x 49 bins of the [R*49, C] view); MMAs and their order are those of the [R,C,7,7] mode: bit-identical values.
+template <typename TOut, bool kRHWC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-roi_align_fwd_tc_kernel(const __grid_constant__ CUtensorMap fmap, int C, int H, int W, int R,
+roi_align_fwd_tc_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_constant__ CUtensorMap omap, int C, int H, int W, int R,
                         const unsigned char* __restrict__ ws, TOut* __restrict__ out, int dbg) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -301,7 +304,21 @@ roi_align_fwd_tc_kernel(const __grid_constant__ CUtensorMap fmap, int C, int H, 
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty0 + 8 * (accb + j));
-          TOut* stg = reinterpret_cast<TOut*>(gen + (stage0 - base) + sb * STG) + (size_t)(q * 32 + lane) * PP;
+          TOut* stg = reinterpret_cast<TOut*>(gen + (stage0 - base) + sb * STG) + (size_t)(q * 32 + lane) * (kRHWC ? 1 : PP);
+          if constexpr (kRHWC) {
+            // bin-major staging [49][128 ch]: a warp's store covers 32 consecutive channels of one bin (conflict-free)
+#pragma unroll
+            for (int k = 0; k < 32; ++k) stg[k * TC_MCH] = from_f32<TOut>(__uint_as_float(v0[k]));
+#pragma unroll
+            for (int k = 32; k < PP; ++k) stg[k * TC_MCH] = from_f32<TOut>(__uint_as_float(v1[k - 32]));
+            fence_proxy_async();
+            named_bar_sync(2, 128);
+            if (tid == 0 && !(dbg & 2)) {
+              tma_store_2d(&omap, stage0 + sb * STG, mb * TC_MCH, r * PP);     // channels past C are clipped by the tensor map
+              bulk_commit();
+            }
+            continue;
+          }
           bool packed = false;
           if constexpr (sizeof(TOut) == 2) packed = !(dbg & 4);       // bit 2 of roi_fwd_dbg: the old 2-byte stores (A/B)
           if (packed) {
@@ -345,22 +362,32 @@ roi_align_fwd_tc_kernel(const __grid_constant__ CUtensorMap fmap, int C, int H, 
   }
 }
 
-template <typename TOut>
+template <typename TOut, bool kRHWC>
 static int launch_tc(const CUtensorMap& fmap, int C, int H, int W, int R, const void* ws, void* out, cudaStream_t st) {
   const size_t smem = tc_smem_bytes<TOut>(H, W);
   DA_REQUIRE(smem <= 227 * 1024, DA_ERR_UNSUPPORTED, "roi_align tc: H+W too large for shared memory");
-  auto k = roi_align_fwd_tc_kernel<TOut>;
+  CUtensorMap omap;
+  memset(&omap, 0, sizeof(omap));
+  if (kRHWC) {
+    DA_REQUIRE((long long)R * PP <= 0x7fffffffll, DA_ERR_UNSUPPORTED, "roi_align tc: too many RoIs");
+    const uint64_t dims[2] = {(uint64_t)C, (uint64_t)R * PP};
+    const uint64_t strides[1] = {(uint64_t)C * sizeof(TOut)};
+    const uint32_t box[2] = {TC_MCH, PP};
+    int rc = encode_map_plain(&omap, out, (int)sizeof(TOut), 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  auto k = roi_align_fwd_tc_kernel<TOut, kRHWC>;
   DA_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // the footprint-sorted RoI order was left in the workspace by the last block of roi_prep_kernel
   const int grid = R < num_sms() ? R : num_sms();
-  k<<<grid, TC_THREADS, smem, st>>>(fmap, C, H, W, R, (const unsigned char*)ws, (TOut*)out, g_opt.roi_fwd_dbg);
+  k<<<grid, TC_THREADS, smem, st>>>(fmap, omap, C, H, W, R, (const unsigned char*)ws, (TOut*)out, g_opt.roi_fwd_dbg);
   DA_LAUNCH_CHECK();
   return DA_OK;
 }
 
 // Requires C % 64 == 0: the channel axis is viewed as (C/64 groups) x 64 so that one rank-4 box
 // (64 ch, 4 px, 4 rows, 8 groups) fetches a quad for 512 channels.
-int roi_align_fwd_tc(const void* feat, int N, int C, int H, int W, int R, const void* ws, void* out, int out_dtype,
+int roi_align_fwd_tc(const void* feat, int N, int C, int H, int W, int R, const void* ws, void* out, int out_dtype, int layout,
                      cudaStream_t st) {
   CUtensorMap fmap;
   const uint64_t dims[4] = {64, (uint64_t)W, (uint64_t)N * H, (uint64_t)(C / 64)};
@@ -368,8 +395,12 @@ int roi_align_fwd_tc(const void* feat, int N, int C, int H, int W, int R, const 
   const uint32_t box[4] = {64, 4, 4, 2 * TC_GB};
   int rc = encode_map(&fmap, feat, 4, dims, strides, box);
   if (rc) return rc;
-  if (out_dtype == DA_BF16) return launch_tc<__nv_bfloat16>(fmap, C, H, W, R, ws, out, st);
-  return launch_tc<float>(fmap, C, H, W, R, ws, out, st);
+  if (layout == DA_ROI_OUT_RHWC) {
+    if (out_dtype == DA_BF16) return launch_tc<__nv_bfloat16, true>(fmap, C, H, W, R, ws, out, st);
+    return launch_tc<float, true>(fmap, C, H, W, R, ws, out, st);
+  }
+  if (out_dtype == DA_BF16) return launch_tc<__nv_bfloat16, false>(fmap, C, H, W, R, ws, out, st);
+  return launch_tc<float, false>(fmap, C, H, W, R, ws, out, st);
 }
 
 }  // namespace da

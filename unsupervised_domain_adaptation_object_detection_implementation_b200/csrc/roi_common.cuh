@@ -30,8 +30,8 @@ __host__ __device__ inline size_t ws_order_off(int R, int H, int W) {
 // tensor-core forward (roi_align_tc.cu) handles every RoI with a non-empty footprint
 __host__ __device__ inline bool roi_tc_eligible(const RoiMeta& m) { return m.ny > 0 && m.nx > 0; }
 
-int roi_align_bwd_tc(const void* grad_out, int N, int C, int H, int W, int R, const void* ws, void* grad_in, int grad_in_dtype, cudaStream_t st);
-int roi_align_fwd_tc(const void* feat, int N, int C, int H, int W, int R, const void* ws, void* out, int out_dtype,
+int roi_align_bwd_tc(const void* grad_out, int layout, int N, int C, int H, int W, int R, const void* ws, void* grad_in, int grad_in_dtype, cudaStream_t st);
+int roi_align_fwd_tc(const void* feat, int N, int C, int H, int W, int R, const void* ws, void* out, int out_dtype, int layout,
                      cudaStream_t st);
 
 }  // namespace da

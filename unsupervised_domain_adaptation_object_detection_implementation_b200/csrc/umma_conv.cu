@@ -1009,6 +1009,26 @@ int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
   return DA_OK;
 }
 
+int encode_map_plain(CUtensorMap* m, const void* base, int elem_bytes, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box) {
+  EncodeTiledFn fn = get_encode();
+  DA_REQUIRE(fn != nullptr, DA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  DA_REQUIRE(elem_bytes == 2 || elem_bytes == 4, DA_ERR_INVALID_ARG, "tensor map: element size %d", elem_bytes);
+  cuuint64_t gd[5];
+  cuuint64_t gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i < rank - 1; ++i) gs[i] = strides_bytes[i];
+  DA_REQUIRE(((uintptr_t)base & 15) == 0, DA_ERR_INVALID_ARG, "tensor map base %p is not 16-byte aligned", base);
+  for (int i = 0; i < rank - 1; ++i)
+    DA_REQUIRE((gs[i] & 15) == 0, DA_ERR_UNSUPPORTED, "tensor map stride %llu is not a multiple of 16 bytes", (unsigned long long)gs[i]);
+  CUresult r = fn(m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
+                  const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DA_REQUIRE(r == CUDA_SUCCESS, DA_ERR_CUDA, "cuTensorMapEncodeTiled (plain) failed with CUresult %d", (int)r);
+  return DA_OK;
+}
+
 static inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 static inline int posmod(int a, int b) { int m = a % b; return m < 0 ? m + b : m; }
 static inline int ilog2(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }

@@ -226,7 +226,8 @@ class RoIAlignFunction(Function):
         gout = gout.contiguous()
         # bf16 features + bf16 [R,C,7,7] gradients: the tensor-core kernel rounds its fp32 accumulators once and
         # writes bf16 directly (no fp32 staging tensor, no cast pass)
-        direct = fdtype == torch.bfloat16 and gout.dtype == torch.bfloat16 and layout == 0 and C % 8 == 0 and R > 0 \
+        # ([R,7,7,C] gradients: the kernel's TMA fetches the operand as it lies in memory; needs C % 64 == 0)
+        direct = fdtype == torch.bfloat16 and gout.dtype == torch.bfloat16 and C % (8 if layout == 0 else 64) == 0 and R > 0 \
             and not _OPTIONS.get("roi_no_tc")
         gin = torch.empty((N, H, W, C), dtype=torch.bfloat16 if direct else torch.float32, device=gout.device)
         ws = workspace(lib.da_roi_align_workspace_bytes(R, H, W), gout.device, "roi")

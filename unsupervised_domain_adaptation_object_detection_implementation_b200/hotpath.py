@@ -59,16 +59,62 @@ class SharedFCs(nn.Module):
     (mmdet/models/roi_heads/bbox_heads/convfc_bbox_head.py:198-237): flatten(1) -> FC -> ReLU -> FC -> ReLU.
     Adjacent to the hot path; it produces the 1024-d features the instance head consumes."""
 
-    def __init__(self, in_channels=2048, roi_feat_size=7, fc_out_channels=1024, num_shared_fcs=2):
+    def __init__(self, in_channels=2048, roi_feat_size=7, fc_out_channels=1024, num_shared_fcs=2, roi_layout="rchw"):
+        """roi_layout="rhwc": the RoI features arrive bin-major ([R,7,7,C] memory, logical [R,C,7,7]) and the first FC's
+        weight is HELD with its input columns in (bin, channel) order, so that `flatten` is a view and the tensor-core RoIAlign
+        backward gets its operand as it lies in memory.  state_dict()/load_state_dict() still speak the
+        reference's (channel, bin) column order (convfc_bbox_head.py:229: `x.flatten(1)` of [R,C,7,7]); the optimizer is
+        elementwise, so training in the permuted order is the same training."""
         super().__init__()
+        if roi_layout not in ("rchw", "rhwc"):
+            raise ValueError(f"roi_layout {roi_layout!r}")
+        self.roi_layout = roi_layout
+        self.in_channels, self.bins = in_channels, roi_feat_size * roi_feat_size
         dims = [in_channels * roi_feat_size * roi_feat_size] + [fc_out_channels] * num_shared_fcs
         self.shared_fcs = nn.ModuleList([nn.Linear(dims[i], dims[i + 1]) for i in range(num_shared_fcs)])
         for fc in self.shared_fcs:
             nn.init.xavier_uniform_(fc.weight)
             nn.init.constant_(fc.bias, 0)
+        if roi_layout == "rhwc":
+            with torch.no_grad():
+                self.shared_fcs[0].weight.copy_(self.to_held_order(self.shared_fcs[0].weight))
+            self._register_state_dict_hook(SharedFCs._export_reference_order)
+            self._register_load_state_dict_pre_hook(self._import_reference_order)
+
+    # ---- (channel, bin) <-> (bin, channel) column order of the first FC (roi_layout="rhwc" only)
+    def to_held_order(self, w):
+        """[out, C*49] in the reference's (channel, bin) column order -> the order this module holds."""
+        if self.roi_layout != "rhwc":
+            return w
+        return w.reshape(w.shape[0], self.in_channels, self.bins).transpose(1, 2).reshape(w.shape[0], -1)
+
+    def to_reference_order(self, w):
+        """Inverse of to_held_order (weights, gradients and momentum buffers of shared_fcs[0].weight alike)."""
+        if self.roi_layout != "rhwc":
+            return w
+        return w.reshape(w.shape[0], self.bins, self.in_channels).transpose(1, 2).reshape(w.shape[0], -1)
+
+    @staticmethod
+    def _export_reference_order(module, state_dict, prefix, local_metadata):
+        key = prefix + "shared_fcs.0.weight"
+        if key in state_dict:
+            state_dict[key] = module.to_reference_order(state_dict[key])
+
+    def _import_reference_order(self, state_dict, prefix, *args):
+        key = prefix + "shared_fcs.0.weight"
+        if key in state_dict and state_dict[key].dim() == 2 and state_dict[key].shape[1] == self.in_channels * self.bins:
+            state_dict[key] = self.to_held_order(state_dict[key])
+
+    def _flatten(self, x):
+        if self.roi_layout == "rhwc":
+            if x.dim() != 4:
+                raise RuntimeError("SharedFCs(roi_layout='rhwc') takes the [R,C,7,7] RoI features, not a flattened tensor")
+            x = x.permute(0, 2, 3, 1)                     # a view when the RoI tensor is bin-major; else one re-layout pass
+            return x.reshape(x.shape[0], -1)
+        return x.flatten(1)
 
     def forward(self, x):
-        x = F_.cast(x.flatten(1), F_.act_dtype())
+        x = F_.cast(self._flatten(x), F_.act_dtype())
         k = x.shape[0]
         x = x.view(k, 1, 1, -1)
         for fc in self.shared_fcs:
@@ -86,7 +132,7 @@ class SharedFCs(nn.Module):
         head's chain kernel runs it (forward and backward), applies the ReLU derivative of the layer before it and returns
         that layer's bias gradient, so the layer before runs with preact_grad=True (no activation-backward / bias-sum kernels).
         Only for callers whose ONLY consumer of the shared features is the instance head (the hot path)."""
-        x = F_.cast(x.flatten(1), F_.act_dtype())
+        x = F_.cast(self._flatten(x), F_.act_dtype())
         k = x.shape[0]
         x = x.view(k, 1, 1, -1)
         fcs = list(self.shared_fcs)
@@ -109,13 +155,19 @@ def instance_branch(bbox_head, local_da, roi_feats, label_da):
 
 class DAFOrgHotPath(nn.Module):
     def __init__(self, in_channels=2048, featmap_stride=16, fc_out_channels=1024,
-                 lambdas=(0.1, 0.1, 0.1), with_shared_fcs=True):
+                 lambdas=(0.1, 0.1, 0.1), with_shared_fcs=True, roi_layout="rchw"):
+        """roi_layout="rhwc": RoI features bin-major between RoIAlign and the first shared FC (see SharedFCs); same losses and
+        gradients up to the summation order of that FC's 100352-long dot products."""
         super().__init__()
+        if roi_layout == "rhwc" and not with_shared_fcs:
+            raise ValueError("roi_layout='rhwc' needs the shared FCs (they hold the permuted weight)")
         self.da_head_top = da_heads.ImgAlignmentHead(in_channels)
         self.da_head_top._init_weights()
         self.bbox_roi_extractor = SingleRoIExtractor(dict(type="RoIAlign", output_size=7, sampling_ratio=0),
                                                      out_channels=in_channels, featmap_strides=[featmap_stride])
-        self.bbox_head = SharedFCs(in_channels, 7, fc_out_channels) if with_shared_fcs else None
+        for layer in self.bbox_roi_extractor.roi_layers:
+            layer.out_layout = roi_layout
+        self.bbox_head = SharedFCs(in_channels, 7, fc_out_channels, roi_layout=roi_layout) if with_shared_fcs else None
         self.local_da = da_heads.InstanceAlignmentHead()
         self.local_da._init_weights()
         self.global_lamda, self.local_lamda, self.consist_lamda = lambdas

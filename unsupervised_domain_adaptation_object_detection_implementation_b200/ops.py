@@ -27,9 +27,15 @@ class RoIAlign(nn.Module):
         self.pool_mode = pool_mode
         self.aligned = aligned
         self.use_torchvision = use_torchvision
+        # "rhwc": the SAME logical [R,C,7,7] result, stored bin-major ([R,7,7,C] memory = torch.channels_last).  Not part of
+        # mmcv's signature: set by callers that consume channels-last RoI features (hotpath.SharedFCs, roi_layout="rhwc").
+        self.out_layout = "rchw"
 
     def forward(self, input, rois):
         """input: NCHW feature map; rois: [R,5] (batch_index, x1, y1, x2, y2)."""
+        if self.out_layout == "rhwc":
+            return F_.roi_align(input, rois, self.output_size, self.spatial_scale, self.sampling_ratio, self.aligned,
+                                out_layout="rhwc").permute(0, 3, 1, 2)
         return F_.roi_align(input, rois, self.output_size, self.spatial_scale, self.sampling_ratio, self.aligned)
 
     def __repr__(self):
