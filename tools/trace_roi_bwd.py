@@ -9,8 +9,11 @@ N, C, H, W, R = 2, int(os.environ.get('TRACE_C', 2048)), 64, 128, 1024
 g = torch.Generator(device=dev).manual_seed(0)
 feat = torch.relu(torch.randn(N, H, W, C, device=dev, generator=g)).to(torch.bfloat16).permute(0, 3, 1, 2).requires_grad_(True)
 rois = seeded.synthetic_rois(R // N, N, H * 16, W * 16, 0).to(dev)
+LAYOUT = os.environ.get("TRACE_LAYOUT", "rchw")      # rhwc: bin-major RoI tensor (TMA-fed MN-major gradient operand)
 cot = torch.randn(R, C, 7, 7, device=dev, generator=g).to(torch.bfloat16)
-out = F_.roi_align(feat, rois, 7, 1 / 16)
+if LAYOUT == "rhwc":
+    cot = cot.permute(0, 2, 3, 1).contiguous()
+out = F_.roi_align(feat, rois, 7, 1 / 16, out_layout=LAYOUT)
 for _ in range(3): torch.autograd.grad(out, feat, cot, retain_graph=True)
 ncta = 32 * (C // 256) * N
 buf = torch.zeros(ncta + 64, 8, dtype=torch.int64, device=dev)

@@ -88,6 +88,7 @@ roi_prep_kernel(const float* __restrict__ rois, int R, int N, int H, int W,
   int lo = 0x7fffffff, hi = -1;
   if (lane < P) axis_samples(x1, bw, gw_s, lane, W, 0, 0, nullptr, lo, hi);
   else if (lane >= 8 && lane < 8 + P) axis_samples(y1, bh, gh_s, lane - 8, H, 0, 0, nullptr, lo, hi);
+  const int bin_lo = lo, bin_hi = hi;     // lanes 8..14: first / last map row bin (lane - 8) touches (0x7fffffff / -1: none)
   // segmented (8-lane) min / max
 #pragma unroll
   for (int o = 4; o > 0; o >>= 1) {
@@ -110,6 +111,27 @@ roi_prep_kernel(const float* __restrict__ rois, int R, int N, int H, int W,
     int d0, d1;
     if (lane < P) axis_samples(x1, bw, gw_s, lane, W, 1, x_lo, wx, d0, d1);
     else if (lane >= 8 && lane < 8 + P) axis_samples(y1, bh, gh_s, lane - 8, H, 1, y_lo, wy, d0, d1);
+  }
+  {
+    // Pad column of the Wy rows: for map row y, (first bin row reaching y or beyond) | (1 + last bin row starting at y or
+    // before) << 8.  A pixel tile covering rows [ya, yb) then needs only the bin rows [first(ya), last(yb - 1)] of this RoI
+    // (a superset of the intersecting ones whatever the orientation): the tensor-core backward for [R,7,7,C] gradients
+    // fetches and multiplies only those.  No other kernel reads the pad.
+    int l7[P], h7[P];
+#pragma unroll
+    for (int ph = 0; ph < P; ++ph) {
+      l7[ph] = __shfl_sync(0xffffffffu, bin_lo, 8 + ph);
+      h7[ph] = __shfl_sync(0xffffffffu, bin_hi, 8 + ph);
+    }
+    for (int i = lane; i < ny; i += 32) {
+      const int y = y_lo + i;
+      int first = P, last = -1;
+#pragma unroll
+      for (int ph = P - 1; ph >= 0; --ph) if (h7[ph] >= y) first = ph;
+#pragma unroll
+      for (int ph = 0; ph < P; ++ph) if (l7[ph] <= y) last = ph;
+      wy[i * WROW + P] = __int_as_float(first | ((last + 1) << 8));
+    }
   }
   if (lane == 0) {
     RoiMeta m;

@@ -12,11 +12,14 @@
 // TMEM to grad_input NHWC (lanes = consecutive channels: 128 B coalesced stores, every element written once).
 // The CUDA-core kernel (roi_align.cu) measured 8 % of HBM peak, issue bound (profiles/r01_roi_align_ncu.md).
 //
-// kRHWC = gradients in [R,7,7,C] order (DA_ROI_OUT_RHWC): the A operand is then MN-major AS IT LIES IN MEMORY.  One rank-4 TMA
-// box (64 ch, 64 bins of which 15 are out-of-bounds zero fill, 4 channel groups, 1 RoI) = 32 KB lands 128B-swizzled in a 4-deep
-// operand ring, no raw gradient ring and no relayout by the builders (the relayout's reads of 98-byte-pitch rows and its swizzled
-// stores were ~690 of the ~1600 shared-memory-port cycles per (RoI, tile) pair; profiles/r02_roi_bwd_pipeline_study.md).  The
-// builders only build the weight tile; the products and their order are the same as in the [R,C,7,7] mode: bit-identical results.
+// kRHWC = gradients in [R,7,7,C] order (DA_ROI_OUT_RHWC): the A operand is then MN-major AS IT LIES IN MEMORY.  ONE rank-4 TMA box
+// (64 ch, 16 * ksteps bins, 4 channel groups, 1 RoI) per pair lands 128B-swizzled in a 4-slot operand ring (a box per k-step
+// measured slower: the producer warp's wait -> expect_tx -> issue sequences are ~400 cycles each and serialise): no raw
+// gradient ring and no relayout by the builders (the relayout's reads of 98-byte-pitch rows and its swizzled stores were ~690 of
+// the ~1600 shared-memory-port cycles per (RoI, tile) pair; profiles/r02_roi_bwd_pipeline_study.md).  Bin-major order also lets a
+// pair fetch and multiply only the BIN ROWS whose support meets the tile's rows (the prep kernel leaves that range in the pad
+// column of the Wy table): a RoI spanning several tiles vertically costs each of them 1-3 k-steps instead of 4 (bins past 49
+// are out-of-bounds zero fill, bins of the range's last k-step that do not meet the tile multiply zero weights).
 #include <stdlib.h>
 #include <string.h>
 #include "da_common.cuh"
@@ -38,6 +41,8 @@ constexpr int BT_TY = 16, BT_TX = 16, BT_PX = BT_TY * BT_TX;   // 256 pixels = U
 constexpr int BT_CH = 256;                                      // channels per CTA = 2 accumulators of 128
 constexpr int BT_BUILDERS = 512;                                // warps 2..17: two half-rows per operand row
 constexpr int BT_THREADS = 64 + BT_BUILDERS;
+constexpr int BT_XWARPS = 2;                                    // kRHWC only: two more producer warps (Wx slices, gradient boxes)
+constexpr int BT_THREADS_RHWC = BT_THREADS + 32 * BT_XWARPS;
 constexpr int BT_LIST = 1024;
 constexpr int BT_WARPS = BT_THREADS / 32;
 constexpr int BT_ROUNDS = (BT_LIST + BT_THREADS - 1) / BT_THREADS;
@@ -49,11 +54,15 @@ constexpr int BT_RAW_BYTES = 64 + BT_RAW_G + (BT_TY + BT_TX) * WROW * 4 + 64;   
 constexpr int BT_PF = 8;                                       // L2 prefetch distance (pairs)
 constexpr int BT_NRAW = 3;                                     // raw ring depth (copy latency ~3 pair times)
 constexpr size_t BT_SMEM = 1024 + 2 * (size_t)BT_OPS_BYTES + BT_NRAW * (size_t)BT_RAW_BYTES + BT_LIST * 4 + 256;
-// kRHWC layout: [BT_NA][A 32 KB] | [2][B 32 KB] | [BT_NRAW][header | wy | wx] | list | barriers
-constexpr int BT_NA = 4;                                       // A (gradient) ring depth: TMA latency ~2 pair times inside the kernel
+// kRHWC layout: [BT_NA][A slot 32 KB] | [2][B 32 KB] | [BT_NRAW_RHWC][header | wy | wx] | list | barriers
+// A slot = the k-steps of one pair: [4 channel groups][16 * ksteps bins][64 ch] bf16, 128B-swizzled rows
+constexpr int BT_NA = 4;                                       // A (gradient) ring depth in pairs
+constexpr int BT_ASLOT = 2 * BT_A_BYTES;                       // 32 KB: 4 k-steps
+constexpr int BT_NRAW_RHWC = 8;
 constexpr int BT_RAWT_BYTES = 64 + (BT_TY + BT_TX) * WROW * 4 + 64;    // 1152 (128-multiple)
-constexpr size_t BT_SMEM_RHWC = 1024 + (size_t)BT_NA * 2 * BT_A_BYTES + 2 * (size_t)BT_B_BYTES + BT_NRAW * (size_t)BT_RAWT_BYTES + BT_LIST * 4 + 256;
-static_assert(BT_SMEM_RHWC <= 227 * 1024 && BT_NA * 2 * BT_A_BYTES >= BT_PX * BT_CH * 2, "epilogue staging overlays the A ring");
+constexpr size_t BT_SMEM_RHWC = 1024 + (size_t)BT_NA * BT_ASLOT + 2 * (size_t)BT_B_BYTES + BT_NRAW_RHWC * (size_t)BT_RAWT_BYTES + BT_LIST * 4 + 512;
+static_assert(BT_SMEM_RHWC <= 227 * 1024 && BT_NA * BT_ASLOT >= BT_PX * BT_CH * 2, "epilogue staging overlays the A ring");
+struct BwdMaps { CUtensorMap m[4]; };                          // boxes of 16, 32, 48, 64 bins
 
 // Work items = (image, pixel tile) x channel chunk; their cost is the number of RoIs touching the tile (0 ... 54 pairs at the bench
 // size), and the hardware hands CTAs out in index order: with tiles in raster order the last CTAs to start were heavy ones and
@@ -84,8 +93,8 @@ roi_tile_order_kernel(const unsigned char* __restrict__ ws, int R, int N, int H,
 }
 
 template <typename TO, bool kTrace, bool kRHWC>
-__global__ void __launch_bounds__(BT_THREADS, 1)
-roi_align_bwd_tc_kernel(const __grid_constant__ CUtensorMap gmap, const __nv_bfloat16* __restrict__ grad_out, int C, int H, int W, int R,
+__global__ void __launch_bounds__(kRHWC ? BT_THREADS_RHWC : BT_THREADS, 1)
+roi_align_bwd_tc_kernel(const __grid_constant__ BwdMaps gmaps, const __nv_bfloat16* __restrict__ grad_out, int C, int H, int W, int R,
                         const unsigned char* __restrict__ ws, TO* __restrict__ grad_in, int tiles_x, int dbg, unsigned long long* trace,
                         const int* __restrict__ item_order, int tiles, int chunks) {
   if (dbg & 32) return;
@@ -102,14 +111,16 @@ roi_align_bwd_tc_kernel(const __grid_constant__ CUtensorMap gmap, const __nv_bfl
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t ops0 = base;                                   // [2][A0 | A1 | B]   (kRHWC: A ring, then the two B tiles)
-  constexpr int RAW_OFF = kRHWC ? BT_NA * 2 * BT_A_BYTES + 2 * BT_B_BYTES : 2 * BT_OPS_BYTES;
+  constexpr int NRAW = kRHWC ? BT_NRAW_RHWC : BT_NRAW;          // table slots only in the kRHWC mode: cheap, so the producer runs further ahead
+  constexpr int RAW_OFF = kRHWC ? BT_NA * BT_ASLOT + 2 * BT_B_BYTES : 2 * BT_OPS_BYTES;
   constexpr int RAW_PITCH = kRHWC ? BT_RAWT_BYTES : BT_RAW_BYTES;
   constexpr int RAW_TAB = kRHWC ? 0 : BT_RAW_G;                 // offset of the table slices behind a slot's 64-byte header
-  const uint32_t raw0 = ops0 + RAW_OFF;                         // [BT_NRAW] raw slots
-  int* list = reinterpret_cast<int*>(gen + RAW_OFF + BT_NRAW * RAW_PITCH);
+  const uint32_t raw0 = ops0 + RAW_OFF;                         // [NRAW] raw slots
+  int* list = reinterpret_cast<int*>(gen + RAW_OFF + NRAW * RAW_PITCH);
   const uint32_t bars = smem_u32(list + BT_LIST);
-  const uint32_t raw_full0 = bars, raw_empty0 = bars + 32, ops_ready0 = bars + 64, ops_free0 = bars + 80,
-                 tfull = bars + 96, tslot = bars + 104, a_full0 = bars + 112, a_empty0 = bars + 144;
+  const uint32_t raw_full0 = bars, raw_empty0 = bars + 64, ops_ready0 = bars + 128, ops_free0 = bars + 144,
+                 tfull = bars + 160, tslot = bars + 168, u_full0 = bars + 192, u_empty0 = bars + 320;
+  static_assert(NRAW <= 8 && BT_NA <= 16, "barrier block layout");
   volatile uint32_t* tslot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tslot - base));
   __shared__ int s_wcount[BT_ROUNDS * BT_WARPS];
   __shared__ int s_rows[2];     // per operand buffer: first tile row | (end tile row << 8) of the RoI's footprint in this tile
@@ -124,7 +135,7 @@ roi_align_bwd_tc_kernel(const __grid_constant__ CUtensorMap gmap, const __nv_bfl
   const int nch = min(BT_CH, C - c0);
 
   if (t == 0) {
-    for (int i = 0; i < BT_NRAW; ++i) {
+    for (int i = 0; i < NRAW; ++i) {
       mbar_init(raw_full0 + 8 * i, 1);
       mbar_init(raw_empty0 + 8 * i, 1);
     }
@@ -135,8 +146,8 @@ roi_align_bwd_tc_kernel(const __grid_constant__ CUtensorMap gmap, const __nv_bfl
     mbar_init(tfull, 1);
     if (kRHWC)
       for (int i = 0; i < BT_NA; ++i) {
-        mbar_init(a_full0 + 8 * i, 1);
-        mbar_init(a_empty0 + 8 * i, 1);
+        mbar_init(u_full0 + 8 * i, 1);
+        mbar_init(u_empty0 + 8 * i, 1);
       }
     fence_barrier_init();
   }
@@ -157,7 +168,7 @@ roi_align_bwd_tc_kernel(const __grid_constant__ CUtensorMap gmap, const __nv_bfl
     for (int k = 0; k < BT_ROUNDS; ++k) {
       const int r = rbase + k * BT_THREADS + t;
       hit[k] = false;
-      if (r < rend) {
+      if (r < rend && warp < BT_WARPS) {      // (the extra producer warps of the kRHWC mode take no part in the compaction)
         const RoiMeta m = metas[r];
         hit[k] = (m.b == b) && m.ny > 0 && m.y_lo < ty1 && m.y_lo + m.ny > ty0 && m.x_lo < tx1 && m.x_lo + m.nx > tx0;
       }
@@ -166,7 +177,7 @@ roi_align_bwd_tc_kernel(const __grid_constant__ CUtensorMap gmap, const __nv_bfl
 #pragma unroll
     for (int k = 0; k < BT_ROUNDS; ++k) {
       bal[k] = __ballot_sync(0xffffffffu, hit[k]);
-      if (lane == 0) s_wcount[k * BT_WARPS + warp] = __popc(bal[k]);
+      if (lane == 0 && warp < BT_WARPS) s_wcount[k * BT_WARPS + warp] = __popc(bal[k]);
     }
     __syncthreads();
     int total = 0;
@@ -189,11 +200,20 @@ roi_align_bwd_tc_kernel(const __grid_constant__ CUtensorMap gmap, const __nv_bfl
       int my_r = 0;
       RoiMeta my_m = {};
       for (int li = 0; li < n_list; ++li) {
-        const int sq = seq + li, slot = sq % BT_NRAW;
-        const uint32_t par = (uint32_t)(sq / BT_NRAW) & 1u;
+        const int sq = seq + li, slot = sq % NRAW;
+        const uint32_t par = (uint32_t)(sq / NRAW) & 1u;
         if ((li & 31) == 0 && li + lane < n_list) {   // 32 metas per L2 round trip, off the ring's critical path
           my_r = list[li + lane];
           my_m = metas[my_r];
+          if (kRHWC) {   // bin rows of this RoI that meet the tile's rows: pad column of its Wy rows (roi_prep_kernel)
+            const int ya_ = max(my_m.y_lo, ty0), yb_ = min(my_m.y_lo + my_m.ny, ty1);
+            const float* tab_ = tables + (size_t)my_r * (H + W) * WROW;
+            const int fa = __float_as_int(tab_[(size_t)(ya_ - my_m.y_lo) * WROW + P]) & 255;
+            const int lb = (__float_as_int(tab_[(size_t)(yb_ - 1 - my_m.y_lo) * WROW + P]) >> 8) & 255;   // 1 + last bin row
+            const int pa_ = min(fa, P - 1), pb_ = max(min(lb, P), pa_ + 1);
+            my_m.gh = pa_;                                   // (gh / gw are not used by this kernel)
+            my_m.gw = ((pb_ - pa_) * P + 15) >> 4;           // k-steps: 1..4
+          }
         }
         // pull the gradient chunk of the pair BT_PF ring slots ahead into L2 (the ring itself only covers ~3 us)
         if (!kRHWC && lane == 3 && li + BT_PF < n_list && !(dbg & 128))
@@ -206,6 +226,7 @@ roi_align_bwd_tc_kernel(const __grid_constant__ CUtensorMap gmap, const __nv_bfl
         m.x_lo = __shfl_sync(0xffffffffu, my_m.x_lo, src);
         m.nx = __shfl_sync(0xffffffffu, my_m.nx, src);
         m.count = __shfl_sync(0xffffffffu, my_m.count, src);
+        const int pa = kRHWC ? __shfl_sync(0xffffffffu, my_m.gh, src) : 0, ksteps = kRHWC ? __shfl_sync(0xffffffffu, my_m.gw, src) : 4;
         const int ya = max(m.y_lo, ty0), yb = min(m.y_lo + m.ny, ty1);
         const int xa = max(m.x_lo, tx0), xb = min(m.x_lo + m.nx, tx1);
         mbar_wait(raw_empty0 + 8 * slot, par ^ 1u);
@@ -217,6 +238,7 @@ roi_align_bwd_tc_kernel(const __grid_constant__ CUtensorMap gmap, const __nv_bfl
           int* hdr = reinterpret_cast<int*>(sl);
           hdr[0] = ya; hdr[1] = yb; hdr[2] = xa; hdr[3] = xb;
           reinterpret_cast<float*>(sl)[4] = 1.f / (float)m.count;
+          hdr[5] = pa; hdr[6] = ksteps;
           mbar_expect_tx(fb, g_bytes + (uint32_t)((yb - ya) + (xb - xa)) * WROW * 4);
         }
         __syncwarp();
@@ -224,17 +246,54 @@ roi_align_bwd_tc_kernel(const __grid_constant__ CUtensorMap gmap, const __nv_bfl
         const uint32_t sbase = raw0 + slot * RAW_PITCH + 64;
         if (!kRHWC && lane == 0) bulk_g2s(sbase, grad_out + ((size_t)r * C + c0) * PP, g_bytes, fb);
         if (lane == 1) bulk_g2s(sbase + RAW_TAB, tab + (size_t)(ya - m.y_lo) * WROW, (uint32_t)(yb - ya) * WROW * 4, fb);
-        if (lane == 2) bulk_g2s(sbase + RAW_TAB + BT_TY * WROW * 4, tab + (size_t)H * WROW + (size_t)(xa - m.x_lo) * WROW,
-                                (uint32_t)(xb - xa) * WROW * 4, fb);
-        if (kRHWC) {
-          // the gradient chunk of the pair: box (64 ch, 64 bins, 4 channel groups, 1 RoI) -> smem [grp][bin][64 ch], swizzled;
-          // bins 49..63 and channel groups past C/64 are out of bounds = zero fill (counted in the transaction bytes)
-          const int aslot = sq % BT_NA;
-          mbar_wait(a_empty0 + 8 * aslot, ((uint32_t)(sq / BT_NA) & 1u) ^ 1u);
-          if (lane == 0) {
-            mbar_expect_tx(a_full0 + 8 * aslot, 2 * BT_A_BYTES);
-            tma_load_4d(ops0 + aslot * (2 * BT_A_BYTES), &gmap, a_full0 + 8 * aslot, 0, 0, c0 >> 6, r);
+        if (!kRHWC && lane == 2) bulk_g2s(sbase + RAW_TAB + BT_TY * WROW * 4, tab + (size_t)H * WROW + (size_t)(xa - m.x_lo) * WROW,
+                                          (uint32_t)(xb - xa) * WROW * 4, fb);
+      }
+    } else if (kRHWC && warp >= BT_WARPS) {
+      // ------------------------------------------------ kRHWC: two more producer warps.  One wait -> expect_tx -> issue sequence
+      // of a thread costs ~400 cycles whatever its size and the sequences of one warp serialise: with all three copies of a
+      // pair on warp 0 the producer alone was ~1300 cycles per pair (the whole kernel without MMAs and weight build: 1390).
+      // warp BT_WARPS: Wx slice (completes on the slot's raw_full, whose transaction count warp 0 posts);
+      // warp BT_WARPS + 1: the pair's gradient box.
+      const bool is_a = warp == BT_WARPS + 1;
+      int my_r = 0;
+      RoiMeta my_m = {};
+      for (int li = 0; li < n_list; ++li) {
+        const int sq = seq + li;
+        if ((li & 31) == 0 && li + lane < n_list) {
+          my_r = list[li + lane];
+          my_m = metas[my_r];
+          if (is_a) {   // bin rows of this RoI that meet the tile's rows: pad column of its Wy rows (roi_prep_kernel)
+            const int ya_ = max(my_m.y_lo, ty0), yb_ = min(my_m.y_lo + my_m.ny, ty1);
+            const float* tab_ = tables + (size_t)my_r * (H + W) * WROW;
+            const int fa = __float_as_int(tab_[(size_t)(ya_ - my_m.y_lo) * WROW + P]) & 255;
+            const int lb = (__float_as_int(tab_[(size_t)(yb_ - 1 - my_m.y_lo) * WROW + P]) >> 8) & 255;
+            const int pa_ = min(fa, P - 1), pb_ = max(min(lb, P), pa_ + 1);
+            my_m.gh = pa_;
+            my_m.gw = ((pb_ - pa_) * P + 15) >> 4;
           }
+        }
+        const int src = li & 31;
+        const int r = __shfl_sync(0xffffffffu, my_r, src);
+        if (is_a) {
+          const int pa = __shfl_sync(0xffffffffu, my_m.gh, src), ksteps = __shfl_sync(0xffffffffu, my_m.gw, src);
+          const int aslot = sq % BT_NA;
+          mbar_wait(u_empty0 + 8 * aslot, ((uint32_t)(sq / BT_NA) & 1u) ^ 1u);
+          if (lane == 0) {
+            // box (64 ch, 16 * ksteps bins from bin row pa on, 4 channel groups, 1 RoI) -> smem [grp][bin][64 ch], swizzled; bins
+            // >= 49 and channel groups past C/64 are out of bounds = zero fill (counted in the transaction bytes)
+            mbar_expect_tx(u_full0 + 8 * aslot, (uint32_t)ksteps * (BT_ASLOT / 4));
+            tma_load_4d(ops0 + aslot * BT_ASLOT, &gmaps.m[ksteps - 1], u_full0 + 8 * aslot, 0, pa * P, c0 >> 6, r);
+          }
+        } else {
+          const int x_lo = __shfl_sync(0xffffffffu, my_m.x_lo, src), nx = __shfl_sync(0xffffffffu, my_m.nx, src);
+          const int xa = max(x_lo, tx0), xb = min(x_lo + nx, tx1);
+          const int slot = sq % NRAW;
+          mbar_wait(raw_empty0 + 8 * slot, ((uint32_t)(sq / NRAW) & 1u) ^ 1u);
+          if (lane == 0)
+            bulk_g2s(raw0 + slot * RAW_PITCH + 64 + RAW_TAB + BT_TY * WROW * 4,
+                     tables + (size_t)r * (H + W) * WROW + (size_t)H * WROW + (size_t)(xa - x_lo) * WROW, (uint32_t)(xb - xa) * WROW * 4,
+                     raw_full0 + 8 * slot);
         }
       }
     } else if (warp == 1) {
@@ -244,33 +303,47 @@ roi_align_bwd_tc_kernel(const __grid_constant__ CUtensorMap gmap, const __nv_bfl
           const int sq = seq + li, ob = sq & 1;
           const uint32_t par = (uint32_t)(sq >> 1) & 1u;
           mbar_wait(ops_ready0 + 8 * ob, par);
-          if (kRHWC) mbar_wait(a_full0 + 8 * (sq % BT_NA), (uint32_t)(sq / BT_NA) & 1u);
           PSTAMP(sq, 1);
           tc_fence_after();
           const uint32_t ops = ops0 + ob * BT_OPS_BYTES;
-          const uint32_t a_tile = kRHWC ? ops0 + (sq % BT_NA) * (2 * BT_A_BYTES) : ops;
-          const uint32_t b_tile = kRHWC ? ops0 + BT_NA * 2 * BT_A_BYTES + ob * BT_B_BYTES : ops + 2 * BT_A_BYTES;
+          const uint32_t b_tile = kRHWC ? ops0 + BT_NA * BT_ASLOT + ob * BT_B_BYTES : ops + 2 * BT_A_BYTES;
           // Only the tile rows the RoI touches take part: N = 16 px x (rows touched) instead of the whole 16x16 tile (the
           // weight rows of the other pixels are zero, and are not even built any more).  The very first pair of the CTA runs
           // the full N = 256 with accumulate = 0: it is what initialises both TMEM accumulators.
-          int r0 = 0, nrows = BT_TY;
+          int r0 = 0, nrows = BT_TY, ksteps = 4;
+          const int rr = *reinterpret_cast<volatile int*>(&s_rows[ob]);
           if (sq > 0) {
-            const int rr = *reinterpret_cast<volatile int*>(&s_rows[ob]);
             r0 = rr & 255;
-            nrows = (rr >> 8) - r0;
+            nrows = ((rr >> 8) & 255) - r0;
           }
-          // kRHWC: A is MN-major (channels contiguous): 64-channel groups 8 KB apart (LBO), 8-bin atoms 1 KB apart, 16 bins = 2 KB per k-step
+          if (kRHWC) ksteps = rr >> 16;
           const uint32_t idesc_n = make_idesc(128, sq > 0 ? BT_TX * nrows : BT_PX, kRHWC ? 1 : 0, 0);
           const uint64_t bd = desc_kmajor_sw128(b_tile + (uint32_t)r0 * (BT_TX * 128));
+          if constexpr (kRHWC) {
+            // A is MN-major (channels contiguous): 64-channel groups ksteps * 2 KB apart (LBO), 8-bin atoms 1 KB apart (SBO),
+            // 16 bins = 2 KB per k-step, the second 128-channel block 2 groups further
+            const int aslot = sq % BT_NA;
+            mbar_wait(u_full0 + 8 * aslot, (uint32_t)(sq / BT_NA) & 1u);
+            tc_fence_after();
+            const uint32_t a_tile = ops0 + aslot * BT_ASLOT, gpitch = (uint32_t)ksteps * 2048u;
+            for (int kk = 0; kk < ksteps; ++kk) {
 #pragma unroll
-          for (int cb = 0; cb < 2; ++cb) {
-            const uint64_t ad = kRHWC ? desc_mnmajor_sw128(a_tile + cb * BT_A_BYTES, 8192) : desc_kmajor_sw128(a_tile + cb * BT_A_BYTES);
+              for (int cb = 0; cb < 2; ++cb)
+                if (!(dbg & 1))
+                  umma_bf16(tmem_base + cb * BT_PX + r0 * BT_TX, desc_mnmajor_sw128(a_tile + cb * 2 * gpitch + kk * 2048, gpitch),
+                            bd + (uint64_t)(kk * 2), idesc_n, (sq > 0 || kk > 0) ? 1u : 0u);
+            }
+            umma_commit(u_empty0 + 8 * aslot);
+          } else {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              if (!(dbg & 1)) umma_bf16(tmem_base + cb * BT_PX + r0 * BT_TX, ad + (uint64_t)(kk * (kRHWC ? 128 : 2)), bd + (uint64_t)(kk * 2), idesc_n, (sq > 0 || kk > 0) ? 1u : 0u);
+            for (int cb = 0; cb < 2; ++cb) {
+              const uint64_t ad = desc_kmajor_sw128(ops + cb * BT_A_BYTES);
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                if (!(dbg & 1)) umma_bf16(tmem_base + cb * BT_PX + r0 * BT_TX, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc_n, (sq > 0 || kk > 0) ? 1u : 0u);
+            }
           }
           umma_commit(ops_free0 + 8 * ob);
-          if (kRHWC) umma_commit(a_empty0 + 8 * (sq % BT_NA));
           PSTAMP(sq, 2);
         }
       }
@@ -282,10 +355,17 @@ roi_align_bwd_tc_kernel(const __grid_constant__ CUtensorMap gmap, const __nv_bfl
       // profiles/r02_roi_bwd_pipeline_study.md).  Within each group of 64 rows the two warps take the row sets below instead:
       // floor(24.5 r) mod 32 is distinct over a warp (conflict-free loads) and every aligned octet of lanes holds all residues
       // r mod 8 (conflict-free 128B-swizzled STS.128, as before).  Pure re-assignment of work: results are bit-identical.
-      const int bt = t - 64, half = bt >> 8, row = (dbg & 256) ? (bt & 255) : ((bt & 192) | kRowPerm[bt & 63]);
+      // kRHWC: the builders only build the weight tile, and what a pair costs them is latency (two barrier waits, table reads,
+      // proxy fence, team barrier, arrive: ~700-1000 cycles with ~150 of arithmetic), so they work as TWO TEAMS of 256 threads on
+      // alternate pairs -- team t owns weight buffer t, a thread builds a whole 128-byte row -- and the latencies of consecutive
+      // pairs overlap (tools/trace_roi_bwd.py: the kernel without MMAs and weight arithmetic was 1145 cycles per pair).
+      const int bt = t - 64, row = (dbg & 256) ? (bt & 255) : ((bt & 192) | kRowPerm[bt & 63]);
+      const int team = kRHWC ? (bt >> 8) : 0;
+      const bool leader = kRHWC ? (bt & 255) == 0 : bt == 0;
       for (int li = 0; li < n_list; ++li) {
-        const int sq = seq + li, slot = sq % BT_NRAW, ob = sq & 1;
-        mbar_wait(raw_full0 + 8 * slot, (uint32_t)(sq / BT_NRAW) & 1u);
+        const int sq = seq + li, slot = sq % NRAW, ob = sq & 1;
+        if (kRHWC && ob != team) continue;
+        mbar_wait(raw_full0 + 8 * slot, (uint32_t)(sq / NRAW) & 1u);
         if (bt == 0) PSTAMP(sq, 3);
         mbar_wait(ops_free0 + 8 * ob, ((uint32_t)(sq >> 1) & 1u) ^ 1u);
         if (bt == 0) PSTAMP(sq, 4);
@@ -296,10 +376,12 @@ roi_align_bwd_tc_kernel(const __grid_constant__ CUtensorMap gmap, const __nv_bfl
         const float* wy_s = reinterpret_cast<const float*>(sl + 64 + RAW_TAB);
         const float* wx_s = wy_s + BT_TY * WROW;
         uint8_t* ops = gen + ob * BT_OPS_BYTES;
-        uint8_t* b_ops = kRHWC ? gen + BT_NA * 2 * BT_A_BYTES + ob * BT_B_BYTES : ops + 2 * BT_A_BYTES;
+        uint8_t* b_ops = kRHWC ? gen + BT_NA * BT_ASLOT + ob * BT_B_BYTES : ops + 2 * BT_A_BYTES;
+        const int pa = kRHWC ? hdr[5] : 0, ksteps = kRHWC ? hdr[6] : 4;
         // (1) A: 49 bf16 of channel `row` -> 64 (zero padded), 128B-swizzled K-major row.  Rows start on
         // 2-byte boundaries (98 B pitch): read aligned words and funnel-shift by 0 or 16 bits.
         if constexpr (!kRHWC) {
+          const int half = bt >> 8;
           const int cb = row >> 7, mrow = row & 127;
           uint32_t pk[16];
           if (row < nch && !(dbg & 2)) {
@@ -333,7 +415,10 @@ roi_align_bwd_tc_kernel(const __grid_constant__ CUtensorMap gmap, const __nv_bfl
         }
         // (2) B: Wt[px][bin] = Wy[y][ph] * Wx[x][pw] / count inside the footprint, else 0.  Tile rows the RoI does not
         // touch are skipped (the MMA only reads rows [ya, yb)); the first pair of the CTA still writes all 256 rows.
-        if (sq == 0 || ((ty0 + (row >> 4)) >= ya && (ty0 + (row >> 4)) < yb)) {
+#pragma unroll
+        for (int hh = 0; hh < (kRHWC ? 2 : 1); ++hh) {
+        const int half = kRHWC ? hh : (bt >> 8);
+        if ((sq == 0 || ((ty0 + (row >> 4)) >= ya && (ty0 + (row >> 4)) < yb)) && half * 2 < ksteps) {
           const int y = ty0 + (row >> 4), x = tx0 + (row & 15);
           const bool in = (y >= ya) && (y < yb) && (x >= xa) && (x < xb);
           uint32_t pk[16];
@@ -342,8 +427,13 @@ roi_align_bwd_tc_kernel(const __grid_constant__ CUtensorMap gmap, const __nv_bfl
           if (in && !(dbg & 4)) {
             const float4 wa = reinterpret_cast<const float4*>(wy_s)[(y - ya) * 2], wb = reinterpret_cast<const float4*>(wy_s)[(y - ya) * 2 + 1];
             const float4 xa4 = reinterpret_cast<const float4*>(wx_s)[(x - xa) * 2], xb4 = reinterpret_cast<const float4*>(wx_s)[(x - xa) * 2 + 1];
-            const float wyv[P] = {wa.x * inv_count, wa.y * inv_count, wa.z * inv_count, wa.w * inv_count,
-                                  wb.x * inv_count, wb.y * inv_count, wb.z * inv_count};
+            float wyv[P] = {wa.x * inv_count, wa.y * inv_count, wa.z * inv_count, wa.w * inv_count,
+                            wb.x * inv_count, wb.y * inv_count, wb.z * inv_count};
+            if (kRHWC && pa > 0) {   // K column j of the pair is bin pa*7 + j: bin row pa + j/7 (zero weight past the last one)
+              const float* wrow = wy_s + (y - ya) * WROW;
+#pragma unroll
+              for (int i = 0; i < P; ++i) wyv[i] = (pa + i < P) ? wrow[pa + i] * inv_count : 0.f;
+            }
             const float wxv[P] = {xa4.x, xa4.y, xa4.z, xa4.w, xb4.x, xb4.y, xb4.z};
             if (half == 0) {
 #pragma unroll
@@ -367,12 +457,13 @@ roi_align_bwd_tc_kernel(const __grid_constant__ CUtensorMap gmap, const __nv_bfl
           for (int k = 0; k < 4; ++k)
             *reinterpret_cast<uint4*>(brow + (((half * 4 + k) ^ (row & 7)) << 4)) = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
         }
+        }
         if (bt == 0) PSTAMP(sq, 5);
         fence_proxy_async();
-        named_bar_sync(2, BT_BUILDERS);
+        named_bar_sync(kRHWC ? 3 + team : 2, kRHWC ? BT_BUILDERS / 2 : BT_BUILDERS);
         if (bt == 0) PSTAMP(sq, 6);
-        if (bt == 0) {
-          s_rows[ob] = (ya - ty0) | ((yb - ty0) << 8);     // read by the MMA thread after it has seen ops_ready (release/acquire)
+        if (leader) {
+          s_rows[ob] = (ya - ty0) | ((yb - ty0) << 8) | (ksteps << 16);     // read by the MMA thread after it has seen ops_ready (release/acquire)
           mbar_arrive(ops_ready0 + 8 * ob);
           mbar_arrive(raw_empty0 + 8 * slot);
         }
@@ -384,7 +475,7 @@ roi_align_bwd_tc_kernel(const __grid_constant__ CUtensorMap gmap, const __nv_bfl
   if (kTrace && trace && threadIdx.x == 64) tr2 = globaltimer_ns();
   // ---- epilogue: TMEM -> grad_input (or zeros when no RoI touches the tile)
   if (warp == 1 && lane == 0 && seq > 0) umma_commit(tfull);
-  if (warp >= 2) {
+  if (warp >= 2 && warp < BT_WARPS) {
     const int q = warp & 3, cb = ((warp - 2) >> 2) & 1, chalf = (warp - 2) >> 3;   // TMEM quadrant, accumulator, pixel half
     const int c = c0 + cb * 128 + q * 32 + lane;
     if (seq > 0) {
@@ -454,16 +545,18 @@ static int launch_bwd_tc(const void* grad_out, int N, int C, int H, int W, int R
   const int tiles = tiles_x * tiles_y, chunks = (C + BT_CH - 1) / BT_CH;
   DA_REQUIRE((long long)N * tiles * chunks <= 0x7fffffffll, DA_ERR_UNSUPPORTED, "roi_align_backward tc: grid too large");
   dim3 grid((unsigned)(N * tiles * chunks));
-  CUtensorMap gmap;
-  memset(&gmap, 0, sizeof(gmap));
+  BwdMaps gmaps;
+  memset(&gmaps, 0, sizeof(gmaps));
   if (kRHWC) {
-    // grad_out [R][49][C] viewed as (64 ch, 49 bins, C/64 groups, R): one box = the [64 bins][256 ch] chunk of a (RoI, CTA) pair
+    // grad_out [R][49][C] viewed as (64 ch, 49 bins, C/64 groups, R): one box = the k-steps ([16 k bins][256 ch]) of a (RoI, CTA) pair
     DA_REQUIRE(C % 64 == 0, DA_ERR_UNSUPPORTED, "roi_align_backward tc ([R,7,7,C] gradients): C must be a multiple of 64");
     const uint64_t dims[4] = {64, (uint64_t)PP, (uint64_t)(C / 64), (uint64_t)R};
     const uint64_t strides[3] = {(uint64_t)C * 2, 128, (uint64_t)PP * C * 2};
-    const uint32_t box[4] = {64, 64, BT_CH / 64, 1};
-    int rc = encode_map(&gmap, grad_out, 4, dims, strides, box);
-    if (rc) return rc;
+    for (int k = 1; k <= 4; ++k) {
+      const uint32_t box[4] = {64, (uint32_t)(16 * k), BT_CH / 64, 1};
+      int rc = encode_map(&gmaps.m[k - 1], grad_out, 4, dims, strides, box);
+      if (rc) return rc;
+    }
   }
   // longest-processing-time-first order of the (image, tile) items; the list lives in the workspace's RoI-order region (only the
   // forward reads that one, and every forward rewrites it)
@@ -484,10 +577,10 @@ static int launch_bwd_tc(const void* grad_out, int N, int C, int H, int W, int R
     attr_set = true;
   }
   if (trace)
-    roi_align_bwd_tc_kernel<TO, true, kRHWC><<<grid, BT_THREADS, smem, st>>>(gmap, (const __nv_bfloat16*)grad_out, C, H, W, R, (const unsigned char*)ws,
+    roi_align_bwd_tc_kernel<TO, true, kRHWC><<<grid, kRHWC ? BT_THREADS_RHWC : BT_THREADS, smem, st>>>(gmaps, (const __nv_bfloat16*)grad_out, C, H, W, R, (const unsigned char*)ws,
                                                                                  static_cast<TO*>(grad_in), tiles_x, dbg, trace, item_order, tiles, chunks);
   else
-    roi_align_bwd_tc_kernel<TO, false, kRHWC><<<grid, BT_THREADS, smem, st>>>(gmap, (const __nv_bfloat16*)grad_out, C, H, W, R, (const unsigned char*)ws,
+    roi_align_bwd_tc_kernel<TO, false, kRHWC><<<grid, kRHWC ? BT_THREADS_RHWC : BT_THREADS, smem, st>>>(gmaps, (const __nv_bfloat16*)grad_out, C, H, W, R, (const unsigned char*)ws,
                                                                                   static_cast<TO*>(grad_in), tiles_x, dbg, trace, item_order, tiles, chunks);
   DA_LAUNCH_CHECK();
   return DA_OK;
