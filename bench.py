@@ -38,7 +38,7 @@ WORKLOAD = "daf_org_r50dc5_da_hot_path_1024x2048"
 C, H, W, STRIDE = 2048, 64, 128, 16
 ROIS_PER_IMG = 512
 FC_OUT = 1024
-ROI_LAYOUT_DEFAULT = "rchw"      # memory order of the RoI features in the timed step (see --roi-layout)
+ROI_LAYOUT_DEFAULT = "rhwc"      # memory order of the RoI features in the timed step (see --roi-layout)
 
 
 def parse_args():
@@ -189,7 +189,9 @@ def measure_engine(args, engine, rank, local, world, sample_clocks):
     pairs = args.pairs_per_gpu
 
     torch.manual_seed(0)
-    model = hotpath.DAFOrgHotPath(C, STRIDE, FC_OUT, roi_layout=args.roi_layout).to(dev).train()
+    # the bin-major RoI tensor is the bf16 tensor-core engine's layout; the fp32-class engines keep the reference's [R,C,7,7]
+    roi_layout = args.roi_layout if engine == "umma_bf16" else "rchw"
+    model = hotpath.DAFOrgHotPath(C, STRIDE, FC_OUT, roi_layout=roi_layout).to(dev).train()
     params = ddist.trainable_parameters(model, model.unused_parameters())
     sgd = dict(lr=1e-3, momentum=0.9, weight_decay=5e-4)                      # reference recipe (faster_rcnn_r50_daf_c2f.py:8)
     peer_opt, sync_note = None, "none (1 GPU)"
@@ -398,7 +400,7 @@ def measure_engine(args, engine, rank, local, world, sample_clocks):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if engine == "umma_bf16" else "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "pairs_per_gpu": pairs, "c5": [2 * pairs, C, H, W], "rois_per_img": ROIS_PER_IMG,
-                   "engine": engine, "roi_layout": args.roi_layout, "launch": graph_note, "grad_allreduce": sync_note, "step": "H1+L1, RoIAlign fwd/bwd, shared FCs, I1+L4, L7, backward, SGD",
+                   "engine": engine, "roi_layout": roi_layout, "launch": graph_note, "grad_allreduce": sync_note, "step": "H1+L1, RoIAlign fwd/bwd, shared FCs, I1+L4, L7, backward, SGD",
                    "l2_policy": "inputs_and_weights_exceed_L2 (C5 67MB/pair bf16, FC1 weight 411MB, RoI features 205MB); two input sets alternated"},
         "e2e": {"value": round(e2e_value, 3), "unit": "img-pairs/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4,
                 "ms_per_step": round(ms_e2e / args.steps, 4),

@@ -20,8 +20,12 @@
  * Layouts: activation tensors are NHWC ("channels-last", the physical layout of a
  * torch channels_last tensor).  The reference's NCHW tensors enter through
  * da_nchw_to_nhwc.  RoI features keep the reference layout [R,C,ph,pw]
- * (DA_ROI_OUT_RCHW) because the bbox head flattens them as (c,ph,pw)
- * (mmdet/models/roi_heads/bbox_heads/convfc_bbox_head.py:208).
+ * (DA_ROI_OUT_RCHW) by default because the bbox head flattens them as (c,ph,pw)
+ * (mmdet/models/roi_heads/bbox_heads/convfc_bbox_head.py:208).  DA_ROI_OUT_RHWC
+ * ([R,ph,pw,C], "bin-major") is the faster layout for bf16 tensors with C % 64 == 0
+ * (both tensor-core kernels serve it; the backward then fetches its operand by TMA as it
+ * lies in memory); a caller using it holds the first shared FC's weight with its input
+ * columns in (ph,pw,c) order ("bin-major RoI features").
  */
 #ifndef DA_B200_H_
 #define DA_B200_H_

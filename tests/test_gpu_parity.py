@@ -772,9 +772,15 @@ def test_daf_org_hot_path_at_bench_shape_vs_oracle(engine, roi_layout):
     bf16 = engine == "umma_bf16"
     q = "bf16" if bf16 else None
     torch.manual_seed(0)
-    model = hotpath.DAFOrgHotPath(2048, 16, 1024, roi_layout=roi_layout).eval()
+    model = hotpath.DAFOrgHotPath(2048, 16, 1024).eval()
     seeded.fill_state_(model, 7, "bench.")                                  # O(1) activations everywhere (Q17)
-    # (roi_layout="rhwc": the first shared FC holds its columns in (bin, channel) order; state_dict() below is in the reference's)
+    if roi_layout == "rhwc":
+        # the SAME model through the reference-order state_dict: the first shared FC then holds its columns in (bin, channel)
+        # order, state_dict() below gives them back in the reference's
+        sd0 = model.state_dict()
+        model = hotpath.DAFOrgHotPath(2048, 16, 1024, roi_layout="rhwc").eval()
+        model.load_state_dict(sd0)
+        del sd0
     c5_nhwc, boxes = _bench_shape_inputs()
     if bf16:
         c5_nhwc = c5_nhwc.bfloat16().float()
