@@ -36,7 +36,8 @@ last_start = start.max(); print(f"last CTA starts at {last_start/1e3:.1f} us; it
 
 print(f"epilogue: tfull wait mean {(t[:,6]-t[:,2])[pairs>0].mean()/1e3:.2f} us; TMEM->global mean {(t[:,3]-t[:,6])[pairs>0].mean()/1e3:.2f} us")
 base = pt[0, 0]
-print("pair | prod:slot free | bld:raw here  ops free  built  synced | mma:ops ready  committed   (SM cycles from first)")
+print("pair | prod:slot free | bld:raw here  ops free  built  synced | mma:ops ready  (gradient here)  committed   (SM cycles from first; builder columns: team 0 = even pairs)")
 for i in range(24):
     r = pt[i] - base
-    print(f"{i:3d} | {r[0]:8.0f} | {r[3]:8.0f} {r[4]:8.0f} {r[5]:8.0f} {r[6]:8.0f} | {r[1]:8.0f} {r[2]:8.0f}")
+    b = [f"{v:8.0f}" if v > -1e9 else "       -" for v in (r[3], r[4], r[5], r[6])]
+    print(f"{i:3d} | {r[0]:8.0f} | {' '.join(b)} | {r[1]:8.0f} {r[7]:8.0f} {r[2]:8.0f}")

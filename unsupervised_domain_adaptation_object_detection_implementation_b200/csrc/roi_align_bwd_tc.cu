@@ -41,7 +41,7 @@ constexpr int BT_TY = 16, BT_TX = 16, BT_PX = BT_TY * BT_TX;   // 256 pixels = U
 constexpr int BT_CH = 256;                                      // channels per CTA = 2 accumulators of 128
 constexpr int BT_BUILDERS = 512;                                // warps 2..17: two half-rows per operand row
 constexpr int BT_THREADS = 64 + BT_BUILDERS;
-constexpr int BT_XWARPS = 2;                                    // kRHWC only: two more producer warps (Wx slices, gradient boxes)
+constexpr int BT_XWARPS = 3;                                    // kRHWC only: two more producer warps (Wx slices, gradient boxes) + a second MMA issuer
 constexpr int BT_THREADS_RHWC = BT_THREADS + 32 * BT_XWARPS;
 constexpr int BT_LIST = 1024;
 constexpr int BT_WARPS = BT_THREADS / 32;
@@ -56,7 +56,7 @@ constexpr int BT_NRAW = 3;                                     // raw ring depth
 constexpr size_t BT_SMEM = 1024 + 2 * (size_t)BT_OPS_BYTES + BT_NRAW * (size_t)BT_RAW_BYTES + BT_LIST * 4 + 256;
 // kRHWC layout: [BT_NA][A slot 32 KB] | [2][B 32 KB] | [BT_NRAW_RHWC][header | wy | wx] | list | barriers
 // A slot = the k-steps of one pair: [4 channel groups][16 * ksteps bins][64 ch] bf16, 128B-swizzled rows
-constexpr int BT_NA = 4;                                       // A (gradient) ring depth in pairs
+constexpr int BT_NA = 4;                                       // A (gradient) ring depth in pairs (a variable-size ring holding 5.9 pairs: no gain)
 constexpr int BT_ASLOT = 2 * BT_A_BYTES;                       // 32 KB: 4 k-steps
 constexpr int BT_NRAW_RHWC = 8;
 constexpr int BT_RAWT_BYTES = 64 + (BT_TY + BT_TX) * WROW * 4 + 64;    // 1152 (128-multiple)
@@ -141,13 +141,13 @@ roi_align_bwd_tc_kernel(const __grid_constant__ BwdMaps gmaps, const __nv_bfloat
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(ops_ready0 + 8 * i, 1);
-      mbar_init(ops_free0 + 8 * i, 1);
+      mbar_init(ops_free0 + 8 * i, kRHWC ? 2 : 1);     // kRHWC: two MMA issuers (one per accumulator) commit
     }
-    mbar_init(tfull, 1);
+    mbar_init(tfull, kRHWC ? 2 : 1);
     if (kRHWC)
       for (int i = 0; i < BT_NA; ++i) {
         mbar_init(u_full0 + 8 * i, 1);
-        mbar_init(u_empty0 + 8 * i, 1);
+        mbar_init(u_empty0 + 8 * i, 2);
       }
     fence_barrier_init();
   }
@@ -249,7 +249,7 @@ roi_align_bwd_tc_kernel(const __grid_constant__ BwdMaps gmaps, const __nv_bfloat
         if (!kRHWC && lane == 2) bulk_g2s(sbase + RAW_TAB + BT_TY * WROW * 4, tab + (size_t)H * WROW + (size_t)(xa - m.x_lo) * WROW,
                                           (uint32_t)(xb - xa) * WROW * 4, fb);
       }
-    } else if (kRHWC && warp >= BT_WARPS) {
+    } else if (kRHWC && warp >= BT_WARPS && warp < BT_WARPS + 2) {
       // ------------------------------------------------ kRHWC: two more producer warps.  One wait -> expect_tx -> issue sequence
       // of a thread costs ~400 cycles whatever its size and the sequences of one warp serialise: with all three copies of a
       // pair on warp 0 the producer alone was ~1300 cycles per pair (the whole kernel without MMAs and weight build: 1390).
@@ -296,19 +296,25 @@ roi_align_bwd_tc_kernel(const __grid_constant__ BwdMaps gmaps, const __nv_bfloat
                      raw_full0 + 8 * slot);
         }
       }
-    } else if (warp == 1) {
-      // ------------------------------------------------ MMA issuer
+    } else if (warp == 1 || (kRHWC && warp == BT_WARPS + 2)) {
+      // ------------------------------------------------ MMA issuer(s)
+      // kRHWC: TWO issuers, one per accumulator (128-channel block).  The cycle stamps showed the single issuer as the serial
+      // bottleneck of the pair loop: ~1450 cycles per pair = two barrier waits that had long completed (~150-250 each), ~130-150
+      // per tcgen05.mma whatever its N, the commits.  Each accumulator still sees its MMAs in RoI order (deterministic sums).
+      const int my_cb = (warp == 1) ? 0 : 1;
       if (lane == 0) {
         for (int li = 0; li < n_list; ++li) {
           const int sq = seq + li, ob = sq & 1;
           const uint32_t par = (uint32_t)(sq >> 1) & 1u;
           mbar_wait(ops_ready0 + 8 * ob, par);
-          PSTAMP(sq, 1);
+          if (my_cb == 0) PSTAMP(sq, 1);
           tc_fence_after();
           const uint32_t ops = ops0 + ob * BT_OPS_BYTES;
           const uint32_t b_tile = kRHWC ? ops0 + BT_NA * BT_ASLOT + ob * BT_B_BYTES : ops + 2 * BT_A_BYTES;
           // Only the tile rows the RoI touches take part: N = 16 px x (rows touched) instead of the whole 16x16 tile (the
-          // weight rows of the other pixels are zero, and are not even built any more).  The very first pair of the CTA runs
+          // weight rows of the other pixels are zero, and are not even built any more).  (Saves builder work only: the cycle
+          // stamps show ~130-150 cycles per tcgen05.mma whatever N <= 256 is -- an M = 128 instruction is paced by its A
+          // operand.  Fewer, wider MMAs would need the roles swapped: pixels as M, 256 channels as N)  The very first pair of the CTA runs
           // the full N = 256 with accumulate = 0: it is what initialises both TMEM accumulators.
           int r0 = 0, nrows = BT_TY, ksteps = 4;
           const int rr = *reinterpret_cast<volatile int*>(&s_rows[ob]);
@@ -324,11 +330,12 @@ roi_align_bwd_tc_kernel(const __grid_constant__ BwdMaps gmaps, const __nv_bfloat
             // 16 bins = 2 KB per k-step, the second 128-channel block 2 groups further
             const int aslot = sq % BT_NA;
             mbar_wait(u_full0 + 8 * aslot, (uint32_t)(sq / BT_NA) & 1u);
+            if (my_cb == 0) PSTAMP(sq, 7);
             tc_fence_after();
             const uint32_t a_tile = ops0 + aslot * BT_ASLOT, gpitch = (uint32_t)ksteps * 2048u;
             for (int kk = 0; kk < ksteps; ++kk) {
 #pragma unroll
-              for (int cb = 0; cb < 2; ++cb)
+              for (int cb = my_cb; cb <= my_cb; ++cb)
                 if (!(dbg & 1))
                   umma_bf16(tmem_base + cb * BT_PX + r0 * BT_TX, desc_mnmajor_sw128(a_tile + cb * 2 * gpitch + kk * 2048, gpitch),
                             bd + (uint64_t)(kk * 2), idesc_n, (sq > 0 || kk > 0) ? 1u : 0u);
@@ -344,7 +351,7 @@ roi_align_bwd_tc_kernel(const __grid_constant__ BwdMaps gmaps, const __nv_bfloat
             }
           }
           umma_commit(ops_free0 + 8 * ob);
-          PSTAMP(sq, 2);
+          if (my_cb == 0) PSTAMP(sq, 2);
         }
       }
     } else {
@@ -474,7 +481,7 @@ roi_align_bwd_tc_kernel(const __grid_constant__ BwdMaps gmaps, const __nv_bfloat
 
   if (kTrace && trace && threadIdx.x == 64) tr2 = globaltimer_ns();
   // ---- epilogue: TMEM -> grad_input (or zeros when no RoI touches the tile)
-  if (warp == 1 && lane == 0 && seq > 0) umma_commit(tfull);
+  if ((warp == 1 || (kRHWC && warp == BT_WARPS + 2)) && lane == 0 && seq > 0) umma_commit(tfull);
   if (warp >= 2 && warp < BT_WARPS) {
     const int q = warp & 3, cb = ((warp - 2) >> 2) & 1, chalf = (warp - 2) >> 3;   // TMEM quadrant, accumulator, pixel half
     const int c = c0 + cb * 128 + q * 32 + lane;
