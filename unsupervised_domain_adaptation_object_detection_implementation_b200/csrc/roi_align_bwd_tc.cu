@@ -62,6 +62,8 @@ constexpr int BT_NRAW_RHWC = 8;
 constexpr int BT_RAWT_BYTES = 64 + (BT_TY + BT_TX) * WROW * 4 + 64;    // 1152 (128-multiple)
 constexpr size_t BT_SMEM_RHWC = 1024 + (size_t)BT_NA * BT_ASLOT + 2 * (size_t)BT_B_BYTES + BT_NRAW_RHWC * (size_t)BT_RAWT_BYTES + BT_LIST * 4 + 512;
 static_assert(BT_SMEM_RHWC <= 227 * 1024 && BT_NA * BT_ASLOT >= BT_PX * BT_CH * 2, "epilogue staging overlays the A ring");
+constexpr int BT_STAGE_PITCH = BT_CH * 2 + 16;                 // epilogue staging row: 512 B of channels + 16 B (bank rotation)
+static_assert((size_t)BT_PX * BT_STAGE_PITCH <= (size_t)BT_NA * BT_ASLOT + 2 * BT_B_BYTES, "epilogue staging fits the operand buffers");
 struct BwdMaps { CUtensorMap m[4]; };                          // boxes of 16, 32, 48, 64 bins
 
 // Work items = (image, pixel tile) x channel chunk; their cost is the number of RoIs touching the tile (0 ... 54 pairs at the bench
@@ -326,20 +328,25 @@ roi_align_bwd_tc_kernel(const __grid_constant__ BwdMaps gmaps, const __nv_bfloat
           const uint32_t idesc_n = make_idesc(128, sq > 0 ? BT_TX * nrows : BT_PX, kRHWC ? 1 : 0, 0);
           const uint64_t bd = desc_kmajor_sw128(b_tile + (uint32_t)r0 * (BT_TX * 128));
           if constexpr (kRHWC) {
-            // A is MN-major (channels contiguous): 64-channel groups ksteps * 2 KB apart (LBO), 8-bin atoms 1 KB apart (SBO),
-            // 16 bins = 2 KB per k-step, the second 128-channel block 2 groups further
+            // ROLES SWAPPED against the [R,C,7,7] mode: D_h[128 px x 256 ch] += Wt_h[128 px x bins] . G[bins x 256 ch] for the
+            // pixel half h (tile rows 8h .. 8h+7) of this issuer, skipped when the RoI misses that half.  An M = 128 tcgen05.mma
+            // costs ~130-150 cycles whatever its N (cycle stamps, profiles/r02_roi_align_rhwc.md): restricting N to the touched
+            // rows never saved tensor-pipe time; one full-N MMA per touched half does (1.45 instead of 2 per k-step at the bench
+            // size).  A = weight tile (K-major, 128B swizzle, rows = pixels); B = gradient box, MN-major as it lies in memory:
+            // 64-channel groups ksteps * 2 KB apart (LBO), 8-bin atoms 1 KB apart (SBO), 16 bins = 2 KB per k-step.
             const int aslot = sq % BT_NA;
             mbar_wait(u_full0 + 8 * aslot, (uint32_t)(sq / BT_NA) & 1u);
             if (my_cb == 0) PSTAMP(sq, 7);
             tc_fence_after();
             const uint32_t a_tile = ops0 + aslot * BT_ASLOT, gpitch = (uint32_t)ksteps * 2048u;
-            for (int kk = 0; kk < ksteps; ++kk) {
-#pragma unroll
-              for (int cb = my_cb; cb <= my_cb; ++cb)
-                if (!(dbg & 1))
-                  umma_bf16(tmem_base + cb * BT_PX + r0 * BT_TX, desc_mnmajor_sw128(a_tile + cb * 2 * gpitch + kk * 2048, gpitch),
-                            bd + (uint64_t)(kk * 2), idesc_n, (sq > 0 || kk > 0) ? 1u : 0u);
-            }
+            const int ya_r = rr & 255, yb_r = (rr >> 8) & 255;
+            const bool touched = sq == 0 || (ya_r < 8 * (my_cb + 1) && yb_r > 8 * my_cb);   // first pair: initialises the accumulator
+            constexpr uint32_t idesc_sw = make_idesc(128, BT_CH, 0, 1);
+            const uint64_t wd = desc_kmajor_sw128(b_tile + (uint32_t)my_cb * (128 * 128));
+            if (touched && !(dbg & 1))
+              for (int kk = 0; kk < ksteps; ++kk)
+                umma_bf16(tmem_base + my_cb * BT_CH, wd + (uint64_t)(kk * 2), desc_mnmajor_sw128(a_tile + kk * 2048, gpitch), idesc_sw,
+                          (sq > 0 || kk > 0) ? 1u : 0u);
             umma_commit(u_empty0 + 8 * aslot);
           } else {
 #pragma unroll
@@ -425,7 +432,12 @@ roi_align_bwd_tc_kernel(const __grid_constant__ BwdMaps gmaps, const __nv_bfloat
 #pragma unroll
         for (int hh = 0; hh < (kRHWC ? 2 : 1); ++hh) {
         const int half = kRHWC ? hh : (bt >> 8);
-        if ((sq == 0 || ((ty0 + (row >> 4)) >= ya && (ty0 + (row >> 4)) < yb)) && half * 2 < ksteps) {
+        // ([R,C,7,7] mode: only the tile rows the RoI touches are read by the restricted-N MMAs; kRHWC: every row of a pixel half
+        // the RoI touches is an M row of that half's MMA, rows outside the footprint are written as zeros)
+        const int hrow = row >> 7;
+        const bool row_used = kRHWC ? ((ya - ty0) < 8 * (hrow + 1) && (yb - ty0) > 8 * hrow)
+                                    : ((ty0 + (row >> 4)) >= ya && (ty0 + (row >> 4)) < yb);
+        if ((sq == 0 || row_used) && half * 2 < ksteps) {
           const int y = ty0 + (row >> 4), x = tx0 + (row & 15);
           const bool in = (y >= ya) && (y < yb) && (x >= xa) && (x < xb);
           uint32_t pk[16];
@@ -482,7 +494,69 @@ roi_align_bwd_tc_kernel(const __grid_constant__ BwdMaps gmaps, const __nv_bfloat
   if (kTrace && trace && threadIdx.x == 64) tr2 = globaltimer_ns();
   // ---- epilogue: TMEM -> grad_input (or zeros when no RoI touches the tile)
   if ((warp == 1 || (kRHWC && warp == BT_WARPS + 2)) && lane == 0 && seq > 0) umma_commit(tfull);
-  if (warp >= 2 && warp < BT_WARPS) {
+  if (kRHWC && warp >= 2 && warp < BT_WARPS) {
+    // pixel-major accumulators: lane = pixel of half h, columns = the CTA's 256 channels.  A thread holds 32 consecutive channels of
+    // its pixel per TMEM load: 64 (bf16) / 128 (fp32) contiguous bytes of grad_input NHWC, stored directly -- no transpose through
+    // shared memory (the [R,C,7,7] mode's epilogue is 256 2-byte shared stores per thread + bulk stores: 3.7 us per CTA).
+    const int q = warp & 3, h = ((warp - 2) >> 2) & 1, chalf = (warp - 2) >> 3;   // TMEM quadrant, pixel half, channel half
+    const int px = h * 128 + q * 32 + lane;
+    const int y = ty0 + (px >> 4), x = tx0 + (px & 15);
+    if (seq > 0) {
+      mbar_wait(tfull, 0);
+      tc_fence_after();
+    }
+    if (kTrace && trace && threadIdx.x == 64) tr3 = globaltimer_ns();
+#pragma unroll 1
+    for (int cc = chalf * 4; cc < chalf * 4 + 4; ++cc) {
+      uint32_t v[32];
+      if (seq > 0) {
+        DA_TMEM_LD32(tmem_base + ((uint32_t)(q * 32) << 16) + h * BT_CH + cc * 32, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      const int c = c0 + cc * 32;
+      if (y < H && x < W && c < C && !(dbg & 8)) {      // C % 64 == 0: a 32-channel run is inside or outside as a whole
+        TO* dst = grad_in + (((size_t)b * H + y) * W + x) * C + c;
+        if constexpr (sizeof(TO) == 4) {
+          uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) d4[k] = make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        }
+      }
+      if constexpr (sizeof(TO) == 2) {
+        // bf16: stage[px][256 ch] over the (now idle) operand buffers with a 528-byte row pitch -- the 16-byte stores of 8
+        // consecutive pixels then fall on 8 different bank groups -- and one 512 B bulk store per pixel (16-byte global stores
+        // at a 4 KB stride measured 6.8 us per CTA)
+        uint4* s4 = reinterpret_cast<uint4*>(gen + (size_t)px * BT_STAGE_PITCH + cc * 64);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(v[8 * k + 2 * i]), __uint_as_float(v[8 * k + 2 * i + 1]));
+            pk[i] = *reinterpret_cast<const uint32_t*>(&t2);
+          }
+          s4[k] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+    }
+    if constexpr (sizeof(TO) == 2) {
+      fence_proxy_async();
+      named_bar_sync(2, BT_BUILDERS);
+      const int p2 = t - 64;
+      if (p2 < BT_PX) {
+        const int y2 = ty0 + (p2 >> 4), x2 = tx0 + (p2 & 15);
+        if (y2 < H && x2 < W && !(dbg & 8)) {
+          bulk_s2g(grad_in + (((size_t)b * H + y2) * W + x2) * C + c0, base + (uint32_t)p2 * BT_STAGE_PITCH, (uint32_t)nch * 2u);
+          bulk_commit();
+          bulk_wait_read0();
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp >= 2 && warp < BT_WARPS) {
     const int q = warp & 3, cb = ((warp - 2) >> 2) & 1, chalf = (warp - 2) >> 3;   // TMEM quadrant, accumulator, pixel half
     const int c = c0 + cb * 128 + q * 32 + lane;
     if (seq > 0) {
