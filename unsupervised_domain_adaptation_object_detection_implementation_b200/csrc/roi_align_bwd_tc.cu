@@ -56,7 +56,8 @@ constexpr int BT_NRAW = 3;                                     // raw ring depth
 constexpr size_t BT_SMEM = 1024 + 2 * (size_t)BT_OPS_BYTES + BT_NRAW * (size_t)BT_RAW_BYTES + BT_LIST * 4 + 256;
 // kRHWC layout: [BT_NA][A slot 32 KB] | [2][B 32 KB] | [BT_NRAW_RHWC][header | wy | wx] | list | barriers
 // A slot = the k-steps of one pair: [4 channel groups][16 * ksteps bins][64 ch] bf16, 128B-swizzled rows
-constexpr int BT_NA = 4;                                       // A (gradient) ring depth in pairs (a variable-size ring holding 5.9 pairs: no gain)
+constexpr int BT_NA = 4;                                       // gradient ring depth in pairs.  Measured and not kept: a variable-size ring (18 units of
+                                                               // 8 KB = 5.9 pairs in flight) and an L2 tensor prefetch 8 pairs ahead: both +-0
 constexpr int BT_ASLOT = 2 * BT_A_BYTES;                       // 32 KB: 4 k-steps
 constexpr int BT_NRAW_RHWC = 8;
 constexpr int BT_RAWT_BYTES = 64 + (BT_TY + BT_TX) * WROW * 4 + 64;    // 1152 (128-multiple)
@@ -334,10 +335,11 @@ roi_align_bwd_tc_kernel(const __grid_constant__ BwdMaps gmaps, const __nv_bfloat
             // rows never saved tensor-pipe time; one full-N MMA per touched half does (1.45 instead of 2 per k-step at the bench
             // size).  A = weight tile (K-major, 128B swizzle, rows = pixels); B = gradient box, MN-major as it lies in memory:
             // 64-channel groups ksteps * 2 KB apart (LBO), 8-bin atoms 1 KB apart (SBO), 16 bins = 2 KB per k-step.
+            // (the team leader waited for the pair's gradient box before it arrived on ops_ready: ONE barrier wait and ONE commit
+            // per pair on this thread -- each already-completed mbarrier wait cost it 150-300 cycles, two of them plus two commits
+            // were ~530 of its ~1090 cycles per pair)
             const int aslot = sq % BT_NA;
-            mbar_wait(u_full0 + 8 * aslot, (uint32_t)(sq / BT_NA) & 1u);
             if (my_cb == 0) PSTAMP(sq, 7);
-            tc_fence_after();
             const uint32_t a_tile = ops0 + aslot * BT_ASLOT, gpitch = (uint32_t)ksteps * 2048u;
             const int ya_r = rr & 255, yb_r = (rr >> 8) & 255;
             const bool touched = sq == 0 || (ya_r < 8 * (my_cb + 1) && yb_r > 8 * my_cb);   // first pair: initialises the accumulator
@@ -357,7 +359,7 @@ roi_align_bwd_tc_kernel(const __grid_constant__ BwdMaps gmaps, const __nv_bfloat
                 if (!(dbg & 1)) umma_bf16(tmem_base + cb * BT_PX + r0 * BT_TX, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc_n, (sq > 0 || kk > 0) ? 1u : 0u);
             }
           }
-          umma_commit(ops_free0 + 8 * ob);
+          if (!kRHWC) umma_commit(ops_free0 + 8 * ob);     // kRHWC: the weight buffer is released by the pair's u_empty commit
           if (my_cb == 0) PSTAMP(sq, 2);
         }
       }
@@ -381,7 +383,11 @@ roi_align_bwd_tc_kernel(const __grid_constant__ BwdMaps gmaps, const __nv_bfloat
         if (kRHWC && ob != team) continue;
         mbar_wait(raw_full0 + 8 * slot, (uint32_t)(sq / NRAW) & 1u);
         if (bt == 0) PSTAMP(sq, 3);
-        mbar_wait(ops_free0 + 8 * ob, ((uint32_t)(sq >> 1) & 1u) ^ 1u);
+        if (kRHWC) {     // weight buffer ob was last read by the MMAs of pair sq - 2: its u_empty completion releases it
+          if (sq >= 2) mbar_wait(u_empty0 + 8 * ((sq - 2) % BT_NA), (uint32_t)((sq - 2) / BT_NA) & 1u);
+        } else {
+          mbar_wait(ops_free0 + 8 * ob, ((uint32_t)(sq >> 1) & 1u) ^ 1u);
+        }
         if (bt == 0) PSTAMP(sq, 4);
         const uint8_t* sl = gen + RAW_OFF + slot * RAW_PITCH;
         const int* hdr = reinterpret_cast<const int*>(sl);
@@ -483,6 +489,7 @@ roi_align_bwd_tc_kernel(const __grid_constant__ BwdMaps gmaps, const __nv_bfloat
         if (bt == 0) PSTAMP(sq, 6);
         if (leader) {
           s_rows[ob] = (ya - ty0) | ((yb - ty0) << 8) | (ksteps << 16);     // read by the MMA thread after it has seen ops_ready (release/acquire)
+          if (kRHWC) mbar_wait(u_full0 + 8 * (sq % BT_NA), (uint32_t)(sq / BT_NA) & 1u);   // the pair's gradient box has landed
           mbar_arrive(ops_ready0 + 8 * ob);
           mbar_arrive(raw_empty0 + 8 * slot);
         }
