@@ -64,7 +64,9 @@ class SharedFCs(nn.Module):
         weight is HELD with its input columns in (bin, channel) order, so that `flatten` is a view and the tensor-core RoIAlign
         backward gets its operand as it lies in memory.  state_dict()/load_state_dict() still speak the
         reference's (channel, bin) column order (convfc_bbox_head.py:229: `x.flatten(1)` of [R,C,7,7]); the optimizer is
-        elementwise, so training in the permuted order is the same training."""
+        elementwise, so training in the permuted order is the same training.  Optimizer STATE of shared_fcs[0].weight (momentum
+        in FusedSGD.state_dict()) is in the held order: a checkpoint resumes with the same roi_layout, or its buffer goes
+        through to_reference_order / to_held_order like the weight."""
         super().__init__()
         if roi_layout not in ("rchw", "rhwc"):
             raise ValueError(f"roi_layout {roi_layout!r}")
