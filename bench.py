@@ -607,6 +607,15 @@ def kernel_rooflines(dev, act, step_ms, fused_step=True, roi_layout=ROI_LAYOUT_D
             for rec in launches:
                 if rec["kernel"].startswith(prefix) and rec["instance"] == inst:
                     prof[name] = rec
+        if roi_layout == "rhwc":     # the RoIAlign kernels of the bin-major layout have their own capture (tools/prof_roi2.py)
+            try:
+                for rec in json.load(open(os.path.join(ROOT, "profiles", "r02_roi_rhwc_ncu.json")))["launches"]:
+                    if rec["kernel"].startswith("roi_align_fwd_tc_kernel"):
+                        prof["roi_align_fwd"] = rec
+                    if rec["kernel"].startswith("roi_align_bwd_tc_kernel"):
+                        prof["roi_align_bwd"] = rec
+            except (OSError, KeyError, ValueError):
+                pass
         for k, rec in prof.items():
             if k in table:
                 table[k]["ncu_dram_bytes"] = rec["dram_bytes"]
